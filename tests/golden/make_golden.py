@@ -1,0 +1,136 @@
+#!/usr/bin/env python
+"""Regenerates the committed golden fixtures by RUNNING THE COMPILED REFERENCE
+(oracle/_ref/libcrass_ref.so, built from /root/reference by `make -C oracle ref`).
+
+Outputs (all under tests/golden/):
+  bundled/<name>.dump.gz     "crass-dump v1" of searchFile -> createNonRedundantSet -> findSingletons
+                             on each read set the reference ships in test/ (default options)
+  bundled/MD5SUMS            md5 of the uncompressed dumps
+  search_core_vectors.json   seeded per-read vectors: read, params -> (found, start/stops, repeat length)
+  edit_distance_vectors.json seeded string pairs -> (distance, similarity as float32 hex)
+  lowlexi_vectors.json       seeded (read, start/stops) -> (DR, flag, mirrored start/stops)
+  ac_vectors.json            seeded pattern sets + texts -> first match (end, length) or null
+  kseq_vectors.json          hand-made FASTA/FASTQ edge-case files -> record stream seen by searchFile
+
+catch_vectors.json is NOT generated: it restates the known-answer tests of the reference's own
+src/test/test_libcrispr.cpp by hand (each entry cites its line range).
+"""
+import gzip
+import hashlib
+import json
+import os
+import random
+import struct
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import checkers  # noqa: E402
+import fuzzgen  # noqa: E402
+
+KSEQ_CASES = {
+    "plain_fasta": ">r1 first comment\nACGTACGT\nACGT\n>r2\nGGGG\n>r3\tx y\nTTTT",
+    "fastq_then_fasta_stale_qual": "@q1 c1\nACGTAC\n+\nIIIIII\n>f1\nACGTACGTAA\n>f2 c2\nAC\n@q2\nAAAA\n+q2\n!!!!\n",
+    "crlf": ">r1 c\r\nACGT\r\nAC\r\n>r2\r\nGG\r\n",
+    "multiline_fastq": "@m1\nACGT\nACGT\n+\nIIII\nIIII\n@m2\nAC\n+\nII\n",
+    "qual_with_at": "@a1\nACGTA\n+\n@@@@@\n@a2\nCC\n+\n@I\n",
+    "truncated_qual": "@t1\nACGTACGT\n+\nIIII\n@t2\nAC\n+\nII\n",
+    "leading_garbage": "garbage line\n\n>r1\nAC GT\n>r2\nA+C\nGG\n",
+    "plus_in_fasta": ">p1\nACGT\n+\nIIII\n>p2\nTT\n",
+    "no_trailing_newline": ">r1\nACGT\n>r2 last",
+    "empty_comment_then_stale": ">r1 \nAAAA\n>r2 real\nCCCC\n>r3\nGGGG\n",
+    "lowercase_and_iupac": ">l1\nacgtNNRYacgt\n>l2\nACGTUacgtu\n",
+}
+
+
+def main():
+    R = checkers.ref()
+    os.makedirs(os.path.join(HERE, "bundled"), exist_ok=True)
+    sums = []
+    for f in sorted(os.listdir(checkers.REF_DATA)):
+        if not f.endswith(".gz"):
+            continue
+        dump, _ = R.run_files([os.path.join(checkers.REF_DATA, f)])
+        raw = dump.encode("latin-1")
+        sums.append("%s  %s.dump" % (hashlib.md5(raw).hexdigest(), f))
+        with gzip.GzipFile(os.path.join(HERE, "bundled", f + ".dump.gz"), "wb", mtime=0) as g:
+            g.write(raw)
+    with open(os.path.join(HERE, "bundled", "MD5SUMS"), "w") as g:
+        g.write("\n".join(sums) + "\n")
+
+    rng = random.Random(20240)
+    vec = []
+    while len(vec) < 1500:
+        s = fuzzgen.fuzz_read(rng)
+        prm = None
+        if rng.random() < 0.25:
+            prm = dict(window=rng.choice([6, 7, 8, 9]), min_repeats=rng.choice([2, 3, 4]), low_dr=rng.choice([23, 20, 30]),
+                       high_dr=rng.choice([47, 60]), low_spacer=rng.choice([26, 20, 10]), high_spacer=rng.choice([50, 60]))
+        found, ss, rl = R.search_core(s, prm)
+        if found != 1 and rng.random() < 0.5 and len(vec) > 200:
+            continue
+        vec.append(dict(seq=s.decode("latin-1"), params=prm, found=found, ss=ss, replen=rl))
+    json.dump(vec, open(os.path.join(HERE, "search_core_vectors.json"), "w"), indent=0)
+
+    vec = []
+    for _ in range(2000):
+        a = fuzzgen.rand_seq(rng, rng.randint(0, 55), b"ACGTN")
+        b = fuzzgen.mutate(rng, a, 0.2) if rng.random() < 0.6 else fuzzgen.rand_seq(rng, rng.randint(0, 55))
+        if rng.random() < 0.3:
+            b = b[rng.randint(0, 3):]
+        vec.append([a.decode(), b.decode(), R.edit_distance(a, b), struct.pack(">f", R.similarity(a, b)).hex()])
+    json.dump(vec, open(os.path.join(HERE, "edit_distance_vectors.json"), "w"))
+
+    vec = []
+    for _ in range(600):
+        L = rng.randint(60, 300)
+        s = fuzzgen.rand_seq(rng, L, b"ACGTNRYacgtU")
+        n = rng.choice([1, 2, 2, 3, 4])
+        pts = sorted(rng.sample(range(0, L), 2 * n))
+        if rng.random() < 0.3:
+            pts[0] = 0
+        if rng.random() < 0.3:
+            pts[-1] = L - 1
+        dr, low, ss2, seq2 = R.dr_lowlexi(s, pts)
+        vec.append(dict(seq=s.decode(), ss=pts, dr=dr.decode(), lowlexi=low, ss_out=ss2, seq_out=seq2.decode()))
+    json.dump(vec, open(os.path.join(HERE, "lowlexi_vectors.json"), "w"))
+
+    vec = []
+    for _ in range(40):
+        pats = fuzzgen.dr_like_patterns(rng, rng.randint(1, 60))
+        if rng.random() < 0.3:
+            pats += [p[rng.randint(0, 5):len(p) - rng.randint(0, 5)] for p in pats[:10]]
+        h = R.ac_create(pats)
+        texts = []
+        for _k in range(60):
+            t = fuzzgen.rand_seq(rng, rng.randint(0, 200), b"ACGTN" if rng.random() < 0.2 else b"ACGT")
+            if rng.random() < 0.6 and len(t) > 60:
+                p = rng.choice(pats)
+                pos = rng.randint(0, len(t) - 1)
+                t = (t[:pos] + p + t[pos:])[:len(t)]
+            texts.append([t.decode(), R.ac_first_match(h, t)])
+        R.ac_destroy(h)
+        vec.append(dict(patterns=[p.decode() for p in pats], texts=texts))
+    json.dump(vec, open(os.path.join(HERE, "ac_vectors.json"), "w"))
+
+    vec = {}
+    with tempfile.TemporaryDirectory() as d:
+        for name, content in KSEQ_CASES.items():
+            for gz in (False, True):
+                p = os.path.join(d, name + (".gz" if gz else ".fx"))
+                if gz:
+                    with gzip.open(p, "wb") as g:
+                        g.write(content.encode())
+                else:
+                    open(p, "wb").write(content.encode())
+                out = R.kseq_dump(p).decode("latin-1")
+                if name in vec:
+                    assert vec[name]["records"] == out
+                vec[name] = dict(content=content, records=out)
+    json.dump(vec, open(os.path.join(HERE, "kseq_vectors.json"), "w"), indent=1)
+    print("golden fixtures regenerated from", checkers.REF_SO)
+
+
+if __name__ == "__main__":
+    main()
