@@ -1,0 +1,398 @@
+"""ctypes binding of the C-ABI in include/crass_b200.h (libcrass_b200.so, built in-tree).
+
+This is the Python face of the product used by tests/, bench.py and the multi-GPU driver; every
+compute call goes straight into the CUDA library.  There is no Python or CPU implementation of
+the path here: if the shared library is missing the import fails loudly, and on a machine without
+a CUDA device every compute entry point raises ``CrassB200Error`` (status ENODEVICE).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcrass_b200.so")
+
+
+class CrassB200Error(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("crass_b200 status %d: %s" % (status, msg))
+        self.status = status
+
+
+class Params(C.Structure):
+    """The searched fields of the reference's ``options`` struct (crassDefines.h:140-170)."""
+    _fields_ = [("low_dr", C.c_uint32), ("high_dr", C.c_uint32), ("low_spacer", C.c_uint32), ("high_spacer", C.c_uint32),
+                ("window", C.c_uint32), ("min_repeats", C.c_uint32), ("kmer_clust", C.c_uint32), ("scan_range", C.c_uint32)]
+
+    def __init__(self, **kw):
+        super().__init__()
+        lib().crass_b200_default_params(C.byref(self))
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise TypeError("unknown parameter %r" % k)
+            setattr(self, k, v)
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Hit(C.Structure):
+    _fields_ = [("read_index", C.c_uint32), ("n_ss", C.c_uint32), ("ss_offset", C.c_uint32), ("repeat_len", C.c_uint32)]
+
+
+HIT_DTYPE = np.dtype([("read_index", "<u4"), ("n_ss", "<u4"), ("ss_offset", "<u4"), ("repeat_len", "<u4")])
+
+ENODEVICE = -2
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C crass_b200/csrc` (there is no fallback implementation)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u8p, u32p, u64p, cp = C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_char_p
+    sig = {
+        "crass_b200_last_error": (cp, []),
+        "crass_b200_abi_version": (C.c_int, []),
+        "crass_b200_build_info": (cp, []),
+        "crass_b200_device_count": (C.c_int, []),
+        "crass_b200_default_params": (None, [C.POINTER(Params)]),
+        "crass_b200_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "crass_b200_ctx_destroy": (None, [vp]),
+        "crass_b200_ctx_device": (C.c_int, [vp]),
+        "crass_b200_ctx_launch_count": (C.c_uint64, [vp]),
+        "crass_b200_dr_search_dev": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, C.POINTER(Params), vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp]),
+        "crass_b200_dr_search": (C.c_int, [vp, vp, vp, C.c_uint32, C.POINTER(Params), vp, C.POINTER(vp), u32p, C.POINTER(vp), u32p]),
+        "crass_b200_ac_build": (C.c_int, [vp, vp, C.c_uint32, C.POINTER(vp)]),
+        "crass_b200_ac_destroy": (None, [vp]),
+        "crass_b200_ac_num_states": (C.c_uint32, [vp]),
+        "crass_b200_ac_num_symbols": (C.c_uint32, [vp]),
+        "crass_b200_ac_table_bytes": (C.c_uint64, [vp]),
+        "crass_b200_ac_scan_dev": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp]),
+        "crass_b200_ac_scan": (C.c_int, [vp, vp, vp, vp, C.c_uint32, vp, vp, C.POINTER(vp), u32p, C.POINTER(vp), u32p]),
+        "crass_b200_edit_distance_batch": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, vp, C.c_uint32, vp, vp]),
+        "crass_b200_scan_right": (C.c_int, [vp, cp, C.c_uint32, u32p, u32p, C.c_uint32, cp, C.c_uint32, C.c_uint32, C.c_uint32]),
+        "crass_b200_extend_pre_repeat": (C.c_int, [vp, cp, C.c_uint32, u32p, C.c_uint32, C.c_uint32, C.c_uint32, u32p]),
+        "crass_b200_parse_file": (C.c_int, [cp, C.POINTER(vp)]),
+        "crass_b200_batch_from_memory": (C.c_int, [vp, vp, C.c_uint32, vp, C.POINTER(vp)]),
+        "crass_b200_batch_destroy": (None, [vp]),
+        "crass_b200_batch_num_reads": (C.c_uint32, [vp]),
+        "crass_b200_batch_max_read_len": (C.c_uint32, [vp]),
+        "crass_b200_batch_parse_status": (C.c_int, [vp]),
+        "crass_b200_batch_bases": (vp, [vp]),
+        "crass_b200_batch_offsets": (vp, [vp]),
+        "crass_b200_batch_name": (cp, [vp, C.c_uint32]),
+        "crass_b200_batch_comment": (cp, [vp, C.c_uint32, C.POINTER(C.c_int)]),
+        "crass_b200_batch_qual": (cp, [vp, C.c_uint32, C.POINTER(C.c_int)]),
+        "crass_b200_results_create": (C.c_int, [C.POINTER(vp)]),
+        "crass_b200_results_destroy": (None, [vp]),
+        "crass_b200_results_add_phase1": (C.c_int, [vp, vp, vp, C.c_uint32, vp]),
+        "crass_b200_results_add_phase2": (C.c_int, [vp, vp, vp, C.c_uint32, vp]),
+        "crass_b200_results_num_tokens": (C.c_uint32, [vp]),
+        "crass_b200_results_num_reads": (C.c_uint32, [vp]),
+        "crass_b200_results_dr_list": (vp, [vp]),
+        "crass_b200_results_adopt_tokens": (C.c_int, [vp, cp]),
+        "crass_b200_results_non_redundant": (vp, [vp, C.c_uint32, u32p]),
+        "crass_b200_results_dump": (vp, [vp, C.c_int]),
+        "crass_b200_non_redundant_set": (vp, [cp, C.c_uint32]),
+        "crass_b200_run_files": (C.c_int, [vp, C.POINTER(cp), C.c_uint32, C.POINTER(Params), C.c_int, C.POINTER(vp), C.POINTER(C.c_int)]),
+        "crass_b200_free": (None, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)          # AttributeError here == the library does not export what the header declares
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = None  # filled lazily by exported_symbols()
+
+
+def _check(status):
+    if status != 0:
+        raise CrassB200Error(status, lib().crass_b200_last_error().decode("utf-8", "replace"))
+
+
+def _take_str(ptr):
+    if not ptr:
+        return None
+    s = C.string_at(ptr)
+    lib().crass_b200_free(C.c_void_p(ptr))
+    return s
+
+
+def device_count():
+    return lib().crass_b200_device_count()
+
+
+def _np_ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def pack_reads(reads):
+    """list of bytes -> (bases uint8[n_bases], offsets uint64[n+1]) in the byte-packed batch layout."""
+    offs = np.zeros(len(reads) + 1, dtype=np.uint64)
+    if reads:
+        offs[1:] = np.cumsum([len(r) for r in reads], dtype=np.uint64)
+    bases = np.frombuffer(b"".join(reads), dtype=np.uint8).copy() if reads else np.zeros(0, dtype=np.uint8)
+    return bases, offs
+
+
+class Batch:
+    """A parsed read set (crass_b200_batch): what kseq_read hands to searchFile."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @classmethod
+    def from_file(cls, path):
+        h = C.c_void_p()
+        _check(lib().crass_b200_parse_file(path.encode(), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_arrays(cls, bases, offsets, names=None):
+        h = C.c_void_p()
+        n = len(offsets) - 1
+        arr = None
+        if names is not None:
+            arr = (C.c_char_p * n)(*[x if isinstance(x, bytes) else x.encode() for x in names])
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        _check(lib().crass_b200_batch_from_memory(_np_ptr(bases), _np_ptr(offsets), n, C.cast(arr, C.c_void_p) if arr is not None else None, C.byref(h)))
+        return cls(h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().crass_b200_batch_destroy(self.h)
+            self.h = None
+
+    def __len__(self):
+        return lib().crass_b200_batch_num_reads(self.h)
+
+    @property
+    def max_read_len(self):
+        return lib().crass_b200_batch_max_read_len(self.h)
+
+    @property
+    def parse_status(self):
+        return lib().crass_b200_batch_parse_status(self.h)
+
+    @property
+    def offsets(self):
+        n = len(self)
+        p = lib().crass_b200_batch_offsets(self.h)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(n + 1,))
+
+    @property
+    def bases(self):
+        n = int(self.offsets[-1])
+        p = lib().crass_b200_batch_bases(self.h)
+        if n == 0:
+            return np.zeros(0, dtype=np.uint8)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n,))
+
+    def name(self, i):
+        return lib().crass_b200_batch_name(self.h, i)
+
+    def comment(self, i):
+        has = C.c_int(0)
+        s = lib().crass_b200_batch_comment(self.h, i, C.byref(has))
+        return s if has.value else None
+
+    def qual(self, i):
+        has = C.c_int(0)
+        s = lib().crass_b200_batch_qual(self.h, i, C.byref(has))
+        return s if has.value else None
+
+    def record_stream(self):
+        """Same text as the checkers' kseq_dump (tests compare them)."""
+        out = []
+        offs, bases = self.offsets, self.bases
+        for i in range(len(self)):
+            c, q = self.comment(i), self.qual(i)
+            seq = bases[int(offs[i]):int(offs[i + 1])].tobytes()
+            out.append(b"\t".join([self.name(i), c if c is not None else b"\x01", seq, q if q is not None else b"\x01"]))
+        out.append(b"#ret=%d" % self.parse_status)
+        return b"\n".join(out) + b"\n"
+
+
+class Automaton:
+    def __init__(self, patterns):
+        pats = [p if isinstance(p, bytes) else p.encode() for p in patterns]
+        data = np.frombuffer(b"".join(pats), dtype=np.uint8).copy() if pats else np.zeros(1, dtype=np.uint8)
+        offs = np.zeros(len(pats) + 1, dtype=np.uint32)
+        if pats:
+            offs[1:] = np.cumsum([len(p) for p in pats], dtype=np.uint32)
+        self.h = C.c_void_p()
+        _check(lib().crass_b200_ac_build(_np_ptr(data), _np_ptr(offs), len(pats), C.byref(self.h)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().crass_b200_ac_destroy(self.h)
+            self.h = None
+
+    @property
+    def num_states(self):
+        return lib().crass_b200_ac_num_states(self.h)
+
+    @property
+    def table_bytes(self):
+        return lib().crass_b200_ac_table_bytes(self.h)
+
+
+class Results:
+    """Mirror of the containers the reference fills (ReadMap / StringCheck / lookupTables)."""
+
+    def __init__(self, handle=None):
+        if handle is None:
+            handle = C.c_void_p()
+            _check(lib().crass_b200_results_create(C.byref(handle)))
+        self.h = handle
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().crass_b200_results_destroy(self.h)
+            self.h = None
+
+    def add_phase1(self, batch, hits, pool):
+        _check(lib().crass_b200_results_add_phase1(self.h, batch.h, _np_ptr(hits), len(hits), _np_ptr(pool)))
+
+    def add_phase2(self, batch, hits, pool):
+        _check(lib().crass_b200_results_add_phase2(self.h, batch.h, _np_ptr(hits), len(hits), _np_ptr(pool)))
+
+    @property
+    def num_tokens(self):
+        return lib().crass_b200_results_num_tokens(self.h)
+
+    @property
+    def num_reads(self):
+        return lib().crass_b200_results_num_reads(self.h)
+
+    def dr_list(self):
+        s = _take_str(lib().crass_b200_results_dr_list(self.h))
+        return [x for x in s.split(b"\n") if x]
+
+    def adopt_tokens(self, all_drs):
+        _check(lib().crass_b200_results_adopt_tokens(self.h, b"".join(d + b"\n" for d in all_drs)))
+
+    def non_redundant(self, kmer_clust=6):
+        n = C.c_uint32(0)
+        s = _take_str(lib().crass_b200_results_non_redundant(self.h, kmer_clust, C.byref(n)))
+        return [x for x in s.split(b"\n") if x]
+
+    def dump(self, max_read_len):
+        return _take_str(lib().crass_b200_results_dump(self.h, max_read_len)).decode("latin-1")
+
+
+def non_redundant_set(drs, kmer_clust=6):
+    s = _take_str(lib().crass_b200_non_redundant_set(b"".join(d + b"\n" for d in drs), kmer_clust))
+    return s.decode()
+
+
+class Context:
+    """One per GPU (crass_b200_ctx): stream, staging buffers, workspaces."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _check(lib().crass_b200_ctx_create(device, C.byref(self.h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().crass_b200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def launch_count(self):
+        return int(lib().crass_b200_ctx_launch_count(self.h))
+
+    # -- host-buffer entry points (the reference-facing calls; copies inside) -----------------------
+    def _collect(self, call, n_reads, want_found):
+        found = np.zeros(n_reads, dtype=np.uint8) if want_found else None
+        hp, pp = C.c_void_p(), C.c_void_p()
+        nh, npool = C.c_uint32(0), C.c_uint32(0)
+        _check(call(_np_ptr(found) if found is not None else None, C.byref(hp), C.byref(nh), C.byref(pp), C.byref(npool)))
+        try:
+            hits = np.frombuffer(C.string_at(hp, nh.value * 16), dtype=HIT_DTYPE).copy() if nh.value else np.zeros(0, dtype=HIT_DTYPE)
+            pool = np.frombuffer(C.string_at(pp, npool.value * 4), dtype=np.uint32).copy() if npool.value else np.zeros(0, dtype=np.uint32)
+        finally:
+            lib().crass_b200_free(hp)
+            lib().crass_b200_free(pp)
+        return hits, pool, found
+
+    def dr_search(self, bases, offsets, params=None, want_found=True):
+        """searchCore over a host batch -> (hits sorted by read index, start/stop pool, found flags)."""
+        params = params or Params()
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        return self._collect(lambda f, hp, nh, pp, npl: lib().crass_b200_dr_search(
+            self.h, _np_ptr(bases), _np_ptr(offsets), n, C.byref(params), f, hp, nh, pp, npl), n, want_found)
+
+    def ac_scan(self, ac, bases, offsets, skip=None, want_found=True):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        if skip is not None:
+            skip = np.ascontiguousarray(skip, dtype=np.uint8)
+        return self._collect(lambda f, hp, nh, pp, npl: lib().crass_b200_ac_scan(
+            self.h, ac.h, _np_ptr(bases), _np_ptr(offsets), n, _np_ptr(skip) if skip is not None else None, f, hp, nh, pp, npl), n, want_found)
+
+    def edit_distance_batch(self, pairs):
+        blob = bytearray()
+        a_off, a_len, b_off, b_len = [], [], [], []
+        for a, b in pairs:
+            a_off.append(len(blob)); a_len.append(len(a)); blob += a
+            b_off.append(len(blob)); b_len.append(len(b)); blob += b
+        blob += b"\0"
+        data = np.frombuffer(bytes(blob), dtype=np.uint8).copy()
+        arrs = [np.asarray(x, dtype=np.uint32) for x in (a_off, a_len, b_off, b_len)]
+        dist = np.zeros(len(pairs), dtype=np.int32)
+        sim = np.zeros(len(pairs), dtype=np.float32)
+        _check(lib().crass_b200_edit_distance_batch(self.h, _np_ptr(data), len(data), *[_np_ptr(x) for x in arrs], len(pairs), _np_ptr(dist), _np_ptr(sim)))
+        return dist, sim
+
+    def scan_right(self, seq, ss, pattern, min_spacer, scan_range=24):
+        cap = 2 * (len(seq) // 4 + 8)
+        arr = (C.c_uint32 * cap)(*ss)
+        n = C.c_uint32(len(ss))
+        _check(lib().crass_b200_scan_right(self.h, seq, len(seq), arr, C.byref(n), cap, pattern, len(pattern), min_spacer, scan_range))
+        return list(arr[: n.value])
+
+    def extend_pre_repeat(self, seq, ss, window, min_spacer):
+        arr = (C.c_uint32 * len(ss))(*ss)
+        rl = C.c_uint32(0)
+        _check(lib().crass_b200_extend_pre_repeat(self.h, seq, len(seq), arr, len(ss), window, min_spacer, C.byref(rl)))
+        return rl.value, list(arr)
+
+    def run_files(self, paths, params=None, phases=2):
+        """searchFile* -> createNonRedundantSet -> findSingletons*; returns (Results, max_read_len)."""
+        params = params or Params()
+        arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+        out = C.c_void_p()
+        ml = C.c_int(0)
+        _check(lib().crass_b200_run_files(self.h, arr, len(paths), C.byref(params), phases, C.byref(out), C.byref(ml)))
+        return Results(out), ml.value
+
+    # -- device-resident entry points (torch tensors; only enqueue) ------------------------------------
+    def dr_search_dev(self, d_bases, d_offsets, n_reads, max_read_len, params, d_found, d_hits, d_pool, d_counters, stream=0):
+        _check(lib().crass_b200_dr_search_dev(self.h, d_bases.data_ptr(), d_offsets.data_ptr(), n_reads, max_read_len, C.byref(params),
+                                              d_found.data_ptr() if d_found is not None else None, d_hits.data_ptr(), d_hits.numel() // 4,
+                                              d_pool.data_ptr(), d_pool.numel(), d_counters.data_ptr(), stream))
+
+    def ac_scan_dev(self, ac, d_bases, d_offsets, n_reads, max_read_len, d_skip, d_found, d_hits, d_pool, d_counters, stream=0):
+        _check(lib().crass_b200_ac_scan_dev(self.h, ac.h, d_bases.data_ptr(), d_offsets.data_ptr(), n_reads, max_read_len,
+                                            d_skip.data_ptr() if d_skip is not None else None,
+                                            d_found.data_ptr() if d_found is not None else None, d_hits.data_ptr(), d_hits.numel() // 4,
+                                            d_pool.data_ptr(), d_pool.numel(), d_counters.data_ptr(), stream))

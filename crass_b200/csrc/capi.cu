@@ -1,0 +1,437 @@
+// capi.cu -- the extern "C" boundary (include/crass_b200.h): contexts, launches, host<->device plumbing.
+//
+// No CPU fallback lives here: every compute entry point needs a CUDA device and fails with
+// CRASS_B200_ENODEVICE otherwise.  Host-side bookkeeping (parser, replay, clustering, automaton
+// construction) is in host/*.cpp.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/crass_b200.h"
+#include "host/internal.h"
+#include "kernels.cuh"
+
+namespace cbh { const char* last_error_cstr(); }
+
+#define CB_STR2(x) #x
+#define CB_STR(x) CB_STR2(x)
+
+namespace {
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            std::ostringstream _s;                                                                       \
+            _s << #expr << " failed: " << cudaGetErrorString(_e) << " (" << __FILE__ << ":" << __LINE__ << ")"; \
+            return cbh::fail(_e == cudaErrorMemoryAllocation ? CRASS_B200_ENOMEM : CRASS_B200_ECUDA, _s.str()); \
+        }                                                                                                \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        CUDA_TRY(cudaMalloc(&p, want));
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+int g_device_count = -2;    // -2: not probed
+
+int probe_devices() {
+    if (g_device_count == -2) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        g_device_count = (e == cudaSuccess) ? n : 0;
+        if (e != cudaSuccess) (void)cudaGetLastError();
+    }
+    return g_device_count;
+}
+
+cb::Params to_core(const crass_b200_params& p) {
+    cb::Params o;
+    o.low_dr = p.low_dr; o.high_dr = p.high_dr; o.low_spacer = p.low_spacer; o.high_spacer = p.high_spacer;
+    o.window = p.window; o.min_repeats = p.min_repeats; o.kmer_clust = p.kmer_clust; o.scan_range = p.scan_range;
+    return o;
+}
+
+int validate_params(const crass_b200_params* p) {
+    if (!p) return cbh::fail(CRASS_B200_EINVAL, "params is NULL");
+    if (p->window < 1 || p->window > 32) return cbh::fail(CRASS_B200_EINVAL, "window must be in 1..32 (the reference CLI clamps it to 6..9)");
+    if (p->min_repeats < 1) return cbh::fail(CRASS_B200_EINVAL, "min_repeats must be >= 1 (0 is undefined behaviour in the reference)");
+    if (p->high_dr > (uint32_t)cb::kMaxEdit || p->high_spacer > (uint32_t)cb::kMaxEdit)
+        return cbh::fail(CRASS_B200_EINVAL, "high_dr / high_spacer above 255 are not supported");
+    if (p->low_dr > p->high_dr || p->low_spacer > p->high_spacer) return cbh::fail(CRASS_B200_EINVAL, "low bound above high bound");
+    return 0;
+}
+
+}  // namespace
+
+struct crass_b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    uint64_t launches = 0;
+    DevBuf d_bases, d_offsets, d_found, d_skip, d_hits, d_pool, d_counters, d_scratch, d_error, d_misc, d_symv;
+    uint32_t* h_counters = nullptr;   // pinned, 8 words
+};
+
+namespace cbh {
+
+void* alloc_host(size_t bytes, bool* pinned) {
+    *pinned = false;
+    if (probe_devices() > 0) {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) { *pinned = true; return p; }
+        (void)cudaGetLastError();
+    }
+    return malloc(bytes);
+}
+
+void free_host(void* p, bool pinned) {
+    if (!p) return;
+    if (pinned) cudaFreeHost(p); else free(p);
+}
+
+void free_device_tables(Automaton* a) {
+    if (a->d_table) { cudaFree(a->d_table); a->d_table = nullptr; }
+    if (a->d_out_len) { cudaFree(a->d_out_len); a->d_out_len = nullptr; }
+}
+
+}  // namespace cbh
+
+// ======================================================================================================
+extern "C" {
+
+const char* crass_b200_last_error(void) { return cbh::last_error_cstr(); }
+int crass_b200_abi_version(void) { return CRASS_B200_ABI_VERSION; }
+const char* crass_b200_build_info(void) {
+    return "crass_b200 hot path; CUDA " CB_STR(CUDART_VERSION) "; sm_100a; kernels: dr_search_generic, ac_scan_generic, edit_distance";
+}
+int crass_b200_device_count(void) { return probe_devices(); }
+
+void crass_b200_default_params(crass_b200_params* p) {
+    p->low_dr = 23; p->high_dr = 47; p->low_spacer = 26; p->high_spacer = 50;      // crassDefines.h:121-124
+    p->window = 8; p->min_repeats = 2; p->kmer_clust = 6; p->scan_range = 24;        // :56,:91,:67 ; libcrispr.cpp:347
+}
+
+int crass_b200_ctx_create(int device, crass_b200_ctx** out) {
+    if (!out) return cbh::fail(CRASS_B200_EINVAL, "out is NULL");
+    if (probe_devices() <= 0) return cbh::fail(CRASS_B200_ENODEVICE, "no CUDA device: crass_b200 has no CPU execution path");
+    if (device < 0 || device >= probe_devices()) return cbh::fail(CRASS_B200_EINVAL, "bad device ordinal");
+    CUDA_TRY(cudaSetDevice(device));
+    crass_b200_ctx* c = new crass_b200_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaHostAlloc((void**)&c->h_counters, 8 * sizeof(uint32_t), cudaHostAllocDefault));
+    *out = c;
+    return 0;
+}
+
+void crass_b200_ctx_destroy(crass_b200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->d_bases, &c->d_offsets, &c->d_found, &c->d_skip, &c->d_hits, &c->d_pool, &c->d_counters,
+                      &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv};
+    for (DevBuf* b : bufs) b->release();
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int crass_b200_ctx_device(const crass_b200_ctx* c) { return c ? c->device : -1; }
+uint64_t crass_b200_ctx_launch_count(const crass_b200_ctx* c) { return c ? c->launches : 0; }
+
+// ---- K1 ------------------------------------------------------------------------------------------------
+int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
+                             uint32_t max_read_len, const crass_b200_params* params, uint8_t* d_found,
+                             crass_b200_hit* d_hits, uint32_t hits_cap, uint32_t* d_ss_pool, uint32_t ss_cap,
+                             uint32_t* d_counters, void* stream_v) {
+    if (!c) return cbh::fail(CRASS_B200_EINVAL, "ctx is NULL");
+    if (int r = validate_params(params)) return r;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
+    const cb::Params o = to_core(*params);
+    CUDA_TRY(cudaMemsetAsync(d_counters, 0, 4 * sizeof(uint32_t), st));
+    if (n_reads == 0) return 0;
+    if (int r = c->d_error.reserve(sizeof(int))) return r;
+    CUDA_TRY(cudaMemsetAsync(c->d_error.p, 0, sizeof(int), st));
+    cbk::HitSink sink{d_hits, hits_cap, d_ss_pool, ss_cap, d_counters};
+    const uint32_t cap = cb::ss_capacity(o, max_read_len);
+    const int threads = 128;
+    if (cap <= 32) {
+        int blocks = (int)std::min<uint64_t>(((uint64_t)n_reads + threads - 1) / threads, (uint64_t)c->sm_count * 64);
+        cbk::k_dr_search_generic<32><<<blocks, threads, 0, st>>>(d_bases, d_offsets, n_reads, o, d_found, sink, nullptr, 0, c->d_error.as<int>());
+    } else {
+        int blocks = (int)std::min<uint64_t>(((uint64_t)n_reads + threads - 1) / threads, (uint64_t)c->sm_count * 16);
+        if (int r = c->d_scratch.reserve((size_t)blocks * threads * cap * sizeof(uint32_t))) return r;
+        cbk::k_dr_search_generic<0><<<blocks, threads, 0, st>>>(d_bases, d_offsets, n_reads, o, d_found, sink, c->d_scratch.as<uint32_t>(), cap, c->d_error.as<int>());
+    }
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"
+
+namespace {
+
+// shared tail of the two host-facing search calls: run `launch` with growing output buffers until nothing
+// overflows, then bring the hits back sorted by read index.
+template <class Launch>
+int run_with_outputs(crass_b200_ctx* c, uint32_t n_reads, uint64_t n_bases, uint8_t* found_host, Launch launch,
+                     crass_b200_hit** hits, uint32_t* n_hits, uint32_t** ss_pool, uint32_t* n_ss_pool) {
+    uint32_t hits_cap = std::max<uint32_t>(4096, n_reads / 4 + 16);
+    uint32_t pool_cap = hits_cap * 6;
+    if (int r = c->d_counters.reserve(8 * sizeof(uint32_t))) return r;
+    if (int r = c->d_found.reserve((size_t)n_reads + 16)) return r;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        if (int r = c->d_hits.reserve((size_t)hits_cap * sizeof(crass_b200_hit))) return r;
+        if (int r = c->d_pool.reserve((size_t)pool_cap * sizeof(uint32_t))) return r;
+        if (int r = launch(hits_cap, pool_cap)) return r;
+        CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->d_counters.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (!c->h_counters[2]) break;
+        hits_cap = c->h_counters[0] + 16;
+        pool_cap = c->h_counters[1] + 16;
+        if (attempt == 2) return cbh::fail(CRASS_B200_EOVERFLOW, "hit buffers overflowed three times");
+    }
+    int err = 0;
+    if (c->d_error.p) {
+        CUDA_TRY(cudaMemcpyAsync(&err, c->d_error.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (err) return cbh::fail(CRASS_B200_EINVAL, "kernel reported a condition where the reference throws");
+    }
+    const uint32_t nh = c->h_counters[0], np = c->h_counters[1];
+    crass_b200_hit* h = (crass_b200_hit*)malloc(sizeof(crass_b200_hit) * (size_t)(nh ? nh : 1));
+    uint32_t* p = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(np ? np : 1));
+    if (!h || !p) { free(h); free(p); return cbh::fail(CRASS_B200_ENOMEM, "malloc"); }
+    if (nh) CUDA_TRY(cudaMemcpyAsync(h, c->d_hits.p, sizeof(crass_b200_hit) * (size_t)nh, cudaMemcpyDeviceToHost, c->stream));
+    if (np) CUDA_TRY(cudaMemcpyAsync(p, c->d_pool.p, sizeof(uint32_t) * (size_t)np, cudaMemcpyDeviceToHost, c->stream));
+    if (found_host) CUDA_TRY(cudaMemcpyAsync(found_host, c->d_found.p, n_reads, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    std::sort(h, h + nh, [](const crass_b200_hit& a, const crass_b200_hit& b) { return a.read_index < b.read_index; });
+    *hits = h; *n_hits = nh; *ss_pool = p; *n_ss_pool = np;
+    (void)n_bases;
+    return 0;
+}
+
+int upload_batch(crass_b200_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, uint64_t n_bases) {
+    if (int r = c->d_bases.reserve(n_bases + 64)) return r;
+    if (int r = c->d_offsets.reserve(((size_t)n_reads + 1) * sizeof(uint64_t))) return r;
+    CUDA_TRY(cudaMemcpyAsync(c->d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_offsets.p, offsets, ((size_t)n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+uint32_t max_len_of(const uint64_t* offsets, uint32_t n_reads) {
+    uint64_t m = 0;
+    for (uint32_t i = 0; i < n_reads; ++i) m = std::max<uint64_t>(m, offsets[i + 1] - offsets[i]);
+    return (uint32_t)m;
+}
+
+}  // namespace
+
+extern "C" {
+
+int crass_b200_dr_search(crass_b200_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
+                         const crass_b200_params* params, uint8_t* found, crass_b200_hit** hits, uint32_t* n_hits,
+                         uint32_t** ss_pool, uint32_t* n_ss_pool) {
+    if (!c) return cbh::fail(CRASS_B200_EINVAL, "ctx is NULL");
+    if (!hits || !n_hits || !ss_pool || !n_ss_pool) return cbh::fail(CRASS_B200_EINVAL, "output pointer is NULL");
+    if (int r = validate_params(params)) return r;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const uint64_t n_bases = n_reads ? offsets[n_reads] : 0;
+    if (n_reads && offsets[0] != 0) return cbh::fail(CRASS_B200_EINVAL, "offsets[0] must be 0");
+    const uint32_t max_len = max_len_of(offsets, n_reads);
+    if (int r = upload_batch(c, bases, offsets, n_reads, n_bases)) return r;
+    auto launch = [&](uint32_t hits_cap, uint32_t pool_cap) {
+        return crass_b200_dr_search_dev(c, c->d_bases.as<uint8_t>(), c->d_offsets.as<uint64_t>(), n_reads, max_len, params,
+                                        c->d_found.as<uint8_t>(), c->d_hits.as<crass_b200_hit>(), hits_cap,
+                                        c->d_pool.as<uint32_t>(), pool_cap, c->d_counters.as<uint32_t>(), c->stream);
+    };
+    return run_with_outputs(c, n_reads, n_bases, found, launch, hits, n_hits, ss_pool, n_ss_pool);
+}
+
+// ---- K2 ------------------------------------------------------------------------------------------------
+int crass_b200_ac_build(const uint8_t* pat_bytes, const uint32_t* pat_offsets, uint32_t n_patterns, crass_b200_ac** out) {
+    if (!pat_bytes || !pat_offsets || !out) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    cbh::Automaton* a = nullptr;
+    if (int r = cbh::build_automaton(pat_bytes, pat_offsets, n_patterns, &a)) return r;
+    // crass_b200_ac is a thin wrapper; move the automaton in
+    crass_b200_ac* h = new crass_b200_ac();
+    h->a.n_states = a->n_states; h->a.n_syms = a->n_syms; memcpy(h->a.symv, a->symv, 256);
+    h->a.table.swap(a->table); h->a.stride = a->stride; h->a.out_len.swap(a->out_len);
+    h->a.min_pattern_len = a->min_pattern_len; h->a.max_pattern_len = a->max_pattern_len; h->a.n_patterns = a->n_patterns;
+    delete a;
+    *out = h;
+    return 0;
+}
+
+void crass_b200_ac_destroy(crass_b200_ac* ac) { delete ac; }
+uint32_t crass_b200_ac_num_states(const crass_b200_ac* ac) { return ac ? ac->a.n_states : 0; }
+uint32_t crass_b200_ac_num_symbols(const crass_b200_ac* ac) { return ac ? ac->a.n_syms : 0; }
+uint64_t crass_b200_ac_table_bytes(const crass_b200_ac* ac) { return ac ? (uint64_t)ac->a.table.size() * 4 : 0; }
+
+}  // extern "C"
+
+namespace {
+int ensure_ac_on_device(crass_b200_ctx* c, crass_b200_ac* ac) {
+    cbh::Automaton& a = ac->a;
+    if (a.d_table && a.device == c->device) return 0;
+    cbh::free_device_tables(&a);
+    CUDA_TRY(cudaMalloc(&a.d_table, a.table.size() * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&a.d_out_len, 256));                           // symv lives here
+    CUDA_TRY(cudaMemcpyAsync(a.d_table, a.table.data(), a.table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(a.d_out_len, a.symv, 256, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    a.device = c->device;
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const uint8_t* d_bases, const uint64_t* d_offsets,
+                           uint32_t n_reads, uint32_t max_read_len, const uint8_t* d_skip, uint8_t* d_found,
+                           crass_b200_hit* d_hits, uint32_t hits_cap, uint32_t* d_ss_pool, uint32_t ss_cap,
+                           uint32_t* d_counters, void* stream_v) {
+    (void)max_read_len;
+    if (!c || !ac_c) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    crass_b200_ac* ac = const_cast<crass_b200_ac*>(ac_c);
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (int r = ensure_ac_on_device(c, ac)) return r;
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
+    CUDA_TRY(cudaMemsetAsync(d_counters, 0, 4 * sizeof(uint32_t), st));
+    if (n_reads == 0) return 0;
+    cbk::HitSink sink{d_hits, hits_cap, d_ss_pool, ss_cap, d_counters};
+    uint32_t stride_log2 = 0;
+    while ((1u << stride_log2) < ac->a.stride) ++stride_log2;
+    const int threads = 256;
+    int blocks = (int)std::min<uint64_t>(((uint64_t)n_reads + threads - 1) / threads, (uint64_t)c->sm_count * 32);
+    cbk::k_ac_scan_generic<<<blocks, threads, 0, st>>>(d_bases, d_offsets, n_reads, (const uint32_t*)ac->a.d_table, stride_log2,
+                                                       (const uint8_t*)ac->a.d_out_len, d_skip, d_found, sink);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int crass_b200_ac_scan(crass_b200_ctx* c, const crass_b200_ac* ac, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
+                       const uint8_t* skip, uint8_t* found, crass_b200_hit** hits, uint32_t* n_hits, uint32_t** ss_pool,
+                       uint32_t* n_ss_pool) {
+    if (!c || !ac) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    if (!hits || !n_hits || !ss_pool || !n_ss_pool) return cbh::fail(CRASS_B200_EINVAL, "output pointer is NULL");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const uint64_t n_bases = n_reads ? offsets[n_reads] : 0;
+    const uint32_t max_len = max_len_of(offsets, n_reads);
+    if (int r = upload_batch(c, bases, offsets, n_reads, n_bases)) return r;
+    if (skip) {
+        if (int r = c->d_skip.reserve((size_t)n_reads + 16)) return r;
+        CUDA_TRY(cudaMemcpyAsync(c->d_skip.p, skip, n_reads, cudaMemcpyHostToDevice, c->stream));
+    }
+    auto launch = [&](uint32_t hits_cap, uint32_t pool_cap) {
+        return crass_b200_ac_scan_dev(c, ac, c->d_bases.as<uint8_t>(), c->d_offsets.as<uint64_t>(), n_reads, max_len,
+                                      skip ? c->d_skip.as<uint8_t>() : nullptr, c->d_found.as<uint8_t>(),
+                                      c->d_hits.as<crass_b200_hit>(), hits_cap, c->d_pool.as<uint32_t>(), pool_cap,
+                                      c->d_counters.as<uint32_t>(), c->stream);
+    };
+    return run_with_outputs(c, n_reads, n_bases, found, launch, hits, n_hits, ss_pool, n_ss_pool);
+}
+
+// ---- K3 ------------------------------------------------------------------------------------------------
+int crass_b200_edit_distance_batch(crass_b200_ctx* c, const uint8_t* bytes, uint64_t n_bytes, const uint32_t* a_off,
+                                   const uint32_t* a_len, const uint32_t* b_off, const uint32_t* b_len, uint32_t n_pairs,
+                                   int32_t* out_dist, float* out_sim) {
+    if (!c) return cbh::fail(CRASS_B200_EINVAL, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n_pairs == 0) return 0;
+    for (uint32_t i = 0; i < n_pairs; ++i) {
+        if (a_len[i] > (uint32_t)cb::kMaxEdit || b_len[i] > (uint32_t)cb::kMaxEdit) return cbh::fail(CRASS_B200_EINVAL, "string longer than 255");
+        if ((uint64_t)a_off[i] + a_len[i] > n_bytes || (uint64_t)b_off[i] + b_len[i] > n_bytes) return cbh::fail(CRASS_B200_EINVAL, "pair out of range");
+    }
+    const size_t idx_bytes = (size_t)n_pairs * sizeof(uint32_t);
+    if (int r = c->d_bases.reserve(n_bytes + 64)) return r;
+    if (int r = c->d_misc.reserve(idx_bytes * 6)) return r;
+    uint8_t* m = c->d_misc.as<uint8_t>();
+    CUDA_TRY(cudaMemcpyAsync(c->d_bases.p, bytes, n_bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(m + 0 * idx_bytes, a_off, idx_bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(m + 1 * idx_bytes, a_len, idx_bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(m + 2 * idx_bytes, b_off, idx_bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(m + 3 * idx_bytes, b_len, idx_bytes, cudaMemcpyHostToDevice, c->stream));
+    const int threads = 128;
+    const int blocks = (int)((n_pairs + threads - 1) / threads);
+    cbk::k_edit_distance<<<blocks, threads, 0, c->stream>>>(c->d_bases.as<uint8_t>(), (uint32_t*)(m + 0 * idx_bytes), (uint32_t*)(m + 1 * idx_bytes),
+                                                             (uint32_t*)(m + 2 * idx_bytes), (uint32_t*)(m + 3 * idx_bytes), n_pairs,
+                                                             (int32_t*)(m + 4 * idx_bytes), (float*)(m + 5 * idx_bytes));
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_dist, m + 4 * idx_bytes, idx_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(out_sim, m + 5 * idx_bytes, idx_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- KAT entry points -----------------------------------------------------------------------------------
+int crass_b200_scan_right(crass_b200_ctx* c, const uint8_t* seq, uint32_t len, uint32_t* ss, uint32_t* n_ss, uint32_t ss_cap,
+                          const uint8_t* pattern, uint32_t pattern_len, uint32_t min_spacer, uint32_t scan_range) {
+    if (!c || !seq || !ss || !n_ss || !pattern) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    if (*n_ss < 4 || *n_ss > ss_cap) return cbh::fail(CRASS_B200_EINVAL, "need at least two repeats in ss");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (int r = c->d_bases.reserve((size_t)len + pattern_len + 64)) return r;
+    if (int r = c->d_misc.reserve(((size_t)ss_cap + 4) * sizeof(uint32_t))) return r;
+    uint32_t* d_ss = c->d_misc.as<uint32_t>() + 4;
+    uint32_t* d_n = c->d_misc.as<uint32_t>();
+    CUDA_TRY(cudaMemcpyAsync(c->d_bases.p, seq, len, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_bases.as<uint8_t>() + len, pattern, pattern_len, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_ss, ss, *n_ss * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_n, n_ss, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    cbk::k_scan_right_one<<<1, 1, 0, c->stream>>>(c->d_bases.as<uint8_t>(), len, d_ss, d_n, ss_cap, pattern_len, min_spacer, scan_range);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(n_ss, d_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpyAsync(ss, d_ss, *n_ss * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int crass_b200_extend_pre_repeat(crass_b200_ctx* c, const uint8_t* seq, uint32_t len, uint32_t* ss, uint32_t n_ss,
+                                 uint32_t window, uint32_t min_spacer, uint32_t* repeat_len) {
+    if (!c || !seq || !ss || !repeat_len) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    if (n_ss < 4 || (n_ss & 1)) return cbh::fail(CRASS_B200_EINVAL, "need at least two repeats in ss");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (int r = c->d_bases.reserve((size_t)len + 64)) return r;
+    if (int r = c->d_misc.reserve(((size_t)n_ss + 4) * sizeof(uint32_t))) return r;
+    uint32_t* d_ss = c->d_misc.as<uint32_t>() + 4;
+    uint32_t* d_r = c->d_misc.as<uint32_t>();
+    CUDA_TRY(cudaMemcpyAsync(c->d_bases.p, seq, len, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_ss, ss, n_ss * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    cbk::k_extend_one<<<1, 1, 0, c->stream>>>(c->d_bases.as<uint8_t>(), len, d_ss, n_ss, window, min_spacer, d_r);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(repeat_len, d_r, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(ss, d_ss, n_ss * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+void crass_b200_free(void* p) { free(p); }
+
+}  // extern "C"

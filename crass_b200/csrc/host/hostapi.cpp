@@ -1,0 +1,281 @@
+// hostapi.cpp -- the host-only entry points of include/crass_b200.h: feed path, replay containers, the
+// step between the phases, and the whole-path driver that strings the kernels together the way
+// WorkHorse::parseSeqFiles does (WorkHorse.cpp:321-414).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+
+using namespace cbh;
+
+namespace {
+
+char* dup_cstr(const std::string& s) {
+    char* p = (char*)malloc(s.size() + 1);
+    if (!p) return nullptr;
+    memcpy(p, s.data(), s.size());
+    p[s.size()] = 0;
+    return p;
+}
+
+std::vector<std::string> split_lines(const char* text) {
+    std::vector<std::string> v;
+    if (!text) return v;
+    const char* p = text;
+    while (*p) {
+        const char* e = strchr(p, '\n');
+        if (!e) e = p + strlen(p);
+        if (e > p) v.push_back(std::string(p, e));
+        p = *e ? e + 1 : e;
+    }
+    return v;
+}
+
+// the (header, comment, qual) triple searchFile copies into the ReadHolder (libcrispr.cpp:112-131)
+void fill_holder(HeldRead& h, const Batch& b, uint32_t i) {
+    h.seq.assign((const char*)b.bases + b.offsets[i], (size_t)(b.offsets[i + 1] - b.offsets[i]));
+    h.header = b.name_pool.data() + b.name_off[i];
+    if (b.comment_off[i] >= 0) h.comment = b.text_pool.data() + b.comment_off[i];
+    if (b.qual_off[i] >= 0) { h.qual = b.text_pool.data() + b.qual_off[i]; h.is_fasta = false; }
+}
+
+int check_hits(const Batch& b, const crass_b200_hit* hits, uint32_t n_hits) {
+    for (uint32_t k = 0; k < n_hits; ++k) {
+        if (hits[k].read_index >= b.n()) return fail(CRASS_B200_EINVAL, "hit refers to a read outside the batch");
+        if (k && hits[k].read_index < hits[k - 1].read_index) return fail(CRASS_B200_EINVAL, "hits must be sorted by read_index (replay is order sensitive)");
+        if (hits[k].n_ss < 2 || (hits[k].n_ss & 1)) return fail(CRASS_B200_EINVAL, "malformed start/stop list");
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- feed path -----------------------------------------------------------------------------------------
+int crass_b200_parse_file(const char* path, crass_b200_batch** out) {
+    if (!path || !out) return fail(CRASS_B200_EINVAL, "NULL argument");
+    Batch* b = nullptr;
+    if (int r = parse_file(path, &b)) return r;
+    crass_b200_batch* h = new crass_b200_batch();
+    // move the parsed content into the handle
+    std::swap(h->b.bases, b->bases); std::swap(h->b.bases_cap, b->bases_cap); std::swap(h->b.pinned, b->pinned);
+    h->b.offsets.swap(b->offsets); h->b.name_pool.swap(b->name_pool); h->b.name_off.swap(b->name_off);
+    h->b.text_pool.swap(b->text_pool); h->b.comment_off.swap(b->comment_off); h->b.qual_off.swap(b->qual_off);
+    h->b.max_len = b->max_len; h->b.parse_status = b->parse_status;
+    delete b;
+    *out = h;
+    return 0;
+}
+
+int crass_b200_batch_from_memory(const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, const char* const* names,
+                                 crass_b200_batch** out) {
+    if (!offsets || !out || (n_reads && !bases)) return fail(CRASS_B200_EINVAL, "NULL argument");
+    crass_b200_batch* h = new crass_b200_batch();
+    Batch& b = h->b;
+    try {
+        b.offsets.assign(offsets, offsets + n_reads + 1);
+        b.reserve_bases((size_t)offsets[n_reads] + 16);
+        memcpy(b.bases, bases, (size_t)offsets[n_reads]);
+        char tmp[32];
+        for (uint32_t i = 0; i < n_reads; ++i) {
+            const char* nm = names ? names[i] : tmp;
+            if (!names) snprintf(tmp, sizeof tmp, "r%010u", i);
+            b.name_off.push_back(b.name_pool.size());
+            b.name_pool.insert(b.name_pool.end(), nm, nm + strlen(nm) + 1);
+            b.comment_off.push_back(-1);
+            b.qual_off.push_back(-1);
+            const uint64_t L = offsets[i + 1] - offsets[i];
+            if (L > b.max_len) b.max_len = (uint32_t)L;
+        }
+    } catch (std::exception& e) {
+        delete h;
+        return fail(CRASS_B200_ENOMEM, e.what());
+    }
+    *out = h;
+    return 0;
+}
+
+void crass_b200_batch_destroy(crass_b200_batch* b) { delete b; }
+uint32_t crass_b200_batch_num_reads(const crass_b200_batch* b) { return b ? b->b.n() : 0; }
+uint32_t crass_b200_batch_max_read_len(const crass_b200_batch* b) { return b ? b->b.max_len : 0; }
+int crass_b200_batch_parse_status(const crass_b200_batch* b) { return b ? b->b.parse_status : -1; }
+const uint8_t* crass_b200_batch_bases(const crass_b200_batch* b) { return b ? b->b.bases : nullptr; }
+const uint64_t* crass_b200_batch_offsets(const crass_b200_batch* b) { return b ? b->b.offsets.data() : nullptr; }
+const char* crass_b200_batch_name(const crass_b200_batch* b, uint32_t i) {
+    return (b && i < b->b.n()) ? b->b.name_pool.data() + b->b.name_off[i] : nullptr;
+}
+const char* crass_b200_batch_comment(const crass_b200_batch* b, uint32_t i, int* has) {
+    if (!b || i >= b->b.n()) { if (has) *has = 0; return nullptr; }
+    const int64_t o = b->b.comment_off[i];
+    if (has) *has = o >= 0;
+    return o >= 0 ? b->b.text_pool.data() + o : "";
+}
+const char* crass_b200_batch_qual(const crass_b200_batch* b, uint32_t i, int* has) {
+    if (!b || i >= b->b.n()) { if (has) *has = 0; return nullptr; }
+    const int64_t o = b->b.qual_off[i];
+    if (has) *has = o >= 0;
+    return o >= 0 ? b->b.text_pool.data() + o : "";
+}
+
+// ---- replay ----------------------------------------------------------------------------------------------
+int crass_b200_results_create(crass_b200_results** out) {
+    if (!out) return fail(CRASS_B200_EINVAL, "NULL argument");
+    *out = new crass_b200_results();
+    return 0;
+}
+void crass_b200_results_destroy(crass_b200_results* r) { delete r; }
+
+int crass_b200_results_add_phase1(crass_b200_results* rh, const crass_b200_batch* bh, const crass_b200_hit* hits, uint32_t n_hits,
+                                  const uint32_t* ss_pool) {
+    if (!rh || !bh || (n_hits && (!hits || !ss_pool))) return fail(CRASS_B200_EINVAL, "NULL argument");
+    Results& r = rh->r;
+    const Batch& b = bh->b;
+    if (int e = check_hits(b, hits, n_hits)) return e;
+    for (uint32_t k = 0; k < n_hits; ++k) {                                 // searchFile's loop body for a hit (libcrispr.cpp:134-139)
+        const crass_b200_hit& ht = hits[k];
+        HeldRead* h = new HeldRead();
+        fill_holder(*h, b, ht.read_index);
+        h->ss.assign(ss_pool + ht.ss_offset, ss_pool + ht.ss_offset + ht.n_ss);
+        h->repeat_len = ht.repeat_len;
+        h->phase = 1;
+        // patternsHash takes repeatStringAt(0) of the un-flipped temporary holder
+        const uint32_t st = h->ss[0];
+        std::string raw0 = st <= h->seq.size() ? h->seq.substr(st, (size_t)(h->ss[1] - h->ss[0] + 1)) : std::string();
+        add_read_holder(r, h);
+        r.patterns_hash[raw0] = true;
+        r.reads_found[h->header] = true;
+    }
+    r.n_found_phase1 = r.reads_found.size();
+    return 0;
+}
+
+int crass_b200_results_add_phase2(crass_b200_results* rh, const crass_b200_batch* bh, const crass_b200_hit* hits, uint32_t n_hits,
+                                  const uint32_t* ss_pool) {
+    if (!rh || !bh || (n_hits && (!hits || !ss_pool))) return fail(CRASS_B200_EINVAL, "NULL argument");
+    Results& r = rh->r;
+    const Batch& b = bh->b;
+    if (int e = check_hits(b, hits, n_hits)) return e;
+    for (uint32_t k = 0; k < n_hits; ++k) {                                 // on_match (libcrispr.cpp:408-442)
+        const crass_b200_hit& ht = hits[k];
+        const char* name = b.name_pool.data() + b.name_off[ht.read_index];
+        if (r.reads_found.find(name) != r.reads_found.end()) continue;      // keyed by HEADER, not by index
+        HeldRead* h = new HeldRead();
+        fill_holder(*h, b, ht.read_index);
+        h->ss.assign(ss_pool + ht.ss_offset, ss_pool + ht.ss_offset + ht.n_ss);
+        h->repeat_len = 0;
+        h->phase = 2;
+        add_read_holder(r, h);
+    }
+    return 0;
+}
+
+uint32_t crass_b200_results_num_tokens(const crass_b200_results* r) { return r ? (uint32_t)r->r.t2s.size() : 0; }
+uint32_t crass_b200_results_num_reads(const crass_b200_results* r) { return r ? (uint32_t)r->r.num_reads() : 0; }
+
+char* crass_b200_results_dr_list(const crass_b200_results* r) {
+    std::string s;
+    if (r) for (const std::string& d : r->r.t2s) { s += d; s += '\n'; }
+    return dup_cstr(s);
+}
+
+int crass_b200_results_adopt_tokens(crass_b200_results* rh, const char* dr_list_all_ranks) {
+    if (!rh) return fail(CRASS_B200_EINVAL, "NULL argument");
+    Results& r = rh->r;
+    // global first-appearance order over the rank-ordered concatenation == the sequential token order
+    std::vector<std::string> all = split_lines(dr_list_all_ranks);
+    std::map<std::string, int> s2t;
+    std::vector<std::string> t2s;
+    for (const std::string& d : all) if (s2t.find(d) == s2t.end()) { s2t[d] = (int)t2s.size() + 2; t2s.push_back(d); }
+    for (const std::string& d : r.t2s) if (s2t.find(d) == s2t.end()) return fail(CRASS_B200_EINVAL, "local DR missing from the gathered list");
+    std::map<int, std::vector<HeldRead*> > reads;
+    for (auto& kv : r.reads) {
+        const int nt = s2t[r.t2s[kv.first - 2]];
+        for (HeldRead* h : kv.second) { h->token = nt; reads[nt].push_back(h); }
+    }
+    r.reads.swap(reads);
+    r.s2t.swap(s2t);
+    r.t2s.swap(t2s);
+    r.next_free_token = (int)r.t2s.size() + 1;
+    return 0;
+}
+
+char* crass_b200_results_non_redundant(crass_b200_results* rh, uint32_t kmer_clust, uint32_t* n_patterns) {
+    if (!rh) return nullptr;
+    Results& r = rh->r;
+    r.token_groups.clear();
+    r.non_redundant = non_redundant_set(r.t2s, (int)kmer_clust, &r.token_groups);
+    if (n_patterns) *n_patterns = (uint32_t)r.non_redundant.size();
+    std::string s;
+    for (const std::string& p : r.non_redundant) { s += p; s += '\n'; }
+    return dup_cstr(s);
+}
+
+char* crass_b200_results_dump(crass_b200_results* r, int max_read_len) {
+    if (!r) return nullptr;
+    return dup_cstr(dump_results(r->r, max_read_len));
+}
+
+char* crass_b200_non_redundant_set(const char* dr_list, uint32_t kmer_clust) {
+    std::vector<std::string> drs = split_lines(dr_list);
+    std::vector<std::pair<int, int> > groups;
+    std::vector<std::string> nr = non_redundant_set(drs, (int)kmer_clust, &groups);
+    std::ostringstream os;
+    for (auto& g : groups) os << "G\t" << g.first << "\t" << g.second << "\n";
+    for (auto& p : nr) os << "P\t" << p << "\n";
+    return dup_cstr(os.str());
+}
+
+// ---- the whole path -------------------------------------------------------------------------------------------
+int crass_b200_run_files(crass_b200_ctx* ctx, const char* const* paths, uint32_t n_paths, const crass_b200_params* params,
+                         int phases, crass_b200_results** out, int* max_read_len) {
+    if (!ctx || !paths || !params || !out) return fail(CRASS_B200_EINVAL, "NULL argument");
+    crass_b200_results* res = nullptr;
+    if (int r = crass_b200_results_create(&res)) return r;
+    std::vector<crass_b200_batch*> batches(n_paths, nullptr);
+    std::vector<std::vector<uint8_t> > found(n_paths);
+    int rc = 0, max_len = 0;
+    auto cleanup = [&]() { for (auto* b : batches) crass_b200_batch_destroy(b); };
+    for (uint32_t f = 0; f < n_paths && !rc; ++f) {                          // phase 1: searchFile per file
+        rc = crass_b200_parse_file(paths[f], &batches[f]);
+        if (rc) break;
+        const Batch& b = batches[f]->b;
+        if ((int)b.max_len > max_len) max_len = (int)b.max_len;
+        found[f].assign(b.n() + 1, 0);
+        crass_b200_hit* hits = nullptr; uint32_t nh = 0, np = 0; uint32_t* pool = nullptr;
+        rc = crass_b200_dr_search(ctx, b.bases, b.offsets.data(), b.n(), params, found[f].data(), &hits, &nh, &pool, &np);
+        if (!rc) rc = crass_b200_results_add_phase1(res, batches[f], hits, nh, pool);
+        free(hits); free(pool);
+    }
+    if (!rc) {
+        uint32_t n_pat = 0;
+        char* pats = crass_b200_results_non_redundant(res, params->kmer_clust, &n_pat);   // createNonRedundantSet
+        if (phases >= 2 && n_pat > 0) {                                      // WorkHorse.cpp:373 guards the empty set
+            std::vector<uint8_t> bytes; std::vector<uint32_t> offs(1, 0);
+            for (const std::string& p : res->r.non_redundant) { bytes.insert(bytes.end(), p.begin(), p.end()); offs.push_back((uint32_t)bytes.size()); }
+            crass_b200_ac* ac = nullptr;
+            rc = crass_b200_ac_build(bytes.data(), offs.data(), n_pat, &ac);
+            for (uint32_t f = 0; f < n_paths && !rc; ++f) {                  // phase 2: findSingletons per file
+                const Batch& b = batches[f]->b;
+                crass_b200_hit* hits = nullptr; uint32_t nh = 0, np = 0; uint32_t* pool = nullptr;
+                rc = crass_b200_ac_scan(ctx, ac, b.bases, b.offsets.data(), b.n(), found[f].data(), nullptr, &hits, &nh, &pool, &np);
+                if (!rc) rc = crass_b200_results_add_phase2(res, batches[f], hits, nh, pool);
+                free(hits); free(pool);
+            }
+            crass_b200_ac_destroy(ac);
+        }
+        free(pats);
+    }
+    cleanup();
+    if (rc) { crass_b200_results_destroy(res); return rc; }
+    if (max_read_len) *max_read_len = max_len;
+    *out = res;
+    return 0;
+}
+
+}  // extern "C"

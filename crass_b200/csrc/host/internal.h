@@ -1,0 +1,99 @@
+// internal.h -- host-side structures behind the opaque handles of include/crass_b200.h
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../../include/crass_b200.h"
+
+namespace cbh {
+
+// ---- error reporting (thread-local message behind crass_b200_last_error) ----------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+// ---- pinned host memory hooks (implemented next to the CUDA runtime; plain malloc without a device)
+void* alloc_host(size_t bytes, bool* pinned);
+void free_host(void* p, bool pinned);
+
+// ---- a parsed read set: the record stream kseq_read() hands to searchFile ------------------------
+struct Batch {
+    uint8_t* bases = nullptr;           // all reads back to back (pinned when a device exists)
+    size_t bases_cap = 0;
+    bool pinned = false;
+    std::vector<uint64_t> offsets;      // n+1
+    std::vector<char> name_pool;        // NUL-terminated strings
+    std::vector<uint64_t> name_off;
+    std::vector<char> text_pool;        // comments and qualities, NUL-terminated
+    std::vector<int64_t> comment_off;   // -1: seq->comment.s == NULL ; else offset of the string searchFile sees
+    std::vector<int64_t> qual_off;      // -1: seq->qual.s == NULL    ; (may be a STALE string of an earlier record)
+    uint32_t max_len = 0;
+    int parse_status = -1;              // value of the kseq_read() call that ended the loop
+    uint32_t n() const { return (uint32_t)(offsets.size() - 1); }
+    ~Batch();
+    void reserve_bases(size_t need);
+};
+
+int parse_file(const char* path, Batch** out);
+
+// ---- the containers the reference fills (ReadMap / StringCheck / lookupTable) ----------------------
+struct HeldRead {                       // the fields of ReadHolder the path sets (ReadHolder.h:440-451)
+    int token = 0;
+    int phase = 0;
+    bool was_lowlexi = false;           // RH_WasLowLexi
+    bool is_fasta = true;               // RH_IsFasta
+    uint32_t repeat_len = 0;            // RH_RepeatLength
+    std::vector<uint32_t> ss;           // RH_StartStops
+    std::string seq, header, comment, qual;
+};
+
+struct Results {
+    // StringCheck: first token is 2 (StringCheck.cpp:46-55)
+    int next_free_token = 1;
+    std::map<std::string, int> s2t;
+    std::vector<std::string> t2s;       // index = token - 2
+    // ReadMap: token -> reads in insertion order
+    std::map<int, std::vector<HeldRead*> > reads;
+    std::map<std::string, bool> patterns_hash, reads_found;
+    size_t n_found_phase1 = 0;
+    std::vector<std::string> non_redundant;          // last computed pattern list
+    std::vector<std::pair<int, int> > token_groups;  // (token, group id) in group order
+    ~Results();
+    size_t num_reads() const;
+};
+
+void reverse_complement(const uint8_t* in, size_t n, uint8_t* out);
+std::string reverse_complement(const std::string& s);
+// ReadHolder::DRLowLexi on a held read; returns the token string
+std::string dr_lowlexi(HeldRead& h);
+void add_read_holder(Results& r, HeldRead* h);
+// WorkHorse::createNonRedundantSet on tokens 2..; fills groups (token, gid) when not NULL
+std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, int min_count,
+                                           std::vector<std::pair<int, int> >* groups);
+std::string dump_results(Results& r, int max_read_len);
+
+// ---- multi-pattern automaton (dense DFA, failure links resolved) ---------------------------------------
+struct Automaton {
+    uint32_t n_states = 0, n_syms = 0;          // n_syms includes symbol 0 = "byte not in any pattern"
+    uint8_t symv[256];
+    std::vector<uint32_t> table;                // n_states * stride entries: next_state | (out_len << 24)?  see ac_build.cpp
+    uint32_t stride = 0;                        // entries per state (n_syms rounded up to a power of two)
+    uint32_t min_pattern_len = 0, max_pattern_len = 0, n_patterns = 0;
+    std::vector<uint16_t> out_len;              // longest pattern ending in the state (0 = none)
+    // device copies, owned by the context that uploaded them
+    void* d_table = nullptr;
+    void* d_out_len = nullptr;
+    int device = -1;
+    ~Automaton();
+};
+int build_automaton(const uint8_t* bytes, const uint32_t* offs, uint32_t n, Automaton** out);
+void free_device_tables(Automaton* a);          // implemented in the CUDA TU
+
+}  // namespace cbh
+
+struct crass_b200_batch { cbh::Batch b; };
+struct crass_b200_results { cbh::Results r; };
+struct crass_b200_ac { cbh::Automaton a; };

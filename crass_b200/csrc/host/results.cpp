@@ -1,0 +1,199 @@
+// results.cpp -- host replay of device hits into the containers the reference fills, and the
+// step between the two phases.
+//
+//   add_read_holder     addReadHolder               libcrispr.cpp:1119-1162
+//   dr_lowlexi          ReadHolder::DRLowLexi       ReadHolder.cpp:513-591 (+ reverseComplementSeq :593-610,
+//                                                   reverseStartStops :321-380)
+//   reverse_complement  reverseComplement/comp_tab  SeqUtils.cpp:51-87
+//   non_redundant_set   WorkHorse::createNonRedundantSet / clusterDRReads / removeRedundantRepeats
+//                                                   WorkHorse.cpp:648-709, 1404-1637, 612-645, 78-86
+// The GPU kernels decide WHICH reads hit and WHERE; everything here is O(hits) bookkeeping that has
+// to happen in read order on one thread because token numbers are handed out by first appearance.
+#include <string.h>
+
+#include <algorithm>
+#include <sstream>
+#include <unordered_map>
+
+#include "internal.h"
+
+namespace cbh {
+
+namespace {
+thread_local std::string g_err;
+// complement table of the reference: identity outside the letters, IUPAC aware, 'U'->'A',
+// and the reference's own oddity '`' (96) -> '@' (64)
+struct CompTab {
+    uint8_t t[128];
+    CompTab() {
+        for (int i = 0; i < 128; ++i) t[i] = (uint8_t)i;
+        const char* from = "ABCDEFGHIJKLMNOPQRSTUVWXYZ";
+        const char* to   = "TVGHEFCDIJMLKNOPQYSAABWXRZ";
+        for (int i = 0; i < 26; ++i) { t[(int)from[i]] = (uint8_t)to[i]; t[(int)from[i] + 32] = (uint8_t)(to[i] + 32); }
+        t[96] = 64;
+    }
+};
+const CompTab kComp;
+}  // namespace
+
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+const char* last_error_cstr() { return g_err.c_str(); }
+
+void reverse_complement(const uint8_t* in, size_t n, uint8_t* out) {
+    for (size_t i = 0; i < n; ++i) out[n - 1 - i] = kComp.t[in[i] & 127];
+}
+
+std::string reverse_complement(const std::string& s) {
+    std::string r(s.size(), '\0');
+    reverse_complement((const uint8_t*)s.data(), s.size(), (uint8_t*)&r[0]);
+    return r;
+}
+
+Results::~Results() {
+    for (auto& kv : reads) for (HeldRead* h : kv.second) delete h;
+}
+
+size_t Results::num_reads() const {
+    size_t n = 0;
+    for (auto& kv : reads) n += kv.second.size();
+    return n;
+}
+
+static std::string repeat_string_at(const HeldRead& h, size_t i) {
+    // ReadHolder::repeatStringAt: substr(start, end - start + 1)
+    const uint32_t st = h.ss[i];
+    if (st > h.seq.size()) return std::string();
+    return h.seq.substr(st, (size_t)(h.ss[i + 1] - h.ss[i] + 1));
+}
+
+std::string dr_lowlexi(HeldRead& h) {
+    const size_t n_rep = h.ss.size() / 2;
+    size_t idx;
+    if (n_rep == 1) idx = 0;
+    else if (n_rep == 2) {
+        if (h.ss.front() == 0) idx = 2;                                   // first repeat is a partial
+        else if (h.ss.back() == (uint32_t)h.seq.size()) idx = 0;          // never true: ends are clamped to L-1
+        else idx = ((int)(h.ss[1] - h.ss[0]) > (int)(h.ss[3] - h.ss[2])) ? 0 : 2;
+    } else idx = 2;
+    std::string dr = repeat_string_at(h, idx);
+    std::string rc = reverse_complement(dr);
+    if (dr < rc) { h.was_lowlexi = true; return dr; }
+    // flip the read and mirror the coordinates (palindromes take this branch too)
+    h.seq = reverse_complement(h.seq);
+    const uint32_t L = (uint32_t)h.seq.size();
+    std::vector<uint32_t> m(h.ss.size());
+    for (size_t i = 0; i < h.ss.size(); ++i) m[i] = L - 1 - h.ss[h.ss.size() - 1 - i];
+    h.ss.swap(m);
+    h.was_lowlexi = false;
+    return rc;
+}
+
+void add_read_holder(Results& r, HeldRead* h) {
+    std::string dr = dr_lowlexi(*h);
+    auto it = r.s2t.find(dr);
+    int tok;
+    if (it == r.s2t.end()) {
+        tok = ++r.next_free_token;                                        // first token is 2
+        r.s2t[dr] = tok;
+        r.t2s.push_back(dr);
+    } else tok = it->second;
+    h->token = tok;
+    r.reads[tok].push_back(h);
+}
+
+// ---- the step between the phases -------------------------------------------------------------------
+namespace {
+const size_t kClusterKmer = 11;                                            // CRASS_DEF_KMER_SIZE, crassDefines.h:66
+
+std::string low_lexi_kmer(const std::string& dr, size_t pos) {            // laurenize (SeqUtils.cpp:89-97)
+    std::string k = dr.substr(pos, kClusterKmer);
+    std::string rc = reverse_complement(k);
+    return k < rc ? k : rc;
+}
+
+bool contains_either_strand(const std::string& longer, const std::string& shorter) {   // includeSubstring
+    if (longer.find(shorter) != std::string::npos) return true;
+    return longer.find(reverse_complement(shorter)) != std::string::npos;
+}
+}  // namespace
+
+std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, int min_count,
+                                           std::vector<std::pair<int, int> >* groups_out) {
+    // (1) greedy k-mer clustering in token order.  A DR joins the first group that reaches min_count shared
+    //     11-mers while walking its k-mers left to right (the test is only made from a group's second hit on);
+    //     otherwise it founds a new group.  K-mers never seen before are then given to the chosen group.
+    std::unordered_map<std::string, int> kmer_group;
+    std::vector<std::vector<int> > members;                               // group id - 1 -> tokens
+    for (size_t t = 0; t < drs.size(); ++t) {
+        const std::string& dr = drs[t];
+        const long n_mers = (long)dr.size() - (long)kClusterKmer + 1;
+        std::vector<std::string> unseen;
+        std::vector<std::pair<int, int> > counts;                         // (group, shared so far)
+        int group = 0;
+        for (long i = 0; i < n_mers; ++i) {
+            std::string km = low_lexi_kmer(dr, (size_t)i);
+            auto it = kmer_group.find(km);
+            if (it == kmer_group.end()) { unseen.push_back(km); continue; }
+            if (group) continue;
+            auto c = std::find_if(counts.begin(), counts.end(), [&](const std::pair<int, int>& p) { return p.first == it->second; });
+            if (c == counts.end()) counts.push_back(std::make_pair(it->second, 1));
+            else if (++c->second >= min_count) group = it->second;
+        }
+        if (!group) { members.emplace_back(); group = (int)members.size(); }
+        members[group - 1].push_back((int)t + 2);
+        for (const std::string& km : unseen) kmer_group[km] = group;
+    }
+    // (2) per group: drop every variant that contains a shorter surviving variant (either strand), then emit
+    //     the survivors followed by their reverse complements.
+    std::vector<std::string> out;
+    for (size_t g = 0; g < members.size(); ++g) {
+        std::vector<std::string> v;
+        for (int tok : members[g]) {
+            v.push_back(drs[tok - 2]);
+            if (groups_out) groups_out->push_back(std::make_pair(tok, (int)g + 1));
+        }
+        std::stable_sort(v.begin(), v.end(), [](const std::string& a, const std::string& b) { return a.size() < b.size(); });
+        std::vector<bool> dead(v.size(), false);
+        for (size_t i = 0; i < v.size(); ++i) {
+            if (dead[i] || v[i].empty()) continue;
+            for (size_t j = i + 1; j < v.size(); ++j)
+                if (!dead[j] && !v[j].empty() && contains_either_strand(v[j], v[i])) dead[j] = true;
+        }
+        const size_t first = out.size();
+        for (size_t i = 0; i < v.size(); ++i) if (!dead[i] && !v[i].empty()) out.push_back(v[i]);
+        const size_t last = out.size();
+        for (size_t i = first; i < last; ++i) out.push_back(reverse_complement(out[i]));
+    }
+    return out;
+}
+
+// ---- "crass-dump v1" (tests/dumpfmt.py documents the format; the oracle emits the same text) ----------
+static uint32_t fnv1a32(const std::string& s) {
+    uint32_t h = 2166136261u;
+    for (unsigned char c : s) { h ^= c; h *= 16777619u; }
+    return h;
+}
+
+std::string dump_results(Results& r, int max_read_len) {
+    std::ostringstream os;
+    os << "# crass-dump v1\n";
+    os << "M\t" << max_read_len << "\t" << r.n_found_phase1 << "\t" << r.patterns_hash.size() << "\n";
+    for (auto& tg : r.token_groups) os << "G\t" << tg.first << "\t" << tg.second << "\n";
+    std::vector<std::string> p(r.non_redundant);
+    std::sort(p.begin(), p.end());
+    for (auto& s : p) os << "P\t" << s << "\n";
+    for (auto& kv : r.patterns_hash) os << "H\t" << kv.first << "\n";
+    for (auto& kv : r.reads) {
+        os << "T\t" << kv.first << "\t" << r.t2s[kv.first - 2] << "\t" << kv.second.size() << "\n";
+        for (HeldRead* h : kv.second) {
+            os << "R\t" << kv.first << "\t" << h->phase << "\t" << h->header << "\t" << (h->was_lowlexi ? 1 : 0) << "\t"
+               << h->repeat_len << "\t";
+            for (size_t i = 0; i < h->ss.size(); ++i) { if (i) os << ","; os << h->ss[i]; }
+            os << "\t" << h->seq << "\t" << h->comment << "\t" << (h->is_fasta ? 1 : 0) << "\t" << fnv1a32(h->qual) << "\n";
+        }
+    }
+    return os.str();
+}
+
+}  // namespace cbh

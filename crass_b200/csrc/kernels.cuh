@@ -1,0 +1,131 @@
+// kernels.cuh -- sm_100a kernels of the read-scanning hot path (device code only).
+//
+//   K1  k_dr_search_generic   searchCore for any parameter set / read length, one thread per read
+//   K2  k_ac_scan_generic     first-match multi-pattern scan, one thread per read
+//   K3  k_edit_distance       batched modified edit distance + similarity, one thread per pair
+//   KAT k_scan_right_one / k_extend_one : single-read entry points for the reference's unit-test vectors
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/crass_b200.h"
+#include "dr_core.cuh"
+
+namespace cbk {
+
+using cb::Params;
+
+struct HitSink {
+    crass_b200_hit* hits;
+    uint32_t hits_cap;
+    uint32_t* pool;
+    uint32_t pool_cap;
+    uint32_t* counters;      // [0] hits, [1] pool entries, [2] overflow flag, [3] exact-path reads
+};
+
+// global-memory byte accessor through the read-only path
+struct GmemSeq {
+    const uint8_t* p;
+    __device__ __forceinline__ uint8_t operator[](uint32_t i) const { return __ldg(p + i); }
+};
+
+__device__ __forceinline__ void emit_hit(const HitSink& sink, uint32_t read_index, const uint32_t* ss, uint32_t n_ss, uint32_t replen) {
+    const uint32_t slot = atomicAdd(&sink.counters[0], 1u);
+    const uint32_t off = atomicAdd(&sink.counters[1], n_ss);
+    if (slot < sink.hits_cap && off + n_ss <= sink.pool_cap) {
+        crass_b200_hit h;
+        h.read_index = read_index; h.n_ss = n_ss; h.ss_offset = off; h.repeat_len = replen;
+        sink.hits[slot] = h;
+        for (uint32_t i = 0; i < n_ss; ++i) sink.pool[off + i] = ss[i];
+    } else {
+        sink.counters[2] = 1u;
+    }
+}
+
+// ---- K1 generic --------------------------------------------------------------------------------------
+// LOCAL_SS > 0: the start/stop list lives in thread-local memory (short reads); otherwise in a slice of
+// ss_scratch (ss_cap entries per thread).
+template <int LOCAL_SS>
+__global__ void __launch_bounds__(128)
+k_dr_search_generic(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads, Params o,
+                    uint8_t* __restrict__ found, HitSink sink, uint32_t* __restrict__ ss_scratch, uint32_t ss_cap,
+                    int* __restrict__ error_flag) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nthreads = gridDim.x * blockDim.x;
+    uint32_t local_ss[LOCAL_SS > 0 ? LOCAL_SS : 1];
+    uint32_t* ss = LOCAL_SS > 0 ? local_ss : ss_scratch + (size_t)tid * ss_cap;
+    const uint32_t cap = LOCAL_SS > 0 ? (uint32_t)LOCAL_SS : ss_cap;
+    for (uint32_t r = tid; r < n_reads; r += nthreads) {
+        const uint64_t b = offsets[r];
+        const uint32_t L = (uint32_t)(offsets[r + 1] - b);
+        GmemSeq s{bases + b};
+        uint32_t n_ss = 0, replen = 0;
+        const int f = cb::search_core(s, L, o, ss, cap, n_ss, replen);
+        if (f < 0) *error_flag = f;
+        if (found) found[r] = (f == 1);
+        if (f == 1) emit_hit(sink, r, ss, n_ss, replen);
+    }
+}
+
+// ---- K2 generic --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_ac_scan_generic(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads,
+                  const uint32_t* __restrict__ table, uint32_t stride_log2, const uint8_t* __restrict__ symv_g,
+                  const uint8_t* __restrict__ skip, uint8_t* __restrict__ found, HitSink sink) {
+    __shared__ uint8_t symv[256];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) symv[i] = symv_g[i];
+    __syncthreads();
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nthreads = gridDim.x * blockDim.x;
+    for (uint32_t r = tid; r < n_reads; r += nthreads) {
+        if (skip && skip[r]) { if (found) found[r] = 0; continue; }
+        const uint64_t b = offsets[r];
+        const uint32_t L = (uint32_t)(offsets[r + 1] - b);
+        const uint8_t* s = bases + b;
+        uint32_t st = 0, end = 0, plen = 0;
+        for (uint32_t i = 0; i < L; ++i) {
+            const uint32_t sy = symv[__ldg(s + i)];
+            if (!sy) { st = 0; continue; }
+            const uint32_t e = __ldg(table + ((size_t)st << stride_log2) + (sy - 1));
+            st = e & 0xFFFFFFu;
+            if (e >> 24) { end = i + 1; plen = e >> 24; break; }
+        }
+        if (found) found[r] = plen != 0;
+        if (plen) {
+            // on_match (libcrispr.cpp:420-437): DR_end = textpos-1 clamped to L-1; start = DR_end-(len-1)
+            uint32_t dr_end = end - 1;
+            if (dr_end >= L) dr_end = L - 1;
+            uint32_t ss[2] = { dr_end - (plen - 1), dr_end };
+            emit_hit(sink, r, ss, 2, 0);
+        }
+    }
+}
+
+// ---- K3 ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_edit_distance(const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ a_off, const uint32_t* __restrict__ a_len,
+                const uint32_t* __restrict__ b_off, const uint32_t* __restrict__ b_len, uint32_t n_pairs,
+                int32_t* __restrict__ out_dist, float* __restrict__ out_sim) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    GmemSeq s{bytes};
+    out_dist[i] = cb::osa_distance(s, a_off[i], a_len[i], b_off[i], b_len[i]);
+    out_sim[i] = cb::similarity(s, a_off[i], a_len[i], b_off[i], b_len[i]);
+}
+
+// ---- KAT entry points --------------------------------------------------------------------------------
+__global__ void k_scan_right_one(const uint8_t* __restrict__ seq_and_pat, uint32_t L, uint32_t* ss, uint32_t* n_ss, uint32_t cap,
+                                 uint32_t w, uint32_t min_spacer, uint32_t scan_range) {
+    GmemSeq s{seq_and_pat};
+    uint32_t n = *n_ss;
+    cb::scan_right(s, L, ss, n, cap, L, w, min_spacer, scan_range);
+    *n_ss = n;
+}
+
+__global__ void k_extend_one(const uint8_t* __restrict__ seq, uint32_t L, uint32_t* ss, uint32_t n_ss, uint32_t window,
+                             uint32_t min_spacer, uint32_t* replen) {
+    GmemSeq s{seq};
+    *replen = cb::extend_pre_repeat(s, L, ss, n_ss, window, min_spacer);
+}
+
+}  // namespace cbk

@@ -1,0 +1,197 @@
+/* crass_b200.h -- C-ABI of the B200-native read-scanning hot path of crass.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no STL, no torch types.  The C++
+ * shim that a crass maintainer links instead of src/crass/libcrispr.cpp (see INTEGRATION.md,
+ * crass_b200/csrc/dropin/libcrispr_b200.cpp) is the only caller the reference needs; the Python
+ * package (crass_b200/) binds the same symbols through ctypes for tests and bench.py.
+ *
+ * Reference interfaces replaced (all /root/reference/src/crass/...):
+ *   searchFile()      libcrispr.h:74-80  / libcrispr.cpp:68-166    -> crass_b200_parse_file + crass_b200_dr_search
+ *   searchCore()      libcrispr.h:82-84  / libcrispr.cpp:265-395   -> crass_b200_dr_search[_dev]      (kernel K1)
+ *   scanRight()       libcrispr.h:94-97  / libcrispr.cpp:170-263   -> inside K1; crass_b200_scan_right (KAT entry)
+ *   extendPreRepeat() libcrispr.h:99-101 / libcrispr.cpp:520-772   -> inside K1; crass_b200_extend_pre_repeat (KAT entry)
+ *   qcFoundRepeats()  libcrispr.h:113-115/ libcrispr.cpp:869-1029  -> inside K1
+ *   PatternMatcher::levenstheinDistance / getStringSimilarity  PatternMatcher.cpp:111-204 -> crass_b200_edit_distance_batch (K3)
+ *   findSingletons()  libcrispr.h:86-92  / libcrispr.cpp:444-518   -> crass_b200_ac_build + crass_b200_ac_scan[_dev] (kernel K2)
+ *   acism_create/acism_scan  src/aho-corasick/acism.h:34,52-57     -> crass_b200_ac_build / crass_b200_ac_scan
+ *   addReadHolder() + ReadHolder::DRLowLexi  libcrispr.cpp:1119-1162, ReadHolder.cpp:513-610 -> crass_b200_results_* (host replay)
+ *   WorkHorse::createNonRedundantSet  WorkHorse.cpp:612-709,1404-1637 -> crass_b200_non_redundant_set
+ *   kseq_read()       kseq.cpp:171-225                              -> crass_b200_parse_file
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative crass_b200_status; crass_b200_last_error()
+ *     gives the message of the last failure on the calling thread.
+ *   - "_dev" entry points take DEVICE pointers and a CUDA stream (void* = cudaStream_t, NULL = default
+ *     stream) and only enqueue work; the others take HOST pointers and do the H2D / D2H copies.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     CRASS_B200_ENODEVICE.
+ *   - a read batch is byte-packed: bases[] holds the reads back to back exactly as kseq delivers them
+ *     (any byte 33..126, no case folding), offsets[n_reads+1] are uint64 byte offsets (offsets[0]==0).
+ */
+#ifndef CRASS_B200_H
+#define CRASS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRASS_B200_ABI_VERSION 1
+
+typedef enum {
+    CRASS_B200_OK = 0,
+    CRASS_B200_EINVAL = -1,      /* bad argument / unsupported parameter combination */
+    CRASS_B200_ENODEVICE = -2,   /* no CUDA device / driver */
+    CRASS_B200_ECUDA = -3,       /* a CUDA call failed (message has the CUDA error string) */
+    CRASS_B200_ENOMEM = -4,
+    CRASS_B200_EIO = -5,         /* cannot open / read input file */
+    CRASS_B200_EOVERFLOW = -6    /* caller-provided output capacity too small (needed size is reported) */
+} crass_b200_status;
+
+/* the searched fields of the reference's `options` struct (crassDefines.h:140-170) */
+typedef struct {
+    uint32_t low_dr;        /* lowDRsize           (23) */
+    uint32_t high_dr;       /* highDRsize          (47) */
+    uint32_t low_spacer;    /* lowSpacerSize       (26) */
+    uint32_t high_spacer;   /* highSpacerSize      (50) */
+    uint32_t window;        /* searchWindowLength  (8), CLI clamps it to 6..9 */
+    uint32_t min_repeats;   /* minNumRepeats       (2) */
+    uint32_t kmer_clust;    /* kmer_clust_size     (6) */
+    uint32_t scan_range;    /* hard-coded 24 in libcrispr.cpp:347 */
+} crass_b200_params;
+
+void crass_b200_default_params(crass_b200_params* p);
+
+/* one found read of phase 1 (searchCore returned true) or phase 2 (first automaton match) */
+typedef struct {
+    uint32_t read_index;    /* index into the batch */
+    uint32_t n_ss;          /* number of start/stop entries (2 per repeat) */
+    uint32_t ss_offset;     /* first entry in the start/stop pool */
+    uint32_t repeat_len;    /* RH_RepeatLength (0 for phase-2 hits, as in the reference) */
+} crass_b200_hit;
+
+typedef struct crass_b200_ctx crass_b200_ctx;     /* one per GPU: stream, staging, workspaces */
+typedef struct crass_b200_ac crass_b200_ac;       /* compiled multi-pattern automaton */
+typedef struct crass_b200_batch crass_b200_batch; /* parsed reads (host) */
+typedef struct crass_b200_results crass_b200_results; /* ReadMap / StringCheck / lookupTable mirror */
+
+const char* crass_b200_last_error(void);
+int crass_b200_abi_version(void);
+const char* crass_b200_build_info(void);
+int crass_b200_device_count(void);
+
+int crass_b200_ctx_create(int device, crass_b200_ctx** out);
+void crass_b200_ctx_destroy(crass_b200_ctx* ctx);
+int crass_b200_ctx_device(const crass_b200_ctx* ctx);
+/* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
+uint64_t crass_b200_ctx_launch_count(const crass_b200_ctx* ctx);
+/* device time of the most recent *_dev call's dominant kernel is measured by the caller with events */
+
+/* ---- phase 1: direct-repeat search (kernel K1) -------------------------------------------------
+ * Device-resident form.  Outputs (all device memory, caller-allocated):
+ *   d_found[n_reads]            1 if searchCore would return true for the read, else 0
+ *   d_hits[hits_cap], d_ss_pool[ss_cap]   hit records in arbitrary order + their start/stop entries
+ *   d_counters[4]               [0]=number of hits, [1]=number of pool entries used,
+ *                               [2]=1 if a capacity was exceeded (hits beyond capacity are dropped
+ *                                   but still counted, so the caller can re-run with larger buffers)
+ *                               [3]=number of reads that took the exact (candidate) path
+ * The counters are zeroed by the call (on the stream). */
+int crass_b200_dr_search_dev(crass_b200_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets,
+                             uint32_t n_reads, uint32_t max_read_len, const crass_b200_params* params,
+                             uint8_t* d_found, crass_b200_hit* d_hits, uint32_t hits_cap,
+                             uint32_t* d_ss_pool, uint32_t ss_cap, uint32_t* d_counters, void* stream);
+
+/* Host form: copies the batch in (pinned, chunked, double-buffered), runs K1, copies the hits out,
+ * sorted by read_index.  hits/ss_pool are malloc'd by the library (free with crass_b200_free).
+ * found may be NULL. */
+int crass_b200_dr_search(crass_b200_ctx* ctx, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
+                         const crass_b200_params* params, uint8_t* found,
+                         crass_b200_hit** hits, uint32_t* n_hits, uint32_t** ss_pool, uint32_t* n_ss_pool);
+
+/* ---- phase 2: singleton scan (kernel K2) ---------------------------------------------------------
+ * patterns: n_patterns byte strings back to back, pat_offsets[n_patterns+1]. */
+int crass_b200_ac_build(const uint8_t* pat_bytes, const uint32_t* pat_offsets, uint32_t n_patterns, crass_b200_ac** out);
+void crass_b200_ac_destroy(crass_b200_ac* ac);
+uint32_t crass_b200_ac_num_states(const crass_b200_ac* ac);
+uint32_t crass_b200_ac_num_symbols(const crass_b200_ac* ac);
+uint64_t crass_b200_ac_table_bytes(const crass_b200_ac* ac);
+
+/* d_skip[n_reads] may be NULL; reads with d_skip[i]!=0 are not scanned (the readsFound test of
+ * on_match, libcrispr.cpp:411, for reads already found in phase 1).  For every scanned read with a
+ * match a hit {read_index, n_ss=2, repeat_len=0} is appended and ss_pool gets (start, end) exactly as
+ * on_match computes them (libcrispr.cpp:420-437).  d_found[n_reads] (may be NULL) gets 1/0. */
+int crass_b200_ac_scan_dev(crass_b200_ctx* ctx, const crass_b200_ac* ac, const uint8_t* d_bases, const uint64_t* d_offsets,
+                           uint32_t n_reads, uint32_t max_read_len, const uint8_t* d_skip, uint8_t* d_found,
+                           crass_b200_hit* d_hits, uint32_t hits_cap, uint32_t* d_ss_pool, uint32_t ss_cap,
+                           uint32_t* d_counters, void* stream);
+
+int crass_b200_ac_scan(crass_b200_ctx* ctx, const crass_b200_ac* ac, const uint8_t* bases, const uint64_t* offsets,
+                       uint32_t n_reads, const uint8_t* skip, uint8_t* found,
+                       crass_b200_hit** hits, uint32_t* n_hits, uint32_t** ss_pool, uint32_t* n_ss_pool);
+
+/* ---- K3: batched modified edit distance (PatternMatcher::levenstheinDistance) --------------------
+ * pair i compares a = bytes[a_off[i] .. a_off[i]+a_len[i]) with b likewise; all HOST pointers.
+ * out_dist[n_pairs] int32, out_sim[n_pairs] float (getStringSimilarity, bit-exact). */
+int crass_b200_edit_distance_batch(crass_b200_ctx* ctx, const uint8_t* bytes, uint64_t n_bytes,
+                                   const uint32_t* a_off, const uint32_t* a_len, const uint32_t* b_off, const uint32_t* b_len,
+                                   uint32_t n_pairs, int32_t* out_dist, float* out_sim);
+
+/* ---- known-answer entry points for the two functions the reference's own unit tests pin ----------
+ * (src/test/test_libcrispr.cpp).  They run the SAME device code K1 uses, one read per call. */
+int crass_b200_scan_right(crass_b200_ctx* ctx, const uint8_t* seq, uint32_t len, uint32_t* ss, uint32_t* n_ss, uint32_t ss_cap,
+                          const uint8_t* pattern, uint32_t pattern_len, uint32_t min_spacer, uint32_t scan_range);
+int crass_b200_extend_pre_repeat(crass_b200_ctx* ctx, const uint8_t* seq, uint32_t len, uint32_t* ss, uint32_t n_ss,
+                                 uint32_t window, uint32_t min_spacer, uint32_t* repeat_len);
+
+/* ---- feed path: kseq-compatible FASTA/FASTQ(.gz) parser ------------------------------------------ */
+int crass_b200_parse_file(const char* path, crass_b200_batch** out);      /* "-" = stdin */
+int crass_b200_batch_from_memory(const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
+                                 const char* const* names /* may be NULL: r%010u */, crass_b200_batch** out);
+void crass_b200_batch_destroy(crass_b200_batch* b);
+uint32_t crass_b200_batch_num_reads(const crass_b200_batch* b);
+uint32_t crass_b200_batch_max_read_len(const crass_b200_batch* b);
+int crass_b200_batch_parse_status(const crass_b200_batch* b);             /* last kseq_read return: -1 EOF, -2 truncated */
+const uint8_t* crass_b200_batch_bases(const crass_b200_batch* b);         /* pinned host memory when a device exists */
+const uint64_t* crass_b200_batch_offsets(const crass_b200_batch* b);
+/* record fields exactly as searchFile sees them (stale comment/qual buffers of kseq included);
+ * has_comment / has_qual mirror (seq->comment.s != NULL) / (seq->qual.s != NULL) */
+const char* crass_b200_batch_name(const crass_b200_batch* b, uint32_t i);
+const char* crass_b200_batch_comment(const crass_b200_batch* b, uint32_t i, int* has_comment);
+const char* crass_b200_batch_qual(const crass_b200_batch* b, uint32_t i, int* has_qual);
+
+/* ---- host replay: the containers the reference fills --------------------------------------------- */
+int crass_b200_results_create(crass_b200_results** out);
+void crass_b200_results_destroy(crass_b200_results* r);
+/* replays phase-1 hits in read order: addReadHolder (DRLowLexi, token), patternsHash, readsFound */
+int crass_b200_results_add_phase1(crass_b200_results* r, const crass_b200_batch* b,
+                                  const crass_b200_hit* hits, uint32_t n_hits, const uint32_t* ss_pool);
+/* replays phase-2 hits in read order: on_match (header not in readsFound -> addReadHolder) */
+int crass_b200_results_add_phase2(crass_b200_results* r, const crass_b200_batch* b,
+                                  const crass_b200_hit* hits, uint32_t n_hits, const uint32_t* ss_pool);
+uint32_t crass_b200_results_num_tokens(const crass_b200_results* r);
+uint32_t crass_b200_results_num_reads(const crass_b200_results* r);
+/* the distinct low-lexi DR strings in token order (token = index + 2), '\n'-separated; malloc'd */
+char* crass_b200_results_dr_list(const crass_b200_results* r);
+/* merges DR strings discovered by other shards in front of / behind this one (multi-GPU): the list is
+ * the concatenation over ranks in rank order; tokens are renumbered by first appearance */
+int crass_b200_results_adopt_tokens(crass_b200_results* r, const char* dr_list_all_ranks);
+/* WorkHorse::createNonRedundantSet on the current token set; patterns '\n'-separated; malloc'd */
+char* crass_b200_results_non_redundant(crass_b200_results* r, uint32_t kmer_clust, uint32_t* n_patterns);
+/* "crass-dump v1" text of the whole state (same format the oracle emits); malloc'd */
+char* crass_b200_results_dump(crass_b200_results* r, int max_read_len);
+
+/* clustering step alone on an ordered DR list ('\n'-separated, token order); "G"/"P" lines; malloc'd */
+char* crass_b200_non_redundant_set(const char* dr_list, uint32_t kmer_clust);
+
+/* ---- whole path, one call: searchFile* -> createNonRedundantSet -> findSingletons* --------------- */
+int crass_b200_run_files(crass_b200_ctx* ctx, const char* const* paths, uint32_t n_paths,
+                         const crass_b200_params* params, int phases, crass_b200_results** out, int* max_read_len);
+
+void crass_b200_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRASS_B200_H */

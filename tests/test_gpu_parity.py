@@ -1,0 +1,233 @@
+"""Parity of the CUDA path against the oracle, through the C-ABI (libcrass_b200.so) -- needs a B200.
+
+Bit-exact for everything: hit/no-hit per read, start/stop lists, repeat length, match offsets, edit
+distances, float similarities (compared as bit patterns), token numbering and the whole ReadMap dump.
+"""
+import gzip
+import json
+import os
+import random
+import struct
+
+import numpy as np
+import pytest
+
+import checkers
+import fuzzgen
+import crass_b200 as cb
+from crass_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+BUNDLED = ["Ill100.fx.gz", "CN_gDC.fa.gz", "Ill.nr.miss.fa.gz", "front_offset_bug.fa.gz", "poor_dr_ext.fa.gz"]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = cb.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def P():
+    return checkers.port()
+
+
+def load(name):
+    return json.load(open(os.path.join(G, name)))
+
+
+def hits_by_read(hits, pool):
+    return {int(h["read_index"]): (list(map(int, pool[h["ss_offset"]:h["ss_offset"] + h["n_ss"]])), int(h["repeat_len"])) for h in hits}
+
+
+def check_batch_against_oracle(ctx, P, reads, params=None):
+    """dr_search over `reads` must equal the oracle's searchCore read by read."""
+    bases, offs = cb.pack_reads(reads)
+    prm = cb.Params(**params) if params else cb.Params()
+    hits, pool, found = ctx.dr_search(bases, offs, prm)
+    got = hits_by_read(hits, pool)
+    assert list(hits["read_index"]) == sorted(hits["read_index"])
+    n_hit = 0
+    for i, s in enumerate(reads):
+        f, ss, rl = P.search_core(s, params)
+        assert int(found[i]) == (1 if f == 1 else 0), (i, s, params)
+        if f == 1:
+            n_hit += 1
+            assert got[i] == (ss, rl), (i, s, params)
+        else:
+            assert i not in got
+    assert len(got) == n_hit
+    return n_hit
+
+
+# ---- the reference's own known-answer tests (src/test/test_libcrispr.cpp) through the device code ----
+def test_catch_scan_right(ctx):
+    for v in load("catch_vectors.json")["scan_right"]:
+        assert ctx.scan_right(v["seq"].encode(), v["ss"], v["pattern"].encode(), v["min_spacer"], v["scan_range"]) == v["expect"], v["cite"]
+
+
+def test_catch_extend_pre_repeat(ctx):
+    for v in load("catch_vectors.json")["extend_pre_repeat"]:
+        assert ctx.extend_pre_repeat(v["seq"].encode(), v["ss"], v["window"], v["min_spacer"]) == (v["expect_len"], v["expect"]), v["cite"]
+
+
+# ---- golden vectors produced by the reference ---------------------------------------------------------
+def test_search_core_golden_vectors(ctx):
+    vec = load("search_core_vectors.json")
+    groups = {}
+    for v in vec:
+        groups.setdefault(json.dumps(v["params"], sort_keys=True), []).append(v)
+    for key, vs in groups.items():
+        params = json.loads(key)
+        reads = [v["seq"].encode("latin-1") for v in vs]
+        bases, offs = cb.pack_reads(reads)
+        hits, pool, found = ctx.dr_search(bases, offs, cb.Params(**params) if params else cb.Params())
+        got = hits_by_read(hits, pool)
+        for i, v in enumerate(vs):
+            assert int(found[i]) == (1 if v["found"] == 1 else 0)
+            if v["found"] == 1:
+                assert got[i] == (v["ss"], v["replen"])
+
+
+def test_edit_distance_golden_vectors(ctx):
+    vec = load("edit_distance_vectors.json")
+    dist, sim = ctx.edit_distance_batch([(a.encode(), b.encode()) for a, b, _, _ in vec])
+    for i, (_, _, d, simhex) in enumerate(vec):
+        assert int(dist[i]) == d
+        assert struct.pack(">f", float(sim[i])).hex() == simhex
+
+
+def test_ac_golden_vectors(ctx):
+    for case in load("ac_vectors.json"):
+        ac = cb.Automaton([p.encode() for p in case["patterns"]])
+        texts = [t.encode() for t, _ in case["texts"]]
+        bases, offs = cb.pack_reads(texts)
+        hits, pool, found = ctx.ac_scan(ac, bases, offs)
+        got = hits_by_read(hits, pool)
+        for i, (t, expect) in enumerate(case["texts"]):
+            if expect is None:
+                assert i not in got and found[i] == 0
+            else:
+                end, plen = expect
+                dr_end = min(end - 1, len(t) - 1)
+                assert got[i] == ([dr_end - (plen - 1), dr_end], 0)
+                assert found[i] == 1
+
+
+@pytest.mark.parametrize("name", BUNDLED)
+def test_bundled_files_whole_path(ctx, name):
+    """BASELINE.json configs[0]: searchFile -> createNonRedundantSet -> findSingletons on the reference's bundled
+    read sets; the dump (tokens, DRs, read order, orientation, start/stops, patterns) must match the reference's."""
+    path = os.path.join(checkers.REF_DATA, name)
+    if not os.path.exists(path):
+        pytest.skip("bundled read sets not staged")
+    want = gzip.open(os.path.join(G, "bundled", name + ".dump.gz")).read().decode("latin-1")
+    res, max_len = ctx.run_files([path])
+    assert res.dump(max_len) == want
+
+
+def test_bundled_files_other_options(ctx, P):
+    path = os.path.join(checkers.REF_DATA, "Ill100.fx.gz")
+    if not os.path.exists(path):
+        pytest.skip("bundled read sets not staged")
+    for prm in (dict(window=6), dict(min_repeats=3), dict(window=9, low_dr=20), dict(window=7, low_spacer=20, high_spacer=60)):
+        want, _ = P.run_files([path], prm)
+        res, max_len = ctx.run_files([path], cb.Params(**prm))
+        assert res.dump(max_len) == want, prm
+
+
+# ---- seeded fuzz against the oracle -----------------------------------------------------------------------
+def test_fuzz_default_params(ctx, P):
+    rng = random.Random(101)
+    reads = [fuzzgen.fuzz_read(rng) for _ in range(20000)]
+    assert check_batch_against_oracle(ctx, P, reads) > 1500
+
+
+def test_fuzz_other_params(ctx, P):
+    rng = random.Random(102)
+    for _ in range(12):
+        prm = dict(window=rng.choice([6, 7, 8, 9]), min_repeats=rng.choice([2, 3, 4]), low_dr=rng.choice([23, 23, 20, 17, 30]),
+                   high_dr=rng.choice([47, 40, 60]), low_spacer=rng.choice([26, 20, 30, 10]), high_spacer=rng.choice([50, 60, 40]))
+        reads = [fuzzgen.fuzz_read(rng) for _ in range(1500)]
+        check_batch_against_oracle(ctx, P, reads, prm)
+
+
+def test_edge_batches(ctx, P):
+    assert check_batch_against_oracle(ctx, P, []) == 0                        # empty batch
+    assert check_batch_against_oracle(ctx, P, [b"", b"A", b"ACGT" * 14, b"", b"N" * 200]) == 0   # empty / short / below 58 bp
+    rng = random.Random(103)
+    ragged = [fuzzgen.planted_read(rng, rng.choice([58, 59, 60, 61, 100, 333, 1021])) for _ in range(300)]
+    check_batch_against_oracle(ctx, P, ragged)
+
+
+def test_long_reads(ctx, P):
+    rng = random.Random(104)
+    reads = []
+    for _ in range(200):
+        L = rng.randint(1000, 10000)
+        reads.append(fuzzgen.planted_read(rng, L, sub_rate=rng.choice([0, 0.005, 0.02])) if rng.random() < 0.6 else fuzzgen.rand_seq(rng, L))
+    assert check_batch_against_oracle(ctx, P, reads) > 40
+
+
+def test_synthetic_config2_prefix(ctx, P):
+    """A 300k-read prefix of the BASELINE config-2 recipe, compared read by read with the oracle."""
+    genome, drs, _ = synth.make_genome(20242)
+    n = 300_000
+    bases, offs = synth.sample_fixed(genome, n, 150, 21242)
+    hits, pool, found = ctx.dr_search(bases, offs)
+    want = np.zeros(n, dtype=np.uint8)
+    nf = P.lib.orc_phase1_batch(bases.ctypes.data, offs.ctypes.data, n, checkers.params_array(), want.ctypes.data)
+    assert nf > 500
+    assert np.array_equal(found, want)
+    got = hits_by_read(hits, pool)
+    for i in np.flatnonzero(want):
+        s = bases[int(offs[i]):int(offs[i + 1])].tobytes()
+        f, ss, rl = P.search_core(s)
+        assert got[int(i)] == (ss, rl)
+
+
+def test_singleton_scan_fuzz(ctx, P):
+    rng = random.Random(105)
+    for n_pat in (1, 7, 100, 1500):
+        pats = fuzzgen.dr_like_patterns(rng, n_pat)
+        if n_pat == 7:
+            pats += [p[2:-3] for p in pats] + [fuzzgen.mutate(rng, p, 0.1, b"ACGTN") for p in pats]
+        texts = []
+        for _ in range(3000):
+            t = fuzzgen.rand_seq(rng, rng.choice([0, 10, 100, 150, 150, 400]), b"ACGTN" if rng.random() < 0.2 else b"ACGT")
+            if rng.random() < 0.5 and len(t) > 60:
+                p = rng.choice(pats)
+                pos = rng.randint(0, len(t) - 1)
+                t = (t[:pos] + p + t[pos:])[:len(t)]
+            texts.append(t)
+        skip = np.array([rng.random() < 0.1 for _ in texts], dtype=np.uint8)
+        bases, offs = cb.pack_reads(texts)
+        hits, pool, found = ctx.ac_scan(cb.Automaton(pats), bases, offs, skip)
+        got = hits_by_read(hits, pool)
+        h = P.ac_create(pats)
+        for i, t in enumerate(texts):
+            m = None if skip[i] else P.ac_first_match(h, t)
+            if m is None:
+                assert i not in got and found[i] == 0
+            else:
+                dr_end = min(m[0] - 1, len(t) - 1)
+                assert got[i] == ([dr_end - (m[1] - 1), dr_end], 0)
+        P.ac_destroy(h)
+
+
+def test_whole_path_synthetic_against_oracle(ctx, P, tmp_path):
+    """Both phases + clustering on a synthetic FASTA file: the product's dump must equal the oracle's."""
+    genome, drs, _ = synth.make_genome(777, n_dr_types=12, array_fraction=0.05)
+    bases, offs = synth.sample_fixed(genome, 60000, 150, 778)
+    path = str(tmp_path / "synth.fa")
+    with open(path, "wb") as fh:
+        for i in range(60000):
+            fh.write(b">r%010d\n" % i + bases[int(offs[i]):int(offs[i + 1])].tobytes() + b"\n")
+    want, _ = P.run_files([path])
+    res, max_len = ctx.run_files([path])
+    got = res.dump(max_len)
+    assert got == want
+    assert sum(1 for l in got.split("\n") if l.startswith("R\t")) > 1000

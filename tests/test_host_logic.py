@@ -1,0 +1,210 @@
+"""Host-side logic of the product library, no GPU needed: feed path (kseq-compatible parser), replay
+into the ReadMap/StringCheck mirror, the step between the phases, automaton construction, and the C-ABI
+surface.  Device results are stood in for by the oracle here (test_gpu_parity.py uses the real kernels)."""
+import ctypes as C
+import gzip
+import json
+import os
+import random
+import re
+import tempfile
+
+import numpy as np
+import pytest
+
+import checkers
+import fuzzgen
+import crass_b200 as cb
+from crass_b200 import api
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+BUNDLED = ["Ill100.fx.gz", "CN_gDC.fa.gz", "Ill.nr.miss.fa.gz", "front_offset_bug.fa.gz", "poor_dr_ext.fa.gz"]
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(checkers.ROOT, "include", "crass_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(crass_b200_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) > 40
+    L = C.CDLL(api.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert cb.lib().crass_b200_abi_version() == 1
+
+
+def test_no_device_means_loud_failure():
+    if cb.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(cb.CrassB200Error) as e:
+        cb.Context(0)
+    assert e.value.status == api.ENODEVICE
+
+
+def test_default_params_match_reference_defaults():
+    p = cb.Params()
+    assert p.as_dict() == dict(low_dr=23, high_dr=47, low_spacer=26, high_spacer=50, window=8, min_repeats=2, kmer_clust=6, scan_range=24)
+
+
+def test_parser_kseq_vectors():
+    with tempfile.TemporaryDirectory() as d:
+        for name, v in json.load(open(os.path.join(G, "kseq_vectors.json"))).items():
+            for gz in (False, True):
+                p = os.path.join(d, name + (".gz" if gz else ".fx"))
+                with (gzip.open if gz else open)(p, "wb") as fh:
+                    fh.write(v["content"].encode())
+                assert cb.Batch.from_file(p).record_stream().decode("latin-1") == v["records"], name
+
+
+@pytest.mark.parametrize("name", BUNDLED)
+def test_parser_bundled_files(name):
+    path = os.path.join(checkers.REF_DATA, name)
+    if not os.path.exists(path):
+        pytest.skip("bundled read sets not staged")
+    b = cb.Batch.from_file(path)
+    assert b.record_stream() == checkers.port().kseq_dump(path)
+    lens = np.diff(b.offsets.astype(np.int64))
+    assert int(lens.max()) == b.max_read_len
+
+
+def test_parser_fuzz_against_oracle():
+    rng = random.Random(3)
+    P = checkers.port()
+    with tempfile.TemporaryDirectory() as d:
+        for it in range(60):
+            parts = []
+            for _ in range(rng.randint(0, 12)):
+                seq = fuzzgen.rand_seq(rng, rng.randint(1, 120), b"ACGTNacgt")
+                name = "r%d" % rng.randint(0, 999)
+                cmt = rng.choice(["", " c", "\tc d", " ", "  x"])
+                wrap = rng.choice([0, 0, 30, 60])
+                body = seq.decode() if not wrap else "\n".join(seq.decode()[i:i + wrap] for i in range(0, len(seq), wrap))
+                if rng.random() < 0.5:
+                    parts.append(">%s%s\n%s\n" % (name, cmt, body))
+                else:
+                    q = "".join(rng.choice("!#5I@>+") for _ in seq)
+                    if rng.random() < 0.05:
+                        q = q[:-1]
+                    parts.append("@%s%s\n%s\n+%s\n%s\n" % (name, cmt, body, rng.choice(["", name]), q))
+            text = "".join(parts)
+            if rng.random() < 0.2:
+                text = text.replace("\n", "\r\n")
+            if rng.random() < 0.2:
+                text = text.rstrip("\n")
+            p = os.path.join(d, "f%d.fx" % it)
+            with open(p, "wb") as fh:
+                fh.write(text.encode())
+            assert cb.Batch.from_file(p).record_stream() == P.kseq_dump(p), text
+
+
+def test_parse_missing_file_is_an_error():
+    with pytest.raises(cb.CrassB200Error):
+        cb.Batch.from_file("/nonexistent/file.fa")
+
+
+def test_non_redundant_set_fuzz_against_oracle():
+    rng = random.Random(17)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    P = checkers.port()
+    for _ in range(150):
+        base = [fuzzgen.rand_seq(rng, rng.randint(23, 47)) for _k in range(rng.randint(1, 12))]
+        drs = []
+        for b in base:
+            for _k in range(rng.randint(1, 8)):
+                v = fuzzgen.mutate(rng, b, rng.choice([0, 0.02, 0.05]), b"ACGT")
+                a, e = rng.randint(0, 4), rng.randint(0, 4)
+                v = v[a:len(v) - e] if rng.random() < 0.5 else fuzzgen.rand_seq(rng, a) + v + fuzzgen.rand_seq(rng, e)
+                drs.append(min(v, v.translate(comp)[::-1]))
+        uniq = list(dict.fromkeys(drs))
+        rng.shuffle(uniq)
+        a, b = P.non_redundant(uniq), cb.non_redundant_set(uniq)
+        assert [l for l in a.split("\n") if l.startswith("G")] == [l for l in b.split("\n") if l.startswith("G")]
+        assert sorted(l for l in a.split("\n") if l.startswith("P")) == sorted(l for l in b.split("\n") if l.startswith("P"))
+
+
+def oracle_hits_phase1(batch, params=None):
+    """Stand-in for kernel K1 on a box without a GPU: the oracle decides, the product replays."""
+    P = checkers.port()
+    offs, bases = batch.offsets, batch.bases
+    hits, pool = [], []
+    for i in range(len(batch)):
+        s = bases[int(offs[i]):int(offs[i + 1])].tobytes()
+        f, ss, rl = P.search_core(s, params)
+        if f == 1:
+            hits.append((i, len(ss), len(pool), rl))
+            pool += ss
+    return np.array(hits, dtype=api.HIT_DTYPE), np.array(pool + [0], dtype=np.uint32)
+
+
+def oracle_hits_phase2(batch, patterns, skip):
+    P = checkers.port()
+    h = P.ac_create(patterns)
+    offs, bases = batch.offsets, batch.bases
+    hits, pool = [], []
+    for i in range(len(batch)):
+        if skip[i]:
+            continue
+        s = bases[int(offs[i]):int(offs[i + 1])].tobytes()
+        m = P.ac_first_match(h, s)
+        if m:
+            end, plen = m
+            dr_end = min(end - 1, len(s) - 1)
+            hits.append((i, 2, len(pool), 0))
+            pool += [dr_end - (plen - 1), dr_end]
+    P.ac_destroy(h)
+    return np.array(hits, dtype=api.HIT_DTYPE), np.array(pool + [0], dtype=np.uint32)
+
+
+@pytest.mark.parametrize("name", BUNDLED)
+def test_replay_reproduces_reference_dump(name):
+    """Parser + replay (addReadHolder/DRLowLexi/tokens) + createNonRedundantSet + on_match bookkeeping of the
+    PRODUCT, fed with oracle-decided hits, must reproduce the reference's dump byte for byte."""
+    path = os.path.join(checkers.REF_DATA, name)
+    if not os.path.exists(path):
+        pytest.skip("bundled read sets not staged")
+    want = gzip.open(os.path.join(G, "bundled", name + ".dump.gz")).read().decode("latin-1")
+    b = cb.Batch.from_file(path)
+    res = cb.Results()
+    hits, pool = oracle_hits_phase1(b)
+    res.add_phase1(b, hits, pool)
+    pats = res.non_redundant(6)
+    skip = np.zeros(len(b), dtype=np.uint8)
+    skip[hits["read_index"]] = 1
+    if pats:
+        h2, p2 = oracle_hits_phase2(b, pats, skip)
+        res.add_phase2(b, h2, p2)
+    assert res.dump(b.max_read_len) == want
+
+
+def test_adopt_tokens_renumbers_like_a_sequential_run():
+    """Multi-GPU merge: shard-local token numbers -> global first-appearance order."""
+    path = os.path.join(checkers.REF_DATA, "Ill100.fx.gz")
+    if not os.path.exists(path):
+        pytest.skip("bundled read sets not staged")
+    b = cb.Batch.from_file(path)
+    hits, pool = oracle_hits_phase1(b)
+    whole = cb.Results()
+    whole.add_phase1(b, hits, pool)
+    n = len(b)
+    cut = n // 2
+    offs, bases = b.offsets, b.bases
+    names = [b.name(i) for i in range(n)]
+    shards = []
+    for lo, hi in ((0, cut), (cut, n)):
+        sb = cb.Batch.from_arrays(bases[int(offs[lo]):int(offs[hi])], offs[lo:hi + 1] - offs[lo], names[lo:hi])
+        sh = hits[(hits["read_index"] >= lo) & (hits["read_index"] < hi)].copy()
+        sh["read_index"] -= lo
+        r = cb.Results()
+        r.add_phase1(sb, sh, pool)
+        shards.append(r)
+    gathered = shards[0].dr_list() + shards[1].dr_list()
+    for r in shards:
+        r.adopt_tokens(gathered)
+    assert shards[0].dr_list() == whole.dr_list() == shards[1].dr_list()
+    assert shards[0].non_redundant() == whole.non_redundant()
+
+
+def test_automaton_shape():
+    ac = cb.Automaton([b"ACGTACGTACGTACGTACGTACG", b"ACGTACGTACGTACGTACGTACGTT", b"TTTTTTTTTTTTTTTTTTTTTTTTT"])
+    assert ac.num_states == 1 + 25 + 25
+    assert ac.table_bytes == ac.num_states * 4 * 4
+    with pytest.raises(cb.CrassB200Error):
+        cb.Automaton([])

@@ -70,7 +70,8 @@ def test_kseq_vectors(P):
     with tempfile.TemporaryDirectory() as d:
         for name, v in load("kseq_vectors.json").items():
             p = os.path.join(d, name + ".fx")
-            open(p, "wb").write(v["content"].encode())
+            with open(p, "wb") as fh:
+                fh.write(v["content"].encode())
             assert P.kseq_dump(p).decode("latin-1") == v["records"], name
             with gzip.open(p + ".gz", "wb") as g:
                 g.write(v["content"].encode())
