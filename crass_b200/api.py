@@ -69,6 +69,11 @@ def lib():
         "crass_b200_ctx_launch_count": (C.c_uint64, [vp]),
         "crass_b200_dr_search_dev": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, C.POINTER(Params), vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp]),
         "crass_b200_dr_search": (C.c_int, [vp, vp, vp, C.c_uint32, C.POINTER(Params), vp, C.POINTER(vp), u32p, C.POINTER(vp), u32p]),
+        "crass_b200_batch_upload": (C.c_int, [vp, vp, vp, C.c_uint32]),
+        "crass_b200_dr_search_resident": (C.c_int, [vp, C.POINTER(Params), vp, C.POINTER(vp), u32p, C.POINTER(vp), u32p]),
+        "crass_b200_ac_scan_resident": (C.c_int, [vp, vp, C.c_int, vp, C.POINTER(vp), u32p, C.POINTER(vp), u32p]),
+        "crass_b200_dr_list_from_hits": (vp, [vp, vp, C.c_uint32, vp, C.c_uint32, vp]),
+        "crass_b200_merge_dr_lists": (vp, [cp]),
         "crass_b200_ac_build": (C.c_int, [vp, vp, C.c_uint32, C.POINTER(vp)]),
         "crass_b200_ac_destroy": (None, [vp]),
         "crass_b200_ac_num_states": (C.c_uint32, [vp]),
@@ -292,6 +297,30 @@ class Results:
         return _take_str(lib().crass_b200_results_dump(self.h, max_read_len)).decode("latin-1")
 
 
+def _addr(x):
+    """host address of a numpy array or a (pinned) CPU torch tensor"""
+    return x.ctypes.data if isinstance(x, np.ndarray) else x.data_ptr()
+
+
+def dr_list_from_hits(bases, offsets, hits, pool):
+    n = len(offsets) - 1
+    s = _take_str(lib().crass_b200_dr_list_from_hits(C.c_void_p(_addr(bases)), C.c_void_p(_addr(offsets)), n, _np_ptr(hits), len(hits), _np_ptr(pool)))
+    if s is None:
+        _check(-1)
+    return [x for x in s.split(b"\n") if x]
+
+
+def merge_dr_lists(drs):
+    s = _take_str(lib().crass_b200_merge_dr_lists(b"".join(d + b"\n" for d in drs)))
+    return [x for x in s.split(b"\n") if x]
+
+
+def non_redundant_list(drs, kmer_clust=6):
+    """createNonRedundantSet on an ordered DR list -> pattern list (survivors + reverse complements)."""
+    out = non_redundant_set(drs, kmer_clust)
+    return [l[2:].encode() for l in out.split("\n") if l.startswith("P\t")]
+
+
 def non_redundant_set(drs, kmer_clust=6):
     s = _take_str(lib().crass_b200_non_redundant_set(b"".join(d + b"\n" for d in drs), kmer_clust))
     return s.decode()
@@ -339,6 +368,21 @@ class Context:
         n = len(offsets) - 1
         return self._collect(lambda f, hp, nh, pp, npl: lib().crass_b200_dr_search(
             self.h, _np_ptr(bases), _np_ptr(offsets), n, C.byref(params), f, hp, nh, pp, npl), n, want_found)
+
+    def upload(self, bases, offsets):
+        """H2D of a host batch into the context (pinned sources copy at full PCIe rate)."""
+        n = len(offsets) - 1
+        _check(lib().crass_b200_batch_upload(self.h, C.c_void_p(_addr(bases)), C.c_void_p(_addr(offsets)), n))
+        self._resident_n = n
+
+    def dr_search_resident(self, params=None, want_found=False):
+        params = params or Params()
+        return self._collect(lambda f, hp, nh, pp, npl: lib().crass_b200_dr_search_resident(self.h, C.byref(params), f, hp, nh, pp, npl),
+                             self._resident_n, want_found)
+
+    def ac_scan_resident(self, ac, skip_found=True, want_found=False):
+        return self._collect(lambda f, hp, nh, pp, npl: lib().crass_b200_ac_scan_resident(self.h, ac.h, 1 if skip_found else 0, f, hp, nh, pp, npl),
+                             self._resident_n, want_found)
 
     def ac_scan(self, ac, bases, offsets, skip=None, want_found=True):
         bases = np.ascontiguousarray(bases, dtype=np.uint8)

@@ -87,6 +87,11 @@ struct crass_b200_ctx {
     uint64_t launches = 0;
     DevBuf d_bases, d_offsets, d_found, d_skip, d_hits, d_pool, d_counters, d_scratch, d_error, d_misc, d_symv;
     uint32_t* h_counters = nullptr;   // pinned, 8 words
+    // resident batch (crass_b200_batch_upload)
+    uint32_t res_n_reads = 0, res_max_len = 0;
+    uint64_t res_n_bases = 0;
+    bool res_valid = false, res_found_valid = false;
+    DevBuf d_found_p1;
 };
 
 namespace cbh {
@@ -149,7 +154,7 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->d_bases, &c->d_offsets, &c->d_found, &c->d_skip, &c->d_hits, &c->d_pool, &c->d_counters,
-                      &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv};
+                      &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv, &c->d_found_p1};
     for (DevBuf* b : bufs) b->release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     cudaStreamDestroy(c->stream);
@@ -234,6 +239,7 @@ int run_with_outputs(crass_b200_ctx* c, uint32_t n_reads, uint64_t n_bases, uint
 }
 
 int upload_batch(crass_b200_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, uint64_t n_bases) {
+    c->res_valid = false; c->res_found_valid = false;
     if (int r = c->d_bases.reserve(n_bases + 64)) return r;
     if (int r = c->d_offsets.reserve(((size_t)n_reads + 1) * sizeof(uint64_t))) return r;
     CUDA_TRY(cudaMemcpyAsync(c->d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, c->stream));
@@ -268,6 +274,37 @@ int crass_b200_dr_search(crass_b200_ctx* c, const uint8_t* bases, const uint64_t
                                         c->d_pool.as<uint32_t>(), pool_cap, c->d_counters.as<uint32_t>(), c->stream);
     };
     return run_with_outputs(c, n_reads, n_bases, found, launch, hits, n_hits, ss_pool, n_ss_pool);
+}
+
+int crass_b200_batch_upload(crass_b200_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads) {
+    if (!c || !offsets || (n_reads && !bases)) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n_reads && offsets[0] != 0) return cbh::fail(CRASS_B200_EINVAL, "offsets[0] must be 0");
+    const uint64_t n_bases = n_reads ? offsets[n_reads] : 0;
+    if (int r = upload_batch(c, bases, offsets, n_reads, n_bases)) return r;
+    c->res_n_reads = n_reads; c->res_n_bases = n_bases; c->res_max_len = max_len_of(offsets, n_reads);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->res_valid = true;
+    return 0;
+}
+
+int crass_b200_dr_search_resident(crass_b200_ctx* c, const crass_b200_params* params, uint8_t* found, crass_b200_hit** hits,
+                                  uint32_t* n_hits, uint32_t** ss_pool, uint32_t* n_ss_pool) {
+    if (!c || !c->res_valid) return cbh::fail(CRASS_B200_EINVAL, "no resident batch: call crass_b200_batch_upload first");
+    if (!hits || !n_hits || !ss_pool || !n_ss_pool) return cbh::fail(CRASS_B200_EINVAL, "output pointer is NULL");
+    if (int r = validate_params(params)) return r;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const uint32_t n_reads = c->res_n_reads;
+    auto launch = [&](uint32_t hits_cap, uint32_t pool_cap) {
+        return crass_b200_dr_search_dev(c, c->d_bases.as<uint8_t>(), c->d_offsets.as<uint64_t>(), n_reads, c->res_max_len, params,
+                                        c->d_found.as<uint8_t>(), c->d_hits.as<crass_b200_hit>(), hits_cap,
+                                        c->d_pool.as<uint32_t>(), pool_cap, c->d_counters.as<uint32_t>(), c->stream);
+    };
+    if (int r = run_with_outputs(c, n_reads, c->res_n_bases, found, launch, hits, n_hits, ss_pool, n_ss_pool)) return r;
+    if (int r = c->d_found_p1.reserve((size_t)n_reads + 16)) return r;
+    if (n_reads) CUDA_TRY(cudaMemcpyAsync(c->d_found_p1.p, c->d_found.p, n_reads, cudaMemcpyDeviceToDevice, c->stream));
+    c->res_found_valid = true;
+    return 0;
 }
 
 // ---- K2 ------------------------------------------------------------------------------------------------
@@ -353,6 +390,23 @@ int crass_b200_ac_scan(crass_b200_ctx* c, const crass_b200_ac* ac, const uint8_t
                                       c->d_counters.as<uint32_t>(), c->stream);
     };
     return run_with_outputs(c, n_reads, n_bases, found, launch, hits, n_hits, ss_pool, n_ss_pool);
+}
+
+int crass_b200_ac_scan_resident(crass_b200_ctx* c, const crass_b200_ac* ac, int skip_found, uint8_t* found, crass_b200_hit** hits,
+                                uint32_t* n_hits, uint32_t** ss_pool, uint32_t* n_ss_pool) {
+    if (!c || !ac) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    if (!c->res_valid) return cbh::fail(CRASS_B200_EINVAL, "no resident batch: call crass_b200_batch_upload first");
+    if (skip_found && !c->res_found_valid) return cbh::fail(CRASS_B200_EINVAL, "skip_found needs a preceding crass_b200_dr_search_resident");
+    if (!hits || !n_hits || !ss_pool || !n_ss_pool) return cbh::fail(CRASS_B200_EINVAL, "output pointer is NULL");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const uint32_t n_reads = c->res_n_reads;
+    auto launch = [&](uint32_t hits_cap, uint32_t pool_cap) {
+        return crass_b200_ac_scan_dev(c, ac, c->d_bases.as<uint8_t>(), c->d_offsets.as<uint64_t>(), n_reads, c->res_max_len,
+                                      skip_found ? c->d_found_p1.as<uint8_t>() : nullptr, c->d_found.as<uint8_t>(),
+                                      c->d_hits.as<crass_b200_hit>(), hits_cap, c->d_pool.as<uint32_t>(), pool_cap,
+                                      c->d_counters.as<uint32_t>(), c->stream);
+    };
+    return run_with_outputs(c, n_reads, c->res_n_bases, found, launch, hits, n_hits, ss_pool, n_ss_pool);
 }
 
 // ---- K3 ------------------------------------------------------------------------------------------------

@@ -221,6 +221,45 @@ char* crass_b200_results_dump(crass_b200_results* r, int max_read_len) {
     return dup_cstr(dump_results(r->r, max_read_len));
 }
 
+char* crass_b200_dr_list_from_hits(const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, const crass_b200_hit* hits,
+                                   uint32_t n_hits, const uint32_t* ss_pool) {
+    if ((n_hits && (!bases || !offsets || !hits || !ss_pool))) { fail(CRASS_B200_EINVAL, "NULL argument"); return nullptr; }
+    std::map<std::string, bool> seen;
+    std::string out, rc;
+    for (uint32_t k = 0; k < n_hits; ++k) {
+        const crass_b200_hit& h = hits[k];
+        if (h.read_index >= n_reads || h.n_ss < 2) { fail(CRASS_B200_EINVAL, "malformed hit"); return nullptr; }
+        const uint8_t* s = bases + offsets[h.read_index];
+        const uint32_t L = (uint32_t)(offsets[h.read_index + 1] - offsets[h.read_index]);
+        const uint32_t* ss = ss_pool + h.ss_offset;
+        // representative repeat exactly as ReadHolder::DRLowLexi picks it (ReadHolder.cpp:513-566)
+        uint32_t idx;
+        const uint32_t n_rep = h.n_ss / 2;
+        if (n_rep == 1) idx = 0;
+        else if (n_rep == 2) {
+            if (ss[0] == 0) idx = 2;
+            else if (ss[3] == L) idx = 0;
+            else idx = ((int)(ss[1] - ss[0]) > (int)(ss[3] - ss[2])) ? 0 : 2;
+        } else idx = 2;
+        uint32_t st = ss[idx], ln = ss[idx + 1] - ss[idx] + 1;
+        if (st > L) st = L;
+        if (ln > L - st) ln = L - st;
+        std::string dr((const char*)s + st, ln);
+        rc.resize(ln);
+        reverse_complement((const uint8_t*)dr.data(), ln, (uint8_t*)&rc[0]);
+        const std::string& tok = dr < rc ? dr : rc;
+        if (seen.emplace(tok, true).second) { out += tok; out += '\n'; }
+    }
+    return dup_cstr(out);
+}
+
+char* crass_b200_merge_dr_lists(const char* concatenated) {
+    std::map<std::string, bool> seen;
+    std::string out;
+    for (const std::string& d : split_lines(concatenated)) if (seen.emplace(d, true).second) { out += d; out += '\n'; }
+    return dup_cstr(out);
+}
+
 char* crass_b200_non_redundant_set(const char* dr_list, uint32_t kmer_clust) {
     std::vector<std::string> drs = split_lines(dr_list);
     std::vector<std::pair<int, int> > groups;
@@ -248,7 +287,8 @@ int crass_b200_run_files(crass_b200_ctx* ctx, const char* const* paths, uint32_t
         if ((int)b.max_len > max_len) max_len = (int)b.max_len;
         found[f].assign(b.n() + 1, 0);
         crass_b200_hit* hits = nullptr; uint32_t nh = 0, np = 0; uint32_t* pool = nullptr;
-        rc = crass_b200_dr_search(ctx, b.bases, b.offsets.data(), b.n(), params, found[f].data(), &hits, &nh, &pool, &np);
+        rc = crass_b200_batch_upload(ctx, b.bases, b.offsets.data(), b.n());
+        if (!rc) rc = crass_b200_dr_search_resident(ctx, params, found[f].data(), &hits, &nh, &pool, &np);
         if (!rc) rc = crass_b200_results_add_phase1(res, batches[f], hits, nh, pool);
         free(hits); free(pool);
     }
@@ -263,7 +303,8 @@ int crass_b200_run_files(crass_b200_ctx* ctx, const char* const* paths, uint32_t
             for (uint32_t f = 0; f < n_paths && !rc; ++f) {                  // phase 2: findSingletons per file
                 const Batch& b = batches[f]->b;
                 crass_b200_hit* hits = nullptr; uint32_t nh = 0, np = 0; uint32_t* pool = nullptr;
-                rc = crass_b200_ac_scan(ctx, ac, b.bases, b.offsets.data(), b.n(), found[f].data(), nullptr, &hits, &nh, &pool, &np);
+                if (n_paths == 1) rc = crass_b200_ac_scan_resident(ctx, ac, 1, nullptr, &hits, &nh, &pool, &np);   // batch still resident
+                else rc = crass_b200_ac_scan(ctx, ac, b.bases, b.offsets.data(), b.n(), found[f].data(), nullptr, &hits, &nh, &pool, &np);
                 if (!rc) rc = crass_b200_results_add_phase2(res, batches[f], hits, nh, pool);
                 free(hits); free(pool);
             }

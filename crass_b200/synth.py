@@ -161,3 +161,38 @@ def plant_patterns(bases, offsets, patterns, fraction, seed):
         b0 = int(offsets[r]) + at
         bases[b0:b0 + len(p)] = np.frombuffer(p, dtype=np.uint8)
     return pick
+
+
+def sample_fixed_torch(genome, n_reads, read_len, seed, device, sub_rate=0.001, n_rate=0.0005, chunk=1 << 21):
+    """Same recipe as sample_fixed but gathered on `device` with torch (fast enough for 10M+ reads inside a
+    benchmark run).  Deterministic for a given seed / torch build; not byte-identical to sample_fixed.
+    Returns (bases uint8 tensor on device, offsets int64 tensor on device)."""
+    import torch
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    dev = torch.device(device)
+    G = torch.from_numpy(genome).to(dev)
+    comp = torch.from_numpy(_COMP).to(dev)
+    acgt = torch.from_numpy(_ACGT.copy()).to(dev)
+    out = torch.empty(n_reads * read_len, dtype=torch.uint8, device=dev)
+    ar = torch.arange(read_len, dtype=torch.int64, device=dev)
+    hi = len(genome) - read_len
+    for lo_i in range(0, n_reads, chunk):
+        m = min(chunk, n_reads - lo_i)
+        starts = torch.randint(0, hi, (m,), generator=g, dtype=torch.int64).to(dev)
+        rev = torch.randint(0, 2, (m,), generator=g, dtype=torch.int64).to(dev).bool()
+        idx = torch.where(rev[:, None], starts[:, None] + (read_len - 1) - ar[None, :], starts[:, None] + ar[None, :])
+        blk = G[idx]
+        blk = torch.where(rev[:, None], comp[blk.long()], blk)
+        flat = blk.reshape(-1)
+        n = flat.numel()
+        k = int(torch.binomial(torch.tensor(float(n)), torch.tensor(sub_rate), generator=g).item()) if sub_rate > 0 else 0
+        if k:
+            pos = torch.randint(0, n, (k,), generator=g, dtype=torch.int64).to(dev)
+            flat[pos] = acgt[torch.randint(0, 4, (k,), generator=g, dtype=torch.int64).to(dev)]
+        k = int(torch.binomial(torch.tensor(float(n)), torch.tensor(n_rate), generator=g).item()) if n_rate > 0 else 0
+        if k:
+            flat[torch.randint(0, n, (k,), generator=g, dtype=torch.int64).to(dev)] = ord("N")
+        out[lo_i * read_len:(lo_i + m) * read_len] = flat
+    offsets = torch.arange(n_reads + 1, dtype=torch.int64, device=dev) * read_len
+    return out, offsets

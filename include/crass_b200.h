@@ -110,6 +110,17 @@ int crass_b200_dr_search(crass_b200_ctx* ctx, const uint8_t* bases, const uint64
                          const crass_b200_params* params, uint8_t* found,
                          crass_b200_hit** hits, uint32_t* n_hits, uint32_t** ss_pool, uint32_t* n_ss_pool);
 
+/* Resident form: upload a host batch once, then run both phases on it without copying it again.
+ *   crass_b200_batch_upload       H2D of bases+offsets into context-owned device buffers (replaces the previous one)
+ *   crass_b200_dr_search_resident K1 on the resident batch; remembers the found flags on the device
+ *   crass_b200_ac_scan_resident   K2 on the resident batch; skip_found != 0 skips the reads phase 1 flagged
+ * Output conventions as in crass_b200_dr_search. */
+int crass_b200_batch_upload(crass_b200_ctx* ctx, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads);
+int crass_b200_dr_search_resident(crass_b200_ctx* ctx, const crass_b200_params* params, uint8_t* found,
+                                  crass_b200_hit** hits, uint32_t* n_hits, uint32_t** ss_pool, uint32_t* n_ss_pool);
+int crass_b200_ac_scan_resident(crass_b200_ctx* ctx, const crass_b200_ac* ac, int skip_found, uint8_t* found,
+                                crass_b200_hit** hits, uint32_t* n_hits, uint32_t** ss_pool, uint32_t* n_ss_pool);
+
 /* ---- phase 2: singleton scan (kernel K2) ---------------------------------------------------------
  * patterns: n_patterns byte strings back to back, pat_offsets[n_patterns+1]. */
 int crass_b200_ac_build(const uint8_t* pat_bytes, const uint32_t* pat_offsets, uint32_t n_patterns, crass_b200_ac** out);
@@ -181,6 +192,13 @@ int crass_b200_results_adopt_tokens(crass_b200_results* r, const char* dr_list_a
 char* crass_b200_results_non_redundant(crass_b200_results* r, uint32_t kmer_clust, uint32_t* n_patterns);
 /* "crass-dump v1" text of the whole state (same format the oracle emits); malloc'd */
 char* crass_b200_results_dump(crass_b200_results* r, int max_read_len);
+
+/* the distinct low-lexi DR strings (ReadHolder::DRLowLexi) of a sorted hit list in first-appearance order,
+ * '\n'-separated, without building any container: what a shard contributes to the multi-GPU merge; malloc'd */
+char* crass_b200_dr_list_from_hits(const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
+                                   const crass_b200_hit* hits, uint32_t n_hits, const uint32_t* ss_pool);
+/* first-appearance de-duplication of the rank-ordered concatenation of such lists; malloc'd */
+char* crass_b200_merge_dr_lists(const char* concatenated);
 
 /* clustering step alone on an ordered DR list ('\n'-separated, token order); "G"/"P" lines; malloc'd */
 char* crass_b200_non_redundant_set(const char* dr_list, uint32_t kmer_clust);
