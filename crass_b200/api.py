@@ -67,6 +67,7 @@ def lib():
         "crass_b200_ctx_destroy": (None, [vp]),
         "crass_b200_ctx_device": (C.c_int, [vp]),
         "crass_b200_ctx_launch_count": (C.c_uint64, [vp]),
+        "crass_b200_ctx_last_candidates": (C.c_uint64, [vp]),
         "crass_b200_dr_search_dev": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, C.POINTER(Params), vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp]),
         "crass_b200_dr_search": (C.c_int, [vp, vp, vp, C.c_uint32, C.POINTER(Params), vp, C.POINTER(vp), u32p, C.POINTER(vp), u32p]),
         "crass_b200_batch_upload": (C.c_int, [vp, vp, vp, C.c_uint32]),
@@ -345,6 +346,10 @@ class Context:
     @property
     def launch_count(self):
         return int(lib().crass_b200_ctx_launch_count(self.h))
+
+    @property
+    def last_candidates(self):
+        return int(lib().crass_b200_ctx_last_candidates(self.h))
 
     # -- host-buffer entry points (the reference-facing calls; copies inside) -----------------------
     def _collect(self, call, n_reads, want_found):

@@ -85,13 +85,14 @@ struct crass_b200_ctx {
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     uint64_t launches = 0;
+    uint64_t last_candidates = 0;
     DevBuf d_bases, d_offsets, d_found, d_skip, d_hits, d_pool, d_counters, d_scratch, d_error, d_misc, d_symv;
     uint32_t* h_counters = nullptr;   // pinned, 8 words
     // resident batch (crass_b200_batch_upload)
     uint32_t res_n_reads = 0, res_max_len = 0;
     uint64_t res_n_bases = 0;
     bool res_valid = false, res_found_valid = false;
-    DevBuf d_found_p1;
+    DevBuf d_found_p1, d_cand;
 };
 
 namespace cbh {
@@ -124,7 +125,7 @@ extern "C" {
 const char* crass_b200_last_error(void) { return cbh::last_error_cstr(); }
 int crass_b200_abi_version(void) { return CRASS_B200_ABI_VERSION; }
 const char* crass_b200_build_info(void) {
-    return "crass_b200 hot path; CUDA " CB_STR(CUDART_VERSION) "; sm_100a; kernels: dr_search_generic, ac_scan_generic, edit_distance";
+    return "crass_b200 hot path; CUDA " CB_STR(CUDART_VERSION) "; sm_100a; kernels: dr_filter(2-bit)+dr_exact_list, dr_search_generic, ac_scan_generic, edit_distance";
 }
 int crass_b200_device_count(void) { return probe_devices(); }
 
@@ -154,7 +155,7 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->d_bases, &c->d_offsets, &c->d_found, &c->d_skip, &c->d_hits, &c->d_pool, &c->d_counters,
-                      &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv, &c->d_found_p1};
+                      &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv, &c->d_found_p1, &c->d_cand};
     for (DevBuf* b : bufs) b->release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     cudaStreamDestroy(c->stream);
@@ -163,6 +164,7 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
 
 int crass_b200_ctx_device(const crass_b200_ctx* c) { return c ? c->device : -1; }
 uint64_t crass_b200_ctx_launch_count(const crass_b200_ctx* c) { return c ? c->launches : 0; }
+uint64_t crass_b200_ctx_last_candidates(const crass_b200_ctx* c) { return c ? c->last_candidates : 0; }
 
 // ---- K1 ------------------------------------------------------------------------------------------------
 int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
@@ -181,6 +183,33 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
     cbk::HitSink sink{d_hits, hits_cap, d_ss_pool, ss_cap, d_counters};
     const uint32_t cap = cb::ss_capacity(o, max_read_len);
     const int threads = 128;
+    // Fast path: 2-bit seed filter over every read + exact search on the few candidates.  Needs the default
+    // window geometry (8-mers every 8 bases, seed distances 49..97) and reads that fit a thread's registers.
+    const char* force = getenv("CRASS_B200_K1");
+    const bool fast_ok = o.window == 8 && cb::window_skips(o) == 8 && o.low_dr + o.low_spacer == 49 &&
+                         o.high_dr + o.high_spacer == 97 && max_read_len <= 304 && (((uintptr_t)d_bases) & 15) == 0;
+    if (fast_ok && !(force && !strcmp(force, "generic"))) {
+        if (!d_found) { if (int r = c->d_found.reserve((size_t)n_reads + 16)) return r; d_found = c->d_found.as<uint8_t>(); }
+        if (int r = c->d_cand.reserve(((size_t)n_reads + 16) * sizeof(uint32_t))) return r;
+        uint32_t* cand = c->d_cand.as<uint32_t>();
+        const uint32_t n_tiles = (n_reads + cbk::kFilterTile - 1) / cbk::kFilterTile;
+        const int fblocks = (int)std::min<uint32_t>(n_tiles, (uint32_t)c->sm_count * 16);
+        const int se = (int)max_read_len - 58;
+        const int nwin = se < 0 ? 1 : se / 16 + 1;
+#define CB_FILTER(NW, NWIN) cbk::k_dr_filter<NW, NWIN, 49, 97><<<fblocks, cbk::kFilterTile, 0, st>>>(d_bases, d_offsets, n_reads, d_found, cand, d_counters)
+        if (max_read_len <= 112) { if (nwin <= 3) CB_FILTER(7, 3); else CB_FILTER(7, 4); }
+        else if (max_read_len <= 160) { if (nwin <= 6) CB_FILTER(10, 6); else CB_FILTER(10, 7); }
+        else if (max_read_len <= 256) { if (nwin <= 12) CB_FILTER(16, 12); else CB_FILTER(16, 13); }
+        else { if (nwin <= 15) CB_FILTER(19, 15); else CB_FILTER(19, 16); }
+#undef CB_FILTER
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        const int eblocks = c->sm_count * 8;
+        cbk::k_dr_exact_list<32><<<eblocks, threads, 0, st>>>(d_bases, d_offsets, cand, o, d_found, sink, c->d_error.as<int>());
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     if (cap <= 32) {
         int blocks = (int)std::min<uint64_t>(((uint64_t)n_reads + threads - 1) / threads, (uint64_t)c->sm_count * 64);
         cbk::k_dr_search_generic<32><<<blocks, threads, 0, st>>>(d_bases, d_offsets, n_reads, o, d_found, sink, nullptr, 0, c->d_error.as<int>());
@@ -225,6 +254,7 @@ int run_with_outputs(crass_b200_ctx* c, uint32_t n_reads, uint64_t n_bases, uint
         if (err) return cbh::fail(CRASS_B200_EINVAL, "kernel reported a condition where the reference throws");
     }
     const uint32_t nh = c->h_counters[0], np = c->h_counters[1];
+    c->last_candidates = c->h_counters[3];
     crass_b200_hit* h = (crass_b200_hit*)malloc(sizeof(crass_b200_hit) * (size_t)(nh ? nh : 1));
     uint32_t* p = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(np ? np : 1));
     if (!h || !p) { free(h); free(p); return cbh::fail(CRASS_B200_ENOMEM, "malloc"); }

@@ -10,6 +10,7 @@
 
 #include "../../include/crass_b200.h"
 #include "dr_core.cuh"
+#include "dr_filter.cuh"
 
 namespace cbk {
 
@@ -64,6 +65,85 @@ k_dr_search_generic(const uint8_t* __restrict__ bases, const uint64_t* __restric
         if (f < 0) *error_flag = f;
         if (found) found[r] = (f == 1);
         if (f == 1) emit_hit(sink, r, ss, n_ss, replen);
+    }
+}
+
+// ---- K1 fast path, stage 1: 2-bit seed filter ------------------------------------------------------------
+// One thread per read, 128 reads per tile.  The tile's bytes are contiguous in the batch: the CTA streams them
+// once with coalesced 128-bit loads, recodes 16 bases -> one 32-bit word on the fly and keeps only the packed
+// words in shared memory (4x smaller than the bytes).  Each thread then realigns its read out of the packed
+// tile with funnel shifts and runs cb::seed_filter entirely in registers.  Reads with a possible seed are
+// appended to cand_list; every read gets found[r] = 0 (the exact kernel overwrites the hits with 1).
+constexpr int kFilterTile = 128;
+
+__device__ __forceinline__ uint4 ldg_stream128(const uint8_t* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+template <int NW, int NWIN, int DMIN, int DMAX>
+__global__ void __launch_bounds__(kFilterTile)
+k_dr_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads,
+            uint8_t* __restrict__ found, uint32_t* __restrict__ cand_list, uint32_t* __restrict__ counters) {
+    constexpr int kWords = kFilterTile * NW + NW + 8;          // packed words a tile can need (+ look-ahead + realignment)
+    __shared__ uint32_t sm[kWords];
+    const uint32_t n_tiles = (n_reads + kFilterTile - 1) / kFilterTile;
+    const uint64_t n_bases = offsets[n_reads];
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t r0 = tile * kFilterTile;
+        const uint32_t r1 = min(r0 + (uint32_t)kFilterTile, n_reads);
+        const uint64_t lo = offsets[r0], hi = offsets[r1];
+        const uint64_t a0 = lo & ~(uint64_t)15;                 // 16-byte aligned start of the tile in the batch
+        uint32_t nvec = (uint32_t)((hi - a0 + 15) >> 4) + NW + 4;
+        if (nvec > (uint32_t)kWords) nvec = kWords;
+        __syncthreads();                                        // previous tile fully consumed
+        for (uint32_t v = threadIdx.x; v < nvec; v += kFilterTile) {
+            const uint64_t at = a0 + 16ull * v;
+            uint32_t w;
+            if (at + 16 <= n_bases) {
+                const uint4 x = ldg_stream128(bases + at);
+                w = cb::pack16(x.x, x.y, x.z, x.w);
+            } else {                                            // ragged end of the batch: byte loads, zero fill
+                uint32_t q[4] = {0, 0, 0, 0};
+                for (int i = 0; i < 16; ++i)
+                    if (at + i < n_bases) q[i >> 2] |= (uint32_t)__ldg(bases + at + i) << (8 * (i & 3));
+                w = cb::pack16(q[0], q[1], q[2], q[3]);
+            }
+            sm[v] = w;
+        }
+        __syncthreads();
+        const uint32_t r = r0 + threadIdx.x;
+        if (r < r1) {
+            const uint32_t b = (uint32_t)(offsets[r] - a0);     // base offset of the read inside the packed tile
+            const uint32_t wi = b >> 4, sh = (b & 15u) * 2u;
+            uint32_t R[NW + 2];
+#pragma unroll
+            for (int k = 0; k < NW + 2; ++k) R[k] = cb::funnel_r(sm[wi + k], sm[wi + k + 1], sh);
+            const bool cand = cb::seed_filter<NW, NWIN, DMIN, DMAX>(R);
+            found[r] = 0;
+            if (cand) cand_list[atomicAdd(&counters[3], 1u)] = r;
+        }
+    }
+}
+
+// ---- K1 fast path, stage 2: exact searchCore on the candidate list ---------------------------------------------
+template <int LOCAL_SS>
+__global__ void __launch_bounds__(128)
+k_dr_exact_list(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ cand_list,
+                Params o, uint8_t* __restrict__ found, HitSink sink, int* __restrict__ error_flag) {
+    const uint32_t n_cand = sink.counters[3];
+    const uint32_t nthreads = gridDim.x * blockDim.x;
+    uint32_t ss[LOCAL_SS];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += nthreads) {
+        const uint32_t r = cand_list[i];
+        const uint64_t b = offsets[r];
+        const uint32_t L = (uint32_t)(offsets[r + 1] - b);
+        GmemSeq s{bases + b};
+        uint32_t n_ss = 0, replen = 0;
+        const int f = cb::search_core(s, L, o, ss, (uint32_t)LOCAL_SS, n_ss, replen);
+        if (f < 0) *error_flag = f;
+        if (f == 1) { found[r] = 1; emit_hit(sink, r, ss, n_ss, replen); }
     }
 }
 

@@ -87,7 +87,9 @@ void crass_b200_ctx_destroy(crass_b200_ctx* ctx);
 int crass_b200_ctx_device(const crass_b200_ctx* ctx);
 /* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
 uint64_t crass_b200_ctx_launch_count(const crass_b200_ctx* ctx);
-/* device time of the most recent *_dev call's dominant kernel is measured by the caller with events */
+/* number of reads the most recent host-form search/scan sent to the exact (candidate) path; equals the number
+ * of reads when the generic kernels ran */
+uint64_t crass_b200_ctx_last_candidates(const crass_b200_ctx* ctx);
 
 /* ---- phase 1: direct-repeat search (kernel K1) -------------------------------------------------
  * Device-resident form.  Outputs (all device memory, caller-allocated):

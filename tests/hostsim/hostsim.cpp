@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../crass_b200/csrc/dr_core.cuh"
+#include "../../crass_b200/csrc/dr_filter.cuh"
 
 using namespace cb;
 
@@ -72,6 +73,35 @@ float hs_similarity(const uint8_t* a, uint32_t la, const uint8_t* b, uint32_t lb
 int hs_low_complexity(const uint8_t* a, uint32_t la) {
     PtrSeq s{a};
     return low_complexity(s, 0, la) ? 1 : 0;
+}
+
+// 2-bit seed pre-filter exactly as the K1 filter kernel runs it: pack 16 bytes per word (zero padded), realign
+// to an arbitrary base offset `shift_bases` (as a read inside a tile is), then seed_filter<NW,NWIN,49,97>.
+int hs_seed_filter(const uint8_t* seq, uint32_t len, uint32_t shift_bases, int nw, const uint8_t* tail, uint32_t tail_len) {
+    std::vector<uint8_t> buf(shift_bases, (uint8_t)'G');
+    buf.insert(buf.end(), seq, seq + len);
+    buf.insert(buf.end(), tail, tail + tail_len);       // what follows the read in the batch
+    buf.resize(buf.size() + 16 * 40, 0);
+    std::vector<uint32_t> packed(buf.size() / 16);
+    for (size_t v = 0; v < packed.size(); ++v) {
+        uint32_t w[4];
+        memcpy(w, buf.data() + 16 * v, 16);
+        packed[v] = pack16(w[0], w[1], w[2], w[3]);
+    }
+    uint32_t R[40];
+    const uint32_t wi = shift_bases >> 4, sh = (shift_bases & 15) * 2;
+    for (int k = 0; k < nw + 2; ++k) R[k] = funnel_r(packed[wi + k], packed[wi + k + 1], sh);
+    const int se = (int)len - 58;
+    const int nwin = se < 0 ? 1 : se / 16 + 1;
+    if (nw == 7 && nwin <= 3) return seed_filter<7, 3, 49, 97>(R);
+    if (nw == 7) return seed_filter<7, 4, 49, 97>(R);
+    if (nw == 10 && nwin <= 6) return seed_filter<10, 6, 49, 97>(R);
+    if (nw == 10) return seed_filter<10, 7, 49, 97>(R);
+    if (nw == 16 && nwin <= 12) return seed_filter<16, 12, 49, 97>(R);
+    if (nw == 16) return seed_filter<16, 13, 49, 97>(R);
+    if (nw == 19 && nwin <= 15) return seed_filter<19, 15, 49, 97>(R);
+    if (nw == 19) return seed_filter<19, 16, 49, 97>(R);
+    return -1;
 }
 
 }  // extern "C"

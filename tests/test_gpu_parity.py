@@ -30,6 +30,19 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(params=["fast", "generic"])
+def k1path(request):
+    """K1 has two device paths with identical results: the 2-bit seed filter + exact candidate kernel (default
+    options, reads <= 304 bp) and the generic one-thread-per-read kernel."""
+    old = os.environ.get("CRASS_B200_K1")
+    os.environ["CRASS_B200_K1"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("CRASS_B200_K1", None)
+    else:
+        os.environ["CRASS_B200_K1"] = old
+
+
 @pytest.fixture(scope="module")
 def P():
     return checkers.port()
@@ -140,10 +153,35 @@ def test_bundled_files_other_options(ctx, P):
 
 
 # ---- seeded fuzz against the oracle -----------------------------------------------------------------------
-def test_fuzz_default_params(ctx, P):
+def test_fuzz_default_params(ctx, P, k1path):
     rng = random.Random(101)
     reads = [fuzzgen.fuzz_read(rng) for _ in range(20000)]
     assert check_batch_against_oracle(ctx, P, reads) > 1500
+    if k1path == "fast":
+        assert 0 < ctx.last_candidates < len(reads)           # the filter really ran and really filtered
+
+
+@pytest.mark.parametrize("max_len", [100, 105, 112, 150, 153, 160, 249, 256, 297, 304, 305])
+def test_fast_path_length_buckets(ctx, P, max_len):
+    """Every register-layout instantiation of the filter (and the hand-over to the generic kernel above 304 bp)."""
+    rng = random.Random(1000 + max_len)
+    reads = []
+    for _ in range(3000):
+        L = max_len if rng.random() < 0.5 else rng.randint(0, max_len)
+        kind = rng.random()
+        if L == 0:
+            s = b""
+        elif kind < 0.3:
+            s = fuzzgen.rand_seq(rng, L)
+        elif kind < 0.9:
+            s = fuzzgen.planted_read(rng, L, sub_rate=rng.choice([0, 0, 0.01]))
+        else:
+            s = fuzzgen.microsat_read(rng, L)
+        if rng.random() < 0.1:
+            s = fuzzgen.mutate(rng, s, 0.01, b"NnacgtRY")
+        reads.append(s)
+    reads[-1] = fuzzgen.planted_read(rng, max_len)               # make sure the longest length is present
+    assert check_batch_against_oracle(ctx, P, reads) > 100
 
 
 def test_fuzz_other_params(ctx, P):
@@ -155,7 +193,7 @@ def test_fuzz_other_params(ctx, P):
         check_batch_against_oracle(ctx, P, reads, prm)
 
 
-def test_edge_batches(ctx, P):
+def test_edge_batches(ctx, P, k1path):
     assert check_batch_against_oracle(ctx, P, []) == 0                        # empty batch
     assert check_batch_against_oracle(ctx, P, [b"", b"A", b"ACGT" * 14, b"", b"N" * 200]) == 0   # empty / short / below 58 bp
     rng = random.Random(103)
@@ -172,7 +210,7 @@ def test_long_reads(ctx, P):
     assert check_batch_against_oracle(ctx, P, reads) > 40
 
 
-def test_synthetic_config2_prefix(ctx, P):
+def test_synthetic_config2_prefix(ctx, P, k1path):
     """A 300k-read prefix of the BASELINE config-2 recipe, compared read by read with the oracle."""
     genome, drs, _ = synth.make_genome(20242)
     n = 300_000
