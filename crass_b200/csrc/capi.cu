@@ -115,6 +115,8 @@ void free_host(void* p, bool pinned) {
 void free_device_tables(Automaton* a) {
     if (a->d_table) { cudaFree(a->d_table); a->d_table = nullptr; }
     if (a->d_out_len) { cudaFree(a->d_out_len); a->d_out_len = nullptr; }
+    if (a->d_q_bitmap) { cudaFree(a->d_q_bitmap); a->d_q_bitmap = nullptr; }
+    if (a->d_q_keys) { cudaFree(a->d_q_keys); a->d_q_keys = nullptr; }
 }
 
 }  // namespace cbh
@@ -125,7 +127,7 @@ extern "C" {
 const char* crass_b200_last_error(void) { return cbh::last_error_cstr(); }
 int crass_b200_abi_version(void) { return CRASS_B200_ABI_VERSION; }
 const char* crass_b200_build_info(void) {
-    return "crass_b200 hot path; CUDA " CB_STR(CUDART_VERSION) "; sm_100a; kernels: dr_filter(2-bit)+dr_exact_list, dr_search_generic, ac_scan_generic, edit_distance";
+    return "crass_b200 hot path; CUDA " CB_STR(CUDART_VERSION) "; sm_100a; kernels: dr_filter+dr_exact_packed (2-bit), ac_filter(q-gram)+ac_scan_list, dr_search_generic, ac_scan_generic, edit_distance";
 }
 int crass_b200_device_count(void) { return probe_devices(); }
 
@@ -196,17 +198,19 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
         const int fblocks = (int)std::min<uint32_t>(n_tiles, (uint32_t)c->sm_count * 16);
         const int se = (int)max_read_len - 58;
         const int nwin = se < 0 ? 1 : se / 16 + 1;
-#define CB_FILTER(NW, NWIN) cbk::k_dr_filter<NW, NWIN, 49, 97><<<fblocks, cbk::kFilterTile, 0, st>>>(d_bases, d_offsets, n_reads, d_found, cand, d_counters)
-        if (max_read_len <= 112) { if (nwin <= 3) CB_FILTER(7, 3); else CB_FILTER(7, 4); }
-        else if (max_read_len <= 160) { if (nwin <= 6) CB_FILTER(10, 6); else CB_FILTER(10, 7); }
-        else if (max_read_len <= 256) { if (nwin <= 12) CB_FILTER(16, 12); else CB_FILTER(16, 13); }
-        else { if (nwin <= 15) CB_FILTER(19, 15); else CB_FILTER(19, 16); }
-#undef CB_FILTER
-        c->launches++;
-        CUDA_TRY(cudaGetLastError());
         const int eblocks = c->sm_count * 8;
-        cbk::k_dr_exact_list<32><<<eblocks, threads, 0, st>>>(d_bases, d_offsets, cand, o, d_found, sink, c->d_error.as<int>());
-        c->launches++;
+        int* d_err = c->d_error.as<int>();
+#define CB_FAST(NW, NWIN)                                                                                                           \
+    do {                                                                                                                            \
+        cbk::k_dr_filter<NW, NWIN, 49, 97><<<fblocks, cbk::kFilterTile, 0, st>>>(d_bases, d_offsets, n_reads, d_found, cand, d_counters); \
+        cbk::k_dr_exact_packed<NW, NWIN, 49, 97><<<eblocks, cbk::kExactThreads, 0, st>>>(d_bases, d_offsets, n_reads, cand, o, d_found, sink, d_err); \
+    } while (0)
+        if (max_read_len <= 112) { if (nwin <= 3) CB_FAST(7, 3); else CB_FAST(7, 4); }
+        else if (max_read_len <= 160) { if (nwin <= 6) CB_FAST(10, 6); else CB_FAST(10, 7); }
+        else if (max_read_len <= 256) { if (nwin <= 12) CB_FAST(16, 12); else CB_FAST(16, 13); }
+        else { if (nwin <= 15) CB_FAST(19, 15); else CB_FAST(19, 16); }
+#undef CB_FAST
+        c->launches += 2;
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
@@ -344,9 +348,7 @@ int crass_b200_ac_build(const uint8_t* pat_bytes, const uint32_t* pat_offsets, u
     if (int r = cbh::build_automaton(pat_bytes, pat_offsets, n_patterns, &a)) return r;
     // crass_b200_ac is a thin wrapper; move the automaton in
     crass_b200_ac* h = new crass_b200_ac();
-    h->a.n_states = a->n_states; h->a.n_syms = a->n_syms; memcpy(h->a.symv, a->symv, 256);
-    h->a.table.swap(a->table); h->a.stride = a->stride; h->a.out_len.swap(a->out_len);
-    h->a.min_pattern_len = a->min_pattern_len; h->a.max_pattern_len = a->max_pattern_len; h->a.n_patterns = a->n_patterns;
+    h->a = *a;                     // no device copies exist yet, so a plain member-wise copy is safe
     delete a;
     *out = h;
     return 0;
@@ -368,6 +370,12 @@ int ensure_ac_on_device(crass_b200_ctx* c, crass_b200_ac* ac) {
     CUDA_TRY(cudaMalloc(&a.d_out_len, 256));                           // symv lives here
     CUDA_TRY(cudaMemcpyAsync(a.d_table, a.table.data(), a.table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(a.d_out_len, a.symv, 256, cudaMemcpyHostToDevice, c->stream));
+    if (a.q_bits) {
+        CUDA_TRY(cudaMalloc(&a.d_q_bitmap, a.q_bitmap.size() * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc(&a.d_q_keys, a.q_keys.size() * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemcpyAsync(a.d_q_bitmap, a.q_bitmap.data(), a.q_bitmap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(a.d_q_keys, a.q_keys.data(), a.q_keys.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     a.device = c->device;
     return 0;
@@ -391,6 +399,35 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
     cbk::HitSink sink{d_hits, hits_cap, d_ss_pool, ss_cap, d_counters};
     uint32_t stride_log2 = 0;
     while ((1u << stride_log2) < ac->a.stride) ++stride_log2;
+    // Fast path: 16-mer q-gram filter over every read + automaton walk over the few candidates.
+    const char* force = getenv("CRASS_B200_K2");
+    if (ac->a.q_bits && max_read_len <= 304 && (((uintptr_t)d_bases) & 15) == 0 && !(force && !strcmp(force, "generic"))) {
+        if (!d_found) { if (int r = c->d_found.reserve((size_t)n_reads + 16)) return r; d_found = c->d_found.as<uint8_t>(); }
+        if (int r = c->d_cand.reserve(((size_t)n_reads + 16) * sizeof(uint32_t))) return r;
+        uint32_t* cand = c->d_cand.as<uint32_t>();
+        cbk::QgramFilter q{(const uint32_t*)ac->a.d_q_bitmap, (const uint32_t*)ac->a.d_q_keys, ac->a.q_bits, ac->a.q_table_bits, ac->a.q_has_ones};
+        const uint32_t n_tiles = (n_reads + cbk::kAcTile - 1) / cbk::kAcTile;
+        const size_t bm_bytes = ((size_t)1 << ac->a.q_bits) / 8;
+#define CB_ACF(NW)                                                                                                              \
+    do {                                                                                                                        \
+        const size_t smem = bm_bytes + (size_t)(cbk::kAcTile * NW + NW + 8) * sizeof(uint32_t);                                 \
+        CUDA_TRY(cudaFuncSetAttribute(cbk::k_ac_filter<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        const int per_sm = std::max<int>(1, (int)((size_t)220 * 1024 / smem));                                                  \
+        const int fblocks = (int)std::min<uint32_t>(n_tiles, (uint32_t)(c->sm_count * std::min(per_sm, 8)));                    \
+        cbk::k_ac_filter<NW><<<fblocks, cbk::kAcTile, smem, st>>>(d_bases, d_offsets, n_reads, q, d_skip, d_found, cand, d_counters); \
+    } while (0)
+        if (max_read_len <= 112) CB_ACF(7);
+        else if (max_read_len <= 160) CB_ACF(10);
+        else if (max_read_len <= 256) CB_ACF(16);
+        else CB_ACF(19);
+#undef CB_ACF
+        CUDA_TRY(cudaGetLastError());
+        cbk::k_ac_scan_list<<<c->sm_count * 8, 128, 0, st>>>(d_bases, d_offsets, cand, (const uint32_t*)ac->a.d_table, stride_log2,
+                                                             (const uint8_t*)ac->a.d_out_len, d_found, sink);
+        c->launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     const int threads = 256;
     int blocks = (int)std::min<uint64_t>(((uint64_t)n_reads + threads - 1) / threads, (uint64_t)c->sm_count * 32);
     cbk::k_ac_scan_generic<<<blocks, threads, 0, st>>>(d_bases, d_offsets, n_reads, (const uint32_t*)ac->a.d_table, stride_log2,

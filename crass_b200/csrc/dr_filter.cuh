@@ -1,21 +1,22 @@
-// dr_filter.cuh -- 2-bit "any seed?" pre-filter for the direct-repeat search (K1 fast path).
+// dr_filter.cuh -- 2-bit seed detection for the direct-repeat search (K1 fast path).
 //
 // searchCore (libcrispr.cpp:295-348) looks, for every window start j = 0, 8, 16, ... <= L-58, for the
-// 8-mer read[j, j+8) at a position p with  j+49 <= p <= j+97  and  p+8 <= L-1.  A read in which no window
-// has such a second occurrence can never reach scanRight / extendPreRepeat, so searchCore returns false
-// for it.  This header answers exactly that question on a 2-bit recoding of the read:
+// 8-mer read[j, j+8) at a position p with  j+49 <= p <= j+97  and  p+8 <= L-1.  A window without such a
+// second occurrence can never reach scanRight / extendPreRepeat.  This header answers "which windows can
+// have one?" on a 2-bit recoding of the read:
 //
 //     code(byte) = (byte >> 1) & 3          A->0 C->1 T->2 G->3 ; N, IUPAC and lower case alias onto these
 //
-// Equal bytes give equal codes, so a byte-level seed is always a code-level seed: the filter can only
-// over-report (aliasing, the excluded last base, windows/positions past the read end), never miss.  Reads it
-// flags go to the exact kernel, which re-does the whole search on the bytes.
+// Equal bytes give equal codes, so a byte-level seed is always a code-level seed: the flags can only
+// over-report (aliasing, the excluded last base, positions past the read end), never miss.  Flagged windows
+// are re-examined on the bytes (find_left), everything after a confirmed seed runs the exact byte code of
+// dr_core.cuh.
 //
 // Layout: base i of the read sits in bits [2i, 2i+2) of a little-endian word stream R[]; an 8-mer at a
 // multiple of 8 is one aligned 16-bit half-word.  For a distance d, (R >> 2d) XOR R has a zero half-word h
 // exactly when window j = 8h re-occurs at j+d, so one funnel shift + one XOR test two windows, and a packed
-// unsigned 16-bit minimum (VIMNMX3.U16x2 on sm_100a) folds the tests: a half-word of the running minimum is
-// zero iff some (window, distance) pair matched.
+// unsigned 16-bit minimum (VIMNMX3.U16x2 on sm_100a) folds two distances into the running minimum of a
+// window word: a half-word of acc[k] ends up zero iff some distance matched for that window.
 #pragma once
 #include <stdint.h>
 
@@ -43,6 +44,14 @@ CB_HD uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c) {
 #endif
 }
 
+CB_HD int first_set(uint32_t x) {                                       // index of the lowest set bit, x != 0
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+
 // 4 bytes -> 8 bits (base k of the word in bits [2k, 2k+2))
 CB_HD uint32_t code4(uint32_t w) { return (((w >> 1) & 0x03030303u) * 0x01041040u) >> 24; }
 // 16 bytes -> 32 bits
@@ -56,34 +65,107 @@ CB_HD bool has_zero_half(uint32_t x) { return (x & 0xFFFFu) == 0 || (x >> 16) ==
 //        (whatever follows the read in the batch, or zeros -- it can only add false positives)
 // NWIN : words holding window starts, i.e. floor((max_len - 58) / 16) + 1
 // DMIN..DMAX : seed distances, low_dr + low_spacer .. high_dr + high_spacer (49..97 with default options)
+// acc[k] (k < NWIN): half-word h of acc[k] is zero iff window 16k + 8h has a code-level seed.
 template <int NW, int NWIN, int DMIN, int DMAX>
-CB_HD bool seed_filter(const uint32_t* R) {
-    uint32_t acc0 = 0xFFFFFFFFu, acc1 = 0xFFFFFFFFu;
+CB_HD void seed_flags(const uint32_t* R, uint32_t* acc) {
     constexpr int OLO = DMIN / 16, OHI = DMAX / 16;
 #pragma unroll
+    for (int k = 0; k < NWIN; ++k) acc[k] = 0xFFFFFFFFu;
+#pragma unroll
     for (int phi = 0; phi < 16; ++phi) {
-        uint32_t T[NW + 1];
+        uint32_t T[NW + 1];                                     // the stream shifted right by phi bases
 #pragma unroll
         for (int k = OLO; k <= NW; ++k) T[k] = phi ? funnel_r(R[k], R[k + 1], 2 * phi) : R[k];
-        uint32_t pend = 0xFFFFFFFFu;
-        bool has_pend = false;
 #pragma unroll
-        for (int o = OLO; o <= OHI; ++o) {
-            const int d = 16 * o + phi;
-            if (d < DMIN || d > DMAX) continue;
+        for (int k = 0; k < NWIN; ++k) {
+            uint32_t pend = 0;
+            bool has_pend = false;
 #pragma unroll
-            for (int k = 0; k < NWIN; ++k) {
-                if (k + o > NW - 1) continue;               // every position of this word pair lies past the read
+            for (int o = OLO; o <= OHI; ++o) {
+                const int d = 16 * o + phi;
+                if (d < DMIN || d > DMAX) continue;
+                if (k + o > NW - 1) continue;                   // every position of this word pair lies past the read
                 const uint32_t x = R[k] ^ T[k + o];
-                if (has_pend) {
-                    if ((k & 1) == 0) acc0 = min3_u16x2(acc0, pend, x); else acc1 = min3_u16x2(acc1, pend, x);
-                    has_pend = false;
-                } else { pend = x; has_pend = true; }
+                if (has_pend) { acc[k] = min3_u16x2(acc[k], pend, x); has_pend = false; }
+                else { pend = x; has_pend = true; }
+            }
+            if (has_pend) acc[k] = min3_u16x2(acc[k], pend, pend);
+        }
+    }
+}
+
+template <int NWIN>
+CB_HD bool any_flag(const uint32_t* acc) {
+    uint32_t m = acc[0];
+#pragma unroll
+    for (int k = 1; k + 1 < NWIN; k += 2) m = min3_u16x2(m, acc[k], acc[k + 1]);
+    if ((NWIN & 1) == 0) m = min3_u16x2(m, acc[NWIN - 1], acc[NWIN - 1]);
+    return has_zero_half(m);
+}
+
+template <int NWIN>
+CB_HD uint32_t flag_mask(const uint32_t* acc) {                 // bit h <-> window 8h ; NWIN <= 16
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < NWIN; ++k) {
+        if ((acc[k] & 0xFFFFu) == 0) m |= 1u << (2 * k);
+        if ((acc[k] >> 16) == 0) m |= 2u << (2 * k);
+    }
+    return m;
+}
+
+template <int NW, int NWIN, int DMIN, int DMAX>
+CB_HD bool seed_filter(const uint32_t* R) {
+    uint32_t acc[NWIN];
+    seed_flags<NW, NWIN, DMIN, DMAX>(R, acc);
+    return any_flag<NWIN>(acc);
+}
+
+// ---- searchCore driven by the window flags -----------------------------------------------------------------------
+// S[0 .. NW+1] is the packed read (dynamically indexable: shared or local memory), mask0 the flags of the windows
+// 0, 8, 16, ... (phase 0).  Identical results to cb::search_core: windows without a flag cannot have a seed, flagged
+// windows are checked on the bytes, and after a rejected candidate the window grid restarts at back()-1+8
+// (libcrispr.cpp:390), for which the flags are recomputed on the re-phased stream.
+template <int NW, int NWIN, int DMIN, int DMAX, class Seq>
+CB_HD int search_core_packed(const Seq& s, uint32_t L, const Params& o, const uint32_t* S, uint32_t mask0,
+                             uint32_t* ss, uint32_t cap, uint32_t& n_ss, uint32_t& replen) {
+    n_ss = 0; replen = 0;
+    const int se = search_end(o, L);
+    if (se < 0) return 0;
+    uint32_t base = 0, mask = mask0;
+    for (;;) {
+        while (mask) {
+            const int h = first_set(mask);
+            mask &= mask - 1;
+            const uint32_t j = base + 8u * (uint32_t)h;
+            if (j > (uint32_t)se) return 0;
+            uint32_t begin, end;
+            window_text(o, L, j, begin, end);
+            const int pos = find_left(s, begin, end, j, o.window);
+            if (pos < 0) continue;                              // code-level alias only
+            bool advance; uint32_t nj;
+            const int r = process_seed(s, L, o, j, begin + (uint32_t)pos, ss, n_ss, cap, replen, advance, nj);
+            if (r != 0) return r;
+            if (advance) {
+                base = nj + 8u;                                 // j = back() - 1, then j += skips
+                if (base > (uint32_t)se) return 0;
+                const uint32_t q = base >> 4, sh = (base & 15u) * 2u;
+                uint32_t Q[NW + 2];
+#pragma unroll
+                for (int k = 0; k < NW + 2; ++k) {
+                    const uint32_t lo = (q + k < (uint32_t)(NW + 2)) ? S[q + k] : 0u;
+                    const uint32_t hi = (q + k + 1 < (uint32_t)(NW + 2)) ? S[q + k + 1] : 0u;
+                    Q[k] = funnel_r(lo, hi, sh);
+                }
+                uint32_t acc[NWIN];
+                seed_flags<NW, NWIN, DMIN, DMAX>(Q, acc);
+                mask = flag_mask<NWIN>(acc);
+                goto next_phase;
             }
         }
-        if (has_pend) acc0 = min3_u16x2(acc0, pend, pend);
+        return 0;
+    next_phase:;
     }
-    return has_zero_half(acc0) || has_zero_half(acc1);
 }
 
 }  // namespace cb

@@ -12,11 +12,14 @@
 // read keeps visiting form a contiguous prefix that the kernel stages in shared memory.
 #include <string.h>
 
+#include <algorithm>
 #include <queue>
 
 #include "internal.h"
 
 namespace cbh {
+
+void build_qgram_filter(Automaton* A, const uint8_t* bytes, const uint32_t* offs, uint32_t n);
 
 Automaton::~Automaton() { free_device_tables(this); }
 
@@ -91,8 +94,51 @@ int build_automaton(const uint8_t* bytes, const uint32_t* offs, uint32_t n, Auto
             A->table[(size_t)id * stride + sy] = newid[to] | ((uint32_t)term[to] << 24);
         }
     }
+    build_qgram_filter(A, bytes, offs, n);
     *out = A;
     return 0;
+}
+
+// ---- q-gram pre-filter of kernel K2 ----------------------------------------------------------------------
+// Every pattern is at least 23 bytes long (DRs are >= lowDRsize), so any occurrence [a, a+len) in a read contains the
+// read-aligned 16-mer that starts at 8*ceil(a/8): 8i <= a+7 and 8i+16 <= a+23 <= a+len.  The kernel therefore only has to
+// look up the 16-mers at offsets 0, 8, 16, ... of a read in the set of all 16-mers of all patterns (2-bit codes,
+// (byte>>1)&3, so that equal bytes give equal codes and the test can only over-report).  Two levels:
+//   bitmap  2^bits-bit Bloom-style bitmap (one multiplicative hash), staged in shared memory by every CTA
+//   keys    open-addressing table of the exact 32-bit codes in global memory (L2 resident), probed only on bitmap hits
+uint32_t qgram_hash(uint32_t code, uint32_t bits) { return (code * 0x9E3779B1u) >> (32 - bits); }
+
+void build_qgram_filter(Automaton* A, const uint8_t* bytes, const uint32_t* offs, uint32_t n) {
+    A->q_bits = 0;
+    A->q_bitmap.clear(); A->q_keys.clear();
+    if (A->min_pattern_len < 23) return;                            // no guarantee of an aligned 16-mer: K2 uses the plain scan
+    std::vector<uint32_t> codes;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t len = offs[i + 1] - offs[i];
+        uint32_t code = 0;
+        for (uint32_t k = 0; k < len; ++k) {
+            code = (code >> 2) | ((uint32_t)((bytes[offs[i] + k] >> 1) & 3) << 30);   // base k of the window in bits [2k,2k+2)
+            if (k >= 15) codes.push_back(code);
+        }
+    }
+    std::sort(codes.begin(), codes.end());
+    codes.erase(std::unique(codes.begin(), codes.end()), codes.end());
+    A->q_count = (uint32_t)codes.size();
+    A->q_bits = codes.size() <= 40000 ? 19 : 20;                     // 64 KB or 128 KB of shared memory
+    A->q_bitmap.assign((size_t)1 << (A->q_bits - 5), 0);
+    uint32_t tbits = 4;
+    while (((size_t)1 << tbits) < codes.size() * 2 + 2) ++tbits;
+    A->q_table_bits = tbits;
+    A->q_keys.assign((size_t)1 << tbits, 0xFFFFFFFFu);               // 0xFFFFFFFF = empty; the all-G 16-mer is kept in q_has_ones
+    A->q_has_ones = 0;
+    for (uint32_t c : codes) {
+        const uint32_t h = qgram_hash(c, A->q_bits);
+        A->q_bitmap[h >> 5] |= 1u << (h & 31);
+        if (c == 0xFFFFFFFFu) { A->q_has_ones = 1; continue; }
+        uint32_t slot = (c * 0x85EBCA6Bu) >> (32 - tbits);
+        while (A->q_keys[slot] != 0xFFFFFFFFu) slot = (slot + 1) & (((uint32_t)1 << tbits) - 1);
+        A->q_keys[slot] = c;
+    }
 }
 
 }  // namespace cbh

@@ -83,9 +83,14 @@ struct Automaton {
     uint32_t stride = 0;                        // entries per state (n_syms rounded up to a power of two)
     uint32_t min_pattern_len = 0, max_pattern_len = 0, n_patterns = 0;
     std::vector<uint16_t> out_len;              // longest pattern ending in the state (0 = none)
+    // q-gram pre-filter (ac_build.cpp): empty when the shortest pattern is below 23 bytes
+    uint32_t q_bits = 0, q_table_bits = 0, q_count = 0, q_has_ones = 0;
+    std::vector<uint32_t> q_bitmap, q_keys;
     // device copies, owned by the context that uploaded them
     void* d_table = nullptr;
     void* d_out_len = nullptr;
+    void* d_q_bitmap = nullptr;
+    void* d_q_keys = nullptr;
     int device = -1;
     ~Automaton();
 };

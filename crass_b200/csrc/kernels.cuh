@@ -120,7 +120,9 @@ k_dr_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs
             uint32_t R[NW + 2];
 #pragma unroll
             for (int k = 0; k < NW + 2; ++k) R[k] = cb::funnel_r(sm[wi + k], sm[wi + k + 1], sh);
-            const bool cand = cb::seed_filter<NW, NWIN, DMIN, DMAX>(R);
+            uint32_t acc[NWIN];
+            cb::seed_flags<NW, NWIN, DMIN, DMAX>(R, acc);
+            const bool cand = cb::any_flag<NWIN>(acc);
             found[r] = 0;
             if (cand) cand_list[atomicAdd(&counters[3], 1u)] = r;
         }
@@ -128,20 +130,54 @@ k_dr_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs
 }
 
 // ---- K1 fast path, stage 2: exact searchCore on the candidate list ---------------------------------------------
-template <int LOCAL_SS>
-__global__ void __launch_bounds__(128)
-k_dr_exact_list(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ cand_list,
-                Params o, uint8_t* __restrict__ found, HitSink sink, int* __restrict__ error_flag) {
+// One thread per candidate read.  The thread re-packs its read (128-bit loads straight from the batch), recomputes
+// the window flags and then runs cb::search_core_packed: only flagged windows are looked at on the bytes, and the
+// flags are recomputed on the re-phased stream whenever a rejected candidate moves the window grid.
+constexpr int kExactThreads = 128;
+
+template <int NW, int NWIN, int DMIN, int DMAX>
+__global__ void __launch_bounds__(kExactThreads)
+k_dr_exact_packed(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads,
+                  const uint32_t* __restrict__ cand_list, Params o, uint8_t* __restrict__ found, HitSink sink,
+                  int* __restrict__ error_flag) {
+    constexpr int kSlot = (NW + 4) | 1;                         // odd stride: conflict-free per-thread slots
+    __shared__ uint32_t sm[kExactThreads * kSlot];
     const uint32_t n_cand = sink.counters[3];
+    const uint64_t n_bases = offsets[n_reads];
     const uint32_t nthreads = gridDim.x * blockDim.x;
-    uint32_t ss[LOCAL_SS];
+    uint32_t* S = sm + threadIdx.x * kSlot;
+    uint32_t ss[32];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += nthreads) {
         const uint32_t r = cand_list[i];
         const uint64_t b = offsets[r];
         const uint32_t L = (uint32_t)(offsets[r + 1] - b);
+        const uint64_t a0 = b & ~(uint64_t)15;
+        const uint32_t sh = (uint32_t)(b & 15u) * 2u;
+        uint32_t prev = 0;
+        uint32_t R[NW + 2];
+#pragma unroll
+        for (int v = 0; v < NW + 3; ++v) {
+            const uint64_t at = a0 + 16ull * v;
+            uint32_t w = 0;
+            if (at + 16 <= n_bases) {
+                const uint4 x = __ldg(reinterpret_cast<const uint4*>(bases + at));
+                w = cb::pack16(x.x, x.y, x.z, x.w);
+            } else {
+                uint32_t q[4] = {0, 0, 0, 0};
+                for (int t = 0; t < 16; ++t)
+                    if (at + t < n_bases) q[t >> 2] |= (uint32_t)__ldg(bases + at + t) << (8 * (t & 3));
+                w = cb::pack16(q[0], q[1], q[2], q[3]);
+            }
+            if (v > 0) R[v - 1] = cb::funnel_r(prev, w, sh);
+            prev = w;
+        }
+#pragma unroll
+        for (int k = 0; k < NW + 2; ++k) S[k] = R[k];
+        uint32_t acc[NWIN];
+        cb::seed_flags<NW, NWIN, DMIN, DMAX>(R, acc);
         GmemSeq s{bases + b};
         uint32_t n_ss = 0, replen = 0;
-        const int f = cb::search_core(s, L, o, ss, (uint32_t)LOCAL_SS, n_ss, replen);
+        const int f = cb::search_core_packed<NW, NWIN, DMIN, DMAX>(s, L, o, S, cb::flag_mask<NWIN>(acc), ss, 32u, n_ss, replen);
         if (f < 0) *error_flag = f;
         if (f == 1) { found[r] = 1; emit_hit(sink, r, ss, n_ss, replen); }
     }
@@ -176,6 +212,135 @@ k_ac_scan_generic(const uint8_t* __restrict__ bases, const uint64_t* __restrict_
             uint32_t dr_end = end - 1;
             if (dr_end >= L) dr_end = L - 1;
             uint32_t ss[2] = { dr_end - (plen - 1), dr_end };
+            emit_hit(sink, r, ss, 2, 0);
+        }
+    }
+}
+
+// ---- K2 fast path, stage 1: 16-mer q-gram filter -----------------------------------------------------------
+// Same tile staging as k_dr_filter (coalesced 128-bit loads, 2-bit recoding into shared memory, one thread per
+// read).  Every pattern is >= 23 bytes, so an occurrence always contains the read-aligned 16-mer at a multiple of 8
+// (see host/ac_build.cpp); the thread looks those 16-mers up in a shared-memory bitmap and, on a bitmap hit, in
+// the exact key table in global memory.  Reads with a confirmed pattern 16-mer go to the automaton kernel.
+struct QgramFilter {
+    const uint32_t* bitmap;     // 2^bits bits
+    const uint32_t* keys;       // 2^table_bits slots, 0xFFFFFFFF = empty
+    uint32_t bits, table_bits, has_ones;
+};
+
+constexpr int kAcTile = 256;
+
+__device__ __forceinline__ bool qgram_member(const QgramFilter& q, uint32_t code) {
+    if (code == 0xFFFFFFFFu) return q.has_ones != 0;
+    const uint32_t mask = (1u << q.table_bits) - 1u;
+    uint32_t slot = (code * 0x85EBCA6Bu) >> (32 - q.table_bits);
+    for (;;) {
+        const uint32_t k = __ldg(q.keys + slot);
+        if (k == code) return true;
+        if (k == 0xFFFFFFFFu) return false;
+        slot = (slot + 1) & mask;
+    }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kAcTile)
+k_ac_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads, QgramFilter q,
+            const uint8_t* __restrict__ skip, uint8_t* __restrict__ found, uint32_t* __restrict__ cand_list,
+            uint32_t* __restrict__ counters) {
+    constexpr int kWords = kAcTile * NW + NW + 8;
+    extern __shared__ uint32_t dsm[];
+    uint32_t* bm = dsm;                                          // bitmap, (1 << bits) / 32 words
+    uint32_t* sm = dsm + (1u << (q.bits - 5));                   // packed tile
+    for (uint32_t i = threadIdx.x; i < (1u << (q.bits - 5)); i += kAcTile) bm[i] = __ldg(q.bitmap + i);
+    const uint32_t n_tiles = (n_reads + kAcTile - 1) / kAcTile;
+    const uint64_t n_bases = offsets[n_reads];
+    const uint32_t hshift = 32 - q.bits;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t r0 = tile * kAcTile;
+        const uint32_t r1 = min(r0 + (uint32_t)kAcTile, n_reads);
+        const uint64_t lo = offsets[r0], hi = offsets[r1];
+        const uint64_t a0 = lo & ~(uint64_t)15;
+        uint32_t nvec = (uint32_t)((hi - a0 + 15) >> 4) + NW + 4;
+        if (nvec > (uint32_t)kWords) nvec = kWords;
+        __syncthreads();
+        for (uint32_t v = threadIdx.x; v < nvec; v += kAcTile) {
+            const uint64_t at = a0 + 16ull * v;
+            uint32_t w;
+            if (at + 16 <= n_bases) {
+                const uint4 x = ldg_stream128(bases + at);
+                w = cb::pack16(x.x, x.y, x.z, x.w);
+            } else {
+                uint32_t qq[4] = {0, 0, 0, 0};
+                for (int i = 0; i < 16; ++i)
+                    if (at + i < n_bases) qq[i >> 2] |= (uint32_t)__ldg(bases + at + i) << (8 * (i & 3));
+                w = cb::pack16(qq[0], qq[1], qq[2], qq[3]);
+            }
+            sm[v] = w;
+        }
+        __syncthreads();
+        const uint32_t r = r0 + threadIdx.x;
+        if (r < r1) {
+            const uint64_t rb = offsets[r];
+            const uint32_t L = (uint32_t)(offsets[r + 1] - rb);
+            const uint32_t b = (uint32_t)(rb - a0);
+            const uint32_t wi = b >> 4, sh = (b & 15u) * 2u;
+            uint32_t R[NW + 1];
+#pragma unroll
+            for (int k = 0; k < NW + 1; ++k) R[k] = cb::funnel_r(sm[wi + k], sm[wi + k + 1], sh);
+            // 16-mer i starts at base 8i: even i is word i/2, odd i straddles two words
+            uint64_t hits = 0;
+#pragma unroll
+            for (int i = 0; i < 2 * NW - 1; ++i) {
+                const uint32_t code = (i & 1) ? cb::funnel_r(R[i >> 1], R[(i >> 1) + 1], 16) : R[i >> 1];
+                const uint32_t h = (code * 0x9E3779B1u) >> hshift;
+                const uint32_t bit = (bm[h >> 5] >> (h & 31u)) & 1u;
+                hits |= (uint64_t)bit << i;
+            }
+            const int n_kmers = L >= 16 ? (int)((L - 16) >> 3) + 1 : 0;        // 16-mers that lie inside the read
+            if (n_kmers < 64) hits &= (1ull << n_kmers) - 1ull;
+            bool cand = false;
+            while (hits && !cand) {
+                const int i = __ffsll((long long)hits) - 1;
+                hits &= hits - 1;
+                const uint32_t w0 = cb::funnel_r(sm[wi + (i >> 1)], sm[wi + (i >> 1) + 1], sh);
+                const uint32_t w1 = cb::funnel_r(sm[wi + (i >> 1) + 1], sm[wi + (i >> 1) + 2], sh);
+                const uint32_t code = (i & 1) ? cb::funnel_r(w0, w1, 16) : w0;
+                cand = qgram_member(q, code);
+            }
+            found[r] = 0;
+            if (cand && !(skip && skip[r])) cand_list[atomicAdd(&counters[3], 1u)] = r;
+        }
+    }
+}
+
+// ---- K2 fast path, stage 2: automaton walk over the candidate reads ---------------------------------------------
+__global__ void __launch_bounds__(128)
+k_ac_scan_list(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ cand_list,
+               const uint32_t* __restrict__ table, uint32_t stride_log2, const uint8_t* __restrict__ symv_g,
+               uint8_t* __restrict__ found, HitSink sink) {
+    __shared__ uint8_t symv[256];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) symv[i] = symv_g[i];
+    __syncthreads();
+    const uint32_t n_cand = sink.counters[3];
+    const uint32_t nthreads = gridDim.x * blockDim.x;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cand; c += nthreads) {
+        const uint32_t r = cand_list[c];
+        const uint64_t b = offsets[r];
+        const uint32_t L = (uint32_t)(offsets[r + 1] - b);
+        const uint8_t* s = bases + b;
+        uint32_t st = 0, end = 0, plen = 0;
+        for (uint32_t i = 0; i < L; ++i) {
+            const uint32_t sy = symv[__ldg(s + i)];
+            if (!sy) { st = 0; continue; }
+            const uint32_t e = __ldg(table + ((size_t)st << stride_log2) + (sy - 1));
+            st = e & 0xFFFFFFu;
+            if (e >> 24) { end = i + 1; plen = e >> 24; break; }
+        }
+        if (plen) {
+            uint32_t dr_end = end - 1;
+            if (dr_end >= L) dr_end = L - 1;
+            uint32_t ss[2] = { dr_end - (plen - 1), dr_end };
+            found[r] = 1;
             emit_hit(sink, r, ss, 2, 0);
         }
     }

@@ -75,9 +75,35 @@ int hs_low_complexity(const uint8_t* a, uint32_t la) {
     return low_complexity(s, 0, la) ? 1 : 0;
 }
 
-// 2-bit seed pre-filter exactly as the K1 filter kernel runs it: pack 16 bytes per word (zero padded), realign
-// to an arbitrary base offset `shift_bases` (as a read inside a tile is), then seed_filter<NW,NWIN,49,97>.
-int hs_seed_filter(const uint8_t* seq, uint32_t len, uint32_t shift_bases, int nw, const uint8_t* tail, uint32_t tail_len) {
+}  // extern "C"
+
+// 2-bit seed flags exactly as the K1 filter kernel computes them: pack 16 bytes per word (zero padded), realign
+// to an arbitrary base offset `shift_bases` (as a read inside a tile is), then seed_flags<NW,NWIN,49,97>.
+// mode 0: returns the filter decision; mode 1: runs search_core_packed (the exact candidate kernel's logic) and
+// returns found, filling ss / n_ss / replen.
+template <int NW, int NWIN>
+static int run_packed(const uint32_t* R, const uint8_t* seq, uint32_t len, int mode, uint32_t* ss, uint32_t* n_ss, uint32_t* replen) {
+    uint32_t acc[NWIN];
+    seed_flags<NW, NWIN, 49, 97>(R, acc);
+    const bool cand = any_flag<NWIN>(acc);
+    if (mode == 0) return cand ? 1 : 0;
+    *n_ss = 0; *replen = 0;
+    if (!cand) return 0;
+    Params o; o.low_dr = 23; o.high_dr = 47; o.low_spacer = 26; o.high_spacer = 50; o.window = 8; o.min_repeats = 2; o.kmer_clust = 6; o.scan_range = 24;
+    PtrSeq s{seq};
+    uint32_t S[NW + 4];
+    for (int k = 0; k < NW + 2; ++k) S[k] = R[k];
+    S[NW + 2] = S[NW + 3] = 0;
+    uint32_t n = 0, rl = 0;
+    const int r = search_core_packed<NW, NWIN, 49, 97>(s, len, o, S, flag_mask<NWIN>(acc), ss, 32, n, rl);
+    *n_ss = n; *replen = rl;
+    return r;
+}
+
+extern "C" {
+
+int hs_packed(const uint8_t* seq, uint32_t len, uint32_t shift_bases, int nw, const uint8_t* tail, uint32_t tail_len, int mode,
+              uint32_t* ss, uint32_t* n_ss, uint32_t* replen) {
     std::vector<uint8_t> buf(shift_bases, (uint8_t)'G');
     buf.insert(buf.end(), seq, seq + len);
     buf.insert(buf.end(), tail, tail + tail_len);       // what follows the read in the batch
@@ -93,15 +119,17 @@ int hs_seed_filter(const uint8_t* seq, uint32_t len, uint32_t shift_bases, int n
     for (int k = 0; k < nw + 2; ++k) R[k] = funnel_r(packed[wi + k], packed[wi + k + 1], sh);
     const int se = (int)len - 58;
     const int nwin = se < 0 ? 1 : se / 16 + 1;
-    if (nw == 7 && nwin <= 3) return seed_filter<7, 3, 49, 97>(R);
-    if (nw == 7) return seed_filter<7, 4, 49, 97>(R);
-    if (nw == 10 && nwin <= 6) return seed_filter<10, 6, 49, 97>(R);
-    if (nw == 10) return seed_filter<10, 7, 49, 97>(R);
-    if (nw == 16 && nwin <= 12) return seed_filter<16, 12, 49, 97>(R);
-    if (nw == 16) return seed_filter<16, 13, 49, 97>(R);
-    if (nw == 19 && nwin <= 15) return seed_filter<19, 15, 49, 97>(R);
-    if (nw == 19) return seed_filter<19, 16, 49, 97>(R);
-    return -1;
+#define HS_RUN(NW, NWIN) return run_packed<NW, NWIN>(R, seq, len, mode, ss, n_ss, replen)
+    if (nw == 7 && nwin <= 3) HS_RUN(7, 3);
+    if (nw == 7) HS_RUN(7, 4);
+    if (nw == 10 && nwin <= 6) HS_RUN(10, 6);
+    if (nw == 10) HS_RUN(10, 7);
+    if (nw == 16 && nwin <= 12) HS_RUN(16, 12);
+    if (nw == 16) HS_RUN(16, 13);
+    if (nw == 19 && nwin <= 15) HS_RUN(19, 15);
+    if (nw == 19) HS_RUN(19, 16);
+#undef HS_RUN
+    return -9;
 }
 
 }  // extern "C"

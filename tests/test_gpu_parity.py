@@ -43,6 +43,18 @@ def k1path(request):
         os.environ["CRASS_B200_K1"] = old
 
 
+@pytest.fixture(params=["fast", "generic"])
+def k2path(request):
+    """K2 likewise: 16-mer q-gram filter + automaton walk over the candidates, or the plain one-thread-per-read walk."""
+    old = os.environ.get("CRASS_B200_K2")
+    os.environ["CRASS_B200_K2"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("CRASS_B200_K2", None)
+    else:
+        os.environ["CRASS_B200_K2"] = old
+
+
 @pytest.fixture(scope="module")
 def P():
     return checkers.port()
@@ -113,7 +125,7 @@ def test_edit_distance_golden_vectors(ctx):
         assert struct.pack(">f", float(sim[i])).hex() == simhex
 
 
-def test_ac_golden_vectors(ctx):
+def test_ac_golden_vectors(ctx, k2path):
     for case in load("ac_vectors.json"):
         ac = cb.Automaton([p.encode() for p in case["patterns"]])
         texts = [t.encode() for t, _ in case["texts"]]
@@ -155,7 +167,7 @@ def test_bundled_files_other_options(ctx, P):
 # ---- seeded fuzz against the oracle -----------------------------------------------------------------------
 def test_fuzz_default_params(ctx, P, k1path):
     rng = random.Random(101)
-    reads = [fuzzgen.fuzz_read(rng) for _ in range(20000)]
+    reads = [fuzzgen.fuzz_read(rng, max_len=300) for _ in range(20000)]
     assert check_batch_against_oracle(ctx, P, reads) > 1500
     if k1path == "fast":
         assert 0 < ctx.last_candidates < len(reads)           # the filter really ran and really filtered
@@ -227,9 +239,9 @@ def test_synthetic_config2_prefix(ctx, P, k1path):
         assert got[int(i)] == (ss, rl)
 
 
-def test_singleton_scan_fuzz(ctx, P):
+def test_singleton_scan_fuzz(ctx, P, k2path):
     rng = random.Random(105)
-    for n_pat in (1, 7, 100, 1500):
+    for n_pat in (1, 7, 100, 1500, 12000):
         pats = fuzzgen.dr_like_patterns(rng, n_pat)
         if n_pat == 7:
             pats += [p[2:-3] for p in pats] + [fuzzgen.mutate(rng, p, 0.1, b"ACGTN") for p in pats]
