@@ -209,14 +209,18 @@ def main():
     kt = {"k1": [], "k2": []}
     stats = {}
 
-    def fetch_hits():
+    TOK = 64                                                           # bytes per K4 token record (>= high_dr + 2)
+    d_tokens = torch.empty(hits_cap * TOK, dtype=torch.uint8, device=dev)
+    host_ms = {"fetch": [], "dr_list": [], "merge": [], "cluster": [], "ac_build": []}
+
+    def fetch_hits(with_tokens=False):
         h_cnt.copy_(d_cnt, non_blocking=False)
         nh, npool, ovf = int(h_cnt[0]), int(h_cnt[1]), int(h_cnt[2])
         assert not ovf, "bench hit buffers overflowed"
         hits = d_hits[: nh * 4].cpu().numpy().view(api.HIT_DTYPE)
         pool = d_pool[: max(npool, 1)].cpu().numpy().view(np.uint32)
-        order = np.argsort(hits["read_index"], kind="stable")
-        return hits[order], pool
+        toks = d_tokens[: max(nh, 1) * TOK].cpu().numpy() if with_tokens else None
+        return hits, pool, toks                                        # device order (unsorted); consumers sort by read index
 
     def merge_dr_lists(local):
         if world == 1:
@@ -239,32 +243,41 @@ def main():
     def step_resident(record):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         e[0].record()
+        ctx.set_token_output(d_tokens, TOK)                            # K4: DR tokens are extracted where the hits are found
         ctx.dr_search_dev(d_bases, d_offsets, n, READ_LEN, params, d_found, d_hits, d_pool, d_cnt, stream)
+        ctx.set_token_output(None)
         e[1].record()
-        hits, pool = fetch_hits()
-        local = api.dr_list_from_hits(np_bases, np_offsets, hits, pool)
+        t0 = time.perf_counter()
+        hits, pool, toks = fetch_hits(with_tokens=True)
+        t1 = time.perf_counter()
+        local = api.dr_list_from_tokens(toks, TOK, hits)               # distinct low-lexi DRs, first-appearance order
+        t2 = time.perf_counter()
         merged = merge_dr_lists(local)
+        t3 = time.perf_counter()
         pats = api.non_redundant_list(merged, params.kmer_clust)
+        t4 = time.perf_counter()
         n2 = 0
         if pats:
             ac = cb.Automaton(pats)
+            t5 = time.perf_counter()
             e[2].record()
             ctx.ac_scan_dev(ac, d_bases, d_offsets, n, READ_LEN, d_found, d_found2, d_hits, d_pool, d_cnt, stream)
             e[3].record()
-            hits2, pool2 = fetch_hits()
+            hits2, pool2, _ = fetch_hits()
             n2 = len(hits2)
         torch.cuda.synchronize()
         if record:
             kt["k1"].append(e[0].elapsed_time(e[1]))
             if pats:
                 kt["k2"].append(e[2].elapsed_time(e[3]))
+                for k, v in zip(("fetch", "dr_list", "merge", "cluster", "ac_build"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+                    host_ms[k].append(v * 1e3)
         stats.update(hits_phase1=len(hits), dr_variants_local=len(local), dr_variants_merged=len(merged), patterns=len(pats), hits_phase2=n2)
 
     def step_e2e():
         ctx.upload(h_bases, h_offsets)                                 # H2D from pinned host memory
         hits, pool, _ = ctx.dr_search_resident(params)
-        batch_names = None
-        local = api.dr_list_from_hits(np_bases, np_offsets, hits, pool)
+        local = ctx.last_dr_list()
         merged = merge_dr_lists(local)
         pats = api.non_redundant_list(merged, params.kmer_clust)
         nb = hits.nbytes + pool.nbytes
@@ -329,7 +342,8 @@ def main():
                              "kernel_ms": dom_ms},
                 "kernels": {"k1_dr_search_ms": k1, "k1_frac_of_hbm": bytes_k1 / (k1 / 1e3) / 1e9 / peak,
                             "k2_singleton_scan_ms": k2, "k2_frac_of_hbm": (bytes_k2 / (k2 / 1e3) / 1e9 / peak) if k2 else None,
-                            "host_between_kernels_ms": ms_step - k1 - k2},
+                            "host_between_kernels_ms": ms_step - k1 - k2,
+                            "host_breakdown_ms": {k: float(np.mean(v)) for k, v in host_ms.items() if v}},
                 "stats": stats, "clocks": clocks}
         if not args.no_cpu_baseline:
             ns = min(args.cpu_sample, n)

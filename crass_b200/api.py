@@ -68,6 +68,9 @@ def lib():
         "crass_b200_ctx_device": (C.c_int, [vp]),
         "crass_b200_ctx_launch_count": (C.c_uint64, [vp]),
         "crass_b200_ctx_last_candidates": (C.c_uint64, [vp]),
+        "crass_b200_ctx_set_token_output": (C.c_int, [vp, vp, C.c_uint32]),
+        "crass_b200_ctx_last_dr_list": (cp, [vp]),
+        "crass_b200_dr_list_from_tokens": (vp, [vp, C.c_uint32, vp, C.c_uint32]),
         "crass_b200_dr_search_dev": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, C.POINTER(Params), vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp]),
         "crass_b200_dr_search": (C.c_int, [vp, vp, vp, C.c_uint32, C.POINTER(Params), vp, C.POINTER(vp), u32p, C.POINTER(vp), u32p]),
         "crass_b200_batch_upload": (C.c_int, [vp, vp, vp, C.c_uint32]),
@@ -311,6 +314,12 @@ def dr_list_from_hits(bases, offsets, hits, pool):
     return [x for x in s.split(b"\n") if x]
 
 
+def dr_list_from_tokens(records, stride, hits):
+    """records: uint8 numpy array [n_hits*stride] copied back from the device; hits: unsorted HIT_DTYPE array."""
+    s = _take_str(lib().crass_b200_dr_list_from_tokens(_np_ptr(records), stride, _np_ptr(hits), len(hits)))
+    return [x for x in s.split(b"\n") if x]
+
+
 def merge_dr_lists(drs):
     s = _take_str(lib().crass_b200_merge_dr_lists(b"".join(d + b"\n" for d in drs)))
     return [x for x in s.split(b"\n") if x]
@@ -350,6 +359,14 @@ class Context:
     @property
     def last_candidates(self):
         return int(lib().crass_b200_ctx_last_candidates(self.h))
+
+    def set_token_output(self, d_tokens, stride=64):
+        """K4: let dr_search_dev also write the low-lexi DR token of every hit (torch uint8 tensor, stride bytes per hit slot)."""
+        _check(lib().crass_b200_ctx_set_token_output(self.h, d_tokens.data_ptr() if d_tokens is not None else None, stride))
+
+    def last_dr_list(self):
+        s = lib().crass_b200_ctx_last_dr_list(self.h)
+        return [x for x in s.split(b"\n") if x]
 
     # -- host-buffer entry points (the reference-facing calls; copies inside) -----------------------
     def _collect(self, call, n_reads, want_found):

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <sstream>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/crass_b200.h"
@@ -92,7 +93,11 @@ struct crass_b200_ctx {
     uint32_t res_n_reads = 0, res_max_len = 0;
     uint64_t res_n_bases = 0;
     bool res_valid = false, res_found_valid = false;
-    DevBuf d_found_p1, d_cand;
+    DevBuf d_found_p1, d_cand, d_tokens;
+    // K4 token output of the next dr_search launches (crass_b200_ctx_set_token_output / host forms)
+    uint8_t* tok_ptr = nullptr;
+    uint32_t tok_stride = 0;
+    std::string last_dr_list;
 };
 
 namespace cbh {
@@ -157,7 +162,7 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->d_bases, &c->d_offsets, &c->d_found, &c->d_skip, &c->d_hits, &c->d_pool, &c->d_counters,
-                      &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv, &c->d_found_p1, &c->d_cand};
+                      &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv, &c->d_found_p1, &c->d_cand, &c->d_tokens};
     for (DevBuf* b : bufs) b->release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     cudaStreamDestroy(c->stream);
@@ -167,6 +172,13 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
 int crass_b200_ctx_device(const crass_b200_ctx* c) { return c ? c->device : -1; }
 uint64_t crass_b200_ctx_launch_count(const crass_b200_ctx* c) { return c ? c->launches : 0; }
 uint64_t crass_b200_ctx_last_candidates(const crass_b200_ctx* c) { return c ? c->last_candidates : 0; }
+int crass_b200_ctx_set_token_output(crass_b200_ctx* c, void* d_tokens, uint32_t stride) {
+    if (!c) return cbh::fail(CRASS_B200_EINVAL, "ctx is NULL");
+    if (d_tokens && stride < 8) return cbh::fail(CRASS_B200_EINVAL, "token stride too small");
+    c->tok_ptr = (uint8_t*)d_tokens; c->tok_stride = d_tokens ? stride : 0;
+    return 0;
+}
+const char* crass_b200_ctx_last_dr_list(const crass_b200_ctx* c) { return c ? c->last_dr_list.c_str() : ""; }
 
 // ---- K1 ------------------------------------------------------------------------------------------------
 int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
@@ -182,7 +194,8 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
     if (n_reads == 0) return 0;
     if (int r = c->d_error.reserve(sizeof(int))) return r;
     CUDA_TRY(cudaMemsetAsync(c->d_error.p, 0, sizeof(int), st));
-    cbk::HitSink sink{d_hits, hits_cap, d_ss_pool, ss_cap, d_counters};
+    if (c->tok_ptr && c->tok_stride < params->high_dr + 2) return cbh::fail(CRASS_B200_EINVAL, "token stride must be at least high_dr + 2");
+    cbk::HitSink sink{d_hits, hits_cap, d_ss_pool, ss_cap, d_counters, c->tok_ptr, c->tok_stride};
     const uint32_t cap = cb::ss_capacity(o, max_read_len);
     const int threads = 128;
     // Fast path: 2-bit seed filter over every read + exact search on the few candidates.  Needs the default
@@ -235,7 +248,7 @@ namespace {
 // overflows, then bring the hits back sorted by read index.
 template <class Launch>
 int run_with_outputs(crass_b200_ctx* c, uint32_t n_reads, uint64_t n_bases, uint8_t* found_host, Launch launch,
-                     crass_b200_hit** hits, uint32_t* n_hits, uint32_t** ss_pool, uint32_t* n_ss_pool) {
+                     crass_b200_hit** hits, uint32_t* n_hits, uint32_t** ss_pool, uint32_t* n_ss_pool, uint32_t token_stride = 0) {
     uint32_t hits_cap = std::max<uint32_t>(4096, n_reads / 4 + 16);
     uint32_t pool_cap = hits_cap * 6;
     if (int r = c->d_counters.reserve(8 * sizeof(uint32_t))) return r;
@@ -243,7 +256,13 @@ int run_with_outputs(crass_b200_ctx* c, uint32_t n_reads, uint64_t n_bases, uint
     for (int attempt = 0; attempt < 3; ++attempt) {
         if (int r = c->d_hits.reserve((size_t)hits_cap * sizeof(crass_b200_hit))) return r;
         if (int r = c->d_pool.reserve((size_t)pool_cap * sizeof(uint32_t))) return r;
-        if (int r = launch(hits_cap, pool_cap)) return r;
+        if (token_stride) {
+            if (int r = c->d_tokens.reserve((size_t)hits_cap * token_stride)) return r;
+            c->tok_ptr = c->d_tokens.as<uint8_t>(); c->tok_stride = token_stride;
+        }
+        const int lr = launch(hits_cap, pool_cap);
+        if (token_stride) { c->tok_ptr = nullptr; c->tok_stride = 0; }
+        if (lr) return lr;
         CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->d_counters.p, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         if (!c->h_counters[2]) break;
@@ -265,7 +284,25 @@ int run_with_outputs(crass_b200_ctx* c, uint32_t n_reads, uint64_t n_bases, uint
     if (nh) CUDA_TRY(cudaMemcpyAsync(h, c->d_hits.p, sizeof(crass_b200_hit) * (size_t)nh, cudaMemcpyDeviceToHost, c->stream));
     if (np) CUDA_TRY(cudaMemcpyAsync(p, c->d_pool.p, sizeof(uint32_t) * (size_t)np, cudaMemcpyDeviceToHost, c->stream));
     if (found_host) CUDA_TRY(cudaMemcpyAsync(found_host, c->d_found.p, n_reads, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<uint8_t> tok;
+    if (token_stride && nh) {
+        tok.resize((size_t)nh * token_stride);
+        CUDA_TRY(cudaMemcpyAsync(tok.data(), c->d_tokens.p, tok.size(), cudaMemcpyDeviceToHost, c->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (token_stride) {
+        // distinct tokens in read order (== first-appearance order of a sequential run)
+        std::vector<uint32_t> order(nh);
+        for (uint32_t i = 0; i < nh; ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h[a].read_index < h[b].read_index; });
+        c->last_dr_list.clear();
+        std::unordered_set<std::string> seen;
+        for (uint32_t i = 0; i < nh; ++i) {
+            const uint8_t* rec = tok.data() + (size_t)order[i] * token_stride;
+            std::string t((const char*)rec + 2, rec[0]);
+            if (seen.insert(t).second) { c->last_dr_list += t; c->last_dr_list += '\n'; }
+        }
+    }
     std::sort(h, h + nh, [](const crass_b200_hit& a, const crass_b200_hit& b) { return a.read_index < b.read_index; });
     *hits = h; *n_hits = nh; *ss_pool = p; *n_ss_pool = np;
     (void)n_bases;
@@ -334,7 +371,8 @@ int crass_b200_dr_search_resident(crass_b200_ctx* c, const crass_b200_params* pa
                                         c->d_found.as<uint8_t>(), c->d_hits.as<crass_b200_hit>(), hits_cap,
                                         c->d_pool.as<uint32_t>(), pool_cap, c->d_counters.as<uint32_t>(), c->stream);
     };
-    if (int r = run_with_outputs(c, n_reads, c->res_n_bases, found, launch, hits, n_hits, ss_pool, n_ss_pool)) return r;
+    const uint32_t tstride = (params->high_dr + 2 + 15) & ~15u;
+    if (int r = run_with_outputs(c, n_reads, c->res_n_bases, found, launch, hits, n_hits, ss_pool, n_ss_pool, tstride)) return r;
     if (int r = c->d_found_p1.reserve((size_t)n_reads + 16)) return r;
     if (n_reads) CUDA_TRY(cudaMemcpyAsync(c->d_found_p1.p, c->d_found.p, n_reads, cudaMemcpyDeviceToDevice, c->stream));
     c->res_found_valid = true;
@@ -396,7 +434,7 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
     cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
     CUDA_TRY(cudaMemsetAsync(d_counters, 0, 4 * sizeof(uint32_t), st));
     if (n_reads == 0) return 0;
-    cbk::HitSink sink{d_hits, hits_cap, d_ss_pool, ss_cap, d_counters};
+    cbk::HitSink sink{d_hits, hits_cap, d_ss_pool, ss_cap, d_counters, nullptr, 0};
     uint32_t stride_log2 = 0;
     while ((1u << stride_log2) < ac->a.stride) ++stride_log2;
     // Fast path: 16-mer q-gram filter over every read + automaton walk over the few candidates.

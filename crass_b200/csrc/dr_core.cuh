@@ -214,11 +214,53 @@ CB_HD_NOINLINE int osa_distance(const Seq& s, uint32_t a0, uint32_t n, uint32_t 
     return (int)prev[m];
 }
 
+// Bit-parallel form of the same distance (Hyyro's Damerau bit-vector recurrence, one 64-bit column per text byte)
+// for the common case: both strings upper-case A/C/G/T only and the row string at most 64 long.  The reference's
+// transposition term is D[i-2][j-2] + 1 + [a(i-1) != b(j)] + [a(i) != b(j-1)], which can only improve a cell when both
+// cross comparisons match, i.e. it is the restricted (OSA) transposition; the guard i > 2 && j > 2 clears the
+// transposition bits of row 2 and of column 2.  Returns -1 when the fast form does not apply (caller falls back).
+template <class Seq>
+CB_HD int osa_distance_bitpar(const Seq& s, uint32_t a0, uint32_t n, uint32_t b0, uint32_t m) {
+    if (n == 0 || m == 0 || n > 64) return -1;
+    uint64_t peq[4] = {0, 0, 0, 0};
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint8_t c = s[a0 + i];
+        if (c != 'A' && c != 'C' && c != 'G' && c != 'T') return -1;
+        peq[(c >> 1) & 3] |= 1ull << i;
+    }
+    const uint64_t top = 1ull << (n - 1);
+    uint64_t vp = n == 64 ? ~0ull : ((1ull << n) - 1ull), vn = 0, d0 = 0, pm_prev = 0;
+    int score = (int)n;
+    for (uint32_t j = 0; j < m; ++j) {
+        const uint8_t c = s[b0 + j];
+        if (c != 'A' && c != 'C' && c != 'G' && c != 'T') return -1;
+        const uint64_t pm = peq[(c >> 1) & 3];
+        uint64_t tr = ((((~d0) & pm) << 1) & pm_prev) & ~3ull;          // rows 1 and 2 never transpose
+        if (j < 2) tr = 0;                                              // columns 1 and 2 never transpose
+        d0 = (((pm & vp) + vp) ^ vp) | pm | vn | tr;
+        const uint64_t hp = vn | ~(d0 | vp);
+        const uint64_t hn = d0 & vp;
+        score += (hp & top) ? 1 : 0;
+        score -= (hn & top) ? 1 : 0;
+        const uint64_t x = (hp << 1) | 1ull;
+        vp = (hn << 1) | ~(d0 | x);
+        vn = d0 & x;
+        pm_prev = pm;
+    }
+    return score;
+}
+
+template <class Seq>
+CB_HD int edit_distance(const Seq& s, uint32_t a0, uint32_t n, uint32_t b0, uint32_t m) {
+    const int fast = osa_distance_bitpar(s, a0, n, b0, m);
+    return fast >= 0 ? fast : osa_distance(s, a0, n, b0, m);
+}
+
 template <class Seq>
 CB_HD float similarity(const Seq& s, uint32_t a0, uint32_t n, uint32_t b0, uint32_t m) {
     if (n < 3 || m < 3) return 0.0f;
     float max_length = (float)(n > m ? n : m);
-    float d = (float)osa_distance(s, a0, n, b0, m);
+    float d = (float)edit_distance(s, a0, n, b0, m);
     return one_minus(f_div(d, max_length));
 }
 

@@ -5,8 +5,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <sstream>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "internal.h"
@@ -224,9 +226,11 @@ char* crass_b200_results_dump(crass_b200_results* r, int max_read_len) {
 char* crass_b200_dr_list_from_hits(const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, const crass_b200_hit* hits,
                                    uint32_t n_hits, const uint32_t* ss_pool) {
     if ((n_hits && (!bases || !offsets || !hits || !ss_pool))) { fail(CRASS_B200_EINVAL, "NULL argument"); return nullptr; }
-    std::map<std::string, bool> seen;
+    std::unordered_set<std::string> seen;
+    seen.reserve(4096);
     std::string out, rc;
     for (uint32_t k = 0; k < n_hits; ++k) {
+        if (k + 8 < n_hits) __builtin_prefetch(bases + offsets[hits[k + 8].read_index]);
         const crass_b200_hit& h = hits[k];
         if (h.read_index >= n_reads || h.n_ss < 2) { fail(CRASS_B200_EINVAL, "malformed hit"); return nullptr; }
         const uint8_t* s = bases + offsets[h.read_index];
@@ -248,7 +252,22 @@ char* crass_b200_dr_list_from_hits(const uint8_t* bases, const uint64_t* offsets
         rc.resize(ln);
         reverse_complement((const uint8_t*)dr.data(), ln, (uint8_t*)&rc[0]);
         const std::string& tok = dr < rc ? dr : rc;
-        if (seen.emplace(tok, true).second) { out += tok; out += '\n'; }
+        if (seen.insert(tok).second) { out += tok; out += '\n'; }
+    }
+    return dup_cstr(out);
+}
+
+char* crass_b200_dr_list_from_tokens(const uint8_t* records, uint32_t stride, const crass_b200_hit* hits, uint32_t n_hits) {
+    if (n_hits && (!records || !hits)) { fail(CRASS_B200_EINVAL, "NULL argument"); return nullptr; }
+    std::vector<uint32_t> order(n_hits);
+    for (uint32_t i = 0; i < n_hits; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hits[a].read_index < hits[b].read_index; });
+    std::unordered_set<std::string> seen;
+    std::string out;
+    for (uint32_t i = 0; i < n_hits; ++i) {
+        const uint8_t* rec = records + (size_t)order[i] * stride;
+        std::string t((const char*)rec + 2, rec[0]);
+        if (seen.insert(t).second) { out += t; out += '\n'; }
     }
     return dup_cstr(out);
 }

@@ -123,26 +123,76 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
     // (1) greedy k-mer clustering in token order.  A DR joins the first group that reaches min_count shared
     //     11-mers while walking its k-mers left to right (the test is only made from a group's second hit on);
     //     otherwise it founds a new group.  K-mers never seen before are then given to the chosen group.
-    std::unordered_map<std::string, int> kmer_group;
+    //     K-mers made of A/C/G/T only (practically all of them) are handled as 22-bit integers: with A<C<G<T packed
+    //     big-endian, min(forward, reverse complement) as numbers is the lexicographic minimum laurenize() takes.
+    //     Anything else goes through the string map; the two key spaces cannot collide because the canonical form of
+    //     a k-mer is routed by its own bytes.
+    std::unordered_map<std::string, int> kmer_group_str;
+    size_t total_kmers = 0;
+    for (const std::string& d : drs) if (d.size() >= kClusterKmer) total_kmers += d.size() - kClusterKmer + 1;
+    size_t tsize = 1024;
+    while (tsize < total_kmers * 2 + 16) tsize <<= 1;
+    std::vector<uint32_t> tkey(tsize, 0xFFFFFFFFu);
+    std::vector<int> tval(tsize, 0);
+    auto slot_of = [&](uint32_t key) {
+        size_t s = (size_t)(key * 0x9E3779B1u) & (tsize - 1);
+        while (tkey[s] != 0xFFFFFFFFu && tkey[s] != key) s = (s + 1) & (tsize - 1);
+        return s;
+    };
+    static const int8_t kCode[256] = {
+#define X4 -1, -1, -1, -1
+#define X16 X4, X4, X4, X4
+        X16, X16, X16, X16,
+        -1, 0, -1, 1, -1, -1, -1, 2, X4, X4, -1, -1, -1, -1, 3, -1, -1, -1, X4, X4,     // 'A'=65 'C'=67 'G'=71 'T'=84
+        X16, X16, X16, X16, X16, X16, X16, X16, X16, X16
+#undef X16
+#undef X4
+    };
     std::vector<std::vector<int> > members;                               // group id - 1 -> tokens
+    std::vector<uint32_t> unseen_int;
+    std::vector<std::string> unseen_str;
+    std::vector<std::pair<int, int> > counts;                             // (group, shared so far)
     for (size_t t = 0; t < drs.size(); ++t) {
         const std::string& dr = drs[t];
         const long n_mers = (long)dr.size() - (long)kClusterKmer + 1;
-        std::vector<std::string> unseen;
-        std::vector<std::pair<int, int> > counts;                         // (group, shared so far)
+        unseen_int.clear(); unseen_str.clear(); counts.clear();
         int group = 0;
-        for (long i = 0; i < n_mers; ++i) {
-            std::string km = low_lexi_kmer(dr, (size_t)i);
-            auto it = kmer_group.find(km);
-            if (it == kmer_group.end()) { unseen.push_back(km); continue; }
-            if (group) continue;
-            auto c = std::find_if(counts.begin(), counts.end(), [&](const std::pair<int, int>& p) { return p.first == it->second; });
-            if (c == counts.end()) counts.push_back(std::make_pair(it->second, 1));
-            else if (++c->second >= min_count) group = it->second;
+        uint32_t fw = 0, rc = 0;
+        int valid = 0;                                                   // trailing run of A/C/G/T bytes
+        const uint32_t kmask = (1u << (2 * kClusterKmer)) - 1u;
+        for (long p = 0; p < (long)dr.size(); ++p) {
+            const int c = kCode[(uint8_t)dr[(size_t)p]];
+            if (c < 0) valid = 0;
+            else { valid++; fw = ((fw << 2) | (uint32_t)c) & kmask; rc = (rc >> 2) | ((uint32_t)(3 - c) << (2 * (kClusterKmer - 1))); }
+            const long i = p - (long)kClusterKmer + 1;                    // k-mer start
+            if (i < 0 || i >= n_mers) continue;
+            int known = 0;                                               // group of this k-mer, 0 = never seen
+            if (valid >= (int)kClusterKmer) {
+                const uint32_t key = fw < rc ? fw : rc;
+                const size_t s = slot_of(key);
+                if (tkey[s] == key) known = tval[s]; else unseen_int.push_back(key);
+            } else {
+                std::string km = low_lexi_kmer(dr, (size_t)i);
+                bool acgt = true;
+                uint32_t key = 0;
+                for (char ch : km) { const int c2 = kCode[(uint8_t)ch]; if (c2 < 0) { acgt = false; break; } key = (key << 2) | (uint32_t)c2; }
+                if (acgt) {                                              // e.g. a 'U' whose reverse complement is all A/C/G/T
+                    const size_t s = slot_of(key);
+                    if (tkey[s] == key) known = tval[s]; else unseen_int.push_back(key);
+                } else {
+                    auto it = kmer_group_str.find(km);
+                    if (it != kmer_group_str.end()) known = it->second; else unseen_str.push_back(km);
+                }
+            }
+            if (!known || group) continue;
+            auto c2 = std::find_if(counts.begin(), counts.end(), [&](const std::pair<int, int>& q) { return q.first == known; });
+            if (c2 == counts.end()) counts.push_back(std::make_pair(known, 1));
+            else if (++c2->second >= min_count) group = known;
         }
         if (!group) { members.emplace_back(); group = (int)members.size(); }
         members[group - 1].push_back((int)t + 2);
-        for (const std::string& km : unseen) kmer_group[km] = group;
+        for (uint32_t key : unseen_int) { const size_t s = slot_of(key); tkey[s] = key; tval[s] = group; }
+        for (const std::string& km : unseen_str) kmer_group_str[km] = group;
     }
     // (2) per group: drop every variant that contains a shorter surviving variant (either strand), then emit
     //     the survivors followed by their reverse complements.
@@ -157,8 +207,13 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
         std::vector<bool> dead(v.size(), false);
         for (size_t i = 0; i < v.size(); ++i) {
             if (dead[i] || v[i].empty()) continue;
-            for (size_t j = i + 1; j < v.size(); ++j)
-                if (!dead[j] && !v[j].empty() && contains_either_strand(v[j], v[i])) dead[j] = true;
+            const std::string rc = reverse_complement(v[i]);
+            for (size_t j = i + 1; j < v.size(); ++j) {
+                if (dead[j] || v[j].empty()) continue;
+                if (v[j].size() == v[i].size()) {                         // same length: containment is equality
+                    if (v[j] == v[i] || v[j] == rc) dead[j] = true;
+                } else if (v[j].find(v[i]) != std::string::npos || v[j].find(rc) != std::string::npos) dead[j] = true;
+            }
         }
         const size_t first = out.size();
         for (size_t i = 0; i < v.size(); ++i) if (!dead[i] && !v[i].empty()) out.push_back(v[i]);

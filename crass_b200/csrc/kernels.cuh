@@ -22,6 +22,8 @@ struct HitSink {
     uint32_t* pool;
     uint32_t pool_cap;
     uint32_t* counters;      // [0] hits, [1] pool entries, [2] overflow flag, [3] exact-path reads
+    uint8_t* tokens;         // optional: one DR token record per hit slot (K4), NULL = off
+    uint32_t token_stride;
 };
 
 // global-memory byte accessor through the read-only path
@@ -30,7 +32,7 @@ struct GmemSeq {
     __device__ __forceinline__ uint8_t operator[](uint32_t i) const { return __ldg(p + i); }
 };
 
-__device__ __forceinline__ void emit_hit(const HitSink& sink, uint32_t read_index, const uint32_t* ss, uint32_t n_ss, uint32_t replen) {
+__device__ __forceinline__ uint32_t emit_hit(const HitSink& sink, uint32_t read_index, const uint32_t* ss, uint32_t n_ss, uint32_t replen) {
     const uint32_t slot = atomicAdd(&sink.counters[0], 1u);
     const uint32_t off = atomicAdd(&sink.counters[1], n_ss);
     if (slot < sink.hits_cap && off + n_ss <= sink.pool_cap) {
@@ -38,9 +40,44 @@ __device__ __forceinline__ void emit_hit(const HitSink& sink, uint32_t read_inde
         h.read_index = read_index; h.n_ss = n_ss; h.ss_offset = off; h.repeat_len = replen;
         sink.hits[slot] = h;
         for (uint32_t i = 0; i < n_ss; ++i) sink.pool[off + i] = ss[i];
-    } else {
-        sink.counters[2] = 1u;
+        return slot;
     }
+    sink.counters[2] = 1u;
+    return 0xFFFFFFFFu;
+}
+
+// ---- K4: the low-lexi DR token of a hit (ReadHolder::DRLowLexi, ReadHolder.cpp:513-591), computed where the hit is
+// found so that the multi-GPU merge / pattern-set construction never has to touch the reads on the host.
+// Record layout (stride bytes): [0] length, [1] 1 = read kept its orientation (RH_WasLowLexi), [2..] the token.
+__constant__ uint8_t c_comp_tab[128] = {                       // SeqUtils.cpp:51-60
+    0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31,
+    32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 63,
+    64, 'T', 'V', 'G', 'H', 'E', 'F', 'C', 'D', 'I', 'J', 'M', 'L', 'K', 'N', 'O', 'P', 'Q', 'Y', 'S', 'A', 'A', 'B', 'W', 'X', 'R', 'Z', 91, 92, 93, 94, 95,
+    64, 't', 'v', 'g', 'h', 'e', 'f', 'c', 'd', 'i', 'j', 'm', 'l', 'k', 'n', 'o', 'p', 'q', 'y', 's', 'a', 'a', 'b', 'w', 'x', 'r', 'z', 123, 124, 125, 126, 127};
+
+template <class Seq>
+__device__ __noinline__ void emit_token(uint8_t* __restrict__ rec, uint32_t stride, const Seq& s, uint32_t L, const uint32_t* ss, uint32_t n_ss) {
+    const uint32_t n_rep = n_ss / 2;
+    uint32_t idx;
+    if (n_rep == 1) idx = 0;
+    else if (n_rep == 2) {
+        if (ss[0] == 0) idx = 2;
+        else if (ss[3] == L) idx = 0;
+        else idx = ((int)(ss[1] - ss[0]) > (int)(ss[3] - ss[2])) ? 0 : 2;
+    } else idx = 2;
+    uint32_t st = ss[idx], ln = ss[idx + 1] - ss[idx] + 1;
+    if (st > L) st = L;
+    if (ln > L - st) ln = L - st;
+    if (ln > stride - 2) ln = stride - 2;                        // cannot happen: stride >= high_dr + 2
+    // forward < reverse complement ?  (std::string operator<, unsigned bytes; equal -> take the reverse complement)
+    bool fwd_less = false;
+    for (uint32_t i = 0; i < ln; ++i) {
+        const uint8_t a = s[st + i], b = c_comp_tab[s[st + ln - 1 - i] & 127];
+        if (a != b) { fwd_less = a < b; break; }
+    }
+    rec[0] = (uint8_t)ln;
+    rec[1] = fwd_less ? 1 : 0;
+    for (uint32_t i = 0; i < ln; ++i) rec[2 + i] = fwd_less ? s[st + i] : c_comp_tab[s[st + ln - 1 - i] & 127];
 }
 
 // ---- K1 generic --------------------------------------------------------------------------------------
@@ -64,7 +101,10 @@ k_dr_search_generic(const uint8_t* __restrict__ bases, const uint64_t* __restric
         const int f = cb::search_core(s, L, o, ss, cap, n_ss, replen);
         if (f < 0) *error_flag = f;
         if (found) found[r] = (f == 1);
-        if (f == 1) emit_hit(sink, r, ss, n_ss, replen);
+        if (f == 1) {
+            const uint32_t slot = emit_hit(sink, r, ss, n_ss, replen);
+            if (sink.tokens && slot != 0xFFFFFFFFu) emit_token(sink.tokens + (size_t)slot * sink.token_stride, sink.token_stride, s, L, ss, n_ss);
+        }
     }
 }
 
@@ -179,7 +219,11 @@ k_dr_exact_packed(const uint8_t* __restrict__ bases, const uint64_t* __restrict_
         uint32_t n_ss = 0, replen = 0;
         const int f = cb::search_core_packed<NW, NWIN, DMIN, DMAX>(s, L, o, S, cb::flag_mask<NWIN>(acc), ss, 32u, n_ss, replen);
         if (f < 0) *error_flag = f;
-        if (f == 1) { found[r] = 1; emit_hit(sink, r, ss, n_ss, replen); }
+        if (f == 1) {
+            found[r] = 1;
+            const uint32_t slot = emit_hit(sink, r, ss, n_ss, replen);
+            if (sink.tokens && slot != 0xFFFFFFFFu) emit_token(sink.tokens + (size_t)slot * sink.token_stride, sink.token_stride, s, L, ss, n_ss);
+        }
     }
 }
 
@@ -354,7 +398,7 @@ k_edit_distance(const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ 
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pairs) return;
     GmemSeq s{bytes};
-    out_dist[i] = cb::osa_distance(s, a_off[i], a_len[i], b_off[i], b_len[i]);
+    out_dist[i] = cb::edit_distance(s, a_off[i], a_len[i], b_off[i], b_len[i]);
     out_sim[i] = cb::similarity(s, a_off[i], a_len[i], b_off[i], b_len[i]);
 }
 

@@ -90,6 +90,14 @@ uint64_t crass_b200_ctx_launch_count(const crass_b200_ctx* ctx);
 /* number of reads the most recent host-form search/scan sent to the exact (candidate) path; equals the number
  * of reads when the generic kernels ran */
 uint64_t crass_b200_ctx_last_candidates(const crass_b200_ctx* ctx);
+/* K4: make the following crass_b200_dr_search_dev launches also write, for the hit stored in slot k of d_hits, its
+ * low-lexi DR token (ReadHolder::DRLowLexi) to d_tokens + k*stride: byte 0 = length, byte 1 = 1 if the read keeps its
+ * orientation, bytes 2.. = the token.  stride >= high_dr + 2.  NULL switches it off. */
+int crass_b200_ctx_set_token_output(crass_b200_ctx* ctx, void* d_tokens, uint32_t stride);
+/* the distinct tokens of the most recent crass_b200_dr_search_resident in read order, '\n'-separated (owned by ctx) */
+const char* crass_b200_ctx_last_dr_list(const crass_b200_ctx* ctx);
+/* the same list from token records copied back by the caller: records[k] belongs to hits[k] (unsorted, as on the device) */
+char* crass_b200_dr_list_from_tokens(const uint8_t* records, uint32_t stride, const crass_b200_hit* hits, uint32_t n_hits);
 
 /* ---- phase 1: direct-repeat search (kernel K1) -------------------------------------------------
  * Device-resident form.  Outputs (all device memory, caller-allocated):

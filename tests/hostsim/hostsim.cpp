@@ -59,7 +59,7 @@ int hs_edit_distance(const uint8_t* a, uint32_t la, const uint8_t* b, uint32_t l
     buf.insert(buf.end(), b, b + lb);
     buf.push_back(0);
     PtrSeq s{buf.data()};
-    return osa_distance(s, 0, la, la, lb);
+    return edit_distance(s, 0, la, la, lb);
 }
 
 float hs_similarity(const uint8_t* a, uint32_t la, const uint8_t* b, uint32_t lb) {

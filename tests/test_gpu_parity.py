@@ -239,6 +239,24 @@ def test_synthetic_config2_prefix(ctx, P, k1path):
         assert got[int(i)] == (ss, rl)
 
 
+def test_device_dr_tokens_match_host_lowlexi(ctx, k1path):
+    """K4: the low-lexi DR token written next to every hit on the device == ReadHolder::DRLowLexi replayed on the host
+    (which test_host_logic pins against the reference), including first-appearance order of the distinct tokens."""
+    rng = random.Random(106)
+    reads = [fuzzgen.planted_read(rng, rng.choice([100, 150, 150, 250]), sub_rate=rng.choice([0, 0.01])) for _ in range(6000)]
+    reads += [fuzzgen.mutate(rng, r, 0.01, b"NnacgtRYU") for r in reads[:1500]]
+    bases, offs = cb.pack_reads(reads)
+    ctx.upload(bases, offs)
+    hits, pool, _ = ctx.dr_search_resident(cb.Params())
+    assert len(hits) > 2000
+    want = api.dr_list_from_hits(bases, offs, hits, pool)
+    assert ctx.last_dr_list() == want
+    batch = cb.Batch.from_arrays(bases, offs)
+    res = cb.Results()
+    res.add_phase1(batch, hits, pool)
+    assert res.dr_list() == want
+
+
 def test_singleton_scan_fuzz(ctx, P, k2path):
     rng = random.Random(105)
     for n_pat in (1, 7, 100, 1500, 12000):
