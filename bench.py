@@ -213,14 +213,25 @@ def main():
     d_tokens = torch.empty(hits_cap * TOK, dtype=torch.uint8, device=dev)
     host_ms = {"fetch": [], "dr_list": [], "merge": [], "cluster": [], "ac_build": []}
 
-    def fetch_hits(with_tokens=False):
-        h_cnt.copy_(d_cnt, non_blocking=False)
+    d_utok = torch.empty(hits_cap * TOK, dtype=torch.uint8, device=dev)
+    d_ufr = torch.empty(hits_cap, dtype=torch.int32, device=dev)
+    d_ucnt = torch.zeros(4, dtype=torch.int32, device=dev)
+    h_hits = [torch.empty(hits_cap * 4, dtype=torch.int32, pin_memory=True) for _ in range(2)]
+    h_pool = [torch.empty(pool_cap, dtype=torch.int32, pin_memory=True) for _ in range(2)]
+
+    def read_counters():
+        h_cnt.copy_(d_cnt, non_blocking=False)                         # 32 bytes, synchronises the stream
         nh, npool, ovf = int(h_cnt[0]), int(h_cnt[1]), int(h_cnt[2])
         assert not ovf, "bench hit buffers overflowed"
-        hits = d_hits[: nh * 4].cpu().numpy().view(api.HIT_DTYPE)
-        pool = d_pool[: max(npool, 1)].cpu().numpy().view(np.uint32)
-        toks = d_tokens[: max(nh, 1) * TOK].cpu().numpy() if with_tokens else None
-        return hits, pool, toks                                        # device order (unsorted); consumers sort by read index
+        return nh, npool
+
+    def fetch_hits_async(which, nh, npool):
+        """hit records -> pinned host memory, asynchronously on the work stream (device order; consumers sort by read index)"""
+        h_hits[which][: nh * 4].copy_(d_hits[: nh * 4], non_blocking=True)
+        h_pool[which][: max(npool, 1)].copy_(d_pool[: max(npool, 1)], non_blocking=True)
+
+    def host_hits(which, nh, npool):
+        return h_hits[which][: nh * 4].numpy().view(api.HIT_DTYPE), h_pool[which][: max(npool, 1)].numpy().view(np.uint32)
 
     def merge_dr_lists(local):
         if world == 1:
@@ -248,9 +259,14 @@ def main():
         ctx.set_token_output(None)
         e[1].record()
         t0 = time.perf_counter()
-        hits, pool, toks = fetch_hits(with_tokens=True)
+        nh, npool = read_counters()
+        ctx.unique_tokens_dev(d_hits, nh, d_tokens, TOK, d_utok, d_ufr, d_ucnt, stream)   # K4b: distinct tokens + first read
+        fetch_hits_async(0, nh, npool)                                 # the phase-1 hit records travel while the host clusters
+        nu = int(d_ucnt[:1].cpu()[0])
+        utok = d_utok[: max(nu, 1) * TOK].cpu().numpy()
+        ufr = d_ufr[: max(nu, 1)].cpu().numpy().view(np.uint32)[:nu]
         t1 = time.perf_counter()
-        local = api.dr_list_from_tokens(toks, TOK, hits)               # distinct low-lexi DRs, first-appearance order
+        local = api.dr_list_from_unique(utok, TOK, ufr)                # distinct low-lexi DRs in first-appearance order
         t2 = time.perf_counter()
         merged = merge_dr_lists(local)
         t3 = time.perf_counter()
@@ -263,9 +279,10 @@ def main():
             e[2].record()
             ctx.ac_scan_dev(ac, d_bases, d_offsets, n, READ_LEN, d_found, d_found2, d_hits, d_pool, d_cnt, stream)
             e[3].record()
-            hits2, pool2, _ = fetch_hits()
-            n2 = len(hits2)
-        torch.cuda.synchronize()
+            n2, npool2 = read_counters()
+            fetch_hits_async(1, n2, npool2)
+        torch.cuda.synchronize()                                       # both hit lists are on the host now
+        hits, pool = host_hits(0, nh, npool)
         if record:
             kt["k1"].append(e[0].elapsed_time(e[1]))
             if pats:

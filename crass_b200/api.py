@@ -71,6 +71,8 @@ def lib():
         "crass_b200_ctx_set_token_output": (C.c_int, [vp, vp, C.c_uint32]),
         "crass_b200_ctx_last_dr_list": (cp, [vp]),
         "crass_b200_dr_list_from_tokens": (vp, [vp, C.c_uint32, vp, C.c_uint32]),
+        "crass_b200_unique_tokens_dev": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp]),
+        "crass_b200_dr_list_from_unique": (vp, [vp, C.c_uint32, vp, C.c_uint32]),
         "crass_b200_dr_search_dev": (C.c_int, [vp, vp, vp, C.c_uint32, C.c_uint32, C.POINTER(Params), vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp]),
         "crass_b200_dr_search": (C.c_int, [vp, vp, vp, C.c_uint32, C.POINTER(Params), vp, C.POINTER(vp), u32p, C.POINTER(vp), u32p]),
         "crass_b200_batch_upload": (C.c_int, [vp, vp, vp, C.c_uint32]),
@@ -320,6 +322,12 @@ def dr_list_from_tokens(records, stride, hits):
     return [x for x in s.split(b"\n") if x]
 
 
+def dr_list_from_unique(records, stride, first_read):
+    """records/first_read: the outputs of Context.unique_tokens_dev copied to numpy -> DRs in first-appearance order."""
+    s = _take_str(lib().crass_b200_dr_list_from_unique(_np_ptr(records), stride, _np_ptr(first_read), len(first_read)))
+    return [x for x in s.split(b"\n") if x]
+
+
 def merge_dr_lists(drs):
     s = _take_str(lib().crass_b200_merge_dr_lists(b"".join(d + b"\n" for d in drs)))
     return [x for x in s.split(b"\n") if x]
@@ -363,6 +371,11 @@ class Context:
     def set_token_output(self, d_tokens, stride=64):
         """K4: let dr_search_dev also write the low-lexi DR token of every hit (torch uint8 tensor, stride bytes per hit slot)."""
         _check(lib().crass_b200_ctx_set_token_output(self.h, d_tokens.data_ptr() if d_tokens is not None else None, stride))
+
+    def unique_tokens_dev(self, d_hits, n_hits, d_tokens, stride, d_out_tokens, d_out_first_read, d_out_count, stream=0):
+        """K4b: device-side de-duplication of the token records of the first n_hits hit slots (torch tensors)."""
+        _check(lib().crass_b200_unique_tokens_dev(self.h, d_hits.data_ptr(), n_hits, d_tokens.data_ptr(), stride, d_out_tokens.data_ptr(),
+                                                  d_out_first_read.data_ptr(), d_out_count.data_ptr(), stream))
 
     def last_dr_list(self):
         s = lib().crass_b200_ctx_last_dr_list(self.h)

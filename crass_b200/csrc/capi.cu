@@ -93,7 +93,7 @@ struct crass_b200_ctx {
     uint32_t res_n_reads = 0, res_max_len = 0;
     uint64_t res_n_bases = 0;
     bool res_valid = false, res_found_valid = false;
-    DevBuf d_found_p1, d_cand, d_tokens;
+    DevBuf d_found_p1, d_cand, d_tokens, d_tok_table, d_tok_unique;
     // K4 token output of the next dr_search launches (crass_b200_ctx_set_token_output / host forms)
     uint8_t* tok_ptr = nullptr;
     uint32_t tok_stride = 0;
@@ -162,7 +162,7 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->d_bases, &c->d_offsets, &c->d_found, &c->d_skip, &c->d_hits, &c->d_pool, &c->d_counters,
-                      &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv, &c->d_found_p1, &c->d_cand, &c->d_tokens};
+                      &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv, &c->d_found_p1, &c->d_cand, &c->d_tokens, &c->d_tok_table, &c->d_tok_unique};
     for (DevBuf* b : bufs) b->release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     cudaStreamDestroy(c->stream);
@@ -179,6 +179,29 @@ int crass_b200_ctx_set_token_output(crass_b200_ctx* c, void* d_tokens, uint32_t 
     return 0;
 }
 const char* crass_b200_ctx_last_dr_list(const crass_b200_ctx* c) { return c ? c->last_dr_list.c_str() : ""; }
+
+int crass_b200_unique_tokens_dev(crass_b200_ctx* c, const crass_b200_hit* d_hits, uint32_t n_hits, const void* d_tokens, uint32_t stride,
+                                 void* d_out_tokens, uint32_t* d_out_first_read, uint32_t* d_out_count, void* stream_v) {
+    if (!c || !d_out_count) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    if (stride < 8 || (stride & 3)) return cbh::fail(CRASS_B200_EINVAL, "token stride must be a multiple of 4, at least 8");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
+    CUDA_TRY(cudaMemsetAsync(d_out_count, 0, sizeof(uint32_t), st));
+    if (n_hits == 0) return 0;
+    if (!d_hits || !d_tokens || !d_out_tokens || !d_out_first_read) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    uint32_t cap = 1024;
+    while (cap < 2u * n_hits) cap <<= 1;
+    if (int r = c->d_tok_table.reserve((size_t)cap * 2 * sizeof(uint32_t))) return r;
+    uint32_t* rep = c->d_tok_table.as<uint32_t>();
+    uint32_t* first_read = rep + cap;
+    CUDA_TRY(cudaMemsetAsync(rep, 0xFF, (size_t)cap * 2 * sizeof(uint32_t), st));
+    cbk::k_token_dedupe<<<(n_hits + 255) / 256, 256, 0, st>>>(d_hits, n_hits, (const uint8_t*)d_tokens, stride, rep, first_read, cap - 1);
+    cbk::k_token_compact<<<(cap + 255) / 256, 256, 0, st>>>(rep, first_read, cap, (const uint8_t*)d_tokens, stride, (uint8_t*)d_out_tokens,
+                                                           d_out_first_read, d_out_count);
+    c->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
 
 // ---- K1 ------------------------------------------------------------------------------------------------
 int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
@@ -284,25 +307,35 @@ int run_with_outputs(crass_b200_ctx* c, uint32_t n_reads, uint64_t n_bases, uint
     if (nh) CUDA_TRY(cudaMemcpyAsync(h, c->d_hits.p, sizeof(crass_b200_hit) * (size_t)nh, cudaMemcpyDeviceToHost, c->stream));
     if (np) CUDA_TRY(cudaMemcpyAsync(p, c->d_pool.p, sizeof(uint32_t) * (size_t)np, cudaMemcpyDeviceToHost, c->stream));
     if (found_host) CUDA_TRY(cudaMemcpyAsync(found_host, c->d_found.p, n_reads, cudaMemcpyDeviceToHost, c->stream));
-    std::vector<uint8_t> tok;
-    if (token_stride && nh) {
-        tok.resize((size_t)nh * token_stride);
-        CUDA_TRY(cudaMemcpyAsync(tok.data(), c->d_tokens.p, tok.size(), cudaMemcpyDeviceToHost, c->stream));
-    }
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (token_stride) {
-        // distinct tokens in read order (== first-appearance order of a sequential run)
-        std::vector<uint32_t> order(nh);
-        for (uint32_t i = 0; i < nh; ++i) order[i] = i;
-        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h[a].read_index < h[b].read_index; });
+        // K4b: distinct tokens + the first read that carries each, de-duplicated on the device; only those come back
         c->last_dr_list.clear();
-        std::unordered_set<std::string> seen;
-        for (uint32_t i = 0; i < nh; ++i) {
-            const uint8_t* rec = tok.data() + (size_t)order[i] * token_stride;
-            std::string t((const char*)rec + 2, rec[0]);
-            if (seen.insert(t).second) { c->last_dr_list += t; c->last_dr_list += '\n'; }
+        if (nh) {
+            const size_t rec_bytes = (size_t)nh * token_stride;
+            if (int r = c->d_tok_unique.reserve(rec_bytes + (size_t)nh * sizeof(uint32_t) + 16)) { free(h); free(p); return r; }
+            uint8_t* d_ut = c->d_tok_unique.as<uint8_t>();
+            uint32_t* d_fr = (uint32_t*)(d_ut + rec_bytes);
+            uint32_t* d_cnt = d_fr + nh;
+            if (int r = crass_b200_unique_tokens_dev(c, c->d_hits.as<crass_b200_hit>(), nh, c->d_tokens.p, token_stride, d_ut, d_fr, d_cnt, c->stream)) { free(h); free(p); return r; }
+            uint32_t nu = 0;
+            CUDA_TRY(cudaMemcpyAsync(&nu, d_cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            std::vector<uint8_t> ut((size_t)nu * token_stride);
+            std::vector<uint32_t> fr(nu);
+            CUDA_TRY(cudaMemcpyAsync(ut.data(), d_ut, ut.size(), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(fr.data(), d_fr, (size_t)nu * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            std::vector<uint32_t> order(nu);
+            for (uint32_t i = 0; i < nu; ++i) order[i] = i;
+            std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return fr[a] < fr[b]; });
+            for (uint32_t i = 0; i < nu; ++i) {
+                const uint8_t* rec = ut.data() + (size_t)order[i] * token_stride;
+                c->last_dr_list.append((const char*)rec + 2, rec[0]);
+                c->last_dr_list += '\n';
+            }
         }
     }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     std::sort(h, h + nh, [](const crass_b200_hit& a, const crass_b200_hit& b) { return a.read_index < b.read_index; });
     *hits = h; *n_hits = nh; *ss_pool = p; *n_ss_pool = np;
     (void)n_bases;

@@ -272,6 +272,20 @@ char* crass_b200_dr_list_from_tokens(const uint8_t* records, uint32_t stride, co
     return dup_cstr(out);
 }
 
+char* crass_b200_dr_list_from_unique(const uint8_t* records, uint32_t stride, const uint32_t* first_read, uint32_t n) {
+    if (n && (!records || !first_read)) { fail(CRASS_B200_EINVAL, "NULL argument"); return nullptr; }
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return first_read[a] < first_read[b]; });
+    std::string out;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint8_t* rec = records + (size_t)order[i] * stride;
+        out.append((const char*)rec + 2, rec[0]);
+        out += '\n';
+    }
+    return dup_cstr(out);
+}
+
 char* crass_b200_merge_dr_lists(const char* concatenated) {
     std::map<std::string, bool> seen;
     std::string out;

@@ -80,6 +80,54 @@ __device__ __noinline__ void emit_token(uint8_t* __restrict__ rec, uint32_t stri
     for (uint32_t i = 0; i < ln; ++i) rec[2 + i] = fwd_less ? s[st + i] : c_comp_tab[s[st + ln - 1 - i] & 127];
 }
 
+// ---- K4b: distinct DR tokens of a hit list, with the smallest read index that carries each --------------------
+// (what StringCheck::addString's first-appearance numbering needs).  Open-addressing table keyed by the token bytes:
+// rep[i] = hit slot of the first thread that claimed entry i, first_read[i] = min read index over all equal tokens.
+__device__ __forceinline__ uint32_t token_hash(const uint8_t* rec) {
+    uint32_t h = 2166136261u;
+    const uint32_t n = rec[0];
+    for (uint32_t i = 0; i < n; ++i) { h ^= rec[2 + i]; h *= 16777619u; }
+    return h ^ (h >> 15);
+}
+
+__device__ __forceinline__ bool token_equal(const uint8_t* a, const uint8_t* b) {
+    if (a[0] != b[0]) return false;
+    const uint32_t n = a[0];
+    for (uint32_t i = 0; i < n; ++i) if (a[2 + i] != b[2 + i]) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(256)
+k_token_dedupe(const crass_b200_hit* __restrict__ hits, uint32_t n_hits, const uint8_t* __restrict__ tokens, uint32_t stride,
+               uint32_t* __restrict__ rep, uint32_t* __restrict__ first_read, uint32_t table_mask) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_hits) return;
+    const uint8_t* mine = tokens + (size_t)k * stride;
+    const uint32_t read = hits[k].read_index;
+    uint32_t i = token_hash(mine) & table_mask;
+    for (;;) {
+        uint32_t cur = atomicCAS(&rep[i], 0xFFFFFFFFu, k);
+        if (cur == 0xFFFFFFFFu) cur = k;
+        if (cur == k || token_equal(mine, tokens + (size_t)cur * stride)) { atomicMin(&first_read[i], read); return; }
+        i = (i + 1) & table_mask;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_token_compact(const uint32_t* __restrict__ rep, const uint32_t* __restrict__ first_read, uint32_t table_size,
+                const uint8_t* __restrict__ tokens, uint32_t stride, uint8_t* __restrict__ out_tokens,
+                uint32_t* __restrict__ out_first_read, uint32_t* __restrict__ out_count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= table_size) return;
+    const uint32_t r = rep[i];
+    if (r == 0xFFFFFFFFu) return;
+    const uint32_t j = atomicAdd(out_count, 1u);
+    out_first_read[j] = first_read[i];
+    const uint8_t* src = tokens + (size_t)r * stride;
+    uint8_t* dst = out_tokens + (size_t)j * stride;
+    for (uint32_t b = 0; b < stride; b += 4) *reinterpret_cast<uint32_t*>(dst + b) = *reinterpret_cast<const uint32_t*>(src + b);
+}
+
 // ---- K1 generic --------------------------------------------------------------------------------------
 // LOCAL_SS > 0: the start/stop list lives in thread-local memory (short reads); otherwise in a slice of
 // ss_scratch (ss_cap entries per thread).

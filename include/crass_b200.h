@@ -96,6 +96,13 @@ uint64_t crass_b200_ctx_last_candidates(const crass_b200_ctx* ctx);
 int crass_b200_ctx_set_token_output(crass_b200_ctx* ctx, void* d_tokens, uint32_t stride);
 /* the distinct tokens of the most recent crass_b200_dr_search_resident in read order, '\n'-separated (owned by ctx) */
 const char* crass_b200_ctx_last_dr_list(const crass_b200_ctx* ctx);
+/* K4b: de-duplicate the token records of d_hits[0..n_hits) on the device.  Writes the distinct records to d_out_tokens
+ * (same stride), the smallest read index carrying each to d_out_first_read, and their number to d_out_count; all three
+ * must hold n_hits entries in the worst case.  Order is arbitrary: sort by first_read for first-appearance order
+ * (crass_b200_dr_list_from_unique does that on the host). */
+int crass_b200_unique_tokens_dev(crass_b200_ctx* ctx, const crass_b200_hit* d_hits, uint32_t n_hits, const void* d_tokens,
+                                 uint32_t stride, void* d_out_tokens, uint32_t* d_out_first_read, uint32_t* d_out_count, void* stream);
+char* crass_b200_dr_list_from_unique(const uint8_t* records, uint32_t stride, const uint32_t* first_read, uint32_t n);
 /* the same list from token records copied back by the caller: records[k] belongs to hits[k] (unsorted, as on the device) */
 char* crass_b200_dr_list_from_tokens(const uint8_t* records, uint32_t stride, const crass_b200_hit* hits, uint32_t n_hits);
 
