@@ -275,6 +275,7 @@ def main():
         n2 = 0
         if pats:
             ac = cb.Automaton(pats)
+            ctx.ac_upload(ac)
             t5 = time.perf_counter()
             e[2].record()
             ctx.ac_scan_dev(ac, d_bases, d_offsets, n, READ_LEN, d_found, d_found2, d_hits, d_pool, d_cnt, stream)

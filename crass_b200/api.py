@@ -82,6 +82,7 @@ def lib():
         "crass_b200_merge_dr_lists": (vp, [cp]),
         "crass_b200_ac_build": (C.c_int, [vp, vp, C.c_uint32, C.POINTER(vp)]),
         "crass_b200_ac_destroy": (None, [vp]),
+        "crass_b200_ac_upload": (C.c_int, [vp, vp]),
         "crass_b200_ac_num_states": (C.c_uint32, [vp]),
         "crass_b200_ac_num_symbols": (C.c_uint32, [vp]),
         "crass_b200_ac_table_bytes": (C.c_uint64, [vp]),
@@ -403,6 +404,9 @@ class Context:
         n = len(offsets) - 1
         return self._collect(lambda f, hp, nh, pp, npl: lib().crass_b200_dr_search(
             self.h, _np_ptr(bases), _np_ptr(offsets), n, C.byref(params), f, hp, nh, pp, npl), n, want_found)
+
+    def ac_upload(self, ac):
+        _check(lib().crass_b200_ac_upload(self.h, ac.h))
 
     def upload(self, bases, offsets):
         """H2D of a host batch into the context (pinned sources copy at full PCIe rate)."""

@@ -93,7 +93,8 @@ struct crass_b200_ctx {
     uint32_t res_n_reads = 0, res_max_len = 0;
     uint64_t res_n_bases = 0;
     bool res_valid = false, res_found_valid = false;
-    DevBuf d_found_p1, d_cand, d_tokens, d_tok_table, d_tok_unique;
+    DevBuf d_found_p1, d_cand, d_tokens, d_tok_table, d_tok_unique, d_ac_table, d_ac_symv, d_ac_bitmap, d_ac_keys;
+    uint64_t ac_serial = 0;              // build serial of the automaton currently held in d_ac_*
     // K4 token output of the next dr_search launches (crass_b200_ctx_set_token_output / host forms)
     uint8_t* tok_ptr = nullptr;
     uint32_t tok_stride = 0;
@@ -117,12 +118,7 @@ void free_host(void* p, bool pinned) {
     if (pinned) cudaFreeHost(p); else free(p);
 }
 
-void free_device_tables(Automaton* a) {
-    if (a->d_table) { cudaFree(a->d_table); a->d_table = nullptr; }
-    if (a->d_out_len) { cudaFree(a->d_out_len); a->d_out_len = nullptr; }
-    if (a->d_q_bitmap) { cudaFree(a->d_q_bitmap); a->d_q_bitmap = nullptr; }
-    if (a->d_q_keys) { cudaFree(a->d_q_keys); a->d_q_keys = nullptr; }
-}
+void free_device_tables(Automaton*) {}                     // device copies are owned by the contexts (d_ac_*)
 
 }  // namespace cbh
 
@@ -162,7 +158,8 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->d_bases, &c->d_offsets, &c->d_found, &c->d_skip, &c->d_hits, &c->d_pool, &c->d_counters,
-                      &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv, &c->d_found_p1, &c->d_cand, &c->d_tokens, &c->d_tok_table, &c->d_tok_unique};
+                      &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv, &c->d_found_p1, &c->d_cand, &c->d_tokens, &c->d_tok_table, &c->d_tok_unique, &c->d_ac_table, &c->d_ac_symv,
+                      &c->d_ac_bitmap, &c->d_ac_keys};
     for (DevBuf* b : bufs) b->release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     cudaStreamDestroy(c->stream);
@@ -413,6 +410,9 @@ int crass_b200_dr_search_resident(crass_b200_ctx* c, const crass_b200_params* pa
 }
 
 // ---- K2 ------------------------------------------------------------------------------------------------
+}  // extern "C"
+namespace { int ensure_ac_on_device(crass_b200_ctx* c, crass_b200_ac* ac); }
+extern "C" {
 int crass_b200_ac_build(const uint8_t* pat_bytes, const uint32_t* pat_offsets, uint32_t n_patterns, crass_b200_ac** out) {
     if (!pat_bytes || !pat_offsets || !out) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
     cbh::Automaton* a = nullptr;
@@ -426,6 +426,11 @@ int crass_b200_ac_build(const uint8_t* pat_bytes, const uint32_t* pat_offsets, u
 }
 
 void crass_b200_ac_destroy(crass_b200_ac* ac) { delete ac; }
+int crass_b200_ac_upload(crass_b200_ctx* c, const crass_b200_ac* ac) {
+    if (!c || !ac) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    return ensure_ac_on_device(c, const_cast<crass_b200_ac*>(ac));
+}
 uint32_t crass_b200_ac_num_states(const crass_b200_ac* ac) { return ac ? ac->a.n_states : 0; }
 uint32_t crass_b200_ac_num_symbols(const crass_b200_ac* ac) { return ac ? ac->a.n_syms : 0; }
 uint64_t crass_b200_ac_table_bytes(const crass_b200_ac* ac) { return ac ? (uint64_t)ac->a.table.size() * 4 : 0; }
@@ -434,21 +439,22 @@ uint64_t crass_b200_ac_table_bytes(const crass_b200_ac* ac) { return ac ? (uint6
 
 namespace {
 int ensure_ac_on_device(crass_b200_ctx* c, crass_b200_ac* ac) {
+    // The device copy lives in context-owned, grow-only buffers (no cudaMalloc/cudaFree per pattern set); it is
+    // refreshed whenever a different automaton (by build serial) is used with this context.
     cbh::Automaton& a = ac->a;
-    if (a.d_table && a.device == c->device) return 0;
-    cbh::free_device_tables(&a);
-    CUDA_TRY(cudaMalloc(&a.d_table, a.table.size() * sizeof(uint32_t)));
-    CUDA_TRY(cudaMalloc(&a.d_out_len, 256));                           // symv lives here
-    CUDA_TRY(cudaMemcpyAsync(a.d_table, a.table.data(), a.table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(a.d_out_len, a.symv, 256, cudaMemcpyHostToDevice, c->stream));
+    if (c->ac_serial == a.serial && a.serial != 0) return 0;
+    if (int r = c->d_ac_table.reserve(a.table.size() * sizeof(uint32_t))) return r;
+    if (int r = c->d_ac_symv.reserve(256)) return r;
+    CUDA_TRY(cudaMemcpyAsync(c->d_ac_table.p, a.table.data(), a.table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_ac_symv.p, a.symv, 256, cudaMemcpyHostToDevice, c->stream));
     if (a.q_bits) {
-        CUDA_TRY(cudaMalloc(&a.d_q_bitmap, a.q_bitmap.size() * sizeof(uint32_t)));
-        CUDA_TRY(cudaMalloc(&a.d_q_keys, a.q_keys.size() * sizeof(uint32_t)));
-        CUDA_TRY(cudaMemcpyAsync(a.d_q_bitmap, a.q_bitmap.data(), a.q_bitmap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(a.d_q_keys, a.q_keys.data(), a.q_keys.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        if (int r = c->d_ac_bitmap.reserve(a.q_bitmap.size() * sizeof(uint32_t))) return r;
+        if (int r = c->d_ac_keys.reserve(a.q_keys.size() * sizeof(uint32_t))) return r;
+        CUDA_TRY(cudaMemcpyAsync(c->d_ac_bitmap.p, a.q_bitmap.data(), a.q_bitmap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->d_ac_keys.p, a.q_keys.data(), a.q_keys.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    a.device = c->device;
+    c->ac_serial = a.serial;
     return 0;
 }
 }  // namespace
@@ -476,7 +482,7 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         if (!d_found) { if (int r = c->d_found.reserve((size_t)n_reads + 16)) return r; d_found = c->d_found.as<uint8_t>(); }
         if (int r = c->d_cand.reserve(((size_t)n_reads + 16) * sizeof(uint32_t))) return r;
         uint32_t* cand = c->d_cand.as<uint32_t>();
-        cbk::QgramFilter q{(const uint32_t*)ac->a.d_q_bitmap, (const uint32_t*)ac->a.d_q_keys, ac->a.q_bits, ac->a.q_table_bits, ac->a.q_has_ones};
+        cbk::QgramFilter q{c->d_ac_bitmap.as<uint32_t>(), c->d_ac_keys.as<uint32_t>(), ac->a.q_bits, ac->a.q_table_bits, ac->a.q_has_ones};
         const uint32_t n_tiles = (n_reads + cbk::kAcTile - 1) / cbk::kAcTile;
         const size_t bm_bytes = ((size_t)1 << ac->a.q_bits) / 8;
 #define CB_ACF(NW)                                                                                                              \
@@ -493,16 +499,16 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         else CB_ACF(19);
 #undef CB_ACF
         CUDA_TRY(cudaGetLastError());
-        cbk::k_ac_scan_list<<<c->sm_count * 8, 128, 0, st>>>(d_bases, d_offsets, cand, (const uint32_t*)ac->a.d_table, stride_log2,
-                                                             (const uint8_t*)ac->a.d_out_len, d_found, sink);
+        cbk::k_ac_scan_list<<<c->sm_count * 8, 128, 0, st>>>(d_bases, d_offsets, cand, c->d_ac_table.as<uint32_t>(), stride_log2,
+                                                             c->d_ac_symv.as<uint8_t>(), d_found, sink);
         c->launches += 2;
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
     const int threads = 256;
     int blocks = (int)std::min<uint64_t>(((uint64_t)n_reads + threads - 1) / threads, (uint64_t)c->sm_count * 32);
-    cbk::k_ac_scan_generic<<<blocks, threads, 0, st>>>(d_bases, d_offsets, n_reads, (const uint32_t*)ac->a.d_table, stride_log2,
-                                                       (const uint8_t*)ac->a.d_out_len, d_skip, d_found, sink);
+    cbk::k_ac_scan_generic<<<blocks, threads, 0, st>>>(d_bases, d_offsets, n_reads, c->d_ac_table.as<uint32_t>(), stride_log2,
+                                                       c->d_ac_symv.as<uint8_t>(), d_skip, d_found, sink);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;

@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <queue>
 
 #include "internal.h"
@@ -95,6 +96,8 @@ int build_automaton(const uint8_t* bytes, const uint32_t* offs, uint32_t n, Auto
         }
     }
     build_qgram_filter(A, bytes, offs, n);
+    static std::atomic<uint64_t> next_serial{1};
+    A->serial = next_serial++;
     *out = A;
     return 0;
 }

@@ -92,6 +92,7 @@ struct Automaton {
     void* d_q_bitmap = nullptr;
     void* d_q_keys = nullptr;
     int device = -1;
+    uint64_t serial = 0;                        // unique per build; contexts key their device copy on it
     ~Automaton();
 };
 int build_automaton(const uint8_t* bytes, const uint32_t* offs, uint32_t n, Automaton** out);

@@ -142,6 +142,8 @@ int crass_b200_ac_scan_resident(crass_b200_ctx* ctx, const crass_b200_ac* ac, in
  * patterns: n_patterns byte strings back to back, pat_offsets[n_patterns+1]. */
 int crass_b200_ac_build(const uint8_t* pat_bytes, const uint32_t* pat_offsets, uint32_t n_patterns, crass_b200_ac** out);
 void crass_b200_ac_destroy(crass_b200_ac* ac);
+/* copy the automaton into the context's device buffers now (otherwise the first scan does it) */
+int crass_b200_ac_upload(crass_b200_ctx* ctx, const crass_b200_ac* ac);
 uint32_t crass_b200_ac_num_states(const crass_b200_ac* ac);
 uint32_t crass_b200_ac_num_symbols(const crass_b200_ac* ac);
 uint64_t crass_b200_ac_table_bytes(const crass_b200_ac* ac);
