@@ -12,7 +12,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <sstream>
+#include <thread>
 #include <unordered_map>
 
 #include "internal.h"
@@ -132,8 +134,19 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
     for (const std::string& d : drs) if (d.size() >= kClusterKmer) total_kmers += d.size() - kClusterKmer + 1;
     size_t tsize = 1024;
     while (tsize < total_kmers * 2 + 16) tsize <<= 1;
-    std::vector<uint32_t> tkey(tsize, 0xFFFFFFFFu);
-    std::vector<int> tval(tsize, 0);
+    // the table is kept across calls (fresh multi-megabyte vectors cost more in page faults than the clustering itself);
+    // only the slots this call touches are reset on the way out
+    static thread_local std::vector<uint32_t> tkey_store;
+    static thread_local std::vector<int> tval_store;
+    if (tkey_store.size() < tsize) { tkey_store.assign(tsize, 0xFFFFFFFFu); tval_store.assign(tsize, 0); }
+    tsize = tkey_store.size();
+    uint32_t* const tkey = tkey_store.data();           // plain pointers: TLS lookups are not free inside a shared object
+    int* const tval = tval_store.data();
+    std::vector<size_t> touched;
+    struct Reset {
+        uint32_t* k; std::vector<size_t>& t;
+        ~Reset() { for (size_t s : t) k[s] = 0xFFFFFFFFu; }
+    } reset_on_exit{tkey, touched};
     auto slot_of = [&](uint32_t key) {
         size_t s = (size_t)(key * 0x9E3779B1u) & (tsize - 1);
         while (tkey[s] != 0xFFFFFFFFu && tkey[s] != key) s = (s + 1) & (tsize - 1);
@@ -191,35 +204,65 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
         }
         if (!group) { members.emplace_back(); group = (int)members.size(); }
         members[group - 1].push_back((int)t + 2);
-        for (uint32_t key : unseen_int) { const size_t s = slot_of(key); tkey[s] = key; tval[s] = group; }
+        for (uint32_t key : unseen_int) {
+            const size_t s = slot_of(key);
+            if (tkey[s] != key) touched.push_back(s);
+            tkey[s] = key; tval[s] = group;
+        }
         for (const std::string& km : unseen_str) kmer_group_str[km] = group;
     }
     // (2) per group: drop every variant that contains a shorter surviving variant (either strand), then emit
     //     the survivors followed by their reverse complements.
-    std::vector<std::string> out;
-    for (size_t g = 0; g < members.size(); ++g) {
-        std::vector<std::string> v;
-        for (int tok : members[g]) {
-            v.push_back(drs[tok - 2]);
-            if (groups_out) groups_out->push_back(std::make_pair(tok, (int)g + 1));
-        }
-        std::stable_sort(v.begin(), v.end(), [](const std::string& a, const std::string& b) { return a.size() < b.size(); });
-        std::vector<bool> dead(v.size(), false);
+    //     Groups are independent, so they are spread over a few worker threads; the output order (group id, then
+    //     survivors, then their reverse complements) does not depend on the thread count.
+#ifdef CB_PROFILE_NR
+    const auto t_cluster_done = std::chrono::steady_clock::now();
+#endif
+    if (groups_out)
+        for (size_t g = 0; g < members.size(); ++g)
+            for (int tok : members[g]) groups_out->push_back(std::make_pair(tok, (int)g + 1));
+    std::vector<std::vector<std::string> > survivors(members.size());
+    auto reduce_group = [&](size_t g) {
+        std::vector<const std::string*> v;
+        for (int tok : members[g]) v.push_back(&drs[tok - 2]);
+        std::stable_sort(v.begin(), v.end(), [](const std::string* a, const std::string* b) { return a->size() < b->size(); });
+        std::vector<char> dead(v.size(), 0);
         for (size_t i = 0; i < v.size(); ++i) {
-            if (dead[i] || v[i].empty()) continue;
-            const std::string rc = reverse_complement(v[i]);
+            if (dead[i] || v[i]->empty()) continue;
+            const std::string& a = *v[i];
+            const std::string rc = reverse_complement(a);
             for (size_t j = i + 1; j < v.size(); ++j) {
-                if (dead[j] || v[j].empty()) continue;
-                if (v[j].size() == v[i].size()) {                         // same length: containment is equality
-                    if (v[j] == v[i] || v[j] == rc) dead[j] = true;
-                } else if (v[j].find(v[i]) != std::string::npos || v[j].find(rc) != std::string::npos) dead[j] = true;
+                if (dead[j] || v[j]->empty()) continue;
+                const std::string& b = *v[j];
+                if (b.size() == a.size()) {                               // same length: containment is equality
+                    if (b == a || b == rc) dead[j] = 1;
+                } else if (memmem(b.data(), b.size(), a.data(), a.size()) || memmem(b.data(), b.size(), rc.data(), rc.size())) dead[j] = 1;
             }
         }
-        const size_t first = out.size();
-        for (size_t i = 0; i < v.size(); ++i) if (!dead[i] && !v[i].empty()) out.push_back(v[i]);
-        const size_t last = out.size();
-        for (size_t i = first; i < last; ++i) out.push_back(reverse_complement(out[i]));
+        for (size_t i = 0; i < v.size(); ++i) if (!dead[i] && !v[i]->empty()) survivors[g].push_back(*v[i]);
+    };
+    size_t work = 0;
+    for (auto& m : members) work += m.size() * m.size();
+    unsigned n_threads = work > 200000 ? std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency())) : 1;
+    if (n_threads <= 1) {
+        for (size_t g = 0; g < members.size(); ++g) reduce_group(g);
+    } else {
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < n_threads; ++t)
+            pool.emplace_back([&]() { for (size_t g; (g = next++) < members.size();) reduce_group(g); });
+        for (auto& th : pool) th.join();
     }
+    std::vector<std::string> out;
+    for (size_t g = 0; g < members.size(); ++g) {
+        for (const std::string& s : survivors[g]) out.push_back(s);
+        for (const std::string& s : survivors[g]) out.push_back(reverse_complement(s));
+    }
+#ifdef CB_PROFILE_NR
+    const auto t_end = std::chrono::steady_clock::now();
+    fprintf(stderr, "non_redundant_set: %zu groups, work %zu, threads %u, reduce+emit %.2f ms\n", members.size(), work, n_threads,
+            std::chrono::duration<double, std::milli>(t_end - t_cluster_done).count());
+#endif
     return out;
 }
 

@@ -320,7 +320,7 @@ struct QgramFilter {
     uint32_t bits, table_bits, has_ones;
 };
 
-constexpr int kAcTile = 256;
+constexpr int kAcTile = 1024;     // big CTAs: the 64-128 KB bitmap is staged once per CTA, so threads/CTA sets the occupancy
 
 __device__ __forceinline__ bool qgram_member(const QgramFilter& q, uint32_t code) {
     if (code == 0xFFFFFFFFu) return q.has_ones != 0;
