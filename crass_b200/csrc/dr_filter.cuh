@@ -126,46 +126,91 @@ CB_HD bool seed_filter(const uint32_t* R) {
 // 0, 8, 16, ... (phase 0).  Identical results to cb::search_core: windows without a flag cannot have a seed, flagged
 // windows are checked on the bytes, and after a rejected candidate the window grid restarts at back()-1+8
 // (libcrispr.cpp:390), for which the flags are recomputed on the re-phased stream.
+//
+// The search is written as a per-lane state machine with four straight-line stages (pick a flagged window, byte-level
+// find_left, process the seed, recompute the flags) so that a warp that walks 32 candidates can execute every stage
+// in lock-step: an implementation with early returns out of nested loops left the lanes diverged for good (ncu: 1.7
+// active threads per instruction), this form re-converges after every stage.
+template <int NW, int NWIN, int DMIN, int DMAX, class Seq>
+struct PackedSearch {
+    const Seq& s;
+    const uint32_t L;
+    const Params& o;
+    const uint32_t* S;
+    uint32_t* ss;
+    const uint32_t cap;
+    int se = -1, result = 0, pos = -1;
+    uint32_t base = 0, mask = 0, j = 0, n_ss = 0, replen = 0;
+    bool done = true, have = false, need_flags = false;
+
+    CB_HD PackedSearch(const Seq& s_, uint32_t L_, const Params& o_, const uint32_t* S_, uint32_t* ss_, uint32_t cap_)
+        : s(s_), L(L_), o(o_), S(S_), ss(ss_), cap(cap_) {}
+
+    CB_HD void init(uint32_t mask0) {
+        se = search_end(o, L);
+        base = 0; mask = mask0; n_ss = 0; replen = 0; result = 0; pos = -1;
+        done = se < 0; have = false; need_flags = false;
+    }
+    CB_HD void pick() {                                         // next flagged window of the current grid, in order
+        have = false;
+        if (done) return;
+        if (!mask) { done = true; return; }
+        const int h = first_set(mask);
+        mask &= mask - 1;
+        j = base + 8u * (uint32_t)h;
+        if (j > (uint32_t)se) { done = true; return; }
+        have = true;
+    }
+    CB_HD void find() {                                         // is the flag a real (byte-level) seed, and where is the leftmost one
+        pos = -1;
+        if (!have) return;
+        uint32_t begin, end;
+        window_text(o, L, j, begin, end);
+        const int p = find_left(s, begin, end, j, o.window);
+        if (p >= 0) pos = (int)(begin + (uint32_t)p);
+    }
+    CB_HD void seed() {                                         // scanRight / extendPreRepeat / qcFoundRepeats
+        need_flags = false;
+        if (pos < 0) return;
+        bool advance = false; uint32_t nj = 0;
+        const int r = process_seed(s, L, o, j, (uint32_t)pos, ss, n_ss, cap, replen, advance, nj);
+        if (r != 0) { result = r; done = true; }
+        else if (advance) {
+            base = nj + 8u;                                     // j = back() - 1, then j += skips (libcrispr.cpp:390,295)
+            if (base > (uint32_t)se) done = true; else need_flags = true;
+        }
+    }
+    CB_HD void reflag() {                                       // the window grid moved: flags of the re-phased stream
+        if (!need_flags) return;
+        const uint32_t q = base >> 4, sh = (base & 15u) * 2u;
+        uint32_t Q[NW + 2];
+#pragma unroll
+        for (int k = 0; k < NW + 2; ++k) {
+            const uint32_t lo = (q + k < (uint32_t)(NW + 2)) ? S[q + k] : 0u;
+            const uint32_t hi = (q + k + 1 < (uint32_t)(NW + 2)) ? S[q + k + 1] : 0u;
+            Q[k] = funnel_r(lo, hi, sh);
+        }
+        uint32_t acc[NWIN];
+        seed_flags<NW, NWIN, DMIN, DMAX>(Q, acc);
+        mask = flag_mask<NWIN>(acc);
+    }
+};
+
 template <int NW, int NWIN, int DMIN, int DMAX, class Seq>
 CB_HD int search_core_packed(const Seq& s, uint32_t L, const Params& o, const uint32_t* S, uint32_t mask0,
                              uint32_t* ss, uint32_t cap, uint32_t& n_ss, uint32_t& replen) {
-    n_ss = 0; replen = 0;
-    const int se = search_end(o, L);
-    if (se < 0) return 0;
-    uint32_t base = 0, mask = mask0;
+    PackedSearch<NW, NWIN, DMIN, DMAX, Seq> st(s, L, o, S, ss, cap);
+    st.init(mask0);
     for (;;) {
-        while (mask) {
-            const int h = first_set(mask);
-            mask &= mask - 1;
-            const uint32_t j = base + 8u * (uint32_t)h;
-            if (j > (uint32_t)se) return 0;
-            uint32_t begin, end;
-            window_text(o, L, j, begin, end);
-            const int pos = find_left(s, begin, end, j, o.window);
-            if (pos < 0) continue;                              // code-level alias only
-            bool advance; uint32_t nj;
-            const int r = process_seed(s, L, o, j, begin + (uint32_t)pos, ss, n_ss, cap, replen, advance, nj);
-            if (r != 0) return r;
-            if (advance) {
-                base = nj + 8u;                                 // j = back() - 1, then j += skips
-                if (base > (uint32_t)se) return 0;
-                const uint32_t q = base >> 4, sh = (base & 15u) * 2u;
-                uint32_t Q[NW + 2];
-#pragma unroll
-                for (int k = 0; k < NW + 2; ++k) {
-                    const uint32_t lo = (q + k < (uint32_t)(NW + 2)) ? S[q + k] : 0u;
-                    const uint32_t hi = (q + k + 1 < (uint32_t)(NW + 2)) ? S[q + k + 1] : 0u;
-                    Q[k] = funnel_r(lo, hi, sh);
-                }
-                uint32_t acc[NWIN];
-                seed_flags<NW, NWIN, DMIN, DMAX>(Q, acc);
-                mask = flag_mask<NWIN>(acc);
-                goto next_phase;
-            }
-        }
-        return 0;
-    next_phase:;
+        st.pick();
+        if (!st.have) break;
+        st.find();
+        st.seed();
+        st.reflag();
     }
+    n_ss = st.result == 1 ? st.n_ss : 0;
+    replen = st.replen;
+    return st.result;
 }
 
 }  // namespace cb

@@ -235,43 +235,64 @@ k_dr_exact_packed(const uint8_t* __restrict__ bases, const uint64_t* __restrict_
     const uint32_t nthreads = gridDim.x * blockDim.x;
     uint32_t* S = sm + threadIdx.x * kSlot;
     uint32_t ss[32];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += nthreads) {
-        const uint32_t r = cand_list[i];
-        const uint64_t b = offsets[r];
-        const uint32_t L = (uint32_t)(offsets[r + 1] - b);
-        const uint64_t a0 = b & ~(uint64_t)15;
-        const uint32_t sh = (uint32_t)(b & 15u) * 2u;
-        uint32_t prev = 0;
-        uint32_t R[NW + 2];
-#pragma unroll
-        for (int v = 0; v < NW + 3; ++v) {
-            const uint64_t at = a0 + 16ull * v;
-            uint32_t w = 0;
-            if (at + 16 <= n_bases) {
-                const uint4 x = __ldg(reinterpret_cast<const uint4*>(bases + at));
-                w = cb::pack16(x.x, x.y, x.z, x.w);
-            } else {
-                uint32_t q[4] = {0, 0, 0, 0};
-                for (int t = 0; t < 16; ++t)
-                    if (at + t < n_bases) q[t >> 2] |= (uint32_t)__ldg(bases + at + t) << (8 * (t & 3));
-                w = cb::pack16(q[0], q[1], q[2], q[3]);
-            }
-            if (v > 0) R[v - 1] = cb::funnel_r(prev, w, sh);
-            prev = w;
-        }
-#pragma unroll
-        for (int k = 0; k < NW + 2; ++k) S[k] = R[k];
-        uint32_t acc[NWIN];
-        cb::seed_flags<NW, NWIN, DMIN, DMAX>(R, acc);
+    // every warp takes 32 candidates at a time and walks the stages of cb::PackedSearch in lock-step
+    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n_cand; i0 += nthreads) {
+        const uint32_t i = i0 + (threadIdx.x & 31u);
+        const bool active = i < n_cand;
+        const uint32_t r = active ? cand_list[i] : 0u;
+        const uint64_t b = active ? offsets[r] : 0ull;
+        const uint32_t L = active ? (uint32_t)(offsets[r + 1] - b) : 0u;
         GmemSeq s{bases + b};
-        uint32_t n_ss = 0, replen = 0;
-        const int f = cb::search_core_packed<NW, NWIN, DMIN, DMAX>(s, L, o, S, cb::flag_mask<NWIN>(acc), ss, 32u, n_ss, replen);
+        uint32_t mask0 = 0;
+        if (active) {
+            const uint64_t a0 = b & ~(uint64_t)15;
+            const uint32_t sh = (uint32_t)(b & 15u) * 2u;
+            uint32_t prev = 0;
+            uint32_t R[NW + 2];
+#pragma unroll
+            for (int v = 0; v < NW + 3; ++v) {
+                const uint64_t at = a0 + 16ull * v;
+                uint32_t w = 0;
+                if (at + 16 <= n_bases) {
+                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(bases + at));
+                    w = cb::pack16(x.x, x.y, x.z, x.w);
+                } else {
+                    uint32_t q[4] = {0, 0, 0, 0};
+                    for (int t = 0; t < 16; ++t)
+                        if (at + t < n_bases) q[t >> 2] |= (uint32_t)__ldg(bases + at + t) << (8 * (t & 3));
+                    w = cb::pack16(q[0], q[1], q[2], q[3]);
+                }
+                if (v > 0) R[v - 1] = cb::funnel_r(prev, w, sh);
+                prev = w;
+            }
+#pragma unroll
+            for (int k = 0; k < NW + 2; ++k) S[k] = R[k];
+            uint32_t acc[NWIN];
+            cb::seed_flags<NW, NWIN, DMIN, DMAX>(R, acc);
+            mask0 = cb::flag_mask<NWIN>(acc);
+        }
+        cb::PackedSearch<NW, NWIN, DMIN, DMAX, GmemSeq> st(s, L, o, S, ss, 32u);
+        st.init(mask0);
+        if (!active) st.done = true;
+        __syncwarp();
+        for (;;) {
+            st.pick();
+            if (!__any_sync(0xFFFFFFFFu, st.have)) break;
+            st.find();
+            __syncwarp();
+            st.seed();
+            __syncwarp();
+            st.reflag();
+            __syncwarp();
+        }
+        const int f = st.result;
         if (f < 0) *error_flag = f;
         if (f == 1) {
             found[r] = 1;
-            const uint32_t slot = emit_hit(sink, r, ss, n_ss, replen);
-            if (sink.tokens && slot != 0xFFFFFFFFu) emit_token(sink.tokens + (size_t)slot * sink.token_stride, sink.token_stride, s, L, ss, n_ss);
+            const uint32_t slot = emit_hit(sink, r, ss, st.n_ss, st.replen);
+            if (sink.tokens && slot != 0xFFFFFFFFu) emit_token(sink.tokens + (size_t)slot * sink.token_stride, sink.token_stride, s, L, ss, st.n_ss);
         }
+        __syncwarp();
     }
 }
 
