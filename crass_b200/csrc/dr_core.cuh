@@ -219,35 +219,59 @@ CB_HD_NOINLINE int osa_distance(const Seq& s, uint32_t a0, uint32_t n, uint32_t 
 // transposition term is D[i-2][j-2] + 1 + [a(i-1) != b(j)] + [a(i) != b(j-1)], which can only improve a cell when both
 // cross comparisons match, i.e. it is the restricted (OSA) transposition; the guard i > 2 && j > 2 clears the
 // transposition bits of row 2 and of column 2.  Returns -1 when the fast form does not apply (caller falls back).
+// byte -> slot of the match-vector table: A C G T N get their own, anything else is "unsupported"
+CB_HD int osa_slot(uint8_t c) {
+    return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : c == 'N' ? 4 : -1;
+}
+
+// Loop bounds are made warp-uniform on the device (maximum over the lanes that are here together) and the bodies are
+// predicated instead: lanes with different string lengths then stay converged through both loops.
+CB_HD uint32_t uniform_bound(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __reduce_max_sync(__activemask(), v);
+#else
+    return v;
+#endif
+}
+
 template <class Seq>
 CB_HD int osa_distance_bitpar(const Seq& s, uint32_t a0, uint32_t n, uint32_t b0, uint32_t m) {
-    if (n == 0 || m == 0 || n > 64) return -1;
-    uint64_t peq[4] = {0, 0, 0, 0};
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint8_t c = s[a0 + i];
-        if (c != 'A' && c != 'C' && c != 'G' && c != 'T') return -1;
-        peq[(c >> 1) & 3] |= 1ull << i;
+    const bool usable = !(n == 0 || m == 0 || n > 64);
+    if (!usable) { n = 0; m = 0; }
+    uint64_t p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0;
+    bool bad = !usable;
+    const uint32_t n_loop = uniform_bound(n);
+    for (uint32_t i = 0; i < n_loop; ++i) {
+        if (i < n) {
+            const int k = osa_slot(s[a0 + i]);
+            const uint64_t bit = 1ull << i;
+            bad |= k < 0;
+            p0 |= k == 0 ? bit : 0; p1 |= k == 1 ? bit : 0; p2 |= k == 2 ? bit : 0; p3 |= k == 3 ? bit : 0; p4 |= k == 4 ? bit : 0;
+        }
     }
-    const uint64_t top = 1ull << (n - 1);
-    uint64_t vp = n == 64 ? ~0ull : ((1ull << n) - 1ull), vn = 0, d0 = 0, pm_prev = 0;
+    const uint64_t top = n ? 1ull << (n - 1) : 0;
+    uint64_t vp = n >= 64 ? ~0ull : ((1ull << n) - 1ull), vn = 0, d0 = 0, pm_prev = 0;
     int score = (int)n;
-    for (uint32_t j = 0; j < m; ++j) {
-        const uint8_t c = s[b0 + j];
-        if (c != 'A' && c != 'C' && c != 'G' && c != 'T') return -1;
-        const uint64_t pm = peq[(c >> 1) & 3];
-        uint64_t tr = ((((~d0) & pm) << 1) & pm_prev) & ~3ull;          // rows 1 and 2 never transpose
-        if (j < 2) tr = 0;                                              // columns 1 and 2 never transpose
-        d0 = (((pm & vp) + vp) ^ vp) | pm | vn | tr;
-        const uint64_t hp = vn | ~(d0 | vp);
-        const uint64_t hn = d0 & vp;
-        score += (hp & top) ? 1 : 0;
-        score -= (hn & top) ? 1 : 0;
-        const uint64_t x = (hp << 1) | 1ull;
-        vp = (hn << 1) | ~(d0 | x);
-        vn = d0 & x;
-        pm_prev = pm;
+    const uint32_t m_loop = uniform_bound(m);
+    for (uint32_t j = 0; j < m_loop; ++j) {
+        if (j < m) {
+            const int k = osa_slot(s[b0 + j]);
+            bad |= k < 0;
+            const uint64_t pm = k == 0 ? p0 : k == 1 ? p1 : k == 2 ? p2 : k == 3 ? p3 : k == 4 ? p4 : 0;
+            uint64_t tr = ((((~d0) & pm) << 1) & pm_prev) & ~3ull;      // rows 1 and 2 never transpose
+            if (j < 2) tr = 0;                                          // columns 1 and 2 never transpose
+            d0 = (((pm & vp) + vp) ^ vp) | pm | vn | tr;
+            const uint64_t hp = vn | ~(d0 | vp);
+            const uint64_t hn = d0 & vp;
+            score += (hp & top) ? 1 : 0;
+            score -= (hn & top) ? 1 : 0;
+            const uint64_t x = (hp << 1) | 1ull;
+            vp = (hn << 1) | ~(d0 | x);
+            vn = d0 & x;
+            pm_prev = pm;
+        }
     }
-    return score;
+    return bad ? -1 : score;
 }
 
 template <class Seq>
