@@ -235,7 +235,12 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
         int* d_err = c->d_error.as<int>();
 #define CB_FAST(NW, NWIN)                                                                                                           \
     do {                                                                                                                            \
-        cbk::k_dr_filter<NW, NWIN, 49, 97><<<fblocks, cbk::kFilterTile, 0, st>>>(d_bases, d_offsets, n_reads, d_found, cand, d_counters); \
+        const size_t fsmem = cbk::dr_filter_smem_bytes<NW>();                                                                       \
+        CUDA_TRY(cudaFuncSetAttribute(cbk::k_dr_filter<NW, NWIN, 49, 97>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); \
+        int per_sm = 1;                                                                                                             \
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbk::k_dr_filter<NW, NWIN, 49, 97>, cbk::kFilterTile, fsmem)); \
+        const int pblocks = (int)std::min<uint32_t>(n_tiles, (uint32_t)(c->sm_count * std::max(per_sm, 1)));    /* persistent: one wave */ \
+        cbk::k_dr_filter<NW, NWIN, 49, 97><<<pblocks, cbk::kFilterTile, fsmem, st>>>(d_bases, d_offsets, n_reads, d_found, cand, d_counters); \
         cbk::k_dr_exact_packed<NW, NWIN, 49, 97><<<eblocks, cbk::kExactThreads, 0, st>>>(d_bases, d_offsets, n_reads, cand, o, d_found, sink, d_err); \
     } while (0)
         if (max_read_len <= 112) { if (nwin <= 3) CB_FAST(7, 3); else CB_FAST(7, 4); }

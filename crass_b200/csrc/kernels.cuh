@@ -170,37 +170,113 @@ __device__ __forceinline__ uint4 ldg_stream128(const uint8_t* p) {
     return v;
 }
 
+// ---- TMA tile staging (cp.async.bulk + mbarrier) shared by the two filter kernels ----------------------------------
+// A tile = TILE consecutive reads = one contiguous byte range of the batch.  One elected thread issues a 1-D bulk copy
+// (UBLKCP) of that range into shared memory and arms an mbarrier with the byte count; the copy of tile i+1 is in flight
+// while the CTA computes on tile i.  Consumers recode the bytes to 2 bits (16 bases -> one word) cooperatively.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// bytes of tile `tile` that a bulk copy may fetch: [a0, a0 + tma_bytes), 16-byte granular, never past the batch end
+template <int TILE, int NW>
+__device__ __forceinline__ void tile_extent(const uint64_t* __restrict__ offsets, uint32_t n_reads, uint64_t n_bases, uint32_t tile,
+                                            uint64_t& a0, uint32_t& want_bytes, uint32_t& tma_bytes) {
+    const uint32_t r0 = tile * TILE;
+    const uint32_t r1 = min(r0 + (uint32_t)TILE, n_reads);
+    const uint64_t lo = offsets[r0], hi = offsets[r1];
+    a0 = lo & ~(uint64_t)15;
+    constexpr uint32_t kMax = (uint32_t)(TILE * NW + NW + 8) * 16u;
+    uint32_t want = (uint32_t)(((hi - a0 + 15) >> 4) + NW + 4) * 16u;        // + look-ahead for the last read's realignment
+    if (want > kMax) want = kMax;
+    want_bytes = want;
+    const uint64_t n16 = n_bases & ~(uint64_t)15;
+    tma_bytes = a0 >= n16 ? 0u : (uint32_t)((n16 - a0) < (uint64_t)want ? (n16 - a0) : (uint64_t)want);
+}
+
+template <int TILE, int NW>
+__device__ __forceinline__ void tile_issue(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads,
+                                           uint64_t n_bases, uint32_t tile, uint8_t* buf, uint64_t* bar) {
+    uint64_t a0; uint32_t want, tma_bytes;
+    tile_extent<TILE, NW>(offsets, n_reads, n_bases, tile, a0, want, tma_bytes);
+    if (tma_bytes) {
+        mbar_arrive_expect_tx(bar, tma_bytes);
+        tma_load_1d(buf, bases + a0, tma_bytes, bar);
+    } else {
+        mbar_arrive(bar);
+    }
+}
+
+// cooperative 2-bit recoding of the staged bytes into `packed` (one word per 16 bases); vectors the bulk copy could not
+// cover (ragged end of the batch) are fetched with guarded byte loads
+template <int TILE>
+__device__ __forceinline__ void tile_pack(const uint8_t* __restrict__ bases, uint64_t n_bases, uint64_t a0, uint32_t want_bytes,
+                                          uint32_t tma_bytes, const uint8_t* buf, uint32_t* packed) {
+    const uint32_t nvec = want_bytes >> 4, nt = tma_bytes >> 4;
+    for (uint32_t v = threadIdx.x; v < nvec; v += TILE) {
+        uint32_t w;
+        if (v < nt) {
+            const uint4 x = *reinterpret_cast<const uint4*>(buf + 16u * v);
+            w = cb::pack16(x.x, x.y, x.z, x.w);
+        } else {
+            const uint64_t at = a0 + 16ull * v;
+            uint32_t q[4] = {0, 0, 0, 0};
+            for (int i = 0; i < 16; ++i)
+                if (at + i < n_bases) q[i >> 2] |= (uint32_t)__ldg(bases + at + i) << (8 * (i & 3));
+            w = cb::pack16(q[0], q[1], q[2], q[3]);
+        }
+        packed[v] = w;
+    }
+}
+
+template <int NW>
+constexpr size_t dr_filter_smem_bytes() { return (size_t)(kFilterTile * NW + NW + 8) * 20; }   // 16 B/vector bytes + 4 B/vector packed
+
 template <int NW, int NWIN, int DMIN, int DMAX>
 __global__ void __launch_bounds__(kFilterTile)
 k_dr_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads,
             uint8_t* __restrict__ found, uint32_t* __restrict__ cand_list, uint32_t* __restrict__ counters) {
     constexpr int kWords = kFilterTile * NW + NW + 8;          // packed words a tile can need (+ look-ahead + realignment)
-    __shared__ uint32_t sm[kWords];
+    extern __shared__ __align__(128) uint8_t dyn_smem[];       // dr_filter_smem_bytes<NW>() bytes
+    uint8_t* buf = dyn_smem;                                   // the tile's bytes, written by the bulk copy
+    uint32_t* sm = reinterpret_cast<uint32_t*>(dyn_smem + kWords * 16);   // the same tile, 2 bits per base
+    __shared__ uint64_t full;
     const uint32_t n_tiles = (n_reads + kFilterTile - 1) / kFilterTile;
     const uint64_t n_bases = offsets[n_reads];
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (threadIdx.x == 0) mbar_init(&full, 1);
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x < n_tiles) tile_issue<kFilterTile, NW>(bases, offsets, n_reads, n_bases, blockIdx.x, buf, &full);
+    uint32_t parity = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, parity ^= 1u) {
         const uint32_t r0 = tile * kFilterTile;
         const uint32_t r1 = min(r0 + (uint32_t)kFilterTile, n_reads);
-        const uint64_t lo = offsets[r0], hi = offsets[r1];
-        const uint64_t a0 = lo & ~(uint64_t)15;                 // 16-byte aligned start of the tile in the batch
-        uint32_t nvec = (uint32_t)((hi - a0 + 15) >> 4) + NW + 4;
-        if (nvec > (uint32_t)kWords) nvec = kWords;
-        __syncthreads();                                        // previous tile fully consumed
-        for (uint32_t v = threadIdx.x; v < nvec; v += kFilterTile) {
-            const uint64_t at = a0 + 16ull * v;
-            uint32_t w;
-            if (at + 16 <= n_bases) {
-                const uint4 x = ldg_stream128(bases + at);
-                w = cb::pack16(x.x, x.y, x.z, x.w);
-            } else {                                            // ragged end of the batch: byte loads, zero fill
-                uint32_t q[4] = {0, 0, 0, 0};
-                for (int i = 0; i < 16; ++i)
-                    if (at + i < n_bases) q[i >> 2] |= (uint32_t)__ldg(bases + at + i) << (8 * (i & 3));
-                w = cb::pack16(q[0], q[1], q[2], q[3]);
-            }
-            sm[v] = w;
-        }
-        __syncthreads();
+        uint64_t a0; uint32_t want, tma_bytes;
+        tile_extent<kFilterTile, NW>(offsets, n_reads, n_bases, tile, a0, want, tma_bytes);
+        mbar_wait(&full, parity);                               // the tile's bytes have landed
+        tile_pack<kFilterTile>(bases, n_bases, a0, want, tma_bytes, buf, sm);
+        __syncthreads();                                        // packed tile complete, byte buffer free again
+        if (threadIdx.x == 0 && tile + gridDim.x < n_tiles)
+            tile_issue<kFilterTile, NW>(bases, offsets, n_reads, n_bases, tile + gridDim.x, buf, &full);   // overlaps the compute below
         const uint32_t r = r0 + threadIdx.x;
         if (r < r1) {
             const uint32_t b = (uint32_t)(offsets[r] - a0);     // base offset of the read inside the packed tile
@@ -214,6 +290,7 @@ k_dr_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs
             found[r] = 0;
             if (cand) cand_list[atomicAdd(&counters[3], 1u)] = r;
         }
+        __syncthreads();                                        // everyone is done with the packed tile
     }
 }
 
