@@ -52,11 +52,42 @@ CB_HD int first_set(uint32_t x) {                                       // index
 #endif
 }
 
-// 4 bytes -> 8 bits (base k of the word in bits [2k, 2k+2))
-CB_HD uint32_t code4(uint32_t w) { return (((w >> 1) & 0x03030303u) * 0x01041040u) >> 24; }
-// 16 bytes -> 32 bits
+// min(a + b, c) per unsigned 16-bit lane, modular add: one VIADDMNMX.U16x2 on sm_100a.  With b = -R (per lane) the
+// sum is zero exactly where a == R, so "compare + fold into the running minimum" is a single instruction.
+CB_HD uint32_t addmin_u16x2(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+    return __viaddmin_u16x2(a, b, c);
+#else
+    auto mn = [](uint32_t x, uint32_t y) { return x < y ? x : y; };
+    const uint32_t lo = mn(((a & 0xFFFFu) + (b & 0xFFFFu)) & 0xFFFFu, c & 0xFFFFu);
+    const uint32_t hi = mn(((a >> 16) + (b >> 16)) & 0xFFFFu, c >> 16);
+    return lo | (hi << 16);
+#endif
+}
+CB_HD uint32_t neg_u16x2(uint32_t a) {                                   // per-lane two's complement
+    const uint32_t lo = (0u - (a & 0xFFFFu)) & 0xFFFFu, hi = (0u - (a >> 16)) & 0xFFFFu;
+    return lo | (hi << 16);
+}
+CB_HD uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, y, sel);
+#else
+    const uint64_t v = (uint64_t)x | ((uint64_t)y << 32);
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+#endif
+}
+
+// 4 bytes -> 8 bits in the TOP byte of the result (base k of the word in bits [24+2k, 24+2k+2)):
+// (b & 6) is the 2-bit code shifted left by one, the multiplier gathers the four fields without carries
+CB_HD uint32_t code4_top(uint32_t w) { return (w & 0x06060606u) * 0x00820820u; }
+CB_HD uint32_t code4(uint32_t w) { return code4_top(w) >> 24; }
+// 16 bytes -> 32 bits: the four top bytes are collected with three byte permutes
 CB_HD uint32_t pack16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
-    return code4(w0) | (code4(w1) << 8) | (code4(w2) << 16) | (code4(w3) << 24);
+    const uint32_t lo = byte_perm(code4_top(w0), code4_top(w1), 0x0073u);
+    const uint32_t hi = byte_perm(code4_top(w2), code4_top(w3), 0x0073u);
+    return byte_perm(lo, hi, 0x5410u);
 }
 
 CB_HD bool has_zero_half(uint32_t x) { return (x & 0xFFFFu) == 0 || (x >> 16) == 0; }
@@ -69,8 +100,9 @@ CB_HD bool has_zero_half(uint32_t x) { return (x & 0xFFFFu) == 0 || (x >> 16) ==
 template <int NW, int NWIN, int DMIN, int DMAX>
 CB_HD void seed_flags(const uint32_t* R, uint32_t* acc) {
     constexpr int OLO = DMIN / 16, OHI = DMAX / 16;
+    uint32_t negR[NWIN];                                        // -window per 16-bit lane: T + negR == 0  <=>  T == window
 #pragma unroll
-    for (int k = 0; k < NWIN; ++k) acc[k] = 0xFFFFFFFFu;
+    for (int k = 0; k < NWIN; ++k) { acc[k] = 0xFFFFFFFFu; negR[k] = neg_u16x2(R[k]); }
 #pragma unroll
     for (int phi = 0; phi < 16; ++phi) {
         uint32_t T[NW + 1];                                     // the stream shifted right by phi bases
@@ -78,18 +110,13 @@ CB_HD void seed_flags(const uint32_t* R, uint32_t* acc) {
         for (int k = OLO; k <= NW; ++k) T[k] = phi ? funnel_r(R[k], R[k + 1], 2 * phi) : R[k];
 #pragma unroll
         for (int k = 0; k < NWIN; ++k) {
-            uint32_t pend = 0;
-            bool has_pend = false;
 #pragma unroll
             for (int o = OLO; o <= OHI; ++o) {
                 const int d = 16 * o + phi;
                 if (d < DMIN || d > DMAX) continue;
                 if (k + o > NW - 1) continue;                   // every position of this word pair lies past the read
-                const uint32_t x = R[k] ^ T[k + o];
-                if (has_pend) { acc[k] = min3_u16x2(acc[k], pend, x); has_pend = false; }
-                else { pend = x; has_pend = true; }
+                acc[k] = addmin_u16x2(T[k + o], negR[k], acc[k]);   // one VIADDMNMX.U16x2 per (window word, distance)
             }
-            if (has_pend) acc[k] = min3_u16x2(acc[k], pend, pend);
         }
     }
 }
