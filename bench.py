@@ -178,6 +178,7 @@ def main():
     import torch.distributed as dist
     import crass_b200 as cb
     from crass_b200 import api
+    from crass_b200 import dist as cbdist
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -234,22 +235,8 @@ def main():
         return h_hits[which][: nh * 4].numpy().view(api.HIT_DTYPE), h_pool[which][: max(npool, 1)].numpy().view(np.uint32)
 
     def merge_dr_lists(local):
-        if world == 1:
-            return local
-        blob = b"".join(d + b"\n" for d in local)
-        size = torch.tensor([len(blob)], dtype=torch.int64, device=dev)
-        sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-        dist.all_gather(sizes, size)                                  # NCCL over NVLink: counts ...
-        mx = max(int(s.item()) for s in sizes)
-        buf = torch.zeros(mx, dtype=torch.uint8, device=dev)
-        buf[: len(blob)] = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
-        allb = torch.empty(world * mx, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(allb, buf)                        # ... then the fixed-width DR records
-        allb = allb.cpu().numpy()
-        drs_all = []
-        for r in range(world):
-            drs_all += [x for x in allb[r * mx: r * mx + int(sizes[r].item())].tobytes().split(b"\n") if x]
-        return api.merge_dr_lists(drs_all)                             # rank-ordered first appearance == sequential token order
+        # one NCCL all-gather of the per-shard DR sets + deterministic merge (crass_b200/dist.py); identity at N=1
+        return cbdist.allgather_dr_lists(local, device=dev)
 
     def step_resident(record):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]

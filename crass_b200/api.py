@@ -91,6 +91,7 @@ def lib():
         "crass_b200_edit_distance_batch": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, vp, C.c_uint32, vp, vp]),
         "crass_b200_scan_right": (C.c_int, [vp, cp, C.c_uint32, u32p, u32p, C.c_uint32, cp, C.c_uint32, C.c_uint32, C.c_uint32]),
         "crass_b200_extend_pre_repeat": (C.c_int, [vp, cp, C.c_uint32, u32p, C.c_uint32, C.c_uint32, C.c_uint32, u32p]),
+        "crass_b200_qc_found_repeats": (C.c_int, [vp, cp, C.c_uint32, u32p, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_int)]),
         "crass_b200_parse_file": (C.c_int, [cp, C.POINTER(vp)]),
         "crass_b200_batch_from_memory": (C.c_int, [vp, vp, C.c_uint32, vp, C.POINTER(vp)]),
         "crass_b200_batch_destroy": (None, [vp]),

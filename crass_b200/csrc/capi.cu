@@ -635,6 +635,25 @@ int crass_b200_extend_pre_repeat(crass_b200_ctx* c, const uint8_t* seq, uint32_t
     return 0;
 }
 
+int crass_b200_qc_found_repeats(crass_b200_ctx* c, const uint8_t* seq, uint32_t len, const uint32_t* ss, uint32_t n_ss,
+                                int min_spacer, int max_spacer, int* result) {
+    if (!c || !seq || !ss || !result) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    if (n_ss < 4 || (n_ss & 1)) return cbh::fail(CRASS_B200_EINVAL, "need at least two repeats in ss");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (int r = c->d_bases.reserve((size_t)len + 64)) return r;
+    if (int r = c->d_misc.reserve(((size_t)n_ss + 4) * sizeof(uint32_t))) return r;
+    uint32_t* d_ss = c->d_misc.as<uint32_t>() + 4;
+    int* d_r = c->d_misc.as<int>();
+    CUDA_TRY(cudaMemcpyAsync(c->d_bases.p, seq, len, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_ss, ss, n_ss * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    cbk::k_qc_one<<<1, 1, 0, c->stream>>>(c->d_bases.as<uint8_t>(), len, d_ss, n_ss, min_spacer, max_spacer, d_r);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(result, d_r, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 void crass_b200_free(void* p) { free(p); }
 
 }  // extern "C"

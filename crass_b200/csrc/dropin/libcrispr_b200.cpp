@@ -244,7 +244,11 @@ bool drHasHighlyAbundantKmers(std::string& directRepeat, float& maxFrequency) { 
     const size_t kmer_length = 3;
     const size_t max_index = directRepeat.length() - kmer_length;
     int total_count = 0, max_count = 0;
-    for (size_t i = 0; i < max_index; i++) { addOrIncrement(kmer_counter, directRepeat.substr(i, kmer_length)); total_count++; }
+    for (size_t i = 0; i < max_index; i++) {
+        std::string kmer = directRepeat.substr(i, kmer_length);
+        addOrIncrement(kmer_counter, kmer);
+        total_count++;
+    }
     for (std::map<std::string, int>::iterator it = kmer_counter.begin(); it != kmer_counter.end(); ++it)
         if (it->second > max_count) max_count = it->second;
     maxFrequency = static_cast<float>(max_count) / static_cast<float>(total_count);

@@ -563,4 +563,10 @@ __global__ void k_extend_one(const uint8_t* __restrict__ seq, uint32_t L, uint32
     *replen = cb::extend_pre_repeat(s, L, ss, n_ss, window, min_spacer);
 }
 
+__global__ void k_qc_one(const uint8_t* __restrict__ seq, uint32_t L, const uint32_t* ss, uint32_t n_ss, int min_spacer, int max_spacer,
+                         int* result) {
+    GmemSeq s{seq};
+    *result = cb::qc_found_repeats(s, L, ss, n_ss, min_spacer, max_spacer);
+}
+
 }  // namespace cbk

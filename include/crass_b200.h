@@ -174,6 +174,9 @@ int crass_b200_scan_right(crass_b200_ctx* ctx, const uint8_t* seq, uint32_t len,
                           const uint8_t* pattern, uint32_t pattern_len, uint32_t min_spacer, uint32_t scan_range);
 int crass_b200_extend_pre_repeat(crass_b200_ctx* ctx, const uint8_t* seq, uint32_t len, uint32_t* ss, uint32_t n_ss,
                                  uint32_t window, uint32_t min_spacer, uint32_t* repeat_len);
+/* qcFoundRepeats (libcrispr.h:113-115) on one read: *result = 1 pass, 0 fail, -1 where the reference throws */
+int crass_b200_qc_found_repeats(crass_b200_ctx* ctx, const uint8_t* seq, uint32_t len, const uint32_t* ss, uint32_t n_ss,
+                                int min_spacer, int max_spacer, int* result);
 
 /* ---- feed path: kseq-compatible FASTA/FASTQ(.gz) parser ------------------------------------------ */
 int crass_b200_parse_file(const char* path, crass_b200_batch** out);      /* "-" = stdin */

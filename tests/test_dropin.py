@@ -1,0 +1,82 @@
+"""Drop-in proof (needs a B200 and the reference-compiled harness in oracle/_ref/).
+
+oracle/_ref/libcrass_dropin.so is the REFERENCE's own code (ReadHolder, StringCheck, kseq, PatternMatcher, the harness
+in oracle/refshim) with exactly one translation unit swapped: src/crass/libcrispr.cpp is replaced by the product's
+crass_b200/csrc/dropin/libcrispr_b200.cpp, which exports the same C++ functions and runs the two hot loops on the GPU
+through libcrass_b200.so.  The reference's containers (ReadMap, StringCheck, lookupTables) filled through it must be
+identical to the ones the unmodified reference fills -- that is what lets WorkHorse / NodeManager / the XML writer run
+unchanged.  crass-test-b200 is the reference's own Catch test binary linked the same way.
+"""
+import ctypes as C
+import gzip
+import os
+import subprocess
+
+import pytest
+
+import checkers
+
+pytestmark = pytest.mark.gpu
+
+DROPIN_SO = os.path.join(checkers.ORACLE_DIR, "_ref", "libcrass_dropin.so")
+CATCH_B200 = os.path.join(checkers.ORACLE_DIR, "_ref", "crass-test-b200")
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+class DropIn(checkers._Base):
+    prefix = "ref_"
+
+    def __init__(self):
+        lib = C.CDLL(DROPIN_SO)
+        lib.ref_init()
+        super().__init__(lib)
+
+
+@pytest.fixture(scope="module")
+def D():
+    if not os.path.exists(DROPIN_SO):
+        pytest.skip("oracle/_ref/libcrass_dropin.so not built (needs /root/reference at build time)")
+    return DropIn()
+
+
+@pytest.mark.parametrize("name", ["Ill100.fx.gz", "CN_gDC.fa.gz", "Ill.nr.miss.fa.gz", "front_offset_bug.fa.gz", "poor_dr_ext.fa.gz"])
+def test_reference_harness_with_swapped_libcrispr(D, name):
+    path = os.path.join(checkers.REF_DATA, name)
+    want = gzip.open(os.path.join(G, "bundled", name + ".dump.gz")).read().decode("latin-1")
+    got, _ = D.run_files([path])
+    assert got == want
+
+
+def test_other_options_through_the_shim(D):
+    P = checkers.port()
+    path = os.path.join(checkers.REF_DATA, "CN_gDC.fa.gz")
+    for prm in (dict(window=6), dict(min_repeats=3), dict(low_spacer=20, high_spacer=60)):
+        want, _ = P.run_files([path], prm)
+        got, _ = D.run_files([path], prm)
+        assert got == want, prm
+
+
+def test_single_read_entry_points(D):
+    """searchCore / scanRight / extendPreRepeat / qcFoundRepeats of the shim, called one read at a time."""
+    import random
+    import fuzzgen
+    P = checkers.port()
+    rng = random.Random(31)
+    hits = 0
+    for _ in range(150):
+        s = fuzzgen.fuzz_read(rng, max_len=300)
+        a = P.search_core(s)
+        b = D.search_core(s)
+        assert a[0] == b[0]
+        if a[0] == 1:
+            hits += 1
+            assert a == b
+            assert D.qc_found_repeats(s, a[1]) == P.qc_found_repeats(s, a[1])
+    assert hits > 10
+
+
+def test_reference_catch_tests_on_the_gpu():
+    if not os.path.exists(CATCH_B200):
+        pytest.skip("crass-test-b200 not built")
+    out = subprocess.run([CATCH_B200], capture_output=True, text=True, env=dict(os.environ, MALLOC_PERTURB_="255"))
+    assert out.returncode == 0 and "139 assertions in 7 test cases" in out.stdout, out.stdout[-2000:]
