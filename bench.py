@@ -137,6 +137,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
+    # stdout carries exactly ONE JSON line: everything libraries print while the run is going on (e.g. NCCL's version
+    # banner) is sent to stderr, the line is written to the saved descriptor at the very end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -170,7 +179,7 @@ def main():
                 "cpu_baseline": {"value": rate, "unit": "reads/s", "cores": n_procs, "kind": vals[0]["kind"],
                                  "sample": "%d-read prefix of the config2 recipe split over %d processes (searchFile + createNonRedundantSet + findSingletons each, FASTA in tmpfs)" % (n_sample, n_procs)},
                 "e2e": {"value": rate, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ------------------------------------------------------------------------------------------------ own arm
@@ -356,7 +365,7 @@ def main():
                 r = cpu_reference_rate(np_bases, np_offsets, ns, 1, d)
             line["cpu_baseline"] = {"value": r["rate"], "unit": "reads/s", "cores": 1, "kind": r["kind"],
                                     "sample": "first %d reads of rank 0's shard as FASTA in tmpfs: searchFile %.2fs + findSingletons %.2fs, 1 thread" % (ns, r["phase1_s"], r["phase2_s"])}
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
