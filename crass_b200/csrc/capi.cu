@@ -94,7 +94,9 @@ struct crass_b200_ctx {
     uint64_t res_n_bases = 0;
     bool res_valid = false, res_found_valid = false;
     DevBuf d_found_p1, d_cand, d_tokens, d_tok_table, d_tok_unique, d_ac_table, d_ac_symv, d_ac_bitmap, d_ac_keys;
+    DevBuf d_ac_skeys, d_ac_shead, d_ac_pnext, d_ac_poffs, d_ac_pbytes;
     uint64_t ac_serial = 0;              // build serial of the automaton currently held in d_ac_*
+    uint64_t ac_dfa_serial = 0;          // ... and of the dense DFA (generic K2 path), uploaded lazily
     // K4 token output of the next dr_search launches (crass_b200_ctx_set_token_output / host forms)
     uint8_t* tok_ptr = nullptr;
     uint32_t tok_stride = 0;
@@ -159,7 +161,7 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->d_bases, &c->d_offsets, &c->d_found, &c->d_skip, &c->d_hits, &c->d_pool, &c->d_counters,
                       &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv, &c->d_found_p1, &c->d_cand, &c->d_tokens, &c->d_tok_table, &c->d_tok_unique, &c->d_ac_table, &c->d_ac_symv,
-                      &c->d_ac_bitmap, &c->d_ac_keys};
+                      &c->d_ac_bitmap, &c->d_ac_keys, &c->d_ac_skeys, &c->d_ac_shead, &c->d_ac_pnext, &c->d_ac_poffs, &c->d_ac_pbytes};
     for (DevBuf* b : bufs) b->release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     cudaStreamDestroy(c->stream);
@@ -436,9 +438,18 @@ int crass_b200_ac_upload(crass_b200_ctx* c, const crass_b200_ac* ac) {
     CUDA_TRY(cudaSetDevice(c->device));
     return ensure_ac_on_device(c, const_cast<crass_b200_ac*>(ac));
 }
-uint32_t crass_b200_ac_num_states(const crass_b200_ac* ac) { return ac ? ac->a.n_states : 0; }
+// introspection of the dense DFA (built on first use: the fast path never needs it)
+uint32_t crass_b200_ac_num_states(const crass_b200_ac* ac) {
+    if (!ac) return 0;
+    cbh::ensure_dfa(&const_cast<crass_b200_ac*>(ac)->a);
+    return ac->a.n_states;
+}
 uint32_t crass_b200_ac_num_symbols(const crass_b200_ac* ac) { return ac ? ac->a.n_syms : 0; }
-uint64_t crass_b200_ac_table_bytes(const crass_b200_ac* ac) { return ac ? (uint64_t)ac->a.table.size() * 4 : 0; }
+uint64_t crass_b200_ac_table_bytes(const crass_b200_ac* ac) {
+    if (!ac) return 0;
+    cbh::ensure_dfa(&const_cast<crass_b200_ac*>(ac)->a);
+    return (uint64_t)ac->a.table.size() * 4;
+}
 
 }  // extern "C"
 
@@ -448,18 +459,37 @@ int ensure_ac_on_device(crass_b200_ctx* c, crass_b200_ac* ac) {
     // refreshed whenever a different automaton (by build serial) is used with this context.
     cbh::Automaton& a = ac->a;
     if (c->ac_serial == a.serial && a.serial != 0) return 0;
+    c->ac_dfa_serial = 0;
+    if (a.q_bits) {                                   // filter + pattern-start table (fast path)
+        struct Up { DevBuf* d; const void* h; size_t bytes; } ups[] = {
+            {&c->d_ac_bitmap, a.q_bitmap.data(), a.q_bitmap.size() * sizeof(uint32_t)},
+            {&c->d_ac_keys, a.q_keys.data(), a.q_keys.size() * sizeof(uint32_t)},
+            {&c->d_ac_skeys, a.s_keys.data(), a.s_keys.size() * sizeof(uint32_t)},
+            {&c->d_ac_shead, a.s_head.data(), a.s_head.size() * sizeof(uint32_t)},
+            {&c->d_ac_pnext, a.p_next.data(), a.p_next.size() * sizeof(uint32_t)},
+            {&c->d_ac_poffs, a.p_offs.data(), a.p_offs.size() * sizeof(uint32_t)},
+            {&c->d_ac_pbytes, a.p_bytes.data(), a.p_bytes.size()},
+        };
+        for (const Up& u : ups) {
+            if (int r = u.d->reserve(u.bytes + 16)) return r;
+            CUDA_TRY(cudaMemcpyAsync(u.d->p, u.h, u.bytes, cudaMemcpyHostToDevice, c->stream));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->ac_serial = a.serial;
+    return 0;
+}
+
+int ensure_dfa_on_device(crass_b200_ctx* c, crass_b200_ac* ac) {      // generic K2 path only
+    cbh::Automaton& a = ac->a;
+    if (c->ac_dfa_serial == a.serial && a.serial != 0) return 0;
+    cbh::ensure_dfa(&a);
     if (int r = c->d_ac_table.reserve(a.table.size() * sizeof(uint32_t))) return r;
     if (int r = c->d_ac_symv.reserve(256)) return r;
     CUDA_TRY(cudaMemcpyAsync(c->d_ac_table.p, a.table.data(), a.table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->d_ac_symv.p, a.symv, 256, cudaMemcpyHostToDevice, c->stream));
-    if (a.q_bits) {
-        if (int r = c->d_ac_bitmap.reserve(a.q_bitmap.size() * sizeof(uint32_t))) return r;
-        if (int r = c->d_ac_keys.reserve(a.q_keys.size() * sizeof(uint32_t))) return r;
-        CUDA_TRY(cudaMemcpyAsync(c->d_ac_bitmap.p, a.q_bitmap.data(), a.q_bitmap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(c->d_ac_keys.p, a.q_keys.data(), a.q_keys.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    c->ac_serial = a.serial;
+    c->ac_dfa_serial = a.serial;
     return 0;
 }
 }  // namespace
@@ -504,12 +534,15 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         else CB_ACF(19);
 #undef CB_ACF
         CUDA_TRY(cudaGetLastError());
-        cbk::k_ac_scan_list<<<c->sm_count * 8, 128, 0, st>>>(d_bases, d_offsets, cand, c->d_ac_table.as<uint32_t>(), stride_log2,
-                                                             c->d_ac_symv.as<uint8_t>(), d_found, sink);
+        cbk::PatternStarts ps{c->d_ac_pbytes.as<uint8_t>(), c->d_ac_poffs.as<uint32_t>(), c->d_ac_skeys.as<uint32_t>(),
+                              c->d_ac_shead.as<uint32_t>(), c->d_ac_pnext.as<uint32_t>(), ac->a.s_bits, ac->a.s_ones_head,
+                              ac->a.min_pattern_len};
+        cbk::k_ac_verify_list<<<c->sm_count * 8, 128, 0, st>>>(d_bases, d_offsets, cand, ps, d_found, sink);
         c->launches += 2;
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
+    if (int r = ensure_dfa_on_device(c, ac)) return r;
     const int threads = 256;
     int blocks = (int)std::min<uint64_t>(((uint64_t)n_reads + threads - 1) / threads, (uint64_t)c->sm_count * 32);
     cbk::k_ac_scan_generic<<<blocks, threads, 0, st>>>(d_bases, d_offsets, n_reads, c->d_ac_table.as<uint32_t>(), stride_log2,

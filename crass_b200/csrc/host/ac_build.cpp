@@ -1,28 +1,93 @@
-// ac_build.cpp -- compiles the non-redundant DR patterns into the automaton kernel K2 walks.
+// ac_build.cpp -- compiles the non-redundant DR patterns into what kernel K2 needs.
 //
 // The reference builds a mischasan/aho-corasick interleaved state matrix (acism_create,
 // src/aho-corasick/acism_create.c:72-132) and stops at the first callback (on_match returns 1,
 // libcrispr.cpp:441; acism.c:86-87), i.e. it only ever needs, per read, the match with the smallest
-// end offset and, among those, the longest pattern.  That is what a dense DFA (goto function with the
-// failure links folded in) with one "longest pattern ending here" value per state answers with a
-// single table load per base:
-//     entry = table[state * stride + (sym - 1)]      next = entry & 0xFFFFFF, out_len = entry >> 24
-// symv maps a byte to 1..n_syms-1, or 0 for bytes that occur in no pattern (those reset the scan to the
-// root exactly like acism.c:36-42).  States are numbered breadth-first so that the shallow states a random
-// read keeps visiting form a contiguous prefix that the kernel stages in shared memory.
+// end offset and, among those, the longest pattern.  Two device structures answer that question:
+//
+//  (1) fast path, all patterns >= 23 bytes (DRs are >= lowDRsize, so always with default options):
+//      * q-gram filter: every occurrence [a, a+len) of a pattern contains the read-aligned 16-mer that starts at
+//        8*ceil(a/8) (8i <= a+7 and 8i+16 <= a+23 <= a+len), so a read can only match if one of its 16-mers at
+//        offsets 0, 8, 16, ... is a 16-mer of some pattern.  16-mers are 2-bit codes ((byte>>1)&3: equal bytes
+//        give equal codes, the test can only over-report).  Two levels: a 2^19/2^20-bit bitmap staged in shared
+//        memory, and the exact open-addressing key table in global memory probed on bitmap hits.
+//      * start table: first 16-mer of every pattern -> chain of the patterns that begin with it.  The candidate
+//        kernel slides over the read, looks every 16-mer up and verifies the chained patterns byte by byte; the
+//        earliest end (longest pattern on ties) over all verified occurrences is exactly acism's first callback.
+//      Both are built in one linear pass over the patterns (no trie, no sorting): O(#pattern bytes).
+//  (2) generic path (some pattern < 23 bytes, or CRASS_B200_K2=generic): a dense DFA (goto function with the failure
+//      links folded in) with one "longest pattern ending here" value per state, one table load per base:
+//          entry = table[state * stride + (sym - 1)]      next = entry & 0xFFFFFF, out_len = entry >> 24
+//      symv maps a byte to 1..n_syms-1, or 0 for bytes that occur in no pattern (those reset the scan to the root
+//      exactly like acism.c:36-42).  Built lazily (ensure_dfa) because it is the expensive part.
 #include <string.h>
 
 #include <algorithm>
 #include <atomic>
-#include <queue>
 
 #include "internal.h"
 
 namespace cbh {
 
-void build_qgram_filter(Automaton* A, const uint8_t* bytes, const uint32_t* offs, uint32_t n);
-
 Automaton::~Automaton() { free_device_tables(this); }
+
+uint32_t qgram_hash(uint32_t code, uint32_t bits) { return (code * 0x9E3779B1u) >> (32 - bits); }
+
+static void build_filter_and_starts(Automaton* A) {
+    A->q_bits = 0;
+    A->q_bitmap.clear(); A->q_keys.clear(); A->s_keys.clear(); A->s_head.clear(); A->p_next.clear();
+    if (A->min_pattern_len < 23) return;                             // no aligned 16-mer guaranteed: K2 walks the DFA instead
+    const uint32_t n = A->n_patterns;
+    const uint8_t* bytes = A->p_bytes.data();
+    const uint32_t* offs = A->p_offs.data();
+    // the key table is sized for the number of 16-mer POSITIONS (an upper bound of the distinct codes), so that the
+    // codes can be inserted in one pass without sorting
+    size_t positions = 0;
+    for (uint32_t i = 0; i < n; ++i) positions += (offs[i + 1] - offs[i]) - 15;
+    uint32_t tbits = 4;
+    while (((size_t)1 << tbits) < positions * 2 + 2) ++tbits;
+    A->q_table_bits = tbits;
+    A->q_keys.assign((size_t)1 << tbits, 0xFFFFFFFFu);               // 0xFFFFFFFF = empty; the all-G 16-mer is kept in q_has_ones
+    A->q_has_ones = 0;
+    A->q_bits = positions <= 60000 ? 19 : 20;                        // 64 KB or 128 KB of shared memory
+    A->q_bitmap.assign((size_t)1 << (A->q_bits - 5), 0);
+    uint32_t sbits = 4;
+    while (((size_t)1 << sbits) < (size_t)n * 2 + 2) ++sbits;
+    A->s_bits = sbits;
+    A->s_keys.assign((size_t)1 << sbits, 0xFFFFFFFFu);
+    A->s_head.assign((size_t)1 << sbits, 0xFFFFFFFFu);
+    A->p_next.assign(n, 0xFFFFFFFFu);
+    A->s_ones_head = 0xFFFFFFFFu;
+    const uint32_t tmask = ((uint32_t)1 << tbits) - 1, smask = ((uint32_t)1 << sbits) - 1;
+    uint32_t distinct = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t len = offs[i + 1] - offs[i];
+        uint32_t code = 0;
+        for (uint32_t k = 0; k < len; ++k) {
+            code = (code >> 2) | ((uint32_t)((bytes[offs[i] + k] >> 1) & 3) << 30);   // base k of the window in bits [2k,2k+2)
+            if (k < 15) continue;
+            const uint32_t h = qgram_hash(code, A->q_bits);
+            A->q_bitmap[h >> 5] |= 1u << (h & 31);
+            if (code == 0xFFFFFFFFu) { distinct += !A->q_has_ones; A->q_has_ones = 1; }
+            else {
+                uint32_t slot = (code * 0x85EBCA6Bu) >> (32 - tbits);
+                while (A->q_keys[slot] != 0xFFFFFFFFu && A->q_keys[slot] != code) slot = (slot + 1) & tmask;
+                if (A->q_keys[slot] != code) { A->q_keys[slot] = code; ++distinct; }
+            }
+            if (k == 15) {                                           // the pattern's first 16-mer: chain it in the start table
+                if (code == 0xFFFFFFFFu) { A->p_next[i] = A->s_ones_head; A->s_ones_head = i; }
+                else {
+                    uint32_t slot = (code * 0x85EBCA6Bu) >> (32 - sbits);
+                    while (A->s_keys[slot] != 0xFFFFFFFFu && A->s_keys[slot] != code) slot = (slot + 1) & smask;
+                    A->s_keys[slot] = code;
+                    A->p_next[i] = A->s_head[slot];
+                    A->s_head[slot] = i;
+                }
+            }
+        }
+    }
+    A->q_count = distinct;
+}
 
 int build_automaton(const uint8_t* bytes, const uint32_t* offs, uint32_t n, Automaton** out) {
     if (n == 0) return fail(CRASS_B200_EINVAL, "ac_build: empty pattern set (the reference guards this case in WorkHorse.cpp:373)");
@@ -44,11 +109,27 @@ int build_automaton(const uint8_t* bytes, const uint32_t* offs, uint32_t n, Auto
     if (total >= (1u << 24)) { delete A; return fail(CRASS_B200_EINVAL, "ac_build: more than 2^24 automaton states"); }
     A->n_syms = ns;
     A->n_patterns = n;
-    const uint32_t real = ns - 1;                                   // symbols that have transitions
     uint32_t stride = 1;
-    while (stride < real) stride <<= 1;
+    while (stride < ns - 1) stride <<= 1;
     A->stride = stride;
+    A->p_bytes.assign(bytes, bytes + offs[n]);
+    A->p_bytes.resize(A->p_bytes.size() + 16, 0);                    // slack for word-wise device reads
+    A->p_offs.assign(offs, offs + n + 1);
+    build_filter_and_starts(A);
+    static std::atomic<uint64_t> next_serial{1};
+    A->serial = next_serial++;
+    *out = A;
+    return 0;
+}
 
+void ensure_dfa(Automaton* A) {
+    if (A->has_dfa) return;
+    const uint32_t n = A->n_patterns;
+    const uint8_t* bytes = A->p_bytes.data();
+    const uint32_t* offs = A->p_offs.data();
+    const uint32_t real = A->n_syms - 1;                            // symbols that have transitions
+    const uint32_t stride = A->stride;
+    const size_t total = (size_t)offs[n] + 1;
     // trie in insertion order
     std::vector<int32_t> child(total * real, -1);
     std::vector<uint16_t> depth(total, 0), term(total, 0);
@@ -95,53 +176,7 @@ int build_automaton(const uint8_t* bytes, const uint32_t* offs, uint32_t n, Auto
             A->table[(size_t)id * stride + sy] = newid[to] | ((uint32_t)term[to] << 24);
         }
     }
-    build_qgram_filter(A, bytes, offs, n);
-    static std::atomic<uint64_t> next_serial{1};
-    A->serial = next_serial++;
-    *out = A;
-    return 0;
-}
-
-// ---- q-gram pre-filter of kernel K2 ----------------------------------------------------------------------
-// Every pattern is at least 23 bytes long (DRs are >= lowDRsize), so any occurrence [a, a+len) in a read contains the
-// read-aligned 16-mer that starts at 8*ceil(a/8): 8i <= a+7 and 8i+16 <= a+23 <= a+len.  The kernel therefore only has to
-// look up the 16-mers at offsets 0, 8, 16, ... of a read in the set of all 16-mers of all patterns (2-bit codes,
-// (byte>>1)&3, so that equal bytes give equal codes and the test can only over-report).  Two levels:
-//   bitmap  2^bits-bit Bloom-style bitmap (one multiplicative hash), staged in shared memory by every CTA
-//   keys    open-addressing table of the exact 32-bit codes in global memory (L2 resident), probed only on bitmap hits
-uint32_t qgram_hash(uint32_t code, uint32_t bits) { return (code * 0x9E3779B1u) >> (32 - bits); }
-
-void build_qgram_filter(Automaton* A, const uint8_t* bytes, const uint32_t* offs, uint32_t n) {
-    A->q_bits = 0;
-    A->q_bitmap.clear(); A->q_keys.clear();
-    if (A->min_pattern_len < 23) return;                            // no guarantee of an aligned 16-mer: K2 uses the plain scan
-    std::vector<uint32_t> codes;
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t len = offs[i + 1] - offs[i];
-        uint32_t code = 0;
-        for (uint32_t k = 0; k < len; ++k) {
-            code = (code >> 2) | ((uint32_t)((bytes[offs[i] + k] >> 1) & 3) << 30);   // base k of the window in bits [2k,2k+2)
-            if (k >= 15) codes.push_back(code);
-        }
-    }
-    std::sort(codes.begin(), codes.end());
-    codes.erase(std::unique(codes.begin(), codes.end()), codes.end());
-    A->q_count = (uint32_t)codes.size();
-    A->q_bits = codes.size() <= 40000 ? 19 : 20;                     // 64 KB or 128 KB of shared memory
-    A->q_bitmap.assign((size_t)1 << (A->q_bits - 5), 0);
-    uint32_t tbits = 4;
-    while (((size_t)1 << tbits) < codes.size() * 2 + 2) ++tbits;
-    A->q_table_bits = tbits;
-    A->q_keys.assign((size_t)1 << tbits, 0xFFFFFFFFu);               // 0xFFFFFFFF = empty; the all-G 16-mer is kept in q_has_ones
-    A->q_has_ones = 0;
-    for (uint32_t c : codes) {
-        const uint32_t h = qgram_hash(c, A->q_bits);
-        A->q_bitmap[h >> 5] |= 1u << (h & 31);
-        if (c == 0xFFFFFFFFu) { A->q_has_ones = 1; continue; }
-        uint32_t slot = (c * 0x85EBCA6Bu) >> (32 - tbits);
-        while (A->q_keys[slot] != 0xFFFFFFFFu) slot = (slot + 1) & (((uint32_t)1 << tbits) - 1);
-        A->q_keys[slot] = c;
-    }
+    A->has_dfa = true;
 }
 
 }  // namespace cbh

@@ -83,9 +83,15 @@ struct Automaton {
     uint32_t stride = 0;                        // entries per state (n_syms rounded up to a power of two)
     uint32_t min_pattern_len = 0, max_pattern_len = 0, n_patterns = 0;
     std::vector<uint16_t> out_len;              // longest pattern ending in the state (0 = none)
-    // q-gram pre-filter (ac_build.cpp): empty when the shortest pattern is below 23 bytes
+    bool has_dfa = false;                       // table/out_len are built lazily by ensure_dfa()
+    // the patterns themselves (+16 bytes of slack), kept for the verify kernel and the lazy DFA
+    std::vector<uint8_t> p_bytes;
+    std::vector<uint32_t> p_offs;
+    // q-gram pre-filter + pattern-start table (ac_build.cpp): empty when the shortest pattern is below 23 bytes
     uint32_t q_bits = 0, q_table_bits = 0, q_count = 0, q_has_ones = 0;
     std::vector<uint32_t> q_bitmap, q_keys;
+    uint32_t s_bits = 0, s_ones_head = 0xFFFFFFFFu;
+    std::vector<uint32_t> s_keys, s_head, p_next;
     // device copies, owned by the context that uploaded them
     void* d_table = nullptr;
     void* d_out_len = nullptr;
@@ -96,6 +102,7 @@ struct Automaton {
     ~Automaton();
 };
 int build_automaton(const uint8_t* bytes, const uint32_t* offs, uint32_t n, Automaton** out);
+void ensure_dfa(Automaton* a);                  // builds table/out_len on first use (generic K2 path, introspection)
 void free_device_tables(Automaton* a);          // implemented in the CUDA TU
 
 }  // namespace cbh

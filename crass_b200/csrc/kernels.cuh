@@ -503,7 +503,71 @@ k_ac_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs
     }
 }
 
-// ---- K2 fast path, stage 2: automaton walk over the candidate reads ---------------------------------------------
+// ---- K2 fast path, stage 2: exact verification of the candidate reads ---------------------------------------------
+// Slides over the read, looks the 16-mer starting at every position up in the pattern-start table (first 16-mer of each
+// pattern -> chain of patterns) and compares the chained patterns byte by byte.  Over all verified occurrences it keeps
+// the smallest end offset and, on ties, the longest pattern: exactly the first callback acism delivers
+// (acism.c:26-104 with on_match returning 1).  A byte that occurs in no pattern can never be inside an occurrence,
+// which is all the "reset to ROOT" rule of acism.c:36-42 means for the first match.
+struct PatternStarts {
+    const uint8_t* p_bytes;
+    const uint32_t* p_offs;
+    const uint32_t* s_keys;
+    const uint32_t* s_head;
+    const uint32_t* p_next;
+    uint32_t s_bits, s_ones_head, min_len;
+};
+
+__global__ void __launch_bounds__(128)
+k_ac_verify_list(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ cand_list,
+                 PatternStarts ps, uint8_t* __restrict__ found, HitSink sink) {
+    const uint32_t n_cand = sink.counters[3];
+    const uint32_t nthreads = gridDim.x * blockDim.x;
+    const uint32_t smask = (1u << ps.s_bits) - 1u;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cand; c += nthreads) {
+        const uint32_t r = cand_list[c];
+        const uint64_t b = offsets[r];
+        const uint32_t L = (uint32_t)(offsets[r + 1] - b);
+        const uint8_t* s = bases + b;
+        uint32_t best_end = 0xFFFFFFFFu, best_len = 0, code = 0;
+        for (uint32_t i = 0; i < L; ++i) {
+            code = (code >> 2) | ((uint32_t)((__ldg(s + i) >> 1) & 3u) << 30);
+            if (i < 15) continue;
+            const uint32_t p = i - 15;                               // start of this 16-mer
+            if (best_len && p + ps.min_len > best_end) break;        // later starts cannot end earlier
+            uint32_t pi;
+            if (code == 0xFFFFFFFFu) pi = ps.s_ones_head;
+            else {
+                uint32_t slot = (code * 0x85EBCA6Bu) >> (32 - ps.s_bits);
+                for (;;) {
+                    const uint32_t k = __ldg(ps.s_keys + slot);
+                    if (k == code) { pi = __ldg(ps.s_head + slot); break; }
+                    if (k == 0xFFFFFFFFu) { pi = 0xFFFFFFFFu; break; }
+                    slot = (slot + 1) & smask;
+                }
+            }
+            for (; pi != 0xFFFFFFFFu; pi = __ldg(ps.p_next + pi)) {
+                const uint32_t po = __ldg(ps.p_offs + pi), len = __ldg(ps.p_offs + pi + 1) - po;
+                if (p + len > L) continue;
+                const uint32_t end = p + len;
+                if (end > best_end || (end == best_end && len <= best_len)) continue;
+                bool same = true;
+                for (uint32_t k = 0; k < len; ++k)
+                    if (__ldg(s + p + k) != __ldg(ps.p_bytes + po + k)) { same = false; break; }
+                if (same) { best_end = end; best_len = len; }
+            }
+        }
+        if (best_len) {
+            uint32_t dr_end = best_end - 1;                          // on_match (libcrispr.cpp:420-437)
+            if (dr_end >= L) dr_end = L - 1;
+            uint32_t ss[2] = { dr_end - (best_len - 1), dr_end };
+            found[r] = 1;
+            emit_hit(sink, r, ss, 2, 0);
+        }
+    }
+}
+
+// ---- K2 generic helper: automaton walk over a candidate list (kept for pattern sets the verify kernel cannot take) -----
 __global__ void __launch_bounds__(128)
 k_ac_scan_list(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ cand_list,
                const uint32_t* __restrict__ table, uint32_t stride_log2, const uint8_t* __restrict__ symv_g,
