@@ -165,52 +165,79 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
     std::vector<uint32_t> unseen_int;
     std::vector<std::string> unseen_str;
     std::vector<std::pair<int, int> > counts;                             // (group, shared so far)
-    for (size_t t = 0; t < drs.size(); ++t) {
-        const std::string& dr = drs[t];
-        const long n_mers = (long)dr.size() - (long)kClusterKmer + 1;
-        unseen_int.clear(); unseen_str.clear(); counts.clear();
-        int group = 0;
-        uint32_t fw = 0, rc = 0;
-        int valid = 0;                                                   // trailing run of A/C/G/T bytes
+    // pass A (no dependencies, streams through the strings): canonical integer key of every k-mer, kStr for the rare
+    // k-mers that need the string map
+    const uint32_t kStr = 0xFFFFFFFFu;
+    std::vector<uint32_t> keys(total_kmers);
+    std::vector<size_t> koff(drs.size() + 1, 0);
+    {
+        size_t w = 0;
         const uint32_t kmask = (1u << (2 * kClusterKmer)) - 1u;
-        for (long p = 0; p < (long)dr.size(); ++p) {
-            const int c = kCode[(uint8_t)dr[(size_t)p]];
-            if (c < 0) valid = 0;
-            else { valid++; fw = ((fw << 2) | (uint32_t)c) & kmask; rc = (rc >> 2) | ((uint32_t)(3 - c) << (2 * (kClusterKmer - 1))); }
-            const long i = p - (long)kClusterKmer + 1;                    // k-mer start
-            if (i < 0 || i >= n_mers) continue;
-            int known = 0;                                               // group of this k-mer, 0 = never seen
-            if (valid >= (int)kClusterKmer) {
-                const uint32_t key = fw < rc ? fw : rc;
-                const size_t s = slot_of(key);
-                if (tkey[s] == key) known = tval[s]; else unseen_int.push_back(key);
-            } else {
-                std::string km = low_lexi_kmer(dr, (size_t)i);
-                bool acgt = true;
-                uint32_t key = 0;
-                for (char ch : km) { const int c2 = kCode[(uint8_t)ch]; if (c2 < 0) { acgt = false; break; } key = (key << 2) | (uint32_t)c2; }
-                if (acgt) {                                              // e.g. a 'U' whose reverse complement is all A/C/G/T
-                    const size_t s = slot_of(key);
-                    if (tkey[s] == key) known = tval[s]; else unseen_int.push_back(key);
-                } else {
-                    auto it = kmer_group_str.find(km);
-                    if (it != kmer_group_str.end()) known = it->second; else unseen_str.push_back(km);
+        for (size_t t = 0; t < drs.size(); ++t) {
+            const std::string& dr = drs[t];
+            koff[t] = w;
+            uint32_t fw = 0, rc = 0;
+            int valid = 0;                                               // trailing run of A/C/G/T bytes
+            for (size_t p = 0; p < dr.size(); ++p) {
+                const int c = kCode[(uint8_t)dr[p]];
+                if (c < 0) valid = 0;
+                else { valid++; fw = ((fw << 2) | (uint32_t)c) & kmask; rc = (rc >> 2) | ((uint32_t)(3 - c) << (2 * (kClusterKmer - 1))); }
+                if (p + 1 < kClusterKmer) continue;
+                uint32_t key = kStr;
+                if (valid >= (int)kClusterKmer) key = fw < rc ? fw : rc;
+                else {
+                    const std::string km = low_lexi_kmer(dr, p + 1 - kClusterKmer);
+                    uint32_t k2 = 0; bool acgt = true;                   // e.g. a 'U' whose reverse complement is all A/C/G/T
+                    for (char ch : km) { const int c2 = kCode[(uint8_t)ch]; if (c2 < 0) { acgt = false; break; } k2 = (k2 << 2) | (uint32_t)c2; }
+                    if (acgt) key = k2;
                 }
+                keys[w++] = key;
             }
-            if (!known || group) continue;
-            auto c2 = std::find_if(counts.begin(), counts.end(), [&](const std::pair<int, int>& q) { return q.first == known; });
+        }
+        koff[drs.size()] = w;
+    }
+    // pass B (no dependencies either): first[q] = index of the first DR, in token order, that contains k-mer q.
+    // A k-mer is "seen globally" for DR t exactly when first[q] < t, and its group is the group of that first DR:
+    // the reference hands its homeless k-mers to the DR's group when the DR is done (WorkHorse.cpp:1611-1617).
+    // One hash probe per k-mer with the probes prefetched a fixed distance ahead.
+    std::vector<uint32_t> first(total_kmers);
+    {
+        const size_t kAhead = 24;
+        size_t t = 0;
+        for (size_t q = 0; q < total_kmers; ++q) {
+            if (q + kAhead < total_kmers && keys[q + kAhead] != kStr) {
+                const size_t s = (size_t)(keys[q + kAhead] * 0x9E3779B1u) & (tsize - 1);
+                __builtin_prefetch(&tkey[s]); __builtin_prefetch(&tval[s]);
+            }
+            while (q >= koff[t + 1]) ++t;
+            const uint32_t key = keys[q];
+            if (key != kStr) {
+                const size_t s = slot_of(key);
+                if (tkey[s] != key) { tkey[s] = key; tval[s] = (int)t; touched.push_back(s); }
+                first[q] = (uint32_t)tval[s];
+            } else {
+                auto ins = kmer_group_str.emplace(low_lexi_kmer(drs[t], q - koff[t]), (int)t);
+                first[q] = (uint32_t)ins.first->second;
+            }
+        }
+    }
+    // pass C (the order-dependent greedy walk, now on small sequential arrays only)
+    std::vector<int> group_of(drs.size(), 0);
+    for (size_t t = 0; t < drs.size(); ++t) {
+        counts.clear();
+        int group = 0;
+        for (size_t q = koff[t]; q < koff[t + 1] && !group; ++q) {
+            if (first[q] >= t) continue;                                 // never seen before this DR
+            const int known = group_of[first[q]];
+            auto c2 = std::find_if(counts.begin(), counts.end(), [&](const std::pair<int, int>& p) { return p.first == known; });
             if (c2 == counts.end()) counts.push_back(std::make_pair(known, 1));
             else if (++c2->second >= min_count) group = known;
         }
         if (!group) { members.emplace_back(); group = (int)members.size(); }
+        group_of[t] = group;
         members[group - 1].push_back((int)t + 2);
-        for (uint32_t key : unseen_int) {
-            const size_t s = slot_of(key);
-            if (tkey[s] != key) touched.push_back(s);
-            tkey[s] = key; tval[s] = group;
-        }
-        for (const std::string& km : unseen_str) kmer_group_str[km] = group;
     }
+    (void)unseen_int; (void)unseen_str;
     // (2) per group: drop every variant that contains a shorter surviving variant (either strand), then emit
     //     the survivors followed by their reverse complements.
     //     Groups are independent, so they are spread over a few worker threads; the output order (group id, then
