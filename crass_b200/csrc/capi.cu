@@ -254,6 +254,23 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
+    // Long reads (config 3): one warp per read, 2-bit window flags in shared memory, warp-cooperative candidate handling.
+    const bool geometry_ok = o.window == 8 && cb::window_skips(o) == 8 && o.low_dr + o.low_spacer == 49 && o.high_dr + o.high_spacer == 97;
+    if (geometry_ok && max_read_len > 304 && max_read_len <= 65536 && (((uintptr_t)d_bases) & 15) == 0 && !(force && !strcmp(force, "generic"))) {
+        const uint32_t words = max_read_len / 16 + 32;
+        const size_t smem = (size_t)cbk::kLongWarps * 2 * words * sizeof(uint32_t);
+        CUDA_TRY(cudaFuncSetAttribute(cbk::k_dr_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbk::k_dr_long, cbk::kLongWarps * 32, smem));
+        const uint32_t want_blocks = (n_reads + cbk::kLongWarps - 1) / cbk::kLongWarps;
+        const int blocks = (int)std::min<uint32_t>(want_blocks, (uint32_t)(c->sm_count * std::max(per_sm, 1)));
+        if (int r = c->d_scratch.reserve((size_t)blocks * cbk::kLongWarps * 2 * cap * sizeof(uint32_t))) return r;
+        cbk::k_dr_long<<<blocks, cbk::kLongWarps * 32, smem, st>>>(d_bases, d_offsets, n_reads, o, d_found, sink, c->d_scratch.as<uint32_t>(), cap,
+                                                                   c->d_error.as<int>(), words);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     if (cap <= 32) {
         int blocks = (int)std::min<uint64_t>(((uint64_t)n_reads + threads - 1) / threads, (uint64_t)c->sm_count * 64);
         cbk::k_dr_search_generic<32><<<blocks, threads, 0, st>>>(d_bases, d_offsets, n_reads, o, d_found, sink, nullptr, 0, c->d_error.as<int>());

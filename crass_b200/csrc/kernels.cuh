@@ -11,6 +11,7 @@
 #include "../../include/crass_b200.h"
 #include "dr_core.cuh"
 #include "dr_filter.cuh"
+#include "dr_long.cuh"
 
 namespace cbk {
 
@@ -368,6 +369,107 @@ k_dr_exact_packed(const uint8_t* __restrict__ bases, const uint64_t* __restrict_
             found[r] = 1;
             const uint32_t slot = emit_hit(sink, r, ss, st.n_ss, st.replen);
             if (sink.tokens && slot != 0xFFFFFFFFu) emit_token(sink.tokens + (size_t)slot * sink.token_stride, sink.token_stride, s, L, ss, st.n_ss);
+        }
+        __syncwarp();
+    }
+}
+
+// ---- K1 for long reads: one warp per read (dr_long.cuh) -------------------------------------------------------
+constexpr int kLongWarps = 4;
+
+__global__ void __launch_bounds__(kLongWarps * 32)
+k_dr_long(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads, Params o,
+          uint8_t* __restrict__ found, HitSink sink, uint32_t* __restrict__ ss_scratch, uint32_t ss_cap, int* __restrict__ error_flag,
+          uint32_t words_per_warp) {
+    extern __shared__ uint32_t long_smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    uint32_t* P = long_smem + (size_t)warp * 2 * words_per_warp;      // packed, aligned to the 16-byte grid of the batch
+    uint32_t* S = P + words_per_warp;                                   // packed, aligned to the read start, zero padded
+    const uint32_t gw = blockIdx.x * kLongWarps + warp, nw = gridDim.x * kLongWarps;
+    uint32_t* ss = ss_scratch + (size_t)gw * 2 * ss_cap;
+    float* sims = reinterpret_cast<float*>(ss + ss_cap);
+    const uint64_t n_bases = offsets[n_reads];
+    for (uint32_t r = gw; r < n_reads; r += nw) {
+        const uint64_t b = offsets[r];
+        const uint32_t L = (uint32_t)(offsets[r + 1] - b);
+        const int se = cb::search_end(o, L);
+        if (se < 0) { if (lane == 0 && found) found[r] = 0; continue; }
+        cbl::GSeq s{bases + b};
+        const uint64_t a0 = b & ~(uint64_t)15;
+        const uint32_t shb = (uint32_t)(b & 15u);
+        const uint32_t nvec = (shb + L + 15) >> 4;
+        for (uint32_t v = lane; v < nvec + 2; v += 32) {
+            uint32_t w = 0;
+            if (v < nvec) {
+                const uint64_t at = a0 + 16ull * v;
+                if (at + 16 <= n_bases) {
+                    const uint4 x = ldg_stream128(bases + at);
+                    w = cb::pack16(x.x, x.y, x.z, x.w);
+                } else {
+                    uint32_t q[4] = {0, 0, 0, 0};
+                    for (int i = 0; i < 16; ++i)
+                        if (at + i < n_bases) q[i >> 2] |= (uint32_t)__ldg(bases + at + i) << (8 * (i & 3));
+                    w = cb::pack16(q[0], q[1], q[2], q[3]);
+                }
+            }
+            P[v] = w;
+        }
+        __syncwarp();
+        const uint32_t nW = (L + 15) >> 4;
+        for (uint32_t k = lane; k < nW + 24; k += 32) S[k] = k < nW ? cb::funnel_r(P[k], P[k + 1], 2 * shb) : 0u;
+        __syncwarp();
+        uint32_t base = 0, n_ss = 0, replen = 0;
+        int result = 0;
+        for (;;) {                                                      // one iteration per phase of the window grid
+            const uint32_t q = base >> 4, sh = 2 * (base & 15u);
+            const uint32_t nwin = ((uint32_t)se - base) / 8 + 1;
+            const uint32_t nseg = (nwin + 11) / 12;
+            bool restart = false, finished = false;
+            for (uint32_t seg0 = 0; seg0 < nseg && !restart && !finished; seg0 += 32) {
+                const uint32_t seg = seg0 + lane;
+                uint32_t mask = 0;
+                if (seg < nseg) {
+                    uint32_t Q[15];
+                    const uint32_t i0 = q + 6 * seg;
+#pragma unroll
+                    for (int i = 0; i < 15; ++i) Q[i] = cb::funnel_r(S[i0 + i], S[i0 + i + 1], sh);
+                    uint32_t acc[6];
+                    cb::seed_flags<13, 6, 49, 97>(Q, acc);
+                    mask = cb::flag_mask<6>(acc);
+                    const uint32_t nvalid = nwin - 12 * seg;
+                    if (nvalid < 12) mask &= (1u << nvalid) - 1u;
+                }
+                uint32_t bal = __ballot_sync(cbl::kFull, mask != 0);
+                while (bal && !restart && !finished) {
+                    const int f = __ffs((int)bal) - 1;
+                    const uint32_t m = __shfl_sync(cbl::kFull, mask, f);
+                    const int h = __ffs((int)m) - 1;
+                    if ((int)lane == f) mask &= mask - 1;
+                    const uint32_t j = base + 8u * (12u * (seg0 + (uint32_t)f) + (uint32_t)h);
+                    uint32_t begin, end;
+                    cb::window_text(o, L, j, begin, end);
+                    const int pos = cbl::warp_find_left8(s, begin, end, j);
+                    if (pos >= 0) {
+                        bool advance = false; uint32_t nj = 0;
+                        const int rr = cbl::warp_process_seed(s, L, o, j, begin + (uint32_t)pos, ss, n_ss, ss_cap, replen, advance, nj, sims);
+                        if (rr != 0) { result = rr; finished = true; }
+                        else if (advance) {
+                            base = nj + 8u;
+                            if (base > (uint32_t)se) finished = true; else restart = true;
+                        }
+                    }
+                    bal = __ballot_sync(cbl::kFull, mask != 0);
+                }
+            }
+            if (!restart) break;
+        }
+        if (lane == 0) {
+            if (found) found[r] = result == 1;
+            if (result < 0) *error_flag = result;
+            if (result == 1) {
+                const uint32_t slot = emit_hit(sink, r, ss, n_ss, replen);
+                if (sink.tokens && slot != 0xFFFFFFFFu) emit_token(sink.tokens + (size_t)slot * sink.token_stride, sink.token_stride, s, L, ss, n_ss);
+            }
         }
         __syncwarp();
     }

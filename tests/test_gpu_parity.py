@@ -213,13 +213,36 @@ def test_edge_batches(ctx, P, k1path):
     check_batch_against_oracle(ctx, P, ragged)
 
 
-def test_long_reads(ctx, P):
+def test_long_reads(ctx, P, k1path):
+    """BASELINE.json configs[2]: 1-10 kb reads (warp-per-read kernel on the fast path, generic kernel otherwise)."""
     rng = random.Random(104)
     reads = []
-    for _ in range(200):
+    for _ in range(400):
         L = rng.randint(1000, 10000)
         reads.append(fuzzgen.planted_read(rng, L, sub_rate=rng.choice([0, 0.005, 0.02])) if rng.random() < 0.6 else fuzzgen.rand_seq(rng, L))
-    assert check_batch_against_oracle(ctx, P, reads) > 40
+    assert check_batch_against_oracle(ctx, P, reads) > 80
+
+
+def test_long_reads_mixed_lengths_and_odd_content(ctx, P, k1path):
+    """Ragged batch around the long-read kernel: empty / sub-58 / short / long reads, microsatellites (window grid keeps
+    re-phasing), N and lower case, tandem arrays with many repeats."""
+    rng = random.Random(107)
+    reads = [b"", b"ACGT", fuzzgen.rand_seq(rng, 57), fuzzgen.rand_seq(rng, 58)]
+    for _ in range(500):
+        L = rng.choice([60, 150, 305, 306, 777, 1500, 3000, 6000])
+        kind = rng.random()
+        if kind < 0.25:
+            s = fuzzgen.rand_seq(rng, L)
+        elif kind < 0.75:
+            s = fuzzgen.planted_read(rng, L, sub_rate=rng.choice([0, 0.01]))
+        elif kind < 0.9:
+            s = fuzzgen.microsat_read(rng, L)
+        else:
+            s = fuzzgen.planted_read(rng, L, spacer_lo=rng.randint(1, 30), spacer_hi=rng.randint(30, 60), jitter=rng.randint(0, 12))
+        if rng.random() < 0.2:
+            s = fuzzgen.mutate(rng, s, 0.01, b"NnacgtRY")
+        reads.append(s)
+    assert check_batch_against_oracle(ctx, P, reads) > 100
 
 
 def test_synthetic_config2_prefix(ctx, P, k1path):
