@@ -559,6 +559,28 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
+    if (ac->a.q_bits && max_read_len > 304 && (((uintptr_t)d_bases) & 15) == 0 && !(force && !strcmp(force, "generic"))) {
+        // long reads: warp-per-read q-gram filter, then the same verify kernel over the candidates
+        if (!d_found) { if (int r = c->d_found.reserve((size_t)n_reads + 16)) return r; d_found = c->d_found.as<uint8_t>(); }
+        if (int r = c->d_cand.reserve(((size_t)n_reads + 16) * sizeof(uint32_t))) return r;
+        uint32_t* cand = c->d_cand.as<uint32_t>();
+        cbk::QgramFilter q{c->d_ac_bitmap.as<uint32_t>(), c->d_ac_keys.as<uint32_t>(), ac->a.q_bits, ac->a.q_table_bits, ac->a.q_has_ones};
+        const size_t smem = ((size_t)1 << ac->a.q_bits) / 8;
+        CUDA_TRY(cudaFuncSetAttribute(cbk::k_ac_filter_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 1;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbk::k_ac_filter_long, cbk::kAcLongThreads, smem));
+        const uint32_t want_blocks = (n_reads + (cbk::kAcLongThreads / 32) - 1) / (cbk::kAcLongThreads / 32);
+        const int blocks = (int)std::min<uint32_t>(want_blocks, (uint32_t)(c->sm_count * std::max(per_sm, 1)));
+        cbk::k_ac_filter_long<<<blocks, cbk::kAcLongThreads, smem, st>>>(d_bases, d_offsets, n_reads, q, d_skip, d_found, cand, d_counters);
+        CUDA_TRY(cudaGetLastError());
+        cbk::PatternStarts ps{c->d_ac_pbytes.as<uint8_t>(), c->d_ac_poffs.as<uint32_t>(), c->d_ac_skeys.as<uint32_t>(),
+                              c->d_ac_shead.as<uint32_t>(), c->d_ac_pnext.as<uint32_t>(), ac->a.s_bits, ac->a.s_ones_head,
+                              ac->a.min_pattern_len};
+        cbk::k_ac_verify_list<<<c->sm_count * 8, 128, 0, st>>>(d_bases, d_offsets, cand, ps, d_found, sink);
+        c->launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     if (int r = ensure_dfa_on_device(c, ac)) return r;
     const int threads = 256;
     int blocks = (int)std::min<uint64_t>(((uint64_t)n_reads + threads - 1) / threads, (uint64_t)c->sm_count * 32);

@@ -605,6 +605,68 @@ k_ac_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs
     }
 }
 
+// ---- K2 fast path for long reads: the same 16-mer filter, one warp per read -------------------------------------------
+// Lanes take consecutive 16-byte vectors of the read (coalesced), recode them to one word each, fetch the neighbour's
+// word with a shuffle and test the two read-aligned 16-mers that start inside their vector (offsets == read start mod 8).
+constexpr int kAcLongThreads = 256;
+
+__global__ void __launch_bounds__(kAcLongThreads)
+k_ac_filter_long(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads, QgramFilter q,
+                 const uint8_t* __restrict__ skip, uint8_t* __restrict__ found, uint32_t* __restrict__ cand_list,
+                 uint32_t* __restrict__ counters) {
+    extern __shared__ uint32_t dsm[];
+    uint32_t* bm = dsm;
+    for (uint32_t i = threadIdx.x; i < (1u << (q.bits - 5)); i += kAcLongThreads) bm[i] = __ldg(q.bitmap + i);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gw = (blockIdx.x * kAcLongThreads + threadIdx.x) >> 5, nw = (gridDim.x * kAcLongThreads) >> 5;
+    const uint64_t n_bases = offsets[n_reads];
+    const uint32_t hshift = 32 - q.bits;
+    for (uint32_t r = gw; r < n_reads; r += nw) {
+        if (lane == 0) found[r] = 0;
+        if (skip && skip[r]) continue;
+        const uint64_t b = offsets[r];
+        const uint32_t L = (uint32_t)(offsets[r + 1] - b);
+        if (L < 16) continue;
+        const uint64_t a0 = b & ~(uint64_t)15;
+        const uint32_t shb = (uint32_t)(b & 15u), d = shb & 7u;
+        const uint32_t nvec = (shb + L + 15) >> 4;
+        const uint32_t x_end = shb + L;                             // one past the last base, in stream coordinates
+        bool cand = false;
+        for (uint32_t v0 = 0; v0 < nvec && !cand; v0 += 31) {
+            const uint32_t v = v0 + lane;
+            uint32_t w = 0;
+            if (v < nvec) {
+                const uint64_t at = a0 + 16ull * v;
+                if (at + 16 <= n_bases) {
+                    const uint4 x = ldg_stream128(bases + at);
+                    w = cb::pack16(x.x, x.y, x.z, x.w);
+                } else {
+                    uint32_t qq[4] = {0, 0, 0, 0};
+                    for (int i = 0; i < 16; ++i)
+                        if (at + i < n_bases) qq[i >> 2] |= (uint32_t)__ldg(bases + at + i) << (8 * (i & 3));
+                    w = cb::pack16(qq[0], qq[1], qq[2], qq[3]);
+                }
+            }
+            const uint32_t wn = __shfl_down_sync(0xFFFFFFFFu, w, 1);
+            bool hit = false;
+            if (lane < 31 && v < nvec) {
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const uint32_t x = 16u * v + d + 8u * (uint32_t)t;          // start of the 16-mer in stream coordinates
+                    if (x >= shb && x + 16 <= x_end) {
+                        const uint32_t code = cb::funnel_r(w, wn, 2u * (d + 8u * (uint32_t)t));
+                        const uint32_t h = (code * 0x9E3779B1u) >> hshift;
+                        if ((bm[h >> 5] >> (h & 31u)) & 1u) hit = hit || qgram_member(q, code);
+                    }
+                }
+            }
+            cand = __any_sync(0xFFFFFFFFu, hit);
+        }
+        if (cand && lane == 0) cand_list[atomicAdd(&counters[3], 1u)] = r;
+    }
+}
+
 // ---- K2 fast path, stage 2: exact verification of the candidate reads ---------------------------------------------
 // Slides over the read, looks the 16-mer starting at every position up in the pattern-start table (first 16-mer of each
 // pattern -> chain of patterns) and compares the chained patterns byte by byte.  Over all verified occurrences it keeps

@@ -309,6 +309,39 @@ def test_singleton_scan_fuzz(ctx, P, k2path):
         P.ac_destroy(h)
 
 
+def test_singleton_scan_long_reads(ctx, P, k2path):
+    """K2 on 0.3-8 kb reads (warp-per-read q-gram filter + verify, or the generic automaton walk)."""
+    rng = random.Random(108)
+    pats = fuzzgen.dr_like_patterns(rng, 200)
+    texts = []
+    for _ in range(600):
+        t = fuzzgen.rand_seq(rng, rng.choice([15, 16, 305, 400, 1000, 3000, 8000]), b"ACGTN" if rng.random() < 0.2 else b"ACGT")
+        for _k in range(rng.choice([0, 0, 1, 1, 3])):
+            if len(t) > 60:
+                p = rng.choice(pats)
+                if rng.random() < 0.3:
+                    p = p[:-1]                                             # near miss
+                pos = rng.randint(0, len(t) - 1)
+                t = (t[:pos] + p + t[pos:])[:len(t)]
+        texts.append(t)
+    skip = np.array([rng.random() < 0.1 for _ in texts], dtype=np.uint8)
+    bases, offs = cb.pack_reads(texts)
+    hits, pool, found = ctx.ac_scan(cb.Automaton(pats), bases, offs, skip)
+    got = hits_by_read(hits, pool)
+    h = P.ac_create(pats)
+    n_match = 0
+    for i, t in enumerate(texts):
+        m = None if skip[i] else P.ac_first_match(h, t)
+        if m is None:
+            assert i not in got and found[i] == 0
+        else:
+            n_match += 1
+            dr_end = min(m[0] - 1, len(t) - 1)
+            assert got[i] == ([dr_end - (m[1] - 1), dr_end], 0)
+    P.ac_destroy(h)
+    assert n_match > 150
+
+
 def test_whole_path_synthetic_against_oracle(ctx, P, tmp_path):
     """Both phases + clustering on a synthetic FASTA file: the product's dump must equal the oracle's."""
     genome, drs, _ = synth.make_genome(777, n_dr_types=12, array_fraction=0.05)
