@@ -731,6 +731,65 @@ k_ac_verify_list(const uint8_t* __restrict__ bases, const uint64_t* __restrict__
     }
 }
 
+// Same verification with one WARP per candidate (long reads: a single thread walking 10 kb of dependent table probes
+// is latency-bound).  Lanes take 32 consecutive start positions per round; every lane keeps its own best occurrence,
+// the warp minimum of (end, -len) is the answer.  The scan stops once no later start can end earlier.
+__global__ void __launch_bounds__(128)
+k_ac_verify_warp(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ cand_list,
+                 PatternStarts ps, uint8_t* __restrict__ found, HitSink sink) {
+    const uint32_t n_cand = sink.counters[3];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t smask = (1u << ps.s_bits) - 1u;
+    for (uint32_t c = gw; c < n_cand; c += nw) {
+        const uint32_t r = cand_list[c];
+        const uint64_t b = offsets[r];
+        const uint32_t L = (uint32_t)(offsets[r + 1] - b);
+        const uint8_t* s = bases + b;
+        uint32_t best = 0xFFFFFFFFu;                                  // (end << 8) | (255 - len): min == earliest end, longest pattern
+        for (uint32_t p0 = 0; p0 + 16 <= L; p0 += 32) {
+            const uint32_t warp_best = __reduce_min_sync(0xFFFFFFFFu, best);
+            if (warp_best != 0xFFFFFFFFu && p0 + ps.min_len > (warp_best >> 8)) break;
+            const uint32_t p = p0 + lane;
+            if (p + 16 <= L) {
+                uint32_t code = 0;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) code |= (uint32_t)((__ldg(s + p + k) >> 1) & 3u) << (2 * k);
+                uint32_t pi;
+                if (code == 0xFFFFFFFFu) pi = ps.s_ones_head;
+                else {
+                    uint32_t slot = (code * 0x85EBCA6Bu) >> (32 - ps.s_bits);
+                    for (;;) {
+                        const uint32_t k = __ldg(ps.s_keys + slot);
+                        if (k == code) { pi = __ldg(ps.s_head + slot); break; }
+                        if (k == 0xFFFFFFFFu) { pi = 0xFFFFFFFFu; break; }
+                        slot = (slot + 1) & smask;
+                    }
+                }
+                for (; pi != 0xFFFFFFFFu; pi = __ldg(ps.p_next + pi)) {
+                    const uint32_t po = __ldg(ps.p_offs + pi), len = __ldg(ps.p_offs + pi + 1) - po;
+                    if (p + len > L) continue;
+                    const uint32_t key = ((p + len) << 8) | (255u - len);
+                    if (key >= best) continue;
+                    bool same = true;
+                    for (uint32_t k = 0; k < len; ++k)
+                        if (__ldg(s + p + k) != __ldg(ps.p_bytes + po + k)) { same = false; break; }
+                    if (same) best = key;
+                }
+            }
+        }
+        best = __reduce_min_sync(0xFFFFFFFFu, best);
+        if (best != 0xFFFFFFFFu && lane == 0) {
+            const uint32_t best_end = best >> 8, best_len = 255u - (best & 255u);
+            uint32_t dr_end = best_end - 1;                          // on_match (libcrispr.cpp:420-437)
+            if (dr_end >= L) dr_end = L - 1;
+            uint32_t ss[2] = { dr_end - (best_len - 1), dr_end };
+            found[r] = 1;
+            emit_hit(sink, r, ss, 2, 0);
+        }
+    }
+}
+
 // ---- K2 generic helper: automaton walk over a candidate list (kept for pattern sets the verify kernel cannot take) -----
 __global__ void __launch_bounds__(128)
 k_ac_scan_list(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ cand_list,
