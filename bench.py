@@ -135,6 +135,7 @@ def main():
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU (weak scaling)")
     ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-dr-list", default=None, help="write the merged DR list of the last step here (host-side tuning input)")
     args = ap.parse_args()
 
     # stdout carries exactly ONE JSON line: everything libraries print while the run is going on (e.g. NCCL's version
@@ -221,7 +222,7 @@ def main():
 
     TOK = 64                                                           # bytes per K4 token record (>= high_dr + 2)
     d_tokens = torch.empty(hits_cap * TOK, dtype=torch.uint8, device=dev)
-    host_ms = {"fetch": [], "dr_list": [], "merge": [], "cluster": [], "ac_build": []}
+    host_ms = {"fetch": [], "merge": [], "cluster_build": [], "ac_upload": []}
 
     d_utok = torch.empty(hits_cap * TOK, dtype=torch.uint8, device=dev)
     d_ufr = torch.empty(hits_cap, dtype=torch.int32, device=dev)
@@ -259,18 +260,18 @@ def main():
         ctx.unique_tokens_dev(d_hits, nh, d_tokens, TOK, d_utok, d_ufr, d_ucnt, stream)   # K4b: distinct tokens + first read
         fetch_hits_async(0, nh, npool)                                 # the phase-1 hit records travel while the host clusters
         nu = int(d_ucnt[:1].cpu()[0])
-        utok = d_utok[: max(nu, 1) * TOK].cpu().numpy()
-        ufr = d_ufr[: max(nu, 1)].cpu().numpy().view(np.uint32)[:nu]
         t1 = time.perf_counter()
-        local = api.dr_list_from_unique(utok, TOK, ufr)                # distinct low-lexi DRs in first-appearance order
-        t2 = time.perf_counter()
-        merged = merge_dr_lists(local)
+        # distinct low-lexi DRs of all shards in first-appearance order: one NCCL all-gather of the K4b records and a
+        # deterministic merge (crass_b200/dist.py); at N=1 just the device-to-host copy of this shard's records
+        merged = cbdist.allgather_unique_tokens(d_utok, d_ufr, nu, TOK)
         t3 = time.perf_counter()
-        pats = api.non_redundant_list(merged, params.kmer_clust)
+        if args.dump_dr_list and rank == 0 and not record:
+            open(args.dump_dr_list, "wb").write(merged)
+        ac = cb.Automaton.from_dr_list(merged, params.kmer_clust) if merged else None   # createNonRedundantSet + matcher
+        pats = ac.num_patterns if ac else 0
         t4 = time.perf_counter()
         n2 = 0
         if pats:
-            ac = cb.Automaton(pats)
             ctx.ac_upload(ac)
             t5 = time.perf_counter()
             e[2].record()
@@ -284,19 +285,17 @@ def main():
             kt["k1"].append(e[0].elapsed_time(e[1]))
             if pats:
                 kt["k2"].append(e[2].elapsed_time(e[3]))
-                for k, v in zip(("fetch", "dr_list", "merge", "cluster", "ac_build"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+                for k, v in zip(("fetch", "merge", "cluster_build", "ac_upload"), (t1 - t0, t3 - t1, t4 - t3, t5 - t4)):
                     host_ms[k].append(v * 1e3)
-        stats.update(hits_phase1=len(hits), dr_variants_local=len(local), dr_variants_merged=len(merged), patterns=len(pats), hits_phase2=n2)
+        stats.update(hits_phase1=len(hits), dr_variants_local=nu, dr_variants_merged=merged.count(b"\n"), patterns=pats, hits_phase2=n2)
 
     def step_e2e():
         ctx.upload(h_bases, h_offsets)                                 # H2D from pinned host memory
         hits, pool, _ = ctx.dr_search_resident(params)
-        local = ctx.last_dr_list()
-        merged = merge_dr_lists(local)
-        pats = api.non_redundant_list(merged, params.kmer_clust)
+        merged = merge_dr_lists(ctx.last_dr_list())
         nb = hits.nbytes + pool.nbytes
-        if pats:
-            ac = cb.Automaton(pats)
+        if merged:
+            ac = cb.Automaton.from_dr_list(merged, params.kmer_clust)
             hits2, pool2, _ = ctx.ac_scan_resident(ac, skip_found=True)
             nb += hits2.nbytes + pool2.nbytes
         return nb

@@ -114,6 +114,7 @@ def lib():
         "crass_b200_results_non_redundant": (vp, [vp, C.c_uint32, u32p]),
         "crass_b200_results_dump": (vp, [vp, C.c_int]),
         "crass_b200_non_redundant_set": (vp, [cp, C.c_uint32]),
+        "crass_b200_ac_build_from_dr_list": (C.c_int, [cp, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_uint32)]),
         "crass_b200_run_files": (C.c_int, [vp, C.POINTER(cp), C.c_uint32, C.POINTER(Params), C.c_int, C.POINTER(vp), C.POINTER(C.c_int)]),
         "crass_b200_free": (None, [vp]),
     }
@@ -246,6 +247,18 @@ class Automaton:
             offs[1:] = np.cumsum([len(p) for p in pats], dtype=np.uint32)
         self.h = C.c_void_p()
         _check(lib().crass_b200_ac_build(_np_ptr(data), _np_ptr(offs), len(pats), C.byref(self.h)))
+        self.num_patterns = len(pats)
+
+    @classmethod
+    def from_dr_list(cls, drs, kmer_clust=6):
+        """createNonRedundantSet + matcher build in one native call; `drs` in token order (list or '\\n'-joined bytes)."""
+        text = drs if isinstance(drs, (bytes, bytearray)) else b"".join((d if isinstance(d, bytes) else d.encode()) + b"\n" for d in drs)
+        self = cls.__new__(cls)
+        self.h = C.c_void_p()
+        n = C.c_uint32(0)
+        _check(lib().crass_b200_ac_build_from_dr_list(bytes(text), kmer_clust, C.byref(self.h), C.byref(n)))
+        self.num_patterns = n.value
+        return self
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -324,13 +337,17 @@ def dr_list_from_tokens(records, stride, hits):
     return [x for x in s.split(b"\n") if x]
 
 
-def dr_list_from_unique(records, stride, first_read):
-    """records/first_read: the outputs of Context.unique_tokens_dev copied to numpy -> DRs in first-appearance order."""
+def dr_list_from_unique(records, stride, first_read, raw=False):
+    """records/first_read: the outputs of Context.unique_tokens_dev copied to numpy -> DRs in first-appearance order
+    (a list, or with raw=True the '\\n'-terminated text the C-ABI hands out)."""
     s = _take_str(lib().crass_b200_dr_list_from_unique(_np_ptr(records), stride, _np_ptr(first_read), len(first_read)))
-    return [x for x in s.split(b"\n") if x]
+    return s if raw else [x for x in s.split(b"\n") if x]
 
 
 def merge_dr_lists(drs):
+    """First-appearance de-duplication; a list gives a list, '\\n'-terminated text gives text."""
+    if isinstance(drs, (bytes, bytearray)):
+        return _take_str(lib().crass_b200_merge_dr_lists(bytes(drs)))
     s = _take_str(lib().crass_b200_merge_dr_lists(b"".join(d + b"\n" for d in drs)))
     return [x for x in s.split(b"\n") if x]
 

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <sstream>
 #include <string>
+#include <string_view>
 #include <unordered_set>
 #include <vector>
 
@@ -287,9 +288,19 @@ char* crass_b200_dr_list_from_unique(const uint8_t* records, uint32_t stride, co
 }
 
 char* crass_b200_merge_dr_lists(const char* concatenated) {
-    std::map<std::string, bool> seen;
+    if (!concatenated) return dup_cstr(std::string());
+    std::unordered_set<std::string_view> seen;                                  // views into the caller's text
+    const std::string_view all(concatenated);
+    seen.reserve(all.size() / 24 + 16);
     std::string out;
-    for (const std::string& d : split_lines(concatenated)) if (seen.emplace(d, true).second) { out += d; out += '\n'; }
+    out.reserve(all.size());
+    for (size_t p = 0; p < all.size();) {
+        size_t e = all.find('\n', p);
+        if (e == std::string_view::npos) e = all.size();
+        const std::string_view d = all.substr(p, e - p);
+        if (!d.empty() && seen.insert(d).second) { out.append(d); out += '\n'; }
+        p = e + 1;
+    }
     return dup_cstr(out);
 }
 
@@ -301,6 +312,21 @@ char* crass_b200_non_redundant_set(const char* dr_list, uint32_t kmer_clust) {
     for (auto& g : groups) os << "G\t" << g.first << "\t" << g.second << "\n";
     for (auto& p : nr) os << "P\t" << p << "\n";
     return dup_cstr(os.str());
+}
+
+int crass_b200_ac_build_from_dr_list(const char* dr_list, uint32_t kmer_clust, crass_b200_ac** out, uint32_t* n_patterns) {
+    if (!dr_list || !out) return fail(CRASS_B200_EINVAL, "NULL argument");
+    const std::vector<std::string> nr = non_redundant_set(split_lines(dr_list), (int)kmer_clust, nullptr);
+    if (n_patterns) *n_patterns = (uint32_t)nr.size();
+    std::vector<uint8_t> bytes;
+    std::vector<uint32_t> offs(1, 0);
+    size_t total = 0;
+    for (const std::string& p : nr) total += p.size();
+    bytes.reserve(total + 1);
+    offs.reserve(nr.size() + 1);
+    for (const std::string& p : nr) { bytes.insert(bytes.end(), p.begin(), p.end()); offs.push_back((uint32_t)bytes.size()); }
+    if (bytes.empty()) bytes.push_back(0);
+    return crass_b200_ac_build(bytes.data(), offs.data(), (uint32_t)nr.size(), out);
 }
 
 // ---- the whole path -------------------------------------------------------------------------------------------

@@ -9,10 +9,12 @@
 //                                                   WorkHorse.cpp:648-709, 1404-1637, 612-645, 78-86
 // The GPU kernels decide WHICH reads hit and WHERE; everything here is O(hits) bookkeeping that has
 // to happen in read order on one thread because token numbers are handed out by first appearance.
+#include <limits.h>
 #include <string.h>
 
 #include <algorithm>
 #include <atomic>
+#include <functional>
 #include <sstream>
 #include <thread>
 #include <unordered_map>
@@ -114,10 +116,6 @@ std::string low_lexi_kmer(const std::string& dr, size_t pos) {            // lau
     return k < rc ? k : rc;
 }
 
-bool contains_either_strand(const std::string& longer, const std::string& shorter) {   // includeSubstring
-    if (longer.find(shorter) != std::string::npos) return true;
-    return longer.find(reverse_complement(shorter)) != std::string::npos;
-}
 }  // namespace
 
 std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, int min_count,
@@ -129,6 +127,13 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
     //     big-endian, min(forward, reverse complement) as numbers is the lexicographic minimum laurenize() takes.
     //     Anything else goes through the string map; the two key spaces cannot collide because the canonical form of
     //     a k-mer is routed by its own bytes.
+#ifdef CB_PROFILE_NR
+    auto t_mark = std::chrono::steady_clock::now();
+#define CB_NR_MARK(what) do { const auto now_ = std::chrono::steady_clock::now(); \
+        fprintf(stderr, "non_redundant_set: %-10s %.3f ms\n", what, std::chrono::duration<double, std::milli>(now_ - t_mark).count()); t_mark = now_; } while (0)
+#else
+#define CB_NR_MARK(what) do {} while (0)
+#endif
     std::unordered_map<std::string, int> kmer_group_str;
     size_t total_kmers = 0;
     for (const std::string& d : drs) if (d.size() >= kClusterKmer) total_kmers += d.size() - kClusterKmer + 1;
@@ -138,20 +143,15 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
     // only the slots this call touches are reset on the way out
     static thread_local std::vector<uint32_t> tkey_store;
     static thread_local std::vector<int> tval_store;
-    if (tkey_store.size() < tsize) { tkey_store.assign(tsize, 0xFFFFFFFFu); tval_store.assign(tsize, 0); }
+    if (tkey_store.size() < tsize) { tkey_store.assign(tsize, 0xFFFFFFFFu); tval_store.assign(tsize, INT_MAX); }
     tsize = tkey_store.size();
     uint32_t* const tkey = tkey_store.data();           // plain pointers: TLS lookups are not free inside a shared object
     int* const tval = tval_store.data();
-    std::vector<size_t> touched;
+    std::vector<std::vector<size_t> > touched_by;       // per worker: the slots it claimed
     struct Reset {
-        uint32_t* k; std::vector<size_t>& t;
-        ~Reset() { for (size_t s : t) k[s] = 0xFFFFFFFFu; }
-    } reset_on_exit{tkey, touched};
-    auto slot_of = [&](uint32_t key) {
-        size_t s = (size_t)(key * 0x9E3779B1u) & (tsize - 1);
-        while (tkey[s] != 0xFFFFFFFFu && tkey[s] != key) s = (s + 1) & (tsize - 1);
-        return s;
-    };
+        uint32_t* k; int* v; std::vector<std::vector<size_t> >& t;
+        ~Reset() { for (auto& l : t) for (size_t s : l) { k[s] = 0xFFFFFFFFu; v[s] = INT_MAX; } }
+    } reset_on_exit{tkey, tval, touched_by};
     static const int8_t kCode[256] = {
 #define X4 -1, -1, -1, -1
 #define X16 X4, X4, X4, X4
@@ -170,12 +170,32 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
     const uint32_t kStr = 0xFFFFFFFFu;
     std::vector<uint32_t> keys(total_kmers);
     std::vector<size_t> koff(drs.size() + 1, 0);
-    {
-        size_t w = 0;
+    for (size_t t = 0; t < drs.size(); ++t)
+        koff[t + 1] = koff[t] + (drs[t].size() >= kClusterKmer ? drs[t].size() - kClusterKmer + 1 : 0);
+    // passes A and B are cut into contiguous DR ranges for a few worker threads when the list is long (a merged
+    // multi-rank list, or a deep sample); the result does not depend on the cut
+    const unsigned n_workers = total_kmers > (1u << 17) ? std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency())) : 1;
+    auto for_dr_ranges = [&](const std::function<void(unsigned, size_t, size_t)>& body) {
+        if (n_workers <= 1) { body(0, 0, drs.size()); return; }
+        std::vector<std::thread> pool;
+        size_t t0 = 0;
+        for (unsigned w = 0; w < n_workers; ++w) {                      // equal shares of k-mers, not of DRs
+            const size_t want = total_kmers * (w + 1) / n_workers;
+            size_t t1 = (size_t)(std::upper_bound(koff.begin(), koff.end(), want) - koff.begin()) - 1;
+            if (w + 1 == n_workers) t1 = drs.size();
+            if (t1 < t0) t1 = t0;
+            pool.emplace_back(body, w, t0, t1);
+            t0 = t1;
+        }
+        for (auto& th : pool) th.join();
+    };
+    std::atomic<bool> any_str{false};
+    CB_NR_MARK("setup");
+    for_dr_ranges([&](unsigned, size_t t_begin, size_t t_end) {
         const uint32_t kmask = (1u << (2 * kClusterKmer)) - 1u;
-        for (size_t t = 0; t < drs.size(); ++t) {
+        for (size_t t = t_begin; t < t_end; ++t) {
             const std::string& dr = drs[t];
-            koff[t] = w;
+            size_t w = koff[t];
             uint32_t fw = 0, rc = 0;
             int valid = 0;                                               // trailing run of A/C/G/T bytes
             for (size_t p = 0; p < dr.size(); ++p) {
@@ -191,36 +211,58 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
                     for (char ch : km) { const int c2 = kCode[(uint8_t)ch]; if (c2 < 0) { acgt = false; break; } k2 = (k2 << 2) | (uint32_t)c2; }
                     if (acgt) key = k2;
                 }
+                if (key == kStr) any_str.store(true, std::memory_order_relaxed);
                 keys[w++] = key;
             }
         }
-        koff[drs.size()] = w;
-    }
+    });
+    CB_NR_MARK("pass A");
     // pass B (no dependencies either): first[q] = index of the first DR, in token order, that contains k-mer q.
     // A k-mer is "seen globally" for DR t exactly when first[q] < t, and its group is the group of that first DR:
     // the reference hands its homeless k-mers to the DR's group when the DR is done (WorkHorse.cpp:1611-1617).
     // One hash probe per k-mer with the probes prefetched a fixed distance ahead.
+    //   Workers claim a slot with a compare-and-swap on its key and lower its value with an atomic minimum, so the
+    //   table ends up holding min(t) per k-mer whatever the interleaving; untouched slots hold (empty, INT_MAX).
     std::vector<uint32_t> first(total_kmers);
-    {
+    touched_by.assign(n_workers, std::vector<size_t>());
+    for_dr_ranges([&](unsigned w, size_t t_begin, size_t t_end) {
         const size_t kAhead = 24;
-        size_t t = 0;
-        for (size_t q = 0; q < total_kmers; ++q) {
-            if (q + kAhead < total_kmers && keys[q + kAhead] != kStr) {
+        const size_t q_end = koff[t_end];
+        size_t t = t_begin;
+        for (size_t q = koff[t_begin]; q < q_end; ++q) {
+            if (q + kAhead < q_end && keys[q + kAhead] != kStr) {
                 const size_t s = (size_t)(keys[q + kAhead] * 0x9E3779B1u) & (tsize - 1);
                 __builtin_prefetch(&tkey[s]); __builtin_prefetch(&tval[s]);
             }
             while (q >= koff[t + 1]) ++t;
             const uint32_t key = keys[q];
-            if (key != kStr) {
-                const size_t s = slot_of(key);
-                if (tkey[s] != key) { tkey[s] = key; tval[s] = (int)t; touched.push_back(s); }
-                first[q] = (uint32_t)tval[s];
-            } else {
+            if (key == kStr) continue;
+            size_t s = (size_t)(key * 0x9E3779B1u) & (tsize - 1);
+            for (;;) {
+                uint32_t cur = __atomic_load_n(&tkey[s], __ATOMIC_RELAXED);
+                if (cur == key) break;
+                if (cur == 0xFFFFFFFFu) {
+                    if (__atomic_compare_exchange_n(&tkey[s], &cur, key, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { touched_by[w].push_back(s); break; }
+                    if (cur == key) break;
+                }
+                s = (s + 1) & (tsize - 1);
+            }
+            int seen = __atomic_load_n(&tval[s], __ATOMIC_RELAXED);
+            while ((int)t < seen && !__atomic_compare_exchange_n(&tval[s], &seen, (int)t, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+            first[q] = (uint32_t)s;                                      // the slot for now; resolved below
+        }
+    });
+    for_dr_ranges([&](unsigned, size_t t_begin, size_t t_end) {
+        for (size_t q = koff[t_begin]; q < koff[t_end]; ++q)
+            if (keys[q] != kStr) first[q] = (uint32_t)tval[first[q]];
+    });
+    for (size_t t = 0; any_str.load() && t < drs.size(); ++t)             // the rare k-mers with other letters
+        for (size_t q = koff[t]; q < koff[t + 1]; ++q)
+            if (keys[q] == kStr) {
                 auto ins = kmer_group_str.emplace(low_lexi_kmer(drs[t], q - koff[t]), (int)t);
                 first[q] = (uint32_t)ins.first->second;
             }
-        }
-    }
+    CB_NR_MARK("pass B");
     // pass C (the order-dependent greedy walk, now on small sequential arrays only)
     std::vector<int> group_of(drs.size(), 0);
     for (size_t t = 0; t < drs.size(); ++t) {
@@ -242,9 +284,7 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
     //     the survivors followed by their reverse complements.
     //     Groups are independent, so they are spread over a few worker threads; the output order (group id, then
     //     survivors, then their reverse complements) does not depend on the thread count.
-#ifdef CB_PROFILE_NR
-    const auto t_cluster_done = std::chrono::steady_clock::now();
-#endif
+    CB_NR_MARK("pass C");
     if (groups_out)
         for (size_t g = 0; g < members.size(); ++g)
             for (int tok : members[g]) groups_out->push_back(std::make_pair(tok, (int)g + 1));
@@ -280,16 +320,14 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
             pool.emplace_back([&]() { for (size_t g; (g = next++) < members.size();) reduce_group(g); });
         for (auto& th : pool) th.join();
     }
+    CB_NR_MARK("reduce");
     std::vector<std::string> out;
     for (size_t g = 0; g < members.size(); ++g) {
         for (const std::string& s : survivors[g]) out.push_back(s);
         for (const std::string& s : survivors[g]) out.push_back(reverse_complement(s));
     }
-#ifdef CB_PROFILE_NR
-    const auto t_end = std::chrono::steady_clock::now();
-    fprintf(stderr, "non_redundant_set: %zu groups, work %zu, threads %u, reduce+emit %.2f ms\n", members.size(), work, n_threads,
-            std::chrono::duration<double, std::milli>(t_end - t_cluster_done).count());
-#endif
+    CB_NR_MARK("emit");
+#undef CB_NR_MARK
     return out;
 }
 

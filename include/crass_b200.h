@@ -224,6 +224,10 @@ char* crass_b200_merge_dr_lists(const char* concatenated);
 
 /* clustering step alone on an ordered DR list ('\n'-separated, token order); "G"/"P" lines; malloc'd */
 char* crass_b200_non_redundant_set(const char* dr_list, uint32_t kmer_clust);
+/* the same clustering followed by crass_b200_ac_build on its pattern list, without the text round trip: the step
+ * WorkHorse.cpp:367-379 takes between the phases (createNonRedundantSet, then findSingletons builds its matcher,
+ * libcrispr.cpp:455-470).  *n_patterns (optional) = size of the non-redundant set; an empty set is EINVAL. */
+int crass_b200_ac_build_from_dr_list(const char* dr_list, uint32_t kmer_clust, crass_b200_ac** out, uint32_t* n_patterns);
 
 /* ---- whole path, one call: searchFile* -> createNonRedundantSet -> findSingletons* --------------- */
 int crass_b200_run_files(crass_b200_ctx* ctx, const char* const* paths, uint32_t n_paths,

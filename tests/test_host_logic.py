@@ -120,6 +120,29 @@ def test_non_redundant_set_fuzz_against_oracle():
         assert sorted(l for l in a.split("\n") if l.startswith("P")) == sorted(l for l in b.split("\n") if l.startswith("P"))
 
 
+def test_non_redundant_set_long_list_worker_threads():
+    """A list long enough (> 2^17 k-mers) to take the multi-threaded clustering passes; a few DRs carry 'N'."""
+    rng = random.Random(23)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    P = checkers.port()
+    base = [fuzzgen.rand_seq(rng, rng.randint(23, 47)) for _k in range(300)]
+    drs = []
+    for b in base:
+        for _k in range(20):
+            v = fuzzgen.mutate(rng, b, rng.choice([0, 0.02, 0.05]), b"ACGT" if rng.random() < 0.97 else b"ACGTN")
+            a, e = rng.randint(0, 4), rng.randint(0, 4)
+            v = v[a:len(v) - e] if rng.random() < 0.5 else fuzzgen.rand_seq(rng, a) + v + fuzzgen.rand_seq(rng, e)
+            drs.append(min(v, v.translate(comp)[::-1]))
+    uniq = list(dict.fromkeys(drs))
+    rng.shuffle(uniq)
+    assert sum(max(0, len(d) - 10) for d in uniq) > (1 << 17)
+    a = P.non_redundant(uniq)
+    for _rep in range(3):                                                 # the table is reused across calls
+        b = cb.non_redundant_set(uniq)
+        assert [l for l in a.split("\n") if l.startswith("G")] == [l for l in b.split("\n") if l.startswith("G")]
+        assert sorted(l for l in a.split("\n") if l.startswith("P")) == sorted(l for l in b.split("\n") if l.startswith("P"))
+
+
 def oracle_hits_phase1(batch, params=None):
     """Stand-in for kernel K1 on a box without a GPU: the oracle decides, the product replays."""
     P = checkers.port()

@@ -39,6 +39,19 @@ def _worker(rank, world, port, path, out_dir):
     local = api.dr_list_from_hits(shard.bases, shard.offsets, hits, pool)
     merged = cbdist.allgather_dr_lists(local)                        # the collective under test
     pats = api.non_redundant_list(merged, 6)
+    # the same exchange fed with K4b-style records (64-byte token records + first-read index, in device hash order)
+    import torch
+    order = np.random.default_rng(rank).permutation(len(local))
+    rec = np.zeros((len(local) + 3, 64), dtype=np.uint8)
+    fr = np.zeros(len(local) + 3, dtype=np.int32)
+    for slot, i in enumerate(order):
+        d = local[i]
+        rec[slot, 0] = len(d)
+        rec[slot, 2:2 + len(d)] = np.frombuffer(d, dtype=np.uint8)
+        fr[slot] = 10 * i + 7
+    blob = cbdist.allgather_unique_tokens(torch.from_numpy(rec.reshape(-1)), torch.from_numpy(fr), len(local), 64)
+    assert blob == b"".join(d + b"\n" for d in merged)
+    assert cb.Automaton.from_dr_list(blob, 6).num_patterns == len(pats)
     res = cb.Results()
     res.add_phase1(shard, hits, pool)
     res.adopt_tokens(merged)
