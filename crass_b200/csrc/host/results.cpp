@@ -10,6 +10,7 @@
 // The GPU kernels decide WHICH reads hit and WHERE; everything here is O(hits) bookkeeping that has
 // to happen in read order on one thread because token numbers are handed out by first appearance.
 #include <limits.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -109,6 +110,7 @@ void add_read_holder(Results& r, HeldRead* h) {
 // ---- the step between the phases -------------------------------------------------------------------
 namespace {
 const size_t kClusterKmer = 11;                                            // CRASS_DEF_KMER_SIZE, crassDefines.h:66
+const uint32_t kStrKey = 0xFFFFFFFFu;                                      // "this k-mer goes through the string map"
 
 std::string low_lexi_kmer(const std::string& dr, size_t pos) {            // laurenize (SeqUtils.cpp:89-97)
     std::string k = dr.substr(pos, kClusterKmer);
@@ -116,6 +118,51 @@ std::string low_lexi_kmer(const std::string& dr, size_t pos) {            // lau
     return k < rc ? k : rc;
 }
 
+const int8_t kCode[256] = {
+#define X4 -1, -1, -1, -1
+#define X16 X4, X4, X4, X4
+    X16, X16, X16, X16,
+    -1, 0, -1, 1, -1, -1, -1, 2, X4, X4, -1, -1, -1, -1, 3, -1, -1, -1, X4, X4,         // 'A'=65 'C'=67 'G'=71 'T'=84
+    X16, X16, X16, X16, X16, X16, X16, X16, X16, X16
+#undef X16
+#undef X4
+};
+
+// the workers of one call meet here between the passes; waits are short, so they spin politely
+struct SpinBarrier {
+    explicit SpinBarrier(unsigned n) : n_(n) {}
+    void wait() {
+        if (n_ <= 1) return;
+        const unsigned g = gen_.load(std::memory_order_acquire);
+        if (count_.fetch_add(1, std::memory_order_acq_rel) + 1 == n_) {
+            count_.store(0, std::memory_order_relaxed);
+            gen_.fetch_add(1, std::memory_order_release);
+        } else {
+            while (gen_.load(std::memory_order_acquire) == g) std::this_thread::yield();
+        }
+    }
+    unsigned n_;
+    std::atomic<unsigned> count_{0}, gen_{0};
+};
+
+// small per-worker open-addressing map (k-mer key -> head of a chain of survivors) for the substring reduction
+struct HeadTable {
+    std::vector<uint32_t> key;
+    std::vector<int> head;
+    size_t mask = 0;
+    void reset(size_t want) {
+        size_t cap = 16;
+        while (cap < 2 * want + 2) cap <<= 1;
+        key.assign(cap, kStrKey);
+        head.assign(cap, -1);
+        mask = cap - 1;
+    }
+    size_t slot(uint32_t k) const {
+        size_t s = (size_t)(k * 0x9E3779B1u) & mask;
+        while (key[s] != kStrKey && key[s] != k) s = (s + 1) & mask;
+        return s;
+    }
+};
 }  // namespace
 
 std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, int min_count,
@@ -127,6 +174,10 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
     //     big-endian, min(forward, reverse complement) as numbers is the lexicographic minimum laurenize() takes.
     //     Anything else goes through the string map; the two key spaces cannot collide because the canonical form of
     //     a k-mer is routed by its own bytes.
+    // (2) per group: drop every variant that contains a shorter variant (either strand), then emit the survivors
+    //     followed by their reverse complements.
+    // The work is cut into passes; all but the short order-dependent one (C) run on a few worker threads that are
+    // started once per call.  Nothing in the result depends on the number of workers.
 #ifdef CB_PROFILE_NR
     auto t_mark = std::chrono::steady_clock::now();
 #define CB_NR_MARK(what) do { const auto now_ = std::chrono::steady_clock::now(); \
@@ -134,64 +185,51 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
 #else
 #define CB_NR_MARK(what) do {} while (0)
 #endif
-    std::unordered_map<std::string, int> kmer_group_str;
-    size_t total_kmers = 0;
-    for (const std::string& d : drs) if (d.size() >= kClusterKmer) total_kmers += d.size() - kClusterKmer + 1;
+    const size_t n_dr = drs.size();
+    std::vector<size_t> koff(n_dr + 1, 0);                                 // k-mers of DR t: [koff[t], koff[t+1])
+    for (size_t t = 0; t < n_dr; ++t)
+        koff[t + 1] = koff[t] + (drs[t].size() >= kClusterKmer ? drs[t].size() - kClusterKmer + 1 : 0);
+    const size_t total_kmers = koff[n_dr];
     size_t tsize = 1024;
     while (tsize < total_kmers * 2 + 16) tsize <<= 1;
-    // the table is kept across calls (fresh multi-megabyte vectors cost more in page faults than the clustering itself);
-    // only the slots this call touches are reset on the way out
-    static thread_local std::vector<uint32_t> tkey_store;
+    // the work arrays are kept across calls (fresh multi-megabyte vectors cost more in page faults than the clustering
+    // itself); of the hash table only the slots this call touches are reset on the way out, so that untouched slots
+    // always hold (empty, INT_MAX)
+    static thread_local std::vector<uint32_t> tkey_store, keys_store, first_store;
     static thread_local std::vector<int> tval_store;
-    if (tkey_store.size() < tsize) { tkey_store.assign(tsize, 0xFFFFFFFFu); tval_store.assign(tsize, INT_MAX); }
+    if (tkey_store.size() < tsize) { tkey_store.assign(tsize, kStrKey); tval_store.assign(tsize, INT_MAX); }
+    if (keys_store.size() < total_kmers) { keys_store.resize(total_kmers + total_kmers / 4); first_store.resize(keys_store.size()); }
+    uint32_t* const keys = keys_store.data();                              // pass A: canonical key per k-mer
+    uint32_t* const first = first_store.data();                            // pass B: first DR (token order) holding it
     tsize = tkey_store.size();
     uint32_t* const tkey = tkey_store.data();           // plain pointers: TLS lookups are not free inside a shared object
     int* const tval = tval_store.data();
-    std::vector<std::vector<size_t> > touched_by;       // per worker: the slots it claimed
+
+    unsigned n_workers = 1;
+    if (total_kmers > (1u << 15)) n_workers = std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("CRASS_B200_HOST_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 64) n_workers = (unsigned)v; }
+    std::vector<size_t> cut(n_workers + 1, n_dr);                          // worker w owns DRs [cut[w], cut[w+1]): equal k-mer shares
+    cut[0] = 0;
+    for (unsigned w = 1; w < n_workers; ++w) {
+        const size_t want = total_kmers * w / n_workers;
+        cut[w] = std::max(cut[w - 1], (size_t)(std::upper_bound(koff.begin(), koff.end(), want) - koff.begin()) - 1);
+    }
+    std::vector<std::vector<size_t> > touched_by(n_workers);               // per worker: the table slots it claimed
     struct Reset {
         uint32_t* k; int* v; std::vector<std::vector<size_t> >& t;
-        ~Reset() { for (auto& l : t) for (size_t s : l) { k[s] = 0xFFFFFFFFu; v[s] = INT_MAX; } }
+        ~Reset() { for (auto& l : t) for (size_t s : l) { k[s] = kStrKey; v[s] = INT_MAX; } }
     } reset_on_exit{tkey, tval, touched_by};
-    static const int8_t kCode[256] = {
-#define X4 -1, -1, -1, -1
-#define X16 X4, X4, X4, X4
-        X16, X16, X16, X16,
-        -1, 0, -1, 1, -1, -1, -1, 2, X4, X4, -1, -1, -1, -1, 3, -1, -1, -1, X4, X4,     // 'A'=65 'C'=67 'G'=71 'T'=84
-        X16, X16, X16, X16, X16, X16, X16, X16, X16, X16
-#undef X16
-#undef X4
-    };
-    std::vector<std::vector<int> > members;                               // group id - 1 -> tokens
-    std::vector<uint32_t> unseen_int;
-    std::vector<std::string> unseen_str;
-    std::vector<std::pair<int, int> > counts;                             // (group, shared so far)
-    // pass A (no dependencies, streams through the strings): canonical integer key of every k-mer, kStr for the rare
-    // k-mers that need the string map
-    const uint32_t kStr = 0xFFFFFFFFu;
-    std::vector<uint32_t> keys(total_kmers);
-    std::vector<size_t> koff(drs.size() + 1, 0);
-    for (size_t t = 0; t < drs.size(); ++t)
-        koff[t + 1] = koff[t] + (drs[t].size() >= kClusterKmer ? drs[t].size() - kClusterKmer + 1 : 0);
-    // passes A and B are cut into contiguous DR ranges for a few worker threads when the list is long (a merged
-    // multi-rank list, or a deep sample); the result does not depend on the cut
-    const unsigned n_workers = total_kmers > (1u << 17) ? std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency())) : 1;
-    auto for_dr_ranges = [&](const std::function<void(unsigned, size_t, size_t)>& body) {
-        if (n_workers <= 1) { body(0, 0, drs.size()); return; }
-        std::vector<std::thread> pool;
-        size_t t0 = 0;
-        for (unsigned w = 0; w < n_workers; ++w) {                      // equal shares of k-mers, not of DRs
-            const size_t want = total_kmers * (w + 1) / n_workers;
-            size_t t1 = (size_t)(std::upper_bound(koff.begin(), koff.end(), want) - koff.begin()) - 1;
-            if (w + 1 == n_workers) t1 = drs.size();
-            if (t1 < t0) t1 = t0;
-            pool.emplace_back(body, w, t0, t1);
-            t0 = t1;
-        }
-        for (auto& th : pool) th.join();
-    };
     std::atomic<bool> any_str{false};
+    std::vector<std::vector<int> > members;                               // group id - 1 -> tokens
+    std::vector<std::vector<std::string> > survivors, survivors_rc;
+    std::vector<size_t> schedule;                                          // groups, largest first
+    std::atomic<size_t> next_group{0};
+    SpinBarrier barrier(n_workers);
     CB_NR_MARK("setup");
-    for_dr_ranges([&](unsigned, size_t t_begin, size_t t_end) {
+
+    // pass A (no dependencies, streams through the strings): canonical integer key of every k-mer, kStrKey for the
+    // rare k-mers that need the string map
+    auto pass_a = [&](size_t t_begin, size_t t_end) {
         const uint32_t kmask = (1u << (2 * kClusterKmer)) - 1u;
         for (size_t t = t_begin; t < t_end; ++t) {
             const std::string& dr = drs[t];
@@ -203,7 +241,7 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
                 if (c < 0) valid = 0;
                 else { valid++; fw = ((fw << 2) | (uint32_t)c) & kmask; rc = (rc >> 2) | ((uint32_t)(3 - c) << (2 * (kClusterKmer - 1))); }
                 if (p + 1 < kClusterKmer) continue;
-                uint32_t key = kStr;
+                uint32_t key = kStrKey;
                 if (valid >= (int)kClusterKmer) key = fw < rc ? fw : rc;
                 else {
                     const std::string km = low_lexi_kmer(dr, p + 1 - kClusterKmer);
@@ -211,37 +249,34 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
                     for (char ch : km) { const int c2 = kCode[(uint8_t)ch]; if (c2 < 0) { acgt = false; break; } k2 = (k2 << 2) | (uint32_t)c2; }
                     if (acgt) key = k2;
                 }
-                if (key == kStr) any_str.store(true, std::memory_order_relaxed);
+                if (key == kStrKey) any_str.store(true, std::memory_order_relaxed);
                 keys[w++] = key;
             }
         }
-    });
-    CB_NR_MARK("pass A");
+    };
     // pass B (no dependencies either): first[q] = index of the first DR, in token order, that contains k-mer q.
     // A k-mer is "seen globally" for DR t exactly when first[q] < t, and its group is the group of that first DR:
     // the reference hands its homeless k-mers to the DR's group when the DR is done (WorkHorse.cpp:1611-1617).
-    // One hash probe per k-mer with the probes prefetched a fixed distance ahead.
-    //   Workers claim a slot with a compare-and-swap on its key and lower its value with an atomic minimum, so the
-    //   table ends up holding min(t) per k-mer whatever the interleaving; untouched slots hold (empty, INT_MAX).
-    std::vector<uint32_t> first(total_kmers);
-    touched_by.assign(n_workers, std::vector<size_t>());
-    for_dr_ranges([&](unsigned w, size_t t_begin, size_t t_end) {
+    // One hash probe per k-mer with the probes prefetched a fixed distance ahead.  Workers claim a slot with a
+    // compare-and-swap on its key and lower its value with an atomic minimum, so the table ends up holding min(t)
+    // per k-mer whatever the interleaving; first[] holds the slot until every worker is through (pass B2).
+    auto pass_b = [&](unsigned w, size_t t_begin, size_t t_end) {
         const size_t kAhead = 24;
         const size_t q_end = koff[t_end];
         size_t t = t_begin;
         for (size_t q = koff[t_begin]; q < q_end; ++q) {
-            if (q + kAhead < q_end && keys[q + kAhead] != kStr) {
+            if (q + kAhead < q_end && keys[q + kAhead] != kStrKey) {
                 const size_t s = (size_t)(keys[q + kAhead] * 0x9E3779B1u) & (tsize - 1);
                 __builtin_prefetch(&tkey[s]); __builtin_prefetch(&tval[s]);
             }
             while (q >= koff[t + 1]) ++t;
             const uint32_t key = keys[q];
-            if (key == kStr) continue;
+            if (key == kStrKey) continue;
             size_t s = (size_t)(key * 0x9E3779B1u) & (tsize - 1);
             for (;;) {
                 uint32_t cur = __atomic_load_n(&tkey[s], __ATOMIC_RELAXED);
                 if (cur == key) break;
-                if (cur == 0xFFFFFFFFu) {
+                if (cur == kStrKey) {
                     if (__atomic_compare_exchange_n(&tkey[s], &cur, key, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { touched_by[w].push_back(s); break; }
                     if (cur == key) break;
                 }
@@ -249,82 +284,129 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
             }
             int seen = __atomic_load_n(&tval[s], __ATOMIC_RELAXED);
             while ((int)t < seen && !__atomic_compare_exchange_n(&tval[s], &seen, (int)t, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
-            first[q] = (uint32_t)s;                                      // the slot for now; resolved below
+            first[q] = (uint32_t)s;
         }
-    });
-    for_dr_ranges([&](unsigned, size_t t_begin, size_t t_end) {
-        for (size_t q = koff[t_begin]; q < koff[t_end]; ++q)
-            if (keys[q] != kStr) first[q] = (uint32_t)tval[first[q]];
-    });
-    for (size_t t = 0; any_str.load() && t < drs.size(); ++t)             // the rare k-mers with other letters
-        for (size_t q = koff[t]; q < koff[t + 1]; ++q)
-            if (keys[q] == kStr) {
-                auto ins = kmer_group_str.emplace(low_lexi_kmer(drs[t], q - koff[t]), (int)t);
-                first[q] = (uint32_t)ins.first->second;
-            }
-    CB_NR_MARK("pass B");
-    // pass C (the order-dependent greedy walk, now on small sequential arrays only)
-    std::vector<int> group_of(drs.size(), 0);
-    for (size_t t = 0; t < drs.size(); ++t) {
-        counts.clear();
-        int group = 0;
-        for (size_t q = koff[t]; q < koff[t + 1] && !group; ++q) {
-            if (first[q] >= t) continue;                                 // never seen before this DR
-            const int known = group_of[first[q]];
-            auto c2 = std::find_if(counts.begin(), counts.end(), [&](const std::pair<int, int>& p) { return p.first == known; });
-            if (c2 == counts.end()) counts.push_back(std::make_pair(known, 1));
-            else if (++c2->second >= min_count) group = known;
-        }
-        if (!group) { members.emplace_back(); group = (int)members.size(); }
-        group_of[t] = group;
-        members[group - 1].push_back((int)t + 2);
-    }
-    (void)unseen_int; (void)unseen_str;
-    // (2) per group: drop every variant that contains a shorter surviving variant (either strand), then emit
-    //     the survivors followed by their reverse complements.
-    //     Groups are independent, so they are spread over a few worker threads; the output order (group id, then
-    //     survivors, then their reverse complements) does not depend on the thread count.
-    CB_NR_MARK("pass C");
-    if (groups_out)
-        for (size_t g = 0; g < members.size(); ++g)
-            for (int tok : members[g]) groups_out->push_back(std::make_pair(tok, (int)g + 1));
-    std::vector<std::vector<std::string> > survivors(members.size());
-    auto reduce_group = [&](size_t g) {
-        std::vector<const std::string*> v;
-        for (int tok : members[g]) v.push_back(&drs[tok - 2]);
-        std::stable_sort(v.begin(), v.end(), [](const std::string* a, const std::string* b) { return a->size() < b->size(); });
-        std::vector<char> dead(v.size(), 0);
-        for (size_t i = 0; i < v.size(); ++i) {
-            if (dead[i] || v[i]->empty()) continue;
-            const std::string& a = *v[i];
-            const std::string rc = reverse_complement(a);
-            for (size_t j = i + 1; j < v.size(); ++j) {
-                if (dead[j] || v[j]->empty()) continue;
-                const std::string& b = *v[j];
-                if (b.size() == a.size()) {                               // same length: containment is equality
-                    if (b == a || b == rc) dead[j] = 1;
-                } else if (memmem(b.data(), b.size(), a.data(), a.size()) || memmem(b.data(), b.size(), rc.data(), rc.size())) dead[j] = 1;
-            }
-        }
-        for (size_t i = 0; i < v.size(); ++i) if (!dead[i] && !v[i]->empty()) survivors[g].push_back(*v[i]);
     };
-    size_t work = 0;
-    for (auto& m : members) work += m.size() * m.size();
-    unsigned n_threads = work > 200000 ? std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency())) : 1;
-    if (n_threads <= 1) {
-        for (size_t g = 0; g < members.size(); ++g) reduce_group(g);
-    } else {
-        std::atomic<size_t> next{0};
+    auto pass_b2 = [&](size_t t_begin, size_t t_end) {
+        for (size_t q = koff[t_begin]; q < koff[t_end]; ++q)
+            if (keys[q] != kStrKey) first[q] = (uint32_t)tval[first[q]];
+    };
+    // pass C (one thread): the order-dependent greedy walk, on small sequential arrays only
+    auto pass_c = [&]() {
+        if (any_str.load()) {                                             // the rare k-mers with other letters
+            std::unordered_map<std::string, int> kmer_first_str;
+            for (size_t t = 0; t < n_dr; ++t)
+                for (size_t q = koff[t]; q < koff[t + 1]; ++q)
+                    if (keys[q] == kStrKey) first[q] = (uint32_t)kmer_first_str.emplace(low_lexi_kmer(drs[t], q - koff[t]), (int)t).first->second;
+        }
+        std::vector<int> group_of(n_dr, 0);
+        std::vector<std::pair<int, int> > counts;                         // (group, shared so far)
+        for (size_t t = 0; t < n_dr; ++t) {
+            counts.clear();
+            int group = 0;
+            for (size_t q = koff[t]; q < koff[t + 1] && !group; ++q) {
+                if (first[q] >= t) continue;                             // never seen before this DR
+                const int known = group_of[first[q]];
+                auto c2 = std::find_if(counts.begin(), counts.end(), [&](const std::pair<int, int>& p) { return p.first == known; });
+                if (c2 == counts.end()) counts.push_back(std::make_pair(known, 1));
+                else if (++c2->second >= min_count) group = known;
+            }
+            if (!group) { members.emplace_back(); group = (int)members.size(); }
+            group_of[t] = group;
+            members[group - 1].push_back((int)t + 2);
+        }
+        if (groups_out)
+            for (size_t g = 0; g < members.size(); ++g)
+                for (int tok : members[g]) groups_out->push_back(std::make_pair(tok, (int)g + 1));
+        survivors.resize(members.size());
+        survivors_rc.resize(members.size());
+        schedule.resize(members.size());
+        for (size_t g = 0; g < members.size(); ++g) schedule[g] = g;
+        std::stable_sort(schedule.begin(), schedule.end(), [&](size_t a, size_t b) { return members[a].size() > members[b].size(); });
+    };
+    // pass D (groups are independent): removeRedundantRepeats.  Variants are visited shortest first; one dies when an
+    // earlier one is contained in it on either strand (containment is transitive, so only survivors need to be
+    // remembered).  A variant a inside b shows its first 11-mer at the position where it starts, and its reverse
+    // complement shows the same canonical 11-mer where it ends, so b's own k-mer keys from pass A find every candidate
+    // in a small map keyed by the survivors' first k-mers; candidates are confirmed by comparing bytes.
+    // Groups holding k-mers outside A/C/G/T, or variants shorter than a k-mer, take the plain pairwise search.
+    auto reduce_group = [&](size_t g, HeadTable& map) {
+        std::vector<int> v;
+        bool plain = false;
+        for (int tok : members[g]) {
+            const size_t t = (size_t)tok - 2;
+            v.push_back((int)t);
+            if (drs[t].size() < kClusterKmer) plain = true;
+            else if (any_str.load(std::memory_order_relaxed))
+                for (size_t q = koff[t]; q < koff[t + 1] && !plain; ++q) plain = keys[q] == kStrKey;
+        }
+        std::stable_sort(v.begin(), v.end(), [&](int a, int b) { return drs[a].size() < drs[b].size(); });
+        std::vector<std::string>& out = survivors[g];
+        std::vector<std::string>& out_rc = survivors_rc[g];
+        if (plain) {
+            for (int tb : v) {
+                const std::string& b = drs[tb];
+                if (b.empty()) continue;
+                bool dead = false;
+                for (size_t j = 0; j < out.size() && !dead; ++j) {
+                    const std::string& a = out[j];
+                    const std::string& rc = out_rc[j];
+                    if (b.size() == a.size()) dead = b == a || b == rc;   // same length: containment is equality
+                    else dead = memmem(b.data(), b.size(), a.data(), a.size()) || memmem(b.data(), b.size(), rc.data(), rc.size());
+                }
+                if (!dead) { out.push_back(b); out_rc.push_back(reverse_complement(b)); }
+            }
+            return;
+        }
+        map.reset(v.size());
+        std::vector<int> chain;                                           // survivor j -> next survivor with the same first k-mer
+        for (int tb : v) {
+            const std::string& b = drs[tb];
+            const uint32_t* kb = &keys[koff[tb]];
+            const size_t nk = koff[tb + 1] - koff[tb];
+            bool dead = false;
+            for (size_t p = 0; p < nk && !dead; ++p) {
+                const size_t s = map.slot(kb[p]);
+                if (map.key[s] == kStrKey) continue;
+                for (int j = map.head[s]; j >= 0 && !dead; j = chain[j]) {
+                    const std::string& a = out[j];
+                    const size_t la = a.size();
+                    if (p + la <= b.size() && memcmp(b.data() + p, a.data(), la) == 0) dead = true;
+                    else if (p + kClusterKmer >= la && memcmp(b.data() + (p + kClusterKmer - la), out_rc[j].data(), la) == 0) dead = true;
+                }
+            }
+            if (dead) continue;
+            const size_t s = map.slot(kb[0]);
+            chain.push_back(map.key[s] == kStrKey ? -1 : map.head[s]);
+            map.key[s] = kb[0];
+            map.head[s] = (int)out.size();
+            out.push_back(b);
+            out_rc.push_back(reverse_complement(b));
+        }
+    };
+    auto worker = [&](unsigned w) {
+        pass_a(cut[w], cut[w + 1]);
+        pass_b(w, cut[w], cut[w + 1]);
+        barrier.wait();
+        if (w == 0) CB_NR_MARK("pass A+B");
+        pass_b2(cut[w], cut[w + 1]);
+        barrier.wait();
+        if (w == 0) { pass_c(); CB_NR_MARK("pass B2+C"); }
+        barrier.wait();
+        HeadTable map;
+        for (size_t i; (i = next_group.fetch_add(1)) < schedule.size();) reduce_group(schedule[i], map);
+    };
+    {
         std::vector<std::thread> pool;
-        for (unsigned t = 0; t < n_threads; ++t)
-            pool.emplace_back([&]() { for (size_t g; (g = next++) < members.size();) reduce_group(g); });
+        for (unsigned w = 1; w < n_workers; ++w) pool.emplace_back(worker, w);
+        worker(0);
         for (auto& th : pool) th.join();
     }
     CB_NR_MARK("reduce");
     std::vector<std::string> out;
     for (size_t g = 0; g < members.size(); ++g) {
-        for (const std::string& s : survivors[g]) out.push_back(s);
-        for (const std::string& s : survivors[g]) out.push_back(reverse_complement(s));
+        for (std::string& s : survivors[g]) out.push_back(std::move(s));
+        for (std::string& s : survivors_rc[g]) out.push_back(std::move(s));
     }
     CB_NR_MARK("emit");
 #undef CB_NR_MARK
