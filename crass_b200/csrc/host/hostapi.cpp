@@ -316,7 +316,15 @@ char* crass_b200_non_redundant_set(const char* dr_list, uint32_t kmer_clust) {
 
 int crass_b200_ac_build_from_dr_list(const char* dr_list, uint32_t kmer_clust, crass_b200_ac** out, uint32_t* n_patterns) {
     if (!dr_list || !out) return fail(CRASS_B200_EINVAL, "NULL argument");
-    const std::vector<std::string> nr = non_redundant_set(split_lines(dr_list), (int)kmer_clust, nullptr);
+    std::vector<std::string_view> lines;                                        // views into the caller's text
+    const std::string_view all(dr_list);
+    for (size_t p = 0; p < all.size();) {
+        size_t e = all.find('\n', p);
+        if (e == std::string_view::npos) e = all.size();
+        if (e > p) lines.push_back(all.substr(p, e - p));
+        p = e + 1;
+    }
+    const std::vector<std::string> nr = non_redundant_set(lines, (int)kmer_clust, nullptr);
     if (n_patterns) *n_patterns = (uint32_t)nr.size();
     std::vector<uint8_t> bytes;
     std::vector<uint32_t> offs(1, 0);

@@ -5,6 +5,7 @@
 
 #include <map>
 #include <string>
+#include <string_view>
 #include <vector>
 
 #include "../../../include/crass_b200.h"
@@ -72,6 +73,8 @@ std::string dr_lowlexi(HeldRead& h);
 void add_read_holder(Results& r, HeldRead* h);
 // WorkHorse::createNonRedundantSet on tokens 2..; fills groups (token, gid) when not NULL
 std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, int min_count,
+                                           std::vector<std::pair<int, int> >* groups);
+std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& drs, int min_count,
                                            std::vector<std::pair<int, int> >* groups);
 std::string dump_results(Results& r, int max_read_len);
 

@@ -112,8 +112,8 @@ namespace {
 const size_t kClusterKmer = 11;                                            // CRASS_DEF_KMER_SIZE, crassDefines.h:66
 const uint32_t kStrKey = 0xFFFFFFFFu;                                      // "this k-mer goes through the string map"
 
-std::string low_lexi_kmer(const std::string& dr, size_t pos) {            // laurenize (SeqUtils.cpp:89-97)
-    std::string k = dr.substr(pos, kClusterKmer);
+std::string low_lexi_kmer(std::string_view dr, size_t pos) {              // laurenize (SeqUtils.cpp:89-97)
+    std::string k(dr.substr(pos, kClusterKmer));
     std::string rc = reverse_complement(k);
     return k < rc ? k : rc;
 }
@@ -166,6 +166,11 @@ struct HeadTable {
 }  // namespace
 
 std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, int min_count,
+                                           std::vector<std::pair<int, int> >* groups_out) {
+    return non_redundant_set(std::vector<std::string_view>(drs.begin(), drs.end()), min_count, groups_out);
+}
+
+std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& drs, int min_count,
                                            std::vector<std::pair<int, int> >* groups_out) {
     // (1) greedy k-mer clustering in token order.  A DR joins the first group that reaches min_count shared
     //     11-mers while walking its k-mers left to right (the test is only made from a group's second hit on);
@@ -232,7 +237,7 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
     auto pass_a = [&](size_t t_begin, size_t t_end) {
         const uint32_t kmask = (1u << (2 * kClusterKmer)) - 1u;
         for (size_t t = t_begin; t < t_end; ++t) {
-            const std::string& dr = drs[t];
+            const std::string_view dr = drs[t];
             size_t w = koff[t];
             uint32_t fw = 0, rc = 0;
             int valid = 0;                                               // trailing run of A/C/G/T bytes
@@ -329,23 +334,23 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
     // remembered).  A variant a inside b shows its first 11-mer at the position where it starts, and its reverse
     // complement shows the same canonical 11-mer where it ends, so b's own k-mer keys from pass A find every candidate
     // in a small map keyed by the survivors' first k-mers; candidates are confirmed by comparing bytes.
-    // Groups holding k-mers outside A/C/G/T, or variants shorter than a k-mer, take the plain pairwise search.
-    auto reduce_group = [&](size_t g, HeadTable& map) {
+    // Survivors whose first k-mer holds a byte outside A/C/G/T cannot be found that way and are searched for one by
+    // one (there are few); groups with a variant shorter than a k-mer take the plain pairwise search throughout.
+    auto reduce_group = [&](size_t g, HeadTable& map, HeadTable& full) {
+        std::vector<uint32_t> first_key;                                  // survivor j -> canonical key of its first k-mer
         std::vector<int> v;
         bool plain = false;
         for (int tok : members[g]) {
             const size_t t = (size_t)tok - 2;
             v.push_back((int)t);
             if (drs[t].size() < kClusterKmer) plain = true;
-            else if (any_str.load(std::memory_order_relaxed))
-                for (size_t q = koff[t]; q < koff[t + 1] && !plain; ++q) plain = keys[q] == kStrKey;
         }
         std::stable_sort(v.begin(), v.end(), [&](int a, int b) { return drs[a].size() < drs[b].size(); });
         std::vector<std::string>& out = survivors[g];
         std::vector<std::string>& out_rc = survivors_rc[g];
         if (plain) {
             for (int tb : v) {
-                const std::string& b = drs[tb];
+                const std::string_view b = drs[tb];
                 if (b.empty()) continue;
                 bool dead = false;
                 for (size_t j = 0; j < out.size() && !dead; ++j) {
@@ -354,18 +359,53 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
                     if (b.size() == a.size()) dead = b == a || b == rc;   // same length: containment is equality
                     else dead = memmem(b.data(), b.size(), a.data(), a.size()) || memmem(b.data(), b.size(), rc.data(), rc.size());
                 }
-                if (!dead) { out.push_back(b); out_rc.push_back(reverse_complement(b)); }
+                if (!dead) { out.emplace_back(b); out_rc.push_back(reverse_complement(out.back())); }
             }
             return;
         }
+        // survivors enter the k-mer map only once the walk has moved on to longer variants (equal lengths cannot
+        // contain each other); among equal lengths only identity on either strand matters, answered by a hash of the
+        // whole string
         map.reset(v.size());
+        full.reset(2 * v.size());
         std::vector<int> chain;                                           // survivor j -> next survivor with the same first k-mer
+        std::vector<int> odd;                                             // survivors that are not in the map, shortest first
+        size_t n_mapped = 0, cur_len = 0;
+        auto hash_of = [](std::string_view x) {
+            uint64_t h = 1469598103934665603ull;
+            for (unsigned char c : x) { h ^= c; h *= 1099511628211ull; }
+            return (uint32_t)(h ^ (h >> 32)) & 0x7FFFFFFFu;              // never the empty marker
+        };
         for (int tb : v) {
-            const std::string& b = drs[tb];
+            const std::string_view b = drs[tb];
             const uint32_t* kb = &keys[koff[tb]];
             const size_t nk = koff[tb + 1] - koff[tb];
+            if (b.size() != cur_len) {
+                for (; n_mapped < out.size(); ++n_mapped) {
+                    bool acgt = true;
+                    for (size_t i = 0; i < kClusterKmer; ++i) acgt = acgt && kCode[(uint8_t)out[n_mapped][i]] >= 0;
+                    if (!acgt) { odd.push_back((int)n_mapped); continue; }
+                    const size_t s = map.slot(first_key[n_mapped]);
+                    chain[n_mapped] = map.key[s] == kStrKey ? -1 : map.head[s];
+                    map.key[s] = first_key[n_mapped];
+                    map.head[s] = (int)n_mapped;
+                }
+                cur_len = b.size();
+            }
             bool dead = false;
+            const uint32_t hb = hash_of(b);
+            for (size_t s = (size_t)(hb * 0x9E3779B1u) & full.mask; full.key[s] != kStrKey && !dead; s = (s + 1) & full.mask) {
+                if (full.key[s] != hb) continue;
+                const int j = full.head[s] >> 1;                          // bit 0: the entry stands for the reverse complement
+                dead = b == ((full.head[s] & 1) ? out_rc[j] : out[j]);
+            }
+            for (size_t o = 0; o < odd.size() && !dead; ++o) {
+                const std::string& a = out[odd[o]];
+                if (a.size() >= b.size()) break;                          // equal lengths were settled above
+                dead = memmem(b.data(), b.size(), a.data(), a.size()) || memmem(b.data(), b.size(), out_rc[odd[o]].data(), a.size());
+            }
             for (size_t p = 0; p < nk && !dead; ++p) {
+                if (kb[p] == kStrKey) continue;
                 const size_t s = map.slot(kb[p]);
                 if (map.key[s] == kStrKey) continue;
                 for (int j = map.head[s]; j >= 0 && !dead; j = chain[j]) {
@@ -376,12 +416,18 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
                 }
             }
             if (dead) continue;
-            const size_t s = map.slot(kb[0]);
-            chain.push_back(map.key[s] == kStrKey ? -1 : map.head[s]);
-            map.key[s] = kb[0];
-            map.head[s] = (int)out.size();
-            out.push_back(b);
-            out_rc.push_back(reverse_complement(b));
+            const int j = (int)out.size();
+            out.emplace_back(b);
+            out_rc.push_back(reverse_complement(out.back()));
+            first_key.push_back(kb[0]);
+            chain.push_back(-1);
+            for (int strand = 0; strand < 2; ++strand) {
+                const uint32_t h = strand ? hash_of(out_rc[j]) : hb;
+                size_t s = (size_t)(h * 0x9E3779B1u) & full.mask;
+                while (full.key[s] != kStrKey) s = (s + 1) & full.mask;
+                full.key[s] = h;
+                full.head[s] = 2 * j + strand;
+            }
         }
     };
     auto worker = [&](unsigned w) {
@@ -393,8 +439,8 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, 
         barrier.wait();
         if (w == 0) { pass_c(); CB_NR_MARK("pass B2+C"); }
         barrier.wait();
-        HeadTable map;
-        for (size_t i; (i = next_group.fetch_add(1)) < schedule.size();) reduce_group(schedule[i], map);
+        HeadTable map, full;
+        for (size_t i; (i = next_group.fetch_add(1)) < schedule.size();) reduce_group(schedule[i], map, full);
     };
     {
         std::vector<std::thread> pool;
