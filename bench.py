@@ -224,9 +224,7 @@ def main():
     d_tokens = torch.empty(hits_cap * TOK, dtype=torch.uint8, device=dev)
     host_ms = {"fetch": [], "merge": [], "cluster_build": [], "ac_upload": []}
 
-    d_utok = torch.empty(hits_cap * TOK, dtype=torch.uint8, device=dev)
-    d_ufr = torch.empty(hits_cap, dtype=torch.int32, device=dev)
-    d_ucnt = torch.zeros(4, dtype=torch.int32, device=dev)
+    exchange = cbdist.TokenExchange(ctx, dev, shard_reads=n, stride=TOK)   # K4b (+ all-gather + K4c at N > 1)
     h_hits = [torch.empty(hits_cap * 4, dtype=torch.int32, pin_memory=True) for _ in range(2)]
     h_pool = [torch.empty(pool_cap, dtype=torch.int32, pin_memory=True) for _ in range(2)]
 
@@ -257,13 +255,11 @@ def main():
         e[1].record()
         t0 = time.perf_counter()
         nh, npool = read_counters()
-        ctx.unique_tokens_dev(d_hits, nh, d_tokens, TOK, d_utok, d_ufr, d_ucnt, stream)   # K4b: distinct tokens + first read
-        fetch_hits_async(0, nh, npool)                                 # the phase-1 hit records travel while the host clusters
-        nu = int(d_ucnt[:1].cpu()[0])
         t1 = time.perf_counter()
-        # distinct low-lexi DRs of all shards in first-appearance order: one NCCL all-gather of the K4b records and a
-        # deterministic merge (crass_b200/dist.py); at N=1 just the device-to-host copy of this shard's records
-        merged = cbdist.allgather_unique_tokens(d_utok, d_ufr, nu, TOK)
+        # distinct low-lexi DRs of all shards in first-appearance order (crass_b200/dist.py): K4b de-duplicates this
+        # shard's tokens on the device, one NCCL all-gather + K4c merge the shards, one copy brings the list back
+        merged, nu = exchange.run(d_hits, nh, d_tokens, stream)
+        fetch_hits_async(0, nh, npool)                                 # the phase-1 hit records travel while the host clusters
         t3 = time.perf_counter()
         if args.dump_dr_list and rank == 0 and not record:
             open(args.dump_dr_list, "wb").write(merged)
@@ -287,7 +283,7 @@ def main():
                 kt["k2"].append(e[2].elapsed_time(e[3]))
                 for k, v in zip(("fetch", "merge", "cluster_build", "ac_upload"), (t1 - t0, t3 - t1, t4 - t3, t5 - t4)):
                     host_ms[k].append(v * 1e3)
-        stats.update(hits_phase1=len(hits), dr_variants_local=nu, dr_variants_merged=merged.count(b"\n"), patterns=pats, hits_phase2=n2)
+        stats.update(hits_phase1=len(hits), dr_variants_merged=nu, patterns=pats, hits_phase2=n2)
 
     def step_e2e():
         ctx.upload(h_bases, h_offsets)                                 # H2D from pinned host memory

@@ -43,6 +43,7 @@ class Hit(C.Structure):
 
 HIT_DTYPE = np.dtype([("read_index", "<u4"), ("n_ss", "<u4"), ("ss_offset", "<u4"), ("repeat_len", "<u4")])
 
+EINVAL = -1
 ENODEVICE = -2
 
 _lib = None
@@ -113,6 +114,10 @@ def lib():
         "crass_b200_results_adopt_tokens": (C.c_int, [vp, cp]),
         "crass_b200_results_non_redundant": (vp, [vp, C.c_uint32, u32p]),
         "crass_b200_results_dump": (vp, [vp, C.c_int]),
+        "crass_b200_token_block_bytes": (C.c_size_t, [C.c_uint32, C.c_uint32]),
+        "crass_b200_unique_tokens_block_dev": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp]),
+        "crass_b200_merge_token_blocks_dev": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp]),
+        "crass_b200_dr_list_from_block": (vp, [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         "crass_b200_non_redundant_set": (vp, [cp, C.c_uint32]),
         "crass_b200_ac_build_from_dr_list": (C.c_int, [cp, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_uint32)]),
         "crass_b200_run_files": (C.c_int, [vp, C.POINTER(cp), C.c_uint32, C.POINTER(Params), C.c_int, C.POINTER(vp), C.POINTER(C.c_int)]),
@@ -344,6 +349,19 @@ def dr_list_from_unique(records, stride, first_read, raw=False):
     return s if raw else [x for x in s.split(b"\n") if x]
 
 
+def token_block_bytes(cap, stride):
+    return lib().crass_b200_token_block_bytes(cap, stride)
+
+
+def dr_list_from_block(block, cap, stride):
+    """Host copy of a token block (numpy / pinned torch uint8) -> (DR list text in first-appearance order, count, flags)."""
+    n, fl = C.c_uint32(0), C.c_uint32(0)
+    s = _take_str(lib().crass_b200_dr_list_from_block(C.c_void_p(_addr(block)), cap, stride, C.byref(n), C.byref(fl)))
+    if s is None:
+        _check(-1)
+    return s, n.value, fl.value
+
+
 def merge_dr_lists(drs):
     """First-appearance de-duplication; a list gives a list, '\\n'-terminated text gives text."""
     if isinstance(drs, (bytes, bytearray)):
@@ -395,6 +413,14 @@ class Context:
         """K4b: device-side de-duplication of the token records of the first n_hits hit slots (torch tensors)."""
         _check(lib().crass_b200_unique_tokens_dev(self.h, d_hits.data_ptr(), n_hits, d_tokens.data_ptr(), stride, d_out_tokens.data_ptr(),
                                                   d_out_first_read.data_ptr(), d_out_count.data_ptr(), stream))
+
+    def unique_tokens_block_dev(self, d_hits, n_hits, d_tokens, stride, d_block, cap, stream=0):
+        """K4b in block form (see include/crass_b200.h): distinct tokens of the hit list -> one token block."""
+        _check(lib().crass_b200_unique_tokens_block_dev(self.h, d_hits.data_ptr(), n_hits, d_tokens.data_ptr(), stride, d_block.data_ptr(), cap, stream))
+
+    def merge_token_blocks_dev(self, d_blocks, n_ranks, cap, stride, shard_reads, d_out_block, out_cap, stream=0):
+        """K4c: the blocks of all ranks (rank order, back to back) -> one block with global first-appearance keys."""
+        _check(lib().crass_b200_merge_token_blocks_dev(self.h, d_blocks.data_ptr(), n_ranks, cap, stride, shard_reads, d_out_block.data_ptr(), out_cap, stream))
 
     def last_dr_list(self):
         s = lib().crass_b200_ctx_last_dr_list(self.h)

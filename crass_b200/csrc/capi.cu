@@ -202,6 +202,57 @@ int crass_b200_unique_tokens_dev(crass_b200_ctx* c, const crass_b200_hit* d_hits
     return 0;
 }
 
+// ---- K4b/K4c in block form ------------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+template <class Src>
+int dedupe_into_block(crass_b200_ctx* c, const Src& src, uint32_t n_slots, uint32_t stride, void* d_block, uint32_t cap, cudaStream_t st) {
+    CUDA_TRY(cudaMemsetAsync(d_block, 0, cbk::kTokenBlockHeader, st));
+    if (n_slots == 0) return 0;
+    uint32_t table = 1024;
+    while (table < 2u * n_slots) table <<= 1;
+    if (int r = c->d_tok_table.reserve((size_t)table * 2 * sizeof(uint32_t))) return r;
+    uint32_t* rep = c->d_tok_table.as<uint32_t>();
+    uint32_t* first_read = rep + table;
+    CUDA_TRY(cudaMemsetAsync(rep, 0xFF, (size_t)table * 2 * sizeof(uint32_t), st));
+    cbk::k_block_dedupe<Src><<<(n_slots + 255) / 256, 256, 0, st>>>(src, n_slots, rep, first_read, table - 1);
+    cbk::k_block_compact<Src><<<(table + 255) / 256, 256, 0, st>>>(src, rep, first_read, table, (uint8_t*)d_block, cap, stride);
+    c->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+}  // namespace
+extern "C" {
+
+size_t crass_b200_token_block_bytes(uint32_t cap, uint32_t stride) { return cbk::kTokenBlockHeader + (size_t)cap * stride; }
+
+int crass_b200_unique_tokens_block_dev(crass_b200_ctx* c, const crass_b200_hit* d_hits, uint32_t n_hits, const void* d_tokens, uint32_t stride,
+                                       void* d_block, uint32_t cap, void* stream_v) {
+    if (!c || !d_block || (n_hits && (!d_hits || !d_tokens))) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    if (stride < 12 || (stride & 3) || cap == 0) return cbh::fail(CRASS_B200_EINVAL, "token stride must be a multiple of 4, at least 12; cap > 0");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
+    cbk::HitTokens src{d_hits, (const uint8_t*)d_tokens, stride};
+    return dedupe_into_block(c, src, n_hits, stride, d_block, cap, st);
+}
+
+int crass_b200_merge_token_blocks_dev(crass_b200_ctx* c, const void* d_blocks, uint32_t n_ranks, uint32_t cap, uint32_t stride,
+                                      uint32_t shard_reads, void* d_out_block, uint32_t out_cap, void* stream_v) {
+    if (!c || !d_blocks || !d_out_block) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    if (stride < 12 || (stride & 3) || cap == 0 || out_cap == 0 || n_ranks == 0 || n_ranks > 1024)
+        return cbh::fail(CRASS_B200_EINVAL, "bad block geometry");
+    if ((uint64_t)n_ranks * shard_reads > 0xFFFFFFFFull) return cbh::fail(CRASS_B200_EINVAL, "n_ranks * shard_reads must fit 32 bits");
+    if ((uint64_t)n_ranks * cap > 0x7FFFFFFFull) return cbh::fail(CRASS_B200_EINVAL, "n_ranks * cap too large");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
+    cbk::GatheredBlocks src{(const uint8_t*)d_blocks, cap, stride, shard_reads};
+    if (int r = dedupe_into_block(c, src, n_ranks * cap, stride, d_out_block, out_cap, st)) return r;
+    cbk::k_block_flags<<<1, 1024, 0, st>>>(src, n_ranks, (uint8_t*)d_out_block);
+    c->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // ---- K1 ------------------------------------------------------------------------------------------------
 int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const uint64_t* d_offsets, uint32_t n_reads,
                              uint32_t max_read_len, const crass_b200_params* params, uint8_t* d_found,

@@ -287,6 +287,34 @@ char* crass_b200_dr_list_from_unique(const uint8_t* records, uint32_t stride, co
     return dup_cstr(out);
 }
 
+char* crass_b200_dr_list_from_block(const void* block, uint32_t cap, uint32_t stride, uint32_t* count, uint32_t* flags) {
+    if (!block || stride < 12) { fail(CRASS_B200_EINVAL, "bad token block"); return nullptr; }
+    const uint8_t* p = (const uint8_t*)block;
+    uint32_t hdr[2];
+    memcpy(hdr, p, sizeof hdr);
+    if (count) *count = hdr[0];
+    if (flags) *flags = hdr[1];
+    const uint32_t n = hdr[0] < cap ? hdr[0] : cap;
+    const uint8_t* recs = p + 16;
+    std::vector<uint64_t> order(n);                                             // (order key, slot), sorted as one integer
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t key;
+        memcpy(&key, recs + (size_t)i * stride + stride - 4, 4);
+        order[i] = ((uint64_t)key << 32) | i;
+    }
+    std::sort(order.begin(), order.end());
+    std::string out;
+    out.reserve((size_t)n * 40);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint8_t* rec = recs + (size_t)(uint32_t)order[i] * stride;
+        const uint32_t ln = rec[0] + 6u <= stride ? rec[0] : stride - 6;
+        if (!ln) continue;
+        out.append((const char*)rec + 2, ln);
+        out += '\n';
+    }
+    return dup_cstr(out);
+}
+
 char* crass_b200_merge_dr_lists(const char* concatenated) {
     if (!concatenated) return dup_cstr(std::string());
     std::unordered_set<std::string_view> seen;                                  // views into the caller's text

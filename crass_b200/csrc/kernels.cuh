@@ -129,6 +129,71 @@ k_token_compact(const uint32_t* __restrict__ rep, const uint32_t* __restrict__ f
     for (uint32_t b = 0; b < stride; b += 4) *reinterpret_cast<uint32_t*>(dst + b) = *reinterpret_cast<const uint32_t*>(src + b);
 }
 
+// ---- K4b/K4c in block form: the unit of the multi-GPU exchange -----------------------------------------------
+// A token block is 16 header bytes (u32 count, u32 flags, 8 spare) followed by `cap` records of `stride` bytes; the
+// last four bytes of a record hold its order key (read index of first appearance).  count may exceed cap: the block
+// then holds the first cap records that arrived and the caller retries with a larger one.
+const uint32_t kTokenBlockHeader = 16;
+
+struct HitTokens {                                   // source = the token records of a hit list (K4b)
+    const crass_b200_hit* hits;
+    const uint8_t* tokens;
+    uint32_t stride;
+    __device__ bool valid(uint32_t) const { return true; }
+    __device__ const uint8_t* rec(uint32_t k) const { return tokens + (size_t)k * stride; }
+    __device__ uint32_t order(uint32_t k) const { return hits[k].read_index; }
+};
+
+struct GatheredBlocks {                              // source = the blocks of all ranks, rank-major (K4c)
+    const uint8_t* base;
+    uint32_t cap, stride, shard_reads;
+    __device__ size_t block_bytes() const { return kTokenBlockHeader + (size_t)cap * stride; }
+    __device__ const uint8_t* block(uint32_t r) const { return base + r * block_bytes(); }
+    __device__ bool valid(uint32_t k) const { return k % cap < *reinterpret_cast<const uint32_t*>(block(k / cap)); }
+    __device__ const uint8_t* rec(uint32_t k) const { return block(k / cap) + kTokenBlockHeader + (size_t)(k % cap) * stride; }
+    // shards are contiguous read ranges in rank order, so (rank, first read in shard) is the global first appearance
+    __device__ uint32_t order(uint32_t k) const { return (k / cap) * shard_reads + *reinterpret_cast<const uint32_t*>(rec(k) + stride - 4); }
+};
+
+template <class Src>
+__global__ void __launch_bounds__(256)
+k_block_dedupe(Src src, uint32_t n_slots, uint32_t* __restrict__ rep, uint32_t* __restrict__ first_read, uint32_t table_mask) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_slots || !src.valid(k)) return;
+    const uint8_t* mine = src.rec(k);
+    const uint32_t ord = src.order(k);
+    uint32_t i = token_hash(mine) & table_mask;
+    for (;;) {
+        uint32_t cur = atomicCAS(&rep[i], 0xFFFFFFFFu, k);
+        if (cur == 0xFFFFFFFFu) cur = k;
+        if (cur == k || token_equal(mine, src.rec(cur))) { atomicMin(&first_read[i], ord); return; }
+        i = (i + 1) & table_mask;
+    }
+}
+
+template <class Src>
+__global__ void __launch_bounds__(256)
+k_block_compact(Src src, const uint32_t* __restrict__ rep, const uint32_t* __restrict__ first_read, uint32_t table_size,
+                uint8_t* __restrict__ out_block, uint32_t out_cap, uint32_t stride) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= table_size) return;
+    const uint32_t r = rep[i];
+    if (r == 0xFFFFFFFFu) return;
+    const uint32_t j = atomicAdd(reinterpret_cast<uint32_t*>(out_block), 1u);
+    if (j >= out_cap) return;
+    const uint8_t* s = src.rec(r);
+    if (s[0] + 6u > stride) atomicOr(reinterpret_cast<uint32_t*>(out_block) + 1, 2u);      // token would run into its order key
+    uint8_t* dst = out_block + kTokenBlockHeader + (size_t)j * stride;
+    for (uint32_t b = 0; b + 4 < stride; b += 4) *reinterpret_cast<uint32_t*>(dst + b) = *reinterpret_cast<const uint32_t*>(s + b);
+    *reinterpret_cast<uint32_t*>(dst + stride - 4) = first_read[i];
+}
+
+// flags word of the merged block: bit 0 = some rank's own block had overflowed
+__global__ void k_block_flags(GatheredBlocks src, uint32_t n_ranks, uint8_t* __restrict__ out_block) {
+    if (threadIdx.x < n_ranks && *reinterpret_cast<const uint32_t*>(src.block(threadIdx.x)) > src.cap)
+        atomicOr(reinterpret_cast<uint32_t*>(out_block) + 1, 1u);
+}
+
 // ---- K1 generic --------------------------------------------------------------------------------------
 // LOCAL_SS > 0: the start/stop list lives in thread-local memory (short reads); otherwise in a slice of
 // ss_scratch (ss_cap entries per thread).

@@ -13,6 +13,50 @@ import torch.distributed as dist
 from . import api
 
 
+class TokenExchange:
+    """The exchange on the GPUs: K4b writes this shard's distinct DR tokens into a fixed-size token block, one NCCL
+    all-gather delivers every rank's block, K4c de-duplicates them with global first-appearance keys, and one
+    device-to-host copy brings the merged block back (one host synchronisation in total; the host only sorts the
+    merged records).  At world size 1 the all-gather and K4c drop out.  Blocks grow (x2) and the step is repeated if
+    a shard ever has more distinct tokens than fit; every rank sees the same merged header, so all ranks decide alike.
+    """
+
+    def __init__(self, ctx, device, shard_reads, stride=64, cap=16384, group=None):
+        self.ctx, self.dev, self.stride, self.group = ctx, torch.device(device), stride, group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.shard_reads = int(shard_reads)
+        self._alloc(cap)
+
+    def _alloc(self, cap):
+        self.cap = cap
+        self.out_cap = cap * min(self.world, 4) if self.world > 1 else cap
+        nb = api.token_block_bytes(cap, self.stride)
+        self.send = torch.empty(nb, dtype=torch.uint8, device=self.dev)
+        if self.world > 1:
+            self.recv = torch.empty(self.world * nb, dtype=torch.uint8, device=self.dev)
+            self.merged = torch.empty(api.token_block_bytes(self.out_cap, self.stride), dtype=torch.uint8, device=self.dev)
+        else:
+            self.merged = self.send
+        self.host = torch.empty(self.merged.numel(), dtype=torch.uint8, pin_memory=True)
+
+    def run(self, d_hits, n_hits, d_tokens, stream=0):
+        """-> (merged DR list as '\\n'-terminated text, number of distinct tokens of this shard or None when N > 1)"""
+        while True:
+            self.ctx.unique_tokens_block_dev(d_hits, n_hits, d_tokens, self.stride, self.send, self.cap, stream)
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+                self.ctx.merge_token_blocks_dev(self.recv, self.world, self.cap, self.stride, self.shard_reads, self.merged, self.out_cap, stream)
+            self.host.copy_(self.merged, non_blocking=True)
+            torch.cuda.current_stream(self.dev).synchronize()
+            text, count, flags = api.dr_list_from_block(self.host, self.out_cap, self.stride)
+            if flags & 2:
+                raise api.CrassB200Error(api.EINVAL, "token stride too small for the DR lengths in use")
+            if (flags & 1) or count > self.out_cap:
+                self._alloc(self.cap * 2)
+                continue
+            return text, count
+
+
 def allgather_unique_tokens(records, first_read, n_unique, stride=64, group=None):
     """The same exchange, fed straight from the device de-duplication (K4b) without a host round trip per rank.
 

@@ -103,6 +103,24 @@ const char* crass_b200_ctx_last_dr_list(const crass_b200_ctx* ctx);
 int crass_b200_unique_tokens_dev(crass_b200_ctx* ctx, const crass_b200_hit* d_hits, uint32_t n_hits, const void* d_tokens,
                                  uint32_t stride, void* d_out_tokens, uint32_t* d_out_first_read, uint32_t* d_out_count, void* stream);
 char* crass_b200_dr_list_from_unique(const uint8_t* records, uint32_t stride, const uint32_t* first_read, uint32_t n);
+/* K4b/K4c in block form -- the unit of the multi-GPU exchange (stands in for the single StringCheck
+ * that numbers DR tokens by first appearance, StringCheck.cpp:46-55, libcrispr.cpp:1119-1162).
+ * A token block is 16 header bytes {u32 count, u32 flags, 8 spare} followed by cap records of stride bytes (stride a
+ * multiple of 4, >= high_dr + 6): byte 0 = token length, byte 1 = orientation, bytes 2.. = token, last 4 bytes = order
+ * key (read index of first appearance).  count may exceed cap; the block then holds cap of the records and the caller
+ * retries with a larger block.  flags bit 0: a gathered block had overflowed; bit 1: a token did not fit its record.
+ *   unique_tokens_block : distinct tokens of d_hits[0..n_hits) -> d_block (order key = smallest read index)
+ *   merge_token_blocks  : d_blocks = n_ranks blocks of the same geometry back to back in rank order (what one
+ *                         all-gather delivers); shards are contiguous read ranges of at most shard_reads reads, so the
+ *                         merged order key rank*shard_reads + key reproduces the first-appearance order of one
+ *                         sequential run.  Output: one block of out_cap records.
+ *   dr_list_from_block  : host copy of a block -> '\n'-separated DR list in order-key order (malloc'd) */
+size_t crass_b200_token_block_bytes(uint32_t cap, uint32_t stride);
+int crass_b200_unique_tokens_block_dev(crass_b200_ctx* ctx, const crass_b200_hit* d_hits, uint32_t n_hits, const void* d_tokens,
+                                       uint32_t stride, void* d_block, uint32_t cap, void* stream);
+int crass_b200_merge_token_blocks_dev(crass_b200_ctx* ctx, const void* d_blocks, uint32_t n_ranks, uint32_t cap, uint32_t stride,
+                                      uint32_t shard_reads, void* d_out_block, uint32_t out_cap, void* stream);
+char* crass_b200_dr_list_from_block(const void* block, uint32_t cap, uint32_t stride, uint32_t* count, uint32_t* flags);
 /* the same list from token records copied back by the caller: records[k] belongs to hits[k] (unsorted, as on the device) */
 char* crass_b200_dr_list_from_tokens(const uint8_t* records, uint32_t stride, const crass_b200_hit* hits, uint32_t n_hits);
 

@@ -280,6 +280,74 @@ def test_device_dr_tokens_match_host_lowlexi(ctx, k1path):
     assert res.dr_list() == want
 
 
+def test_token_blocks_of_three_shards_merge_like_one_sequential_run(ctx):
+    """K4b in block form + K4c: three contiguous shards of unequal size, searched one after the other on this GPU, are
+    merged on the device exactly as the N-rank exchange does after its all-gather; the merged list must be the token
+    order of one sequential run over the whole batch (StringCheck numbers by first appearance)."""
+    import torch
+    rng = random.Random(107)
+    pool_drs = [fuzzgen.rand_seq(rng, rng.randint(24, 40)) for _ in range(12)]
+    reads = [fuzzgen.planted_read(rng, rng.choice([100, 150, 150, 250]), dr=rng.choice(pool_drs), sub_rate=rng.choice([0, 0.01])) for _ in range(9000)]
+    bases, offs = cb.pack_reads(reads)
+    ctx.upload(bases, offs)
+    hits, pool, _ = ctx.dr_search_resident(cb.Params())
+    want = api.dr_list_from_hits(bases, offs, hits, pool)
+    assert len(want) > 100
+    dev = torch.device("cuda", 0)
+    s = torch.cuda.Stream(device=dev)
+    TOK, cuts = 64, [0, 2500, 6100, len(reads)]
+    shard_reads = max(b - a for a, b in zip(cuts, cuts[1:]))
+    o64 = offs.astype(np.int64)
+
+    def shard_blocks(cap):
+        blocks = []
+        with torch.cuda.stream(s):
+            for lo, hi in zip(cuts, cuts[1:]):
+                n = hi - lo
+                d_b = torch.from_numpy(bases[int(o64[lo]):int(o64[hi])].copy()).to(dev)
+                d_o = torch.from_numpy(o64[lo:hi + 1] - o64[lo]).to(dev)
+                d_found = torch.empty(n, dtype=torch.uint8, device=dev)
+                d_hits = torch.empty((n + 16) * 4, dtype=torch.int32, device=dev)
+                d_pool = torch.empty(64 * n, dtype=torch.int32, device=dev)
+                d_cnt = torch.zeros(8, dtype=torch.int32, device=dev)
+                d_tok = torch.empty((n + 16) * TOK, dtype=torch.uint8, device=dev)
+                ctx.set_token_output(d_tok, TOK)
+                ctx.dr_search_dev(d_b, d_o, n, 256, cb.Params(), d_found, d_hits, d_pool, d_cnt, s.cuda_stream)
+                ctx.set_token_output(None)
+                nh = int(d_cnt.cpu()[0])
+                blk = torch.empty(api.token_block_bytes(cap, TOK), dtype=torch.uint8, device=dev)
+                ctx.unique_tokens_block_dev(d_hits, nh, d_tok, TOK, blk, cap, s.cuda_stream)
+                s.synchronize()
+                # one shard on its own: the block is that shard's list
+                sh = hits[(hits["read_index"] >= lo) & (hits["read_index"] < hi)].copy()
+                sh["read_index"] -= lo
+                text, count, flags = api.dr_list_from_block(blk.cpu().numpy(), cap, TOK)
+                local = api.dr_list_from_hits(bases[int(o64[lo]):int(o64[hi])].copy(), (o64[lo:hi + 1] - o64[lo]).astype(np.uint64), sh, pool)
+                assert count == len(local) and (count > cap or text == b"".join(d + b"\n" for d in local))
+                blocks.append(blk)
+        return blocks
+
+    cap = 4096
+    blocks = shard_blocks(cap)
+    with torch.cuda.stream(s):
+        out = torch.empty(api.token_block_bytes(3 * cap, TOK), dtype=torch.uint8, device=dev)
+        ctx.merge_token_blocks_dev(torch.cat(blocks), 3, cap, TOK, shard_reads, out, 3 * cap, s.cuda_stream)
+        s.synchronize()
+    text, count, flags = api.dr_list_from_block(out.cpu().numpy(), 3 * cap, TOK)
+    assert flags == 0 and count == len(want)
+    assert text == b"".join(d + b"\n" for d in want)
+    # blocks that are too small say so instead of dropping tokens silently
+    blocks = shard_blocks(8)
+    with torch.cuda.stream(s):
+        ctx.merge_token_blocks_dev(torch.cat(blocks), 3, 8, TOK, shard_reads, out, 3 * cap, s.cuda_stream)
+        s.synchronize()
+    assert api.dr_list_from_block(out.cpu().numpy(), 3 * cap, TOK)[2] & 1
+    with torch.cuda.stream(s):
+        ctx.merge_token_blocks_dev(torch.cat(shard_blocks(cap)), 3, cap, TOK, shard_reads, out, 16, s.cuda_stream)
+        s.synchronize()
+    assert api.dr_list_from_block(out.cpu().numpy(), 16, TOK)[1] == len(want)
+
+
 def test_singleton_scan_fuzz(ctx, P, k2path):
     rng = random.Random(105)
     for n_pat in (1, 7, 100, 1500, 12000):

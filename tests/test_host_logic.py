@@ -144,6 +144,29 @@ def test_non_redundant_set_long_list_worker_threads():
         assert sorted(l for l in a.split("\n") if l.startswith("P")) == sorted(l for l in b.split("\n") if l.startswith("P"))
 
 
+def test_dr_list_from_token_block():
+    """Host side of the exchange: a token block (header, records with the order key in their last four bytes)."""
+    rng = random.Random(29)
+    cap, stride = 50, 64
+    drs = [fuzzgen.rand_seq(rng, rng.randint(23, 47)) for _ in range(40)]
+    keys = rng.sample(range(10_000_000), len(drs))
+    blk = np.zeros(api.token_block_bytes(cap, stride), dtype=np.uint8)
+    assert blk.size == 16 + cap * stride
+    blk[:4] = np.frombuffer(np.uint32(len(drs)).tobytes(), dtype=np.uint8)
+    for slot, (d, k) in enumerate(zip(drs, keys)):
+        rec = blk[16 + slot * stride: 16 + (slot + 1) * stride]
+        rec[0] = len(d)
+        rec[2:2 + len(d)] = np.frombuffer(d, dtype=np.uint8)
+        rec[stride - 4:] = np.frombuffer(np.uint32(k).tobytes(), dtype=np.uint8)
+    text, count, flags = api.dr_list_from_block(blk, cap, stride)
+    assert count == len(drs) and flags == 0
+    assert text == b"".join(d + b"\n" for _k, d in sorted(zip(keys, drs)))
+    blk[:4] = np.frombuffer(np.uint32(1000).tobytes(), dtype=np.uint8)      # an overflowed block reports its true count
+    blk[4] = 1
+    text, count, flags = api.dr_list_from_block(blk, cap, stride)
+    assert count == 1000 and flags == 1 and text.count(b"\n") == len(drs)   # slots beyond the 40 written ones are empty
+
+
 def oracle_hits_phase1(batch, params=None):
     """Stand-in for kernel K1 on a box without a GPU: the oracle decides, the product replays."""
     P = checkers.port()
