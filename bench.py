@@ -246,6 +246,8 @@ def main():
         # one NCCL all-gather of the per-shard DR sets + deterministic merge (crass_b200/dist.py); identity at N=1
         return cbdist.allgather_dr_lists(local, device=dev)
 
+    ev_hits1 = torch.cuda.Event()
+
     def step_resident(record):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         e[0].record()
@@ -260,6 +262,7 @@ def main():
         # shard's tokens on the device, one NCCL all-gather + K4c merge the shards, one copy brings the list back
         merged, nu = exchange.run(d_hits, nh, d_tokens, stream)
         fetch_hits_async(0, nh, npool)                                 # the phase-1 hit records travel while the host clusters
+        ev_hits1.record()
         t3 = time.perf_counter()
         if args.dump_dr_list and rank == 0 and not record:
             open(args.dump_dr_list, "wb").write(merged)
@@ -273,10 +276,14 @@ def main():
             e[2].record()
             ctx.ac_scan_dev(ac, d_bases, d_offsets, n, READ_LEN, d_found, d_found2, d_hits, d_pool, d_cnt, stream)
             e[3].record()
+        ev_hits1.synchronize()
+        hits, pool = host_hits(0, nh, npool)
+        api.sort_hits(hits)                                            # read order (what replay consumes), while K2 runs
+        if pats:
             n2, npool2 = read_counters()
             fetch_hits_async(1, n2, npool2)
-        torch.cuda.synchronize()                                       # both hit lists are on the host now
-        hits, pool = host_hits(0, nh, npool)
+            torch.cuda.synchronize()                                   # both hit lists are on the host now
+            api.sort_hits(host_hits(1, n2, npool2)[0])
         if record:
             kt["k1"].append(e[0].elapsed_time(e[1]))
             if pats:

@@ -114,6 +114,7 @@ def lib():
         "crass_b200_results_adopt_tokens": (C.c_int, [vp, cp]),
         "crass_b200_results_non_redundant": (vp, [vp, C.c_uint32, u32p]),
         "crass_b200_results_dump": (vp, [vp, C.c_int]),
+        "crass_b200_sort_hits": (None, [vp, C.c_uint32]),
         "crass_b200_token_block_bytes": (C.c_size_t, [C.c_uint32, C.c_uint32]),
         "crass_b200_unique_tokens_block_dev": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp]),
         "crass_b200_merge_token_blocks_dev": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp]),
@@ -347,6 +348,12 @@ def dr_list_from_unique(records, stride, first_read, raw=False):
     (a list, or with raw=True the '\\n'-terminated text the C-ABI hands out)."""
     s = _take_str(lib().crass_b200_dr_list_from_unique(_np_ptr(records), stride, _np_ptr(first_read), len(first_read)))
     return s if raw else [x for x in s.split(b"\n") if x]
+
+
+def sort_hits(hits):
+    """In-place read-order sort of a host copy of device hit records (HIT_DTYPE numpy array or pinned torch view)."""
+    lib().crass_b200_sort_hits(C.c_void_p(_addr(hits)), len(hits))
+    return hits
 
 
 def token_block_bytes(cap, stride):

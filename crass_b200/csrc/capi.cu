@@ -179,6 +179,29 @@ int crass_b200_ctx_set_token_output(crass_b200_ctx* c, void* d_tokens, uint32_t 
 }
 const char* crass_b200_ctx_last_dr_list(const crass_b200_ctx* c) { return c ? c->last_dr_list.c_str() : ""; }
 
+// hit records come off the device in slot order; replay wants read order.  Read indices are distinct, so three
+// stable 11-bit counting passes do it in a fraction of the time of a comparison sort.
+void crass_b200_sort_hits(crass_b200_hit* hits, uint32_t n) {
+    if (!hits || n < 2) return;
+    if (n < 512) {
+        std::sort(hits, hits + n, [](const crass_b200_hit& a, const crass_b200_hit& b) { return a.read_index < b.read_index; });
+        return;
+    }
+    std::vector<crass_b200_hit> tmp(n);
+    crass_b200_hit* src = hits;
+    crass_b200_hit* dst = tmp.data();
+    uint32_t top = 0;
+    for (uint32_t i = 0; i < n; ++i) top |= hits[i].read_index;
+    for (uint32_t shift = 0; shift < 32 && (top >> shift); shift += 11) {
+        uint32_t count[2049] = {0};
+        for (uint32_t i = 0; i < n; ++i) count[((src[i].read_index >> shift) & 2047u) + 1]++;
+        for (uint32_t b = 0; b < 2048; ++b) count[b + 1] += count[b];
+        for (uint32_t i = 0; i < n; ++i) dst[count[(src[i].read_index >> shift) & 2047u]++] = src[i];
+        std::swap(src, dst);
+    }
+    if (src != hits) memcpy(hits, src, sizeof(crass_b200_hit) * (size_t)n);
+}
+
 int crass_b200_unique_tokens_dev(crass_b200_ctx* c, const crass_b200_hit* d_hits, uint32_t n_hits, const void* d_tokens, uint32_t stride,
                                  void* d_out_tokens, uint32_t* d_out_first_read, uint32_t* d_out_count, void* stream_v) {
     if (!c || !d_out_count) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
@@ -408,7 +431,7 @@ int run_with_outputs(crass_b200_ctx* c, uint32_t n_reads, uint64_t n_bases, uint
         }
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    std::sort(h, h + nh, [](const crass_b200_hit& a, const crass_b200_hit& b) { return a.read_index < b.read_index; });
+    crass_b200_sort_hits(h, nh);
     *hits = h; *n_hits = nh; *ss_pool = p; *n_ss_pool = np;
     (void)n_bases;
     return 0;

@@ -96,6 +96,9 @@ uint64_t crass_b200_ctx_last_candidates(const crass_b200_ctx* ctx);
 int crass_b200_ctx_set_token_output(crass_b200_ctx* ctx, void* d_tokens, uint32_t stride);
 /* the distinct tokens of the most recent crass_b200_dr_search_resident in read order, '\n'-separated (owned by ctx) */
 const char* crass_b200_ctx_last_dr_list(const crass_b200_ctx* ctx);
+/* the *_dev entry points leave hit records in device slot order; this puts a host copy into read order (what the
+ * host-buffer calls return and replay requires), in place */
+void crass_b200_sort_hits(crass_b200_hit* hits, uint32_t n_hits);
 /* K4b: de-duplicate the token records of d_hits[0..n_hits) on the device.  Writes the distinct records to d_out_tokens
  * (same stride), the smallest read index carrying each to d_out_first_read, and their number to d_out_count; all three
  * must hold n_hits entries in the worst case.  Order is arbitrary: sort by first_read for first-appearance order

@@ -144,6 +144,18 @@ def test_non_redundant_set_long_list_worker_threads():
         assert sorted(l for l in a.split("\n") if l.startswith("P")) == sorted(l for l in b.split("\n") if l.startswith("P"))
 
 
+def test_sort_hits_puts_device_order_into_read_order():
+    rng = np.random.default_rng(31)
+    for n, top in ((0, 10), (1, 10), (300, 5000), (2000, 2**11), (5000, 2**22 + 5), (70000, 10_000_000), (40000, 2**32 - 1)):
+        hits = np.zeros(n, dtype=api.HIT_DTYPE)
+        hits["read_index"] = rng.choice(top, size=n, replace=False) if top < 2**31 else rng.integers(0, top, size=n, dtype=np.uint64)
+        hits["ss_offset"] = np.arange(n)
+        hits["n_ss"] = 2 * (1 + np.arange(n) % 5)
+        want = hits[np.argsort(hits["read_index"], kind="stable")]
+        api.sort_hits(hits)
+        assert np.array_equal(hits, want)
+
+
 def test_dr_list_from_token_block():
     """Host side of the exchange: a token block (header, records with the order key in their last four bytes)."""
     rng = random.Random(29)
