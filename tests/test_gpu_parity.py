@@ -43,16 +43,20 @@ def k1path(request):
         os.environ["CRASS_B200_K1"] = old
 
 
-@pytest.fixture(params=["fast", "generic"])
+@pytest.fixture(params=["fast", "fast-list", "generic"])
 def k2path(request):
-    """K2 likewise: 16-mer q-gram filter + automaton walk over the candidates, or the plain one-thread-per-read walk."""
-    old = os.environ.get("CRASS_B200_K2")
-    os.environ["CRASS_B200_K2"] = request.param
+    """K2 likewise: 16-mer q-gram filter + verification of the candidates (one warp, or with "fast-list" one thread, per
+    candidate), or the plain one-thread-per-read automaton walk."""
+    old = os.environ.get("CRASS_B200_K2"), os.environ.get("CRASS_B200_K2V")
+    os.environ["CRASS_B200_K2"] = request.param.split("-")[0]
+    if request.param == "fast-list":
+        os.environ["CRASS_B200_K2V"] = "list"
     yield request.param
-    if old is None:
-        os.environ.pop("CRASS_B200_K2", None)
-    else:
-        os.environ["CRASS_B200_K2"] = old
+    for k, v in zip(("CRASS_B200_K2", "CRASS_B200_K2V"), old):
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
 @pytest.fixture(scope="module")
