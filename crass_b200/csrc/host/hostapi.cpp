@@ -344,6 +344,11 @@ char* crass_b200_non_redundant_set(const char* dr_list, uint32_t kmer_clust) {
 
 int crass_b200_ac_build_from_dr_list(const char* dr_list, uint32_t kmer_clust, crass_b200_ac** out, uint32_t* n_patterns) {
     if (!dr_list || !out) return fail(CRASS_B200_EINVAL, "NULL argument");
+#ifdef CB_PROFILE_NR
+    const auto t_in = std::chrono::steady_clock::now();
+    struct Tail { std::chrono::steady_clock::time_point t0; ~Tail() {
+        fprintf(stderr, "non_redundant_set: whole-call %.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); } } tail{t_in};
+#endif
     std::vector<std::string_view> lines;                                        // views into the caller's text
     const std::string_view all(dr_list);
     for (size_t p = 0; p < all.size();) {
@@ -352,7 +357,15 @@ int crass_b200_ac_build_from_dr_list(const char* dr_list, uint32_t kmer_clust, c
         if (e > p) lines.push_back(all.substr(p, e - p));
         p = e + 1;
     }
+#ifdef CB_PROFILE_NR
+    fprintf(stderr, "non_redundant_set: split %.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_in).count());
+#endif
     const std::vector<std::string> nr = non_redundant_set(lines, (int)kmer_clust, nullptr);
+#ifdef CB_PROFILE_NR
+    const auto t_nr = std::chrono::steady_clock::now();
+    struct Tail2 { std::chrono::steady_clock::time_point t0; ~Tail2() {
+        fprintf(stderr, "non_redundant_set: build %.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); } } tail2{t_nr};
+#endif
     if (n_patterns) *n_patterns = (uint32_t)nr.size();
     std::vector<uint8_t> bytes;
     std::vector<uint32_t> offs(1, 0);

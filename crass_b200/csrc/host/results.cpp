@@ -15,7 +15,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <functional>
+#include <mutex>
 #include <sstream>
 #include <thread>
 #include <unordered_map>
@@ -143,6 +145,56 @@ struct SpinBarrier {
     }
     unsigned n_;
     std::atomic<unsigned> count_{0}, gen_{0};
+};
+
+// Helper threads that outlive the call: starting eight threads costs about as much as the passes they run.
+// run(n, job) executes job(1..n-1) on the helpers and job(0) on the caller and returns when all are through;
+// parallel regions of different callers are serialised.
+class WorkerPool {
+public:
+    static WorkerPool& instance() { static WorkerPool p; return p; }
+    void run(unsigned n, const std::function<void(unsigned)>& job) {
+        if (n <= 1) { job(0); return; }
+        std::lock_guard<std::mutex> one_region(region_);
+        {
+            std::lock_guard<std::mutex> l(m_);
+            while (threads_.size() < n - 1) { const unsigned id = (unsigned)threads_.size(); threads_.emplace_back([this, id]() { loop(id); }); }
+            job_ = &job; n_active_ = n - 1; pending_ = n - 1; ++generation_;
+        }
+        wake_.notify_all();
+        job(0);
+        std::unique_lock<std::mutex> l(m_);
+        done_.wait(l, [this]() { return pending_ == 0; });
+    }
+    ~WorkerPool() {
+        { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+        wake_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+private:
+    void loop(unsigned id) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(unsigned)>* job = nullptr;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                wake_.wait(l, [&]() { return stop_ || (generation_ != seen && id < n_active_); });
+                if (stop_) return;
+                seen = generation_;
+                job = job_;
+            }
+            (*job)(id + 1);
+            std::lock_guard<std::mutex> l(m_);
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    std::mutex region_, m_;
+    std::condition_variable wake_, done_;
+    std::vector<std::thread> threads_;
+    const std::function<void(unsigned)>* job_ = nullptr;
+    unsigned n_active_ = 0, pending_ = 0;
+    uint64_t generation_ = 0;
+    bool stop_ = false;
 };
 
 // small per-worker open-addressing map (k-mer key -> head of a chain of survivors) for the substring reduction
@@ -442,12 +494,7 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& 
         HeadTable map, full;
         for (size_t i; (i = next_group.fetch_add(1)) < schedule.size();) reduce_group(schedule[i], map, full);
     };
-    {
-        std::vector<std::thread> pool;
-        for (unsigned w = 1; w < n_workers; ++w) pool.emplace_back(worker, w);
-        worker(0);
-        for (auto& th : pool) th.join();
-    }
+    WorkerPool::instance().run(n_workers, worker);
     CB_NR_MARK("reduce");
     std::vector<std::string> out;
     for (size_t g = 0; g < members.size(); ++g) {
