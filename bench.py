@@ -6,8 +6,8 @@
 Workload (config.workload = "config2"): BASELINE.json configs[1], synthetic 10M x 150 bp Illumina reads with 50 planted
 CRISPR DR types per GPU (weak scaling: every rank scans its own 10M-read shard; configs[3] is the same recipe sharded).
 A "step" is one pass of the hot path over the shard:
-    K1 direct-repeat search -> hits to host -> distinct DR list -> [NCCL allgather + deterministic merge when N>1]
-    -> createNonRedundantSet -> automaton build + upload -> K2 singleton scan -> hits to host.
+    K1 direct-repeat search (+K4 tokens) -> K4b distinct-token block [-> NCCL all-gather -> K4c merge when N>1] -> DR list
+    to host -> createNonRedundantSet + matcher build + upload -> K2 singleton scan -> both hit lists to host, read order.
 `value`  : reads/s with the batch already resident in HBM (device timed with CUDA events, max over ranks).
 `e2e`    : the same pass through the host-buffer C-ABI (crass_b200_batch_upload / _dr_search_resident / _ac_scan_resident
            + replay into the ReadMap mirror), pinned host input copied H2D and hit records copied D2H inside the timed region.
@@ -346,6 +346,11 @@ def main():
         bytes_k2 = n_bases + 8 * n + n + n + stats["hits_phase2"] * 16
         dom, dom_ms, dom_bytes = ("K1 dr_search", k1, bytes_k1) if k1 >= k2 else ("K2 singleton_scan", k2, bytes_k2)
         achieved = dom_bytes / (dom_ms / 1e3) / 1e9
+        traffic = None                                                         # measured DRAM bytes per launch, from the committed ncu capture
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["config2_%dx%d" % (n, READ_LEN)][dom]["bytes"]
+        except (OSError, KeyError, ValueError):
+            pass
         line = {"metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
                 "data": "synthetic", "config": config,
@@ -354,7 +359,7 @@ def main():
                         "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": int(dom_bytes),
+                             "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": int(dom_bytes),
                              "kernel_ms": dom_ms},
                 "kernels": {"k1_dr_search_ms": k1, "k1_frac_of_hbm": bytes_k1 / (k1 / 1e3) / 1e9 / peak,
                             "k2_singleton_scan_ms": k2, "k2_frac_of_hbm": (bytes_k2 / (k2 / 1e3) / 1e9 / peak) if k2 else None,
