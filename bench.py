@@ -222,7 +222,7 @@ def main():
 
     TOK = 64                                                           # bytes per K4 token record (>= high_dr + 2)
     d_tokens = torch.empty(hits_cap * TOK, dtype=torch.uint8, device=dev)
-    host_ms = {"fetch": [], "merge": [], "cluster_build": [], "ac_upload": []}
+    host_ms = {k: [] for k in ("fetch", "merge", "cluster_build", "ac_upload", "sort_hits1_during_k2", "k2_wait", "fetch_sort_hits2")}
 
     exchange = cbdist.TokenExchange(ctx, dev, shard_reads=n, stride=TOK)   # K4b (+ all-gather + K4c at N > 1)
     h_hits = [torch.empty(hits_cap * 4, dtype=torch.int32, pin_memory=True) for _ in range(2)]
@@ -279,16 +279,20 @@ def main():
         ev_hits1.synchronize()
         hits, pool = host_hits(0, nh, npool)
         api.sort_hits(hits)                                            # read order (what replay consumes), while K2 runs
+        t6 = time.perf_counter()
         if pats:
             n2, npool2 = read_counters()
+            t7 = time.perf_counter()
             fetch_hits_async(1, n2, npool2)
             torch.cuda.synchronize()                                   # both hit lists are on the host now
             api.sort_hits(host_hits(1, n2, npool2)[0])
+            t8 = time.perf_counter()
         if record:
             kt["k1"].append(e[0].elapsed_time(e[1]))
             if pats:
                 kt["k2"].append(e[2].elapsed_time(e[3]))
-                for k, v in zip(("fetch", "merge", "cluster_build", "ac_upload"), (t1 - t0, t3 - t1, t4 - t3, t5 - t4)):
+                for k, v in zip(("fetch", "merge", "cluster_build", "ac_upload", "sort_hits1_during_k2", "k2_wait", "fetch_sort_hits2"),
+                                (t1 - t0, t3 - t1, t4 - t3, t5 - t4, t6 - t5, t7 - t6, t8 - t7)):
                     host_ms[k].append(v * 1e3)
         stats.update(hits_phase1=len(hits), dr_variants_merged=nu, patterns=pats, hits_phase2=n2)
 
