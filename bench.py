@@ -204,6 +204,9 @@ def main():
     torch.cuda.synchronize()
     np_bases, np_offsets = h_bases.numpy(), h_offsets.numpy().view(np.uint64)
 
+    # the host passes between the kernels use a few helper threads per rank: share the box's cores between the ranks
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    os.environ.setdefault("CRASS_B200_HOST_THREADS", str(max(1, min(8, (os.cpu_count() or 8) // max(local_world, 1)))))
     ctx = cb.Context(local_rank)
     params = cb.Params()
     work_stream = torch.cuda.Stream(device=dev)          # a real (non-NULL) stream: kernels, copies and events all go here
@@ -214,6 +217,7 @@ def main():
     d_found = torch.empty(n, dtype=torch.uint8, device=dev)
     d_found2 = torch.empty(n, dtype=torch.uint8, device=dev)
     d_hits = torch.empty(hits_cap * 4, dtype=torch.int32, device=dev)
+    d_sorted = torch.empty(hits_cap * 4, dtype=torch.int32, device=dev)      # the hit records in read order
     d_pool = torch.empty(pool_cap, dtype=torch.int32, device=dev)
     d_cnt = torch.zeros(8, dtype=torch.int32, device=dev)
     h_cnt = torch.zeros(8, dtype=torch.int32, pin_memory=True)
@@ -222,7 +226,7 @@ def main():
 
     TOK = 64                                                           # bytes per K4 token record (>= high_dr + 2)
     d_tokens = torch.empty(hits_cap * TOK, dtype=torch.uint8, device=dev)
-    host_ms = {k: [] for k in ("fetch", "merge", "cluster_build", "ac_upload", "sort_hits1_during_k2", "k2_wait", "fetch_sort_hits2")}
+    host_ms = {k: [] for k in ("fetch", "merge", "cluster_build", "ac_upload", "k2_wait", "fetch_hits2")}
 
     exchange = cbdist.TokenExchange(ctx, dev, shard_reads=n, stride=TOK)   # K4b (+ all-gather + K4c at N > 1)
     h_hits = [torch.empty(hits_cap * 4, dtype=torch.int32, pin_memory=True) for _ in range(2)]
@@ -236,7 +240,7 @@ def main():
 
     def fetch_hits_async(which, nh, npool):
         """hit records -> pinned host memory, asynchronously on the work stream (device order; consumers sort by read index)"""
-        h_hits[which][: nh * 4].copy_(d_hits[: nh * 4], non_blocking=True)
+        h_hits[which][: nh * 4].copy_(d_sorted[: nh * 4], non_blocking=True)
         h_pool[which][: max(npool, 1)].copy_(d_pool[: max(npool, 1)], non_blocking=True)
 
     def host_hits(which, nh, npool):
@@ -246,8 +250,6 @@ def main():
         # one NCCL all-gather of the per-shard DR sets + deterministic merge (crass_b200/dist.py); identity at N=1
         return cbdist.allgather_dr_lists(local, device=dev)
 
-    ev_hits1 = torch.cuda.Event()
-
     def step_resident(record):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         e[0].record()
@@ -255,6 +257,7 @@ def main():
         ctx.dr_search_dev(d_bases, d_offsets, n, READ_LEN, params, d_found, d_hits, d_pool, d_cnt, stream)
         ctx.set_token_output(None)
         e[1].record()
+        ctx.sort_hits_dev(d_found, n, d_hits, d_cnt, hits_cap, d_sorted, stream)       # read order (what replay consumes)
         t0 = time.perf_counter()
         nh, npool = read_counters()
         t1 = time.perf_counter()
@@ -262,7 +265,6 @@ def main():
         # shard's tokens on the device, one NCCL all-gather + K4c merge the shards, one copy brings the list back
         merged, nu = exchange.run(d_hits, nh, d_tokens, stream)
         fetch_hits_async(0, nh, npool)                                 # the phase-1 hit records travel while the host clusters
-        ev_hits1.record()
         t3 = time.perf_counter()
         if args.dump_dr_list and rank == 0 and not record:
             open(args.dump_dr_list, "wb").write(merged)
@@ -276,23 +278,19 @@ def main():
             e[2].record()
             ctx.ac_scan_dev(ac, d_bases, d_offsets, n, READ_LEN, d_found, d_found2, d_hits, d_pool, d_cnt, stream)
             e[3].record()
-        ev_hits1.synchronize()
-        hits, pool = host_hits(0, nh, npool)
-        api.sort_hits(hits)                                            # read order (what replay consumes), while K2 runs
-        t6 = time.perf_counter()
-        if pats:
+            ctx.sort_hits_dev(d_found2, n, d_hits, d_cnt, hits_cap, d_sorted, stream)
             n2, npool2 = read_counters()
-            t7 = time.perf_counter()
+            t6 = time.perf_counter()
             fetch_hits_async(1, n2, npool2)
-            torch.cuda.synchronize()                                   # both hit lists are on the host now
-            api.sort_hits(host_hits(1, n2, npool2)[0])
-            t8 = time.perf_counter()
+        torch.cuda.synchronize()                                       # both hit lists are on the host now, in read order
+        hits, pool = host_hits(0, nh, npool)
+        t7 = time.perf_counter()
         if record:
             kt["k1"].append(e[0].elapsed_time(e[1]))
             if pats:
                 kt["k2"].append(e[2].elapsed_time(e[3]))
-                for k, v in zip(("fetch", "merge", "cluster_build", "ac_upload", "sort_hits1_during_k2", "k2_wait", "fetch_sort_hits2"),
-                                (t1 - t0, t3 - t1, t4 - t3, t5 - t4, t6 - t5, t7 - t6, t8 - t7)):
+                for k, v in zip(("fetch", "merge", "cluster_build", "ac_upload", "k2_wait", "fetch_hits2"),
+                                (t1 - t0, t3 - t1, t4 - t3, t5 - t4, t6 - t5, t7 - t6)):
                     host_ms[k].append(v * 1e3)
         stats.update(hits_phase1=len(hits), dr_variants_merged=nu, patterns=pats, hits_phase2=n2)
 
@@ -327,15 +325,16 @@ def main():
     for _ in range(args.warmup):
         step_resident(False)
     launches0 = ctx.launch_count
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = ClockSampler(local_rank) if rank == 0 else None         # one nvidia-smi poller per job, not per rank
+    if sampler:
+        sampler.start()
     ms_total = timed(lambda: step_resident(True), args.steps)
-    clocks = sampler.stop()
     launches = ctx.launch_count - launches0
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     d2h = [0]
     ms_e2e = timed(lambda: d2h.__setitem__(0, step_e2e()), args.steps)
+    clocks = sampler.stop() if sampler else None                       # sampled across both timed regions
 
     if rank == 0:
         total_reads = n * world

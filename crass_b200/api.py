@@ -115,6 +115,7 @@ def lib():
         "crass_b200_results_non_redundant": (vp, [vp, C.c_uint32, u32p]),
         "crass_b200_results_dump": (vp, [vp, C.c_int]),
         "crass_b200_sort_hits": (None, [vp, C.c_uint32]),
+        "crass_b200_sort_hits_dev": (C.c_int, [vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp, vp]),
         "crass_b200_token_block_bytes": (C.c_size_t, [C.c_uint32, C.c_uint32]),
         "crass_b200_unique_tokens_block_dev": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp]),
         "crass_b200_merge_token_blocks_dev": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp]),
@@ -420,6 +421,11 @@ class Context:
         """K4b: device-side de-duplication of the token records of the first n_hits hit slots (torch tensors)."""
         _check(lib().crass_b200_unique_tokens_dev(self.h, d_hits.data_ptr(), n_hits, d_tokens.data_ptr(), stride, d_out_tokens.data_ptr(),
                                                   d_out_first_read.data_ptr(), d_out_count.data_ptr(), stream))
+
+    def sort_hits_dev(self, d_found, n_reads, d_hits, d_counters, max_hits, d_sorted, stream=0):
+        """Hit records of a *_dev search into read order on the device (d_counters: the launch's counter tensor)."""
+        _check(lib().crass_b200_sort_hits_dev(self.h, d_found.data_ptr(), n_reads, d_hits.data_ptr(), d_counters.data_ptr(), max_hits,
+                                              d_sorted.data_ptr(), stream))
 
     def unique_tokens_block_dev(self, d_hits, n_hits, d_tokens, stride, d_block, cap, stream=0):
         """K4b in block form (see include/crass_b200.h): distinct tokens of the hit list -> one token block."""

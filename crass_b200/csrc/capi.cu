@@ -95,6 +95,7 @@ struct crass_b200_ctx {
     bool res_valid = false, res_found_valid = false;
     DevBuf d_found_p1, d_cand, d_tokens, d_tok_table, d_tok_unique, d_ac_table, d_ac_symv, d_ac_bitmap, d_ac_keys;
     DevBuf d_ac_skeys, d_ac_shead, d_ac_pnext, d_ac_poffs, d_ac_pbytes;
+    DevBuf d_rank, d_hits_sorted;        // crass_b200_sort_hits_dev: per-chunk prefix counts, read-ordered copy of the hits
     uint64_t ac_serial = 0;              // build serial of the automaton currently held in d_ac_*
     uint64_t ac_dfa_serial = 0;          // ... and of the dense DFA (generic K2 path), uploaded lazily
     // K4 token output of the next dr_search launches (crass_b200_ctx_set_token_output / host forms)
@@ -161,7 +162,8 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = {&c->d_bases, &c->d_offsets, &c->d_found, &c->d_skip, &c->d_hits, &c->d_pool, &c->d_counters,
                       &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv, &c->d_found_p1, &c->d_cand, &c->d_tokens, &c->d_tok_table, &c->d_tok_unique, &c->d_ac_table, &c->d_ac_symv,
-                      &c->d_ac_bitmap, &c->d_ac_keys, &c->d_ac_skeys, &c->d_ac_shead, &c->d_ac_pnext, &c->d_ac_poffs, &c->d_ac_pbytes};
+                      &c->d_ac_bitmap, &c->d_ac_keys, &c->d_ac_skeys, &c->d_ac_shead, &c->d_ac_pnext, &c->d_ac_poffs, &c->d_ac_pbytes,
+                      &c->d_rank, &c->d_hits_sorted};
     for (DevBuf* b : bufs) b->release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     cudaStreamDestroy(c->stream);
@@ -179,27 +181,31 @@ int crass_b200_ctx_set_token_output(crass_b200_ctx* c, void* d_tokens, uint32_t 
 }
 const char* crass_b200_ctx_last_dr_list(const crass_b200_ctx* c) { return c ? c->last_dr_list.c_str() : ""; }
 
-// hit records come off the device in slot order; replay wants read order.  Read indices are distinct, so three
-// stable 11-bit counting passes do it in a fraction of the time of a comparison sort.
+// hit records come off the device in slot order; replay wants read order.  Read indices are distinct, so three or four
+// stable 8-bit counting passes over (index, slot) pairs do it in a fraction of the time of a comparison sort.
 void crass_b200_sort_hits(crass_b200_hit* hits, uint32_t n) {
     if (!hits || n < 2) return;
     if (n < 512) {
         std::sort(hits, hits + n, [](const crass_b200_hit& a, const crass_b200_hit& b) { return a.read_index < b.read_index; });
         return;
     }
-    std::vector<crass_b200_hit> tmp(n);
-    crass_b200_hit* src = hits;
-    crass_b200_hit* dst = tmp.data();
+    // sort (read index, slot) pairs, then move every record once; the work arrays are kept per thread
+    static thread_local std::vector<uint64_t> ka, kb;
+    static thread_local std::vector<crass_b200_hit> tmp;
+    if (ka.size() < n) { ka.resize(n + n / 4); kb.resize(ka.size()); tmp.resize(ka.size()); }
+    uint64_t* src = ka.data();
+    uint64_t* dst = kb.data();
     uint32_t top = 0;
-    for (uint32_t i = 0; i < n; ++i) top |= hits[i].read_index;
-    for (uint32_t shift = 0; shift < 32 && (top >> shift); shift += 11) {
-        uint32_t count[2049] = {0};
-        for (uint32_t i = 0; i < n; ++i) count[((src[i].read_index >> shift) & 2047u) + 1]++;
-        for (uint32_t b = 0; b < 2048; ++b) count[b + 1] += count[b];
-        for (uint32_t i = 0; i < n; ++i) dst[count[(src[i].read_index >> shift) & 2047u]++] = src[i];
+    for (uint32_t i = 0; i < n; ++i) { top |= hits[i].read_index; src[i] = ((uint64_t)hits[i].read_index << 32) | i; }
+    for (uint32_t shift = 0; shift < 32 && (top >> shift); shift += 8) {       // 256 write streams stay inside L1
+        uint32_t count[257] = {0};
+        for (uint32_t i = 0; i < n; ++i) count[((src[i] >> (32 + shift)) & 255u) + 1]++;
+        for (uint32_t b = 0; b < 256; ++b) count[b + 1] += count[b];
+        for (uint32_t i = 0; i < n; ++i) dst[count[(src[i] >> (32 + shift)) & 255u]++] = src[i];
         std::swap(src, dst);
     }
-    if (src != hits) memcpy(hits, src, sizeof(crass_b200_hit) * (size_t)n);
+    memcpy(tmp.data(), hits, sizeof(crass_b200_hit) * (size_t)n);
+    for (uint32_t i = 0; i < n; ++i) hits[i] = tmp[(uint32_t)src[i]];
 }
 
 int crass_b200_unique_tokens_dev(crass_b200_ctx* c, const crass_b200_hit* d_hits, uint32_t n_hits, const void* d_tokens, uint32_t stride,
@@ -221,6 +227,24 @@ int crass_b200_unique_tokens_dev(crass_b200_ctx* c, const crass_b200_hit* d_hits
     cbk::k_token_compact<<<(cap + 255) / 256, 256, 0, st>>>(rep, first_read, cap, (const uint8_t*)d_tokens, stride, (uint8_t*)d_out_tokens,
                                                            d_out_first_read, d_out_count);
     c->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int crass_b200_sort_hits_dev(crass_b200_ctx* c, const uint8_t* d_found, uint32_t n_reads, const crass_b200_hit* d_hits,
+                             const uint32_t* d_n_hits, uint32_t max_hits, crass_b200_hit* d_sorted, void* stream_v) {
+    if (!c || !d_found || !d_hits || !d_n_hits || !d_sorted) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    if (((uintptr_t)d_found) & 15) return cbh::fail(CRASS_B200_EINVAL, "found flags must be 16-byte aligned");
+    if (n_reads == 0 || max_hits == 0) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
+    const uint32_t n_chunks = (n_reads + cbk::kRankChunk - 1) / cbk::kRankChunk;
+    if (int r = c->d_rank.reserve((size_t)n_chunks * sizeof(uint32_t))) return r;
+    uint32_t* chunks = c->d_rank.as<uint32_t>();
+    cbk::k_rank_chunks<<<n_chunks, 64, 0, st>>>(d_found, n_reads, chunks);
+    cbk::k_rank_scan<<<1, 1024, 0, st>>>(chunks, n_chunks);
+    cbk::k_rank_scatter<<<(max_hits + 255) / 256, 256, 0, st>>>(d_found, chunks, d_hits, d_n_hits, max_hits, d_sorted);
+    c->launches += 3;
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -399,7 +423,12 @@ int run_with_outputs(crass_b200_ctx* c, uint32_t n_reads, uint64_t n_bases, uint
     crass_b200_hit* h = (crass_b200_hit*)malloc(sizeof(crass_b200_hit) * (size_t)(nh ? nh : 1));
     uint32_t* p = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(np ? np : 1));
     if (!h || !p) { free(h); free(p); return cbh::fail(CRASS_B200_ENOMEM, "malloc"); }
-    if (nh) CUDA_TRY(cudaMemcpyAsync(h, c->d_hits.p, sizeof(crass_b200_hit) * (size_t)nh, cudaMemcpyDeviceToHost, c->stream));
+    if (nh) {                                                  // the hit records travel in read order (what replay consumes)
+        if (int r = c->d_hits_sorted.reserve(sizeof(crass_b200_hit) * (size_t)nh)) { free(h); free(p); return r; }
+        if (int r = crass_b200_sort_hits_dev(c, c->d_found.as<uint8_t>(), n_reads, c->d_hits.as<crass_b200_hit>(), c->d_counters.as<uint32_t>(), nh,
+                                             c->d_hits_sorted.as<crass_b200_hit>(), c->stream)) { free(h); free(p); return r; }
+        CUDA_TRY(cudaMemcpyAsync(h, c->d_hits_sorted.p, sizeof(crass_b200_hit) * (size_t)nh, cudaMemcpyDeviceToHost, c->stream));
+    }
     if (np) CUDA_TRY(cudaMemcpyAsync(p, c->d_pool.p, sizeof(uint32_t) * (size_t)np, cudaMemcpyDeviceToHost, c->stream));
     if (found_host) CUDA_TRY(cudaMemcpyAsync(found_host, c->d_found.p, n_reads, cudaMemcpyDeviceToHost, c->stream));
     if (token_stride) {
@@ -431,7 +460,6 @@ int run_with_outputs(crass_b200_ctx* c, uint32_t n_reads, uint64_t n_bases, uint
         }
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    crass_b200_sort_hits(h, nh);
     *hits = h; *n_hits = nh; *ss_pool = p; *n_ss_pool = np;
     (void)n_bases;
     return 0;

@@ -129,6 +129,75 @@ k_token_compact(const uint32_t* __restrict__ rep, const uint32_t* __restrict__ f
     for (uint32_t b = 0; b < stride; b += 4) *reinterpret_cast<uint32_t*>(dst + b) = *reinterpret_cast<const uint32_t*>(src + b);
 }
 
+// ---- hit records into read order on the device -----------------------------------------------------------------
+// Every read has at most one hit and found[r] != 0 marks exactly the reads that have one, so the position of a hit in
+// read order is the number of marked reads before it: per-chunk counts, one exclusive scan, then every hit counts the
+// marked reads of its own chunk in front of it and moves its record there.  (The flags are 10 MB for 10 M reads and
+// stay in L2 between the three launches.)
+constexpr uint32_t kRankChunk = 1024;                // reads per chunk
+
+__device__ __forceinline__ uint32_t count_marked16(const uint4& v) {                   // 16 flag bytes, each 0 or 1
+    return __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) + __popc(v.w & 0x01010101u);
+}
+
+__global__ void __launch_bounds__(64)
+k_rank_chunks(const uint8_t* __restrict__ found, uint32_t n_reads, uint32_t* __restrict__ chunk_count) {
+    const uint32_t c = blockIdx.x;                                                      // one chunk per CTA, 16 bytes per thread
+    const uint32_t r = c * kRankChunk + threadIdx.x * 16u;
+    uint32_t s = 0;
+    if (r + 16 <= n_reads) s = count_marked16(*reinterpret_cast<const uint4*>(found + r));
+    else for (uint32_t i = r; i < n_reads; ++i) s += found[i] & 1u;
+    s = __reduce_add_sync(0xFFFFFFFFu, s);
+    __shared__ uint32_t w[2];
+    if ((threadIdx.x & 31u) == 0) w[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) chunk_count[c] = w[0] + w[1];
+}
+
+__global__ void __launch_bounds__(1024)
+k_rank_scan(uint32_t* __restrict__ chunk_count, uint32_t n_chunks) {                    // in place: counts -> exclusive prefix
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_chunks; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_chunks ? chunk_count[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+        if ((threadIdx.x & 31u) == 31u) warp_sum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t s = warp_sum[threadIdx.x];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, s, d); if ((int)threadIdx.x >= d) s += y; }
+            warp_sum[threadIdx.x] = s;                                                  // inclusive over the warps
+        }
+        __syncthreads();
+        const uint32_t before = carry + (threadIdx.x >= 32 ? warp_sum[(threadIdx.x >> 5) - 1] : 0u) + x - v;
+        if (i < n_chunks) chunk_count[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_rank_scatter(const uint8_t* __restrict__ found, const uint32_t* __restrict__ chunk_before, const crass_b200_hit* __restrict__ hits,
+               const uint32_t* __restrict__ n_hits_dev, uint32_t max_hits, crass_b200_hit* __restrict__ sorted) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_hits = min(*n_hits_dev, max_hits);
+    if (k >= n_hits) return;
+    const crass_b200_hit h = hits[k];
+    const uint32_t c0 = (h.read_index / kRankChunk) * kRankChunk;
+    uint32_t rank = chunk_before[h.read_index / kRankChunk];
+    uint32_t r = c0;
+    for (; r + 16 <= h.read_index; r += 16) rank += count_marked16(*reinterpret_cast<const uint4*>(found + r));
+    for (; r < h.read_index; ++r) rank += found[r] & 1u;
+    if (rank < max_hits) sorted[rank] = h;
+}
+
 // ---- K4b/K4c in block form: the unit of the multi-GPU exchange -----------------------------------------------
 // A token block is 16 header bytes (u32 count, u32 flags, 8 spare) followed by `cap` records of `stride` bytes; the
 // last four bytes of a record hold its order key (read index of first appearance).  count may exceed cap: the block

@@ -99,6 +99,11 @@ const char* crass_b200_ctx_last_dr_list(const crass_b200_ctx* ctx);
 /* the *_dev entry points leave hit records in device slot order; this puts a host copy into read order (what the
  * host-buffer calls return and replay requires), in place */
 void crass_b200_sort_hits(crass_b200_hit* hits, uint32_t n_hits);
+/* the same on the device, before the copy: d_found are the flags the search launch wrote (16-byte aligned; exactly the
+ * reads with a non-zero flag have a hit record, at most one each), *d_n_hits the hit counter on the device (counters[0]),
+ * max_hits the capacity of d_sorted.  A hit's place in read order is the number of flagged reads before it. */
+int crass_b200_sort_hits_dev(crass_b200_ctx* ctx, const uint8_t* d_found, uint32_t n_reads, const crass_b200_hit* d_hits,
+                             const uint32_t* d_n_hits, uint32_t max_hits, crass_b200_hit* d_sorted, void* stream);
 /* K4b: de-duplicate the token records of d_hits[0..n_hits) on the device.  Writes the distinct records to d_out_tokens
  * (same stride), the smallest read index carrying each to d_out_first_read, and their number to d_out_count; all three
  * must hold n_hits entries in the worst case.  Order is arbitrary: sort by first_read for first-appearance order
