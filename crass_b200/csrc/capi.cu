@@ -95,6 +95,7 @@ struct crass_b200_ctx {
     bool res_valid = false, res_found_valid = false;
     DevBuf d_found_p1, d_cand, d_tokens, d_tok_table, d_tok_unique, d_ac_table, d_ac_symv, d_ac_bitmap, d_ac_keys;
     DevBuf d_ac_skeys, d_ac_shead, d_ac_pnext, d_ac_poffs, d_ac_pbytes;
+    DevBuf d_cand_counts;                // K1 fast path: sizes of the two candidate lists
     DevBuf d_rank, d_hits_sorted;        // crass_b200_sort_hits_dev: per-chunk prefix counts, read-ordered copy of the hits
     uint64_t ac_serial = 0;              // build serial of the automaton currently held in d_ac_*
     uint64_t ac_dfa_serial = 0;          // ... and of the dense DFA (generic K2 path), uploaded lazily
@@ -163,7 +164,7 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
     DevBuf* bufs[] = {&c->d_bases, &c->d_offsets, &c->d_found, &c->d_skip, &c->d_hits, &c->d_pool, &c->d_counters,
                       &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv, &c->d_found_p1, &c->d_cand, &c->d_tokens, &c->d_tok_table, &c->d_tok_unique, &c->d_ac_table, &c->d_ac_symv,
                       &c->d_ac_bitmap, &c->d_ac_keys, &c->d_ac_skeys, &c->d_ac_shead, &c->d_ac_pnext, &c->d_ac_poffs, &c->d_ac_pbytes,
-                      &c->d_rank, &c->d_hits_sorted};
+                      &c->d_rank, &c->d_hits_sorted, &c->d_cand_counts};
     for (DevBuf* b : bufs) b->release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     cudaStreamDestroy(c->stream);
@@ -327,8 +328,10 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
         if (!d_found) { if (int r = c->d_found.reserve((size_t)n_reads + 16)) return r; d_found = c->d_found.as<uint8_t>(); }
         if (int r = c->d_cand.reserve(((size_t)n_reads + 16) * sizeof(uint32_t))) return r;
         uint32_t* cand = c->d_cand.as<uint32_t>();
+        if (int r = c->d_cand_counts.reserve(4 * sizeof(uint32_t))) return r;     // [0] several flagged windows, [1] a single one
+        uint32_t* cand_counts = c->d_cand_counts.as<uint32_t>();
+        CUDA_TRY(cudaMemsetAsync(cand_counts, 0, 4 * sizeof(uint32_t), st));
         const uint32_t n_tiles = (n_reads + cbk::kFilterTile - 1) / cbk::kFilterTile;
-        const int fblocks = (int)std::min<uint32_t>(n_tiles, (uint32_t)c->sm_count * 16);
         const int se = (int)max_read_len - 58;
         const int nwin = se < 0 ? 1 : se / 16 + 1;
         const int eblocks = c->sm_count * 8;
@@ -340,8 +343,8 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
         int per_sm = 1;                                                                                                             \
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbk::k_dr_filter<NW, NWIN, 49, 97>, cbk::kFilterTile, fsmem)); \
         const int pblocks = (int)std::min<uint32_t>(n_tiles, (uint32_t)(c->sm_count * std::max(per_sm, 1)));    /* persistent: one wave */ \
-        cbk::k_dr_filter<NW, NWIN, 49, 97><<<pblocks, cbk::kFilterTile, fsmem, st>>>(d_bases, d_offsets, n_reads, d_found, cand, d_counters); \
-        cbk::k_dr_exact_packed<NW, NWIN, 49, 97><<<eblocks, cbk::kExactThreads, 0, st>>>(d_bases, d_offsets, n_reads, cand, o, d_found, sink, d_err); \
+        cbk::k_dr_filter<NW, NWIN, 49, 97><<<pblocks, cbk::kFilterTile, fsmem, st>>>(d_bases, d_offsets, n_reads, d_found, cand, cand_counts); \
+        cbk::k_dr_exact_packed<NW, NWIN, 49, 97><<<eblocks, cbk::kExactThreads, 0, st>>>(d_bases, d_offsets, n_reads, cand, cand_counts, o, d_found, sink, d_err); \
     } while (0)
         if (max_read_len <= 112) { if (nwin <= 3) CB_FAST(7, 3); else CB_FAST(7, 4); }
         else if (max_read_len <= 160) { if (nwin <= 6) CB_FAST(10, 6); else CB_FAST(10, 7); }

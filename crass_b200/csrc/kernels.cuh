@@ -390,7 +390,7 @@ constexpr size_t dr_filter_smem_bytes() { return (size_t)(kFilterTile * NW + NW 
 template <int NW, int NWIN, int DMIN, int DMAX>
 __global__ void __launch_bounds__(kFilterTile)
 k_dr_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads,
-            uint8_t* __restrict__ found, uint32_t* __restrict__ cand_list, uint32_t* __restrict__ counters) {
+            uint8_t* __restrict__ found, uint32_t* __restrict__ cand_list, uint32_t* __restrict__ cand_counts) {
     constexpr int kWords = kFilterTile * NW + NW + 8;          // packed words a tile can need (+ look-ahead + realignment)
     extern __shared__ __align__(128) uint8_t dyn_smem[];       // dr_filter_smem_bytes<NW>() bytes
     uint8_t* buf = dyn_smem;                                   // the tile's bytes, written by the bulk copy
@@ -423,7 +423,14 @@ k_dr_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs
             cb::seed_flags<NW, NWIN, DMIN, DMAX>(R, acc);
             const bool cand = cb::any_flag<NWIN>(acc);
             found[r] = 0;
-            if (cand) cand_list[atomicAdd(&counters[3], 1u)] = r;
+            if (cand) {
+                // Two lists in one array: reads with several flagged windows (nearly all reads that carry an array) fill it
+                // from the front, reads with a single flagged window (mostly chance 8-mer repeats) from the back.  The
+                // exact kernel never mixes the two in a warp, so the long stages run with full warps and the chance
+                // candidates are dismissed together.
+                if (__popc(cb::flag_mask<NWIN>(acc)) >= 2) cand_list[atomicAdd(&cand_counts[0], 1u)] = r;
+                else cand_list[n_reads - 1u - atomicAdd(&cand_counts[1], 1u)] = r;
+            }
         }
         __syncthreads();                                        // everyone is done with the packed tile
     }
@@ -438,20 +445,23 @@ constexpr int kExactThreads = 128;
 template <int NW, int NWIN, int DMIN, int DMAX>
 __global__ void __launch_bounds__(kExactThreads)
 k_dr_exact_packed(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads,
-                  const uint32_t* __restrict__ cand_list, Params o, uint8_t* __restrict__ found, HitSink sink,
-                  int* __restrict__ error_flag) {
+                  const uint32_t* __restrict__ cand_list, const uint32_t* __restrict__ cand_counts, Params o,
+                  uint8_t* __restrict__ found, HitSink sink, int* __restrict__ error_flag) {
     constexpr int kSlot = (NW + 4) | 1;                         // odd stride: conflict-free per-thread slots
     __shared__ uint32_t sm[kExactThreads * kSlot];
-    const uint32_t n_cand = sink.counters[3];
+    const uint32_t n_front = cand_counts[0], n_back = cand_counts[1];      // the two lists of k_dr_filter
+    if (blockIdx.x == 0 && threadIdx.x == 0) sink.counters[3] = n_front + n_back;
     const uint64_t n_bases = offsets[n_reads];
-    const uint32_t nthreads = gridDim.x * blockDim.x;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t tasks_front = (n_front + 31u) >> 5, tasks = tasks_front + ((n_back + 31u) >> 5);
     uint32_t* S = sm + threadIdx.x * kSlot;
     uint32_t ss[32];
-    // every warp takes 32 candidates at a time and walks the stages of cb::PackedSearch in lock-step
-    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n_cand; i0 += nthreads) {
-        const uint32_t i = i0 + (threadIdx.x & 31u);
-        const bool active = i < n_cand;
-        const uint32_t r = active ? cand_list[i] : 0u;
+    // every warp takes 32 candidates of one list at a time and walks the stages of cb::PackedSearch in lock-step
+    for (uint32_t task = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; task < tasks; task += n_warps) {
+        const bool front = task < tasks_front;
+        const uint32_t i = ((front ? task : task - tasks_front) << 5) + (threadIdx.x & 31u);
+        const bool active = i < (front ? n_front : n_back);
+        const uint32_t r = active ? cand_list[front ? i : n_reads - 1u - i] : 0u;
         const uint64_t b = active ? offsets[r] : 0ull;
         const uint32_t L = active ? (uint32_t)(offsets[r + 1] - b) : 0u;
         GmemSeq s{bases + b};
