@@ -351,6 +351,7 @@ int crass_b200_ac_build_from_dr_list(const char* dr_list, uint32_t kmer_clust, c
 #endif
     std::vector<std::string_view> lines;                                        // views into the caller's text
     const std::string_view all(dr_list);
+    lines.reserve(all.size() / 24 + 16);
     for (size_t p = 0; p < all.size();) {
         size_t e = all.find('\n', p);
         if (e == std::string_view::npos) e = all.size();

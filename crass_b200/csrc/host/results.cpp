@@ -252,15 +252,21 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& 
     // the work arrays are kept across calls (fresh multi-megabyte vectors cost more in page faults than the clustering
     // itself); of the hash table only the slots this call touches are reset on the way out, so that untouched slots
     // always hold (empty, INT_MAX)
-    static thread_local std::vector<uint32_t> tkey_store, keys_store, first_store;
-    static thread_local std::vector<int> tval_store;
-    if (tkey_store.size() < tsize) { tkey_store.assign(tsize, kStrKey); tval_store.assign(tsize, INT_MAX); }
-    if (keys_store.size() < total_kmers) { keys_store.resize(total_kmers + total_kmers / 4); first_store.resize(keys_store.size()); }
+    struct Slot { uint32_t key; int val; };             // key and value share a cache line: one miss per probe
+    static thread_local std::vector<Slot> table_store;
+    static thread_local std::vector<uint32_t> keys_store, first_store, runc_store;
+    if (table_store.size() < tsize) table_store.assign(tsize, Slot{kStrKey, INT_MAX});
+    if (keys_store.size() < total_kmers) {
+        keys_store.resize(total_kmers + total_kmers / 4);
+        first_store.resize(keys_store.size());
+        runc_store.resize(keys_store.size());
+    }
     uint32_t* const keys = keys_store.data();                              // pass A: canonical key per k-mer
-    uint32_t* const first = first_store.data();                            // pass B: first DR (token order) holding it
-    tsize = tkey_store.size();
-    uint32_t* const tkey = tkey_store.data();           // plain pointers: TLS lookups are not free inside a shared object
-    int* const tval = tval_store.data();
+    uint32_t* const first = first_store.data();                            // pass B: first DR (token order) holding it; B2: runs
+    uint32_t* const runc = runc_store.data();                              // pass B2: length of each run
+    std::vector<uint32_t> n_runs(n_dr, 0);
+    tsize = table_store.size();
+    Slot* const table = table_store.data();             // plain pointers: TLS lookups are not free inside a shared object
 
     unsigned n_workers = 1;
     if (total_kmers > (1u << 15)) n_workers = std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency()));
@@ -273,10 +279,11 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& 
     }
     std::vector<std::vector<size_t> > touched_by(n_workers);               // per worker: the table slots it claimed
     struct Reset {
-        uint32_t* k; int* v; std::vector<std::vector<size_t> >& t;
-        ~Reset() { for (auto& l : t) for (size_t s : l) { k[s] = kStrKey; v[s] = INT_MAX; } }
-    } reset_on_exit{tkey, tval, touched_by};
+        Slot* tab; std::vector<std::vector<size_t> >& t;
+        ~Reset() { for (auto& l : t) for (size_t s : l) tab[s] = Slot{kStrKey, INT_MAX}; }
+    } reset_on_exit{table, touched_by};
     std::atomic<bool> any_str{false};
+    std::vector<std::vector<std::pair<uint32_t, uint32_t> > > str_pos(n_workers);   // per worker: (DR, k-mer) that go through the string map
     std::vector<std::vector<int> > members;                               // group id - 1 -> tokens
     std::vector<std::vector<std::string> > survivors, survivors_rc;
     std::vector<size_t> schedule;                                          // groups, largest first
@@ -286,7 +293,7 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& 
 
     // pass A (no dependencies, streams through the strings): canonical integer key of every k-mer, kStrKey for the
     // rare k-mers that need the string map
-    auto pass_a = [&](size_t t_begin, size_t t_end) {
+    auto pass_a = [&](unsigned worker, size_t t_begin, size_t t_end) {
         const uint32_t kmask = (1u << (2 * kClusterKmer)) - 1u;
         for (size_t t = t_begin; t < t_end; ++t) {
             const std::string_view dr = drs[t];
@@ -306,7 +313,7 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& 
                     for (char ch : km) { const int c2 = kCode[(uint8_t)ch]; if (c2 < 0) { acgt = false; break; } k2 = (k2 << 2) | (uint32_t)c2; }
                     if (acgt) key = k2;
                 }
-                if (key == kStrKey) any_str.store(true, std::memory_order_relaxed);
+                if (key == kStrKey) { any_str.store(true, std::memory_order_relaxed); str_pos[worker].push_back(std::make_pair((uint32_t)t, (uint32_t)w)); }
                 keys[w++] = key;
             }
         }
@@ -324,49 +331,67 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& 
         for (size_t q = koff[t_begin]; q < q_end; ++q) {
             if (q + kAhead < q_end && keys[q + kAhead] != kStrKey) {
                 const size_t s = (size_t)(keys[q + kAhead] * 0x9E3779B1u) & (tsize - 1);
-                __builtin_prefetch(&tkey[s]); __builtin_prefetch(&tval[s]);
+                __builtin_prefetch(&table[s]);
             }
             while (q >= koff[t + 1]) ++t;
             const uint32_t key = keys[q];
             if (key == kStrKey) continue;
             size_t s = (size_t)(key * 0x9E3779B1u) & (tsize - 1);
             for (;;) {
-                uint32_t cur = __atomic_load_n(&tkey[s], __ATOMIC_RELAXED);
+                uint32_t cur = __atomic_load_n(&table[s].key, __ATOMIC_RELAXED);
                 if (cur == key) break;
                 if (cur == kStrKey) {
-                    if (__atomic_compare_exchange_n(&tkey[s], &cur, key, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { touched_by[w].push_back(s); break; }
+                    if (__atomic_compare_exchange_n(&table[s].key, &cur, key, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { touched_by[w].push_back(s); break; }
                     if (cur == key) break;
                 }
                 s = (s + 1) & (tsize - 1);
             }
-            int seen = __atomic_load_n(&tval[s], __ATOMIC_RELAXED);
-            while ((int)t < seen && !__atomic_compare_exchange_n(&tval[s], &seen, (int)t, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+            int seen = __atomic_load_n(&table[s].val, __ATOMIC_RELAXED);
+            while ((int)t < seen && !__atomic_compare_exchange_n(&table[s].val, &seen, (int)t, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
             first[q] = (uint32_t)s;
         }
     };
-    auto pass_b2 = [&](size_t t_begin, size_t t_end) {
-        for (size_t q = koff[t_begin]; q < koff[t_end]; ++q)
-            if (keys[q] != kStrKey) first[q] = (uint32_t)tval[first[q]];
+    // the rare k-mers with other letters go through a string map, on one thread between B and B2
+    auto resolve_str = [&]() {
+        std::unordered_map<std::string, int> kmer_first_str;
+        for (const auto& list : str_pos)                                  // worker ranges are in DR order
+            for (const auto& tq : list)
+                first[tq.second] = (uint32_t)kmer_first_str.emplace(low_lexi_kmer(drs[tq.first], tq.second - koff[tq.first]), (int)tq.first).first->second;
     };
-    // pass C (one thread): the order-dependent greedy walk, on small sequential arrays only
-    auto pass_c = [&]() {
-        if (any_str.load()) {                                             // the rare k-mers with other letters
-            std::unordered_map<std::string, int> kmer_first_str;
-            for (size_t t = 0; t < n_dr; ++t)
-                for (size_t q = koff[t]; q < koff[t + 1]; ++q)
-                    if (keys[q] == kStrKey) first[q] = (uint32_t)kmer_first_str.emplace(low_lexi_kmer(drs[t], q - koff[t]), (int)t).first->second;
+    // pass B2: slot -> first DR, and in the same sweep the k-mers of every DR are folded into runs (first DR f, length):
+    // consecutive already-seen k-mers that were first seen in the same DR.  K-mers new to the DR (first >= t) change no
+    // tally in the walk below, so runs reach across them.  The runs overwrite first[] in place.
+    auto pass_b2 = [&](size_t t_begin, size_t t_end) {
+        const size_t kAhead = 24, q_end = koff[t_end];
+        for (size_t t = t_begin; t < t_end; ++t) {
+            size_t out = koff[t];
+            for (size_t q = koff[t]; q < koff[t + 1]; ++q) {
+                if (q + kAhead < q_end && keys[q + kAhead] != kStrKey) __builtin_prefetch(&table[first[q + kAhead]]);
+                const uint32_t f = keys[q] != kStrKey ? (uint32_t)table[first[q]].val : first[q];
+                if (f >= t) continue;                                    // never seen before this DR
+                if (out > koff[t] && first[out - 1] == f) runc[out - 1]++;
+                else { first[out] = f; runc[out] = 1; ++out; }
+            }
+            n_runs[t] = (uint32_t)(out - koff[t]);
         }
+    };
+    // pass C (one thread): the order-dependent greedy walk over the runs.  The reference bumps a group's tally once per
+    // shared k-mer and tests it against min_count from the group's second hit on; a run of c k-mers of one group
+    // therefore wins as soon as the tally it leaves behind is >= min_count (and >= 2 if it opened the tally).
+    auto pass_c = [&]() {
         std::vector<int> group_of(n_dr, 0);
         std::vector<std::pair<int, int> > counts;                         // (group, shared so far)
         for (size_t t = 0; t < n_dr; ++t) {
             counts.clear();
             int group = 0;
-            for (size_t q = koff[t]; q < koff[t + 1] && !group; ++q) {
-                if (first[q] >= t) continue;                             // never seen before this DR
-                const int known = group_of[first[q]];
+            for (size_t j = koff[t], je = koff[t] + n_runs[t]; j < je && !group; ++j) {
+                const int known = group_of[first[j]];
+                const int c = (int)runc[j];
                 auto c2 = std::find_if(counts.begin(), counts.end(), [&](const std::pair<int, int>& p) { return p.first == known; });
-                if (c2 == counts.end()) counts.push_back(std::make_pair(known, 1));
-                else if (++c2->second >= min_count) group = known;
+                if (c2 == counts.end()) {
+                    counts.push_back(std::make_pair(known, c));
+                    if (c >= 2 && c >= min_count) group = known;
+                } else if ((c2->second += c) >= min_count) group = known;
             }
             if (!group) { members.emplace_back(); group = (int)members.size(); }
             group_of[t] = group;
@@ -483,13 +508,17 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& 
         }
     };
     auto worker = [&](unsigned w) {
-        pass_a(cut[w], cut[w + 1]);
+        pass_a(w, cut[w], cut[w + 1]);
         pass_b(w, cut[w], cut[w + 1]);
         barrier.wait();
         if (w == 0) CB_NR_MARK("pass A+B");
+        if (any_str.load()) {
+            if (w == 0) resolve_str();
+            barrier.wait();
+        }
         pass_b2(cut[w], cut[w + 1]);
         barrier.wait();
-        if (w == 0) { pass_c(); CB_NR_MARK("pass B2+C"); }
+        if (w == 0) { CB_NR_MARK("pass B2"); pass_c(); CB_NR_MARK("pass C"); }
         barrier.wait();
         HeadTable map, full;
         for (size_t i; (i = next_group.fetch_add(1)) < schedule.size();) reduce_group(schedule[i], map, full);
