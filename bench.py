@@ -204,9 +204,15 @@ def main():
     torch.cuda.synchronize()
     np_bases, np_offsets = h_bases.numpy(), h_offsets.numpy().view(np.uint64)
 
-    # the host passes between the kernels use a few helper threads per rank: share the box's cores between the ranks
+    # The host passes between the kernels use helper threads.  At N > 1 the clustering runs once, on rank 0
+    # (crass_b200/dist.py::PatternExchange), so rank 0 gets the cores the other ranks do not need.
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    os.environ.setdefault("CRASS_B200_HOST_THREADS", str(max(1, min(8, (os.cpu_count() or 8) // max(local_world, 1)))))
+    cores = os.cpu_count() or 8
+    if world == 1:
+        host_threads = min(8, cores)
+    else:
+        host_threads = max(2, min(16, cores - 2 * local_world)) if rank == 0 else 2
+    os.environ.setdefault("CRASS_B200_HOST_THREADS", str(host_threads))
     ctx = cb.Context(local_rank)
     params = cb.Params()
     work_stream = torch.cuda.Stream(device=dev)          # a real (non-NULL) stream: kernels, copies and events all go here
@@ -228,7 +234,10 @@ def main():
     d_tokens = torch.empty(hits_cap * TOK, dtype=torch.uint8, device=dev)
     host_ms = {k: [] for k in ("fetch", "merge", "cluster_build", "ac_upload", "k2_wait", "fetch_hits2")}
 
-    exchange = cbdist.TokenExchange(ctx, dev, shard_reads=n, stride=TOK)   # K4b (+ all-gather + K4c at N > 1)
+    if world == 1:
+        exchange = cbdist.TokenExchange(ctx, dev, shard_reads=n, stride=TOK)                     # K4b -> DR list
+    else:
+        exchange = cbdist.PatternExchange(ctx, dev, shard_reads=n, kmer_clust=params.kmer_clust, stride=TOK)   # + all-gather, K4c, broadcast
     h_hits = [torch.empty(hits_cap * 4, dtype=torch.int32, pin_memory=True) for _ in range(2)]
     h_pool = [torch.empty(pool_cap, dtype=torch.int32, pin_memory=True) for _ in range(2)]
 
@@ -263,12 +272,15 @@ def main():
         t1 = time.perf_counter()
         # distinct low-lexi DRs of all shards in first-appearance order (crass_b200/dist.py): K4b de-duplicates this
         # shard's tokens on the device, one NCCL all-gather + K4c merge the shards, one copy brings the list back
-        merged, nu = exchange.run(d_hits, nh, d_tokens, stream)
+        merged, nu = exchange.run(d_hits, nh, d_tokens, stream)       # N == 1: the DR list; N > 1: the pattern set from rank 0
         fetch_hits_async(0, nh, npool)                                 # the phase-1 hit records travel while the host clusters
         t3 = time.perf_counter()
-        if args.dump_dr_list and rank == 0 and not record:
+        if args.dump_dr_list and rank == 0 and not record and world == 1:
             open(args.dump_dr_list, "wb").write(merged)
-        ac = cb.Automaton.from_dr_list(merged, params.kmer_clust) if merged else None   # createNonRedundantSet + matcher
+        if world == 1:
+            ac = cb.Automaton.from_dr_list(merged, params.kmer_clust) if merged else None   # createNonRedundantSet + matcher
+        else:
+            ac = cb.Automaton.from_pattern_text(merged) if merged else None
         pats = ac.num_patterns if ac else 0
         t4 = time.perf_counter()
         n2 = 0

@@ -122,6 +122,8 @@ def lib():
         "crass_b200_dr_list_from_block": (vp, [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         "crass_b200_non_redundant_set": (vp, [cp, C.c_uint32]),
         "crass_b200_ac_build_from_dr_list": (C.c_int, [cp, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_uint32)]),
+        "crass_b200_non_redundant_patterns": (vp, [cp, C.c_uint32, C.POINTER(C.c_uint32)]),
+        "crass_b200_ac_build_from_pattern_list": (C.c_int, [cp, C.POINTER(vp), C.POINTER(C.c_uint32)]),
         "crass_b200_run_files": (C.c_int, [vp, C.POINTER(cp), C.c_uint32, C.POINTER(Params), C.c_int, C.POINTER(vp), C.POINTER(C.c_int)]),
         "crass_b200_free": (None, [vp]),
     }
@@ -267,6 +269,16 @@ class Automaton:
         self.num_patterns = n.value
         return self
 
+    @classmethod
+    def from_pattern_text(cls, text):
+        """Matcher from a '\\n'-separated pattern set (what non_redundant_patterns returns)."""
+        self = cls.__new__(cls)
+        self.h = C.c_void_p()
+        n = C.c_uint32(0)
+        _check(lib().crass_b200_ac_build_from_pattern_list(bytes(text), C.byref(self.h), C.byref(n)))
+        self.num_patterns = n.value
+        return self
+
     def __del__(self):
         if getattr(self, "h", None):
             lib().crass_b200_ac_destroy(self.h)
@@ -376,6 +388,15 @@ def merge_dr_lists(drs):
         return _take_str(lib().crass_b200_merge_dr_lists(bytes(drs)))
     s = _take_str(lib().crass_b200_merge_dr_lists(b"".join(d + b"\n" for d in drs)))
     return [x for x in s.split(b"\n") if x]
+
+
+def non_redundant_patterns(dr_text, kmer_clust=6):
+    """createNonRedundantSet on a '\\n'-terminated DR list in token order -> '\\n'-terminated pattern text."""
+    n = C.c_uint32(0)
+    s = _take_str(lib().crass_b200_non_redundant_patterns(bytes(dr_text), kmer_clust, C.byref(n)))
+    if s is None:
+        _check(-1)
+    return s
 
 
 def non_redundant_list(drs, kmer_clust=6):

@@ -379,6 +379,42 @@ int crass_b200_ac_build_from_dr_list(const char* dr_list, uint32_t kmer_clust, c
     return crass_b200_ac_build(bytes.data(), offs.data(), (uint32_t)nr.size(), out);
 }
 
+char* crass_b200_non_redundant_patterns(const char* dr_list, uint32_t kmer_clust, uint32_t* n_patterns) {
+    if (!dr_list) { fail(CRASS_B200_EINVAL, "NULL argument"); return nullptr; }
+    std::vector<std::string_view> lines;
+    const std::string_view all(dr_list);
+    lines.reserve(all.size() / 24 + 16);
+    for (size_t p = 0; p < all.size();) {
+        size_t e = all.find('\n', p);
+        if (e == std::string_view::npos) e = all.size();
+        if (e > p) lines.push_back(all.substr(p, e - p));
+        p = e + 1;
+    }
+    const std::vector<std::string> nr = non_redundant_set(lines, (int)kmer_clust, nullptr);
+    if (n_patterns) *n_patterns = (uint32_t)nr.size();
+    std::string out;
+    out.reserve(all.size());
+    for (const std::string& p : nr) { out += p; out += '\n'; }
+    return dup_cstr(out);
+}
+
+int crass_b200_ac_build_from_pattern_list(const char* patterns, crass_b200_ac** out, uint32_t* n_patterns) {
+    if (!patterns || !out) return fail(CRASS_B200_EINVAL, "NULL argument");
+    const std::string_view all(patterns);
+    std::vector<uint8_t> bytes;
+    std::vector<uint32_t> offs(1, 0);
+    bytes.reserve(all.size() + 1);
+    for (size_t p = 0; p < all.size();) {
+        size_t e = all.find('\n', p);
+        if (e == std::string_view::npos) e = all.size();
+        if (e > p) { bytes.insert(bytes.end(), all.begin() + p, all.begin() + e); offs.push_back((uint32_t)bytes.size()); }
+        p = e + 1;
+    }
+    if (n_patterns) *n_patterns = (uint32_t)offs.size() - 1;
+    if (bytes.empty()) bytes.push_back(0);
+    return crass_b200_ac_build(bytes.data(), offs.data(), (uint32_t)offs.size() - 1, out);
+}
+
 // ---- the whole path -------------------------------------------------------------------------------------------
 int crass_b200_run_files(crass_b200_ctx* ctx, const char* const* paths, uint32_t n_paths, const crass_b200_params* params,
                          int phases, crass_b200_results** out, int* max_read_len) {

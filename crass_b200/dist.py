@@ -57,6 +57,79 @@ class TokenExchange:
             return text, count
 
 
+class PatternExchange(TokenExchange):
+    """The step between the phases for N > 1 with the serial part done once.
+
+    createNonRedundantSet is a serial section of the job: running the identical clustering on every rank does not make
+    it faster, it only divides the box's cores between N copies.  Here the token blocks are gathered as in
+    TokenExchange, but only the root merges them (K4c), brings the DR list to its host and clusters it with all the
+    helper threads it is given; the resulting pattern set (a few hundred KB of text) goes back to every GPU with one
+    NCCL broadcast of a fixed-size message [u32 status, u32 n_variants, u64 text_len | text], and every rank builds its
+    matcher from it.  Status 1 / 2 tell all ranks alike to repeat the round with larger token blocks / a larger message.
+    """
+
+    HEADER = 16
+
+    def __init__(self, ctx, device, shard_reads, kmer_clust=6, stride=64, cap=16384, text_cap=1 << 18, root=0, group=None):
+        super().__init__(ctx, device, shard_reads, stride, cap, group)
+        self.kmer_clust, self.root = kmer_clust, root
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self._alloc_msg(text_cap)
+
+    def _alloc_msg(self, text_cap):
+        self.text_cap = text_cap
+        self.msg = torch.zeros(self.HEADER + text_cap, dtype=torch.uint8, device=self.dev)
+        self.msg_host = torch.zeros(self.HEADER + text_cap, dtype=torch.uint8, pin_memory=True)
+
+    def run(self, d_hits, n_hits, d_tokens, stream=0):
+        """-> (pattern set as '\\n'-terminated text, number of distinct DR variants over all ranks)"""
+        if self.world == 1:
+            text, count = super().run(d_hits, n_hits, d_tokens, stream)
+            return (api.non_redundant_patterns(text, self.kmer_clust) if text else b""), count
+        import numpy as np
+        while True:
+            self.ctx.unique_tokens_block_dev(d_hits, n_hits, d_tokens, self.stride, self.send, self.cap, stream)
+            dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+            hdr = self.msg_host[: self.HEADER].numpy()
+            if self.rank == self.root:
+                self.ctx.merge_token_blocks_dev(self.recv, self.world, self.cap, self.stride, self.shard_reads, self.merged, self.out_cap, stream)
+                self.host.copy_(self.merged, non_blocking=True)
+                torch.cuda.current_stream(self.dev).synchronize()
+                drs, count, flags = api.dr_list_from_block(self.host, self.out_cap, self.stride)
+                if flags & 2:
+                    raise api.CrassB200Error(api.EINVAL, "token stride too small for the DR lengths in use")
+                status, text = 0, b""
+                if (flags & 1) or count > self.out_cap:
+                    status = 1
+                else:
+                    text = api.non_redundant_patterns(drs, self.kmer_clust) if drs else b""
+                    if len(text) > self.text_cap:
+                        status = 2
+                hdr.view(np.uint32)[0:2] = (status, min(count, 0xFFFFFFFF))
+                hdr.view(np.uint64)[1] = len(text)
+                n_send = self.HEADER
+                if status == 0 and text:
+                    self.msg_host[self.HEADER: self.HEADER + len(text)] = torch.frombuffer(bytearray(text), dtype=torch.uint8)
+                    n_send += len(text)
+                self.msg[:n_send].copy_(self.msg_host[:n_send], non_blocking=True)
+            dist.broadcast(self.msg, src=self.root, group=self.group)
+            if self.rank != self.root:
+                self.msg_host.copy_(self.msg, non_blocking=True)
+                torch.cuda.current_stream(self.dev).synchronize()
+            status, count = (int(x) for x in hdr.view(np.uint32)[0:2])
+            text_len = int(hdr.view(np.uint64)[1])
+            if status == 1:
+                self._alloc(self.cap * 2)
+                continue
+            if status == 2:
+                cap = self.text_cap
+                while cap < text_len:
+                    cap *= 2
+                self._alloc_msg(cap)
+                continue
+            return self.msg_host[self.HEADER: self.HEADER + text_len].numpy().tobytes(), count
+
+
 def allgather_unique_tokens(records, first_read, n_unique, stride=64, group=None):
     """The same exchange, fed straight from the device de-duplication (K4b) without a host round trip per rank.
 

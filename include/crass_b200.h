@@ -254,6 +254,11 @@ char* crass_b200_non_redundant_set(const char* dr_list, uint32_t kmer_clust);
  * WorkHorse.cpp:367-379 takes between the phases (createNonRedundantSet, then findSingletons builds its matcher,
  * libcrispr.cpp:455-470).  *n_patterns (optional) = size of the non-redundant set; an empty set is EINVAL. */
 int crass_b200_ac_build_from_dr_list(const char* dr_list, uint32_t kmer_clust, crass_b200_ac** out, uint32_t* n_patterns);
+/* the two halves separately, for drivers that cluster on one rank and hand the pattern set to the others: the
+ * non-redundant set as '\n'-separated text in the reference's order (per group: survivors, then their reverse
+ * complements; malloc'd), and the matcher built from such a text */
+char* crass_b200_non_redundant_patterns(const char* dr_list, uint32_t kmer_clust, uint32_t* n_patterns);
+int crass_b200_ac_build_from_pattern_list(const char* patterns, crass_b200_ac** out, uint32_t* n_patterns);
 
 /* ---- whole path, one call: searchFile* -> createNonRedundantSet -> findSingletons* --------------- */
 int crass_b200_run_files(crass_b200_ctx* ctx, const char* const* paths, uint32_t n_paths,

@@ -144,6 +144,19 @@ def test_non_redundant_set_long_list_worker_threads():
         assert sorted(l for l in a.split("\n") if l.startswith("P")) == sorted(l for l in b.split("\n") if l.startswith("P"))
 
 
+def test_pattern_text_round_trip():
+    """The two halves of ac_build_from_dr_list used by the root-clusters-for-all exchange."""
+    rng = random.Random(37)
+    base = [fuzzgen.rand_seq(rng, rng.randint(23, 47)) for _k in range(30)]
+    drs = list(dict.fromkeys(fuzzgen.mutate(rng, b, rng.choice([0, 0.03]), b"ACGTN") for b in base for _k in range(6)))
+    text = b"".join(d + b"\n" for d in drs)
+    pats = api.non_redundant_patterns(text, 6)
+    assert pats.split(b"\n")[:-1] == api.non_redundant_list(drs, 6)             # same set, same order
+    a, b = cb.Automaton.from_pattern_text(pats), cb.Automaton.from_dr_list(text, 6)
+    assert a.num_patterns == b.num_patterns == pats.count(b"\n")
+    assert api.non_redundant_patterns(b"", 6) == b""
+
+
 def test_sort_hits_puts_device_order_into_read_order():
     rng = np.random.default_rng(31)
     for n, top in ((0, 10), (1, 10), (300, 5000), (2000, 2**11), (5000, 2**22 + 5), (70000, 10_000_000), (40000, 2**32 - 1)):
