@@ -232,7 +232,10 @@ def main():
 
     TOK = 64                                                           # bytes per K4 token record (>= high_dr + 2)
     d_tokens = torch.empty(hits_cap * TOK, dtype=torch.uint8, device=dev)
-    host_ms = {k: [] for k in ("fetch", "merge", "cluster_build", "ac_upload", "k2_wait", "fetch_hits2")}
+    # host time line of a step: wait for K1 | token exchange + clustering (N == 1: + matcher build) | matcher build from the
+    # broadcast pattern set (N > 1) | matcher upload | wait for K2 + ordering | last copy
+    HOST_KEYS = ("k1_wait", "exchange_cluster", "matcher_build", "ac_upload", "k2_wait", "fetch_hits2")
+    host_ms = {k: [] for k in HOST_KEYS}
 
     if world == 1:
         exchange = cbdist.TokenExchange(ctx, dev, shard_reads=n, stride=TOK)                     # K4b -> DR list
@@ -272,17 +275,19 @@ def main():
         t1 = time.perf_counter()
         # distinct low-lexi DRs of all shards in first-appearance order (crass_b200/dist.py): K4b de-duplicates this
         # shard's tokens on the device, one NCCL all-gather + K4c merge the shards, one copy brings the list back
-        merged, nu = exchange.run(d_hits, nh, d_tokens, stream)       # N == 1: the DR list; N > 1: the pattern set from rank 0
         fetch_hits_async(0, nh, npool)                                 # the phase-1 hit records travel while the host clusters
-        t3 = time.perf_counter()
-        if args.dump_dr_list and rank == 0 and not record and world == 1:
-            open(args.dump_dr_list, "wb").write(merged)
         if world == 1:
-            ac = cb.Automaton.from_dr_list(merged, params.kmer_clust) if merged else None   # createNonRedundantSet + matcher
+            # K4b block -> host -> createNonRedundantSet + matcher, straight from the block
+            if args.dump_dr_list and not record:
+                open(args.dump_dr_list, "wb").write(exchange.run(d_hits, nh, d_tokens, stream)[0])
+            ac, nu = exchange.run_matcher(d_hits, nh, d_tokens, params.kmer_clust, stream)
+            t3 = t4 = time.perf_counter()
         else:
-            ac = cb.Automaton.from_pattern_text(merged) if merged else None
+            pat_text, nu = exchange.run(d_hits, nh, d_tokens, stream)  # the pattern set, clustered once on rank 0
+            t3 = time.perf_counter()
+            ac = cb.Automaton.from_pattern_text(pat_text) if pat_text else None
+            t4 = time.perf_counter()
         pats = ac.num_patterns if ac else 0
-        t4 = time.perf_counter()
         n2 = 0
         if pats:
             ctx.ac_upload(ac)
@@ -301,9 +306,11 @@ def main():
             kt["k1"].append(e[0].elapsed_time(e[1]))
             if pats:
                 kt["k2"].append(e[2].elapsed_time(e[3]))
-                for k, v in zip(("fetch", "merge", "cluster_build", "ac_upload", "k2_wait", "fetch_hits2"),
+                for k, v in zip(HOST_KEYS,
                                 (t1 - t0, t3 - t1, t4 - t3, t5 - t4, t6 - t5, t7 - t6)):
                     host_ms[k].append(v * 1e3)
+                for k, v in getattr(exchange, "last_ms", {}).items():                   # rank 0's share of the N > 1 exchange
+                    host_ms.setdefault("root_" + k, []).append(v)
         stats.update(hits_phase1=len(hits), dr_variants_merged=nu, patterns=pats, hits_phase2=n2)
 
     def step_e2e():

@@ -123,6 +123,8 @@ def lib():
         "crass_b200_non_redundant_set": (vp, [cp, C.c_uint32]),
         "crass_b200_ac_build_from_dr_list": (C.c_int, [cp, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_uint32)]),
         "crass_b200_non_redundant_patterns": (vp, [cp, C.c_uint32, C.POINTER(C.c_uint32)]),
+        "crass_b200_non_redundant_patterns_from_block": (vp, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+        "crass_b200_ac_build_from_block": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         "crass_b200_ac_build_from_pattern_list": (C.c_int, [cp, C.POINTER(vp), C.POINTER(C.c_uint32)]),
         "crass_b200_run_files": (C.c_int, [vp, C.POINTER(cp), C.c_uint32, C.POINTER(Params), C.c_int, C.POINTER(vp), C.POINTER(C.c_int)]),
         "crass_b200_free": (None, [vp]),
@@ -270,6 +272,16 @@ class Automaton:
         return self
 
     @classmethod
+    def from_block(cls, block, cap, stride, kmer_clust=6):
+        """createNonRedundantSet + matcher straight from a host copy of a token block -> (matcher or None, count, flags)."""
+        self = cls.__new__(cls)
+        self.h = C.c_void_p()
+        n, cnt, fl = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        _check(lib().crass_b200_ac_build_from_block(C.c_void_p(_addr(block)), cap, stride, kmer_clust, C.byref(self.h), C.byref(cnt), C.byref(fl), C.byref(n)))
+        self.num_patterns = n.value
+        return (self if self.h else None), cnt.value, fl.value
+
+    @classmethod
     def from_pattern_text(cls, text):
         """Matcher from a '\\n'-separated pattern set (what non_redundant_patterns returns)."""
         self = cls.__new__(cls)
@@ -397,6 +409,15 @@ def non_redundant_patterns(dr_text, kmer_clust=6):
     if s is None:
         _check(-1)
     return s
+
+
+def non_redundant_patterns_from_block(block, cap, stride, kmer_clust=6):
+    """Host copy of a token block -> (pattern text, count, flags) without the intermediate DR text."""
+    n, cnt, fl = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+    s = _take_str(lib().crass_b200_non_redundant_patterns_from_block(C.c_void_p(_addr(block)), cap, stride, kmer_clust, C.byref(cnt), C.byref(fl), C.byref(n)))
+    if s is None:
+        _check(-1)
+    return s, cnt.value, fl.value
 
 
 def non_redundant_list(drs, kmer_clust=6):

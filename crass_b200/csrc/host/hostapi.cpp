@@ -287,8 +287,10 @@ char* crass_b200_dr_list_from_unique(const uint8_t* records, uint32_t stride, co
     return dup_cstr(out);
 }
 
-char* crass_b200_dr_list_from_block(const void* block, uint32_t cap, uint32_t stride, uint32_t* count, uint32_t* flags) {
-    if (!block || stride < 12) { fail(CRASS_B200_EINVAL, "bad token block"); return nullptr; }
+}  // extern "C"
+
+// the DR tokens of a host copy of a token block, as views into it, in order-key (first-appearance) order
+static std::vector<std::string_view> block_views(const void* block, uint32_t cap, uint32_t stride, uint32_t* count, uint32_t* flags) {
     const uint8_t* p = (const uint8_t*)block;
     uint32_t hdr[2];
     memcpy(hdr, p, sizeof hdr);
@@ -303,16 +305,52 @@ char* crass_b200_dr_list_from_block(const void* block, uint32_t cap, uint32_t st
         order[i] = ((uint64_t)key << 32) | i;
     }
     std::sort(order.begin(), order.end());
-    std::string out;
-    out.reserve((size_t)n * 40);
+    std::vector<std::string_view> v;
+    v.reserve(n);
     for (uint32_t i = 0; i < n; ++i) {
         const uint8_t* rec = recs + (size_t)(uint32_t)order[i] * stride;
         const uint32_t ln = rec[0] + 6u <= stride ? rec[0] : stride - 6;
-        if (!ln) continue;
-        out.append((const char*)rec + 2, ln);
-        out += '\n';
+        if (ln) v.push_back(std::string_view((const char*)rec + 2, ln));
     }
+    return v;
+}
+
+extern "C" {
+
+char* crass_b200_dr_list_from_block(const void* block, uint32_t cap, uint32_t stride, uint32_t* count, uint32_t* flags) {
+    if (!block || stride < 12) { fail(CRASS_B200_EINVAL, "bad token block"); return nullptr; }
+    std::string out;
+    for (const std::string_view& d : block_views(block, cap, stride, count, flags)) { out.append(d); out += '\n'; }
     return dup_cstr(out);
+}
+
+char* crass_b200_non_redundant_patterns_from_block(const void* block, uint32_t cap, uint32_t stride, uint32_t kmer_clust,
+                                                   uint32_t* count, uint32_t* flags, uint32_t* n_patterns) {
+    if (!block || stride < 12) { fail(CRASS_B200_EINVAL, "bad token block"); return nullptr; }
+    const std::vector<std::string> nr = non_redundant_set(block_views(block, cap, stride, count, flags), (int)kmer_clust, nullptr);
+    if (n_patterns) *n_patterns = (uint32_t)nr.size();
+    std::string out;
+    for (const std::string& p : nr) { out += p; out += '\n'; }
+    return dup_cstr(out);
+}
+
+int crass_b200_ac_build_from_block(const void* block, uint32_t cap, uint32_t stride, uint32_t kmer_clust, crass_b200_ac** out,
+                                   uint32_t* count, uint32_t* flags, uint32_t* n_patterns) {
+    if (!block || stride < 12 || !out) return fail(CRASS_B200_EINVAL, "bad token block");
+    *out = nullptr;
+    uint32_t c = 0, f = 0;
+    const std::vector<std::string_view> drs = block_views(block, cap, stride, &c, &f);
+    if (count) *count = c;
+    if (flags) *flags = f;
+    if (n_patterns) *n_patterns = 0;
+    if (f || c > cap || drs.empty()) return 0;                                  // overflowed or empty: no matcher, the caller looks at count/flags
+    const std::vector<std::string> nr = non_redundant_set(drs, (int)kmer_clust, nullptr);
+    if (n_patterns) *n_patterns = (uint32_t)nr.size();
+    std::vector<uint8_t> bytes;
+    std::vector<uint32_t> offs(1, 0);
+    for (const std::string& p : nr) { bytes.insert(bytes.end(), p.begin(), p.end()); offs.push_back((uint32_t)bytes.size()); }
+    if (bytes.empty()) return 0;
+    return crass_b200_ac_build(bytes.data(), offs.data(), (uint32_t)nr.size(), out);
 }
 
 char* crass_b200_merge_dr_lists(const char* concatenated) {

@@ -1,11 +1,14 @@
 """The one exchange step of the multi-GPU path: merging the per-shard direct-repeat sets.
 
-Reads are sharded contiguously, one process per GPU.  After phase 1 every rank holds the ordered list of the
-distinct low-lexi DR strings of its shard (first-appearance order).  One all-gather of the sizes and one of the
-padded byte records (NCCL over NVLink on GPUs, gloo in the CPU tests) give every rank all lists; concatenating them in
-rank order and keeping first occurrences reproduces exactly the token order a single sequential run would have
-produced (StringCheck numbers tokens by first appearance, StringCheck.cpp:46-55), so clustering, the non-redundant
-pattern set and the automaton come out identical on every rank without any further communication.
+Reads are sharded contiguously, one process per GPU.  After phase 1 every rank holds the distinct low-lexi DR tokens
+of its shard with the read each first appeared in.  Concatenating the shards' tokens in rank order and keeping first
+occurrences reproduces exactly the token order a single sequential run would have produced (StringCheck numbers
+tokens by first appearance, StringCheck.cpp:46-55), so clustering, the non-redundant pattern set and the matcher come
+out identical wherever they are computed.
+
+  TokenExchange     token blocks (K4b) -> one NCCL all-gather -> merged on every GPU (K4c) -> every rank clusters
+  PatternExchange   the same gather, but only the root merges and clusters; one NCCL broadcast returns the pattern set
+  allgather_unique_tokens / allgather_dr_lists   the host-merged forms (any backend; gloo in the CPU tests)
 """
 import torch
 import torch.distributed as dist
@@ -56,6 +59,24 @@ class TokenExchange:
                 continue
             return text, count
 
+    def run_matcher(self, d_hits, n_hits, d_tokens, kmer_clust=6, stream=0):
+        """The same exchange, ending in createNonRedundantSet + matcher build straight from the merged block
+        -> (api.Automaton or None when there is no DR, number of distinct DR variants)."""
+        while True:
+            self.ctx.unique_tokens_block_dev(d_hits, n_hits, d_tokens, self.stride, self.send, self.cap, stream)
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+                self.ctx.merge_token_blocks_dev(self.recv, self.world, self.cap, self.stride, self.shard_reads, self.merged, self.out_cap, stream)
+            self.host.copy_(self.merged, non_blocking=True)
+            torch.cuda.current_stream(self.dev).synchronize()
+            ac, count, flags = api.Automaton.from_block(self.host, self.out_cap, self.stride, kmer_clust)
+            if flags & 2:
+                raise api.CrassB200Error(api.EINVAL, "token stride too small for the DR lengths in use")
+            if (flags & 1) or count > self.out_cap:
+                self._alloc(self.cap * 2)
+                continue
+            return ac, count
+
 
 class PatternExchange(TokenExchange):
     """The step between the phases for N > 1 with the serial part done once.
@@ -86,8 +107,10 @@ class PatternExchange(TokenExchange):
         if self.world == 1:
             text, count = super().run(d_hits, n_hits, d_tokens, stream)
             return (api.non_redundant_patterns(text, self.kmer_clust) if text else b""), count
+        import time
         import numpy as np
         while True:
+            t0 = time.perf_counter()
             self.ctx.unique_tokens_block_dev(d_hits, n_hits, d_tokens, self.stride, self.send, self.cap, stream)
             dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
             hdr = self.msg_host[: self.HEADER].numpy()
@@ -95,16 +118,17 @@ class PatternExchange(TokenExchange):
                 self.ctx.merge_token_blocks_dev(self.recv, self.world, self.cap, self.stride, self.shard_reads, self.merged, self.out_cap, stream)
                 self.host.copy_(self.merged, non_blocking=True)
                 torch.cuda.current_stream(self.dev).synchronize()
-                drs, count, flags = api.dr_list_from_block(self.host, self.out_cap, self.stride)
+                t1 = time.perf_counter()
+                text, count, flags = api.non_redundant_patterns_from_block(self.host, self.out_cap, self.stride, self.kmer_clust)
                 if flags & 2:
                     raise api.CrassB200Error(api.EINVAL, "token stride too small for the DR lengths in use")
-                status, text = 0, b""
+                status = 0
                 if (flags & 1) or count > self.out_cap:
-                    status = 1
-                else:
-                    text = api.non_redundant_patterns(drs, self.kmer_clust) if drs else b""
-                    if len(text) > self.text_cap:
-                        status = 2
+                    status, text = 1, b""
+                elif len(text) > self.text_cap:
+                    status = 2
+                t3 = time.perf_counter()
+                self.last_ms = {"gather_merge_d2h": (t1 - t0) * 1e3, "cluster": (t3 - t1) * 1e3}
                 hdr.view(np.uint32)[0:2] = (status, min(count, 0xFFFFFFFF))
                 hdr.view(np.uint64)[1] = len(text)
                 n_send = self.HEADER
@@ -118,6 +142,8 @@ class PatternExchange(TokenExchange):
                 torch.cuda.current_stream(self.dev).synchronize()
             status, count = (int(x) for x in hdr.view(np.uint32)[0:2])
             text_len = int(hdr.view(np.uint64)[1])
+            if self.rank == self.root:
+                self.last_ms["broadcast"] = (time.perf_counter() - t3) * 1e3
             if status == 1:
                 self._alloc(self.cap * 2)
                 continue

@@ -258,6 +258,12 @@ int crass_b200_ac_build_from_dr_list(const char* dr_list, uint32_t kmer_clust, c
  * non-redundant set as '\n'-separated text in the reference's order (per group: survivors, then their reverse
  * complements; malloc'd), and the matcher built from such a text */
 char* crass_b200_non_redundant_patterns(const char* dr_list, uint32_t kmer_clust, uint32_t* n_patterns);
+/* both straight from a host copy of a token block (no intermediate text): *count / *flags as in dr_list_from_block.
+ * ac_build_from_block leaves *out NULL (and returns 0) when the block had overflowed or holds no token. */
+char* crass_b200_non_redundant_patterns_from_block(const void* block, uint32_t cap, uint32_t stride, uint32_t kmer_clust,
+                                                   uint32_t* count, uint32_t* flags, uint32_t* n_patterns);
+int crass_b200_ac_build_from_block(const void* block, uint32_t cap, uint32_t stride, uint32_t kmer_clust, crass_b200_ac** out,
+                                   uint32_t* count, uint32_t* flags, uint32_t* n_patterns);
 int crass_b200_ac_build_from_pattern_list(const char* patterns, crass_b200_ac** out, uint32_t* n_patterns);
 
 /* ---- whole path, one call: searchFile* -> createNonRedundantSet -> findSingletons* --------------- */
