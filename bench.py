@@ -214,6 +214,7 @@ def main():
         host_threads = max(2, min(16, cores - 2 * local_world)) if rank == 0 else 2
     os.environ.setdefault("CRASS_B200_HOST_THREADS", str(host_threads))
     ctx = cb.Context(local_rank)
+    ctx.keep_packed(True)                                # K2 reads the 2-bit stream K1's filter leaves in HBM (same, unchanged batch)
     params = cb.Params()
     work_stream = torch.cuda.Stream(device=dev)          # a real (non-NULL) stream: kernels, copies and events all go here
     torch.cuda.set_stream(work_stream)

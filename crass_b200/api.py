@@ -114,6 +114,7 @@ def lib():
         "crass_b200_results_adopt_tokens": (C.c_int, [vp, cp]),
         "crass_b200_results_non_redundant": (vp, [vp, C.c_uint32, u32p]),
         "crass_b200_results_dump": (vp, [vp, C.c_int]),
+        "crass_b200_ctx_keep_packed": (C.c_int, [vp, C.c_int]),
         "crass_b200_sort_hits": (None, [vp, C.c_uint32]),
         "crass_b200_sort_hits_dev": (C.c_int, [vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp, vp]),
         "crass_b200_token_block_bytes": (C.c_size_t, [C.c_uint32, C.c_uint32]),
@@ -463,6 +464,10 @@ class Context:
         """K4b: device-side de-duplication of the token records of the first n_hits hit slots (torch tensors)."""
         _check(lib().crass_b200_unique_tokens_dev(self.h, d_hits.data_ptr(), n_hits, d_tokens.data_ptr(), stride, d_out_tokens.data_ptr(),
                                                   d_out_first_read.data_ptr(), d_out_count.data_ptr(), stream))
+
+    def keep_packed(self, on=True):
+        """Let ac_scan_dev reuse the 2-bit stream dr_search_dev wrote for the same (unchanged) batch."""
+        _check(lib().crass_b200_ctx_keep_packed(self.h, 1 if on else 0))
 
     def sort_hits_dev(self, d_found, n_reads, d_hits, d_counters, max_hits, d_sorted, stream=0):
         """Hit records of a *_dev search into read order on the device (d_counters: the launch's counter tensor)."""

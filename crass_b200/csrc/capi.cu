@@ -96,6 +96,13 @@ struct crass_b200_ctx {
     DevBuf d_found_p1, d_cand, d_tokens, d_tok_table, d_tok_unique, d_ac_table, d_ac_symv, d_ac_bitmap, d_ac_keys;
     DevBuf d_ac_skeys, d_ac_shead, d_ac_pnext, d_ac_poffs, d_ac_pbytes;
     DevBuf d_cand_counts;                // K1 fast path: sizes of the two candidate lists
+    // the 2-bit stream of the batch, written by k_dr_filter and read by k_ac_filter_packed (crass_b200_ctx_keep_packed)
+    DevBuf d_packed;
+    uint64_t keep_packed_bases = 0;      // caller opt-in for the *_dev calls: capacity in bases, 0 = off
+    const void* packed_src = nullptr;    // d_bases / n_reads the stream was made from
+    uint32_t packed_reads = 0;
+    bool packed_valid = false;
+    bool packed_internal = false;        // set around the resident calls: the context owns the batch, reuse is always safe
     DevBuf d_rank, d_hits_sorted;        // crass_b200_sort_hits_dev: per-chunk prefix counts, read-ordered copy of the hits
     uint64_t ac_serial = 0;              // build serial of the automaton currently held in d_ac_*
     uint64_t ac_dfa_serial = 0;          // ... and of the dense DFA (generic K2 path), uploaded lazily
@@ -164,7 +171,7 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
     DevBuf* bufs[] = {&c->d_bases, &c->d_offsets, &c->d_found, &c->d_skip, &c->d_hits, &c->d_pool, &c->d_counters,
                       &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv, &c->d_found_p1, &c->d_cand, &c->d_tokens, &c->d_tok_table, &c->d_tok_unique, &c->d_ac_table, &c->d_ac_symv,
                       &c->d_ac_bitmap, &c->d_ac_keys, &c->d_ac_skeys, &c->d_ac_shead, &c->d_ac_pnext, &c->d_ac_poffs, &c->d_ac_pbytes,
-                      &c->d_rank, &c->d_hits_sorted, &c->d_cand_counts};
+                      &c->d_rank, &c->d_hits_sorted, &c->d_cand_counts, &c->d_packed};
     for (DevBuf* b : bufs) b->release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     cudaStreamDestroy(c->stream);
@@ -181,6 +188,12 @@ int crass_b200_ctx_set_token_output(crass_b200_ctx* c, void* d_tokens, uint32_t 
     return 0;
 }
 const char* crass_b200_ctx_last_dr_list(const crass_b200_ctx* c) { return c ? c->last_dr_list.c_str() : ""; }
+int crass_b200_ctx_keep_packed(crass_b200_ctx* c, int on) {
+    if (!c) return cbh::fail(CRASS_B200_EINVAL, "ctx is NULL");
+    c->keep_packed_bases = on ? 1 : 0;
+    if (!on) c->packed_valid = false;
+    return 0;
+}
 
 // hit records come off the device in slot order; replay wants read order.  Read indices are distinct, so three or four
 // stable 8-bit counting passes over (index, slot) pairs do it in a fraction of the time of a comparison sort.
@@ -312,6 +325,7 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
     cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
     const cb::Params o = to_core(*params);
     CUDA_TRY(cudaMemsetAsync(d_counters, 0, 4 * sizeof(uint32_t), st));
+    c->packed_valid = false;                                   // a 2-bit stream of an earlier batch is stale from here on
     if (n_reads == 0) return 0;
     if (int r = c->d_error.reserve(sizeof(int))) return r;
     CUDA_TRY(cudaMemsetAsync(c->d_error.p, 0, sizeof(int), st));
@@ -331,6 +345,17 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
         if (int r = c->d_cand_counts.reserve(4 * sizeof(uint32_t))) return r;     // [0] several flagged windows, [1] a single one
         uint32_t* cand_counts = c->d_cand_counts.as<uint32_t>();
         CUDA_TRY(cudaMemsetAsync(cand_counts, 0, 4 * sizeof(uint32_t), st));
+        // the filter recodes every base to 2 bits anyway; on request it leaves that stream in HBM for the singleton scan
+        uint32_t* keep = nullptr;
+        c->packed_valid = false;
+        if (c->keep_packed_bases || c->packed_internal) {
+            const size_t words = (((size_t)n_reads * max_read_len) >> 4) + 256;      // n_bases <= n_reads * max_read_len
+            const bool grew = words * sizeof(uint32_t) > c->d_packed.cap;
+            if (int r = c->d_packed.reserve(words * sizeof(uint32_t))) return r;
+            if (grew) CUDA_TRY(cudaMemsetAsync(c->d_packed.p, 0, c->d_packed.cap, st));   // look-ahead words past the batch are defined
+            keep = c->d_packed.as<uint32_t>();
+            c->packed_src = d_bases; c->packed_reads = n_reads; c->packed_valid = true;
+        }
         const uint32_t n_tiles = (n_reads + cbk::kFilterTile - 1) / cbk::kFilterTile;
         const int se = (int)max_read_len - 58;
         const int nwin = se < 0 ? 1 : se / 16 + 1;
@@ -343,7 +368,7 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
         int per_sm = 1;                                                                                                             \
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbk::k_dr_filter<NW, NWIN, 49, 97>, cbk::kFilterTile, fsmem)); \
         const int pblocks = (int)std::min<uint32_t>(n_tiles, (uint32_t)(c->sm_count * std::max(per_sm, 1)));    /* persistent: one wave */ \
-        cbk::k_dr_filter<NW, NWIN, 49, 97><<<pblocks, cbk::kFilterTile, fsmem, st>>>(d_bases, d_offsets, n_reads, d_found, cand, cand_counts); \
+        cbk::k_dr_filter<NW, NWIN, 49, 97><<<pblocks, cbk::kFilterTile, fsmem, st>>>(d_bases, d_offsets, n_reads, d_found, cand, cand_counts, keep); \
         cbk::k_dr_exact_packed<NW, NWIN, 49, 97><<<eblocks, cbk::kExactThreads, 0, st>>>(d_bases, d_offsets, n_reads, cand, cand_counts, o, d_found, sink, d_err); \
     } while (0)
         if (max_read_len <= 112) { if (nwin <= 3) CB_FAST(7, 3); else CB_FAST(7, 4); }
@@ -469,7 +494,7 @@ int run_with_outputs(crass_b200_ctx* c, uint32_t n_reads, uint64_t n_bases, uint
 }
 
 int upload_batch(crass_b200_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, uint64_t n_bases) {
-    c->res_valid = false; c->res_found_valid = false;
+    c->res_valid = false; c->res_found_valid = false; c->packed_valid = false;
     if (int r = c->d_bases.reserve(n_bases + 64)) return r;
     if (int r = c->d_offsets.reserve(((size_t)n_reads + 1) * sizeof(uint64_t))) return r;
     CUDA_TRY(cudaMemcpyAsync(c->d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, c->stream));
@@ -531,7 +556,10 @@ int crass_b200_dr_search_resident(crass_b200_ctx* c, const crass_b200_params* pa
                                         c->d_pool.as<uint32_t>(), pool_cap, c->d_counters.as<uint32_t>(), c->stream);
     };
     const uint32_t tstride = (params->high_dr + 2 + 15) & ~15u;
-    if (int r = run_with_outputs(c, n_reads, c->res_n_bases, found, launch, hits, n_hits, ss_pool, n_ss_pool, tstride)) return r;
+    c->packed_internal = true;                                 // the context owns the batch: keep its 2-bit stream for phase 2
+    const int rs = run_with_outputs(c, n_reads, c->res_n_bases, found, launch, hits, n_hits, ss_pool, n_ss_pool, tstride);
+    c->packed_internal = false;
+    if (rs) return rs;
     if (int r = c->d_found_p1.reserve((size_t)n_reads + 16)) return r;
     if (n_reads) CUDA_TRY(cudaMemcpyAsync(c->d_found_p1.p, c->d_found.p, n_reads, cudaMemcpyDeviceToDevice, c->stream));
     c->res_found_valid = true;
@@ -650,11 +678,32 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         const int fblocks = (int)std::min<uint32_t>(n_tiles, (uint32_t)(c->sm_count * std::min(per_sm, 8)));                    \
         cbk::k_ac_filter<NW><<<fblocks, cbk::kAcTile, smem, st>>>(d_bases, d_offsets, n_reads, q, d_skip, d_found, cand, d_counters); \
     } while (0)
-        if (max_read_len <= 112) CB_ACF(7);
+        // the 2-bit stream the direct-repeat search of this very batch left behind: a quarter of the bytes, no recoding
+        const char* fsel = getenv("CRASS_B200_K2F");
+        const bool use_packed = c->packed_valid && c->packed_src == (const void*)d_bases && c->packed_reads == n_reads &&
+                                (c->keep_packed_bases || c->packed_internal) && !(fsel && !strcmp(fsel, "bytes"));
+#define CB_ACP(NW)                                                                                                              \
+    do {                                                                                                                        \
+        const size_t smem = bm_bytes + 2 * (size_t)cbk::ac_packed_words<NW>() * sizeof(uint32_t);                               \
+        CUDA_TRY(cudaFuncSetAttribute(cbk::k_ac_filter_packed<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        int per_sm = 1;                                                                                                         \
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbk::k_ac_filter_packed<NW>, cbk::kAcPackedTile, smem)); \
+        const uint32_t p_tiles = (n_reads + cbk::kAcPackedTile - 1) / cbk::kAcPackedTile;                                       \
+        const int pblocks = (int)std::min<uint32_t>(p_tiles, (uint32_t)(c->sm_count * std::max(per_sm, 1)));                    \
+        cbk::k_ac_filter_packed<NW><<<pblocks, cbk::kAcPackedTile, smem, st>>>(c->d_packed.as<uint32_t>(), d_offsets, n_reads, q, d_skip, d_found, cand, d_counters); \
+    } while (0)
+        if (use_packed) {
+            if (max_read_len <= 112) CB_ACP(7);
+            else if (max_read_len <= 160) CB_ACP(10);
+            else if (max_read_len <= 256) CB_ACP(16);
+            else CB_ACP(19);
+        }
+        else if (max_read_len <= 112) CB_ACF(7);
         else if (max_read_len <= 160) CB_ACF(10);
         else if (max_read_len <= 256) CB_ACF(16);
         else CB_ACF(19);
 #undef CB_ACF
+#undef CB_ACP
         CUDA_TRY(cudaGetLastError());
         cbk::PatternStarts ps{c->d_ac_pbytes.as<uint8_t>(), c->d_ac_poffs.as<uint32_t>(), c->d_ac_skeys.as<uint32_t>(),
                               c->d_ac_shead.as<uint32_t>(), c->d_ac_pnext.as<uint32_t>(), ac->a.s_bits, ac->a.s_ones_head,
@@ -736,7 +785,10 @@ int crass_b200_ac_scan_resident(crass_b200_ctx* c, const crass_b200_ac* ac, int 
                                       c->d_hits.as<crass_b200_hit>(), hits_cap, c->d_pool.as<uint32_t>(), pool_cap,
                                       c->d_counters.as<uint32_t>(), c->stream);
     };
-    return run_with_outputs(c, n_reads, c->res_n_bases, found, launch, hits, n_hits, ss_pool, n_ss_pool);
+    c->packed_internal = true;
+    const int rs = run_with_outputs(c, n_reads, c->res_n_bases, found, launch, hits, n_hits, ss_pool, n_ss_pool);
+    c->packed_internal = false;
+    return rs;
 }
 
 // ---- K3 ------------------------------------------------------------------------------------------------

@@ -364,10 +364,13 @@ __device__ __forceinline__ void tile_issue(const uint8_t* __restrict__ bases, co
 
 // cooperative 2-bit recoding of the staged bytes into `packed` (one word per 16 bases); vectors the bulk copy could not
 // cover (ragged end of the batch) are fetched with guarded byte loads
+// If `keep` is given, the words also go to the batch-wide 2-bit stream keep[w] = recode(bases[16w, 16w+16)) so that the
+// singleton scan of the same batch can read a quarter of the bytes and skip the recoding (k_ac_filter_packed).
 template <int TILE>
 __device__ __forceinline__ void tile_pack(const uint8_t* __restrict__ bases, uint64_t n_bases, uint64_t a0, uint32_t want_bytes,
-                                          uint32_t tma_bytes, const uint8_t* buf, uint32_t* packed) {
+                                          uint32_t tma_bytes, const uint8_t* buf, uint32_t* packed, uint32_t* __restrict__ keep = nullptr) {
     const uint32_t nvec = want_bytes >> 4, nt = tma_bytes >> 4;
+    if (keep) keep += a0 >> 4;
     for (uint32_t v = threadIdx.x; v < nvec; v += TILE) {
         uint32_t w;
         if (v < nt) {
@@ -381,6 +384,7 @@ __device__ __forceinline__ void tile_pack(const uint8_t* __restrict__ bases, uin
             w = cb::pack16(q[0], q[1], q[2], q[3]);
         }
         packed[v] = w;
+        if (keep) keep[v] = w;
     }
 }
 
@@ -390,7 +394,8 @@ constexpr size_t dr_filter_smem_bytes() { return (size_t)(kFilterTile * NW + NW 
 template <int NW, int NWIN, int DMIN, int DMAX>
 __global__ void __launch_bounds__(kFilterTile)
 k_dr_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads,
-            uint8_t* __restrict__ found, uint32_t* __restrict__ cand_list, uint32_t* __restrict__ cand_counts) {
+            uint8_t* __restrict__ found, uint32_t* __restrict__ cand_list, uint32_t* __restrict__ cand_counts,
+            uint32_t* __restrict__ keep_packed) {
     constexpr int kWords = kFilterTile * NW + NW + 8;          // packed words a tile can need (+ look-ahead + realignment)
     extern __shared__ __align__(128) uint8_t dyn_smem[];       // dr_filter_smem_bytes<NW>() bytes
     uint8_t* buf = dyn_smem;                                   // the tile's bytes, written by the bulk copy
@@ -408,7 +413,7 @@ k_dr_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs
         uint64_t a0; uint32_t want, tma_bytes;
         tile_extent<kFilterTile, NW>(offsets, n_reads, n_bases, tile, a0, want, tma_bytes);
         mbar_wait(&full, parity);                               // the tile's bytes have landed
-        tile_pack<kFilterTile>(bases, n_bases, a0, want, tma_bytes, buf, sm);
+        tile_pack<kFilterTile>(bases, n_bases, a0, want, tma_bytes, buf, sm, keep_packed);
         __syncthreads();                                        // packed tile complete, byte buffer free again
         if (threadIdx.x == 0 && tile + gridDim.x < n_tiles)
             tile_issue<kFilterTile, NW>(bases, offsets, n_reads, n_bases, tile + gridDim.x, buf, &full);   // overlaps the compute below
@@ -746,6 +751,90 @@ k_ac_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs
             found[r] = 0;
             if (cand && !(skip && skip[r])) cand_list[atomicAdd(&counters[3], 1u)] = r;
         }
+    }
+}
+
+// ---- K2 fast path, stage 1, on the 2-bit stream phase 1 left behind ----------------------------------------------------
+// When the direct-repeat search of the same batch ran through k_dr_filter, every base of the batch already exists as
+// 2 bits in HBM (tile_pack's `keep` stream).  This form of the filter never touches the bytes: one elected thread
+// moves a tile's packed words into shared memory with a 1-D bulk copy (a quarter of the bytes, no recoding
+// instructions), double-buffered so that the copy of tile i+1 runs under the look-ups of tile i.  The look-ups are
+// those of k_ac_filter, so the candidate set is identical.
+constexpr int kAcPackedTile = 512;                   // reads per tile = threads per CTA
+
+template <int NW>
+__host__ __device__ constexpr int ac_packed_words() { return (kAcPackedTile * NW + NW + 16 + 3) & ~3; }   // per buffer, 16-byte granular
+
+template <int NW>
+__device__ __forceinline__ void ac_packed_issue(const uint32_t* __restrict__ packed, const uint64_t* __restrict__ offsets, uint32_t n_reads,
+                                                uint32_t tile, uint32_t* buf, uint64_t* bar) {
+    const uint32_t r0 = tile * kAcPackedTile;
+    const uint32_t r1 = min(r0 + (uint32_t)kAcPackedTile, n_reads);
+    const uint64_t a0 = offsets[r0] & ~(uint64_t)63;                                    // word index a0/16 is a multiple of 4
+    uint32_t nw = ((uint32_t)((offsets[r1] - a0 + 15) >> 4) + NW + 4 + 3) & ~3u;
+    if (nw > (uint32_t)ac_packed_words<NW>()) nw = ac_packed_words<NW>();
+    mbar_arrive_expect_tx(bar, nw * 4u);
+    tma_load_1d(buf, packed + (a0 >> 4), nw * 4u, bar);
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kAcPackedTile)
+k_ac_filter_packed(const uint32_t* __restrict__ packed, const uint64_t* __restrict__ offsets, uint32_t n_reads, QgramFilter q,
+                   const uint8_t* __restrict__ skip, uint8_t* __restrict__ found, uint32_t* __restrict__ cand_list,
+                   uint32_t* __restrict__ counters) {
+    constexpr int kWords = ac_packed_words<NW>();
+    extern __shared__ __align__(128) uint32_t dsm[];
+    uint32_t* tiles = dsm;                                       // two packed tiles (bulk-copy targets, 16-byte aligned)
+    uint32_t* bm = dsm + 2 * kWords;                             // bitmap, (1 << bits) / 32 words
+    __shared__ uint64_t full[2];
+    for (uint32_t i = threadIdx.x; i < (1u << (q.bits - 5)); i += kAcPackedTile) bm[i] = __ldg(q.bitmap + i);
+    if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
+    __syncthreads();
+    const uint32_t n_tiles = (n_reads + kAcPackedTile - 1) / kAcPackedTile;
+    const uint32_t hshift = 32 - q.bits;
+    if (threadIdx.x == 0 && blockIdx.x < n_tiles) ac_packed_issue<NW>(packed, offsets, n_reads, blockIdx.x, tiles, &full[0]);
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t cur = it & 1u;
+        // the other buffer was last read in the previous iteration, which ended with a CTA barrier
+        if (threadIdx.x == 0 && tile + gridDim.x < n_tiles)
+            ac_packed_issue<NW>(packed, offsets, n_reads, tile + gridDim.x, tiles + (cur ^ 1u) * kWords, &full[cur ^ 1u]);
+        const uint32_t* sm = tiles + cur * kWords;
+        const uint32_t r0 = tile * kAcPackedTile;
+        const uint32_t r1 = min(r0 + (uint32_t)kAcPackedTile, n_reads);
+        const uint64_t a0 = offsets[r0] & ~(uint64_t)63;
+        const uint32_t r = r0 + threadIdx.x;
+        uint64_t rb = 0;
+        uint32_t L = 0;
+        if (r < r1) { rb = offsets[r]; L = (uint32_t)(offsets[r + 1] - rb); }
+        mbar_wait(&full[cur], (it >> 1) & 1u);                   // this tile's words have landed
+        if (r < r1) {
+            const uint32_t b = (uint32_t)(rb - a0);
+            const uint32_t wi = b >> 4, sh = (b & 15u) * 2u;
+            uint32_t R[NW + 1];
+#pragma unroll
+            for (int k = 0; k < NW + 1; ++k) R[k] = cb::funnel_r(sm[wi + k], sm[wi + k + 1], sh);
+            uint64_t hits = 0;                                   // 16-mer i starts at base 8i: even i is word i/2, odd i straddles
+#pragma unroll
+            for (int k = 0; k < 2 * NW - 1; ++k) {
+                const uint32_t code = (k & 1) ? cb::funnel_r(R[k >> 1], R[(k >> 1) + 1], 16) : R[k >> 1];
+                const uint32_t h = (code * 0x9E3779B1u) >> hshift;
+                hits |= (uint64_t)((bm[h >> 5] >> (h & 31u)) & 1u) << k;
+            }
+            const int n_kmers = L >= 16 ? (int)((L - 16) >> 3) + 1 : 0;        // 16-mers that lie inside the read
+            if (n_kmers < 64) hits &= (1ull << n_kmers) - 1ull;
+            bool cand = false;
+            while (hits && !cand) {
+                const int k = __ffsll((long long)hits) - 1;
+                hits &= hits - 1;
+                const uint32_t w0 = cb::funnel_r(sm[wi + (k >> 1)], sm[wi + (k >> 1) + 1], sh);
+                const uint32_t w1 = cb::funnel_r(sm[wi + (k >> 1) + 1], sm[wi + (k >> 1) + 2], sh);
+                cand = qgram_member(q, (k & 1) ? cb::funnel_r(w0, w1, 16) : w0);
+            }
+            found[r] = 0;
+            if (cand && !(skip && skip[r])) cand_list[atomicAdd(&counters[3], 1u)] = r;
+        }
+        __syncthreads();                                         // everyone is done with this buffer
     }
 }
 

@@ -94,6 +94,12 @@ uint64_t crass_b200_ctx_last_candidates(const crass_b200_ctx* ctx);
  * low-lexi DR token (ReadHolder::DRLowLexi) to d_tokens + k*stride: byte 0 = length, byte 1 = 1 if the read keeps its
  * orientation, bytes 2.. = the token.  stride >= high_dr + 2.  NULL switches it off. */
 int crass_b200_ctx_set_token_output(crass_b200_ctx* ctx, void* d_tokens, uint32_t stride);
+/* Reuse of phase 1's work in phase 2 for the *_dev calls.  The direct-repeat filter recodes every base of the batch to
+ * 2 bits; with on != 0 the next crass_b200_dr_search_dev launches leave that stream in HBM (n_reads * max_read_len / 4
+ * bytes, owned by ctx) and crass_b200_ac_scan_dev launches on the SAME d_bases pointer and n_reads read it instead of
+ * the bytes (a quarter of the traffic, no recoding).  The caller promises that the bases are not modified between the
+ * two launches.  Results are identical either way.  The resident host-buffer calls do this on their own. */
+int crass_b200_ctx_keep_packed(crass_b200_ctx* ctx, int on);
 /* the distinct tokens of the most recent crass_b200_dr_search_resident in read order, '\n'-separated (owned by ctx) */
 const char* crass_b200_ctx_last_dr_list(const crass_b200_ctx* ctx);
 /* the *_dev entry points leave hit records in device slot order; this puts a host copy into read order (what the

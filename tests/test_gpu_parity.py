@@ -352,6 +352,43 @@ def test_token_blocks_of_three_shards_merge_like_one_sequential_run(ctx):
     assert api.dr_list_from_block(out.cpu().numpy(), 16, TOK)[1] == len(want)
 
 
+def test_singleton_scan_on_the_kept_2bit_stream(ctx, P):
+    """Phase 2 of a resident batch reads the 2-bit stream phase 1's filter left in HBM (k_ac_filter_packed); the hits must be
+    those of the byte-reading filter and of the oracle, for every read-length bucket and with odd bytes in the reads."""
+    rng = random.Random(108)
+    for max_len in (100, 150, 250, 300):
+        pool_drs = [fuzzgen.rand_seq(rng, rng.randint(24, 40)) for _ in range(8)]
+        reads = [fuzzgen.planted_read(rng, rng.randint(max(60, max_len - 50), max_len), dr=rng.choice(pool_drs), sub_rate=rng.choice([0, 0.01]))
+                 for _ in range(3000)]
+        reads += [fuzzgen.mutate(rng, r, 0.01, b"NnacgtRYU") for r in reads[:800]]
+        reads += [fuzzgen.rand_seq(rng, rng.randint(0, max_len)) for _ in range(1200)]
+        rng.shuffle(reads)
+        bases, offs = cb.pack_reads(reads)
+        ctx.upload(bases, offs)
+        hits, pool, _ = ctx.dr_search_resident(cb.Params())
+        pats = api.non_redundant_list(ctx.last_dr_list(), 6)
+        assert len(pats) >= 8
+        ac = cb.Automaton(pats)
+        got = {}
+        for mode in ("packed", "bytes"):
+            if mode == "bytes":
+                os.environ["CRASS_B200_K2F"] = "bytes"
+            try:
+                h2, p2, f2 = ctx.ac_scan_resident(ac, skip_found=True, want_found=True)
+            finally:
+                os.environ.pop("CRASS_B200_K2F", None)
+            got[mode] = (hits_by_read(h2, p2), f2.tobytes())
+        assert got["packed"] == got["bytes"]
+        by_read = got["packed"][0]
+        skip = set(hits["read_index"].tolist())
+        h = P.ac_create(pats)
+        for i in range(0, len(reads), 7):                                 # oracle on a sample
+            m = None if i in skip else P.ac_first_match(h, reads[i])
+            assert (m is None) == (i not in by_read)
+        P.ac_destroy(h)
+        assert len(h2) > 100
+
+
 def test_singleton_scan_fuzz(ctx, P, k2path):
     rng = random.Random(105)
     for n_pat in (1, 7, 100, 1500, 12000):
