@@ -310,8 +310,8 @@ def main():
                 for k, v in zip(HOST_KEYS,
                                 (t1 - t0, t3 - t1, t4 - t3, t5 - t4, t6 - t5, t7 - t6)):
                     host_ms[k].append(v * 1e3)
-                for k, v in getattr(exchange, "last_ms", {}).items():                   # rank 0's share of the N > 1 exchange
-                    host_ms.setdefault("root_" + k, []).append(v)
+                for k, v in getattr(exchange, "last_ms", {}).items():                   # inside exchange_cluster (rank 0's view)
+                    host_ms.setdefault("exchange:" + k, []).append(v)
         stats.update(hits_phase1=len(hits), dr_variants_merged=nu, patterns=pats, hits_phase2=n2)
 
     def step_e2e():

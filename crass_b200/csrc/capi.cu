@@ -369,7 +369,9 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbk::k_dr_filter<NW, NWIN, 49, 97>, cbk::kFilterTile, fsmem)); \
         const int pblocks = (int)std::min<uint32_t>(n_tiles, (uint32_t)(c->sm_count * std::max(per_sm, 1)));    /* persistent: one wave */ \
         cbk::k_dr_filter<NW, NWIN, 49, 97><<<pblocks, cbk::kFilterTile, fsmem, st>>>(d_bases, d_offsets, n_reads, d_found, cand, cand_counts, keep); \
-        cbk::k_dr_exact_packed<NW, NWIN, 49, 97><<<eblocks, cbk::kExactThreads, 0, st>>>(d_bases, d_offsets, n_reads, cand, cand_counts, o, d_found, sink, d_err); \
+        const size_t esmem = cbk::dr_exact_smem_bytes<NW>();                                                                        \
+        CUDA_TRY(cudaFuncSetAttribute(cbk::k_dr_exact_packed<NW, NWIN, 49, 97>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem)); \
+        cbk::k_dr_exact_packed<NW, NWIN, 49, 97><<<eblocks, cbk::kExactThreads, esmem, st>>>(d_bases, d_offsets, n_reads, cand, cand_counts, o, d_found, sink, d_err); \
     } while (0)
         if (max_read_len <= 112) { if (nwin <= 3) CB_FAST(7, 3); else CB_FAST(7, 4); }
         else if (max_read_len <= 160) { if (nwin <= 6) CB_FAST(10, 6); else CB_FAST(10, 7); }

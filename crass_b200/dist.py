@@ -62,14 +62,18 @@ class TokenExchange:
     def run_matcher(self, d_hits, n_hits, d_tokens, kmer_clust=6, stream=0):
         """The same exchange, ending in createNonRedundantSet + matcher build straight from the merged block
         -> (api.Automaton or None when there is no DR, number of distinct DR variants)."""
+        import time
         while True:
+            t0 = time.perf_counter()
             self.ctx.unique_tokens_block_dev(d_hits, n_hits, d_tokens, self.stride, self.send, self.cap, stream)
             if self.world > 1:
                 dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
                 self.ctx.merge_token_blocks_dev(self.recv, self.world, self.cap, self.stride, self.shard_reads, self.merged, self.out_cap, stream)
             self.host.copy_(self.merged, non_blocking=True)
             torch.cuda.current_stream(self.dev).synchronize()
+            t1 = time.perf_counter()
             ac, count, flags = api.Automaton.from_block(self.host, self.out_cap, self.stride, kmer_clust)
+            self.last_ms = {"tokens_to_host": (t1 - t0) * 1e3, "cluster_build": (time.perf_counter() - t1) * 1e3}
             if flags & 2:
                 raise api.CrassB200Error(api.EINVAL, "token stride too small for the DR lengths in use")
             if (flags & 1) or count > self.out_cap:
