@@ -115,6 +115,8 @@ def lib():
         "crass_b200_results_non_redundant": (vp, [vp, C.c_uint32, u32p]),
         "crass_b200_results_dump": (vp, [vp, C.c_int]),
         "crass_b200_ctx_keep_packed": (C.c_int, [vp, C.c_int]),
+        "crass_b200_cluster_block_dev": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), vp]),
+        "crass_b200_cluster_block_patterns_dev": (vp, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), vp]),
         "crass_b200_sort_hits": (None, [vp, C.c_uint32]),
         "crass_b200_sort_hits_dev": (C.c_int, [vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp, vp]),
         "crass_b200_token_block_bytes": (C.c_size_t, [C.c_uint32, C.c_uint32]),
@@ -464,6 +466,23 @@ class Context:
         """K4b: device-side de-duplication of the token records of the first n_hits hit slots (torch tensors)."""
         _check(lib().crass_b200_unique_tokens_dev(self.h, d_hits.data_ptr(), n_hits, d_tokens.data_ptr(), stride, d_out_tokens.data_ptr(),
                                                   d_out_first_read.data_ptr(), d_out_count.data_ptr(), stream))
+
+    def cluster_block_dev(self, d_block, cap, stride, kmer_clust=6, stream=0):
+        """K5 + host passes + matcher build from a token block on the device -> (Automaton or None, count, flags)."""
+        ac = Automaton.__new__(Automaton)
+        ac.h = C.c_void_p()
+        n, cnt, fl = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        _check(lib().crass_b200_cluster_block_dev(self.h, d_block.data_ptr(), cap, stride, kmer_clust, C.byref(ac.h), C.byref(cnt), C.byref(fl), C.byref(n), stream))
+        ac.num_patterns = n.value
+        return (ac if ac.h else None), cnt.value, fl.value
+
+    def cluster_block_patterns_dev(self, d_block, cap, stride, kmer_clust=6, stream=0):
+        """The same, returning the pattern set as '\\n'-terminated text -> (text, count, flags)."""
+        n, cnt, fl = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        s = _take_str(lib().crass_b200_cluster_block_patterns_dev(self.h, d_block.data_ptr(), cap, stride, kmer_clust, C.byref(cnt), C.byref(fl), C.byref(n), stream))
+        if s is None:
+            _check(-1)
+        return s, cnt.value, fl.value
 
     def keep_packed(self, on=True):
         """Let ac_scan_dev reuse the 2-bit stream dr_search_dev wrote for the same (unchanged) batch."""

@@ -50,6 +50,21 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
+struct PinnedBuf {                                  // grow-only page-locked host staging
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        CUDA_TRY(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
 int g_device_count = -2;    // -2: not probed
 
 int probe_devices() {
@@ -96,6 +111,9 @@ struct crass_b200_ctx {
     DevBuf d_found_p1, d_cand, d_tokens, d_tok_table, d_tok_unique, d_ac_table, d_ac_symv, d_ac_bitmap, d_ac_keys;
     DevBuf d_ac_skeys, d_ac_shead, d_ac_pnext, d_ac_poffs, d_ac_pbytes;
     DevBuf d_cand_counts;                // K1 fast path: sizes of the two candidate lists
+    // K5 (clustering passes A/B on the token block): device arrays and their pinned host mirrors
+    DevBuf d_cl_order, d_cl_koff, d_cl_keys, d_cl_first, d_cl_tab, d_cl_info;
+    PinnedBuf h_cl_block, h_cl_order, h_cl_keys, h_cl_first, h_cl_info;
     // the 2-bit stream of the batch, written by k_dr_filter and read by k_ac_filter_packed (crass_b200_ctx_keep_packed)
     DevBuf d_packed;
     uint64_t keep_packed_bases = 0;      // caller opt-in for the *_dev calls: capacity in bases, 0 = off
@@ -171,8 +189,10 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
     DevBuf* bufs[] = {&c->d_bases, &c->d_offsets, &c->d_found, &c->d_skip, &c->d_hits, &c->d_pool, &c->d_counters,
                       &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv, &c->d_found_p1, &c->d_cand, &c->d_tokens, &c->d_tok_table, &c->d_tok_unique, &c->d_ac_table, &c->d_ac_symv,
                       &c->d_ac_bitmap, &c->d_ac_keys, &c->d_ac_skeys, &c->d_ac_shead, &c->d_ac_pnext, &c->d_ac_poffs, &c->d_ac_pbytes,
-                      &c->d_rank, &c->d_hits_sorted, &c->d_cand_counts, &c->d_packed};
+                      &c->d_rank, &c->d_hits_sorted, &c->d_cand_counts, &c->d_packed,
+                      &c->d_cl_order, &c->d_cl_koff, &c->d_cl_keys, &c->d_cl_first, &c->d_cl_tab, &c->d_cl_info};
     for (DevBuf* b : bufs) b->release();
+    for (PinnedBuf* b : {&c->h_cl_block, &c->h_cl_order, &c->h_cl_keys, &c->h_cl_first, &c->h_cl_info}) b->release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -312,6 +332,114 @@ int crass_b200_merge_token_blocks_dev(crass_b200_ctx* c, const void* d_blocks, u
     c->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return 0;
+}
+
+// ---- K5 + host passes: the step between the phases from a token block on the device --------------------------------
+}  // extern "C"
+namespace {
+const uint32_t kClusterDeviceMax = 32768;            // the rank kernel is O(n^2); longer lists take the host passes
+
+int cluster_block(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t stride, uint32_t kmer_clust,
+                  std::vector<std::string>* patterns, uint32_t* count, uint32_t* flags, cudaStream_t st) {
+    patterns->clear();
+    const size_t block_bytes = cbk::kTokenBlockHeader + (size_t)cap * stride;
+    const size_t max_kmers = (size_t)cap * (stride - 16);
+    size_t tab = 1024;
+    while (tab < 2 * max_kmers) tab <<= 1;
+    if (int r = c->d_cl_order.reserve((size_t)cap * 4)) return r;
+    if (int r = c->d_cl_koff.reserve(((size_t)cap + 1025) * 4)) return r;
+    if (int r = c->d_cl_keys.reserve(max_kmers * 4 + 16)) return r;
+    if (int r = c->d_cl_first.reserve(max_kmers * 4 + 16)) return r;
+    if (int r = c->d_cl_tab.reserve(tab * 8)) return r;
+    if (int r = c->d_cl_info.reserve(16)) return r;
+    if (int r = c->h_cl_block.reserve(block_bytes)) return r;
+    if (int r = c->h_cl_order.reserve((size_t)cap * 4)) return r;
+    if (int r = c->h_cl_info.reserve(16)) return r;
+    cbk::ClusterArrays a{(const uint8_t*)d_block, cap, stride, c->d_cl_order.as<uint32_t>(), c->d_cl_koff.as<uint32_t>(),
+                         c->d_cl_keys.as<uint32_t>(), c->d_cl_first.as<uint32_t>(), c->d_cl_tab.as<uint32_t>(),
+                         c->d_cl_tab.as<uint32_t>() + tab, (uint32_t)(tab - 1), c->d_cl_info.as<uint32_t>()};
+    CUDA_TRY(cudaMemsetAsync(c->d_cl_info.p, 0, 16, st));
+    CUDA_TRY(cudaMemsetAsync(c->d_cl_tab.p, 0xFF, tab * 8, st));
+    cbk::k_cl_rank<<<(cap + 256) / 256, 256, 0, st>>>(a);
+    cbk::k_rank_scan<<<1, 1024, 0, st>>>(a.koff, cap + 1);
+    cbk::k_cl_keys<<<(cap + 127) / 128, 128, 0, st>>>(a);
+    cbk::k_cl_first<<<c->sm_count * 4, 256, 0, st>>>(a);
+    c->launches += 4;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(c->h_cl_block.p, d_block, block_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(c->h_cl_order.p, a.order, (size_t)cap * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(c->h_cl_info.p, a.info, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const uint8_t* hb = c->h_cl_block.as<uint8_t>();
+    uint32_t hdr[2];
+    memcpy(hdr, hb, sizeof hdr);
+    if (count) *count = hdr[0];
+    if (flags) *flags = hdr[1];
+    if (hdr[1] || hdr[0] > cap || hdr[0] == 0) return 0;                       // overflowed / empty: the caller looks at count and flags
+    const uint32_t n = c->h_cl_info.as<uint32_t>()[0], total = c->h_cl_info.as<uint32_t>()[1], n_str = c->h_cl_info.as<uint32_t>()[2];
+    std::vector<std::string_view> drs;
+    bool device_ok = n == hdr[0] && n <= kClusterDeviceMax;
+    if (device_ok) {
+        drs.reserve(n);
+        const uint32_t* order = c->h_cl_order.as<uint32_t>();
+        for (uint32_t t = 0; t < n && device_ok; ++t) {
+            if (order[t] >= n) { device_ok = false; break; }
+            const uint8_t* rec = hb + cbk::kTokenBlockHeader + (size_t)order[t] * stride;
+            const uint32_t ln = rec[0] + 6u <= stride ? rec[0] : stride - 6;
+            if (!ln) device_ok = false;                                     // an empty token would shift the numbering
+            drs.push_back(std::string_view((const char*)rec + 2, ln));
+        }
+    }
+    if (!device_ok) {                                                          // host passes on the copied block
+        *patterns = cbh::non_redundant_set(cbh::block_views(hb, cap, stride, nullptr, nullptr), (int)kmer_clust, nullptr, nullptr);
+        return 0;
+    }
+    if (int r = c->h_cl_keys.reserve((size_t)total * 4 + 16)) return r;
+    if (int r = c->h_cl_first.reserve((size_t)total * 4 + 16)) return r;
+    if (total) {
+        CUDA_TRY(cudaMemcpyAsync(c->h_cl_keys.p, a.keys, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(c->h_cl_first.p, a.first, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    cbh::ClusterPre pre{c->h_cl_keys.as<uint32_t>(), c->h_cl_first.as<uint32_t>(), total, n_str};
+    *patterns = cbh::non_redundant_set(drs, (int)kmer_clust, nullptr, &pre);
+    return 0;
+}
+}  // namespace
+extern "C" {
+
+int crass_b200_cluster_block_dev(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t stride, uint32_t kmer_clust,
+                                 crass_b200_ac** out, uint32_t* count, uint32_t* flags, uint32_t* n_patterns, void* stream_v) {
+    if (!c || !d_block || !out) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    if (stride < 28 || (stride & 3) || cap == 0) return cbh::fail(CRASS_B200_EINVAL, "bad block geometry");
+    *out = nullptr;
+    if (n_patterns) *n_patterns = 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    std::vector<std::string> nr;
+    if (int r = cluster_block(c, d_block, cap, stride, kmer_clust, &nr, count, flags, stream_v ? (cudaStream_t)stream_v : c->stream)) return r;
+    if (n_patterns) *n_patterns = (uint32_t)nr.size();
+    if (nr.empty()) return 0;
+    std::vector<uint8_t> bytes;
+    std::vector<uint32_t> offs(1, 0);
+    for (const std::string& p : nr) { bytes.insert(bytes.end(), p.begin(), p.end()); offs.push_back((uint32_t)bytes.size()); }
+    return crass_b200_ac_build(bytes.data(), offs.data(), (uint32_t)nr.size(), out);
+}
+
+char* crass_b200_cluster_block_patterns_dev(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t stride, uint32_t kmer_clust,
+                                            uint32_t* count, uint32_t* flags, uint32_t* n_patterns, void* stream_v) {
+    if (!c || !d_block || stride < 28 || (stride & 3) || cap == 0) { cbh::fail(CRASS_B200_EINVAL, "bad argument"); return nullptr; }
+    if (cudaSetDevice(c->device) != cudaSuccess) { cbh::fail(CRASS_B200_ECUDA, "cudaSetDevice failed"); return nullptr; }
+    std::vector<std::string> nr;
+    if (cluster_block(c, d_block, cap, stride, kmer_clust, &nr, count, flags, stream_v ? (cudaStream_t)stream_v : c->stream)) return nullptr;
+    if (n_patterns) *n_patterns = (uint32_t)nr.size();
+    size_t total = 1;
+    for (const std::string& p : nr) total += p.size() + 1;
+    char* text = (char*)malloc(total);
+    if (!text) { cbh::fail(CRASS_B200_ENOMEM, "malloc"); return nullptr; }
+    char* w = text;
+    for (const std::string& p : nr) { memcpy(w, p.data(), p.size()); w += p.size(); *w++ = '\n'; }
+    *w = 0;
+    return text;
 }
 
 // ---- K1 ------------------------------------------------------------------------------------------------

@@ -290,7 +290,7 @@ char* crass_b200_dr_list_from_unique(const uint8_t* records, uint32_t stride, co
 }  // extern "C"
 
 // the DR tokens of a host copy of a token block, as views into it, in order-key (first-appearance) order
-static std::vector<std::string_view> block_views(const void* block, uint32_t cap, uint32_t stride, uint32_t* count, uint32_t* flags) {
+std::vector<std::string_view> cbh::block_views(const void* block, uint32_t cap, uint32_t stride, uint32_t* count, uint32_t* flags) {
     const uint8_t* p = (const uint8_t*)block;
     uint32_t hdr[2];
     memcpy(hdr, p, sizeof hdr);

@@ -74,8 +74,18 @@ void add_read_holder(Results& r, HeldRead* h);
 // WorkHorse::createNonRedundantSet on tokens 2..; fills groups (token, gid) when not NULL
 std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, int min_count,
                                            std::vector<std::pair<int, int> >* groups);
+// passes A and B computed elsewhere (K5 on the GPU) for exactly the list handed to non_redundant_set: the canonical key
+// of every 11-mer in token order (0xFFFFFFFF = goes through the string map) and, for integer keys, the first DR holding it
+struct ClusterPre {
+    const uint32_t* keys;
+    uint32_t* first;            // overwritten (folded into runs)
+    size_t total;               // number of 11-mers
+    uint32_t n_string_keys;     // how many keys are 0xFFFFFFFF
+};
 std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& drs, int min_count,
-                                           std::vector<std::pair<int, int> >* groups);
+                                           std::vector<std::pair<int, int> >* groups, const ClusterPre* pre = nullptr);
+// the DR tokens of a host copy of a token block (include/crass_b200.h) as views into it, in first-appearance order
+std::vector<std::string_view> block_views(const void* block, uint32_t cap, uint32_t stride, uint32_t* count, uint32_t* flags);
 std::string dump_results(Results& r, int max_read_len);
 
 // ---- multi-pattern automaton (dense DFA, failure links resolved) ---------------------------------------

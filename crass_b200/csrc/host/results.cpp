@@ -219,11 +219,11 @@ struct HeadTable {
 
 std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, int min_count,
                                            std::vector<std::pair<int, int> >* groups_out) {
-    return non_redundant_set(std::vector<std::string_view>(drs.begin(), drs.end()), min_count, groups_out);
+    return non_redundant_set(std::vector<std::string_view>(drs.begin(), drs.end()), min_count, groups_out, nullptr);
 }
 
 std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& drs, int min_count,
-                                           std::vector<std::pair<int, int> >* groups_out) {
+                                           std::vector<std::pair<int, int> >* groups_out, const ClusterPre* pre_in) {
     // (1) greedy k-mer clustering in token order.  A DR joins the first group that reaches min_count shared
     //     11-mers while walking its k-mers left to right (the test is only made from a group's second hit on);
     //     otherwise it founds a new group.  K-mers never seen before are then given to the chosen group.
@@ -247,8 +247,11 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& 
     for (size_t t = 0; t < n_dr; ++t)
         koff[t + 1] = koff[t] + (drs[t].size() >= kClusterKmer ? drs[t].size() - kClusterKmer + 1 : 0);
     const size_t total_kmers = koff[n_dr];
+    // passes A and B may come from the GPU (K5, kernels.cuh): keys[] and, for every k-mer with an integer key, the first
+    // DR that holds it.  Only arrays of exactly this list are accepted.
+    const ClusterPre* const pre = pre_in && pre_in->total == total_kmers ? pre_in : nullptr;
     size_t tsize = 1024;
-    while (tsize < total_kmers * 2 + 16) tsize <<= 1;
+    while (!pre && tsize < total_kmers * 2 + 16) tsize <<= 1;
     // the work arrays are kept across calls (fresh multi-megabyte vectors cost more in page faults than the clustering
     // itself); of the hash table only the slots this call touches are reset on the way out, so that untouched slots
     // always hold (empty, INT_MAX)
@@ -261,8 +264,8 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& 
         first_store.resize(keys_store.size());
         runc_store.resize(keys_store.size());
     }
-    uint32_t* const keys = keys_store.data();                              // pass A: canonical key per k-mer
-    uint32_t* const first = first_store.data();                            // pass B: first DR (token order) holding it; B2: runs
+    uint32_t* const keys = pre ? const_cast<uint32_t*>(pre->keys) : keys_store.data();   // pass A: canonical key per k-mer (read-only when given)
+    uint32_t* const first = pre ? pre->first : first_store.data();         // pass B: first DR (token order) holding it; B2: runs
     uint32_t* const runc = runc_store.data();                              // pass B2: length of each run
     std::vector<uint32_t> n_runs(n_dr, 0);
     tsize = table_store.size();
@@ -366,8 +369,8 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& 
         for (size_t t = t_begin; t < t_end; ++t) {
             size_t out = koff[t];
             for (size_t q = koff[t]; q < koff[t + 1]; ++q) {
-                if (q + kAhead < q_end && keys[q + kAhead] != kStrKey) __builtin_prefetch(&table[first[q + kAhead]]);
-                const uint32_t f = keys[q] != kStrKey ? (uint32_t)table[first[q]].val : first[q];
+                if (!pre && q + kAhead < q_end && keys[q + kAhead] != kStrKey) __builtin_prefetch(&table[first[q + kAhead]]);
+                const uint32_t f = keys[q] != kStrKey && !pre ? (uint32_t)table[first[q]].val : first[q];
                 if (f >= t) continue;                                    // never seen before this DR
                 if (out > koff[t] && first[out - 1] == f) runc[out - 1]++;
                 else { first[out] = f; runc[out] = 1; ++out; }
@@ -508,8 +511,15 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& 
         }
     };
     auto worker = [&](unsigned w) {
-        pass_a(w, cut[w], cut[w + 1]);
-        pass_b(w, cut[w], cut[w + 1]);
+        if (pre) {                                                        // A and B came from the GPU: only list the string-keyed k-mers
+            if (pre->n_string_keys)
+                for (size_t t = cut[w]; t < cut[w + 1]; ++t)
+                    for (size_t q = koff[t]; q < koff[t + 1]; ++q)
+                        if (keys[q] == kStrKey) { any_str.store(true, std::memory_order_relaxed); str_pos[w].push_back(std::make_pair((uint32_t)t, (uint32_t)q)); }
+        } else {
+            pass_a(w, cut[w], cut[w + 1]);
+            pass_b(w, cut[w], cut[w + 1]);
+        }
         barrier.wait();
         if (w == 0) CB_NR_MARK("pass A+B");
         if (any_str.load()) {

@@ -198,11 +198,130 @@ k_rank_scatter(const uint8_t* __restrict__ found, const uint32_t* __restrict__ c
     if (rank < max_hits) sorted[rank] = h;
 }
 
+// ---- K5: the data-parallel passes of createNonRedundantSet on the token block ---------------------------
+// Input: a token block (K4b/K4c output, records in arbitrary order with their first-appearance key).  Output, all in
+// token order t = rank of the key: order[t] = record slot, koff[t] = offset of DR t's 11-mers, keys[q] = canonical
+// 22-bit key of every 11-mer (min(forward, reverse complement) with A<C<G<T, = laurenize, SeqUtils.cpp:89-97;
+// 0xFFFFFFFF for the rare 11-mers whose canonical form holds another letter: the host sends those through a string map)
+// and first[q] = the first DR in token order that contains the 11-mer (what clusterDRReads' k-mer map answers,
+// WorkHorse.cpp:1404-1637).  The order-dependent walk over these arrays stays on the host (results.cpp, pass C).
+constexpr uint32_t kTokenBlockHeader = 16;          // bytes in front of the records of a token block (see K4b/K4c below)
+constexpr uint32_t kClKmer = 11;
+constexpr uint32_t kClStr = 0xFFFFFFFFu;
+
+__device__ __forceinline__ int cl_code(uint8_t c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; }
+
+struct ClusterArrays {
+    const uint8_t* block;        // token block
+    uint32_t cap, stride;
+    uint32_t* order;             // [cap]
+    uint32_t* koff;              // [cap + 1]
+    uint32_t* keys;              // [cap * (stride - 16)]
+    uint32_t* first;             // same size
+    uint32_t* tab_key;           // open-addressing table: key -> smallest t
+    uint32_t* tab_val;
+    uint32_t tab_mask;
+    uint32_t* info;              // [0] n, [1] total k-mers, [2] k-mers that need the string map
+    __device__ uint32_t n() const { return min(*reinterpret_cast<const uint32_t*>(block), cap); }
+    __device__ const uint8_t* rec(uint32_t slot) const { return block + kTokenBlockHeader + (size_t)slot * stride; }
+    __device__ uint32_t key_of(uint32_t slot) const { return *reinterpret_cast<const uint32_t*>(rec(slot) + stride - 4); }
+    __device__ uint32_t len_of(uint32_t slot) const { const uint32_t l = rec(slot)[0]; return l + 6u <= stride ? l : stride - 6u; }
+};
+
+// token position of every record = number of records with a smaller key (keys are distinct: one token per first read)
+__global__ void __launch_bounds__(256)
+k_cl_rank(ClusterArrays a) {
+    __shared__ uint32_t tile[256];
+    const uint32_t n = a.n();
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (blockIdx.x * 256 >= n) {                                     // CTAs past the list only clear their part of koff
+        if (i <= a.cap) a.koff[i] = 0;
+        if (i == 0) a.info[0] = n;
+        return;
+    }
+    const uint32_t mine = i < n ? a.key_of(i) : 0u;
+    uint32_t rank = 0;
+    for (uint32_t j0 = 0; j0 < n; j0 += 256) {
+        __syncthreads();
+        tile[threadIdx.x] = j0 + threadIdx.x < n ? a.key_of(j0 + threadIdx.x) : 0xFFFFFFFFu;
+        __syncthreads();
+        const uint32_t m = min(256u, n - j0);
+        for (uint32_t j = 0; j < m; ++j) rank += tile[j] < mine ? 1u : 0u;
+    }
+    if (i < n) {
+        a.order[rank] = i;
+        const uint32_t len = a.len_of(i);
+        a.koff[rank] = len >= kClKmer ? len - kClKmer + 1 : 0u;     // counts; k_rank_scan turns them into offsets
+    } else if (i <= a.cap) {
+        a.koff[i] = 0;
+    }
+    if (i == 0) a.info[0] = n;
+}
+
+// pass A + B: keys of DR t and the hash table key -> min t
+__global__ void __launch_bounds__(128)
+k_cl_keys(ClusterArrays a) {
+    const uint32_t n = a.n();
+    const uint32_t t = blockIdx.x * 128 + threadIdx.x;
+    if (t == 0) a.info[1] = a.koff[n];
+    if (t >= n) return;
+    const uint32_t slot = a.order[t];
+    const uint8_t* dr = a.rec(slot) + 2;
+    const uint32_t len = a.len_of(slot);
+    uint32_t q = a.koff[t];
+    const uint32_t kmask = (1u << (2 * kClKmer)) - 1u;
+    uint32_t fw = 0, rc = 0;
+    int valid = 0;                                                   // trailing run of A/C/G/T bytes
+    for (uint32_t p = 0; p < len; ++p) {
+        const int c = cl_code(dr[p]);
+        if (c < 0) valid = 0;
+        else { valid++; fw = ((fw << 2) | (uint32_t)c) & kmask; rc = (rc >> 2) | ((uint32_t)(3 - c) << (2 * (kClKmer - 1))); }
+        if (p + 1 < kClKmer) continue;
+        uint32_t key = kClStr;
+        if (valid >= (int)kClKmer) key = fw < rc ? fw : rc;
+        else {                                                       // another letter in the window: canonical form on the bytes
+            const uint8_t* k = dr + (p + 1 - kClKmer);
+            int cmp = 0;                                             // k vs its reverse complement, as unsigned bytes
+            for (uint32_t i = 0; i < kClKmer && !cmp; ++i) {
+                const uint8_t x = k[i], y = c_comp_tab[k[kClKmer - 1 - i] & 127];
+                cmp = x < y ? -1 : x > y ? 1 : 0;
+            }
+            uint32_t k2 = 0;
+            bool acgt = true;                                        // e.g. a 'U' whose reverse complement is all A/C/G/T
+            for (uint32_t i = 0; i < kClKmer && acgt; ++i) {
+                const int c2 = cl_code(cmp < 0 ? k[i] : c_comp_tab[k[kClKmer - 1 - i] & 127]);
+                if (c2 < 0) acgt = false; else k2 = (k2 << 2) | (uint32_t)c2;
+            }
+            if (acgt) key = k2;
+        }
+        a.keys[q] = key;
+        if (key == kClStr) { atomicAdd(&a.info[2], 1u); a.first[q] = kClStr; }
+        else {
+            uint32_t s = (key * 0x9E3779B1u) & a.tab_mask;
+            for (;;) {
+                const uint32_t cur = atomicCAS(&a.tab_key[s], kClStr, key);
+                if (cur == kClStr || cur == key) break;
+                s = (s + 1) & a.tab_mask;
+            }
+            atomicMin(&a.tab_val[s], t);
+            a.first[q] = s;
+        }
+        ++q;
+    }
+}
+
+// pass B2, first half: slot -> first DR
+__global__ void __launch_bounds__(256)
+k_cl_first(ClusterArrays a) {
+    const uint32_t total = a.koff[a.n()];
+    for (uint32_t q = blockIdx.x * 256 + threadIdx.x; q < total; q += gridDim.x * 256)
+        if (a.keys[q] != kClStr) a.first[q] = a.tab_val[a.first[q]];
+}
+
 // ---- K4b/K4c in block form: the unit of the multi-GPU exchange -----------------------------------------------
 // A token block is 16 header bytes (u32 count, u32 flags, 8 spare) followed by `cap` records of `stride` bytes; the
 // last four bytes of a record hold its order key (read index of first appearance).  count may exceed cap: the block
 // then holds the first cap records that arrived and the caller retries with a larger one.
-const uint32_t kTokenBlockHeader = 16;
 
 struct HitTokens {                                   // source = the token records of a hit list (K4b)
     const crass_b200_hit* hits;

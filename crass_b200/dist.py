@@ -13,7 +13,11 @@ out identical wherever they are computed.
 import torch
 import torch.distributed as dist
 
+import os
+
 from . import api
+
+_HOST_PASSES = os.environ.get("CRASS_B200_CLUSTER", "") == "host"   # comparison knob: clustering passes A/B on the host
 
 
 class TokenExchange:
@@ -69,10 +73,14 @@ class TokenExchange:
             if self.world > 1:
                 dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
                 self.ctx.merge_token_blocks_dev(self.recv, self.world, self.cap, self.stride, self.shard_reads, self.merged, self.out_cap, stream)
-            self.host.copy_(self.merged, non_blocking=True)
-            torch.cuda.current_stream(self.dev).synchronize()
-            t1 = time.perf_counter()
-            ac, count, flags = api.Automaton.from_block(self.host, self.out_cap, self.stride, kmer_clust)
+            if _HOST_PASSES:                                      # CRASS_B200_CLUSTER=host: all clustering passes on the host
+                self.host.copy_(self.merged, non_blocking=True)
+                torch.cuda.current_stream(self.dev).synchronize()
+                t1 = time.perf_counter()
+                ac, count, flags = api.Automaton.from_block(self.host, self.out_cap, self.stride, kmer_clust)
+            else:                                                 # K5: token order, k-mer keys and first holders on the GPU
+                t1 = time.perf_counter()
+                ac, count, flags = self.ctx.cluster_block_dev(self.merged, self.out_cap, self.stride, kmer_clust, stream)
             self.last_ms = {"tokens_to_host": (t1 - t0) * 1e3, "cluster_build": (time.perf_counter() - t1) * 1e3}
             if flags & 2:
                 raise api.CrassB200Error(api.EINVAL, "token stride too small for the DR lengths in use")
@@ -120,10 +128,14 @@ class PatternExchange(TokenExchange):
             hdr = self.msg_host[: self.HEADER].numpy()
             if self.rank == self.root:
                 self.ctx.merge_token_blocks_dev(self.recv, self.world, self.cap, self.stride, self.shard_reads, self.merged, self.out_cap, stream)
-                self.host.copy_(self.merged, non_blocking=True)
-                torch.cuda.current_stream(self.dev).synchronize()
-                t1 = time.perf_counter()
-                text, count, flags = api.non_redundant_patterns_from_block(self.host, self.out_cap, self.stride, self.kmer_clust)
+                if _HOST_PASSES:
+                    self.host.copy_(self.merged, non_blocking=True)
+                    torch.cuda.current_stream(self.dev).synchronize()
+                    t1 = time.perf_counter()
+                    text, count, flags = api.non_redundant_patterns_from_block(self.host, self.out_cap, self.stride, self.kmer_clust)
+                else:
+                    t1 = time.perf_counter()
+                    text, count, flags = self.ctx.cluster_block_patterns_dev(self.merged, self.out_cap, self.stride, self.kmer_clust, stream)
                 if flags & 2:
                     raise api.CrassB200Error(api.EINVAL, "token stride too small for the DR lengths in use")
                 status = 0

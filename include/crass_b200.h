@@ -260,6 +260,16 @@ char* crass_b200_non_redundant_set(const char* dr_list, uint32_t kmer_clust);
  * WorkHorse.cpp:367-379 takes between the phases (createNonRedundantSet, then findSingletons builds its matcher,
  * libcrispr.cpp:455-470).  *n_patterns (optional) = size of the non-redundant set; an empty set is EINVAL. */
 int crass_b200_ac_build_from_dr_list(const char* dr_list, uint32_t kmer_clust, crass_b200_ac** out, uint32_t* n_patterns);
+/* K5: the same step from a token block that is still on the device (the output of unique_tokens_block_dev or
+ * merge_token_blocks_dev).  The data-parallel passes of createNonRedundantSet -- token order, the canonical key of every
+ * 11-mer and the first DR holding it (clusterDRReads' k-mer map, WorkHorse.cpp:1404-1637) -- run as kernels; the
+ * order-dependent walk, the substring reduction and the matcher build follow on the host.  Synchronises the stream.
+ * *count / *flags as in dr_list_from_block; *out stays NULL (return 0) for an overflowed or empty block.
+ * The second form returns the pattern set as '\n'-separated text instead (malloc'd). */
+int crass_b200_cluster_block_dev(crass_b200_ctx* ctx, const void* d_block, uint32_t cap, uint32_t stride, uint32_t kmer_clust,
+                                 crass_b200_ac** out, uint32_t* count, uint32_t* flags, uint32_t* n_patterns, void* stream);
+char* crass_b200_cluster_block_patterns_dev(crass_b200_ctx* ctx, const void* d_block, uint32_t cap, uint32_t stride,
+                                            uint32_t kmer_clust, uint32_t* count, uint32_t* flags, uint32_t* n_patterns, void* stream);
 /* the two halves separately, for drivers that cluster on one rank and hand the pattern set to the others: the
  * non-redundant set as '\n'-separated text in the reference's order (per group: survivors, then their reverse
  * complements; malloc'd), and the matcher built from such a text */

@@ -352,6 +352,53 @@ def test_token_blocks_of_three_shards_merge_like_one_sequential_run(ctx):
     assert api.dr_list_from_block(out.cpu().numpy(), 16, TOK)[1] == len(want)
 
 
+def test_clustering_passes_on_the_device_match_the_host(ctx, P):
+    """K5: token order, 11-mer keys and first holders computed by kernels on a token block must lead to exactly the pattern
+    set (same strings, same order) of the host passes and of the oracle, incl. N/U/R letters, tiny and long lists."""
+    import torch
+    rng = random.Random(109)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    dev = torch.device("cuda", 0)
+    stride = 64
+    for n_base, n_var, alphabet in ((1, 1, b"ACGT"), (3, 4, b"ACGT"), (40, 12, b"ACGTN"), (60, 10, b"ACGTUR"), (400, 16, b"ACGTN"), (1500, 28, b"ACGT")):
+        base = [fuzzgen.rand_seq(rng, rng.randint(23, 47)) for _k in range(n_base)]
+        drs = []
+        for b in base:
+            for _k in range(n_var):
+                v = fuzzgen.mutate(rng, b, rng.choice([0, 0.02, 0.05]), alphabet)
+                a, e = rng.randint(0, 4), rng.randint(0, 4)
+                v = v[a:len(v) - e] if rng.random() < 0.5 else fuzzgen.rand_seq(rng, a) + v + fuzzgen.rand_seq(rng, e)
+                drs.append(min(v, v.translate(comp)[::-1])[:58])
+        uniq = list(dict.fromkeys(drs))
+        rng.shuffle(uniq)                                                 # token order = order of `uniq`
+        keys = sorted(rng.sample(range(50_000_000), len(uniq)))
+        slots = list(range(len(uniq)))
+        rng.shuffle(slots)                                                # records sit in the block in arbitrary order
+        cap = len(uniq) + rng.randint(0, 50)
+        blk = np.zeros(api.token_block_bytes(cap, stride), dtype=np.uint8)
+        blk[:4] = np.frombuffer(np.uint32(len(uniq)).tobytes(), dtype=np.uint8)
+        for t, slot in enumerate(slots):
+            rec = blk[16 + slot * stride: 16 + (slot + 1) * stride]
+            rec[0] = len(uniq[t])
+            rec[2:2 + len(uniq[t])] = np.frombuffer(uniq[t], dtype=np.uint8)
+            rec[stride - 4:] = np.frombuffer(np.uint32(keys[t]).tobytes(), dtype=np.uint8)
+        want, cnt_h, fl_h = api.non_redundant_patterns_from_block(blk, cap, stride, 6)
+        assert want == api.non_redundant_patterns(b"".join(d + b"\n" for d in uniq), 6)
+        d_blk = torch.from_numpy(blk).to(dev)
+        got, cnt, fl = ctx.cluster_block_patterns_dev(d_blk, cap, stride, 6)
+        assert (cnt, fl) == (cnt_h, fl_h) == (len(uniq), 0)
+        assert got == want, (n_base, n_var, alphabet)
+        ac, cnt2, fl2 = ctx.cluster_block_dev(d_blk, cap, stride, 6)
+        assert ac is not None and ac.num_patterns == want.count(b"\n") and cnt2 == len(uniq)
+        if len(uniq) < 3000:                                              # the oracle's clustering is quadratic
+            ref = P.non_redundant(uniq)
+            assert sorted(l[2:] for l in ref.split("\n") if l.startswith("P\t")) == sorted(want.decode().split("\n")[:-1])
+    # an overflowed block is reported, not clustered
+    blk[:4] = np.frombuffer(np.uint32(cap + 5).tobytes(), dtype=np.uint8)
+    got, cnt, fl = ctx.cluster_block_patterns_dev(torch.from_numpy(blk).to(dev), cap, stride, 6)
+    assert got == b"" and cnt == cap + 5
+
+
 def test_singleton_scan_on_the_kept_2bit_stream(ctx, P):
     """Phase 2 of a resident batch reads the 2-bit stream phase 1's filter left in HBM (k_ac_filter_packed); the hits must be
     those of the byte-reading filter and of the oracle, for every read-length bucket and with odd bytes in the reads."""
