@@ -114,6 +114,7 @@ struct crass_b200_ctx {
     // K5 (clustering passes A/B on the token block): device arrays and their pinned host mirrors
     DevBuf d_cl_order, d_cl_koff, d_cl_keys, d_cl_first, d_cl_tab, d_cl_info;
     PinnedBuf h_cl_block, h_cl_order, h_cl_keys, h_cl_first, h_cl_info;
+    PinnedBuf h_ac_stage;                // matcher tables on their way to the device
     // the 2-bit stream of the batch, written by k_dr_filter and read by k_ac_filter_packed (crass_b200_ctx_keep_packed)
     DevBuf d_packed;
     uint64_t keep_packed_bases = 0;      // caller opt-in for the *_dev calls: capacity in bases, 0 = off
@@ -192,7 +193,7 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
                       &c->d_rank, &c->d_hits_sorted, &c->d_cand_counts, &c->d_packed,
                       &c->d_cl_order, &c->d_cl_koff, &c->d_cl_keys, &c->d_cl_first, &c->d_cl_tab, &c->d_cl_info};
     for (DevBuf* b : bufs) b->release();
-    for (PinnedBuf* b : {&c->h_cl_block, &c->h_cl_order, &c->h_cl_keys, &c->h_cl_first, &c->h_cl_info}) b->release();
+    for (PinnedBuf* b : {&c->h_cl_block, &c->h_cl_order, &c->h_cl_keys, &c->h_cl_first, &c->h_cl_info, &c->h_ac_stage}) b->release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -750,9 +751,16 @@ int ensure_ac_on_device(crass_b200_ctx* c, crass_b200_ac* ac) {
             {&c->d_ac_poffs, a.p_offs.data(), a.p_offs.size() * sizeof(uint32_t)},
             {&c->d_ac_pbytes, a.p_bytes.data(), a.p_bytes.size()},
         };
+        // staged through one page-locked buffer: copies from pageable vectors are synchronous and slow for small tables
+        size_t total = 0;
+        for (const Up& u : ups) total += (u.bytes + 63) & ~(size_t)63;
+        if (int r = c->h_ac_stage.reserve(total)) return r;
+        size_t at = 0;
         for (const Up& u : ups) {
             if (int r = u.d->reserve(u.bytes + 16)) return r;
-            CUDA_TRY(cudaMemcpyAsync(u.d->p, u.h, u.bytes, cudaMemcpyHostToDevice, c->stream));
+            memcpy(c->h_ac_stage.as<uint8_t>() + at, u.h, u.bytes);
+            CUDA_TRY(cudaMemcpyAsync(u.d->p, c->h_ac_stage.as<uint8_t>() + at, u.bytes, cudaMemcpyHostToDevice, c->stream));
+            at += (u.bytes + 63) & ~(size_t)63;
         }
     }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
