@@ -113,7 +113,8 @@ struct crass_b200_ctx {
     DevBuf d_cand_counts;                // K1 fast path: sizes of the two candidate lists
     // K5 (clustering passes A/B on the token block): device arrays and their pinned host mirrors
     DevBuf d_cl_order, d_cl_koff, d_cl_keys, d_cl_first, d_cl_tab, d_cl_info;
-    PinnedBuf h_cl_block, h_cl_order, h_cl_keys, h_cl_first, h_cl_info;
+    DevBuf d_cl_group, d_cl_chain, d_cl_next, d_cl_odd, d_cl_dead;
+    PinnedBuf h_cl_block, h_cl_order, h_cl_keys, h_cl_first, h_cl_info, h_cl_group, h_cl_dead;
     PinnedBuf h_ac_stage;                // matcher tables on their way to the device
     // the 2-bit stream of the batch, written by k_dr_filter and read by k_ac_filter_packed (crass_b200_ctx_keep_packed)
     DevBuf d_packed;
@@ -191,9 +192,11 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
                       &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv, &c->d_found_p1, &c->d_cand, &c->d_tokens, &c->d_tok_table, &c->d_tok_unique, &c->d_ac_table, &c->d_ac_symv,
                       &c->d_ac_bitmap, &c->d_ac_keys, &c->d_ac_skeys, &c->d_ac_shead, &c->d_ac_pnext, &c->d_ac_poffs, &c->d_ac_pbytes,
                       &c->d_rank, &c->d_hits_sorted, &c->d_cand_counts, &c->d_packed,
-                      &c->d_cl_order, &c->d_cl_koff, &c->d_cl_keys, &c->d_cl_first, &c->d_cl_tab, &c->d_cl_info};
+                      &c->d_cl_order, &c->d_cl_koff, &c->d_cl_keys, &c->d_cl_first, &c->d_cl_tab, &c->d_cl_info,
+                      &c->d_cl_group, &c->d_cl_chain, &c->d_cl_next, &c->d_cl_odd, &c->d_cl_dead};
     for (DevBuf* b : bufs) b->release();
-    for (PinnedBuf* b : {&c->h_cl_block, &c->h_cl_order, &c->h_cl_keys, &c->h_cl_first, &c->h_cl_info, &c->h_ac_stage}) b->release();
+    for (PinnedBuf* b : {&c->h_cl_block, &c->h_cl_order, &c->h_cl_keys, &c->h_cl_first, &c->h_cl_info, &c->h_ac_stage,
+                         &c->h_cl_group, &c->h_cl_dead}) b->release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -367,8 +370,8 @@ int cluster_block(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t
     cbk::k_cl_first<<<c->sm_count * 4, 256, 0, st>>>(a);
     c->launches += 4;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(c->h_cl_block.p, d_block, block_bytes, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(c->h_cl_order.p, a.order, (size_t)cap * 4, cudaMemcpyDeviceToHost, st));
+    // two round trips: the sizes first, then exactly the records and array entries that exist
+    CUDA_TRY(cudaMemcpyAsync(c->h_cl_block.p, d_block, cbk::kTokenBlockHeader, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(c->h_cl_info.p, a.info, 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     const uint8_t* hb = c->h_cl_block.as<uint8_t>();
@@ -378,6 +381,16 @@ int cluster_block(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t
     if (flags) *flags = hdr[1];
     if (hdr[1] || hdr[0] > cap || hdr[0] == 0) return 0;                       // overflowed / empty: the caller looks at count and flags
     const uint32_t n = c->h_cl_info.as<uint32_t>()[0], total = c->h_cl_info.as<uint32_t>()[1], n_str = c->h_cl_info.as<uint32_t>()[2];
+    if (int r = c->h_cl_keys.reserve((size_t)total * 4 + 16)) return r;
+    if (int r = c->h_cl_first.reserve((size_t)total * 4 + 16)) return r;
+    CUDA_TRY(cudaMemcpyAsync(c->h_cl_block.as<uint8_t>() + cbk::kTokenBlockHeader, (const uint8_t*)d_block + cbk::kTokenBlockHeader,
+                             (size_t)hdr[0] * stride, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(c->h_cl_order.p, a.order, (size_t)hdr[0] * 4, cudaMemcpyDeviceToHost, st));
+    if (total && n == hdr[0] && n <= kClusterDeviceMax) {
+        CUDA_TRY(cudaMemcpyAsync(c->h_cl_keys.p, a.keys, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(c->h_cl_first.p, a.first, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
     std::vector<std::string_view> drs;
     bool device_ok = n == hdr[0] && n <= kClusterDeviceMax;
     if (device_ok) {
@@ -395,16 +408,44 @@ int cluster_block(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t
         *patterns = cbh::non_redundant_set(cbh::block_views(hb, cap, stride, nullptr, nullptr), (int)kmer_clust, nullptr, nullptr);
         return 0;
     }
-    if (int r = c->h_cl_keys.reserve((size_t)total * 4 + 16)) return r;
-    if (int r = c->h_cl_first.reserve((size_t)total * 4 + 16)) return r;
-    if (total) {
-        CUDA_TRY(cudaMemcpyAsync(c->h_cl_keys.p, a.keys, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(c->h_cl_first.p, a.first, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-    }
-    cbh::ClusterPre pre{c->h_cl_keys.as<uint32_t>(), c->h_cl_first.as<uint32_t>(), total, n_str};
+    cbh::ClusterPre pre{c->h_cl_keys.as<uint32_t>(), c->h_cl_first.as<uint32_t>(), total, n_str, nullptr};
+    // pass D on the device as well: the host walk (pass C) sends the group of every DR, the kernels send back the flags
+    size_t ctab = 1024;
+    while (ctab < 2 * (size_t)cap) ctab <<= 1;
+    int reduce_rc = 0;
+    // (measured: no faster than the threaded host reduction at 6.5 k .. 16 k variants -- the chains are walked by pointer
+    // chasing -- so it is opt-in: CRASS_B200_CLUSTER=device-reduce)
+    const char* dsel = getenv("CRASS_B200_CLUSTER");
+    if (dsel && !strcmp(dsel, "device-reduce")) pre.device_reduce = [&](const int* group_of, size_t n_dr, uint8_t* dead) -> bool {
+        if (n_dr != n) return false;
+        auto body = [&]() -> int {
+            if (int r = c->d_cl_group.reserve((size_t)cap * 4)) return r;
+            if (int r = c->d_cl_chain.reserve(ctab * 12)) return r;
+            if (int r = c->d_cl_next.reserve((size_t)cap * 4)) return r;
+            if (int r = c->d_cl_odd.reserve((size_t)cap * 4)) return r;
+            if (int r = c->d_cl_dead.reserve((size_t)cap + 16)) return r;
+            if (int r = c->h_cl_group.reserve((size_t)cap * 4)) return r;
+            if (int r = c->h_cl_dead.reserve((size_t)cap + 16)) return r;
+            memcpy(c->h_cl_group.p, group_of, (size_t)n * 4);
+            cbk::ReduceArrays ra{a, c->d_cl_group.as<uint32_t>(), c->d_cl_chain.as<unsigned long long>(),
+                                 (uint32_t*)(c->d_cl_chain.as<unsigned long long>() + ctab), (uint32_t)(ctab - 1),
+                                 c->d_cl_next.as<uint32_t>(), c->d_cl_odd.as<uint32_t>(), c->d_cl_dead.as<uint8_t>()};
+            CUDA_TRY(cudaMemcpyAsync(c->d_cl_group.p, c->h_cl_group.p, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemsetAsync(c->d_cl_chain.p, 0xFF, ctab * 12, st));
+            cbk::k_cl_chain<<<(n + 127) / 128, 128, 0, st>>>(ra);
+            cbk::k_cl_reduce<<<(n + 127) / 128, 128, 0, st>>>(ra);
+            c->launches += 2;
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(c->h_cl_dead.p, ra.dead, n, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            memcpy(dead, c->h_cl_dead.p, n);
+            return 0;
+        };
+        reduce_rc = body();
+        return reduce_rc == 0;
+    };
     *patterns = cbh::non_redundant_set(drs, (int)kmer_clust, nullptr, &pre);
-    return 0;
+    return reduce_rc;
 }
 }  // namespace
 extern "C" {

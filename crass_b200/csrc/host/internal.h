@@ -3,6 +3,7 @@
 #include <stdint.h>
 #include <stddef.h>
 
+#include <functional>
 #include <map>
 #include <string>
 #include <string_view>
@@ -81,6 +82,9 @@ struct ClusterPre {
     uint32_t* first;            // overwritten (folded into runs)
     size_t total;               // number of 11-mers
     uint32_t n_string_keys;     // how many keys are 0xFFFFFFFF
+    // optional: pass D elsewhere too.  Given the group of every DR (1-based), fills dead[t] = 1 for every DR that holds an
+    // earlier (shorter, or equally long with a smaller t) DR of its group on either strand; returns false to decline.
+    std::function<bool(const int* group_of, size_t n, uint8_t* dead)> device_reduce;
 };
 std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& drs, int min_count,
                                            std::vector<std::pair<int, int> >* groups, const ClusterPre* pre = nullptr);

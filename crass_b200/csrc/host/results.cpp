@@ -381,8 +381,11 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& 
     // pass C (one thread): the order-dependent greedy walk over the runs.  The reference bumps a group's tally once per
     // shared k-mer and tests it against min_count from the group's second hit on; a run of c k-mers of one group
     // therefore wins as soon as the tally it leaves behind is >= min_count (and >= 2 if it opened the tally).
+    std::vector<int> group_of;                                            // DR t -> group id (1-based)
+    std::vector<uint8_t> dead;                                            // pass D result when it ran on the GPU
+    bool use_dead = false;
     auto pass_c = [&]() {
-        std::vector<int> group_of(n_dr, 0);
+        group_of.assign(n_dr, 0);
         std::vector<std::pair<int, int> > counts;                         // (group, shared so far)
         for (size_t t = 0; t < n_dr; ++t) {
             counts.clear();
@@ -400,6 +403,8 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& 
             group_of[t] = group;
             members[group - 1].push_back((int)t + 2);
         }
+        // pass D may run on the GPU as well (K5, k_cl_reduce): it hands back one "dead" flag per DR
+        if (pre && pre->device_reduce) { dead.assign(n_dr, 0); use_dead = pre->device_reduce(group_of.data(), n_dr, dead.data()); }
         if (groups_out)
             for (size_t g = 0; g < members.size(); ++g)
                 for (int tok : members[g]) groups_out->push_back(std::make_pair(tok, (int)g + 1));
@@ -531,7 +536,14 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& 
         if (w == 0) { CB_NR_MARK("pass B2"); pass_c(); CB_NR_MARK("pass C"); }
         barrier.wait();
         HeadTable map, full;
-        for (size_t i; (i = next_group.fetch_add(1)) < schedule.size();) reduce_group(schedule[i], map, full);
+        for (size_t i; (i = next_group.fetch_add(1)) < schedule.size();) {
+            const size_t g = schedule[i];
+            if (!use_dead) { reduce_group(g, map, full); continue; }
+            std::vector<int> v;                                           // the group's survivors, shortest first (stable)
+            for (int tok : members[g]) if (!dead[(size_t)tok - 2] && !drs[(size_t)tok - 2].empty()) v.push_back(tok - 2);
+            std::stable_sort(v.begin(), v.end(), [&](int a, int b) { return drs[a].size() < drs[b].size(); });
+            for (int t : v) { survivors[g].emplace_back(drs[t]); survivors_rc[g].push_back(reverse_complement(survivors[g].back())); }
+        }
     };
     WorkerPool::instance().run(n_workers, worker);
     CB_NR_MARK("reduce");

@@ -318,6 +318,93 @@ k_cl_first(ClusterArrays a) {
         if (a.keys[q] != kClStr) a.first[q] = a.tab_val[a.first[q]];
 }
 
+// pass D (removeRedundantRepeats, WorkHorse.cpp:612-645): DR b is redundant when an earlier DR of its group -- shorter, or
+// equally long with a smaller token position -- is inside it on either strand.  (The reference only remembers survivors;
+// containment is transitive, so "any earlier DR" gives the same answer and needs no order of evaluation.)  A DR a inside
+// b shows its first 11-mer where it starts, its reverse complement shows the same canonical 11-mer where it ends: the
+// candidates for b come from chains keyed by (group, first key) and are confirmed on the bytes.  DRs without an integer
+// first key (another letter in the first window, or shorter than a k-mer) are few and are tried against every b.
+struct ReduceArrays {
+    ClusterArrays a;
+    const uint32_t* group;       // [n] 1-based group of DR t (from the host walk)
+    unsigned long long* ckey;    // chain table: (group << 32 | first key) -> head
+    uint32_t* chead;
+    uint32_t cmask;
+    uint32_t* next;              // [n] next DR with the same (group, first key)
+    uint32_t* odd;               // [n] DRs that are in no chain; info[3] = how many
+    uint8_t* dead;               // [n] out
+};
+
+__global__ void __launch_bounds__(128)
+k_cl_chain(ReduceArrays r) {
+    const uint32_t n = r.a.n();
+    const uint32_t t = blockIdx.x * 128 + threadIdx.x;
+    if (t >= n) return;
+    r.dead[t] = 0;
+    const uint32_t slot = r.a.order[t];
+    const uint32_t len = r.a.len_of(slot);
+    const uint32_t q = r.a.koff[t];
+    // a chain key must be the plain integer key of an all-A/C/G/T window: with another letter in it the canonical form of
+    // the reverse complement need not be the same (the complement table is not an involution, 'U' -> 'A' -> 'T')
+    bool acgt = len >= kClKmer;
+    for (uint32_t i = 0; acgt && i < kClKmer; ++i) acgt = cl_code(r.a.rec(slot)[2 + i]) >= 0;
+    if (!acgt) { r.odd[atomicAdd(&r.a.info[3], 1u)] = t; return; }
+    const unsigned long long k = ((unsigned long long)r.group[t] << 32) | r.a.keys[q];
+    uint32_t s = (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> 32) & r.cmask;
+    for (;;) {
+        const unsigned long long cur = atomicCAS(&r.ckey[s], ~0ull, k);
+        if (cur == ~0ull || cur == k) break;
+        s = (s + 1) & r.cmask;
+    }
+    r.next[t] = atomicExch(&r.chead[s], t);
+}
+
+__device__ __forceinline__ bool cl_inside(const uint8_t* b, uint32_t at, const uint8_t* a, uint32_t la, bool revcomp) {
+    if (!revcomp) { for (uint32_t i = 0; i < la; ++i) if (b[at + i] != a[i]) return false; }
+    else { for (uint32_t i = 0; i < la; ++i) if (b[at + i] != c_comp_tab[a[la - 1 - i] & 127]) return false; }
+    return true;
+}
+
+__global__ void __launch_bounds__(128)
+k_cl_reduce(ReduceArrays r) {
+    const uint32_t n = r.a.n();
+    const uint32_t tb = blockIdx.x * 128 + threadIdx.x;
+    if (tb >= n) return;
+    const uint32_t sb = r.a.order[tb];
+    const uint8_t* b = r.a.rec(sb) + 2;
+    const uint32_t lb = r.a.len_of(sb), g = r.group[tb];
+    const uint32_t q0 = r.a.koff[tb], nk = r.a.koff[tb + 1] - q0;
+    bool dead = false;
+    for (uint32_t p = 0; p < nk && !dead; ++p) {
+        const uint32_t key = r.a.keys[q0 + p];
+        if (key == kClStr) continue;
+        const unsigned long long k = ((unsigned long long)g << 32) | key;
+        uint32_t s = (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> 32) & r.cmask;
+        while (r.ckey[s] != ~0ull && r.ckey[s] != k) s = (s + 1) & r.cmask;
+        if (r.ckey[s] == ~0ull) continue;
+        for (uint32_t ta = r.chead[s]; ta != 0xFFFFFFFFu && !dead; ta = r.next[ta]) {
+            if (ta == tb) continue;
+            const uint32_t sa = r.a.order[ta];
+            const uint32_t la = r.a.len_of(sa);
+            if (!(la < lb || (la == lb && ta < tb))) continue;                 // only earlier DRs count
+            const uint8_t* a = r.a.rec(sa) + 2;
+            if (p + la <= lb && cl_inside(b, p, a, la, false)) dead = true;
+            else if (p + kClKmer >= la && cl_inside(b, p + kClKmer - la, a, la, true)) dead = true;
+        }
+    }
+    const uint32_t n_odd = r.a.info[3];
+    for (uint32_t i = 0; i < n_odd && !dead; ++i) {
+        const uint32_t ta = r.odd[i];
+        if (ta == tb || r.group[ta] != g) continue;
+        const uint32_t sa = r.a.order[ta];
+        const uint32_t la = r.a.len_of(sa);
+        if (!(la < lb || (la == lb && ta < tb))) continue;
+        const uint8_t* a = r.a.rec(sa) + 2;
+        for (uint32_t at = 0; at + la <= lb && !dead; ++at) dead = cl_inside(b, at, a, la, false) || cl_inside(b, at, a, la, true);
+    }
+    r.dead[tb] = dead ? 1 : 0;
+}
+
 // ---- K4b/K4c in block form: the unit of the multi-GPU exchange -----------------------------------------------
 // A token block is 16 header bytes (u32 count, u32 flags, 8 spare) followed by `cap` records of `stride` bytes; the
 // last four bytes of a record hold its order key (read index of first appearance).  count may exceed cap: the block

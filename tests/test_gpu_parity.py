@@ -360,8 +360,9 @@ def test_clustering_passes_on_the_device_match_the_host(ctx, P):
     comp = bytes.maketrans(b"ACGT", b"TGCA")
     dev = torch.device("cuda", 0)
     stride = 64
-    for n_base, n_var, alphabet in ((1, 1, b"ACGT"), (3, 4, b"ACGT"), (40, 12, b"ACGTN"), (60, 10, b"ACGTUR"), (400, 16, b"ACGTN"), (1500, 28, b"ACGT")):
-        base = [fuzzgen.rand_seq(rng, rng.randint(23, 47)) for _k in range(n_base)]
+    for n_base, n_var, alphabet, lo, hi in ((1, 1, b"ACGT", 23, 47), (3, 4, b"ACGT", 23, 47), (40, 12, b"ACGTN", 23, 47), (60, 10, b"ACGTUR", 23, 47),
+                                           (30, 10, b"ACGTN", 6, 20), (25, 14, b"ACUR", 11, 30), (400, 16, b"ACGTN", 23, 47), (1500, 28, b"ACGT", 23, 47)):
+        base = [fuzzgen.rand_seq(rng, rng.randint(lo, hi)) for _k in range(n_base)]
         drs = []
         for b in base:
             for _k in range(n_var):
@@ -369,7 +370,7 @@ def test_clustering_passes_on_the_device_match_the_host(ctx, P):
                 a, e = rng.randint(0, 4), rng.randint(0, 4)
                 v = v[a:len(v) - e] if rng.random() < 0.5 else fuzzgen.rand_seq(rng, a) + v + fuzzgen.rand_seq(rng, e)
                 drs.append(min(v, v.translate(comp)[::-1])[:58])
-        uniq = list(dict.fromkeys(drs))
+        uniq = [u for u in dict.fromkeys(drs) if u]
         rng.shuffle(uniq)                                                 # token order = order of `uniq`
         keys = sorted(rng.sample(range(50_000_000), len(uniq)))
         slots = list(range(len(uniq)))
@@ -387,7 +388,12 @@ def test_clustering_passes_on_the_device_match_the_host(ctx, P):
         d_blk = torch.from_numpy(blk).to(dev)
         got, cnt, fl = ctx.cluster_block_patterns_dev(d_blk, cap, stride, 6)
         assert (cnt, fl) == (cnt_h, fl_h) == (len(uniq), 0)
-        assert got == want, (n_base, n_var, alphabet)
+        assert got == want, (n_base, n_var, alphabet, lo, hi)
+        os.environ["CRASS_B200_CLUSTER"] = "device-reduce"                # ... and with the substring reduction on the device too
+        try:
+            assert ctx.cluster_block_patterns_dev(d_blk, cap, stride, 6)[0] == want
+        finally:
+            os.environ.pop("CRASS_B200_CLUSTER", None)
         ac, cnt2, fl2 = ctx.cluster_block_dev(d_blk, cap, stride, 6)
         assert ac is not None and ac.num_patterns == want.count(b"\n") and cnt2 == len(uniq)
         if len(uniq) < 3000:                                              # the oracle's clustering is quadratic
