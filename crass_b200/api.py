@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcrass_b200.so")
+LIB_PATH = os.environ.get("CRASS_B200_LIB") or os.path.join(_HERE, "libcrass_b200.so")   # override: an instrumented build
 
 
 class CrassB200Error(RuntimeError):

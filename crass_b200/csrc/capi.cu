@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <sstream>
 #include <string>
 #include <unordered_set>
@@ -113,8 +114,8 @@ struct crass_b200_ctx {
     DevBuf d_cand_counts;                // K1 fast path: sizes of the two candidate lists
     // K5 (clustering passes A/B on the token block): device arrays and their pinned host mirrors
     DevBuf d_cl_order, d_cl_koff, d_cl_keys, d_cl_first, d_cl_tab, d_cl_info;
-    DevBuf d_cl_group, d_cl_chain, d_cl_next, d_cl_odd, d_cl_dead;
-    PinnedBuf h_cl_block, h_cl_order, h_cl_keys, h_cl_first, h_cl_info, h_cl_group, h_cl_dead;
+    DevBuf d_cl_group, d_cl_chain, d_cl_next, d_cl_odd, d_cl_dead, d_cl_str;
+    PinnedBuf h_cl_block, h_cl_order, h_cl_keys, h_cl_first, h_cl_info, h_cl_group, h_cl_dead, h_cl_str;
     PinnedBuf h_ac_stage;                // matcher tables on their way to the device
     // the 2-bit stream of the batch, written by k_dr_filter and read by k_ac_filter_packed (crass_b200_ctx_keep_packed)
     DevBuf d_packed;
@@ -193,10 +194,10 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
                       &c->d_ac_bitmap, &c->d_ac_keys, &c->d_ac_skeys, &c->d_ac_shead, &c->d_ac_pnext, &c->d_ac_poffs, &c->d_ac_pbytes,
                       &c->d_rank, &c->d_hits_sorted, &c->d_cand_counts, &c->d_packed,
                       &c->d_cl_order, &c->d_cl_koff, &c->d_cl_keys, &c->d_cl_first, &c->d_cl_tab, &c->d_cl_info,
-                      &c->d_cl_group, &c->d_cl_chain, &c->d_cl_next, &c->d_cl_odd, &c->d_cl_dead};
+                      &c->d_cl_group, &c->d_cl_chain, &c->d_cl_next, &c->d_cl_odd, &c->d_cl_dead, &c->d_cl_str};
     for (DevBuf* b : bufs) b->release();
     for (PinnedBuf* b : {&c->h_cl_block, &c->h_cl_order, &c->h_cl_keys, &c->h_cl_first, &c->h_cl_info, &c->h_ac_stage,
-                         &c->h_cl_group, &c->h_cl_dead}) b->release();
+                         &c->h_cl_group, &c->h_cl_dead, &c->h_cl_str}) b->release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -346,6 +347,15 @@ const uint32_t kClusterDeviceMax = 32768;            // the rank kernel is O(n^2
 int cluster_block(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t stride, uint32_t kmer_clust,
                   std::vector<std::string>* patterns, uint32_t* count, uint32_t* flags, cudaStream_t st) {
     patterns->clear();
+    // CRASS_B200_TRACE=1: stage times of this call on stderr
+    static const bool trace = getenv("CRASS_B200_TRACE") != nullptr;
+    auto t_mark = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "cluster_block: %-18s %.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_mark).count());
+        t_mark = now;
+    };
     const size_t block_bytes = cbk::kTokenBlockHeader + (size_t)cap * stride;
     const size_t max_kmers = (size_t)cap * (stride - 16);
     size_t tab = 1024;
@@ -356,12 +366,16 @@ int cluster_block(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t
     if (int r = c->d_cl_first.reserve(max_kmers * 4 + 16)) return r;
     if (int r = c->d_cl_tab.reserve(tab * 8)) return r;
     if (int r = c->d_cl_info.reserve(16)) return r;
+    const uint32_t kStrListCap = 16384;                                        // (DR, k-mer) pairs of string-keyed 11-mers listed by K5
+    if (int r = c->d_cl_str.reserve((size_t)kStrListCap * 8)) return r;
+    if (int r = c->h_cl_str.reserve((size_t)kStrListCap * 8)) return r;
     if (int r = c->h_cl_block.reserve(block_bytes)) return r;
     if (int r = c->h_cl_order.reserve((size_t)cap * 4)) return r;
     if (int r = c->h_cl_info.reserve(16)) return r;
     cbk::ClusterArrays a{(const uint8_t*)d_block, cap, stride, c->d_cl_order.as<uint32_t>(), c->d_cl_koff.as<uint32_t>(),
                          c->d_cl_keys.as<uint32_t>(), c->d_cl_first.as<uint32_t>(), c->d_cl_tab.as<uint32_t>(),
-                         c->d_cl_tab.as<uint32_t>() + tab, (uint32_t)(tab - 1), c->d_cl_info.as<uint32_t>()};
+                         c->d_cl_tab.as<uint32_t>() + tab, (uint32_t)(tab - 1), c->d_cl_info.as<uint32_t>(),
+                         c->d_cl_str.as<uint32_t>(), kStrListCap};
     CUDA_TRY(cudaMemsetAsync(c->d_cl_info.p, 0, 16, st));
     CUDA_TRY(cudaMemsetAsync(c->d_cl_tab.p, 0xFF, tab * 8, st));
     cbk::k_cl_rank<<<(cap + 256) / 256, 256, 0, st>>>(a);
@@ -374,6 +388,7 @@ int cluster_block(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t
     CUDA_TRY(cudaMemcpyAsync(c->h_cl_block.p, d_block, cbk::kTokenBlockHeader, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(c->h_cl_info.p, a.info, 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    mark("kernels + sizes");
     const uint8_t* hb = c->h_cl_block.as<uint8_t>();
     uint32_t hdr[2];
     memcpy(hdr, hb, sizeof hdr);
@@ -389,8 +404,10 @@ int cluster_block(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t
     if (total && n == hdr[0] && n <= kClusterDeviceMax) {
         CUDA_TRY(cudaMemcpyAsync(c->h_cl_keys.p, a.keys, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(c->h_cl_first.p, a.first, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+        if (n_str && n_str <= kStrListCap) CUDA_TRY(cudaMemcpyAsync(c->h_cl_str.p, a.str_tq, (size_t)n_str * 8, cudaMemcpyDeviceToHost, st));
     }
     CUDA_TRY(cudaStreamSynchronize(st));
+    mark("copies");
     std::vector<std::string_view> drs;
     bool device_ok = n == hdr[0] && n <= kClusterDeviceMax;
     if (device_ok) {
@@ -408,7 +425,8 @@ int cluster_block(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t
         *patterns = cbh::non_redundant_set(cbh::block_views(hb, cap, stride, nullptr, nullptr), (int)kmer_clust, nullptr, nullptr);
         return 0;
     }
-    cbh::ClusterPre pre{c->h_cl_keys.as<uint32_t>(), c->h_cl_first.as<uint32_t>(), total, n_str, nullptr};
+    cbh::ClusterPre pre{c->h_cl_keys.as<uint32_t>(), c->h_cl_first.as<uint32_t>(), total, n_str,
+                        n_str && n_str <= kStrListCap ? c->h_cl_str.as<uint32_t>() : nullptr, nullptr};
     // pass D on the device as well: the host walk (pass C) sends the group of every DR, the kernels send back the flags
     size_t ctab = 1024;
     while (ctab < 2 * (size_t)cap) ctab <<= 1;
@@ -444,7 +462,9 @@ int cluster_block(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t
         reduce_rc = body();
         return reduce_rc == 0;
     };
+    mark("views");
     *patterns = cbh::non_redundant_set(drs, (int)kmer_clust, nullptr, &pre);
+    mark("host passes");
     return reduce_rc;
 }
 }  // namespace

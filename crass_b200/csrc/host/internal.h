@@ -82,6 +82,7 @@ struct ClusterPre {
     uint32_t* first;            // overwritten (folded into runs)
     size_t total;               // number of 11-mers
     uint32_t n_string_keys;     // how many keys are 0xFFFFFFFF
+    const uint32_t* string_tq;  // optional: their (DR, k-mer index) pairs, n_string_keys of them in any order; NULL = scan keys[]
     // optional: pass D elsewhere too.  Given the group of every DR (1-based), fills dead[t] = 1 for every DR that holds an
     // earlier (shorter, or equally long with a smaller t) DR of its group on either strand; returns false to decline.
     std::function<bool(const int* group_of, size_t n, uint8_t* dead)> device_reduce;

@@ -517,7 +517,16 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& 
     };
     auto worker = [&](unsigned w) {
         if (pre) {                                                        // A and B came from the GPU: only list the string-keyed k-mers
-            if (pre->n_string_keys)
+            if (pre->n_string_keys && pre->string_tq) {                   // ... which the GPU may have listed already
+                if (w == 0) {
+                    for (uint32_t i = 0; i < pre->n_string_keys; ++i) {
+                        const uint32_t t = pre->string_tq[2 * i], q = pre->string_tq[2 * i + 1];
+                        if (t < n_dr && q >= koff[t] && q < koff[t + 1] && keys[q] == kStrKey) str_pos[0].push_back(std::make_pair(t, q));
+                    }
+                    std::sort(str_pos[0].begin(), str_pos[0].end());       // DR order, as the sequential map needs it
+                    any_str.store(true, std::memory_order_relaxed);
+                }
+            } else if (pre->n_string_keys)
                 for (size_t t = cut[w]; t < cut[w + 1]; ++t)
                     for (size_t q = koff[t]; q < koff[t + 1]; ++q)
                         if (keys[q] == kStrKey) { any_str.store(true, std::memory_order_relaxed); str_pos[w].push_back(std::make_pair((uint32_t)t, (uint32_t)q)); }

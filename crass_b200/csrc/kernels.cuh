@@ -222,6 +222,8 @@ struct ClusterArrays {
     uint32_t* tab_val;
     uint32_t tab_mask;
     uint32_t* info;              // [0] n, [1] total k-mers, [2] k-mers that need the string map
+    uint32_t* str_tq;            // (t, q) of the first str_cap of those, in no particular order
+    uint32_t str_cap;
     __device__ uint32_t n() const { return min(*reinterpret_cast<const uint32_t*>(block), cap); }
     __device__ const uint8_t* rec(uint32_t slot) const { return block + kTokenBlockHeader + (size_t)slot * stride; }
     __device__ uint32_t key_of(uint32_t slot) const { return *reinterpret_cast<const uint32_t*>(rec(slot) + stride - 4); }
@@ -295,7 +297,11 @@ k_cl_keys(ClusterArrays a) {
             if (acgt) key = k2;
         }
         a.keys[q] = key;
-        if (key == kClStr) { atomicAdd(&a.info[2], 1u); a.first[q] = kClStr; }
+        if (key == kClStr) {                                         // the host resolves these; tell it where they are
+            const uint32_t i = atomicAdd(&a.info[2], 1u);
+            if (i < a.str_cap) { a.str_tq[2 * i] = t; a.str_tq[2 * i + 1] = q; }
+            a.first[q] = kClStr;
+        }
         else {
             uint32_t s = (key * 0x9E3779B1u) & a.tab_mask;
             for (;;) {

@@ -56,6 +56,14 @@ def main():
     with open(args.out, "wb") as fh:
         fh.write(text)
     print("%d ranks -> %d distinct DRs, %d bytes" % (args.ranks, count, len(text)))
+    # what the root of an N-rank run does next: K5 + host passes on the merged block (CRASS_B200_TRACE=1 shows the stages)
+    import time
+    for _ in range(4):
+        t0 = time.perf_counter()
+        pats, cnt, fl = ctx.cluster_block_patterns_dev(merged, out_cap, TOK, 6, s.cuda_stream)
+        dt = time.perf_counter() - t0
+    assert pats == api.non_redundant_patterns(text, 6)
+    print("clustering of the merged block: %.3f ms, %d patterns" % (dt * 1e3, pats.count(b"\n")))
     ctx.close()
 
 
