@@ -38,7 +38,7 @@ def launch_table(path):
     tot_ours = sum(sum(v) for k, v in agg.items() if "cbk::" in k or k.startswith("k_") or "k_dr" in k or "k_ac" in k or "k_token" in k)
     out = ["| kernel | launches | total us | mean us | share of our kernels |", "|---|---|---|---|---|"]
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
-        ours = ("k_dr" in k) or ("k_ac" in k) or ("k_token" in k) or ("k_edit" in k)
+        ours = ("cbk::" in k) or ("k_dr" in k) or ("k_ac" in k) or ("k_token" in k) or ("k_edit" in k)
         name = k.split("(")[0][-70:]
         out.append("| %s%s | %d | %.1f | %.1f | %s |" % ("" if ours else "(torch) ", name, len(v), sum(v) / 1e3, sum(v) / len(v) / 1e3,
                                                          "%.3f" % (sum(v) / tot_ours) if ours and tot_ours else "-"))
