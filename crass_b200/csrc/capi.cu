@@ -378,9 +378,9 @@ int cluster_block(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t
                          c->d_cl_str.as<uint32_t>(), kStrListCap};
     CUDA_TRY(cudaMemsetAsync(c->d_cl_info.p, 0, 16, st));
     CUDA_TRY(cudaMemsetAsync(c->d_cl_tab.p, 0xFF, tab * 8, st));
-    cbk::k_cl_rank<<<(cap + 256) / 256, 256, 0, st>>>(a);
-    cbk::k_rank_scan<<<1, 1024, 0, st>>>(a.koff, cap + 1);
-    cbk::k_cl_keys<<<(cap + 127) / 128, 128, 0, st>>>(a);
+    cbk::k_cl_rank<<<(cap + cbk::kClRankThreads) / cbk::kClRankThreads, cbk::kClRankThreads, 0, st>>>(a);
+    cbk::k_rank_scan<<<1, 1024, 0, st>>>(a.koff, cap + 1, a.info);                  // info[0] = n, written by k_cl_rank
+    cbk::k_cl_keys<<<(cap * 32 + cbk::kClKeysThreads - 1) / cbk::kClKeysThreads, cbk::kClKeysThreads, 0, st>>>(a);
     cbk::k_cl_first<<<c->sm_count * 4, 256, 0, st>>>(a);
     c->launches += 4;
     CUDA_TRY(cudaGetLastError());

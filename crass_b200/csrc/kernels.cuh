@@ -155,7 +155,8 @@ k_rank_chunks(const uint8_t* __restrict__ found, uint32_t n_reads, uint32_t* __r
 }
 
 __global__ void __launch_bounds__(1024)
-k_rank_scan(uint32_t* __restrict__ chunk_count, uint32_t n_chunks) {                    // in place: counts -> exclusive prefix
+k_rank_scan(uint32_t* __restrict__ chunk_count, uint32_t n_chunks, const uint32_t* __restrict__ n_dev = nullptr) {   // in place: counts -> exclusive prefix
+    if (n_dev) n_chunks = min(n_chunks, *n_dev + 1u);                                 // only the part that is in use (+ the total)
     __shared__ uint32_t warp_sum[32];
     __shared__ uint32_t carry;
     if (threadIdx.x == 0) carry = 0;
@@ -231,24 +232,26 @@ struct ClusterArrays {
 };
 
 // token position of every record = number of records with a smaller key (keys are distinct: one token per first read)
-__global__ void __launch_bounds__(256)
+constexpr uint32_t kClRankThreads = 64;              // small CTAs: the O(n^2) loop is spread over n / 64 of them
+
+__global__ void __launch_bounds__(kClRankThreads)
 k_cl_rank(ClusterArrays a) {
-    __shared__ uint32_t tile[256];
+    __shared__ uint32_t tile[kClRankThreads];
     const uint32_t n = a.n();
-    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
-    if (blockIdx.x * 256 >= n) {                                     // CTAs past the list only clear their part of koff
+    const uint32_t i = blockIdx.x * kClRankThreads + threadIdx.x;
+    if (blockIdx.x * kClRankThreads >= n) {                          // CTAs past the list only clear their part of koff
         if (i <= a.cap) a.koff[i] = 0;
         if (i == 0) a.info[0] = n;
         return;
     }
     const uint32_t mine = i < n ? a.key_of(i) : 0u;
     uint32_t rank = 0;
-    for (uint32_t j0 = 0; j0 < n; j0 += 256) {
+    for (uint32_t j0 = 0; j0 < n; j0 += kClRankThreads) {
         __syncthreads();
-        tile[threadIdx.x] = j0 + threadIdx.x < n ? a.key_of(j0 + threadIdx.x) : 0xFFFFFFFFu;
+        tile[threadIdx.x] = j0 + threadIdx.x < n ? a.key_of(j0 + threadIdx.x) : 0xFFFFFFFFu;   // padding never counts
         __syncthreads();
-        const uint32_t m = min(256u, n - j0);
-        for (uint32_t j = 0; j < m; ++j) rank += tile[j] < mine ? 1u : 0u;
+#pragma unroll 16
+        for (uint32_t j = 0; j < kClRankThreads; ++j) rank += tile[j] < mine ? 1u : 0u;
     }
     if (i < n) {
         a.order[rank] = i;
@@ -260,29 +263,32 @@ k_cl_rank(ClusterArrays a) {
     if (i == 0) a.info[0] = n;
 }
 
-// pass A + B: keys of DR t and the hash table key -> min t
-__global__ void __launch_bounds__(128)
+// pass A + B: keys of DR t and the hash table key -> min t.  One warp per DR, one lane per 11-mer.
+constexpr uint32_t kClKeysThreads = 128;
+
+__global__ void __launch_bounds__(kClKeysThreads)
 k_cl_keys(ClusterArrays a) {
     const uint32_t n = a.n();
-    const uint32_t t = blockIdx.x * 128 + threadIdx.x;
-    if (t == 0) a.info[1] = a.koff[n];
+    const uint32_t t = (blockIdx.x * kClKeysThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (t == 0 && lane == 0) a.info[1] = a.koff[n];
     if (t >= n) return;
     const uint32_t slot = a.order[t];
     const uint8_t* dr = a.rec(slot) + 2;
-    const uint32_t len = a.len_of(slot);
-    uint32_t q = a.koff[t];
-    const uint32_t kmask = (1u << (2 * kClKmer)) - 1u;
-    uint32_t fw = 0, rc = 0;
-    int valid = 0;                                                   // trailing run of A/C/G/T bytes
-    for (uint32_t p = 0; p < len; ++p) {
-        const int c = cl_code(dr[p]);
-        if (c < 0) valid = 0;
-        else { valid++; fw = ((fw << 2) | (uint32_t)c) & kmask; rc = (rc >> 2) | ((uint32_t)(3 - c) << (2 * (kClKmer - 1))); }
-        if (p + 1 < kClKmer) continue;
+    const uint32_t q0 = a.koff[t], nk = a.koff[t + 1] - q0;
+    for (uint32_t p = lane; p < nk; p += 32) {
+        const uint8_t* k = dr + p;                                   // the window dr[p, p+11)
+        uint32_t fw = 0, rc = 0;
+        bool valid = true;
+#pragma unroll
+        for (uint32_t i = 0; i < kClKmer; ++i) {
+            const int c = cl_code(k[i]);
+            valid = valid && c >= 0;
+            fw = (fw << 2) | (uint32_t)(c & 3);
+            rc |= (uint32_t)((3 - c) & 3) << (2 * i);
+        }
         uint32_t key = kClStr;
-        if (valid >= (int)kClKmer) key = fw < rc ? fw : rc;
+        if (valid) key = fw < rc ? fw : rc;
         else {                                                       // another letter in the window: canonical form on the bytes
-            const uint8_t* k = dr + (p + 1 - kClKmer);
             int cmp = 0;                                             // k vs its reverse complement, as unsigned bytes
             for (uint32_t i = 0; i < kClKmer && !cmp; ++i) {
                 const uint8_t x = k[i], y = c_comp_tab[k[kClKmer - 1 - i] & 127];
@@ -296,13 +302,13 @@ k_cl_keys(ClusterArrays a) {
             }
             if (acgt) key = k2;
         }
+        const uint32_t q = q0 + p;
         a.keys[q] = key;
         if (key == kClStr) {                                         // the host resolves these; tell it where they are
             const uint32_t i = atomicAdd(&a.info[2], 1u);
             if (i < a.str_cap) { a.str_tq[2 * i] = t; a.str_tq[2 * i + 1] = q; }
             a.first[q] = kClStr;
-        }
-        else {
+        } else {
             uint32_t s = (key * 0x9E3779B1u) & a.tab_mask;
             for (;;) {
                 const uint32_t cur = atomicCAS(&a.tab_key[s], kClStr, key);
@@ -312,7 +318,6 @@ k_cl_keys(ClusterArrays a) {
             atomicMin(&a.tab_val[s], t);
             a.first[q] = s;
         }
-        ++q;
     }
 }
 
