@@ -526,6 +526,18 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
     // Fast path: 2-bit seed filter over every read + exact search on the few candidates.  Needs the default
     // window geometry (8-mers every 8 bases, seed distances 49..97) and reads that fit a thread's registers.
     const char* force = getenv("CRASS_B200_K1");
+    // the 2-bit kernels recode every base anyway; on request they leave that stream in HBM for the singleton scan
+    auto keep_stream = [&](uint32_t** keep) -> int {
+        *keep = nullptr;
+        if (!(c->keep_packed_bases || c->packed_internal)) return 0;
+        const size_t words = (((size_t)n_reads * max_read_len) >> 4) + 256;          // n_bases <= n_reads * max_read_len
+        const bool grew = words * sizeof(uint32_t) > c->d_packed.cap;
+        if (int r = c->d_packed.reserve(words * sizeof(uint32_t))) return r;
+        if (grew) CUDA_TRY(cudaMemsetAsync(c->d_packed.p, 0, c->d_packed.cap, st));       // look-ahead words past the batch are defined
+        *keep = c->d_packed.as<uint32_t>();
+        c->packed_src = d_bases; c->packed_reads = n_reads; c->packed_valid = true;
+        return 0;
+    };
     const bool fast_ok = o.window == 8 && cb::window_skips(o) == 8 && o.low_dr + o.low_spacer == 49 &&
                          o.high_dr + o.high_spacer == 97 && max_read_len <= 304 && (((uintptr_t)d_bases) & 15) == 0;
     if (fast_ok && !(force && !strcmp(force, "generic"))) {
@@ -535,17 +547,8 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
         if (int r = c->d_cand_counts.reserve(4 * sizeof(uint32_t))) return r;     // [0] several flagged windows, [1] a single one
         uint32_t* cand_counts = c->d_cand_counts.as<uint32_t>();
         CUDA_TRY(cudaMemsetAsync(cand_counts, 0, 4 * sizeof(uint32_t), st));
-        // the filter recodes every base to 2 bits anyway; on request it leaves that stream in HBM for the singleton scan
         uint32_t* keep = nullptr;
-        c->packed_valid = false;
-        if (c->keep_packed_bases || c->packed_internal) {
-            const size_t words = (((size_t)n_reads * max_read_len) >> 4) + 256;      // n_bases <= n_reads * max_read_len
-            const bool grew = words * sizeof(uint32_t) > c->d_packed.cap;
-            if (int r = c->d_packed.reserve(words * sizeof(uint32_t))) return r;
-            if (grew) CUDA_TRY(cudaMemsetAsync(c->d_packed.p, 0, c->d_packed.cap, st));   // look-ahead words past the batch are defined
-            keep = c->d_packed.as<uint32_t>();
-            c->packed_src = d_bases; c->packed_reads = n_reads; c->packed_valid = true;
-        }
+        if (int r = keep_stream(&keep)) return r;
         const uint32_t n_tiles = (n_reads + cbk::kFilterTile - 1) / cbk::kFilterTile;
         const int se = (int)max_read_len - 58;
         const int nwin = se < 0 ? 1 : se / 16 + 1;
@@ -583,8 +586,10 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
         const uint32_t want_blocks = (n_reads + cbk::kLongWarps - 1) / cbk::kLongWarps;
         const int blocks = (int)std::min<uint32_t>(want_blocks, (uint32_t)(c->sm_count * std::max(per_sm, 1)));
         if (int r = c->d_scratch.reserve((size_t)blocks * cbk::kLongWarps * 2 * cap * sizeof(uint32_t))) return r;
+        uint32_t* keep = nullptr;
+        if (int r = keep_stream(&keep)) return r;
         cbk::k_dr_long<<<blocks, cbk::kLongWarps * 32, smem, st>>>(d_bases, d_offsets, n_reads, o, d_found, sink, c->d_scratch.as<uint32_t>(), cap,
-                                                                   c->d_error.as<int>(), words);
+                                                                   c->d_error.as<int>(), words, keep);
         c->launches++;
         CUDA_TRY(cudaGetLastError());
         return 0;
@@ -923,12 +928,17 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         uint32_t* cand = c->d_cand.as<uint32_t>();
         cbk::QgramFilter q{c->d_ac_bitmap.as<uint32_t>(), c->d_ac_keys.as<uint32_t>(), ac->a.q_bits, ac->a.q_table_bits, ac->a.q_has_ones};
         const size_t smem = ((size_t)1 << ac->a.q_bits) / 8;
-        CUDA_TRY(cudaFuncSetAttribute(cbk::k_ac_filter_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const char* fsel = getenv("CRASS_B200_K2F");
+        const bool use_packed = c->packed_valid && c->packed_src == (const void*)d_bases && c->packed_reads == n_reads &&
+                                (c->keep_packed_bases || c->packed_internal) && !(fsel && !strcmp(fsel, "bytes"));
+        CUDA_TRY(cudaFuncSetAttribute(cbk::k_ac_filter_long<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(cbk::k_ac_filter_long<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 1;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbk::k_ac_filter_long, cbk::kAcLongThreads, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbk::k_ac_filter_long<false>, cbk::kAcLongThreads, smem));
         const uint32_t want_blocks = (n_reads + (cbk::kAcLongThreads / 32) - 1) / (cbk::kAcLongThreads / 32);
         const int blocks = (int)std::min<uint32_t>(want_blocks, (uint32_t)(c->sm_count * std::max(per_sm, 1)));
-        cbk::k_ac_filter_long<<<blocks, cbk::kAcLongThreads, smem, st>>>(d_bases, d_offsets, n_reads, q, d_skip, d_found, cand, d_counters);
+        if (use_packed) cbk::k_ac_filter_long<true><<<blocks, cbk::kAcLongThreads, smem, st>>>((const uint8_t*)c->d_packed.p, d_offsets, n_reads, q, d_skip, d_found, cand, d_counters);
+        else cbk::k_ac_filter_long<false><<<blocks, cbk::kAcLongThreads, smem, st>>>(d_bases, d_offsets, n_reads, q, d_skip, d_found, cand, d_counters);
         CUDA_TRY(cudaGetLastError());
         cbk::PatternStarts ps{c->d_ac_pbytes.as<uint8_t>(), c->d_ac_poffs.as<uint32_t>(), c->d_ac_skeys.as<uint32_t>(),
                               c->d_ac_shead.as<uint32_t>(), c->d_ac_pnext.as<uint32_t>(), ac->a.s_bits, ac->a.s_ones_head,

@@ -757,7 +757,7 @@ constexpr int kLongWarps = 4;
 __global__ void __launch_bounds__(kLongWarps * 32)
 k_dr_long(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads, Params o,
           uint8_t* __restrict__ found, HitSink sink, uint32_t* __restrict__ ss_scratch, uint32_t ss_cap, int* __restrict__ error_flag,
-          uint32_t words_per_warp) {
+          uint32_t words_per_warp, uint32_t* __restrict__ keep) {
     extern __shared__ uint32_t long_smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     uint32_t* P = long_smem + (size_t)warp * 2 * words_per_warp;      // packed, aligned to the 16-byte grid of the batch
@@ -770,7 +770,7 @@ k_dr_long(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offset
         const uint64_t b = offsets[r];
         const uint32_t L = (uint32_t)(offsets[r + 1] - b);
         const int se = cb::search_end(o, L);
-        if (se < 0) { if (lane == 0 && found) found[r] = 0; continue; }
+        if (se < 0 && !keep) { if (lane == 0 && found) found[r] = 0; continue; }       // too short for an array (but phase 2 may want its words)
         cbl::GSeq s{bases + b};
         const uint64_t a0 = b & ~(uint64_t)15;
         const uint32_t shb = (uint32_t)(b & 15u);
@@ -790,8 +790,10 @@ k_dr_long(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offset
                 }
             }
             P[v] = w;
+            if (keep && v < nvec) keep[(a0 >> 4) + v] = w;              // the batch-wide 2-bit stream for the singleton scan
         }
         __syncwarp();
+        if (se < 0) { if (lane == 0 && found) found[r] = 0; continue; }
         const uint32_t nW = (L + 15) >> 4;
         for (uint32_t k = lane; k < nW + 24; k += 32) S[k] = k < nW ? cb::funnel_r(P[k], P[k + 1], 2 * shb) : 0u;
         __syncwarp();
@@ -1071,6 +1073,7 @@ k_ac_filter_packed(const uint32_t* __restrict__ packed, const uint64_t* __restri
 // word with a shuffle and test the two read-aligned 16-mers that start inside their vector (offsets == read start mod 8).
 constexpr int kAcLongThreads = 256;
 
+template <bool PACKED>                               // PACKED: `bases` is the 2-bit stream of the batch (u32 words) instead of the bytes
 __global__ void __launch_bounds__(kAcLongThreads)
 k_ac_filter_long(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads, QgramFilter q,
                  const uint8_t* __restrict__ skip, uint8_t* __restrict__ found, uint32_t* __restrict__ cand_list,
@@ -1099,7 +1102,8 @@ k_ac_filter_long(const uint8_t* __restrict__ bases, const uint64_t* __restrict__
             uint32_t w = 0;
             if (v < nvec) {
                 const uint64_t at = a0 + 16ull * v;
-                if (at + 16 <= n_bases) {
+                if (PACKED) w = __ldg(reinterpret_cast<const uint32_t*>(bases) + (at >> 4));
+                else if (at + 16 <= n_bases) {
                     const uint4 x = ldg_stream128(bases + at);
                     w = cb::pack16(x.x, x.y, x.z, x.w);
                 } else {

@@ -409,7 +409,7 @@ def test_singleton_scan_on_the_kept_2bit_stream(ctx, P):
     """Phase 2 of a resident batch reads the 2-bit stream phase 1's filter left in HBM (k_ac_filter_packed); the hits must be
     those of the byte-reading filter and of the oracle, for every read-length bucket and with odd bytes in the reads."""
     rng = random.Random(108)
-    for max_len in (100, 150, 250, 300):
+    for max_len in (100, 150, 250, 300, 1500):                            # 1500: the warp-per-read kernels of the long path
         pool_drs = [fuzzgen.rand_seq(rng, rng.randint(24, 40)) for _ in range(8)]
         reads = [fuzzgen.planted_read(rng, rng.randint(max(60, max_len - 50), max_len), dr=rng.choice(pool_drs), sub_rate=rng.choice([0, 0.01]))
                  for _ in range(3000)]

@@ -41,6 +41,7 @@ def main():
     d_bases = torch.from_numpy(bases).to(dev)
     d_offsets = torch.from_numpy(offsets.astype(np.int64)).to(dev)
     ctx = cb.Context(0)
+    ctx.keep_packed(os.environ.get("CRASS_B200_K2F", "") != "bytes")    # K2 reads the 2-bit stream K1 leaves behind
     params = cb.Params()
     hits_cap, pool_cap = n + 1024, 64 * n + 4096
     d_found = torch.empty(n, dtype=torch.uint8, device=dev)
