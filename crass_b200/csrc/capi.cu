@@ -160,7 +160,8 @@ extern "C" {
 const char* crass_b200_last_error(void) { return cbh::last_error_cstr(); }
 int crass_b200_abi_version(void) { return CRASS_B200_ABI_VERSION; }
 const char* crass_b200_build_info(void) {
-    return "crass_b200 hot path; CUDA " CB_STR(CUDART_VERSION) "; sm_100a; kernels: dr_filter+dr_exact_packed (2-bit), ac_filter(q-gram)+ac_scan_list, dr_search_generic, ac_scan_generic, edit_distance";
+    return "crass_b200 hot path; CUDA " CB_STR(CUDART_VERSION) "; sm_100a; kernels: K1 dr_filter (2-bit, TMA) + dr_exact_packed, dr_long; K2 ac_filter[_packed|_long] (16-mer q-gram) + ac_verify_warp; "
+           "K4 tokens, K4b/K4c token blocks, K5 clustering passes, hit ordering; generic dr_search / ac_scan; edit_distance";
 }
 int crass_b200_device_count(void) { return probe_devices(); }
 
