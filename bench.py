@@ -212,6 +212,7 @@ def main():
         host_threads = min(8, cores)
     else:
         host_threads = max(2, min(16, cores - 2 * local_world)) if rank == 0 else 2
+    threads_given = "CRASS_B200_HOST_THREADS" in os.environ
     os.environ.setdefault("CRASS_B200_HOST_THREADS", str(host_threads))
     ctx = cb.Context(local_rank)
     ctx.keep_packed(True)                                # K2 reads the 2-bit stream K1's filter leaves in HBM (same, unchanged batch)
@@ -350,6 +351,9 @@ def main():
         sampler.start()
     ms_total = timed(lambda: step_resident(True), args.steps)
     launches = ctx.launch_count - launches0
+    # in the host-buffer path every rank clusters the merged list itself: share the cores evenly again
+    if not threads_given:
+        os.environ["CRASS_B200_HOST_THREADS"] = str(max(1, min(8, cores // max(local_world, 1))))
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     d2h = [0]
