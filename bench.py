@@ -6,8 +6,10 @@
 Workload (config.workload = "config2"): BASELINE.json configs[1], synthetic 10M x 150 bp Illumina reads with 50 planted
 CRISPR DR types per GPU (weak scaling: every rank scans its own 10M-read shard; configs[3] is the same recipe sharded).
 A "step" is one pass of the hot path over the shard:
-    K1 direct-repeat search (+K4 tokens) -> K4b distinct-token block [-> NCCL all-gather -> K4c merge when N>1] -> DR list
-    to host -> createNonRedundantSet + matcher build + upload -> K2 singleton scan -> both hit lists to host, read order.
+    K1 direct-repeat search (+K4 tokens, hit ordering) -> K4b distinct-token block [-> NCCL all-gather -> K4c merge on rank 0
+    when N>1] -> K5 clustering passes on the GPU + order-dependent passes on the host = createNonRedundantSet [-> NCCL
+    broadcast of the pattern set when N>1] -> matcher build + upload -> K2 singleton scan (on the 2-bit stream K1 left in
+    HBM) -> both hit lists to pinned host memory in read order.
 `value`  : reads/s with the batch already resident in HBM (device timed with CUDA events, max over ranks).
 `e2e`    : the same pass through the host-buffer C-ABI (crass_b200_batch_upload / _dr_search_resident / _ac_scan_resident
            + replay into the ReadMap mirror), pinned host input copied H2D and hit records copied D2H inside the timed region.

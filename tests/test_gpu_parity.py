@@ -361,7 +361,8 @@ def test_clustering_passes_on_the_device_match_the_host(ctx, P):
     dev = torch.device("cuda", 0)
     stride = 64
     for n_base, n_var, alphabet, lo, hi in ((1, 1, b"ACGT", 23, 47), (3, 4, b"ACGT", 23, 47), (40, 12, b"ACGTN", 23, 47), (60, 10, b"ACGTUR", 23, 47),
-                                           (30, 10, b"ACGTN", 6, 20), (25, 14, b"ACUR", 11, 30), (400, 16, b"ACGTN", 23, 47), (1500, 28, b"ACGT", 23, 47)):
+                                           (30, 10, b"ACGTN", 6, 20), (25, 14, b"ACUR", 11, 30), (400, 16, b"ACGTN", 23, 47), (1500, 28, b"ACGT", 23, 47),
+                                           (2200, 16, b"ACGT", 23, 47)):          # the last one is past the device limit (32768): host passes
         base = [fuzzgen.rand_seq(rng, rng.randint(lo, hi)) for _k in range(n_base)]
         drs = []
         for b in base:
@@ -421,6 +422,8 @@ def test_singleton_scan_on_the_kept_2bit_stream(ctx, P):
         hits, pool, _ = ctx.dr_search_resident(cb.Params())
         pats = api.non_redundant_list(ctx.last_dr_list(), 6)
         assert len(pats) >= 8
+        if max_len == 250:                                                # enough 16-mers for the 128 KB bitmap (one CTA per SM)
+            pats += fuzzgen.dr_like_patterns(rng, 7000)
         ac = cb.Automaton(pats)
         got = {}
         for mode in ("packed", "bytes"):
