@@ -385,6 +385,7 @@ int cluster_block(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t
     cbk::k_cl_first<<<c->sm_count * 4, 256, 0, st>>>(a);
     c->launches += 4;
     CUDA_TRY(cudaGetLastError());
+    cbh::prewake_cluster_workers(1000);                        // the host passes start in a few hundred microseconds
     // two round trips: the sizes first, then exactly the records and array entries that exist
     CUDA_TRY(cudaMemcpyAsync(c->h_cl_block.p, d_block, cbk::kTokenBlockHeader, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(c->h_cl_info.p, a.info, 16, cudaMemcpyDeviceToHost, st));

@@ -89,6 +89,8 @@ struct ClusterPre {
 };
 std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& drs, int min_count,
                                            std::vector<std::pair<int, int> >* groups, const ClusterPre* pre = nullptr);
+// wakes the helper threads of non_redundant_set ahead of a call that is about to come (they poll for it for spin_us)
+void prewake_cluster_workers(unsigned spin_us);
 // the DR tokens of a host copy of a token block (include/crass_b200.h) as views into it, in first-appearance order
 std::vector<std::string_view> block_views(const void* block, uint32_t cap, uint32_t stride, uint32_t* count, uint32_t* flags);
 std::string dump_results(Results& r, int max_read_len);

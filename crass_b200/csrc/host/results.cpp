@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -161,10 +162,23 @@ public:
             while (threads_.size() < n - 1) { const unsigned id = (unsigned)threads_.size(); threads_.emplace_back([this, id]() { loop(id); }); }
             job_ = &job; n_active_ = n - 1; pending_ = n - 1; ++generation_;
         }
+        posted_.store(generation_, std::memory_order_release);
         wake_.notify_all();
         job(0);
         std::unique_lock<std::mutex> l(m_);
         done_.wait(l, [this]() { return pending_ == 0; });
+    }
+    // A caller that knows a parallel region is coming within the next fraction of a millisecond (the GPU is still busy
+    // with the kernels that feed it) gets the helpers out of their sleep early: they spin for a job until the deadline.
+    void prewake(unsigned n, unsigned spin_us) {
+        if (n <= 1) return;
+        {
+            std::lock_guard<std::mutex> l(m_);
+            while (threads_.size() < n - 1) { const unsigned id = (unsigned)threads_.size(); threads_.emplace_back([this, id]() { loop(id); }); }
+            spin_until_ = std::chrono::steady_clock::now() + std::chrono::microseconds(spin_us);
+            ++prewake_;
+        }
+        wake_.notify_all();
     }
     ~WorkerPool() {
         { std::lock_guard<std::mutex> l(m_); stop_ = true; }
@@ -173,14 +187,27 @@ public:
     }
 private:
     void loop(unsigned id) {
-        uint64_t seen = 0;
+        uint64_t seen = 0, seen_prewake = 0;
         for (;;) {
             const std::function<void(unsigned)>* job = nullptr;
             {
                 std::unique_lock<std::mutex> l(m_);
-                wake_.wait(l, [&]() { return stop_ || (generation_ != seen && id < n_active_); });
+                wake_.wait(l, [&]() { return stop_ || (generation_ != seen && id < n_active_) || prewake_ != seen_prewake; });
                 if (stop_) return;
+                if (!(generation_ != seen && id < n_active_)) {          // woken ahead of a job: poll for it without the lock
+                    seen_prewake = prewake_;
+                    const auto until = spin_until_;
+                    const uint64_t was = generation_;
+                    l.unlock();
+                    while (posted_.load(std::memory_order_acquire) == was && std::chrono::steady_clock::now() < until) {
+#if defined(__x86_64__)
+                        __builtin_ia32_pause();
+#endif
+                    }
+                    continue;                                            // back to the wait: a posted job passes it at once
+                }
                 seen = generation_;
+                seen_prewake = prewake_;
                 job = job_;
             }
             (*job)(id + 1);
@@ -193,9 +220,18 @@ private:
     std::vector<std::thread> threads_;
     const std::function<void(unsigned)>* job_ = nullptr;
     unsigned n_active_ = 0, pending_ = 0;
-    uint64_t generation_ = 0;
+    uint64_t generation_ = 0, prewake_ = 0;
+    std::atomic<uint64_t> posted_{0};                    // == generation_, readable without the lock
+    std::chrono::steady_clock::time_point spin_until_;
     bool stop_ = false;
 };
+
+unsigned cluster_workers(size_t total_kmers) {
+    unsigned n = 1;
+    if (total_kmers > (1u << 15)) n = std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("CRASS_B200_HOST_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 64) n = (unsigned)v; }
+    return n;
+}
 
 // small per-worker open-addressing map (k-mer key -> head of a chain of survivors) for the substring reduction
 struct HeadTable {
@@ -216,6 +252,8 @@ struct HeadTable {
     }
 };
 }  // namespace
+
+void prewake_cluster_workers(unsigned spin_us) { WorkerPool::instance().prewake(cluster_workers((size_t)1 << 20), spin_us); }
 
 std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, int min_count,
                                            std::vector<std::pair<int, int> >* groups_out) {
@@ -271,9 +309,7 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& 
     tsize = table_store.size();
     Slot* const table = table_store.data();             // plain pointers: TLS lookups are not free inside a shared object
 
-    unsigned n_workers = 1;
-    if (total_kmers > (1u << 15)) n_workers = std::min<unsigned>(8, std::max<unsigned>(1, std::thread::hardware_concurrency()));
-    if (const char* e = getenv("CRASS_B200_HOST_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 64) n_workers = (unsigned)v; }
+    const unsigned n_workers = cluster_workers(total_kmers);
     std::vector<size_t> cut(n_workers + 1, n_dr);                          // worker w owns DRs [cut[w], cut[w+1]): equal k-mer shares
     cut[0] = 0;
     for (unsigned w = 1; w < n_workers; ++w) {
