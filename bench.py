@@ -57,7 +57,28 @@ class ClockSampler(threading.Thread):
         self.max_mhz = None
         self._halt = threading.Event()
 
+    def run_nvml(self):
+        """NVML in-process: a sample costs microseconds, so even a 20 ms timed region gets several."""
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        while not self._halt.is_set():
+            self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            r = int(get_reasons(h))
+            for b, n in bits.items():
+                if r & b:
+                    self.reasons.add(n)
+            self._halt.wait(0.01)
+
     def run(self):
+        try:
+            self.run_nvml()
+            return
+        except Exception:
+            pass                                                       # no NVML binding: poll nvidia-smi instead
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self._halt.is_set():
