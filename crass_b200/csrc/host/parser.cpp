@@ -13,8 +13,12 @@
 //     batch stores, per record, the offset of the string the reference would have seen.
 //   * bytes are fetched as signed chars: 0xFF reads as EOF (-1) for the current loop only.
 #include <ctype.h>
+#include <fcntl.h>
 #include <stdio.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <stdexcept>
@@ -60,6 +64,41 @@ bool inflate_all(const char* path, std::vector<uint8_t>& buf) {
     return true;
 }
 
+// The file's bytes: a read-only mapping for plain files (no copy at all), the inflated stream otherwise (gzip members,
+// stdin).  zlib's transparent mode would read plain files too, but at a third of the speed of the parser behind it.
+struct Input {
+    std::vector<uint8_t> inflated;
+    const uint8_t* data = nullptr;
+    size_t size = 0;
+    void* map = nullptr;
+    size_t map_len = 0;
+    ~Input() { if (map) munmap(map, map_len); }
+    bool open(const char* path) {
+        if (strcmp(path, "-") != 0) {
+            const int fd = ::open(path, O_RDONLY);
+            if (fd < 0) return false;
+            struct stat st;
+            unsigned char magic[2] = {0, 0};
+            const bool regular = fstat(fd, &st) == 0 && S_ISREG(st.st_mode);
+            const ssize_t got = regular ? pread(fd, magic, 2, 0) : 0;
+            const bool gz = got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+            if (regular && !gz) {
+                if (st.st_size == 0) { ::close(fd); data = (const uint8_t*)""; size = 0; return true; }
+                void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+                ::close(fd);
+                if (m != MAP_FAILED) {
+                    madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+                    map = m; map_len = (size_t)st.st_size; data = (const uint8_t*)m; size = map_len;
+                    return true;
+                }
+            } else ::close(fd);
+        }
+        if (!inflate_all(path, inflated)) return false;
+        data = inflated.data(); size = inflated.size();
+        return true;
+    }
+};
+
 struct Cursor {
     const uint8_t* p; size_t n, pos;
     int getc() { return pos < n ? (int)(signed char)p[pos++] : -1; }      // ks_getc (kseq.cpp:55-69)
@@ -67,6 +106,13 @@ struct Cursor {
 
 inline bool c_isspace(uint8_t c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
 inline bool c_isgraph(int c) { return c > 32 && c < 127; }
+
+// bytes a sequence loop appends without a second look: isgraph() and none of '>', '+', '@'
+struct PlainTab {
+    bool t[256];
+    PlainTab() { for (int i = 0; i < 256; ++i) t[i] = c_isgraph(i) && i != '>' && i != '+' && i != '@'; }
+};
+const PlainTab kPlain;
 
 // ks_getuntil (kseq.cpp:71-147); delimiter 0 == any whitespace.  Returns false when already at EOF
 // (the reference returns -1 and leaves the target string untouched).
@@ -87,13 +133,13 @@ bool get_until(Cursor& c, int delimiter, size_t& b, size_t& e, int& dret) {
 }  // namespace
 
 int parse_file(const char* path, Batch** out) {
-    std::vector<uint8_t> buf;
-    if (!inflate_all(path, buf)) return fail(CRASS_B200_EIO, std::string("cannot open ") + path);
+    Input in;
+    if (!in.open(path)) return fail(CRASS_B200_EIO, std::string("cannot open ") + path);
     Batch* B = new Batch();
     try {
         B->offsets.push_back(0);
-        B->reserve_bases(buf.size() + 16);
-        Cursor c{buf.data(), buf.size(), 0};
+        B->reserve_bases(in.size + 16);
+        Cursor c{in.data, in.size, 0};
         int last_char = 0;
         int64_t cur_comment = -1, cur_qual = -1;
         uint64_t nb = 0;
@@ -112,14 +158,21 @@ int parse_file(const char* path, Batch** out) {
                 size_t cb, ce; int d2;
                 if (get_until(c, '\n', cb, ce, d2)) {
                     cur_comment = (int64_t)B->text_pool.size();
-                    B->text_pool.insert(B->text_pool.end(), (const char*)buf.data() + cb, (const char*)buf.data() + ce);
+                    B->text_pool.insert(B->text_pool.end(), (const char*)in.data + cb, (const char*)in.data + ce);
                     B->text_pool.push_back(0);
                 }
             }
             const uint64_t seq_b = nb;
             uint8_t* dst = B->bases;
-            while ((ch = c.getc()) != -1 && ch != '>' && ch != '+' && ch != '@') {
-                if (c_isgraph(ch)) dst[nb++] = (uint8_t)ch;
+            // kseq: while ((c = getc()) != -1 && c != '>' && c != '+' && c != '@') if (isgraph(c)) append(c);
+            // taken in runs: bytes that are isgraph and none of the three terminators are copied in bulk, every other
+            // byte is looked at on its own (0xFF reads as -1 and ends the loop like the others)
+            for (;;) {
+                size_t i = c.pos;
+                while (i < c.n && kPlain.t[c.p[i]]) ++i;
+                if (i > c.pos) { memcpy(dst + nb, c.p + c.pos, i - c.pos); nb += i - c.pos; c.pos = i; }
+                ch = c.getc();
+                if (ch == -1 || ch == '>' || ch == '+' || ch == '@') break;
             }
             if (ch == '>' || ch == '@') last_char = ch;
             const uint64_t L = nb - seq_b;
@@ -130,8 +183,17 @@ int parse_file(const char* path, Batch** out) {
                 else {
                     const int64_t q0 = (int64_t)B->text_pool.size();
                     uint64_t ql = 0;
+                    // kseq: while ((c = getc()) != -1 && qual.l < seq.l) if (c >= 33 && c <= 127) append(c);  -- the byte
+                    // is fetched before the length test, so one byte past the last quality character is consumed
                     while ((ch = c.getc()) != -1 && ql < L) {
-                        if (ch >= 33 && ch <= 127) { B->text_pool.push_back((char)ch); ++ql; }
+                        if (ch < 33) continue;                             // (signed) also skips bytes >= 0x80
+                        size_t i = c.pos;                                  // the rest of this run of quality characters
+                        const size_t lim = c.pos + (size_t)(L - ql - 1) < c.n ? c.pos + (size_t)(L - ql - 1) : c.n;
+                        while (i < lim && c.p[i] >= 33 && c.p[i] <= 127) ++i;
+                        B->text_pool.push_back((char)ch);
+                        B->text_pool.insert(B->text_pool.end(), (const char*)c.p + c.pos, (const char*)c.p + i);
+                        ql += 1 + (i - c.pos);
+                        c.pos = i;
                     }
                     B->text_pool.push_back(0);
                     cur_qual = q0;
@@ -141,7 +203,7 @@ int parse_file(const char* path, Batch** out) {
             }
             if (!emit) { nb = seq_b; break; }
             B->name_off.push_back(B->name_pool.size());
-            B->name_pool.insert(B->name_pool.end(), (const char*)buf.data() + name_b, (const char*)buf.data() + name_e);
+            B->name_pool.insert(B->name_pool.end(), (const char*)in.data + name_b, (const char*)in.data + name_e);
             B->name_pool.push_back(0);
             B->comment_off.push_back(cur_comment);
             B->qual_off.push_back(cur_qual);
