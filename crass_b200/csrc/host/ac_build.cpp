@@ -9,8 +9,11 @@
 //      * q-gram filter: every occurrence [a, a+len) of a pattern contains the read-aligned 16-mer that starts at
 //        8*ceil(a/8) (8i <= a+7 and 8i+16 <= a+23 <= a+len), so a read can only match if one of its 16-mers at
 //        offsets 0, 8, 16, ... is a 16-mer of some pattern.  16-mers are 2-bit codes ((byte>>1)&3: equal bytes
-//        give equal codes, the test can only over-report).  Two levels: a 2^19/2^20-bit bitmap staged in shared
-//        memory, and the exact open-addressing key table in global memory probed on bitmap hits.
+//        give equal codes, the test can only over-report).  That 16-mer starts at pattern offset 8*ceil(a/8) - a,
+//        i.e. at one of the offsets 0..7, so only those eight 16-mers of every pattern are keys (not all len-15 of
+//        them: 2.5x fewer keys, and the share of reads that go to the key table falls with them).  Two levels: a
+//        2^19/2^20-bit bitmap staged in shared memory, and the exact open-addressing key table in global memory
+//        probed on bitmap hits.
 //      * start table: first 16-mer of every pattern -> chain of the patterns that begin with it.  The candidate
 //        kernel slides over the read, looks every 16-mer up and verifies the chained patterns byte by byte; the
 //        earliest end (longest pattern on ties) over all verified occurrences is exactly acism's first callback.
@@ -20,6 +23,7 @@
 //          entry = table[state * stride + (sym - 1)]      next = entry & 0xFFFFFF, out_len = entry >> 24
 //      symv maps a byte to 1..n_syms-1, or 0 for bytes that occur in no pattern (those reset the scan to the root
 //      exactly like acism.c:36-42).  Built lazily (ensure_dfa) because it is the expensive part.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -42,14 +46,17 @@ static void build_filter_and_starts(Automaton* A) {
     const uint32_t* offs = A->p_offs.data();
     // the key table is sized for the number of 16-mer POSITIONS (an upper bound of the distinct codes), so that the
     // codes can be inserted in one pass without sorting
-    size_t positions = 0;
-    for (uint32_t i = 0; i < n; ++i) positions += (offs[i + 1] - offs[i]) - 15;
+    const size_t positions = (size_t)n * 8;                          // pattern offsets 0..7 (every pattern is >= 23 bytes)
     uint32_t tbits = 4;
     while (((size_t)1 << tbits) < positions * 2 + 2) ++tbits;
     A->q_table_bits = tbits;
     A->q_keys.assign((size_t)1 << tbits, 0xFFFFFFFFu);               // 0xFFFFFFFF = empty; the all-G 16-mer is kept in q_has_ones
     A->q_has_ones = 0;
-    A->q_bits = positions <= 60000 ? 19 : 20;                        // 64 KB or 128 KB of shared memory
+    // keys up to which the 64 KB bitmap is used (128 KB above).  Measured on config 5 (tools/bench_ac_sweep.py): even at
+    // 160 k keys (20 k patterns, 27 % of the bits set) two resident CTAs with 64 KB each beat one with 128 KB.
+    uint32_t small_max = 1000000;
+    if (const char* e = getenv("CRASS_B200_QGRAM_SMALL_MAX")) small_max = (uint32_t)strtoul(e, nullptr, 10);
+    A->q_bits = positions <= small_max ? 19 : 20;
     A->q_bitmap.assign((size_t)1 << (A->q_bits - 5), 0);
     uint32_t sbits = 4;
     while (((size_t)1 << sbits) < (size_t)n * 2 + 2) ++sbits;
@@ -66,6 +73,7 @@ static void build_filter_and_starts(Automaton* A) {
         for (uint32_t k = 0; k < len; ++k) {
             code = (code >> 2) | ((uint32_t)((bytes[offs[i] + k] >> 1) & 3) << 30);   // base k of the window in bits [2k,2k+2)
             if (k < 15) continue;
+            if (k > 22) break;                                       // window starts 0..7 only (see the header comment)
             const uint32_t h = qgram_hash(code, A->q_bits);
             A->q_bitmap[h >> 5] |= 1u << (h & 31);
             if (code == 0xFFFFFFFFu) { distinct += !A->q_has_ones; A->q_has_ones = 1; }
