@@ -43,6 +43,8 @@ class Hit(C.Structure):
 
 HIT_DTYPE = np.dtype([("read_index", "<u4"), ("n_ss", "<u4"), ("ss_offset", "<u4"), ("repeat_len", "<u4")])
 
+USS_JOB_DTYPE = np.dtype([("read", "<u4"), ("ss_offset", "<u4"), ("n_ss", "<u4"), ("front_offset", "<i4"), ("dr", "<u4"), ("out_offset", "<u4")])
+
 EINVAL = -1
 ENODEVICE = -2
 
@@ -90,6 +92,8 @@ def lib():
         "crass_b200_ac_scan_dev": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp]),
         "crass_b200_ac_scan": (C.c_int, [vp, vp, vp, vp, C.c_uint32, vp, vp, C.POINTER(vp), u32p, C.POINTER(vp), u32p]),
         "crass_b200_edit_distance_batch": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, vp, C.c_uint32, vp, vp]),
+        "crass_b200_update_start_stops_dev": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp]),
+        "crass_b200_update_start_stops": (C.c_int, [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, vp, C.c_uint32, vp, vp]),
         "crass_b200_scan_right": (C.c_int, [vp, cp, C.c_uint32, u32p, u32p, C.c_uint32, cp, C.c_uint32, C.c_uint32, C.c_uint32]),
         "crass_b200_extend_pre_repeat": (C.c_int, [vp, cp, C.c_uint32, u32p, C.c_uint32, C.c_uint32, C.c_uint32, u32p]),
         "crass_b200_qc_found_repeats": (C.c_int, [vp, cp, C.c_uint32, u32p, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_int)]),
@@ -568,6 +572,40 @@ class Context:
         sim = np.zeros(len(pairs), dtype=np.float32)
         _check(lib().crass_b200_edit_distance_batch(self.h, _np_ptr(data), len(data), *[_np_ptr(x) for x in arrs], len(pairs), _np_ptr(dist), _np_ptr(sim)))
         return dist, sim
+
+    @staticmethod
+    def pack_uss_jobs(jobs):
+        """jobs: (read index, start/stop list, front offset, DR index) -> (USS_JOB_DTYPE array, ss_in, ss_out capacity)"""
+        rec = np.zeros(len(jobs), dtype=USS_JOB_DTYPE)
+        ss_in = []
+        out_off = 0
+        for i, (read, ss, front, dr) in enumerate(jobs):
+            rec[i] = (read, len(ss_in), len(ss), front, dr, out_off)
+            ss_in.extend(ss)
+            out_off += len(ss) + 4
+        return rec, np.asarray(ss_in if ss_in else [0], dtype=np.uint32), max(out_off, 1)
+
+    def update_start_stops(self, bases, offsets, drs, jobs, low_spacer=26):
+        """K6, host buffers: ReadHolder::updateStartStops for every job -> [(status, new start/stop list)]."""
+        rec, ss_in, cap = self.pack_uss_jobs(jobs)
+        dr_bytes, dr_offs = pack_reads(drs if drs else [b""])
+        dr_offs = dr_offs.astype(np.uint32)
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        if not jobs:
+            return []
+        ss_out = np.zeros(cap, dtype=np.uint32)
+        n_out = np.zeros(max(len(jobs), 1), dtype=np.uint32)
+        status = np.zeros(max(len(jobs), 1), dtype=np.uint8)
+        _check(lib().crass_b200_update_start_stops(self.h, _np_ptr(bases), _np_ptr(offsets), len(offsets) - 1, _np_ptr(dr_bytes),
+                                                   _np_ptr(dr_offs), len(drs), _np_ptr(rec), len(jobs), _np_ptr(ss_in), len(ss_in),
+                                                   low_spacer, _np_ptr(ss_out), cap, _np_ptr(n_out), _np_ptr(status)))
+        return [(int(status[i]), ss_out[rec["out_offset"][i]: rec["out_offset"][i] + n_out[i]].tolist()) for i in range(len(jobs))]
+
+    def update_start_stops_dev(self, d_bases, d_offsets, d_dr_bytes, d_dr_offsets, d_jobs, n_jobs, d_ss_in, low_spacer, d_ss_out, d_n_out, d_status, stream=0):
+        _check(lib().crass_b200_update_start_stops_dev(self.h, d_bases.data_ptr(), d_offsets.data_ptr(), d_dr_bytes.data_ptr(), d_dr_offsets.data_ptr(),
+                                                       d_jobs.data_ptr(), n_jobs, d_ss_in.data_ptr(), low_spacer, d_ss_out.data_ptr(),
+                                                       d_n_out.data_ptr(), d_status.data_ptr(), stream))
 
     def scan_right(self, seq, ss, pattern, min_spacer, scan_range=24):
         cap = 2 * (len(seq) // 4 + 8)

@@ -161,7 +161,7 @@ const char* crass_b200_last_error(void) { return cbh::last_error_cstr(); }
 int crass_b200_abi_version(void) { return CRASS_B200_ABI_VERSION; }
 const char* crass_b200_build_info(void) {
     return "crass_b200 hot path; CUDA " CB_STR(CUDART_VERSION) "; sm_100a; kernels: K1 dr_filter (2-bit, TMA) + dr_exact_packed, dr_long; K2 ac_filter[_packed|_long] (16-mer q-gram) + ac_verify_warp; "
-           "K4 tokens, K4b/K4c token blocks, K5 clustering passes, hit ordering; generic dr_search / ac_scan; edit_distance";
+           "K4 tokens, K4b/K4c token blocks, K5 clustering passes, hit ordering; K6 update_start_stops (warp Smith-Waterman); generic dr_search / ac_scan; edit_distance";
 }
 int crass_b200_device_count(void) { return probe_devices(); }
 
@@ -1031,6 +1031,75 @@ int crass_b200_edit_distance_batch(crass_b200_ctx* c, const uint8_t* bytes, uint
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out_dist, m + 4 * idx_bytes, idx_bytes, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaMemcpyAsync(out_sim, m + 5 * idx_bytes, idx_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- K6: partial-DR recovery ----------------------------------------------------------------------------------
+int crass_b200_update_start_stops_dev(crass_b200_ctx* c, const uint8_t* d_bases, const uint64_t* d_offsets,
+                                      const uint8_t* d_dr_bytes, const uint32_t* d_dr_offsets,
+                                      const crass_b200_uss_job* d_jobs, uint32_t n_jobs, const uint32_t* d_ss_in,
+                                      uint32_t low_spacer, uint32_t* d_ss_out, uint32_t* d_n_out, uint8_t* d_status, void* stream) {
+    if (!c) return cbh::fail(CRASS_B200_EINVAL, "ctx is NULL");
+    if (!d_bases || !d_offsets || !d_dr_bytes || !d_dr_offsets || !d_jobs || !d_ss_in || !d_ss_out || !d_n_out || !d_status)
+        return cbh::fail(CRASS_B200_EINVAL, "update_start_stops: NULL argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n_jobs == 0) return 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const char* sel = getenv("CRASS_B200_K6");
+    if (sel && !strcmp(sel, "thread")) {                              // one thread per read: kept for comparison
+        const int blocks = (int)((n_jobs + cbk::kUssThreads - 1) / cbk::kUssThreads);
+        cbk::k_update_start_stops_thread<<<blocks, cbk::kUssThreads, 0, st>>>(d_bases, d_offsets, d_dr_bytes, d_dr_offsets, d_jobs, n_jobs,
+                                                                              d_ss_in, low_spacer, d_ss_out, d_n_out, d_status);
+    } else {                                                          // one warp per read
+        const int blocks = (int)((n_jobs + cbk::kUssWarps - 1) / cbk::kUssWarps);
+        cbk::k_update_start_stops<<<blocks, cbk::kUssWarps * 32, 0, st>>>(d_bases, d_offsets, d_dr_bytes, d_dr_offsets, d_jobs, n_jobs,
+                                                                          d_ss_in, low_spacer, d_ss_out, d_n_out, d_status);
+    }
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int crass_b200_update_start_stops(crass_b200_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
+                                  const uint8_t* dr_bytes, const uint32_t* dr_offsets, uint32_t n_drs,
+                                  const crass_b200_uss_job* jobs, uint32_t n_jobs, const uint32_t* ss_in, uint32_t n_ss_in,
+                                  uint32_t low_spacer, uint32_t* ss_out, uint32_t ss_out_cap, uint32_t* n_out, uint8_t* status) {
+    if (!c) return cbh::fail(CRASS_B200_EINVAL, "ctx is NULL");
+    if (n_jobs == 0) return 0;
+    if (!bases || !offsets || !dr_bytes || !dr_offsets || !jobs || !ss_in || !ss_out || !n_out || !status)
+        return cbh::fail(CRASS_B200_EINVAL, "update_start_stops: NULL argument");
+    for (uint32_t i = 0; i < n_jobs; ++i) {
+        const crass_b200_uss_job& j = jobs[i];
+        if (j.read >= n_reads || j.dr >= n_drs) return cbh::fail(CRASS_B200_EINVAL, "update_start_stops: job names a read or DR that does not exist");
+        if ((uint64_t)j.ss_offset + j.n_ss > n_ss_in) return cbh::fail(CRASS_B200_EINVAL, "update_start_stops: start/stop list out of range");
+        if ((uint64_t)j.out_offset + j.n_ss + 4 > ss_out_cap) return cbh::fail(CRASS_B200_EINVAL, "update_start_stops: ss_out too small (n_ss + 4 entries per job)");
+    }
+    CUDA_TRY(cudaSetDevice(c->device));
+    const uint64_t n_bases = offsets[n_reads];
+    const size_t dr_total = dr_offsets[n_drs];
+    auto up4 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t o_dro = up4(dr_total), o_jobs = o_dro + up4((size_t)(n_drs + 1) * 4), o_in = o_jobs + up4((size_t)n_jobs * sizeof(crass_b200_uss_job)),
+                 o_out = o_in + up4((size_t)n_ss_in * 4), o_n = o_out + up4((size_t)ss_out_cap * 4), o_st = o_n + up4((size_t)n_jobs * 4),
+                 total = o_st + up4(n_jobs);
+    if (int r = c->d_bases.reserve(n_bases + 64)) return r;
+    if (int r = c->d_offsets.reserve((size_t)(n_reads + 1) * sizeof(uint64_t))) return r;
+    if (int r = c->d_misc.reserve(total)) return r;
+    c->res_valid = false; c->res_found_valid = false; c->packed_valid = false;      // the context's batch buffers are reused
+    uint8_t* m = c->d_misc.as<uint8_t>();
+    CUDA_TRY(cudaMemcpyAsync(c->d_bases.p, bases, n_bases, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_offsets.p, offsets, (size_t)(n_reads + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(m, dr_bytes, dr_total, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(m + o_dro, dr_offsets, (size_t)(n_drs + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(m + o_jobs, jobs, (size_t)n_jobs * sizeof(crass_b200_uss_job), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(m + o_in, ss_in, (size_t)n_ss_in * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemsetAsync(m + o_out, 0, (size_t)ss_out_cap * 4, c->stream));
+    if (int r = crass_b200_update_start_stops_dev(c, c->d_bases.as<uint8_t>(), c->d_offsets.as<uint64_t>(), m, (const uint32_t*)(m + o_dro),
+                                                  (const crass_b200_uss_job*)(m + o_jobs), n_jobs, (const uint32_t*)(m + o_in), low_spacer,
+                                                  (uint32_t*)(m + o_out), (uint32_t*)(m + o_n), m + o_st, c->stream)) return r;
+    CUDA_TRY(cudaMemcpyAsync(ss_out, m + o_out, (size_t)ss_out_cap * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(n_out, m + o_n, (size_t)n_jobs * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(status, m + o_st, n_jobs, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }

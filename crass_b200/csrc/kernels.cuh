@@ -12,6 +12,8 @@
 #include "dr_core.cuh"
 #include "dr_filter.cuh"
 #include "dr_long.cuh"
+#include "sw_core.cuh"
+#include "sw_warp.cuh"
 
 namespace cbk {
 
@@ -1298,6 +1300,54 @@ k_edit_distance(const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ 
     GmemSeq s{bytes};
     out_dist[i] = cb::edit_distance(s, a_off[i], a_len[i], b_off[i], b_len[i]);
     out_sim[i] = cb::similarity(s, a_off[i], a_len[i], b_off[i], b_len[i]);
+}
+
+// ---- K6: partial-DR recovery (ReadHolder::updateStartStops + smithWaterman) ------------------------------------------
+// The jobs are the found reads of the DR groups (1-2 % of a metagenome, most of a CRISPR-rich sample).  Each read's
+// repeats are shifted to the group's consensus DR and two ends-free alignments look for a partial repeat in the flanks.
+// k_update_start_stops: one WARP per read, the alignment as a lane wavefront in registers (sw_warp.cuh).
+// k_update_start_stops_thread: one thread per read (sw_core.cuh, the source the CPU fuzz compiles); kept for comparison
+// (CRASS_B200_K6=thread): 4 of 32 lanes busy on the bench workload because the alignments differ in size from read to read.
+constexpr int kUssThreads = 64;
+constexpr int kUssWarps = 4;
+
+__global__ void __launch_bounds__(kUssThreads)
+k_update_start_stops_thread(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, const uint8_t* __restrict__ dr_bytes,
+                            const uint32_t* __restrict__ dr_offsets, const crass_b200_uss_job* __restrict__ jobs, uint32_t n_jobs,
+                            const uint32_t* __restrict__ ss_in, uint32_t low_spacer, uint32_t* __restrict__ ss_out,
+                            uint32_t* __restrict__ n_out, uint8_t* __restrict__ status) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_jobs) return;
+    const crass_b200_uss_job job = jobs[i];
+    const uint64_t lo = offsets[job.read];
+    const uint32_t L = (uint32_t)(offsets[job.read + 1] - lo);
+    GmemSeq s{bases + lo};
+    GmemSeq dr{dr_bytes + dr_offsets[job.dr]};
+    uint32_t n = 0;
+    status[i] = cb::update_start_stops(s, L, ss_in + job.ss_offset, job.n_ss, job.front_offset, dr,
+                                       dr_offsets[job.dr + 1] - dr_offsets[job.dr], low_spacer, ss_out + job.out_offset, n);
+    n_out[i] = n;
+}
+
+__global__ void __launch_bounds__(kUssWarps * 32)
+k_update_start_stops(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, const uint8_t* __restrict__ dr_bytes,
+                     const uint32_t* __restrict__ dr_offsets, const crass_b200_uss_job* __restrict__ jobs, uint32_t n_jobs,
+                     const uint32_t* __restrict__ ss_in, uint32_t low_spacer, uint32_t* __restrict__ ss_out,
+                     uint32_t* __restrict__ n_out, uint8_t* __restrict__ status) {
+    __shared__ uint8_t dr_sm[kUssWarps][cb::kMaxSwDr + 1];
+    const uint32_t w = threadIdx.x >> 5;
+    const uint32_t i = blockIdx.x * kUssWarps + w;
+    if (i >= n_jobs) return;                                         // whole warps leave together
+    const crass_b200_uss_job job = jobs[i];
+    const uint64_t lo = offsets[job.read];
+    const uint32_t L = (uint32_t)(offsets[job.read + 1] - lo);
+    GmemSeq s{bases + lo};
+    GmemSeq dr{dr_bytes + dr_offsets[job.dr]};
+    uint32_t n = 0;
+    const uint8_t st = cbw::update_start_stops_warp(s, L, ss_in + job.ss_offset, job.n_ss, job.front_offset, dr,
+                                                    dr_offsets[job.dr + 1] - dr_offsets[job.dr], low_spacer, dr_sm[w],
+                                                    ss_out + job.out_offset, n);
+    if ((threadIdx.x & 31u) == 0) { status[i] = st; n_out[i] = n; }
 }
 
 // ---- KAT entry points --------------------------------------------------------------------------------

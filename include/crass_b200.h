@@ -17,6 +17,8 @@
  *   addReadHolder() + ReadHolder::DRLowLexi  libcrispr.cpp:1119-1162, ReadHolder.cpp:513-610 -> crass_b200_results_* (host replay)
  *   WorkHorse::createNonRedundantSet  WorkHorse.cpp:612-709,1404-1637 -> crass_b200_non_redundant_set
  *   kseq_read()       kseq.cpp:171-225                              -> crass_b200_parse_file
+ *   ReadHolder::updateStartStops + smithWaterman  ReadHolder.cpp:382-511, SmithWaterman.cpp:151-308
+ *                                                                   -> crass_b200_update_start_stops[_dev] (kernel K6)
  *
  * Conventions
  *   - every function returns 0 on success or a negative crass_b200_status; crass_b200_last_error()
@@ -199,6 +201,36 @@ int crass_b200_ac_scan(crass_b200_ctx* ctx, const crass_b200_ac* ac, const uint8
 int crass_b200_edit_distance_batch(crass_b200_ctx* ctx, const uint8_t* bytes, uint64_t n_bytes,
                                    const uint32_t* a_off, const uint32_t* a_len, const uint32_t* b_off, const uint32_t* b_len,
                                    uint32_t n_pairs, int32_t* out_dist, float* out_sim);
+
+/* ---- K6: partial-DR recovery, batched (first consumer of the path's start/stop lists) -------------
+ * ReadHolder::updateStartStops (ReadHolder.cpp:382-511) with the 7-argument smithWaterman (SmithWaterman.cpp:151-308,
+ * similarity cut-off CRASS_DEF_PARTIAL_SIM_CUT_OFF 0.85, minimum length CRASS_DEF_MIN_PARTIAL_LENGTH 4).  WorkHorse
+ * calls it once per read of a DR group with the group's consensus DR (WorkHorse.cpp:1347); here one call takes the
+ * jobs of any number of groups.  Job i rewrites the read's list ss_in[ss_offset, ss_offset + n_ss) into
+ * ss_out[out_offset, ...) -- reserve n_ss + 4 entries: a partial repeat may be added at either end -- and reports
+ * n_out[i] entries and status[i]: 0 ok; 1 list empty or odd; 2 DR empty or longer than 127; 3 a shifted start lies
+ * at or past the end of the read (the reference logs "Something wrong with front offset!" and reads out of bounds);
+ * 4 read of 65536 bases or more.  For status != 0 nothing is written and n_out[i] = 0. */
+typedef struct crass_b200_uss_job {
+    uint32_t read;          /* index of the read in offsets */
+    uint32_t ss_offset;     /* first entry of its start/stop list in ss_in */
+    uint32_t n_ss;          /* number of entries (even, >= 2) */
+    int32_t  front_offset;  /* dr_aligner.offset(token) - dr_aligner.getDRZoneStart(), may be negative */
+    uint32_t dr;            /* index of the group's consensus DR in dr_offsets */
+    uint32_t out_offset;    /* first entry of the new list in ss_out */
+} crass_b200_uss_job;
+
+/* device pointers + stream: only enqueues */
+int crass_b200_update_start_stops_dev(crass_b200_ctx* ctx, const uint8_t* d_bases, const uint64_t* d_offsets,
+                                      const uint8_t* d_dr_bytes, const uint32_t* d_dr_offsets,
+                                      const crass_b200_uss_job* d_jobs, uint32_t n_jobs, const uint32_t* d_ss_in,
+                                      uint32_t low_spacer, uint32_t* d_ss_out, uint32_t* d_n_out, uint8_t* d_status, void* stream);
+
+/* host pointers: validates the jobs, copies, runs, copies back, synchronises */
+int crass_b200_update_start_stops(crass_b200_ctx* ctx, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
+                                  const uint8_t* dr_bytes, const uint32_t* dr_offsets, uint32_t n_drs,
+                                  const crass_b200_uss_job* jobs, uint32_t n_jobs, const uint32_t* ss_in, uint32_t n_ss_in,
+                                  uint32_t low_spacer, uint32_t* ss_out, uint32_t ss_out_cap, uint32_t* n_out, uint8_t* status);
 
 /* ---- known-answer entry points for the two functions the reference's own unit tests pin ----------
  * (src/test/test_libcrispr.cpp).  They run the SAME device code K1 uses, one read per call. */

@@ -892,4 +892,138 @@ uint64_t orc_phase2_batch(const orc_ac* ac, const uint8_t* bases, const uint64_t
     return nf;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Partial-DR recovery: smithWaterman + ReadHolder::updateStartStops          */
+/* ------------------------------------------------------------------------------------------ */
+static double sw_find_max(double a, double b, double c, double d, int* index) {
+    /* findMax (SmithWaterman.cpp:68-131): ties go to a, then b, then ... exactly as the nested tests do */
+    if (b > a) {
+        if (c > d) { if (c > b) { *index = 2; return c; } *index = 1; return b; }
+        if (d > b) { *index = 3; return d; }
+        *index = 1; return b;
+    }
+    if (c > d) { if (c > a) { *index = 2; return c; } *index = 0; return a; }
+    if (d > a) { *index = 3; return d; }
+    *index = 0; return a;
+}
+
+int orc_smith_waterman(const uint8_t* a, uint32_t la, const uint8_t* b, uint32_t lb, int a_start_search, int a_search_len,
+                       double similarity, int* a_start_align, int* a_end_align,
+                       uint32_t* a_ret_pos, uint32_t* a_ret_len, uint32_t* b_ret_pos, uint32_t* b_ret_len) {
+    /* smithWaterman (SmithWaterman.cpp:151-308).  Scores are doubles (match 1.2, mismatch -1, gap -1,
+     * SmithWaterman.h:60-63) and are added in the reference's order, so equalities between cells are the reference's.
+     * Returns 1 with the two substrings (as positions/lengths in a and b), 0 when the similarity test rejects.
+     * Needs a_search_len >= 1, lb >= 1 and a_start_search + a_search_len <= la (the reference reads out of bounds
+     * otherwise). */
+    const int n = a_search_len, m = (int)lb;
+    const size_t w = (size_t)m + 1;
+    double* M = (double*)calloc((size_t)(n + 1) * w, sizeof(double));
+    int* Ii = (int*)calloc((size_t)(n + 1) * w, sizeof(int));
+    int* Ij = (int*)calloc((size_t)(n + 1) * w, sizeof(int));
+    double matrix_max = -1;
+    int i_max = 0, j_max = 0;
+    for (int i = 1; i <= n; ++i) {
+        for (int j = 1; j <= m; ++j) {
+            int index = -1;
+            const double sim = (a[i - 1 + a_start_search] == b[j - 1]) ? 1.2 : -1;
+            const double v = sw_find_max(M[(size_t)(i - 1) * w + (j - 1)] + sim, M[(size_t)(i - 1) * w + j] + -1,
+                                         M[(size_t)i * w + (j - 1)] + -1, 0, &index);
+            M[(size_t)i * w + j] = v;
+            if (v > matrix_max) { matrix_max = v; i_max = i; j_max = j; }
+            int pi = i, pj = j;
+            if (index == 0) { pi = i - 1; pj = j - 1; } else if (index == 1) { pi = i - 1; } else if (index == 2) { pj = j - 1; }
+            Ii[(size_t)i * w + j] = pi; Ij[(size_t)i * w + j] = pj;
+        }
+    }
+    int ci = i_max, cj = j_max;
+    int ni = Ii[(size_t)ci * w + cj], nj = Ij[(size_t)ci * w + cj];
+    while (nj != 0 && ni != 0 && (ci != ni || cj != nj)) {
+        ci = ni; cj = nj;
+        ni = Ii[(size_t)ci * w + cj]; nj = Ij[(size_t)ci * w + cj];
+    }
+    free(M); free(Ii); free(Ij);
+    ci--; cj--;
+    if (cj < 0) cj = 0;
+    if (ci < 0) ci = 0;
+    *a_start_align = ci + a_start_search;
+    *a_end_align = *a_start_align + i_max - ci - 1;
+    /* a_ret = seqA.substr(current_i + aStartSearch, i_max - current_i + aStartSearch): the LENGTH carries the search
+     * offset as well (:282), std::string::substr clips it at the end of the read */
+    uint32_t ap = (uint32_t)(ci + a_start_search), al = (uint32_t)(i_max - ci + a_start_search);
+    if (al > la - ap) al = la - ap;
+    uint32_t bp = (uint32_t)cj, bl = (uint32_t)(j_max - cj);
+    if (bl > lb - bp) bl = lb - bp;
+    if (similarity != 0) {
+        double sim_ld = 1.0 - (orc_edit_distance(a + ap, al, b + bp, bl) / (double)al);
+        if (!(sim_ld >= similarity)) {
+            *a_start_align = 0; *a_end_align = 0;
+            *a_ret_pos = *a_ret_len = *b_ret_pos = *b_ret_len = 0;
+            return 0;
+        }
+    }
+    *a_ret_pos = ap; *a_ret_len = al; *b_ret_pos = bp; *b_ret_len = bl;
+    return 1;
+}
+
+static int64_t bytes_find(const uint8_t* h, uint32_t hl, const uint8_t* nd, uint32_t nl, int last) {
+    /* std::string::find / rfind of a non-empty needle; -1 = npos */
+    int64_t r = -1;
+    if (nl > hl) return -1;
+    for (uint32_t i = 0; i + nl <= hl; ++i)
+        if (!memcmp(h + i, nd, nl)) { r = i; if (!last) break; }
+    return r;
+}
+
+int orc_update_start_stops(const uint8_t* seq, uint32_t L, uint32_t* ss, uint32_t* n_ss, uint32_t cap, int front_offset,
+                           const uint8_t* dr, uint32_t dr_len, uint32_t low_spacer) {
+    /* ReadHolder::updateStartStops (ReadHolder.cpp:382-511): shift every repeat to the consensus DR, then look for one
+     * more, partial, repeat in front of the first and behind the last one (similarity cut-off 0.85, at least 4 bases,
+     * crassDefines.h:81-82).  n_ss must be even and >= 2; returns -2 if cap is too small, -3 if a shifted start lies
+     * past the read (the reference only logs that case and then reads out of bounds). */
+    const int DR_length = (int)dr_len;
+    uint32_t n = *n_ss;
+    if (n < 2 || (n & 1)) return -1;
+    for (uint32_t k = 0; k < n; k += 2) {
+        int usable_length = DR_length - 1;
+        if (front_offset >= (int)ss[k]) {
+            int below = front_offset - (int)ss[k];
+            usable_length = DR_length - below - 1;
+            ss[k] = 0;
+        } else ss[k] -= (uint32_t)front_offset;
+        if (ss[k] >= L) return -3;
+        ss[k + 1] = ss[k] + (uint32_t)usable_length;
+        if (ss[k + 1] >= L) ss[k + 1] = L - 1;
+    }
+    if (ss[0] > low_spacer) {                                                   /* :443-481 front */
+        int ps = 0, pe = 0;
+        uint32_t ap, al, bp, bl;
+        orc_smith_waterman(seq, L, dr, dr_len, 0, (int)(ss[0] - low_spacer), 0.85, &ps, &pe, &ap, &al, &bp, &bl);
+        if (pe != 0 && pe - ps >= 4) {
+            int64_t at = bytes_find(dr, dr_len, dr + bp, bl, 1);                /* DR->rfind(sp.second) */
+            if (at >= 0 && (uint64_t)at + bl == dr_len && ps == 0) {
+                if (n + 2 > cap) return -2;
+                memmove(ss + 2, ss, n * sizeof(uint32_t));
+                ss[0] = 0; ss[1] = (uint32_t)pe;
+                n += 2;
+            }
+        }
+    }
+    uint32_t end_dist = L - ss[n - 1];                                          /* :483-510 back */
+    if (end_dist > low_spacer) {
+        int ps = 0, pe = 0;
+        uint32_t ap, al, bp, bl;
+        orc_smith_waterman(seq, L, dr, dr_len, (int)(ss[n - 1] + low_spacer), (int)(end_dist - low_spacer), 0.85, &ps, &pe, &ap, &al, &bp, &bl);
+        if (pe != 0 && pe - ps >= 4) {
+            if ((int)L - 1 == pe && bytes_find(dr, dr_len, dr + bp, bl, 0) == 0) {
+                if (n + 2 > cap) return -2;
+                int diff = (int)al - (int)bl;
+                if (diff < 0) diff = -diff;
+                ss_add(ss, &n, L, (uint32_t)(ps + diff), (uint32_t)pe);
+            }
+        }
+    }
+    *n_ss = n;
+    return 0;
+}
+
 void orc_free(void* p) { free(p); }

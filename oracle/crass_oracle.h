@@ -71,6 +71,12 @@ char* orc_run_files(const char* const* paths, uint32_t n_paths, const orc_params
  * returns number of reads found.  found[] (n_reads bytes) may be NULL. */
 uint64_t orc_phase1_batch(const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, const orc_params* p, uint8_t* found);
 uint64_t orc_phase2_batch(const orc_ac* ac, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, uint8_t* found);
+/* smithWaterman (SmithWaterman.cpp:151-308) and ReadHolder::updateStartStops (ReadHolder.cpp:382-511) */
+int orc_smith_waterman(const uint8_t* a, uint32_t la, const uint8_t* b, uint32_t lb, int a_start_search, int a_search_len,
+                       double similarity, int* a_start_align, int* a_end_align,
+                       uint32_t* a_ret_pos, uint32_t* a_ret_len, uint32_t* b_ret_pos, uint32_t* b_ret_len);
+int orc_update_start_stops(const uint8_t* seq, uint32_t L, uint32_t* ss, uint32_t* n_ss, uint32_t cap, int front_offset,
+                           const uint8_t* dr, uint32_t dr_len, uint32_t low_spacer);
 void orc_free(void* p);
 
 #ifdef __cplusplus

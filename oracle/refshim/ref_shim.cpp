@@ -34,6 +34,8 @@
 #include "StringCheck.h"
 #include "kseq.h"
 
+#include "SmithWaterman.h"
+
 extern "C" {
 #include "../aho-corasick/msutil.h"
 #include "../aho-corasick/acism.h"
@@ -429,6 +431,39 @@ char* ref_non_redundant(const char* const* drs, const uint32_t* lens, uint32_t n
     for (size_t i = 0; i < tg.size(); ++i) os << "G\t" << tg[i].first << "\t" << tg[i].second << "\n";
     for (size_t i = 0; i < nr.size(); ++i) os << "P\t" << nr[i] << "\n";
     return dup_string(os.str());
+}
+
+// ---- partial-DR recovery: the consumers of the path's start/stop lists ----
+// smithWaterman (SmithWaterman.cpp:151) as updateStartStops calls it; the two returned strings come back as lengths
+// plus the position of the second one's first/last occurrence in b (what the caller tests with find/rfind).
+int ref_smith_waterman(const char* a, uint32_t la, const char* b, uint32_t lb, int a_start_search, int a_search_len,
+                       double similarity, int* a_start_align, int* a_end_align, uint32_t* first_len, uint32_t* second_len,
+                       int* second_find, int* second_rfind) {
+    ref_init();
+    try {
+        std::string sa(a, la), sb(b, lb);
+        stringPair sp = smithWaterman(sa, sb, a_start_align, a_end_align, a_start_search, a_search_len, similarity);
+        *first_len = (uint32_t)sp.first.length();
+        *second_len = (uint32_t)sp.second.length();
+        *second_find = (int)sb.find(sp.second);
+        *second_rfind = (int)sb.rfind(sp.second);
+        return sp.first.empty() && sp.second.empty() ? 0 : 1;
+    } catch (crispr::exception& e) { return -1; } catch (std::exception& e) { return -3; }
+}
+
+// ReadHolder::updateStartStops (ReadHolder.cpp:382) on a holder with the given start/stop list
+int ref_update_start_stops(const char* seq, uint32_t len, uint32_t* ss, uint32_t* n_ss, uint32_t cap, int front_offset,
+                           const char* dr, uint32_t dr_len, uint32_t low_spacer) {
+    ref_init();
+    try {
+        ReadHolder h; holder_from(h, seq, len, ss, *n_ss);
+        const uint32_t defaults[7] = {23, 47, low_spacer, 50, 8, 2, 6};
+        options o; fill_options(o, defaults);
+        std::string d(dr, dr_len);
+        h.updateStartStops(front_offset, &d, &o);
+        if (copy_ss(h, ss, cap, n_ss)) return -2;
+        return 0;
+    } catch (crispr::exception& e) { return -1; } catch (std::exception& e) { return -3; }
 }
 
 void ref_free(void* p) { free(p); }

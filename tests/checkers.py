@@ -56,6 +56,7 @@ class _Base:
         f("non_redundant", C.c_void_p, [C.POINTER(cp), u32p, C.c_uint32, C.c_int])
         f("run_files", C.c_void_p, [C.POINTER(cp), C.c_uint32, u32p, C.c_int, C.POINTER(C.c_double)])
         f("free", None, [C.c_void_p])
+        f("update_start_stops", C.c_int, [cp, C.c_uint32, u32p, u32p, C.c_uint32, C.c_int, cp, C.c_uint32, C.c_uint32])
 
     def _f(self, name, restype, argtypes):
         fn = getattr(self.lib, self.prefix + name)
@@ -126,6 +127,15 @@ class _Base:
         assert r == 0
         return dr.raw[: drl.value], low.value, list(arr), seq_out
 
+    # -- partial-DR recovery (updateStartStops / smithWaterman) ---------------------------------
+    def update_start_stops(self, seq, ss, front_offset, dr, low_spacer=26):
+        """-> (status, new start/stop list)"""
+        cap = len(ss) + 8
+        arr = (C.c_uint32 * cap)(*ss)
+        n = C.c_uint32(len(ss))
+        r = self._update_start_stops(seq, len(seq), arr, C.byref(n), cap, front_offset, dr, len(dr), low_spacer)
+        return r, list(arr[: n.value])
+
     # -- automaton -----------------------------------------------------------------------------
     def ac_create(self, patterns):
         n = len(patterns)
@@ -168,6 +178,18 @@ class Ref(_Base):
         lib = C.CDLL(REF_SO)
         lib.ref_init()
         super().__init__(lib)
+        i32p, u32p = C.POINTER(C.c_int), C.POINTER(C.c_uint32)
+        lib.ref_smith_waterman.restype = C.c_int
+        lib.ref_smith_waterman.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_int, C.c_int, C.c_double,
+                                           i32p, i32p, u32p, u32p, i32p, i32p]
+
+    def smith_waterman(self, a, b, start, length, similarity=0.85):
+        """-> (ok, a_start_align, a_end_align, len(first), len(second), b.find(second), b.rfind(second))"""
+        s, e, f, r = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        l1, l2 = C.c_uint32(0), C.c_uint32(0)
+        ok = self.lib.ref_smith_waterman(a, len(a), b, len(b), start, length, similarity, C.byref(s), C.byref(e),
+                                         C.byref(l1), C.byref(l2), C.byref(f), C.byref(r))
+        return ok, s.value, e.value, l1.value, l2.value, f.value, r.value
 
 
 class Port(_Base):
@@ -183,6 +205,19 @@ class Port(_Base):
         lib.orc_phase1_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p]
         lib.orc_phase2_batch.restype = C.c_uint64
         lib.orc_phase2_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        i32p, u32p = C.POINTER(C.c_int), C.POINTER(C.c_uint32)
+        lib.orc_smith_waterman.restype = C.c_int
+        lib.orc_smith_waterman.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_int, C.c_int, C.c_double,
+                                           i32p, i32p, u32p, u32p, u32p, u32p]
+
+    def smith_waterman(self, a, b, start, length, similarity=0.85):
+        """Same tuple as Ref.smith_waterman (find/rfind of the second string evaluated here)."""
+        s, e = C.c_int(0), C.c_int(0)
+        ap, al, bp, bl = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        ok = self.lib.orc_smith_waterman(a, len(a), b, len(b), start, length, similarity, C.byref(s), C.byref(e),
+                                         C.byref(ap), C.byref(al), C.byref(bp), C.byref(bl))
+        second = b[bp.value: bp.value + bl.value]
+        return ok, s.value, e.value, al.value, bl.value, b.find(second), b.rfind(second)
 
     def _f(self, name, restype, argtypes):
         # orc_search_core takes (const orc_params*) where ref_ takes the uint32[7] array: same layout

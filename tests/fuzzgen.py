@@ -67,3 +67,39 @@ def dr_like_patterns(rng, n, lo=23, hi=47, both_strands=True):
         if both_strands:
             out.append(p.translate(comp)[::-1])
     return out
+
+
+def uss_case(rng):
+    """Input of ReadHolder::updateStartStops as WorkHorse produces it: a read that carries 1-4 copies of a DR
+    (found repeats = trimmed copies, as seed extension leaves them), often a partial copy at either end, and the
+    group's consensus DR with the offset of the found repeat inside it.  -> (read, start/stops, front offset, DR)"""
+    dr = rand_seq(rng, rng.randint(23, 47))
+    trim_l, trim_r = rng.randint(0, 6), rng.randint(0, 6)
+    parts, ss, pos = [], [], 0
+    if rng.random() < 0.7:
+        k = rng.randint(1, len(dr))
+        piece = mutate(rng, dr[len(dr) - k:], 0.03, b"ACGTN")
+    else:
+        piece = rand_seq(rng, rng.randint(0, 40))
+    parts.append(piece)
+    pos += len(piece)
+    for _ in range(rng.randint(1, 4)):
+        sp = rand_seq(rng, rng.randint(26, 50))
+        parts.append(sp)
+        pos += len(sp)
+        parts.append(mutate(rng, dr, 0.02, b"ACGTN"))
+        ss += [pos + trim_l, pos + len(dr) - 1 - trim_r]
+        pos += len(dr)
+    sp = rand_seq(rng, rng.randint(0, 50))
+    parts.append(sp)
+    if rng.random() < 0.7:
+        parts.append(mutate(rng, dr[: rng.randint(1, len(dr))], 0.03, b"ACGTN"))
+    seq = b"".join(parts)
+    if rng.random() < 0.1:
+        seq = seq[: max(ss[-1] + 1, len(seq) - rng.randint(0, 30))]
+    front = trim_l if rng.random() < 0.7 else rng.randint(-4, 12)
+    if rng.random() < 0.1:
+        dr = dr + rand_seq(rng, rng.randint(1, 10))
+    if rng.random() < 0.05:
+        seq = seq.lower() if rng.random() < 0.5 else seq.replace(b"A", b"R", 1)
+    return seq, ss, front, dr

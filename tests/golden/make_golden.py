@@ -11,6 +11,10 @@ Outputs (all under tests/golden/):
   lowlexi_vectors.json       seeded (read, start/stops) -> (DR, flag, mirrored start/stops)
   ac_vectors.json            seeded pattern sets + texts -> first match (end, length) or null
   kseq_vectors.json          hand-made FASTA/FASTQ edge-case files -> record stream seen by searchFile
+  update_start_stops_vectors.json  seeded (read, start/stops, front offset, DR, lowSpacerSize) -> new start/stops
+                             (ReadHolder::updateStartStops), and smithWaterman calls -> (ok, start, end,
+                             lengths of the two strings, find/rfind of the second in the DR);
+                             `python make_golden.py uss` regenerates this file alone
 
 catch_vectors.json is NOT generated: it restates the known-answer tests of the reference's own
 src/test/test_libcrispr.cpp by hand (each entry cites its line range).
@@ -44,8 +48,32 @@ KSEQ_CASES = {
 }
 
 
+def gen_update_start_stops(R):
+    rng = random.Random(20240)
+    uss, sw = [], []
+    while len(uss) < 400:
+        seq, ss, front, dr = fuzzgen.uss_case(rng)
+        low = rng.choice([26, 26, 26, 20, 35])
+        if checkers.port().update_start_stops(seq, ss, front, dr, low)[0] == -3:
+            continue                                 # shifted start past the read: the reference reads out of bounds
+        st, out = R.update_start_stops(seq, ss, front, dr, low)
+        assert st == 0
+        uss.append(dict(seq=seq.decode(), ss=ss, front=front, dr=dr.decode(), low_spacer=low, ss_out=out))
+    for _ in range(400):
+        seq, ss, front, dr = fuzzgen.uss_case(rng)
+        start = rng.randint(0, len(seq) - 1)
+        length = rng.randint(1, len(seq) - start)
+        sim = 0.85 if rng.random() < 0.8 else 0.0
+        sw.append(dict(a=seq.decode(), b=dr.decode(), start=start, len=length, similarity=sim,
+                       out=list(R.smith_waterman(seq, dr, start, length, sim))))
+    json.dump(dict(update_start_stops=uss, smith_waterman=sw), open(os.path.join(HERE, "update_start_stops_vectors.json"), "w"))
+
+
 def main():
     R = checkers.ref()
+    if sys.argv[1:] == ["uss"]:
+        gen_update_start_stops(R)
+        return
     os.makedirs(os.path.join(HERE, "bundled"), exist_ok=True)
     sums = []
     for f in sorted(os.listdir(checkers.REF_DATA)):
@@ -129,6 +157,7 @@ def main():
                     assert vec[name]["records"] == out
                 vec[name] = dict(content=content, records=out)
     json.dump(vec, open(os.path.join(HERE, "kseq_vectors.json"), "w"), indent=1)
+    gen_update_start_stops(R)
     print("golden fixtures regenerated from", checkers.REF_SO)
 
 

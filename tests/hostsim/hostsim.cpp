@@ -10,6 +10,7 @@
 
 #include "../../crass_b200/csrc/dr_core.cuh"
 #include "../../crass_b200/csrc/dr_filter.cuh"
+#include "../../crass_b200/csrc/sw_core.cuh"
 
 using namespace cb;
 
@@ -130,6 +131,32 @@ int hs_packed(const uint8_t* seq, uint32_t len, uint32_t shift_bases, int nw, co
     if (nw == 19) HS_RUN(19, 16);
 #undef HS_RUN
     return -9;
+}
+
+}  // extern "C"
+
+// partial-DR recovery (sw_core.cuh): the device code of k_update_start_stops, one read per call
+extern "C" {
+
+int hs_smith_waterman(const uint8_t* a, uint32_t la, const uint8_t* b, uint32_t lb, int start, int len, double similarity,
+                      int* start_align, int* end_align, uint32_t* a_pos, uint32_t* a_len, uint32_t* b_pos, uint32_t* b_len) {
+    if (lb > (uint32_t)kMaxSwDr) return -1;
+    PtrSeq s{a};
+    SwResult r;
+    smith_waterman(s, la, b, lb, start, len, similarity, r);
+    *start_align = r.start_align; *end_align = r.end_align;
+    *a_pos = r.a_pos; *a_len = r.a_len; *b_pos = r.b_pos; *b_len = r.b_len;
+    return r.ok;
+}
+
+// out must hold *n_ss + 4 entries; returns the UssStatus
+int hs_update_start_stops(const uint8_t* seq, uint32_t len, const uint32_t* ss, uint32_t n_ss, int front_offset,
+                          const uint8_t* dr, uint32_t dr_len, uint32_t low_spacer, uint32_t* out, uint32_t* n_out) {
+    PtrSeq s{seq}, d{dr};
+    uint32_t n = 0;
+    const uint8_t st = update_start_stops(s, len, ss, n_ss, front_offset, d, dr_len, low_spacer, out, n);
+    *n_out = n;
+    return (int)st;
 }
 
 }  // extern "C"

@@ -520,3 +520,118 @@ def test_whole_path_synthetic_against_oracle(ctx, P, tmp_path):
     got = res.dump(max_len)
     assert got == want
     assert sum(1 for l in got.split("\n") if l.startswith("R\t")) > 1000
+
+
+# ---- K6: partial-DR recovery (ReadHolder::updateStartStops + smithWaterman) ---------------------------------------
+@pytest.fixture(params=["warp", "thread"])
+def k6path(request):
+    """K6 has two kernels with identical results: one warp per read (lane wavefront, the default) and one thread per
+    read (the source tests/hostsim also compiles)."""
+    old = os.environ.get("CRASS_B200_K6")
+    os.environ["CRASS_B200_K6"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("CRASS_B200_K6", None)
+    else:
+        os.environ["CRASS_B200_K6"] = old
+
+
+def test_update_start_stops_golden_vectors(ctx, k6path):
+    """The reference's own outputs (tests/golden/make_golden.py uss), all jobs in one launch, several DRs."""
+    vec = json.load(open(os.path.join(G, "update_start_stops_vectors.json")))["update_start_stops"]
+    reads = [v["seq"].encode() for v in vec]
+    bases, offsets = api.pack_reads(reads)
+    by_low = {}
+    for i, v in enumerate(vec):
+        by_low.setdefault(v["low_spacer"], []).append(i)
+    for low, idx in by_low.items():
+        drs = [vec[i]["dr"].encode() for i in idx]
+        jobs = [(i, vec[i]["ss"], vec[i]["front"], k) for k, i in enumerate(idx)]
+        got = ctx.update_start_stops(bases, offsets, drs, jobs, low)
+        for (st, out), i in zip(got, idx):
+            assert (st, out) == (0, vec[i]["ss_out"])
+
+
+def test_update_start_stops_fuzz_against_oracle(ctx, k6path):
+    P = checkers.port()
+    rng = random.Random(23)
+    cases = [fuzzgen.uss_case(rng) for _ in range(6000)]
+    # long reads and long DRs as well: flanks of a few thousand bases, the DR at the 127-byte limit
+    for _ in range(40):
+        dr = fuzzgen.rand_seq(rng, rng.randint(60, 127))
+        lead = fuzzgen.rand_seq(rng, rng.randint(100, 3000)) + dr[len(dr) - rng.randint(5, 60):]
+        body = fuzzgen.rand_seq(rng, 40) + dr + fuzzgen.rand_seq(rng, 35) + dr
+        tail = fuzzgen.rand_seq(rng, rng.randint(30, 3000)) + dr[: rng.randint(5, 60)]
+        seq = lead + body + tail
+        s0 = len(lead) + 40
+        cases.append((seq, [s0 + 3, s0 + len(dr) - 2, s0 + len(dr) + 35 + 3, s0 + 2 * len(dr) + 35 - 2], 3, dr))
+    # bytes outside A/C/G/T/N (row-DP fallback of the similarity test) and every columns-per-lane bucket of the warp kernel
+    for _ in range(300):
+        seq, ss, front, dr = fuzzgen.uss_case(rng)
+        cases.append((seq.replace(b"G", b"g", 3).replace(b"A", b"R", 2), ss, front, dr.replace(b"G", b"g", 1) if rng.random() < 0.5 else dr))
+    for _ in range(300):
+        dr = fuzzgen.rand_seq(rng, rng.randint(30, 100))
+        sp = [fuzzgen.rand_seq(rng, rng.randint(26, 50)) for _ in range(3)]
+        lead = fuzzgen.mutate(rng, dr[len(dr) - rng.randint(4, len(dr)):], 0.04, b"ACGT")
+        tail = fuzzgen.mutate(rng, dr[: rng.randint(4, len(dr))], 0.04, b"ACGT")
+        seq = lead + sp[0] + dr + sp[1] + dr + sp[2] + tail
+        s0 = len(lead) + len(sp[0])
+        s1 = s0 + len(dr) + len(sp[1])
+        cases.append((seq, [s0 + 2, s0 + len(dr) - 3, s1 + 2, s1 + len(dr) - 3], 2, dr))
+    reads = [c[0] for c in cases]
+    bases, offsets = api.pack_reads(reads)
+    for low in (26, 20, 35):
+        drs = [c[3] for c in cases]
+        jobs = [(i, c[1], c[2], i) for i, c in enumerate(cases)]
+        got = ctx.update_start_stops(bases, offsets, drs, jobs, low)
+        grew = past = 0
+        for (st, out), c in zip(got, cases):
+            want = P.update_start_stops(c[0], c[1], c[2], c[3], low)
+            if want[0] == -3:
+                assert (st, out) == (3, [])
+                past += 1
+                continue
+            assert (st, out) == (0, want[1])
+            grew += len(out) > len(c[1])
+        assert grew > 2000
+
+
+def test_update_start_stops_status_codes_and_validation(ctx, k6path):
+    bases, offsets = api.pack_reads([b"ACGT" * 40])
+    ok = ctx.update_start_stops(bases, offsets, [b"ACGTACGTACGTACGTACGTACGTAC"], [(0, [40, 60], 0, 0)])
+    assert ok[0][0] == 0 and len(ok[0][1]) >= 2
+    assert ctx.update_start_stops(bases, offsets, [b"ACGTACGTACGTACGTACGTACGTAC"], [(0, [40], 0, 0)])[0] == (1, [])
+    assert ctx.update_start_stops(bases, offsets, [b"A" * 128], [(0, [40, 60], 0, 0)])[0] == (2, [])
+    assert ctx.update_start_stops(bases, offsets, [b"ACGTACGTACGTACGTACGTACGTAC"], [(0, [40, 60], -200, 0)])[0] == (3, [])
+    with pytest.raises(cb.CrassB200Error):
+        ctx.update_start_stops(bases, offsets, [b"ACGTACGTACGTACGTACGTACGTAC"], [(1, [40, 60], 0, 0)])      # no such read
+    with pytest.raises(cb.CrassB200Error):
+        ctx.update_start_stops(bases, offsets, [b"ACGTACGTACGTACGTACGTACGTAC"], [(0, [40, 60], 0, 5)])      # no such DR
+    assert ctx.update_start_stops(bases, offsets, [b"ACGT"], []) == []
+
+
+def test_update_start_stops_on_the_hits_of_a_bundled_read_set(ctx, k6path):
+    """K1's own start/stop lists as input: every phase-1 hit of Ill100.fx.gz against its own DR token (front offset 0
+    and a few shifted ones), checked against the oracle."""
+    path = os.path.join(checkers.REF_DATA, "Ill100.fx.gz")
+    if not os.path.exists(path):
+        pytest.skip("bundled read sets not staged")
+    P = checkers.port()
+    batch = cb.Batch.from_file(path)
+    bases, offsets = batch.bases, batch.offsets
+    hits, pool, _ = ctx.dr_search(bases, offsets)
+    assert len(hits) > 500
+    rng = random.Random(2)
+    drs, jobs = [], []
+    for h in hits:
+        r, o, n = int(h["read_index"]), int(h["ss_offset"]), int(h["n_ss"])
+        seq = bytes(bases[int(offsets[r]): int(offsets[r + 1])])
+        ss = [int(x) for x in pool[o: o + n]]
+        k = 2 if n >= 4 else 0
+        drs.append(seq[ss[k]: ss[k + 1] + 1])
+        jobs.append((r, ss, rng.choice([0, 0, 1, 3, -2]), len(drs) - 1))
+    got = ctx.update_start_stops(bases, offsets, drs, jobs)
+    for (st, out), (r, ss, front, d) in zip(got, jobs):
+        seq = bytes(bases[int(offsets[r]): int(offsets[r + 1])])
+        want = P.update_start_stops(seq, ss, front, drs[d])
+        assert (st, out) == ((3, []) if want[0] == -3 else (0, want[1]))

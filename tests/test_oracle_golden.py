@@ -57,6 +57,18 @@ def test_lowlexi_vectors(P):
         assert (dr.decode(), low, ss, seq.decode()) == (v["dr"], v["lowlexi"], v["ss_out"], v["seq_out"])
 
 
+def test_update_start_stops_vectors(P):
+    g = load("update_start_stops_vectors.json")
+    grew = 0
+    for v in g["update_start_stops"]:
+        st, out = P.update_start_stops(v["seq"].encode(), v["ss"], v["front"], v["dr"].encode(), v["low_spacer"])
+        assert (st, out) == (0, v["ss_out"])
+        grew += len(out) > len(v["ss"])
+    assert grew > 100                                    # the fixture does exercise the partial-repeat branches
+    for v in g["smith_waterman"]:
+        assert list(P.smith_waterman(v["a"].encode(), v["b"].encode(), v["start"], v["len"], v["similarity"])) == v["out"]
+
+
 def test_ac_vectors(P):
     for case in load("ac_vectors.json"):
         h = P.ac_create([p.encode() for p in case["patterns"]])

@@ -97,6 +97,25 @@ def test_qc_and_extend_fuzz(R, P):
         assert R.qc_found_repeats(s, ss2) == P.qc_found_repeats(s, ss2)
 
 
+def test_smith_waterman_and_update_start_stops_fuzz(R, P):
+    rng = random.Random(17)
+    grew = 0
+    for _ in range(3000):
+        seq, ss, front, dr = fuzzgen.uss_case(rng)
+        start = rng.randint(0, len(seq) - 1)
+        length = rng.randint(1, len(seq) - start)
+        sim = 0.85 if rng.random() < 0.8 else 0.0
+        assert R.smith_waterman(seq, dr, start, length, sim) == P.smith_waterman(seq, dr, start, length, sim)
+        low = rng.choice([26, 26, 20, 35])
+        got = P.update_start_stops(seq, ss, front, dr, low)
+        if got[0] == -3:
+            continue
+        want = R.update_start_stops(seq, ss, front, dr, low)
+        assert got == want
+        grew += len(want[1]) > len(ss)
+    assert grew > 1000
+
+
 def test_lowlexi_fuzz(R, P):
     rng = random.Random(15)
     for _ in range(10000):
