@@ -87,6 +87,9 @@ CB_HD_NOINLINE int osa_distance_read_vs_dr(const Seq& s, uint32_t a0, uint32_t n
     return (int)prev[m];
 }
 
+struct SwResult;
+template <class Seq> CB_HD bool sw_similarity_ok(const Seq& a, const uint8_t* bb, const SwResult& r, double similarity);
+
 struct SwResult {
     int ok;                       // 0 = rejected by the similarity test (both strings empty, start = end = 0)
     int start_align, end_align;   // *aStartAlign, *aEndAlign
@@ -139,14 +142,18 @@ CB_HD_NOINLINE void smith_waterman(const Seq& a, uint32_t la, const uint8_t* bb,
     r.b_len = (uint32_t)(j_max - cj);
     if (r.b_len > lb - r.b_pos) r.b_len = lb - r.b_pos;
     r.ok = 1;
-    if (similarity != 0) {
-        const int d = osa_distance_read_vs_dr(a, r.a_pos, r.a_len, bb + r.b_pos, r.b_len);
-        const double sim_ld = 1.0 - ((double)d / (double)r.a_len);
-        if (!(sim_ld >= similarity)) {
-            r.ok = 0; r.start_align = 0; r.end_align = 0;
-            r.a_pos = r.a_len = r.b_pos = r.b_len = 0;
-        }
+    if (similarity != 0 && !sw_similarity_ok(a, bb, r, similarity)) {
+        r.ok = 0; r.start_align = 0; r.end_align = 0;
+        r.a_pos = r.a_len = r.b_pos = r.b_len = 0;
     }
+}
+
+// the test at the end of smithWaterman (SmithWaterman.cpp:291-303): 1 - distance / len(first string) >= similarity
+template <class Seq>
+CB_HD bool sw_similarity_ok(const Seq& a, const uint8_t* bb, const SwResult& r, double similarity) {
+    const int d = osa_distance_read_vs_dr(a, r.a_pos, r.a_len, bb + r.b_pos, r.b_len);
+    const double sim_ld = 1.0 - ((double)d / (double)r.a_len);
+    return sim_ld >= similarity;
 }
 
 // position of the first (last = false) or last occurrence of nd[0, nl) in h[0, hl), -1 if none; nl >= 1
@@ -188,12 +195,16 @@ CB_HD uint8_t update_start_stops(const Seq& s, uint32_t L, const uint32_t* ss_in
     uint8_t bb[kMaxSwDr + 1];
     for (uint32_t j = 0; j < dr_len; ++j) bb[j] = dr[j];
     uint32_t base = 2, n = n_in;
+    // The caller's tests on the alignment (:446-451, :498-502) are cheap and nearly always fail for a flank without a
+    // partial repeat, while the similarity test inside smithWaterman costs an edit distance.  A failed similarity test
+    // zeroes start/end, which fails the caller's tests as well, so the order does not matter: align first
+    // (similarity 0 = "just return the substrings"), test, and only then pay for the distance.
     SwResult r;
     if (first_start > low_spacer) {                                   // :443-481: a partial repeat in front of the first one
-        smith_waterman(s, L, bb, dr_len, 0, (int)(first_start - low_spacer), 0.85, r);
+        smith_waterman(s, L, bb, dr_len, 0, (int)(first_start - low_spacer), 0.0, r);
         if (r.end_align != 0 && r.end_align - r.start_align >= 4) {
             const int at = bytes_find(bb, dr_len, bb + r.b_pos, r.b_len, true);
-            if (at >= 0 && (uint32_t)at + r.b_len == dr_len && r.start_align == 0) {
+            if (at >= 0 && (uint32_t)at + r.b_len == dr_len && r.start_align == 0 && sw_similarity_ok(s, bb, r, 0.85)) {
                 out[0] = 0; out[1] = (uint32_t)r.end_align;
                 base = 0; n += 2;
             }
@@ -201,9 +212,9 @@ CB_HD uint8_t update_start_stops(const Seq& s, uint32_t L, const uint32_t* ss_in
     }
     const uint32_t end_dist = L - last_end;                            // :483-510: ... and behind the last one
     if (end_dist > low_spacer) {
-        smith_waterman(s, L, bb, dr_len, (int)(last_end + low_spacer), (int)(end_dist - low_spacer), 0.85, r);
+        smith_waterman(s, L, bb, dr_len, (int)(last_end + low_spacer), (int)(end_dist - low_spacer), 0.0, r);
         if (r.end_align != 0 && r.end_align - r.start_align >= 4) {
-            if ((int)L - 1 == r.end_align && bytes_find(bb, dr_len, bb + r.b_pos, r.b_len, false) == 0) {
+            if ((int)L - 1 == r.end_align && bytes_find(bb, dr_len, bb + r.b_pos, r.b_len, false) == 0 && sw_similarity_ok(s, bb, r, 0.85)) {
                 int diff = (int)r.a_len - (int)r.b_len;
                 if (diff < 0) diff = -diff;
                 uint32_t en = (uint32_t)r.end_align;

@@ -69,6 +69,18 @@ __device__ int osa_bitpar_dr_vs_read(const uint8_t* bb, uint32_t bl, const Seq& 
     return bad ? -1 : score;
 }
 
+// the similarity test of smithWaterman (SmithWaterman.cpp:291-303); all lanes call it and get the same answer
+template <class Seq>
+__device__ bool sw_similarity_ok_warp(const Seq& a, const uint8_t* bb, const cb::SwResult& r, double similarity) {
+    int d = osa_bitpar_dr_vs_read(bb + r.b_pos, r.b_len, a, r.a_pos, r.a_len);
+    if (d < 0) {                                         // uniform: every lane saw the same bytes
+        if ((threadIdx.x & 31u) == 0) d = cb::osa_distance_read_vs_dr(a, r.a_pos, r.a_len, bb + r.b_pos, r.b_len);
+        d = __shfl_sync(kFull, d, 0);
+    }
+    const double sim_ld = __dsub_rn(1.0, __ddiv_rn((double)d, (double)r.a_len));
+    return sim_ld >= similarity;
+}
+
 // smithWaterman(read, DR, ..., start, len, similarity) by one warp; bb = the DR in shared memory.  r is the same on
 // every lane.  Needs len >= 1, 1 <= lb <= 32 * CPL, start + len <= la.
 template <int CPL, class Seq>
@@ -138,17 +150,9 @@ __device__ void smith_waterman_warp(const Seq& a, uint32_t la, const uint8_t* bb
     r.b_len = (uint32_t)(best_j - cj);
     if (r.b_len > lb - r.b_pos) r.b_len = lb - r.b_pos;
     r.ok = 1;
-    if (similarity != 0) {
-        int d = osa_bitpar_dr_vs_read(bb + r.b_pos, r.b_len, a, r.a_pos, r.a_len);
-        if (d < 0) {                                     // uniform: every lane saw the same bytes
-            if (lane == 0) d = cb::osa_distance_read_vs_dr(a, r.a_pos, r.a_len, bb + r.b_pos, r.b_len);
-            d = __shfl_sync(kFull, d, 0);
-        }
-        const double sim_ld = __dsub_rn(1.0, __ddiv_rn((double)d, (double)r.a_len));
-        if (!(sim_ld >= similarity)) {
-            r.ok = 0; r.start_align = 0; r.end_align = 0;
-            r.a_pos = r.a_len = r.b_pos = r.b_len = 0;
-        }
+    if (similarity != 0 && !sw_similarity_ok_warp(a, bb, r, similarity)) {
+        r.ok = 0; r.start_align = 0; r.end_align = 0;
+        r.a_pos = r.a_len = r.b_pos = r.b_len = 0;
     }
 }
 
@@ -194,17 +198,18 @@ __device__ uint8_t update_start_stops_warp(const Seq& s, uint32_t L, const uint3
     bool front = false, back = false;
     uint32_t front_end = 0, back_start = 0, back_end = 0;
     if (first_start > low_spacer) {                                        // :443-481
-        smith_waterman_warp_any(s, L, bb, dr_len, 0, (int)(first_start - low_spacer), 0.85, r);
+        // alignment first, the caller's cheap tests next, the edit distance only for the few that pass (see sw_core.cuh)
+        smith_waterman_warp_any(s, L, bb, dr_len, 0, (int)(first_start - low_spacer), 0.0, r);
         if (r.end_align != 0 && r.end_align - r.start_align >= 4) {
             const int at = cb::bytes_find(bb, dr_len, bb + r.b_pos, r.b_len, true);
-            if (at >= 0 && (uint32_t)at + r.b_len == dr_len && r.start_align == 0) { front = true; front_end = (uint32_t)r.end_align; }
+            if (at >= 0 && (uint32_t)at + r.b_len == dr_len && r.start_align == 0 && sw_similarity_ok_warp(s, bb, r, 0.85)) { front = true; front_end = (uint32_t)r.end_align; }
         }
     }
     const uint32_t end_dist = L - last_end;                                // :483-510
     if (end_dist > low_spacer) {
-        smith_waterman_warp_any(s, L, bb, dr_len, (int)(last_end + low_spacer), (int)(end_dist - low_spacer), 0.85, r);
+        smith_waterman_warp_any(s, L, bb, dr_len, (int)(last_end + low_spacer), (int)(end_dist - low_spacer), 0.0, r);
         if (r.end_align != 0 && r.end_align - r.start_align >= 4) {
-            if ((int)L - 1 == r.end_align && cb::bytes_find(bb, dr_len, bb + r.b_pos, r.b_len, false) == 0) {
+            if ((int)L - 1 == r.end_align && cb::bytes_find(bb, dr_len, bb + r.b_pos, r.b_len, false) == 0 && sw_similarity_ok_warp(s, bb, r, 0.85)) {
                 int diff = (int)r.a_len - (int)r.b_len;
                 if (diff < 0) diff = -diff;
                 back = true;
