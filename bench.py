@@ -111,16 +111,17 @@ def write_fasta(path, bases, offsets, lo, hi):
 
 def ref_worker(args):
     """One reference process over one FASTA shard; returns (reads, seconds phase1, cluster, phase2)."""
-    path, n = args
+    path, n = args[:2]
     import checkers
     R = checkers.ref()
     t = time.time()
-    _, tm = R.run_files([path])
-    return n, tm[0] / 1e3, tm[1] / 1e3, tm[2] / 1e3, time.time() - t
+    dump, tm = R.run_files([path])
+    return n, tm[0] / 1e3, tm[1] / 1e3, tm[2] / 1e3, time.time() - t, (dump if len(args) > 2 and args[2] else None)
 
 
-def cpu_reference_rate(bases, offsets, n_sample, n_procs, tmpdir):
-    """reads/s of the reference's own searchFile + findSingletons on n_sample reads split over n_procs processes."""
+def cpu_reference_rate(bases, offsets, n_sample, n_procs, tmpdir, keep_dump=False):
+    """reads/s of the reference's own searchFile + findSingletons on n_sample reads split over n_procs processes.
+    keep_dump (one process only): also return the reference's result dump and the FASTA path for the parity check."""
     import multiprocessing as mp
     import checkers
     kind = "reference" if checkers.have_ref() else "port"
@@ -133,7 +134,7 @@ def cpu_reference_rate(bases, offsets, n_sample, n_procs, tmpdir):
     t0 = time.time()
     if kind == "reference":
         if n_procs == 1:
-            res = [ref_worker(jobs[0])]
+            res = [ref_worker(jobs[0] + (keep_dump,))]
         else:
             with mp.get_context("spawn").Pool(n_procs) as pool:
                 res = pool.map(ref_worker, jobs)
@@ -142,11 +143,12 @@ def cpu_reference_rate(bases, offsets, n_sample, n_procs, tmpdir):
         res = []
         for path, n in jobs:
             _, tm = P.run_files([path])
-            res.append((n, tm[0] / 1e3, tm[1] / 1e3, tm[2] / 1e3, 0.0))
+            res.append((n, tm[0] / 1e3, tm[1] / 1e3, tm[2] / 1e3, 0.0, None))
     wall = time.time() - t0
     worst = max(r[1] + r[2] + r[3] for r in res)
     return dict(kind=kind, reads=per * n_procs, seconds=worst, wall=wall, rate=per * n_procs / worst,
-                phase1_s=max(r[1] for r in res), phase2_s=max(r[3] for r in res))
+                phase1_s=max(r[1] for r in res), phase2_s=max(r[3] for r in res),
+                dump=res[0][5] if keep_dump else None, path=jobs[0][0])
 
 
 def main():
@@ -420,7 +422,19 @@ def main():
         if not args.no_cpu_baseline:
             ns = min(args.cpu_sample, n)
             with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
-                r = cpu_reference_rate(np_bases, np_offsets, ns, 1, d)
+                r = cpu_reference_rate(np_bases, np_offsets, ns, 1, d, keep_dump=True)
+                if r["dump"] is not None:
+                    # SURVEY 8d "parity check accompanying every timing": the product's whole path (parser -> K1 -> clustering
+                    # -> K2 -> replay) on the very FASTA the reference just processed; the two result dumps (tokens in
+                    # numbering order, DRs, reads, orientation, start/stops, patterns) must be the same bytes.
+                    import hashlib
+                    t0 = time.time()
+                    res, max_len = ctx.run_files([r["path"]])
+                    mine = res.dump(max_len)
+                    line["parity"] = {"sample": "the cpu_baseline sample (%d reads), whole path through the C-ABI vs the reference" % ns,
+                                      "dump_identical": bool(mine == r["dump"]), "dump_bytes": len(r["dump"]),
+                                      "dump_md5": hashlib.md5(r["dump"].encode("latin-1")).hexdigest(),
+                                      "found_reads": int(res.num_reads), "tokens": int(res.num_tokens), "b200_seconds": time.time() - t0}
             line["cpu_baseline"] = {"value": r["rate"], "unit": "reads/s", "cores": 1, "kind": r["kind"],
                                     "sample": "first %d reads of rank 0's shard as FASTA in tmpfs: searchFile %.2fs + findSingletons %.2fs, 1 thread" % (ns, r["phase1_s"], r["phase2_s"])}
         emit(line)
