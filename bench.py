@@ -416,6 +416,7 @@ def main():
                              "kernel_ms": dom_ms},
                 "kernels": {"k1_dr_search_ms": k1, "k1_frac_of_hbm": bytes_k1 / (k1 / 1e3) / 1e9 / peak,
                             "k2_singleton_scan_ms": k2, "k2_frac_of_hbm": (bytes_k2 / (k2 / 1e3) / 1e9 / peak) if k2 else None,
+                            "k1_plus_k2_frac_of_hbm": ((bytes_k1 + bytes_k2) / ((k1 + k2) / 1e3) / 1e9 / peak) if k2 else None,
                             "host_between_kernels_ms": ms_step - k1 - k2,
                             "host_breakdown_ms": {k: float(np.mean(v)) for k, v in host_ms.items() if v}},
                 "stats": stats, "clocks": clocks}

@@ -918,7 +918,13 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         // (CRASS_B200_K2V=list selects the thread-per-candidate form for comparison)
         const char* vsel = getenv("CRASS_B200_K2V");
         if (vsel && !strcmp(vsel, "list")) cbk::k_ac_verify_list<<<c->sm_count * 8, 128, 0, st>>>(d_bases, d_offsets, cand, ps, d_found, sink);
-        else cbk::k_ac_verify_warp<<<c->sm_count * 8, 128, 0, st>>>(d_bases, d_offsets, cand, ps, d_found, sink);
+        else {
+            // 28 registers per thread: 16 CTAs of 4 warps fill an SM; the kernel is a chain of dependent L2 probes, so warps in
+            // flight are what it runs on (CRASS_B200_K2V_CTAS = CTAs per SM, for measurements)
+            int per_sm = 16;
+            if (const char* e = getenv("CRASS_B200_K2V_CTAS")) per_sm = std::max(1, atoi(e));
+            cbk::k_ac_verify_warp<<<c->sm_count * per_sm, 128, 0, st>>>(d_bases, d_offsets, cand, ps, d_found, sink);
+        }
         c->launches += 2;
         CUDA_TRY(cudaGetLastError());
         return 0;

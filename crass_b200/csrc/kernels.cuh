@@ -1238,10 +1238,12 @@ k_ac_verify_warp(const uint8_t* __restrict__ bases, const uint64_t* __restrict__
                     if (p + len > L) continue;
                     const uint32_t key = ((p + len) << 8) | (255u - len);
                     if (key >= best) continue;
-                    bool same = true;
-                    for (uint32_t k = 0; k < len; ++k)
-                        if (__ldg(s + p + k) != __ldg(ps.p_bytes + po + k)) { same = false; break; }
-                    if (same) best = key;
+                    // a chained pattern shares the lane's 16-mer code, so it nearly always matches: no early exit, the byte
+                    // loads of all positions are independent and overlap instead of forming a chain of 2 x len latencies
+                    uint32_t diff = 0;
+#pragma unroll 8
+                    for (uint32_t k = 0; k < len; ++k) diff |= (uint32_t)__ldg(s + p + k) ^ (uint32_t)__ldg(ps.p_bytes + po + k);
+                    if (diff == 0) best = key;
                 }
             }
         }
