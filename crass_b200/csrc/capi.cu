@@ -112,6 +112,7 @@ struct crass_b200_ctx {
     DevBuf d_found_p1, d_cand, d_tokens, d_tok_table, d_tok_unique, d_ac_table, d_ac_symv, d_ac_bitmap, d_ac_keys;
     DevBuf d_ac_skeys, d_ac_shead, d_ac_pnext, d_ac_poffs, d_ac_pbytes;
     DevBuf d_cand_counts;                // K1 fast path: sizes of the two candidate lists
+    DevBuf d_cand_mask;                  // K2 fast path: per candidate, the aligned 16-mers that can belong to an occurrence
     // K5 (clustering passes A/B on the token block): device arrays and their pinned host mirrors
     DevBuf d_cl_order, d_cl_koff, d_cl_keys, d_cl_first, d_cl_tab, d_cl_info;
     DevBuf d_cl_group, d_cl_chain, d_cl_next, d_cl_odd, d_cl_dead, d_cl_str;
@@ -193,7 +194,7 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
     DevBuf* bufs[] = {&c->d_bases, &c->d_offsets, &c->d_found, &c->d_skip, &c->d_hits, &c->d_pool, &c->d_counters,
                       &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv, &c->d_found_p1, &c->d_cand, &c->d_tokens, &c->d_tok_table, &c->d_tok_unique, &c->d_ac_table, &c->d_ac_symv,
                       &c->d_ac_bitmap, &c->d_ac_keys, &c->d_ac_skeys, &c->d_ac_shead, &c->d_ac_pnext, &c->d_ac_poffs, &c->d_ac_pbytes,
-                      &c->d_rank, &c->d_hits_sorted, &c->d_cand_counts, &c->d_packed,
+                      &c->d_rank, &c->d_hits_sorted, &c->d_cand_counts, &c->d_cand_mask, &c->d_packed,
                       &c->d_cl_order, &c->d_cl_koff, &c->d_cl_keys, &c->d_cl_first, &c->d_cl_tab, &c->d_cl_info,
                       &c->d_cl_group, &c->d_cl_chain, &c->d_cl_next, &c->d_cl_odd, &c->d_cl_dead, &c->d_cl_str};
     for (DevBuf* b : bufs) b->release();
@@ -872,7 +873,9 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
     if (ac->a.q_bits && max_read_len <= 304 && (((uintptr_t)d_bases) & 15) == 0 && !(force && !strcmp(force, "generic"))) {
         if (!d_found) { if (int r = c->d_found.reserve((size_t)n_reads + 16)) return r; d_found = c->d_found.as<uint8_t>(); }
         if (int r = c->d_cand.reserve(((size_t)n_reads + 16) * sizeof(uint32_t))) return r;
+        if (int r = c->d_cand_mask.reserve(((size_t)n_reads + 16) * sizeof(uint64_t))) return r;
         uint32_t* cand = c->d_cand.as<uint32_t>();
+        uint64_t* cmask = c->d_cand_mask.as<uint64_t>();
         cbk::QgramFilter q{c->d_ac_bitmap.as<uint32_t>(), c->d_ac_keys.as<uint32_t>(), ac->a.q_bits, ac->a.q_table_bits, ac->a.q_has_ones};
         const uint32_t n_tiles = (n_reads + cbk::kAcTile - 1) / cbk::kAcTile;
         const size_t bm_bytes = ((size_t)1 << ac->a.q_bits) / 8;
@@ -882,7 +885,7 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         CUDA_TRY(cudaFuncSetAttribute(cbk::k_ac_filter<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
         const int per_sm = std::max<int>(1, (int)((size_t)220 * 1024 / smem));                                                  \
         const int fblocks = (int)std::min<uint32_t>(n_tiles, (uint32_t)(c->sm_count * std::min(per_sm, 8)));                    \
-        cbk::k_ac_filter<NW><<<fblocks, cbk::kAcTile, smem, st>>>(d_bases, d_offsets, n_reads, q, d_skip, d_found, cand, d_counters); \
+        cbk::k_ac_filter<NW><<<fblocks, cbk::kAcTile, smem, st>>>(d_bases, d_offsets, n_reads, q, d_skip, d_found, cand, cmask, d_counters); \
     } while (0)
         // the 2-bit stream the direct-repeat search of this very batch left behind: a quarter of the bytes, no recoding
         const char* fsel = getenv("CRASS_B200_K2F");
@@ -896,7 +899,7 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbk::k_ac_filter_packed<NW>, cbk::kAcPackedTile, smem)); \
         const uint32_t p_tiles = (n_reads + cbk::kAcPackedTile - 1) / cbk::kAcPackedTile;                                       \
         const int pblocks = (int)std::min<uint32_t>(p_tiles, (uint32_t)(c->sm_count * std::max(per_sm, 1)));                    \
-        cbk::k_ac_filter_packed<NW><<<pblocks, cbk::kAcPackedTile, smem, st>>>(c->d_packed.as<uint32_t>(), d_offsets, n_reads, q, d_skip, d_found, cand, d_counters); \
+        cbk::k_ac_filter_packed<NW><<<pblocks, cbk::kAcPackedTile, smem, st>>>(c->d_packed.as<uint32_t>(), d_offsets, n_reads, q, d_skip, d_found, cand, cmask, d_counters); \
     } while (0)
         if (use_packed) {
             if (max_read_len <= 112) CB_ACP(7);
@@ -918,6 +921,12 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         // (CRASS_B200_K2V=list selects the thread-per-candidate form for comparison)
         const char* vsel = getenv("CRASS_B200_K2V");
         if (vsel && !strcmp(vsel, "list")) cbk::k_ac_verify_list<<<c->sm_count * 8, 128, 0, st>>>(d_bases, d_offsets, cand, ps, d_found, sink);
+        else if (!(vsel && !strcmp(vsel, "warp"))) {
+            // default: only the starts the filter's 16-mer hits allow (CRASS_B200_K2V=warp: all starts, for comparison)
+            int per_sm = 16;
+            if (const char* e = getenv("CRASS_B200_K2V_CTAS")) per_sm = std::max(1, atoi(e));
+            cbk::k_ac_verify_mask<<<c->sm_count * per_sm, 128, 0, st>>>(d_bases, d_offsets, cand, cmask, ps, d_found, sink);
+        }
         else {
             // 28 registers per thread: 16 CTAs of 4 warps fill an SM; the kernel is a chain of dependent L2 probes, so warps in
             // flight are what it runs on (CRASS_B200_K2V_CTAS = CTAs per SM, for measurements)

@@ -919,7 +919,7 @@ template <int NW>
 __global__ void __launch_bounds__(kAcTile)
 k_ac_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads, QgramFilter q,
             const uint8_t* __restrict__ skip, uint8_t* __restrict__ found, uint32_t* __restrict__ cand_list,
-            uint32_t* __restrict__ counters) {
+            uint64_t* __restrict__ cand_mask, uint32_t* __restrict__ counters) {
     constexpr int kWords = kAcTile * NW + NW + 8;
     extern __shared__ uint32_t dsm[];
     uint32_t* bm = dsm;                                          // bitmap, (1 << bits) / 32 words
@@ -972,6 +972,7 @@ k_ac_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs
             const int n_kmers = L >= 16 ? (int)((L - 16) >> 3) + 1 : 0;        // 16-mers that lie inside the read
             if (n_kmers < 64) hits &= (1ull << n_kmers) - 1ull;
             bool cand = false;
+            uint64_t mask = 0;                                   // the confirmed 16-mer + the bitmap hits behind it (see k_ac_verify_mask)
             while (hits && !cand) {
                 const int i = __ffsll((long long)hits) - 1;
                 hits &= hits - 1;
@@ -979,9 +980,14 @@ k_ac_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs
                 const uint32_t w1 = cb::funnel_r(sm[wi + (i >> 1) + 1], sm[wi + (i >> 1) + 2], sh);
                 const uint32_t code = (i & 1) ? cb::funnel_r(w0, w1, 16) : w0;
                 cand = qgram_member(q, code);
+                if (cand) mask = hits | (1ull << i);
             }
             found[r] = 0;
-            if (cand && !(skip && skip[r])) cand_list[atomicAdd(&counters[3], 1u)] = r;
+            if (cand && !(skip && skip[r])) {
+                const uint32_t slot = atomicAdd(&counters[3], 1u);
+                cand_list[slot] = r;
+                cand_mask[slot] = mask;
+            }
         }
     }
 }
@@ -1012,7 +1018,7 @@ __device__ __forceinline__ void ac_packed_issue(const uint32_t* __restrict__ pac
 template <int NW>
 __global__ void __launch_bounds__(kAcPackedTile)
 k_ac_filter_packed(const uint32_t* __restrict__ packed, const uint64_t* __restrict__ offsets, uint32_t n_reads, QgramFilter q,
-                   const uint8_t* __restrict__ skip, uint8_t* __restrict__ found, uint32_t* __restrict__ cand_list,
+                   const uint8_t* __restrict__ skip, uint8_t* __restrict__ found, uint32_t* __restrict__ cand_list, uint64_t* __restrict__ cand_mask,
                    uint32_t* __restrict__ counters) {
     constexpr int kWords = ac_packed_words<NW>();
     extern __shared__ __align__(128) uint32_t dsm[];
@@ -1056,15 +1062,21 @@ k_ac_filter_packed(const uint32_t* __restrict__ packed, const uint64_t* __restri
             const int n_kmers = L >= 16 ? (int)((L - 16) >> 3) + 1 : 0;        // 16-mers that lie inside the read
             if (n_kmers < 64) hits &= (1ull << n_kmers) - 1ull;
             bool cand = false;
+            uint64_t mask = 0;
             while (hits && !cand) {
                 const int k = __ffsll((long long)hits) - 1;
                 hits &= hits - 1;
                 const uint32_t w0 = cb::funnel_r(sm[wi + (k >> 1)], sm[wi + (k >> 1) + 1], sh);
                 const uint32_t w1 = cb::funnel_r(sm[wi + (k >> 1) + 1], sm[wi + (k >> 1) + 2], sh);
                 cand = qgram_member(q, (k & 1) ? cb::funnel_r(w0, w1, 16) : w0);
+                if (cand) mask = hits | (1ull << k);
             }
             found[r] = 0;
-            if (cand && !(skip && skip[r])) cand_list[atomicAdd(&counters[3], 1u)] = r;
+            if (cand && !(skip && skip[r])) {
+                const uint32_t slot = atomicAdd(&counters[3], 1u);
+                cand_list[slot] = r;
+                cand_mask[slot] = mask;
+            }
         }
         __syncthreads();                                         // everyone is done with this buffer
     }
@@ -1240,6 +1252,80 @@ k_ac_verify_warp(const uint8_t* __restrict__ bases, const uint64_t* __restrict__
                     if (key >= best) continue;
                     // a chained pattern shares the lane's 16-mer code, so it nearly always matches: no early exit, the byte
                     // loads of all positions are independent and overlap instead of forming a chain of 2 x len latencies
+                    uint32_t diff = 0;
+#pragma unroll 8
+                    for (uint32_t k = 0; k < len; ++k) diff |= (uint32_t)__ldg(s + p + k) ^ (uint32_t)__ldg(ps.p_bytes + po + k);
+                    if (diff == 0) best = key;
+                }
+            }
+        }
+        best = __reduce_min_sync(0xFFFFFFFFu, best);
+        if (best != 0xFFFFFFFFu && lane == 0) {
+            const uint32_t best_end = best >> 8, best_len = 255u - (best & 255u);
+            uint32_t dr_end = best_end - 1;                          // on_match (libcrispr.cpp:420-437)
+            if (dr_end >= L) dr_end = L - 1;
+            uint32_t ss[2] = { dr_end - (best_len - 1), dr_end };
+            found[r] = 1;
+            emit_hit(sink, r, ss, 2, 0);
+        }
+    }
+}
+
+// Verification guided by the filter (reads up to 304 bp): an occurrence that starts at a contains the read-aligned 16-mer
+// number i = ceil(a / 8), and that 16-mer is a key of the filter.  The filter hands over, per candidate, the set of its
+// aligned 16-mers that can be keys (bit i: the one it confirmed in the key table and every bitmap hit behind it), so only
+// the eight starts 8i-7 .. 8i of every set bit have to be looked at: one round of the warp (4 bits x 8 starts) for a
+// typical candidate instead of the five rounds over all 150 starts k_ac_verify_warp makes.  Same answer: the minimum of
+// (end, -length) over a superset of the occurrences' starts.
+__global__ void __launch_bounds__(128)
+k_ac_verify_mask(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ cand_list,
+                 const uint64_t* __restrict__ cand_mask, PatternStarts ps, uint8_t* __restrict__ found, HitSink sink) {
+    const uint32_t n_cand = sink.counters[3];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t smask = (1u << ps.s_bits) - 1u;
+    for (uint32_t c = gw; c < n_cand; c += nw) {
+        const uint32_t r = cand_list[c];
+        uint64_t mask = cand_mask[c];
+        const uint64_t b = offsets[r];
+        const uint32_t L = (uint32_t)(offsets[r + 1] - b);
+        const uint8_t* s = bases + b;
+        uint32_t best = 0xFFFFFFFFu;                                  // (end << 8) | (255 - len): min == earliest end, longest pattern
+        while (mask) {
+            const uint32_t warp_best = __reduce_min_sync(0xFFFFFFFFu, best);
+            const int i_lo = __ffsll((long long)mask) - 1;            // no start of this or a later round lies before 8 * i_lo - 7
+            if (warp_best != 0xFFFFFFFFu && (uint32_t)(8 * i_lo > 7 ? 8 * i_lo - 7 : 0) + ps.min_len > (warp_best >> 8)) break;
+            int i = -1;                                               // my bit: the (lane / 8)-th lowest one
+            uint64_t m = mask;
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) {
+                const int lowest = m ? __ffsll((long long)m) - 1 : -1;
+                if (q == (lane >> 3)) i = lowest;
+                m &= m - 1;                                           // (0 & -1 == 0)
+            }
+            mask = m;
+            const int p_signed = 8 * i - 7 + (int)(lane & 7u);
+            if (i >= 0 && p_signed >= 0 && (uint32_t)p_signed + 16 <= L) {
+                const uint32_t p = (uint32_t)p_signed;
+                uint32_t code = 0;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) code |= (uint32_t)((__ldg(s + p + k) >> 1) & 3u) << (2 * k);
+                uint32_t pi;
+                if (code == 0xFFFFFFFFu) pi = ps.s_ones_head;
+                else {
+                    uint32_t slot = (code * 0x85EBCA6Bu) >> (32 - ps.s_bits);
+                    for (;;) {
+                        const uint32_t k = __ldg(ps.s_keys + slot);
+                        if (k == code) { pi = __ldg(ps.s_head + slot); break; }
+                        if (k == 0xFFFFFFFFu) { pi = 0xFFFFFFFFu; break; }
+                        slot = (slot + 1) & smask;
+                    }
+                }
+                for (; pi != 0xFFFFFFFFu; pi = __ldg(ps.p_next + pi)) {
+                    const uint32_t po = __ldg(ps.p_offs + pi), len = __ldg(ps.p_offs + pi + 1) - po;
+                    if (p + len > L) continue;
+                    const uint32_t key = ((p + len) << 8) | (255u - len);
+                    if (key >= best) continue;
                     uint32_t diff = 0;
 #pragma unroll 8
                     for (uint32_t k = 0; k < len; ++k) diff |= (uint32_t)__ldg(s + p + k) ^ (uint32_t)__ldg(ps.p_bytes + po + k);

@@ -43,14 +43,16 @@ def k1path(request):
         os.environ["CRASS_B200_K1"] = old
 
 
-@pytest.fixture(params=["fast", "fast-list", "generic"])
+@pytest.fixture(params=["fast", "fast-warp", "fast-list", "generic"])
 def k2path(request):
-    """K2 likewise: 16-mer q-gram filter + verification of the candidates (one warp, or with "fast-list" one thread, per
-    candidate), or the plain one-thread-per-read automaton walk."""
+    """K2 likewise: 16-mer q-gram filter + verification of the candidates (one warp per candidate over the starts the
+    filter's hits allow; "fast-warp": over all starts; "fast-list": one thread per candidate), or the plain
+    one-thread-per-read automaton walk."""
     old = os.environ.get("CRASS_B200_K2"), os.environ.get("CRASS_B200_K2V")
     os.environ["CRASS_B200_K2"] = request.param.split("-")[0]
-    if request.param == "fast-list":
-        os.environ["CRASS_B200_K2V"] = "list"
+    os.environ.pop("CRASS_B200_K2V", None)
+    if "-" in request.param:
+        os.environ["CRASS_B200_K2V"] = request.param.split("-")[1]
     yield request.param
     for k, v in zip(("CRASS_B200_K2", "CRASS_B200_K2V"), old):
         if v is None:
@@ -472,6 +474,56 @@ def test_singleton_scan_fuzz(ctx, P, k2path):
                 dr_end = min(m[0] - 1, len(t) - 1)
                 assert got[i] == ([dr_end - (m[1] - 1), dr_end], 0)
         P.ac_destroy(h)
+
+
+def test_singleton_scan_short_reads_overlapping_patterns(ctx, P, k2path):
+    """Reads up to 304 bp (the filter + verify kernels of the fast path, bytes form and 2-bit-stream form): several planted
+    occurrences per read, patterns nested in each other and overlapping, occurrences cut by the read end, N runs -- the
+    answer is acism's first callback: earliest end, longest pattern on ties."""
+    rng = random.Random(106)
+    for n_pat in (3, 40, 2500):
+        pats = fuzzgen.dr_like_patterns(rng, n_pat)
+        pats += [p[rng.randint(0, 4): len(p) - rng.randint(0, 4)] for p in pats[: max(2, n_pat // 3)] if len(p) >= 31]     # nested, still >= 23
+        pats += [fuzzgen.mutate(rng, p, 0.05, b"ACGT") for p in pats[: max(2, n_pat // 3)]]
+        pats = [p for p in dict.fromkeys(pats) if len(p) >= 23]
+        texts = []
+        for _ in range(4000):
+            L = rng.choice([0, 15, 23, 40, 100, 150, 150, 151, 250, 304])
+            t = bytearray(fuzzgen.rand_seq(rng, L, b"ACGTN" if rng.random() < 0.2 else b"ACGT"))
+            for _ in range(rng.choice([0, 1, 1, 2, 3])):
+                if L < 23:
+                    break
+                p = rng.choice(pats)
+                pos = rng.randint(-5, L - 10)
+                piece = p[max(0, -pos):]
+                pos = max(pos, 0)
+                piece = piece[: L - pos]
+                t[pos: pos + len(piece)] = piece
+            texts.append(bytes(t))
+        bases, offs = cb.pack_reads(texts)
+        ac = cb.Automaton(pats)
+        h = P.ac_create(pats)
+        want = [P.ac_first_match(h, t) for t in texts]
+        P.ac_destroy(h)
+        assert sum(m is not None for m in want) > 1000
+        # bytes form
+        hits, pool, found = ctx.ac_scan(ac, bases, offs, None)
+        got = hits_by_read(hits, pool)
+        # 2-bit-stream form: phase 1 of the resident batch leaves the stream behind, phase 2 reads it
+        ctx.upload(bases, offs)
+        _, _, f1 = ctx.dr_search_resident(want_found=True)
+        h2, p2, f2 = ctx.ac_scan_resident(ac, skip_found=True, want_found=True)
+        got2 = hits_by_read(h2, p2)
+        for i, (t, m) in enumerate(zip(texts, want)):
+            exp = None
+            if m is not None:
+                dr_end = min(m[0] - 1, len(t) - 1)
+                exp = ([dr_end - (m[1] - 1), dr_end], 0)
+            assert got.get(i) == exp and found[i] == (exp is not None)
+            if f1[i]:
+                assert i not in got2
+            else:
+                assert got2.get(i) == exp and f2[i] == (exp is not None)
 
 
 def test_singleton_scan_long_reads(ctx, P, k2path):
