@@ -112,6 +112,7 @@ struct crass_b200_ctx {
     DevBuf d_found_p1, d_cand, d_tokens, d_tok_table, d_tok_unique, d_ac_table, d_ac_symv, d_ac_bitmap, d_ac_keys;
     DevBuf d_ac_skeys, d_ac_shead, d_ac_pnext, d_ac_poffs, d_ac_pbytes;
     DevBuf d_cand_counts;                // K1 fast path: sizes of the two candidate lists
+    DevBuf d_ac_bitmap_small;            // folded copy of the q-gram bitmap for k_ac_filter_packed (0 bytes when unused)
     DevBuf d_cand_mask;                  // K2 fast path: per candidate, the aligned 16-mers that can belong to an occurrence
     // K5 (clustering passes A/B on the token block): device arrays and their pinned host mirrors
     DevBuf d_cl_order, d_cl_koff, d_cl_keys, d_cl_first, d_cl_tab, d_cl_info;
@@ -194,7 +195,7 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
     DevBuf* bufs[] = {&c->d_bases, &c->d_offsets, &c->d_found, &c->d_skip, &c->d_hits, &c->d_pool, &c->d_counters,
                       &c->d_scratch, &c->d_error, &c->d_misc, &c->d_symv, &c->d_found_p1, &c->d_cand, &c->d_tokens, &c->d_tok_table, &c->d_tok_unique, &c->d_ac_table, &c->d_ac_symv,
                       &c->d_ac_bitmap, &c->d_ac_keys, &c->d_ac_skeys, &c->d_ac_shead, &c->d_ac_pnext, &c->d_ac_poffs, &c->d_ac_pbytes,
-                      &c->d_rank, &c->d_hits_sorted, &c->d_cand_counts, &c->d_cand_mask, &c->d_packed,
+                      &c->d_rank, &c->d_hits_sorted, &c->d_cand_counts, &c->d_cand_mask, &c->d_ac_bitmap_small, &c->d_packed,
                       &c->d_cl_order, &c->d_cl_koff, &c->d_cl_keys, &c->d_cl_first, &c->d_cl_tab, &c->d_cl_info,
                       &c->d_cl_group, &c->d_cl_chain, &c->d_cl_next, &c->d_cl_odd, &c->d_cl_dead, &c->d_cl_str};
     for (DevBuf* b : bufs) b->release();
@@ -813,6 +814,7 @@ int ensure_ac_on_device(crass_b200_ctx* c, crass_b200_ac* ac) {
     if (a.q_bits) {                                   // filter + pattern-start table (fast path)
         struct Up { DevBuf* d; const void* h; size_t bytes; } ups[] = {
             {&c->d_ac_bitmap, a.q_bitmap.data(), a.q_bitmap.size() * sizeof(uint32_t)},
+            {&c->d_ac_bitmap_small, a.q_bitmap_small.data(), a.q_bitmap_small.size() * sizeof(uint32_t)},
             {&c->d_ac_keys, a.q_keys.data(), a.q_keys.size() * sizeof(uint32_t)},
             {&c->d_ac_skeys, a.s_keys.data(), a.s_keys.size() * sizeof(uint32_t)},
             {&c->d_ac_shead, a.s_head.data(), a.s_head.size() * sizeof(uint32_t)},
@@ -826,6 +828,7 @@ int ensure_ac_on_device(crass_b200_ctx* c, crass_b200_ac* ac) {
         if (int r = c->h_ac_stage.reserve(total)) return r;
         size_t at = 0;
         for (const Up& u : ups) {
+            if (!u.bytes) continue;
             if (int r = u.d->reserve(u.bytes + 16)) return r;
             memcpy(c->h_ac_stage.as<uint8_t>() + at, u.h, u.bytes);
             CUDA_TRY(cudaMemcpyAsync(u.d->p, c->h_ac_stage.as<uint8_t>() + at, u.bytes, cudaMemcpyHostToDevice, c->stream));
@@ -891,15 +894,19 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         const char* fsel = getenv("CRASS_B200_K2F");
         const bool use_packed = c->packed_valid && c->packed_src == (const void*)d_bases && c->packed_reads == n_reads &&
                                 (c->keep_packed_bases || c->packed_internal) && !(fsel && !strcmp(fsel, "bytes"));
+        // the 2-bit-stream form takes the folded (half-size) bitmap when the matcher carries one: three CTAs per SM instead of two
+        cbk::QgramFilter qp = q;
+        if (ac->a.q_bits_small) { qp.bitmap = c->d_ac_bitmap_small.as<uint32_t>(); qp.bits = ac->a.q_bits_small; }
+        const size_t bm_bytes_p = ((size_t)1 << qp.bits) / 8;
 #define CB_ACP(NW)                                                                                                              \
     do {                                                                                                                        \
-        const size_t smem = bm_bytes + 2 * (size_t)cbk::ac_packed_words<NW>() * sizeof(uint32_t);                               \
+        const size_t smem = bm_bytes_p + 2 * (size_t)cbk::ac_packed_words<NW>() * sizeof(uint32_t);                             \
         CUDA_TRY(cudaFuncSetAttribute(cbk::k_ac_filter_packed<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
         int per_sm = 1;                                                                                                         \
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbk::k_ac_filter_packed<NW>, cbk::kAcPackedTile, smem)); \
         const uint32_t p_tiles = (n_reads + cbk::kAcPackedTile - 1) / cbk::kAcPackedTile;                                       \
         const int pblocks = (int)std::min<uint32_t>(p_tiles, (uint32_t)(c->sm_count * std::max(per_sm, 1)));                    \
-        cbk::k_ac_filter_packed<NW><<<pblocks, cbk::kAcPackedTile, smem, st>>>(c->d_packed.as<uint32_t>(), d_offsets, n_reads, q, d_skip, d_found, cand, cmask, d_counters); \
+        cbk::k_ac_filter_packed<NW><<<pblocks, cbk::kAcPackedTile, smem, st>>>(c->d_packed.as<uint32_t>(), d_offsets, n_reads, qp, d_skip, d_found, cand, cmask, d_counters); \
     } while (0)
         if (use_packed) {
             if (max_read_len <= 112) CB_ACP(7);

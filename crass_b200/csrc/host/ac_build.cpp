@@ -57,7 +57,20 @@ static void build_filter_and_starts(Automaton* A) {
     uint32_t small_max = 1000000;
     if (const char* e = getenv("CRASS_B200_QGRAM_SMALL_MAX")) small_max = (uint32_t)strtoul(e, nullptr, 10);
     A->q_bits = positions <= small_max ? 19 : 20;
+    if (const char* e = getenv("CRASS_B200_QGRAM_BITS")) { const int b = atoi(e); if (b >= 15 && b <= 20) A->q_bits = (uint32_t)b; }
     A->q_bitmap.assign((size_t)1 << (A->q_bits - 5), 0);
+    // A half-size copy for the 2-bit-stream filter (k_ac_filter_packed): its CTA is the bitmap + 40 KB of tiles, so 32 KB
+    // instead of 64 KB lets three CTAs instead of two live on an SM, which is worth more than the bits while the set is
+    // sparse (config 5, 50 M reads: 100 patterns 1.80 -> 1.63 ms, 1 000: 2.33 -> 2.15 ms, 3 000: level, 20 000: worse).
+    // h18 = h19 >> 1 for the multiplicative hash, so the copy is the OR of neighbouring bits (set during insertion).
+    A->q_bits_small = 0;
+    A->q_bitmap_small.clear();
+    uint32_t fold_max = 16384;
+    if (const char* e = getenv("CRASS_B200_QGRAM_FOLD_MAX")) fold_max = (uint32_t)strtoul(e, nullptr, 10);
+    if (A->q_bits == 19 && positions <= fold_max) {                  // filled next to the main bitmap below
+        A->q_bits_small = 18;
+        A->q_bitmap_small.assign((size_t)1 << (18 - 5), 0);
+    }
     uint32_t sbits = 4;
     while (((size_t)1 << sbits) < (size_t)n * 2 + 2) ++sbits;
     A->s_bits = sbits;
@@ -76,6 +89,7 @@ static void build_filter_and_starts(Automaton* A) {
             if (k > 22) break;                                       // window starts 0..7 only (see the header comment)
             const uint32_t h = qgram_hash(code, A->q_bits);
             A->q_bitmap[h >> 5] |= 1u << (h & 31);
+            if (A->q_bits_small) { const uint32_t hs = h >> 1; A->q_bitmap_small[hs >> 5] |= 1u << (hs & 31); }
             if (code == 0xFFFFFFFFu) { distinct += !A->q_has_ones; A->q_has_ones = 1; }
             else {
                 uint32_t slot = (code * 0x85EBCA6Bu) >> (32 - tbits);

@@ -110,6 +110,8 @@ struct Automaton {
     // q-gram pre-filter + pattern-start table (ac_build.cpp): empty when the shortest pattern is below 23 bytes
     uint32_t q_bits = 0, q_table_bits = 0, q_count = 0, q_has_ones = 0;
     std::vector<uint32_t> q_bitmap, q_keys;
+    uint32_t q_bits_small = 0;                  // 0 = none; else a folded copy of the bitmap with fewer bits (same hash family)
+    std::vector<uint32_t> q_bitmap_small;
     uint32_t s_bits = 0, s_ones_head = 0xFFFFFFFFu;
     std::vector<uint32_t> s_keys, s_head, p_next;
     // device copies, owned by the context that uploaded them
