@@ -411,7 +411,7 @@ def main():
                         "d2h_bytes_per_step": int(d2h[0]), "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                             "launches": (["k_dr_filter", "k_dr_exact_packed"] if dom.startswith("K1") else ["k_ac_filter_packed", "k_ac_verify_warp"]),
+                             "launches": (["k_dr_filter", "k_dr_exact_packed"] if dom.startswith("K1") else ["k_ac_filter_packed", "k_ac_verify_mask"]),
                              "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": int(dom_bytes),
                              "kernel_ms": dom_ms},
                 "kernels": {"k1_dr_search_ms": k1, "k1_frac_of_hbm": bytes_k1 / (k1 / 1e3) / 1e9 / peak,
