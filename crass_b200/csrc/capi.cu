@@ -967,7 +967,7 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         cbk::PatternStarts ps{c->d_ac_pbytes.as<uint8_t>(), c->d_ac_poffs.as<uint32_t>(), c->d_ac_skeys.as<uint32_t>(),
                               c->d_ac_shead.as<uint32_t>(), c->d_ac_pnext.as<uint32_t>(), ac->a.s_bits, ac->a.s_ones_head,
                               ac->a.min_pattern_len};
-        cbk::k_ac_verify_warp<<<c->sm_count * 8, 128, 0, st>>>(d_bases, d_offsets, cand, ps, d_found, sink);
+        cbk::k_ac_verify_warp<<<c->sm_count * 16, 128, 0, st>>>(d_bases, d_offsets, cand, ps, d_found, sink);      // 28 registers: 16 CTAs per SM
         c->launches += 2;
         CUDA_TRY(cudaGetLastError());
         return 0;
