@@ -15,13 +15,18 @@
 #include <ctype.h>
 #include <fcntl.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
 
+#include <atomic>
+#include <chrono>
+#include <memory>
 #include <stdexcept>
+#include <thread>
 
 #include "internal.h"
 
@@ -130,87 +135,299 @@ bool get_until(Cursor& c, int delimiter, size_t& b, size_t& e, int& dret) {
     return true;
 }
 
+// One stretch of the file parsed on its own: records whose header character lies in [start, stop).  The strings are kept
+// in piece-local pools and spliced into the batch afterwards.  A piece never looks at what came before `start`, so the
+// only state it inherits is kseq's stale comment/quality (offset -1 below = "whatever the previous piece left").
+struct Piece {
+    uint8_t* bases = nullptr; size_t cap = 0; bool own = false;
+    uint64_t nb = 0;
+    std::vector<uint64_t> ends;                  // end of each record's bases, piece-relative
+    std::vector<char> name_pool, text_pool;
+    std::vector<uint64_t> name_off;
+    std::vector<int64_t> comment_off, qual_off;  // piece-relative; -1 = inherited
+    int64_t last_comment = -1, last_qual = -1;
+    uint32_t max_len = 0;
+    int status = 0;                              // 0: stopped at a header >= stop (next_hp); -1/-2: the stream ended here
+    size_t next_hp = 0;
+    ~Piece() { if (own) free(bases); }
+    void room(size_t need) {
+        if (need <= cap) return;
+        if (!own) throw std::length_error("base buffer");
+        size_t ncap = cap * 2 > need ? cap * 2 : need;
+        uint8_t* nbuf = (uint8_t*)realloc(bases, ncap);
+        if (!nbuf) throw std::bad_alloc();
+        bases = nbuf; cap = ncap;
+    }
+};
+
+// The reference's read loop (libcrispr.cpp:96 over kseq_read, kseq.cpp:171-225) from the header character at `start`
+// (start == SIZE_MAX: from the top of the file, looking for the first header) until a header at or past `stop`.
+void parse_span(const uint8_t* data, size_t n, size_t start, size_t stop, Piece& P) {
+    Cursor c{data, n, 0};
+    int last_char = 0;
+    if (start != (size_t)-1) { c.pos = start + 1; last_char = (int)(signed char)data[start]; }
+    int64_t cur_comment = -1, cur_qual = -1;
+    uint64_t nb = 0;
+    for (;;) {
+        int ch;
+        if (last_char == 0) {
+            while ((ch = c.getc()) != -1 && ch != '>' && ch != '@') {}
+            if (ch == -1) { P.status = -1; break; }
+            last_char = ch;
+        }
+        if (c.pos - 1 >= stop) { P.status = 0; P.next_hp = c.pos - 1; break; }
+        size_t b, e; int dret;
+        if (!get_until(c, 0, b, e, dret)) { P.status = -1; break; }
+        const size_t name_b = b, name_e = e;
+        if (dret != '\n') {
+            size_t cb, ce; int d2;
+            if (get_until(c, '\n', cb, ce, d2)) {
+                cur_comment = (int64_t)P.text_pool.size();
+                P.text_pool.insert(P.text_pool.end(), (const char*)data + cb, (const char*)data + ce);
+                P.text_pool.push_back(0);
+            }
+        }
+        const uint64_t seq_b = nb;
+        // kseq: while ((c = getc()) != -1 && c != '>' && c != '+' && c != '@') if (isgraph(c)) append(c);
+        // taken in runs: bytes that are isgraph and none of the three terminators are copied in bulk, every other
+        // byte is looked at on its own (0xFF reads as -1 and ends the loop like the others)
+        for (;;) {
+            size_t i = c.pos;
+            while (i < c.n && kPlain.t[c.p[i]]) ++i;
+            if (i > c.pos) {
+                P.room(nb + (i - c.pos));
+                memcpy(P.bases + nb, c.p + c.pos, i - c.pos); nb += i - c.pos; c.pos = i;
+            }
+            ch = c.getc();
+            if (ch == -1 || ch == '>' || ch == '+' || ch == '@') break;
+        }
+        if (ch == '>' || ch == '@') last_char = ch;
+        const uint64_t L = nb - seq_b;
+        bool emit = true;
+        int bad = 0;
+        if (ch == '+') {
+            while ((ch = c.getc()) != -1 && ch != '\n') {}
+            if (ch == -1) { bad = -2; emit = false; }
+            else {
+                const int64_t q0 = (int64_t)P.text_pool.size();
+                uint64_t ql = 0;
+                // kseq: while ((c = getc()) != -1 && qual.l < seq.l) if (c >= 33 && c <= 127) append(c);  -- the byte
+                // is fetched before the length test, so one byte past the last quality character is consumed
+                while ((ch = c.getc()) != -1 && ql < L) {
+                    if (ch < 33) continue;                             // (signed) also skips bytes >= 0x80
+                    size_t i = c.pos;                                  // the rest of this run of quality characters
+                    const size_t lim = c.pos + (size_t)(L - ql - 1) < c.n ? c.pos + (size_t)(L - ql - 1) : c.n;
+                    while (i < lim && c.p[i] >= 33 && c.p[i] <= 127) ++i;
+                    P.text_pool.push_back((char)ch);
+                    P.text_pool.insert(P.text_pool.end(), (const char*)c.p + c.pos, (const char*)c.p + i);
+                    ql += 1 + (i - c.pos);
+                    c.pos = i;
+                }
+                P.text_pool.push_back(0);
+                cur_qual = q0;
+                last_char = 0;
+                if (ql != L) { bad = -2; emit = false; }
+            }
+        }
+        if (!emit) { nb = seq_b; P.status = bad; break; }
+        P.name_off.push_back(P.name_pool.size());
+        P.name_pool.insert(P.name_pool.end(), (const char*)data + name_b, (const char*)data + name_e);
+        P.name_pool.push_back(0);
+        P.comment_off.push_back(cur_comment);
+        P.qual_off.push_back(cur_qual);
+        P.ends.push_back(nb);
+        if (L > P.max_len) P.max_len = (uint32_t)L;
+    }
+    P.nb = nb; P.last_comment = cur_comment; P.last_qual = cur_qual;
+}
+
+// A likely record start at or after `from` (and before `lim`): a '>' or '@' at a line start whose next line is not a
+// header itself (a quality line may begin with either character) and, for '@', whose third line begins with '+'.
+// Only a guess -- parse_file() checks every guess against the piece before it.
+size_t guess_record_start(const uint8_t* d, size_t n, size_t from, size_t lim) {
+    size_t i = from;
+    while (i < lim) {
+        const void* q = memchr(d + i, '\n', lim - i);
+        if (!q) break;
+        const size_t h = (size_t)((const uint8_t*)q - d) + 1;
+        i = h;
+        if (h >= lim || h >= n || (d[h] != '>' && d[h] != '@')) continue;
+        const void* e1 = memchr(d + h, '\n', n - h);
+        if (!e1) break;
+        const size_t l2 = (size_t)((const uint8_t*)e1 - d) + 1;
+        if (l2 >= n || d[l2] == '>' || d[l2] == '@') continue;
+        if (d[h] == '>') return h;
+        const void* e2 = memchr(d + l2, '\n', n - l2);
+        if (!e2) break;
+        const size_t l3 = (size_t)((const uint8_t*)e2 - d) + 1;
+        if (l3 < n && d[l3] == '+') return h;
+    }
+    return (size_t)-1;
+}
+
+size_t env_size(const char* name, size_t dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    char* end = nullptr;
+    const unsigned long long x = strtoull(v, &end, 10);
+    return end && *end == 0 && x > 0 ? (size_t)x : dflt;
+}
+
+void append_piece(Batch* B, const Piece& P, int64_t& cur_comment, int64_t& cur_qual, uint64_t base0) {
+    const uint64_t name0 = B->name_pool.size();
+    const int64_t text0 = (int64_t)B->text_pool.size();
+    B->name_pool.insert(B->name_pool.end(), P.name_pool.begin(), P.name_pool.end());
+    B->text_pool.insert(B->text_pool.end(), P.text_pool.begin(), P.text_pool.end());
+    const size_t m = P.ends.size();
+    for (size_t r = 0; r < m; ++r) {
+        B->name_off.push_back(name0 + P.name_off[r]);
+        B->comment_off.push_back(P.comment_off[r] < 0 ? cur_comment : text0 + P.comment_off[r]);
+        B->qual_off.push_back(P.qual_off[r] < 0 ? cur_qual : text0 + P.qual_off[r]);
+        B->offsets.push_back(base0 + P.ends[r]);
+    }
+    if (P.last_comment >= 0) cur_comment = text0 + P.last_comment;
+    if (P.last_qual >= 0) cur_qual = text0 + P.last_qual;
+    if (P.max_len > B->max_len) B->max_len = P.max_len;
+}
+
 }  // namespace
 
+// Large inputs are cut at guessed record starts and the pieces parsed by worker threads (CRASS_B200_PARSE_THREADS,
+// default min(hardware threads, 16); pieces of CRASS_B200_PARSE_CHUNK bytes, default 16 MiB).  kseq's stream has no
+// resynchronisation point that can be recognised locally ('@' and '>' are legal quality characters), so a piece is
+// only kept when the piece before it ENDS exactly on the header it started from; otherwise the gap is parsed again
+// from the true position on the calling thread.  The record stream is therefore the sequential one by construction.
 int parse_file(const char* path, Batch** out) {
     Input in;
     if (!in.open(path)) return fail(CRASS_B200_EIO, std::string("cannot open ") + path);
     Batch* B = new Batch();
     try {
         B->offsets.push_back(0);
-        B->reserve_bases(in.size + 16);
-        Cursor c{in.data, in.size, 0};
-        int last_char = 0;
-        int64_t cur_comment = -1, cur_qual = -1;
-        uint64_t nb = 0;
+        const size_t n = in.size;
+        unsigned hw = std::thread::hardware_concurrency();
+        if (hw == 0) hw = 1;
+        const size_t n_threads = env_size("CRASS_B200_PARSE_THREADS", hw < 16 ? hw : 16);
+        const size_t chunk = env_size("CRASS_B200_PARSE_CHUNK", (size_t)16 << 20);
+        std::vector<size_t> starts;                       // header positions the pieces 1.. start from
+        if (n_threads > 1 && n > chunk) {
+            for (size_t at = chunk; at < n; at += chunk) {
+                const size_t s = guess_record_start(in.data, n, at, at + chunk < n ? at + chunk : n);
+                if (s != (size_t)-1) starts.push_back(s);
+            }
+        }
+        if (starts.empty()) {                             // one piece, written straight into the batch
+            B->reserve_bases(n + 16);
+            Piece P;
+            P.bases = B->bases; P.cap = B->bases_cap;
+            parse_span(in.data, n, (size_t)-1, (size_t)-1, P);
+            int64_t cc = -1, cq = -1;
+            append_piece(B, P, cc, cq, 0);
+            B->parse_status = P.status;
+            *out = B;
+            return 0;
+        }
+        const size_t np = starts.size() + 1;
+        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t0 = now();
+        std::vector<Piece> pieces(np);
+        std::atomic<size_t> next{0};
+        std::atomic<bool> failed{false};
+        auto work = [&]() {
+            for (;;) {
+                const size_t k = next.fetch_add(1);
+                if (k >= np || failed.load()) return;
+                try {
+                    Piece& P = pieces[k];
+                    const size_t from = k ? starts[k - 1] : 0, stop = k + 1 < np ? starts[k] : (size_t)-1;
+                    P.own = true;
+                    P.cap = (k + 1 < np ? stop - from : n - from) + 64;
+                    P.bases = (uint8_t*)malloc(P.cap);
+                    if (!P.bases) throw std::bad_alloc();
+                    parse_span(in.data, n, k ? from : (size_t)-1, stop, P);
+                } catch (...) { failed.store(true); }
+            }
+        };
+        {
+            std::vector<std::thread> pool;
+            const size_t nt = n_threads < np ? n_threads : np;
+            for (size_t t = 1; t < nt; ++t) pool.emplace_back(work);
+            work();
+            for (auto& t : pool) t.join();
+        }
+        if (failed.load()) throw std::bad_alloc();
+
+        const double t1 = now();
+        // walk the pieces in file order; `order` lists what the sequential reader would have produced
+        std::vector<const Piece*> order;
+        std::vector<std::unique_ptr<Piece>> patches;
+        size_t k = 0;
+        const Piece* cur = &pieces[0];
         int status = -1;
         for (;;) {
-            int ch;
-            if (last_char == 0) {
-                while ((ch = c.getc()) != -1 && ch != '>' && ch != '@') {}
-                if (ch == -1) { status = -1; break; }
-                last_char = ch;
-            }
-            size_t b, e; int dret;
-            if (!get_until(c, 0, b, e, dret)) { status = -1; break; }
-            const size_t name_b = b, name_e = e;
-            if (dret != '\n') {
-                size_t cb, ce; int d2;
-                if (get_until(c, '\n', cb, ce, d2)) {
-                    cur_comment = (int64_t)B->text_pool.size();
-                    B->text_pool.insert(B->text_pool.end(), (const char*)in.data + cb, (const char*)in.data + ce);
-                    B->text_pool.push_back(0);
-                }
-            }
-            const uint64_t seq_b = nb;
-            uint8_t* dst = B->bases;
-            // kseq: while ((c = getc()) != -1 && c != '>' && c != '+' && c != '@') if (isgraph(c)) append(c);
-            // taken in runs: bytes that are isgraph and none of the three terminators are copied in bulk, every other
-            // byte is looked at on its own (0xFF reads as -1 and ends the loop like the others)
+            order.push_back(cur);
+            if (cur->status != 0) { status = cur->status; break; }
+            const size_t hp = cur->next_hp;
+            while (k < starts.size() && starts[k] < hp) ++k;          // pieces that began inside a record
+            if (k < starts.size() && starts[k] == hp) { cur = &pieces[++k]; continue; }
+            std::unique_ptr<Piece> Q(new Piece());                    // no piece begins here: parse up to the next one
+            const size_t stop = k < starts.size() ? starts[k] : (size_t)-1;
+            Q->own = true;
+            Q->cap = (stop == (size_t)-1 ? n - hp : stop - hp) + 64;
+            Q->bases = (uint8_t*)malloc(Q->cap);
+            if (!Q->bases) throw std::bad_alloc();
+            parse_span(in.data, n, hp, stop, *Q);
+            cur = Q.get();
+            patches.push_back(std::move(Q));
+        }
+        // where each piece lands in the batch, and the stale comment/quality it inherits
+        struct Slot { uint64_t base0, rec0, name0; int64_t text0, in_comment, in_qual; };
+        std::vector<Slot> slot(order.size());
+        uint64_t total = 0, n_rec = 0, n_name = 0;
+        int64_t n_text = 0, cc = -1, cq = -1;
+        for (size_t i = 0; i < order.size(); ++i) {
+            const Piece& P = *order[i];
+            slot[i] = Slot{total, n_rec, n_name, n_text, cc, cq};
+            if (P.last_comment >= 0) cc = n_text + P.last_comment;
+            if (P.last_qual >= 0) cq = n_text + P.last_qual;
+            total += P.nb; n_rec += P.ends.size(); n_name += P.name_pool.size(); n_text += (int64_t)P.text_pool.size();
+            if (P.max_len > B->max_len) B->max_len = P.max_len;
+        }
+        const double t2 = now();
+        B->reserve_bases(total + 16);
+        B->offsets.resize(n_rec + 1); B->name_off.resize(n_rec); B->comment_off.resize(n_rec); B->qual_off.resize(n_rec);
+        B->name_pool.resize(n_name); B->text_pool.resize((size_t)n_text);
+        const double t3 = now();
+        std::atomic<size_t> nextc{0};
+        auto splice = [&]() {
             for (;;) {
-                size_t i = c.pos;
-                while (i < c.n && kPlain.t[c.p[i]]) ++i;
-                if (i > c.pos) { memcpy(dst + nb, c.p + c.pos, i - c.pos); nb += i - c.pos; c.pos = i; }
-                ch = c.getc();
-                if (ch == -1 || ch == '>' || ch == '+' || ch == '@') break;
-            }
-            if (ch == '>' || ch == '@') last_char = ch;
-            const uint64_t L = nb - seq_b;
-            bool emit = true;
-            if (ch == '+') {
-                while ((ch = c.getc()) != -1 && ch != '\n') {}
-                if (ch == -1) { status = -2; emit = false; }
-                else {
-                    const int64_t q0 = (int64_t)B->text_pool.size();
-                    uint64_t ql = 0;
-                    // kseq: while ((c = getc()) != -1 && qual.l < seq.l) if (c >= 33 && c <= 127) append(c);  -- the byte
-                    // is fetched before the length test, so one byte past the last quality character is consumed
-                    while ((ch = c.getc()) != -1 && ql < L) {
-                        if (ch < 33) continue;                             // (signed) also skips bytes >= 0x80
-                        size_t i = c.pos;                                  // the rest of this run of quality characters
-                        const size_t lim = c.pos + (size_t)(L - ql - 1) < c.n ? c.pos + (size_t)(L - ql - 1) : c.n;
-                        while (i < lim && c.p[i] >= 33 && c.p[i] <= 127) ++i;
-                        B->text_pool.push_back((char)ch);
-                        B->text_pool.insert(B->text_pool.end(), (const char*)c.p + c.pos, (const char*)c.p + i);
-                        ql += 1 + (i - c.pos);
-                        c.pos = i;
-                    }
-                    B->text_pool.push_back(0);
-                    cur_qual = q0;
-                    last_char = 0;
-                    if (ql != L) { status = -2; emit = false; }
+                const size_t i = nextc.fetch_add(1);
+                if (i >= order.size()) return;
+                const Piece& P = *order[i];
+                const Slot& S = slot[i];
+                if (P.nb) memcpy(B->bases + S.base0, P.bases, (size_t)P.nb);
+                if (!P.name_pool.empty()) memcpy(B->name_pool.data() + S.name0, P.name_pool.data(), P.name_pool.size());
+                if (!P.text_pool.empty()) memcpy(B->text_pool.data() + S.text0, P.text_pool.data(), P.text_pool.size());
+                const size_t m = P.ends.size();
+                for (size_t r = 0; r < m; ++r) {
+                    B->name_off[S.rec0 + r] = S.name0 + P.name_off[r];
+                    B->comment_off[S.rec0 + r] = P.comment_off[r] < 0 ? S.in_comment : S.text0 + P.comment_off[r];
+                    B->qual_off[S.rec0 + r] = P.qual_off[r] < 0 ? S.in_qual : S.text0 + P.qual_off[r];
+                    B->offsets[S.rec0 + r + 1] = S.base0 + P.ends[r];
                 }
             }
-            if (!emit) { nb = seq_b; break; }
-            B->name_off.push_back(B->name_pool.size());
-            B->name_pool.insert(B->name_pool.end(), (const char*)in.data + name_b, (const char*)in.data + name_e);
-            B->name_pool.push_back(0);
-            B->comment_off.push_back(cur_comment);
-            B->qual_off.push_back(cur_qual);
-            B->offsets.push_back(nb);
-            if (L > B->max_len) B->max_len = (uint32_t)L;
+        };
+        {
+            std::vector<std::thread> pool;
+            const size_t nt = n_threads < order.size() ? n_threads : order.size();
+            for (size_t t = 1; t < nt; ++t) pool.emplace_back(splice);
+            splice();
+            for (auto& t : pool) t.join();
         }
         B->parse_status = status;
+        if (getenv("CRASS_B200_TRACE"))
+            fprintf(stderr, "[crass_b200] parse_file: %zu pieces guessed, %zu kept in order, %zu re-parsed gaps, %zu threads; "
+                    "parse %.1f ms, gaps %.1f ms, alloc %.1f ms, splice %.1f ms\n",
+                    np, order.size() - patches.size(), patches.size(), n_threads, t1 - t0, t2 - t1, t3 - t2, now() - t3);
     } catch (std::exception& ex) {
         delete B;
         return fail(CRASS_B200_ENOMEM, std::string("parse_file: ") + ex.what());

@@ -95,6 +95,85 @@ def test_parser_fuzz_against_oracle():
             assert cb.Batch.from_file(p).record_stream() == P.kseq_dump(p), text
 
 
+def _pieces_env(chunk, threads=4):
+    old = {k: os.environ.get(k) for k in ("CRASS_B200_PARSE_CHUNK", "CRASS_B200_PARSE_THREADS")}
+    os.environ["CRASS_B200_PARSE_CHUNK"] = str(chunk)
+    os.environ["CRASS_B200_PARSE_THREADS"] = str(threads)
+    return old
+
+
+def _restore_env(old):
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+def test_parser_pieces_on_worker_threads_match_the_sequential_stream():
+    """parse_file cuts large inputs at guessed record starts; whatever the guesses are, the record stream must be the
+    one kseq_read (kseq.cpp:171-225) produces sequentially -- stale comments/qualities across the cuts included."""
+    rng = random.Random(11)
+    P = checkers.port()
+    with tempfile.TemporaryDirectory() as d:
+        for it in range(40):
+            parts = []
+            style = rng.choice(["fa", "fq", "mixed", "hostile"])
+            for _ in range(rng.randint(20, 200)):
+                seq = fuzzgen.rand_seq(rng, rng.randint(1, 150), b"ACGTNacgt").decode()
+                name = "r%d" % rng.randint(0, 99999)
+                cmt = rng.choice(["", "", " c%d" % rng.randint(0, 99), "\tc d"])
+                wrap = rng.choice([0, 0, 0, 40])
+                body = seq if not wrap else "\n".join(seq[i:i + wrap] for i in range(0, len(seq), wrap))
+                fq = style == "fq" or (style in ("mixed", "hostile") and rng.random() < 0.6)
+                if not fq:
+                    parts.append(">%s%s\n%s\n" % (name, cmt, body))
+                    continue
+                alphabet = "@>+I5" if style == "hostile" else "!#5I@>+FFFFFF"
+                q = "".join(rng.choice(alphabet) for _ in seq)
+                if style == "hostile" and rng.random() < 0.5:
+                    q = rng.choice("@>") + q[1:]
+                if rng.random() < 0.01:
+                    q = q[:-1]
+                parts.append("%s%s%s\n%s\n+%s\n%s\n" % (rng.choice("@@@>"), name, cmt, body, rng.choice(["", name]), q))
+            text = "".join(parts)
+            if rng.random() < 0.15:
+                text = text.replace("\n", "\r\n")
+            if rng.random() < 0.1:
+                cut = rng.randint(0, len(text))
+                text = text[:cut] + "\xff" + text[cut:]
+            p = os.path.join(d, "f%d.fx" % it)
+            with open(p, "wb") as fh:
+                fh.write(text.encode("latin-1"))
+            want = P.kseq_dump(p)
+            for chunk in (64, 257, 1500, 6000):
+                old = _pieces_env(chunk)
+                try:
+                    b = cb.Batch.from_file(p)
+                    got = b.record_stream()
+                finally:
+                    _restore_env(old)
+                assert got == want, (style, chunk, it)
+                lens = np.diff(b.offsets.astype(np.int64))
+                assert (int(lens.max()) if len(lens) else 0) == b.max_read_len
+
+
+@pytest.mark.parametrize("name", BUNDLED)
+def test_parser_pieces_bundled_files(name):
+    path = os.path.join(checkers.REF_DATA, name)
+    if not os.path.exists(path):
+        pytest.skip("bundled read sets not staged")
+    want = cb.Batch.from_file(path)
+    old = _pieces_env(20000, threads=3)
+    try:
+        got = cb.Batch.from_file(path)
+    finally:
+        _restore_env(old)
+    assert got.record_stream() == want.record_stream() == checkers.port().kseq_dump(path)
+    assert np.array_equal(got.offsets, want.offsets) and got.max_read_len == want.max_read_len
+    assert np.array_equal(got.bases, want.bases)
+
+
 def test_parse_missing_file_is_an_error():
     with pytest.raises(cb.CrassB200Error):
         cb.Batch.from_file("/nonexistent/file.fa")
