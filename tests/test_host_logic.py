@@ -7,6 +7,8 @@ import json
 import os
 import random
 import re
+import subprocess
+import sys
 import tempfile
 
 import numpy as np
@@ -95,6 +97,22 @@ def test_parser_fuzz_against_oracle():
             assert cb.Batch.from_file(p).record_stream() == P.kseq_dump(p), text
 
 
+_NAIVE = """
+import os, sys
+sys.path.insert(0, %r)
+import crass_b200 as cb
+n = 0
+for it in range(40):
+    p = os.path.join(sys.argv[1], "f%%d.fx" %% it)
+    want = open(p + ".want", "rb").read()
+    for chunk in (64, 300, 1500):
+        os.environ["CRASS_B200_PARSE_CHUNK"] = str(chunk)
+        assert cb.Batch.from_file(p).record_stream() == want, (it, chunk)
+    n += 1
+print("ok", n)
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
 def _pieces_env(chunk, threads=4):
     old = {k: os.environ.get(k) for k in ("CRASS_B200_PARSE_CHUNK", "CRASS_B200_PARSE_THREADS")}
     os.environ["CRASS_B200_PARSE_CHUNK"] = str(chunk)
@@ -146,6 +164,8 @@ def test_parser_pieces_on_worker_threads_match_the_sequential_stream():
             with open(p, "wb") as fh:
                 fh.write(text.encode("latin-1"))
             want = P.kseq_dump(p)
+            with open(p + ".want", "wb") as fh:
+                fh.write(want)
             for chunk in (64, 257, 1500, 6000):
                 old = _pieces_env(chunk)
                 try:
@@ -156,6 +176,11 @@ def test_parser_pieces_on_worker_threads_match_the_sequential_stream():
                 assert got == want, (style, chunk, it)
                 lens = np.diff(b.offsets.astype(np.int64))
                 assert (int(lens.max()) if len(lens) else 0) == b.max_read_len
+        # wrong guesses on purpose (any '>'/'@' byte is taken for a record start): pieces are dropped and the gaps parsed
+        # again from the true position.  The switch is read once per process, hence the child.
+        r = subprocess.run([sys.executable, "-c", _NAIVE, d], env=dict(os.environ, CRASS_B200_PARSE_GUESS="naive", CRASS_B200_PARSE_THREADS="4"),
+                           capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout.strip() == "ok 40", r.stdout + r.stderr
 
 
 @pytest.mark.parametrize("name", BUNDLED)
