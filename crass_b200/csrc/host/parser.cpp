@@ -280,23 +280,6 @@ size_t env_size(const char* name, size_t dflt) {
     return end && *end == 0 && x > 0 ? (size_t)x : dflt;
 }
 
-void append_piece(Batch* B, const Piece& P, int64_t& cur_comment, int64_t& cur_qual, uint64_t base0) {
-    const uint64_t name0 = B->name_pool.size();
-    const int64_t text0 = (int64_t)B->text_pool.size();
-    B->name_pool.insert(B->name_pool.end(), P.name_pool.begin(), P.name_pool.end());
-    B->text_pool.insert(B->text_pool.end(), P.text_pool.begin(), P.text_pool.end());
-    const size_t m = P.ends.size();
-    for (size_t r = 0; r < m; ++r) {
-        B->name_off.push_back(name0 + P.name_off[r]);
-        B->comment_off.push_back(P.comment_off[r] < 0 ? cur_comment : text0 + P.comment_off[r]);
-        B->qual_off.push_back(P.qual_off[r] < 0 ? cur_qual : text0 + P.qual_off[r]);
-        B->offsets.push_back(base0 + P.ends[r]);
-    }
-    if (P.last_comment >= 0) cur_comment = text0 + P.last_comment;
-    if (P.last_qual >= 0) cur_qual = text0 + P.last_qual;
-    if (P.max_len > B->max_len) B->max_len = P.max_len;
-}
-
 }  // namespace
 
 // Large inputs are cut at guessed record starts and the pieces parsed by worker threads (CRASS_B200_PARSE_THREADS,
@@ -327,8 +310,11 @@ int parse_file(const char* path, Batch** out) {
             Piece P;
             P.bases = B->bases; P.cap = B->bases_cap;
             parse_span(in.data, n, (size_t)-1, (size_t)-1, P);
-            int64_t cc = -1, cq = -1;
-            append_piece(B, P, cc, cq, 0);
+            B->name_pool.swap(P.name_pool); B->text_pool.swap(P.text_pool);   // piece-relative == batch-relative here
+            B->name_off.swap(P.name_off); B->comment_off.swap(P.comment_off); B->qual_off.swap(P.qual_off);
+            B->offsets.reserve(P.ends.size() + 1);
+            B->offsets.insert(B->offsets.end(), P.ends.begin(), P.ends.end());
+            B->max_len = P.max_len;
             B->parse_status = P.status;
             *out = B;
             return 0;
