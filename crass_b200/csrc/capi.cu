@@ -111,7 +111,11 @@ struct crass_b200_ctx {
     bool res_valid = false, res_found_valid = false;
     DevBuf d_found_p1, d_cand, d_tokens, d_tok_table, d_tok_unique, d_ac_table, d_ac_symv, d_ac_bitmap, d_ac_keys;
     DevBuf d_ac_skeys, d_ac_shead, d_ac_pnext, d_ac_poffs, d_ac_pbytes;
-    DevBuf d_cand_counts;                // K1 fast path: sizes of the two candidate lists
+    DevBuf d_cand_counts;                // K1 fast path: per chunk, sizes of the two candidate lists + queue head
+    // K1 fast path, chunk pipeline: the exact kernel of chunk i runs on `side` beside the filter kernel of chunk i+1
+    cudaStream_t side = nullptr;         // highest priority: its few CTAs take the room the filter grid leaves on every SM
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_chunk[16] = {};
     DevBuf d_ac_bitmap_small;            // folded copy of the q-gram bitmap for k_ac_filter_packed (0 bytes when unused)
     DevBuf d_cand_mask;                  // K2 fast path: per candidate, the aligned 16-mers that can belong to an occurrence
     // K5 (clustering passes A/B on the token block): device arrays and their pinned host mirrors
@@ -183,6 +187,12 @@ int crass_b200_ctx_create(int device, crass_b200_ctx** out) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    for (cudaEvent_t& e : c->ev_chunk) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUDA_TRY(cudaHostAlloc((void**)&c->h_counters, 8 * sizeof(uint32_t), cudaHostAllocDefault));
     *out = c;
     return 0;
@@ -202,6 +212,10 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
     for (PinnedBuf* b : {&c->h_cl_block, &c->h_cl_order, &c->h_cl_keys, &c->h_cl_first, &c->h_cl_info, &c->h_ac_stage,
                          &c->h_cl_group, &c->h_cl_dead, &c->h_cl_str}) b->release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    for (cudaEvent_t e : c->ev_chunk) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -255,7 +269,7 @@ int crass_b200_unique_tokens_dev(crass_b200_ctx* c, const crass_b200_hit* d_hits
     if (!c || !d_out_count) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
     if (stride < 8 || (stride & 3)) return cbh::fail(CRASS_B200_EINVAL, "token stride must be a multiple of 4, at least 8");
     CUDA_TRY(cudaSetDevice(c->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
+    cudaStream_t st = (cudaStream_t)stream_v;
     CUDA_TRY(cudaMemsetAsync(d_out_count, 0, sizeof(uint32_t), st));
     if (n_hits == 0) return 0;
     if (!d_hits || !d_tokens || !d_out_tokens || !d_out_first_read) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
@@ -279,7 +293,7 @@ int crass_b200_sort_hits_dev(crass_b200_ctx* c, const uint8_t* d_found, uint32_t
     if (((uintptr_t)d_found) & 15) return cbh::fail(CRASS_B200_EINVAL, "found flags must be 16-byte aligned");
     if (n_reads == 0 || max_hits == 0) return 0;
     CUDA_TRY(cudaSetDevice(c->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
+    cudaStream_t st = (cudaStream_t)stream_v;
     const uint32_t n_chunks = (n_reads + cbk::kRankChunk - 1) / cbk::kRankChunk;
     if (int r = c->d_rank.reserve((size_t)n_chunks * sizeof(uint32_t))) return r;
     uint32_t* chunks = c->d_rank.as<uint32_t>();
@@ -320,7 +334,7 @@ int crass_b200_unique_tokens_block_dev(crass_b200_ctx* c, const crass_b200_hit* 
     if (!c || !d_block || (n_hits && (!d_hits || !d_tokens))) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
     if (stride < 12 || (stride & 3) || cap == 0) return cbh::fail(CRASS_B200_EINVAL, "token stride must be a multiple of 4, at least 12; cap > 0");
     CUDA_TRY(cudaSetDevice(c->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
+    cudaStream_t st = (cudaStream_t)stream_v;
     cbk::HitTokens src{d_hits, (const uint8_t*)d_tokens, stride};
     return dedupe_into_block(c, src, n_hits, stride, d_block, cap, st);
 }
@@ -333,7 +347,7 @@ int crass_b200_merge_token_blocks_dev(crass_b200_ctx* c, const void* d_blocks, u
     if ((uint64_t)n_ranks * shard_reads > 0xFFFFFFFFull) return cbh::fail(CRASS_B200_EINVAL, "n_ranks * shard_reads must fit 32 bits");
     if ((uint64_t)n_ranks * cap > 0x7FFFFFFFull) return cbh::fail(CRASS_B200_EINVAL, "n_ranks * cap too large");
     CUDA_TRY(cudaSetDevice(c->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
+    cudaStream_t st = (cudaStream_t)stream_v;
     cbk::GatheredBlocks src{(const uint8_t*)d_blocks, cap, stride, shard_reads};
     if (int r = dedupe_into_block(c, src, n_ranks * cap, stride, d_out_block, out_cap, st)) return r;
     cbk::k_block_flags<<<1, 1024, 0, st>>>(src, n_ranks, (uint8_t*)d_out_block);
@@ -482,7 +496,7 @@ int crass_b200_cluster_block_dev(crass_b200_ctx* c, const void* d_block, uint32_
     if (n_patterns) *n_patterns = 0;
     CUDA_TRY(cudaSetDevice(c->device));
     std::vector<std::string> nr;
-    if (int r = cluster_block(c, d_block, cap, stride, kmer_clust, &nr, count, flags, stream_v ? (cudaStream_t)stream_v : c->stream)) return r;
+    if (int r = cluster_block(c, d_block, cap, stride, kmer_clust, &nr, count, flags, (cudaStream_t)stream_v)) return r;
     if (n_patterns) *n_patterns = (uint32_t)nr.size();
     if (nr.empty()) return 0;
     std::vector<uint8_t> bytes;
@@ -496,7 +510,7 @@ char* crass_b200_cluster_block_patterns_dev(crass_b200_ctx* c, const void* d_blo
     if (!c || !d_block || stride < 28 || (stride & 3) || cap == 0) { cbh::fail(CRASS_B200_EINVAL, "bad argument"); return nullptr; }
     if (cudaSetDevice(c->device) != cudaSuccess) { cbh::fail(CRASS_B200_ECUDA, "cudaSetDevice failed"); return nullptr; }
     std::vector<std::string> nr;
-    if (cluster_block(c, d_block, cap, stride, kmer_clust, &nr, count, flags, stream_v ? (cudaStream_t)stream_v : c->stream)) return nullptr;
+    if (cluster_block(c, d_block, cap, stride, kmer_clust, &nr, count, flags, (cudaStream_t)stream_v)) return nullptr;
     if (n_patterns) *n_patterns = (uint32_t)nr.size();
     size_t total = 1;
     for (const std::string& p : nr) total += p.size() + 1;
@@ -516,7 +530,7 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
     if (!c) return cbh::fail(CRASS_B200_EINVAL, "ctx is NULL");
     if (int r = validate_params(params)) return r;
     CUDA_TRY(cudaSetDevice(c->device));
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
+    cudaStream_t st = (cudaStream_t)stream_v;
     const cb::Params o = to_core(*params);
     CUDA_TRY(cudaMemsetAsync(d_counters, 0, 4 * sizeof(uint32_t), st));
     c->packed_valid = false;                                   // a 2-bit stream of an earlier batch is stale from here on
@@ -548,34 +562,83 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
         if (!d_found) { if (int r = c->d_found.reserve((size_t)n_reads + 16)) return r; d_found = c->d_found.as<uint8_t>(); }
         if (int r = c->d_cand.reserve(((size_t)n_reads + 16) * sizeof(uint32_t))) return r;
         uint32_t* cand = c->d_cand.as<uint32_t>();
-        if (int r = c->d_cand_counts.reserve(4 * sizeof(uint32_t))) return r;     // [0] several flagged windows, [1] a single one
+        // The batch is cut into chunks of whole tiles; the filter kernels follow each other on the caller's stream, the exact
+        // kernel of chunk i runs on the context's high-priority side stream while the filter works on chunk i+1.  The filter
+        // is bound by the integer pipe, the exact kernel by the latency of a few long dependent chains, so side by side
+        // they cost little more than the filter alone.  (CRASS_B200_K1_CHUNKS=1: one filter launch, then one exact launch.)
+        const uint32_t kChunkAlign = 1024;                                        // a multiple of both tile sizes
+        uint32_t n_chunks = 1;                    // measured (tools/k1_variants.py, 10 M x 150 bp): 1 chunk 0.63 ms, 2: 0.71, 4: 0.78
+        if (const char* e = getenv("CRASS_B200_K1_CHUNKS")) n_chunks = (uint32_t)std::min(16, std::max(1, atoi(e)));
+        uint32_t per_chunk = ((n_reads + n_chunks - 1) / n_chunks + kChunkAlign - 1) / kChunkAlign * kChunkAlign;
+        n_chunks = (n_reads + per_chunk - 1) / per_chunk;
+        if (int r = c->d_cand_counts.reserve(16 * 4 * sizeof(uint32_t))) return r;    // per chunk: [0] several flagged windows, [1] a single one, [2] queue head
         uint32_t* cand_counts = c->d_cand_counts.as<uint32_t>();
-        CUDA_TRY(cudaMemsetAsync(cand_counts, 0, 4 * sizeof(uint32_t), st));
+        CUDA_TRY(cudaMemsetAsync(cand_counts, 0, 16 * 4 * sizeof(uint32_t), st));
         uint32_t* keep = nullptr;
         if (int r = keep_stream(&keep)) return r;
-        const uint32_t n_tiles = (n_reads + cbk::kFilterTile - 1) / cbk::kFilterTile;
         const int se = (int)max_read_len - 58;
         const int nwin = se < 0 ? 1 : se / 16 + 1;
-        const int eblocks = c->sm_count * 8;
         int* d_err = c->d_error.as<int>();
+        const char* fsel = getenv("CRASS_B200_K1F");                               // "tma": CTA tiles staged by bulk copies; default: warp tiles
+        const char* esel = getenv("CRASS_B200_K1E");                               // "lockstep": 32 candidates per warp task; default: lane refill
+        const bool f_tma = fsel && !strcmp(fsel, "tma");
+        const bool e_lockstep = esel && !strcmp(esel, "lockstep");
+        // CTAs per SM: the filter leaves room for the exact kernel's CTAs when the two run side by side
+        int f_ctas = n_chunks > 1 ? 12 : 16, e_ctas = e_lockstep ? 8 : (n_chunks > 1 ? 2 : 4);
+        if (const char* e = getenv("CRASS_B200_K1F_CTAS")) f_ctas = std::max(1, atoi(e));
+        if (const char* e = getenv("CRASS_B200_K1E_CTAS")) e_ctas = std::max(1, atoi(e));
+        const bool piped = n_chunks > 1;
+        if (piped) {
+            CUDA_TRY(cudaEventRecord(c->ev_fork, st));
+            CUDA_TRY(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+        }
 #define CB_FAST(NW, NWIN)                                                                                                           \
     do {                                                                                                                            \
         const size_t fsmem = cbk::dr_filter_smem_bytes<NW>();                                                                       \
-        CUDA_TRY(cudaFuncSetAttribute(cbk::k_dr_filter<NW, NWIN, 49, 97>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); \
-        int per_sm = 1;                                                                                                             \
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbk::k_dr_filter<NW, NWIN, 49, 97>, cbk::kFilterTile, fsmem)); \
-        const int pblocks = (int)std::min<uint32_t>(n_tiles, (uint32_t)(c->sm_count * std::max(per_sm, 1)));    /* persistent: one wave */ \
-        cbk::k_dr_filter<NW, NWIN, 49, 97><<<pblocks, cbk::kFilterTile, fsmem, st>>>(d_bases, d_offsets, n_reads, d_found, cand, cand_counts, keep); \
         const size_t esmem = cbk::dr_exact_smem_bytes<NW>();                                                                        \
+        int per_sm = 1;                                                                                                             \
+        if (f_tma) {                                                                                                                \
+            CUDA_TRY(cudaFuncSetAttribute(cbk::k_dr_filter<NW, NWIN, 49, 97>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); \
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbk::k_dr_filter<NW, NWIN, 49, 97>, cbk::kFilterTile, fsmem)); \
+        } else {                                                                                                                    \
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbk::k_dr_filter_warp<NW, NWIN, 49, 97>, cbk::kFwWarps * 32, 0)); \
+        }                                                                                                                           \
+        per_sm = std::max(1, std::min(per_sm, f_ctas));                                                                             \
         CUDA_TRY(cudaFuncSetAttribute(cbk::k_dr_exact_packed<NW, NWIN, 49, 97>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem)); \
-        cbk::k_dr_exact_packed<NW, NWIN, 49, 97><<<eblocks, cbk::kExactThreads, esmem, st>>>(d_bases, d_offsets, n_reads, cand, cand_counts, o, d_found, sink, d_err); \
+        CUDA_TRY(cudaFuncSetAttribute(cbk::k_dr_exact_refill<NW, NWIN, 49, 97>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem)); \
+        for (uint32_t ch = 0; ch < n_chunks; ++ch) {                                                                                \
+            const uint32_t r_begin = ch * per_chunk, r_end = std::min(n_reads, r_begin + per_chunk);                                \
+            cbk::CandRegion region{cand, r_begin, r_end, cand_counts + 4 * ch};                                                     \
+            if (f_tma) {                                                                                                            \
+                const uint32_t t0 = r_begin / cbk::kFilterTile, t1 = (r_end + cbk::kFilterTile - 1) / cbk::kFilterTile;             \
+                const int pblocks = (int)std::min<uint32_t>(t1 - t0, (uint32_t)(c->sm_count * per_sm));     /* persistent: one wave */ \
+                cbk::k_dr_filter<NW, NWIN, 49, 97><<<pblocks, cbk::kFilterTile, fsmem, st>>>(d_bases, d_offsets, n_reads, t0, t1, d_found, region, keep); \
+            } else {                                                                                                                \
+                const uint32_t w_tiles = (r_end - r_begin + 31) / 32;                                                               \
+                const int pblocks = (int)((w_tiles + cbk::kFwWarps - 1) / cbk::kFwWarps);                    /* one tile per warp */ \
+                cbk::k_dr_filter_warp<NW, NWIN, 49, 97><<<pblocks, cbk::kFwWarps * 32, 0, st>>>(d_bases, d_offsets, n_reads, r_begin, r_end, d_found, region, keep); \
+            }                                                                                                                       \
+            cudaStream_t est = st;                                                                                                  \
+            if (piped) {                                                                                                            \
+                CUDA_TRY(cudaEventRecord(c->ev_chunk[ch], st));                                                                     \
+                CUDA_TRY(cudaStreamWaitEvent(c->side, c->ev_chunk[ch], 0));                                                         \
+                est = c->side;                                                                                                      \
+            }                                                                                                                       \
+            const int eblocks = c->sm_count * e_ctas;                                                                               \
+            if (e_lockstep) cbk::k_dr_exact_packed<NW, NWIN, 49, 97><<<eblocks, cbk::kExactThreads, esmem, est>>>(d_bases, d_offsets, n_reads, region, o, d_found, sink, d_err); \
+            else cbk::k_dr_exact_refill<NW, NWIN, 49, 97><<<eblocks, cbk::kExactThreads, esmem, est>>>(d_bases, d_offsets, n_reads, region, o, d_found, sink, d_err); \
+        }                                                                                                                           \
     } while (0)
         if (max_read_len <= 112) { if (nwin <= 3) CB_FAST(7, 3); else CB_FAST(7, 4); }
         else if (max_read_len <= 160) { if (nwin <= 6) CB_FAST(10, 6); else CB_FAST(10, 7); }
         else if (max_read_len <= 256) { if (nwin <= 12) CB_FAST(16, 12); else CB_FAST(16, 13); }
         else { if (nwin <= 15) CB_FAST(19, 15); else CB_FAST(19, 16); }
 #undef CB_FAST
-        c->launches += 2;
+        if (piped) {
+            CUDA_TRY(cudaEventRecord(c->ev_join, c->side));
+            CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));
+        }
+        c->launches += 2 * n_chunks;
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
@@ -624,6 +687,8 @@ int run_with_outputs(crass_b200_ctx* c, uint32_t n_reads, uint64_t n_bases, uint
     uint32_t pool_cap = hits_cap * 6;
     if (int r = c->d_counters.reserve(8 * sizeof(uint32_t))) return r;
     if (int r = c->d_found.reserve((size_t)n_reads + 16)) return r;
+    // the "reference would throw" flag belongs to this call: a flag left by an earlier search must not fail a scan
+    if (c->d_error.p) CUDA_TRY(cudaMemsetAsync(c->d_error.p, 0, sizeof(int), c->stream));
     for (int attempt = 0; attempt < 3; ++attempt) {
         if (int r = c->d_hits.reserve((size_t)hits_cap * sizeof(crass_b200_hit))) return r;
         if (int r = c->d_pool.reserve((size_t)pool_cap * sizeof(uint32_t))) return r;
@@ -811,6 +876,9 @@ int ensure_ac_on_device(crass_b200_ctx* c, crass_b200_ac* ac) {
     cbh::Automaton& a = ac->a;
     if (c->ac_serial == a.serial && a.serial != 0) return 0;
     c->ac_dfa_serial = 0;
+    // the tables are context-owned and about to be overwritten: a scan of the previous matcher may still be running on
+    // a stream of the caller's that c->stream knows nothing about
+    CUDA_TRY(cudaDeviceSynchronize());
     if (a.q_bits) {                                   // filter + pattern-start table (fast path)
         struct Up { DevBuf* d; const void* h; size_t bytes; } ups[] = {
             {&c->d_ac_bitmap, a.q_bitmap.data(), a.q_bitmap.size() * sizeof(uint32_t)},
@@ -865,7 +933,7 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
     crass_b200_ac* ac = const_cast<crass_b200_ac*>(ac_c);
     CUDA_TRY(cudaSetDevice(c->device));
     if (int r = ensure_ac_on_device(c, ac)) return r;
-    cudaStream_t st = stream_v ? (cudaStream_t)stream_v : c->stream;
+    cudaStream_t st = (cudaStream_t)stream_v;
     CUDA_TRY(cudaMemsetAsync(d_counters, 0, 4 * sizeof(uint32_t), st));
     if (n_reads == 0) return 0;
     cbk::HitSink sink{d_hits, hits_cap, d_ss_pool, ss_cap, d_counters, nullptr, 0};
@@ -1067,7 +1135,7 @@ int crass_b200_update_start_stops_dev(crass_b200_ctx* c, const uint8_t* d_bases,
         return cbh::fail(CRASS_B200_EINVAL, "update_start_stops: NULL argument");
     CUDA_TRY(cudaSetDevice(c->device));
     if (n_jobs == 0) return 0;
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = (cudaStream_t)stream;
     const char* sel = getenv("CRASS_B200_K6");
     if (sel && !strcmp(sel, "thread")) {                              // one thread per read: kept for comparison
         const int blocks = (int)((n_jobs + cbk::kUssThreads - 1) / cbk::kUssThreads);

@@ -160,8 +160,8 @@ CB_HD bool seed_filter(const uint32_t* R) {
 // active threads per instruction), this form re-converges after every stage.
 template <int NW, int NWIN, int DMIN, int DMAX, class Seq>
 struct PackedSearch {
-    const Seq& s;
-    const uint32_t L;
+    Seq s;                                                      // by value: a refilled lane moves on to another read (rebind)
+    uint32_t L;
     const Params& o;
     const uint32_t* S;
     uint32_t* ss;
@@ -173,6 +173,7 @@ struct PackedSearch {
     CB_HD PackedSearch(const Seq& s_, uint32_t L_, const Params& o_, const uint32_t* S_, uint32_t* ss_, uint32_t cap_)
         : s(s_), L(L_), o(o_), S(S_), ss(ss_), cap(cap_) {}
 
+    CB_HD void rebind(const Seq& s_, uint32_t L_) { s = s_; L = L_; }
     CB_HD void init(uint32_t mask0) {
         se = search_end(o, L);
         base = 0; mask = mask0; n_ss = 0; replen = 0; result = 0; pos = -1;

@@ -12,6 +12,7 @@
 #include <limits.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -19,6 +20,7 @@
 #include <condition_variable>
 #include <functional>
 #include <mutex>
+#include <new>
 #include <sstream>
 #include <thread>
 #include <unordered_map>
@@ -156,36 +158,58 @@ public:
     static WorkerPool& instance() { static WorkerPool p; return p; }
     void run(unsigned n, const std::function<void(unsigned)>& job) {
         if (n <= 1) { job(0); return; }
+        after_fork();
         std::lock_guard<std::mutex> one_region(region_);
         {
             std::lock_guard<std::mutex> l(m_);
-            while (threads_.size() < n - 1) { const unsigned id = (unsigned)threads_.size(); threads_.emplace_back([this, id]() { loop(id); }); }
-            job_ = &job; n_active_ = n - 1; pending_ = n - 1; ++generation_;
+            while (threads_->size() < n - 1) { const unsigned id = (unsigned)threads_->size(); threads_->emplace_back([this, id]() { loop(id); }); }
+            job_ = &job; n_active_ = n - 1; pending_ = n - 1; ++generation_; failure_ = nullptr;
         }
         posted_.store(generation_, std::memory_order_release);
         wake_.notify_all();
-        job(0);
+        std::exception_ptr mine;
+        try { job(0); } catch (...) { mine = std::current_exception(); }   // the helpers still have to finish before the caller unwinds
         std::unique_lock<std::mutex> l(m_);
         done_.wait(l, [this]() { return pending_ == 0; });
+        std::exception_ptr theirs = failure_;
+        failure_ = nullptr;
+        l.unlock();
+        if (mine) std::rethrow_exception(mine);
+        if (theirs) std::rethrow_exception(theirs);                     // e.g. bad_alloc inside a helper: the caller turns it into ENOMEM
     }
     // A caller that knows a parallel region is coming within the next fraction of a millisecond (the GPU is still busy
     // with the kernels that feed it) gets the helpers out of their sleep early: they spin for a job until the deadline.
     void prewake(unsigned n, unsigned spin_us) {
         if (n <= 1) return;
+        after_fork();
         {
             std::lock_guard<std::mutex> l(m_);
-            while (threads_.size() < n - 1) { const unsigned id = (unsigned)threads_.size(); threads_.emplace_back([this, id]() { loop(id); }); }
+            while (threads_->size() < n - 1) { const unsigned id = (unsigned)threads_->size(); threads_->emplace_back([this, id]() { loop(id); }); }
             spin_until_ = std::chrono::steady_clock::now() + std::chrono::microseconds(spin_us);
             ++prewake_;
         }
         wake_.notify_all();
     }
     ~WorkerPool() {
+        if (getpid() != pid_) return;                                // a forked child never had the threads
         { std::lock_guard<std::mutex> l(m_); stop_ = true; }
         wake_.notify_all();
-        for (auto& t : threads_) t.join();
+        for (auto& t : *threads_) t.join();
+        delete threads_;
     }
 private:
+    WorkerPool() : threads_(new std::vector<std::thread>()), pid_(getpid()) {}
+    // Helper threads do not survive fork(): in a child (Python multiprocessing with the fork start method) the pool
+    // starts over with fresh threads and fresh synchronisation objects.  The parent's thread handles and whatever
+    // state its mutexes were in at the time of the fork are abandoned, not destroyed.
+    void after_fork() {
+        if (getpid() == pid_) return;
+        threads_ = new std::vector<std::thread>();
+        new (&region_) std::mutex(); new (&m_) std::mutex();
+        new (&wake_) std::condition_variable(); new (&done_) std::condition_variable();
+        job_ = nullptr; n_active_ = pending_ = 0; generation_ = prewake_ = 0; posted_.store(0); stop_ = false; failure_ = nullptr;
+        pid_ = getpid();
+    }
     void loop(unsigned id) {
         uint64_t seen = 0, seen_prewake = 0;
         for (;;) {
@@ -210,14 +234,18 @@ private:
                 seen_prewake = prewake_;
                 job = job_;
             }
-            (*job)(id + 1);
+            std::exception_ptr err;
+            try { (*job)(id + 1); } catch (...) { err = std::current_exception(); }
             std::lock_guard<std::mutex> l(m_);
+            if (err && !failure_) failure_ = err;
             if (--pending_ == 0) done_.notify_one();
         }
     }
     std::mutex region_, m_;
     std::condition_variable wake_, done_;
-    std::vector<std::thread> threads_;
+    std::vector<std::thread>* threads_;
+    pid_t pid_;
+    std::exception_ptr failure_;
     const std::function<void(unsigned)>* job_ = nullptr;
     unsigned n_active_ = 0, pending_ = 0;
     uint64_t generation_ = 0, prewake_ = 0;
@@ -551,46 +579,58 @@ std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& 
             }
         }
     };
+    // A pass that throws (bad_alloc) must not leave the other workers waiting at the next barrier: the failure is noted,
+    // every worker still walks through all the barriers with the remaining passes skipped, and the caller rethrows.
+    std::atomic<bool> failed{false};
+    auto guarded = [&](auto&& pass) {
+        if (failed.load(std::memory_order_relaxed)) return;
+        try { pass(); } catch (...) { failed.store(true); }
+    };
     auto worker = [&](unsigned w) {
-        if (pre) {                                                        // A and B came from the GPU: only list the string-keyed k-mers
-            if (pre->n_string_keys && pre->string_tq) {                   // ... which the GPU may have listed already
-                if (w == 0) {
-                    for (uint32_t i = 0; i < pre->n_string_keys; ++i) {
-                        const uint32_t t = pre->string_tq[2 * i], q = pre->string_tq[2 * i + 1];
-                        if (t < n_dr && q >= koff[t] && q < koff[t + 1] && keys[q] == kStrKey) str_pos[0].push_back(std::make_pair(t, q));
+        guarded([&]() {
+            if (pre) {                                                    // A and B came from the GPU: only list the string-keyed k-mers
+                if (pre->n_string_keys && pre->string_tq) {               // ... which the GPU may have listed already
+                    if (w == 0) {
+                        for (uint32_t i = 0; i < pre->n_string_keys; ++i) {
+                            const uint32_t t = pre->string_tq[2 * i], q = pre->string_tq[2 * i + 1];
+                            if (t < n_dr && q >= koff[t] && q < koff[t + 1] && keys[q] == kStrKey) str_pos[0].push_back(std::make_pair(t, q));
+                        }
+                        std::sort(str_pos[0].begin(), str_pos[0].end());   // DR order, as the sequential map needs it
+                        any_str.store(true, std::memory_order_relaxed);
                     }
-                    std::sort(str_pos[0].begin(), str_pos[0].end());       // DR order, as the sequential map needs it
-                    any_str.store(true, std::memory_order_relaxed);
-                }
-            } else if (pre->n_string_keys)
-                for (size_t t = cut[w]; t < cut[w + 1]; ++t)
-                    for (size_t q = koff[t]; q < koff[t + 1]; ++q)
-                        if (keys[q] == kStrKey) { any_str.store(true, std::memory_order_relaxed); str_pos[w].push_back(std::make_pair((uint32_t)t, (uint32_t)q)); }
-        } else {
-            pass_a(w, cut[w], cut[w + 1]);
-            pass_b(w, cut[w], cut[w + 1]);
-        }
+                } else if (pre->n_string_keys)
+                    for (size_t t = cut[w]; t < cut[w + 1]; ++t)
+                        for (size_t q = koff[t]; q < koff[t + 1]; ++q)
+                            if (keys[q] == kStrKey) { any_str.store(true, std::memory_order_relaxed); str_pos[w].push_back(std::make_pair((uint32_t)t, (uint32_t)q)); }
+            } else {
+                pass_a(w, cut[w], cut[w + 1]);
+                pass_b(w, cut[w], cut[w + 1]);
+            }
+        });
         barrier.wait();
         if (w == 0) CB_NR_MARK("pass A+B");
         if (any_str.load()) {
-            if (w == 0) resolve_str();
+            if (w == 0) guarded(resolve_str);
             barrier.wait();
         }
-        pass_b2(cut[w], cut[w + 1]);
+        guarded([&]() { pass_b2(cut[w], cut[w + 1]); });
         barrier.wait();
-        if (w == 0) { CB_NR_MARK("pass B2"); pass_c(); CB_NR_MARK("pass C"); }
+        if (w == 0) { CB_NR_MARK("pass B2"); guarded(pass_c); CB_NR_MARK("pass C"); }
         barrier.wait();
-        HeadTable map, full;
-        for (size_t i; (i = next_group.fetch_add(1)) < schedule.size();) {
-            const size_t g = schedule[i];
-            if (!use_dead) { reduce_group(g, map, full); continue; }
-            std::vector<int> v;                                           // the group's survivors, shortest first (stable)
-            for (int tok : members[g]) if (!dead[(size_t)tok - 2] && !drs[(size_t)tok - 2].empty()) v.push_back(tok - 2);
-            std::stable_sort(v.begin(), v.end(), [&](int a, int b) { return drs[a].size() < drs[b].size(); });
-            for (int t : v) { survivors[g].emplace_back(drs[t]); survivors_rc[g].push_back(reverse_complement(survivors[g].back())); }
-        }
+        guarded([&]() {
+            HeadTable map, full;
+            for (size_t i; (i = next_group.fetch_add(1)) < schedule.size();) {
+                const size_t g = schedule[i];
+                if (!use_dead) { reduce_group(g, map, full); continue; }
+                std::vector<int> v;                                       // the group's survivors, shortest first (stable)
+                for (int tok : members[g]) if (!dead[(size_t)tok - 2] && !drs[(size_t)tok - 2].empty()) v.push_back(tok - 2);
+                std::stable_sort(v.begin(), v.end(), [&](int a, int b) { return drs[a].size() < drs[b].size(); });
+                for (int t : v) { survivors[g].emplace_back(drs[t]); survivors_rc[g].push_back(reverse_complement(survivors[g].back())); }
+            }
+        });
     };
     WorkerPool::instance().run(n_workers, worker);
+    if (failed.load()) throw std::bad_alloc();
     CB_NR_MARK("reduce");
     std::vector<std::string> out;
     for (size_t g = 0; g < members.size(); ++g) {

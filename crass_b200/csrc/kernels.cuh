@@ -610,23 +610,32 @@ __device__ __forceinline__ void tile_pack(const uint8_t* __restrict__ bases, uin
 template <int NW>
 constexpr size_t dr_filter_smem_bytes() { return (size_t)(kFilterTile * NW + NW + 8) * 20; }   // 16 B/vector bytes + 4 B/vector packed
 
+// Where a filter launch leaves its candidate reads and the exact kernel of the same chunk picks them up.  Two lists
+// in one array: reads with several flagged windows (nearly all reads that carry an array) fill [lo, hi) from the front,
+// reads with a single flagged window (mostly chance 8-mer repeats) from the back.
+struct CandRegion {
+    uint32_t* list;
+    uint32_t lo, hi;
+    uint32_t* counts;          // [0] front entries, [1] back entries, [2] queue head of k_dr_exact_refill
+};
+
 template <int NW, int NWIN, int DMIN, int DMAX>
 __global__ void __launch_bounds__(kFilterTile)
 k_dr_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads,
-            uint8_t* __restrict__ found, uint32_t* __restrict__ cand_list, uint32_t* __restrict__ cand_counts,
+            uint32_t tile_begin, uint32_t tile_end, uint8_t* __restrict__ found, CandRegion cand,
             uint32_t* __restrict__ keep_packed) {
     constexpr int kWords = kFilterTile * NW + NW + 8;          // packed words a tile can need (+ look-ahead + realignment)
     extern __shared__ __align__(128) uint8_t dyn_smem[];       // dr_filter_smem_bytes<NW>() bytes
     uint8_t* buf = dyn_smem;                                   // the tile's bytes, written by the bulk copy
     uint32_t* sm = reinterpret_cast<uint32_t*>(dyn_smem + kWords * 16);   // the same tile, 2 bits per base
     __shared__ uint64_t full;
-    const uint32_t n_tiles = (n_reads + kFilterTile - 1) / kFilterTile;
+    const uint32_t n_tiles = tile_end;                         // this launch covers the tiles [tile_begin, tile_end) of the batch
     const uint64_t n_bases = offsets[n_reads];
     if (threadIdx.x == 0) mbar_init(&full, 1);
     __syncthreads();
-    if (threadIdx.x == 0 && blockIdx.x < n_tiles) tile_issue<kFilterTile, NW>(bases, offsets, n_reads, n_bases, blockIdx.x, buf, &full);
+    if (threadIdx.x == 0 && tile_begin + blockIdx.x < n_tiles) tile_issue<kFilterTile, NW>(bases, offsets, n_reads, n_bases, tile_begin + blockIdx.x, buf, &full);
     uint32_t parity = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, parity ^= 1u) {
+    for (uint32_t tile = tile_begin + blockIdx.x; tile < n_tiles; tile += gridDim.x, parity ^= 1u) {
         const uint32_t r0 = tile * kFilterTile;
         const uint32_t r1 = min(r0 + (uint32_t)kFilterTile, n_reads);
         uint64_t a0; uint32_t want, tma_bytes;
@@ -645,18 +654,95 @@ k_dr_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs
             for (int k = 0; k < NW + 2; ++k) R[k] = cb::funnel_r(sm[wi + k], sm[wi + k + 1], sh);
             uint32_t acc[NWIN];
             cb::seed_flags<NW, NWIN, DMIN, DMAX>(R, acc);
-            const bool cand = cb::any_flag<NWIN>(acc);
             found[r] = 0;
-            if (cand) {
-                // Two lists in one array: reads with several flagged windows (nearly all reads that carry an array) fill it
-                // from the front, reads with a single flagged window (mostly chance 8-mer repeats) from the back.  The
-                // exact kernel never mixes the two in a warp, so the long stages run with full warps and the chance
-                // candidates are dismissed together.
-                if (__popc(cb::flag_mask<NWIN>(acc)) >= 2) cand_list[atomicAdd(&cand_counts[0], 1u)] = r;
-                else cand_list[n_reads - 1u - atomicAdd(&cand_counts[1], 1u)] = r;
+            if (cb::any_flag<NWIN>(acc)) {
+                if (__popc(cb::flag_mask<NWIN>(acc)) >= 2) cand.list[cand.lo + atomicAdd(&cand.counts[0], 1u)] = r;
+                else cand.list[cand.hi - 1u - atomicAdd(&cand.counts[1], 1u)] = r;
             }
         }
         __syncthreads();                                        // everyone is done with the packed tile
+    }
+}
+
+// ---- K1 fast path, stage 1, warp tiles (the default) ------------------------------------------------------------
+// The same filter without a staged copy of the bytes: a tile is the 32 consecutive reads of one WARP.  The lanes fetch the
+// tile's 16-byte vectors straight from global memory (coalesced, streaming), recode them on the way and keep only the
+// 2-bit words in a warp-private slice of shared memory (1.3 KB at 150 bp); then every lane realigns its own read out of
+// that slice and evaluates the window flags in registers as before.  No CTA barrier, no byte buffer: 5.4 KB of shared
+// memory and 32 registers per 128-thread CTA, so all 64 warps of an SM are resident (the CTA-tile kernel above stages
+// 16 + 4 bytes per vector and stops at 8 CTAs), which is what an ALU-bound kernel with ~540 instructions per read needs
+// to keep the pipe fed.  Latency is hidden by the other warps instead of by a bulk copy in flight.
+constexpr int kFwWarps = 4;
+
+__device__ __noinline__ uint4 ragged_vector(const uint8_t* __restrict__ bases, uint64_t at, uint64_t n_bases) {
+    uint32_t q[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 16; ++i)
+        if (at + i < n_bases) q[i >> 2] |= (uint32_t)__ldg(bases + at + i) << (8 * (i & 3));
+    return make_uint4(q[0], q[1], q[2], q[3]);
+}
+
+template <int NW, int NWIN, int DMIN, int DMAX>
+__global__ void __launch_bounds__(kFwWarps * 32, (NW <= 10 ? 16 : 8))
+k_dr_filter_warp(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads,
+                 uint32_t r_begin, uint32_t r_end, uint8_t* __restrict__ found, CandRegion cand,
+                 uint32_t* __restrict__ keep_packed) {
+    constexpr int kWords = 32 * NW + NW + 8;                   // a warp tile's packed words (+ look-ahead + realignment)
+    __shared__ uint32_t sm_all[kFwWarps][kWords];
+    uint32_t* sm = sm_all[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31u;
+    // one tile per warp, no loop: nothing but the read's own registers is live while the flags are evaluated
+    const uint32_t r0 = r_begin + ((blockIdx.x * kFwWarps + (threadIdx.x >> 5)) << 5);
+    if (r0 >= r_end) return;
+    const uint32_t r1 = min(r0 + 32u, r_end);
+    const uint32_t r = r0 + lane;
+    uint32_t b;                                                 // base offset of the lane's read inside the packed tile
+    {
+        const uint64_t my_off = offsets[min(r, r1 - 1u)];       // one coalesced load; the tile's extent comes by shuffle
+        const uint64_t a0 = __shfl_sync(0xFFFFFFFFu, my_off, 0) & ~(uint64_t)15;
+        const uint64_t last_off = __shfl_sync(0xFFFFFFFFu, my_off, (int)(r1 - 1u - r0));
+        b = (uint32_t)(my_off - a0);
+        // the last read's realignment touches the words [wi, wi + NW + 2]
+        uint32_t nvec = (uint32_t)((last_off - a0) >> 4) + NW + 3;
+        if (nvec > (uint32_t)kWords) nvec = kWords;
+        uint32_t* keep = keep_packed ? keep_packed + (a0 >> 4) : nullptr;
+        const uint64_t n_bases = offsets[n_reads];
+        const uint64_t avail = (n_bases - a0) >> 4;             // whole vectors the batch still holds from a0 on
+        const uint32_t n_whole = avail < (uint64_t)nvec ? (uint32_t)avail : nvec;
+        const uint8_t* src = bases + a0 + 16u * lane;
+#pragma unroll 1
+        for (uint32_t v0 = lane; v0 < n_whole; v0 += 128u, src += 2048) {
+            uint4 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)                         // four independent 128-bit loads in flight per lane
+                if (v0 + 32u * u < n_whole) x[u] = ldg_stream128(src + 512 * u);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (v0 + 32u * u < n_whole) {
+                    const uint32_t w = cb::pack16(x[u].x, x[u].y, x[u].z, x[u].w);
+                    sm[v0 + 32u * u] = w;
+                    if (keep) keep[v0 + 32u * u] = w;
+                }
+            }
+        }
+        for (uint32_t v = n_whole + lane; v < nvec; v += 32u) {     // ragged end of the batch (last tile only)
+            const uint4 x = ragged_vector(bases, a0 + 16ull * v, n_bases);
+            const uint32_t w = cb::pack16(x.x, x.y, x.z, x.w);
+            sm[v] = w;
+            if (keep) keep[v] = w;
+        }
+    }
+    __syncwarp();
+    if (r >= r1) return;
+    const uint32_t wi = b >> 4, sh = (b & 15u) * 2u;
+    uint32_t R[NW + 2];
+#pragma unroll
+    for (int k = 0; k < NW + 2; ++k) R[k] = cb::funnel_r(sm[wi + k], sm[wi + k + 1], sh);
+    uint32_t acc[NWIN];
+    cb::seed_flags<NW, NWIN, DMIN, DMAX>(R, acc);
+    found[r] = 0;
+    if (cb::any_flag<NWIN>(acc)) {
+        if (__popc(cb::flag_mask<NWIN>(acc)) >= 2) cand.list[cand.lo + atomicAdd(&cand.counts[0], 1u)] = r;
+        else cand.list[cand.hi - 1u - atomicAdd(&cand.counts[1], 1u)] = r;
     }
 }
 
@@ -678,13 +764,12 @@ constexpr size_t dr_exact_smem_bytes() { return (size_t)kExactThreads * ((((NW +
 template <int NW, int NWIN, int DMIN, int DMAX>
 __global__ void __launch_bounds__(kExactThreads)
 k_dr_exact_packed(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads,
-                  const uint32_t* __restrict__ cand_list, const uint32_t* __restrict__ cand_counts, Params o,
-                  uint8_t* __restrict__ found, HitSink sink, int* __restrict__ error_flag) {
+                  CandRegion cand, Params o, uint8_t* __restrict__ found, HitSink sink, int* __restrict__ error_flag) {
     constexpr int kSlot = (NW + 4) | 1;                         // odd strides: conflict-free per-thread slots
     constexpr int kByteSlot = ((NW + 3) * 4) | 1;               // words holding the NW + 3 byte vectors of the read
     extern __shared__ uint32_t sm[];                            // dr_exact_smem_bytes<NW>()
-    const uint32_t n_front = cand_counts[0], n_back = cand_counts[1];      // the two lists of k_dr_filter
-    if (blockIdx.x == 0 && threadIdx.x == 0) sink.counters[3] = n_front + n_back;
+    const uint32_t n_front = cand.counts[0], n_back = cand.counts[1];      // the two lists of the filter kernel
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&sink.counters[3], n_front + n_back);   // the chunks of a batch add up
     const uint64_t n_bases = offsets[n_reads];
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t tasks_front = (n_front + 31u) >> 5, tasks = tasks_front + ((n_back + 31u) >> 5);
@@ -696,7 +781,7 @@ k_dr_exact_packed(const uint8_t* __restrict__ bases, const uint64_t* __restrict_
         const bool front = task < tasks_front;
         const uint32_t i = ((front ? task : task - tasks_front) << 5) + (threadIdx.x & 31u);
         const bool active = i < (front ? n_front : n_back);
-        const uint32_t r = active ? cand_list[front ? i : n_reads - 1u - i] : 0u;
+        const uint32_t r = active ? cand.list[front ? cand.lo + i : cand.hi - 1u - i] : 0u;
         const uint64_t b = active ? offsets[r] : 0ull;
         const uint32_t L = active ? (uint32_t)(offsets[r + 1] - b) : 0u;
         SmemSeq s{reinterpret_cast<const uint8_t*>(B) + (uint32_t)(b & 15u)};
@@ -748,6 +833,95 @@ k_dr_exact_packed(const uint8_t* __restrict__ bases, const uint64_t* __restrict_
             found[r] = 1;
             const uint32_t slot = emit_hit(sink, r, ss, st.n_ss, st.replen);
             if (sink.tokens && slot != 0xFFFFFFFFu) emit_token(sink.tokens + (size_t)slot * sink.token_stride, sink.token_stride, s, L, ss, st.n_ss);
+        }
+        __syncwarp();
+    }
+}
+
+// ---- K1 fast path, stage 2 with lane refill (the default) ---------------------------------------------------------
+// The same per-lane state machine, but a lane that is through with its candidate takes the next one from a queue instead
+// of idling until the slowest lane of its group of 32 is done: the warp loops over the stages (pick / find / seed /
+// re-flag) and, whenever at least kRefillMin lanes are free, runs one fetch stage in which they load new candidates.
+// A candidate with a rejected array and a second seed further on no longer holds 31 finished lanes hostage, so a few
+// warps per SM get through the list -- which leaves the rest of the SM to the filter kernel of the next chunk running
+// beside it (capi.cu pipelines the chunks on two streams).
+constexpr uint32_t kRefillMin = 8;
+
+template <int NW, int NWIN, int DMIN, int DMAX>
+__global__ void __launch_bounds__(kExactThreads)
+k_dr_exact_refill(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads,
+                  CandRegion cand, Params o, uint8_t* __restrict__ found, HitSink sink, int* __restrict__ error_flag) {
+    constexpr int kSlot = (NW + 4) | 1;
+    constexpr int kByteSlot = ((NW + 3) * 4) | 1;
+    extern __shared__ uint32_t sm[];                            // dr_exact_smem_bytes<NW>()
+    const uint32_t n_front = cand.counts[0], n_back = cand.counts[1], total = n_front + n_back;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&sink.counters[3], total);
+    const uint64_t n_bases = offsets[n_reads];
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t* S = sm + threadIdx.x * kSlot;
+    uint32_t* B = sm + kExactThreads * kSlot + threadIdx.x * kByteSlot;
+    uint32_t ss[32];
+    cb::PackedSearch<NW, NWIN, DMIN, DMAX, SmemSeq> st(SmemSeq{reinterpret_cast<const uint8_t*>(B)}, 0u, o, S, ss, 32u);
+    bool busy = false, exhausted = false;
+    uint32_t r = 0;
+    for (;;) {
+        const uint32_t free_mask = __ballot_sync(0xFFFFFFFFu, !busy);
+        if (!exhausted && (free_mask == 0xFFFFFFFFu || __popc(free_mask) >= kRefillMin)) {
+            const uint32_t want = __popc(free_mask);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&cand.counts[2], want);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            exhausted = base + want >= total;
+            const uint32_t q = base + __popc(free_mask & ((1u << lane) - 1u));
+            if (!busy && q < total) {
+                r = q < n_front ? cand.list[cand.lo + q] : cand.list[cand.hi - 1u - (q - n_front)];
+                const uint64_t b = offsets[r];
+                const uint32_t L = (uint32_t)(offsets[r + 1] - b);
+                const uint64_t a0 = b & ~(uint64_t)15;
+                const uint32_t sh = (uint32_t)(b & 15u) * 2u;
+                uint32_t prev = 0;
+                uint32_t R[NW + 2];
+#pragma unroll
+                for (int v = 0; v < NW + 3; ++v) {
+                    const uint64_t at = a0 + 16ull * v;
+                    uint4 x;
+                    if (at + 16 <= n_bases) x = __ldg(reinterpret_cast<const uint4*>(bases + at));
+                    else x = ragged_vector(bases, at, n_bases);
+                    B[4 * v] = x.x; B[4 * v + 1] = x.y; B[4 * v + 2] = x.z; B[4 * v + 3] = x.w;
+                    const uint32_t w = cb::pack16(x.x, x.y, x.z, x.w);
+                    if (v > 0) R[v - 1] = cb::funnel_r(prev, w, sh);
+                    prev = w;
+                }
+#pragma unroll
+                for (int k = 0; k < NW + 2; ++k) S[k] = R[k];
+                uint32_t acc[NWIN];
+                cb::seed_flags<NW, NWIN, DMIN, DMAX>(R, acc);
+                st.rebind(SmemSeq{reinterpret_cast<const uint8_t*>(B) + (uint32_t)(b & 15u)}, L);
+                st.init(cb::flag_mask<NWIN>(acc));
+                busy = true;
+            }
+            __syncwarp();
+        }
+        if (!__any_sync(0xFFFFFFFFu, busy)) {
+            if (exhausted) break;
+            continue;
+        }
+        st.pick();
+        st.find();
+        __syncwarp();
+        st.seed();
+        __syncwarp();
+        st.reflag();
+        __syncwarp();
+        if (busy && st.done) {                                  // this lane's read is settled: report, then the slot is free
+            const int f = st.result;
+            if (f < 0) *error_flag = f;
+            if (f == 1) {
+                found[r] = 1;
+                const uint32_t slot = emit_hit(sink, r, ss, st.n_ss, st.replen);
+                if (sink.tokens && slot != 0xFFFFFFFFu) emit_token(sink.tokens + (size_t)slot * sink.token_stride, sink.token_stride, st.s, st.L, ss, st.n_ss);
+            }
+            busy = false;
         }
         __syncwarp();
     }

@@ -46,8 +46,14 @@ class TokenExchange:
             self.merged = self.send
         self.host = torch.empty(self.merged.numel(), dtype=torch.uint8, pin_memory=True)
 
-    def run(self, d_hits, n_hits, d_tokens, stream=0):
+    def _stream(self, stream):
+        """The exchange's kernels, the NCCL calls and the host copies must be ordered on ONE stream: torch's current
+        stream of the device unless the caller names another (and has made it torch's current stream)."""
+        return torch.cuda.current_stream(self.dev).cuda_stream if stream is None else stream
+
+    def run(self, d_hits, n_hits, d_tokens, stream=None):
         """-> (merged DR list as '\\n'-terminated text, number of distinct tokens of this shard or None when N > 1)"""
+        stream = self._stream(stream)
         while True:
             self.ctx.unique_tokens_block_dev(d_hits, n_hits, d_tokens, self.stride, self.send, self.cap, stream)
             if self.world > 1:
@@ -63,10 +69,11 @@ class TokenExchange:
                 continue
             return text, count
 
-    def run_matcher(self, d_hits, n_hits, d_tokens, kmer_clust=6, stream=0):
+    def run_matcher(self, d_hits, n_hits, d_tokens, kmer_clust=6, stream=None):
         """The same exchange, ending in createNonRedundantSet + matcher build straight from the merged block
         -> (api.Automaton or None when there is no DR, number of distinct DR variants)."""
         import time
+        stream = self._stream(stream)
         while True:
             t0 = time.perf_counter()
             self.ctx.unique_tokens_block_dev(d_hits, n_hits, d_tokens, self.stride, self.send, self.cap, stream)
@@ -114,8 +121,9 @@ class PatternExchange(TokenExchange):
         self.msg = torch.zeros(self.HEADER + text_cap, dtype=torch.uint8, device=self.dev)
         self.msg_host = torch.zeros(self.HEADER + text_cap, dtype=torch.uint8, pin_memory=True)
 
-    def run(self, d_hits, n_hits, d_tokens, stream=0):
+    def run(self, d_hits, n_hits, d_tokens, stream=None):
         """-> (pattern set as '\\n'-terminated text, number of distinct DR variants over all ranks)"""
+        stream = self._stream(stream)
         if self.world == 1:
             text, count = super().run(d_hits, n_hits, d_tokens, stream)
             return (api.non_redundant_patterns(text, self.kmer_clust) if text else b""), count
@@ -127,28 +135,33 @@ class PatternExchange(TokenExchange):
             dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
             hdr = self.msg_host[: self.HEADER].numpy()
             if self.rank == self.root:
-                self.ctx.merge_token_blocks_dev(self.recv, self.world, self.cap, self.stride, self.shard_reads, self.merged, self.out_cap, stream)
-                if _HOST_PASSES:
-                    self.host.copy_(self.merged, non_blocking=True)
-                    torch.cuda.current_stream(self.dev).synchronize()
-                    t1 = time.perf_counter()
-                    text, count, flags = api.non_redundant_patterns_from_block(self.host, self.out_cap, self.stride, self.kmer_clust)
-                else:
-                    t1 = time.perf_counter()
-                    text, count, flags = self.ctx.cluster_block_patterns_dev(self.merged, self.out_cap, self.stride, self.kmer_clust, stream)
-                if flags & 2:
-                    raise api.CrassB200Error(api.EINVAL, "token stride too small for the DR lengths in use")
-                status = 0
-                if (flags & 1) or count > self.out_cap:
-                    status, text = 1, b""
-                elif len(text) > self.text_cap:
-                    status = 2
+                # whatever goes wrong on the root travels as status 3 + message: the other ranks are already waiting in
+                # the broadcast below and must hear about it instead of hanging there
+                status, count, text, t1 = 0, 0, b"", t0
+                try:
+                    self.ctx.merge_token_blocks_dev(self.recv, self.world, self.cap, self.stride, self.shard_reads, self.merged, self.out_cap, stream)
+                    if _HOST_PASSES:
+                        self.host.copy_(self.merged, non_blocking=True)
+                        torch.cuda.current_stream(self.dev).synchronize()
+                        t1 = time.perf_counter()
+                        text, count, flags = api.non_redundant_patterns_from_block(self.host, self.out_cap, self.stride, self.kmer_clust)
+                    else:
+                        t1 = time.perf_counter()
+                        text, count, flags = self.ctx.cluster_block_patterns_dev(self.merged, self.out_cap, self.stride, self.kmer_clust, stream)
+                    if flags & 2:
+                        raise api.CrassB200Error(api.EINVAL, "token stride too small for the DR lengths in use")
+                    if (flags & 1) or count > self.out_cap:
+                        status, text = 1, b""
+                    elif len(text) > self.text_cap:
+                        status = 2
+                except Exception as e:                            # noqa: BLE001 -- reported on every rank below
+                    status, text = 3, ("%s: %s" % (type(e).__name__, e)).encode()[: self.text_cap]
                 t3 = time.perf_counter()
                 self.last_ms = {"gather_merge_d2h": (t1 - t0) * 1e3, "cluster": (t3 - t1) * 1e3}
                 hdr.view(np.uint32)[0:2] = (status, min(count, 0xFFFFFFFF))
                 hdr.view(np.uint64)[1] = len(text)
                 n_send = self.HEADER
-                if status == 0 and text:
+                if status in (0, 3) and text:
                     self.msg_host[self.HEADER: self.HEADER + len(text)] = torch.frombuffer(bytearray(text), dtype=torch.uint8)
                     n_send += len(text)
                 self.msg[:n_send].copy_(self.msg_host[:n_send], non_blocking=True)
@@ -160,6 +173,9 @@ class PatternExchange(TokenExchange):
             text_len = int(hdr.view(np.uint64)[1])
             if self.rank == self.root:
                 self.last_ms["broadcast"] = (time.perf_counter() - t3) * 1e3
+            if status == 3:
+                raise api.CrassB200Error(api.EINVAL, "pattern exchange failed on rank %d: %s"
+                                         % (self.root, self.msg_host[self.HEADER: self.HEADER + text_len].numpy().tobytes().decode("latin-1")))
             if status == 1:
                 self._alloc(self.cap * 2)
                 continue

@@ -30,17 +30,30 @@ def ctx():
     c.close()
 
 
-@pytest.fixture(params=["fast", "generic"])
+K1_ENV = {"fast": {"CRASS_B200_K1": "fast"},
+          "fast-r1": {"CRASS_B200_K1": "fast", "CRASS_B200_K1F": "tma", "CRASS_B200_K1E": "lockstep"},
+          "fast-piped": {"CRASS_B200_K1": "fast", "CRASS_B200_K1_CHUNKS": "3"},
+          "fast-r1-piped": {"CRASS_B200_K1": "fast", "CRASS_B200_K1F": "tma", "CRASS_B200_K1E": "lockstep", "CRASS_B200_K1_CHUNKS": "5"},
+          "generic": {"CRASS_B200_K1": "generic"}}
+
+
+@pytest.fixture(params=list(K1_ENV))
 def k1path(request):
-    """K1 has two device paths with identical results: the 2-bit seed filter + exact candidate kernel (default
-    options, reads <= 304 bp) and the generic one-thread-per-read kernel."""
-    old = os.environ.get("CRASS_B200_K1")
-    os.environ["CRASS_B200_K1"] = request.param
-    yield request.param
-    if old is None:
-        os.environ.pop("CRASS_B200_K1", None)
-    else:
-        os.environ["CRASS_B200_K1"] = old
+    """K1's device paths, all with identical results: the 2-bit seed filter + exact candidate kernel (default options,
+    reads <= 304 bp) in its warp-tile / lane-refill form ("fast"), in the round-1 form (CTA tiles staged by bulk copies,
+    32 candidates per warp in lock step: "fast-r1"), either of them cut into chunks with the exact kernel of one chunk on
+    a second stream beside the filter of the next ("-piped"), and the generic one-thread-per-read kernel."""
+    keys = ("CRASS_B200_K1", "CRASS_B200_K1F", "CRASS_B200_K1E", "CRASS_B200_K1_CHUNKS")
+    old = {k: os.environ.get(k) for k in keys}
+    for k in keys:
+        os.environ.pop(k, None)
+    os.environ.update(K1_ENV[request.param])
+    yield request.param.split("-")[0]
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
 @pytest.fixture(params=["fast", "fast-warp", "fast-list", "generic"])
