@@ -580,13 +580,17 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
         const int nwin = se < 0 ? 1 : se / 16 + 1;
         int* d_err = c->d_error.as<int>();
         const char* fsel = getenv("CRASS_B200_K1F");                               // "tma": CTA tiles staged by bulk copies; default: warp tiles
-        const char* esel = getenv("CRASS_B200_K1E");                               // "lockstep": 32 candidates per warp task; default: lane refill
+        const char* esel = getenv("CRASS_B200_K1E");                               // "lockstep": 32 candidates per warp task; "refill": lanes refilled; default: staged
         const bool f_tma = fsel && !strcmp(fsel, "tma");
         const bool e_lockstep = esel && !strcmp(esel, "lockstep");
+        const bool e_refill = esel && !strcmp(esel, "refill");
         // CTAs per SM: the filter leaves room for the exact kernel's CTAs when the two run side by side
         int f_ctas = n_chunks > 1 ? 12 : 16, e_ctas = e_lockstep ? 8 : (n_chunks > 1 ? 2 : 4);
         if (const char* e = getenv("CRASS_B200_K1F_CTAS")) f_ctas = std::max(1, atoi(e));
         if (const char* e = getenv("CRASS_B200_K1E_CTAS")) e_ctas = std::max(1, atoi(e));
+        uint32_t quorum = cbk::kStageMin, refill_min = cbk::kRefillMin;
+        if (const char* e = getenv("CRASS_B200_K1_QUORUM")) quorum = (uint32_t)std::min(32, std::max(1, atoi(e)));
+        if (const char* e = getenv("CRASS_B200_K1_REFILL")) refill_min = (uint32_t)std::min(32, std::max(1, atoi(e)));
         const bool piped = n_chunks > 1;
         if (piped) {
             CUDA_TRY(cudaEventRecord(c->ev_fork, st));
@@ -596,6 +600,7 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
     do {                                                                                                                            \
         const size_t fsmem = cbk::dr_filter_smem_bytes<NW>();                                                                       \
         const size_t esmem = cbk::dr_exact_smem_bytes<NW>();                                                                        \
+        const size_t ssmem = cbk::dr_staged_smem_bytes<NW>();                                                                       \
         int per_sm = 1;                                                                                                             \
         if (f_tma) {                                                                                                                \
             CUDA_TRY(cudaFuncSetAttribute(cbk::k_dr_filter<NW, NWIN, 49, 97>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); \
@@ -606,6 +611,7 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
         per_sm = std::max(1, std::min(per_sm, f_ctas));                                                                             \
         CUDA_TRY(cudaFuncSetAttribute(cbk::k_dr_exact_packed<NW, NWIN, 49, 97>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem)); \
         CUDA_TRY(cudaFuncSetAttribute(cbk::k_dr_exact_refill<NW, NWIN, 49, 97>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem)); \
+        CUDA_TRY(cudaFuncSetAttribute(cbk::k_dr_exact_staged<NW, NWIN, 49, 97>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem)); \
         for (uint32_t ch = 0; ch < n_chunks; ++ch) {                                                                                \
             const uint32_t r_begin = ch * per_chunk, r_end = std::min(n_reads, r_begin + per_chunk);                                \
             cbk::CandRegion region{cand, r_begin, r_end, cand_counts + 4 * ch};                                                     \
@@ -626,7 +632,8 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
             }                                                                                                                       \
             const int eblocks = c->sm_count * e_ctas;                                                                               \
             if (e_lockstep) cbk::k_dr_exact_packed<NW, NWIN, 49, 97><<<eblocks, cbk::kExactThreads, esmem, est>>>(d_bases, d_offsets, n_reads, region, o, d_found, sink, d_err); \
-            else cbk::k_dr_exact_refill<NW, NWIN, 49, 97><<<eblocks, cbk::kExactThreads, esmem, est>>>(d_bases, d_offsets, n_reads, region, o, d_found, sink, d_err); \
+            else if (e_refill) cbk::k_dr_exact_refill<NW, NWIN, 49, 97><<<eblocks, cbk::kExactThreads, esmem, est>>>(d_bases, d_offsets, n_reads, region, o, d_found, sink, d_err); \
+            else cbk::k_dr_exact_staged<NW, NWIN, 49, 97><<<eblocks, cbk::kExactThreads, ssmem, est>>>(d_bases, d_offsets, n_reads, region, o, d_found, sink, d_err, quorum, refill_min); \
         }                                                                                                                           \
     } while (0)
         if (max_read_len <= 112) { if (nwin <= 3) CB_FAST(7, 3); else CB_FAST(7, 4); }

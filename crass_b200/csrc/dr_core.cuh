@@ -384,6 +384,99 @@ CB_HD int qc_found_repeats(const Seq& s, uint32_t L, const uint32_t* ss, uint32_
     return 1;
 }
 
+// ---- qcFoundRepeats in resumable form ---------------------------------------------------------------------------
+// The same function cut at its only expensive step, the edit distance behind getStringSimilarity: qc_start runs every
+// test that needs no distance and either settles the result or posts the first similarity job; the caller computes the
+// job's distance whenever it suits it (the staged K1 kernel lets the lanes of a warp wait for each other so that the
+// bit-parallel recurrence runs with full warps) and hands it to qc_feed, which adds the similarity to the float sums in
+// the reference's order and posts the next job or the verdict.  Return values: 1 pass, 0 fail, -1 where the reference
+// would throw, 2 = a job is posted in q.job_*.
+struct QcRun {
+    uint32_t nsp, i, r0, rl, st0, len0, st1, len1;
+    uint32_t job_a0, job_n, job_b0, job_m;
+    float rs, sp;
+    bool is_short, second;                                // second: the posted job is sim(spacer i, spacer i+1)
+};
+
+CB_HD int qc_next(const uint32_t* ss, uint32_t L, QcRun& q) {
+    while (q.i + 1 < q.nsp) {
+        if (!q.second) {                                   // rs += sim(repeat, spacer i)
+            if (q.rl >= 3 && q.len0 >= 3) { q.job_a0 = q.r0; q.job_n = q.rl; q.job_b0 = q.st0; q.job_m = q.len0; return 2; }
+            q.rs = f_add(q.rs, 0.0f);
+            q.second = true;
+        } else {                                           // sp += 0 + sim(spacer i, spacer i+1)
+            spacer_at(ss, L, q.i + 1, q.st1, q.len1);
+            if (q.len0 >= 3 && q.len1 >= 3) { q.job_a0 = q.st0; q.job_n = q.len0; q.job_b0 = q.st1; q.job_m = q.len1; return 2; }
+            q.sp = f_add(q.sp, f_add(0.0f, 0.0f));
+            q.st0 = q.st1; q.len0 = q.len1; q.i++; q.second = false;
+        }
+    }
+    const float nc = (float)(q.nsp - 1);
+    const float sp = f_div(q.sp, nc), rs = f_div(q.rs, nc);
+    if ((double)sp > 0.82) return 0;
+    if ((double)rs > 0.82) return 0;
+    return 1;
+}
+
+template <class Seq>
+CB_HD int qc_start(const Seq& s, uint32_t L, const uint32_t* ss, uint32_t n_ss, int min_spacer, int max_spacer, QcRun& q) {
+    const uint32_t n = n_ss / 2;
+    if (n < 2) return -1;
+    q.r0 = ss[0];
+    q.rl = substr_len(L, q.r0, ss[1] - ss[0] + 1);
+    if (low_complexity(s, q.r0, q.rl)) return 0;
+    if (n >= 3) {
+        q.nsp = n - 1;
+        int min_len = 10000000, max_len = 0;
+        float ssl = 0.0f, rsl = 0.0f;
+        uint32_t prev_len = 0;
+        for (uint32_t i = 0; i < q.nsp; ++i) {
+            uint32_t st, len;
+            spacer_at(ss, L, i, st, len);
+            if ((int)len < min_len) min_len = (int)len;
+            if ((int)len > max_len) max_len = (int)len;
+            if (i > 0) {
+                ssl = f_add(ssl, f_sub((float)prev_len, (float)len));
+                rsl = f_add(rsl, f_sub((float)q.rl, (float)prev_len));
+            }
+            prev_len = len;
+        }
+        const float nc = (float)(q.nsp - 1);
+        if (min_len < min_spacer) return 0;
+        if (max_len > max_spacer) return 0;
+        float a_ssl = f_div(ssl, nc); if (a_ssl < 0) a_ssl = -a_ssl;
+        float a_rsl = f_div(rsl, nc); if (a_rsl < 0) a_rsl = -a_rsl;
+        if ((int)a_ssl > 12) return 0;
+        if ((int)a_rsl > 30) return 0;
+        if (q.rl > (uint32_t)kMaxEdit || max_len > kMaxEdit) return -1;
+        q.is_short = false; q.second = false; q.i = 0; q.rs = 0.0f; q.sp = 0.0f;
+        spacer_at(ss, L, 0, q.st0, q.len0);
+        return qc_next(ss, L, q);
+    }
+    const uint32_t st = ss[1] + 1;
+    const uint32_t en = ss[2] - 1;
+    if (st > L) return -1;
+    const uint32_t sl = substr_len(L, st, en - st);
+    if ((int)sl < min_spacer) return 0;
+    if ((int)sl > max_spacer) return 0;
+    int diff = (int)sl - (int)q.rl; if (diff < 0) diff = -diff;
+    if (diff > 30) return 0;
+    if (q.rl > (uint32_t)kMaxEdit || sl > (uint32_t)kMaxEdit) return -1;
+    if (q.rl < 3 || sl < 3) return 1;                       // similarity 0
+    q.is_short = true;
+    q.job_a0 = q.r0; q.job_n = q.rl; q.job_b0 = st; q.job_m = sl;
+    return 2;
+}
+
+CB_HD int qc_feed(const uint32_t* ss, uint32_t L, QcRun& q, int distance) {
+    const float max_length = (float)(q.job_n > q.job_m ? q.job_n : q.job_m);
+    const float sim = one_minus(f_div((float)distance, max_length));
+    if (q.is_short) return (double)sim > 0.82 ? 0 : 1;
+    if (!q.second) { q.rs = f_add(q.rs, sim); q.second = true; }
+    else { q.sp = f_add(q.sp, f_add(0.0f, sim)); q.st0 = q.st1; q.len0 = q.len1; q.i++; q.second = false; }
+    return qc_next(ss, L, q);
+}
+
 // ---- candidate handling shared by every K1 variant: a verified seed (j, p) ------------------------------------
 // On entry ss is empty.  Returns 1 (array accepted: ss/n_ss/replen hold the result), 0 (rejected; if
 // advance is set the window cursor must jump to *next_j = back()-1, libcrispr.cpp:390), <0 error.
@@ -409,6 +502,40 @@ CB_HD int process_seed(const Seq& s, uint32_t L, const Params& o, uint32_t j, ui
     }
     n_ss = 0;
     return 0;
+}
+
+// process_seed cut at the same place: seed_begin returns 1 / 0 / <0 like process_seed, or 2 with a similarity job
+// posted in q; seed_feed takes the job's distance and returns 1 / 0 / <0 / 2 likewise.  On 0, `advance` / `next_j` are
+// set as by process_seed.
+template <class Seq>
+CB_HD int seed_settle(int verdict, uint32_t* ss, uint32_t& n_ss, bool& advance, uint32_t& next_j) {
+    if (verdict == 1 || verdict < 0 || verdict == 2) return verdict;
+    advance = true;
+    next_j = ss[n_ss - 1] - 1;
+    n_ss = 0;
+    return 0;
+}
+
+template <class Seq>
+CB_HD int seed_begin(const Seq& s, uint32_t L, const Params& o, uint32_t j, uint32_t p, uint32_t* ss, uint32_t& n_ss,
+                     uint32_t cap, uint32_t& replen, bool& advance, uint32_t& next_j, QcRun& q) {
+    const uint32_t w = o.window;
+    n_ss = 0;
+    ss_add(ss, n_ss, L, j, j + w - 1);
+    ss_add(ss, n_ss, L, p, p + w - 1);
+    scan_right(s, L, ss, n_ss, cap, j, w, o.low_spacer, o.scan_range);
+    advance = false;
+    if (n_ss / 2 < o.min_repeats) { n_ss = 0; return 0; }
+    const uint32_t len = extend_pre_repeat(s, L, ss, n_ss, w, o.low_spacer);
+    replen = len;
+    int verdict = 0;
+    if (len >= o.low_dr && len <= o.high_dr) verdict = qc_start(s, L, ss, n_ss, (int)o.low_spacer, (int)o.high_spacer, q);
+    return seed_settle<Seq>(verdict, ss, n_ss, advance, next_j);
+}
+
+template <class Seq>
+CB_HD int seed_feed(uint32_t L, uint32_t* ss, uint32_t& n_ss, bool& advance, uint32_t& next_j, QcRun& q, int distance) {
+    return seed_settle<Seq>(qc_feed(ss, L, q, distance), ss, n_ss, advance, next_j);
 }
 
 CB_HD uint32_t window_skips(const Params& o) {

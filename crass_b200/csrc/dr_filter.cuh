@@ -13,10 +13,10 @@
 // dr_core.cuh.
 //
 // Layout: base i of the read sits in bits [2i, 2i+2) of a little-endian word stream R[]; an 8-mer at a
-// multiple of 8 is one aligned 16-bit half-word.  For a distance d, (R >> 2d) XOR R has a zero half-word h
-// exactly when window j = 8h re-occurs at j+d, so one funnel shift + one XOR test two windows, and a packed
-// unsigned 16-bit minimum (VIMNMX3.U16x2 on sm_100a) folds two distances into the running minimum of a
-// window word: a half-word of acc[k] ends up zero iff some distance matched for that window.
+// multiple of 8 is one aligned 16-bit half-word.  For a distance d, half-word h of (R >> 2d) equals half-word h of R
+// exactly when window j = 8h re-occurs at j+d.  T + ~R is 0xFFFF per 16-bit lane exactly where T == R (modular add), so
+// one VIADDMNMX.U16x2 (max(T + ~R, acc)) compares two windows at one distance AND folds the result into the running
+// maximum of the window word: a half-word of acc[k] ends up 0xFFFF iff some distance matched for that window.
 #pragma once
 #include <stdint.h>
 
@@ -33,17 +33,6 @@ CB_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {        // low w
 #endif
 }
 
-CB_HD uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c) {
-#if defined(__CUDA_ARCH__)
-    return __vimin3_u16x2(a, b, c);
-#else
-    auto mn = [](uint32_t x, uint32_t y) { return x < y ? x : y; };
-    const uint32_t lo = mn(mn(a & 0xFFFFu, b & 0xFFFFu), c & 0xFFFFu);
-    const uint32_t hi = mn(mn(a >> 16, b >> 16), c >> 16);
-    return lo | (hi << 16);
-#endif
-}
-
 CB_HD int first_set(uint32_t x) {                                       // index of the lowest set bit, x != 0
 #if defined(__CUDA_ARCH__)
     return __ffs((int)x) - 1;
@@ -52,21 +41,28 @@ CB_HD int first_set(uint32_t x) {                                       // index
 #endif
 }
 
-// min(a + b, c) per unsigned 16-bit lane, modular add: one VIADDMNMX.U16x2 on sm_100a.  With b = -R (per lane) the
-// sum is zero exactly where a == R, so "compare + fold into the running minimum" is a single instruction.
-CB_HD uint32_t addmin_u16x2(uint32_t a, uint32_t b, uint32_t c) {
+// max(a + b, c) per unsigned 16-bit lane, modular add: one VIADDMNMX.U16x2 on sm_100a.  With b = ~R the sum is 0xFFFF
+// exactly where a == R, so "compare + fold into the running maximum" is a single instruction, and preparing b costs one
+// LOP3 per window word (the min form with b = -R needed a per-lane two's complement, five instructions a word).
+CB_HD uint32_t addmax_u16x2(uint32_t a, uint32_t b, uint32_t c) {
 #if defined(__CUDA_ARCH__)
-    return __viaddmin_u16x2(a, b, c);
+    return __viaddmax_u16x2(a, b, c);
 #else
-    auto mn = [](uint32_t x, uint32_t y) { return x < y ? x : y; };
-    const uint32_t lo = mn(((a & 0xFFFFu) + (b & 0xFFFFu)) & 0xFFFFu, c & 0xFFFFu);
-    const uint32_t hi = mn(((a >> 16) + (b >> 16)) & 0xFFFFu, c >> 16);
+    auto mx = [](uint32_t x, uint32_t y) { return x > y ? x : y; };
+    const uint32_t lo = mx(((a & 0xFFFFu) + (b & 0xFFFFu)) & 0xFFFFu, c & 0xFFFFu);
+    const uint32_t hi = mx(((a >> 16) + (b >> 16)) & 0xFFFFu, c >> 16);
     return lo | (hi << 16);
 #endif
 }
-CB_HD uint32_t neg_u16x2(uint32_t a) {                                   // per-lane two's complement
-    const uint32_t lo = (0u - (a & 0xFFFFu)) & 0xFFFFu, hi = (0u - (a >> 16)) & 0xFFFFu;
+CB_HD uint32_t max3_u16x2(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+    return __vimax3_u16x2(a, b, c);
+#else
+    auto mx = [](uint32_t x, uint32_t y) { return x > y ? x : y; };
+    const uint32_t lo = mx(mx(a & 0xFFFFu, b & 0xFFFFu), c & 0xFFFFu);
+    const uint32_t hi = mx(mx(a >> 16, b >> 16), c >> 16);
     return lo | (hi << 16);
+#endif
 }
 CB_HD uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t sel) {
 #if defined(__CUDA_ARCH__)
@@ -90,19 +86,19 @@ CB_HD uint32_t pack16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
     return byte_perm(lo, hi, 0x5410u);
 }
 
-CB_HD bool has_zero_half(uint32_t x) { return (x & 0xFFFFu) == 0 || (x >> 16) == 0; }
+CB_HD bool has_full_half(uint32_t x) { return (x & 0xFFFFu) == 0xFFFFu || (x >> 16) == 0xFFFFu; }
 
 // NW   : 32-bit words holding the read (16 bases each); R must have NW + 2 entries, the tail is look-ahead
 //        (whatever follows the read in the batch, or zeros -- it can only add false positives)
 // NWIN : words holding window starts, i.e. floor((max_len - 58) / 16) + 1
 // DMIN..DMAX : seed distances, low_dr + low_spacer .. high_dr + high_spacer (49..97 with default options)
-// acc[k] (k < NWIN): half-word h of acc[k] is zero iff window 16k + 8h has a code-level seed.
+// acc[k] (k < NWIN): half-word h of acc[k] is 0xFFFF iff window 16k + 8h has a code-level seed.
 template <int NW, int NWIN, int DMIN, int DMAX>
 CB_HD void seed_flags(const uint32_t* R, uint32_t* acc) {
     constexpr int OLO = DMIN / 16, OHI = DMAX / 16;
-    uint32_t negR[NWIN];                                        // -window per 16-bit lane: T + negR == 0  <=>  T == window
+    uint32_t notR[NWIN];                                        // ~window: T + ~R == 0xFFFF per 16-bit lane  <=>  T == window
 #pragma unroll
-    for (int k = 0; k < NWIN; ++k) { acc[k] = 0xFFFFFFFFu; negR[k] = neg_u16x2(R[k]); }
+    for (int k = 0; k < NWIN; ++k) { acc[k] = 0u; notR[k] = ~R[k]; }
 #pragma unroll
     for (int phi = 0; phi < 16; ++phi) {
         uint32_t T[NW + 1];                                     // the stream shifted right by phi bases
@@ -115,7 +111,7 @@ CB_HD void seed_flags(const uint32_t* R, uint32_t* acc) {
                 const int d = 16 * o + phi;
                 if (d < DMIN || d > DMAX) continue;
                 if (k + o > NW - 1) continue;                   // every position of this word pair lies past the read
-                acc[k] = addmin_u16x2(T[k + o], negR[k], acc[k]);   // one VIADDMNMX.U16x2 per (window word, distance)
+                acc[k] = addmax_u16x2(T[k + o], notR[k], acc[k]);   // one VIADDMNMX.U16x2 per (window word, distance)
             }
         }
     }
@@ -125,9 +121,9 @@ template <int NWIN>
 CB_HD bool any_flag(const uint32_t* acc) {
     uint32_t m = acc[0];
 #pragma unroll
-    for (int k = 1; k + 1 < NWIN; k += 2) m = min3_u16x2(m, acc[k], acc[k + 1]);
-    if ((NWIN & 1) == 0) m = min3_u16x2(m, acc[NWIN - 1], acc[NWIN - 1]);
-    return has_zero_half(m);
+    for (int k = 1; k + 1 < NWIN; k += 2) m = max3_u16x2(m, acc[k], acc[k + 1]);
+    if ((NWIN & 1) == 0) m = max3_u16x2(m, acc[NWIN - 1], acc[NWIN - 1]);
+    return has_full_half(m);
 }
 
 template <int NWIN>
@@ -135,8 +131,8 @@ CB_HD uint32_t flag_mask(const uint32_t* acc) {                 // bit h <-> win
     uint32_t m = 0;
 #pragma unroll
     for (int k = 0; k < NWIN; ++k) {
-        if ((acc[k] & 0xFFFFu) == 0) m |= 1u << (2 * k);
-        if ((acc[k] >> 16) == 0) m |= 2u << (2 * k);
+        if ((acc[k] & 0xFFFFu) == 0xFFFFu) m |= 1u << (2 * k);
+        if ((acc[k] >> 16) == 0xFFFFu) m |= 2u << (2 * k);
     }
     return m;
 }
@@ -208,6 +204,33 @@ struct PackedSearch {
             if (base > (uint32_t)se) done = true; else need_flags = true;
         }
     }
+    // seed() cut at the edit distance (dr_core.cuh: seed_begin / seed_feed): seed_start leaves `osa_pending` set and
+    // the job in q.job_* when the verdict needs a similarity; the caller computes the distance when it suits the warp
+    // and calls seed_resume.
+    QcRun q;
+    bool osa_pending = false;
+    CB_HD void settle(int r, bool advance, uint32_t nj) {
+        osa_pending = r == 2;
+        if (r == 2) return;
+        if (r != 0) { result = r; done = true; }
+        else if (advance) {
+            base = nj + 8u;
+            if (base > (uint32_t)se) done = true; else need_flags = true;
+        }
+    }
+    CB_HD void seed_start() {
+        need_flags = false; osa_pending = false;
+        if (pos < 0) return;
+        bool advance = false; uint32_t nj = 0;
+        const int r = seed_begin(s, L, o, j, (uint32_t)pos, ss, n_ss, cap, replen, advance, nj, q);
+        settle(r, advance, nj);
+    }
+    CB_HD void seed_resume(int distance) {
+        if (!osa_pending) return;
+        bool advance = false; uint32_t nj = 0;
+        const int r = seed_feed<Seq>(L, ss, n_ss, advance, nj, q, distance);
+        settle(r, advance, nj);
+    }
     CB_HD void reflag() {                                       // the window grid moved: flags of the re-phased stream
         if (!need_flags) return;
         const uint32_t q = base >> 4, sh = (base & 15u) * 2u;
@@ -223,6 +246,25 @@ struct PackedSearch {
         mask = flag_mask<NWIN>(acc);
     }
 };
+
+// the staged form driven for one read (what a lane of k_dr_exact_staged goes through, without the waiting)
+template <int NW, int NWIN, int DMIN, int DMAX, class Seq>
+CB_HD int search_core_staged(const Seq& s, uint32_t L, const Params& o, const uint32_t* S, uint32_t mask0,
+                             uint32_t* ss, uint32_t cap, uint32_t& n_ss, uint32_t& replen) {
+    PackedSearch<NW, NWIN, DMIN, DMAX, Seq> st(s, L, o, S, ss, cap);
+    st.init(mask0);
+    for (;;) {
+        st.pick();
+        if (!st.have) break;
+        st.find();
+        st.seed_start();
+        while (st.osa_pending) st.seed_resume(edit_distance(s, st.q.job_a0, st.q.job_n, st.q.job_b0, st.q.job_m));
+        st.reflag();
+    }
+    n_ss = st.result == 1 ? st.n_ss : 0;
+    replen = st.replen;
+    return st.result;
+}
 
 template <int NW, int NWIN, int DMIN, int DMAX, class Seq>
 CB_HD int search_core_packed(const Seq& s, uint32_t L, const Params& o, const uint32_t* S, uint32_t mask0,

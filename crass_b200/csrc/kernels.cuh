@@ -58,6 +58,16 @@ __constant__ uint8_t c_comp_tab[128] = {                       // SeqUtils.cpp:5
     64, 'T', 'V', 'G', 'H', 'E', 'F', 'C', 'D', 'I', 'J', 'M', 'L', 'K', 'N', 'O', 'P', 'Q', 'Y', 'S', 'A', 'A', 'B', 'W', 'X', 'R', 'Z', 91, 92, 93, 94, 95,
     64, 't', 'v', 'g', 'h', 'e', 'f', 'c', 'd', 'i', 'j', 'm', 'l', 'k', 'n', 'o', 'p', 'q', 'y', 's', 'a', 'a', 'b', 'w', 'x', 'r', 'z', 123, 124, 125, 126, 127};
 
+// complement of a base: the four letters that make up nearly every read are settled in registers; the table (constant
+// memory, one serialised access per distinct index in a warp) is only read for the other IUPAC letters
+__device__ __forceinline__ uint8_t comp_byte(uint8_t c) {
+    if (c == 'A') return 'T';
+    if (c == 'T') return 'A';
+    if (c == 'C') return 'G';
+    if (c == 'G') return 'C';
+    return c_comp_tab[c & 127];
+}
+
 template <class Seq>
 __device__ __noinline__ void emit_token(uint8_t* __restrict__ rec, uint32_t stride, const Seq& s, uint32_t L, const uint32_t* ss, uint32_t n_ss) {
     const uint32_t n_rep = n_ss / 2;
@@ -75,12 +85,12 @@ __device__ __noinline__ void emit_token(uint8_t* __restrict__ rec, uint32_t stri
     // forward < reverse complement ?  (std::string operator<, unsigned bytes; equal -> take the reverse complement)
     bool fwd_less = false;
     for (uint32_t i = 0; i < ln; ++i) {
-        const uint8_t a = s[st + i], b = c_comp_tab[s[st + ln - 1 - i] & 127];
+        const uint8_t a = s[st + i], b = comp_byte(s[st + ln - 1 - i]);
         if (a != b) { fwd_less = a < b; break; }
     }
     rec[0] = (uint8_t)ln;
     rec[1] = fwd_less ? 1 : 0;
-    for (uint32_t i = 0; i < ln; ++i) rec[2 + i] = fwd_less ? s[st + i] : c_comp_tab[s[st + ln - 1 - i] & 127];
+    for (uint32_t i = 0; i < ln; ++i) rec[2 + i] = fwd_less ? s[st + i] : comp_byte(s[st + ln - 1 - i]);
 }
 
 // ---- K4b: distinct DR tokens of a hit list, with the smallest read index that carries each --------------------
@@ -924,6 +934,139 @@ k_dr_exact_refill(const uint8_t* __restrict__ bases, const uint64_t* __restrict_
             busy = false;
         }
         __syncwarp();
+    }
+}
+
+// ---- K1 fast path, stage 2, staged (the default) -------------------------------------------------------------------
+// ncu on the two kernels above: 11 of 32 lanes active per instruction, 40 % of the instructions in the bit-parallel edit
+// distance at 8 lanes -- the lanes of a warp reach the expensive steps at different times.  Here a lane's search is cut
+// into stages (fetch a candidate | pick a flagged window + byte-level find | scanRight + extendPreRepeat + the tests of
+// qcFoundRepeats that need no distance | one edit distance | re-flag after a rejected array) and the warp runs a stage
+// only when at least kStageMin lanes are waiting for it, or when nothing else can move; lanes waiting for another stage
+// sit the round out.  The float sums of qcFoundRepeats are fed in the reference's order (dr_core.cuh: qc_start /
+// qc_feed), so the verdicts are bit-identical.  The start/stop list lives in shared memory instead of the thread's
+// stack: with four CTAs on an SM the stacks of the other kernels did not fit the L1 that the shared memory leaves.
+constexpr uint32_t kStageMin = 16;                              // default quorum (CRASS_B200_K1_QUORUM overrides it for measurements)
+constexpr int kStagedSs = 33;                                   // odd stride: conflict-free per-thread lists of 32 entries
+
+template <int NW>
+constexpr size_t dr_staged_smem_bytes() { return (size_t)kExactThreads * ((((NW + 4) | 1) + (((NW + 3) * 4) | 1) + kStagedSs) * 4); }
+
+template <int NW, int NWIN, int DMIN, int DMAX>
+__global__ void __launch_bounds__(kExactThreads)
+k_dr_exact_staged(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads,
+                  CandRegion cand, Params o, uint8_t* __restrict__ found, HitSink sink, int* __restrict__ error_flag,
+                  uint32_t quorum, uint32_t refill_min) {
+    constexpr int kSlot = (NW + 4) | 1;
+    constexpr int kByteSlot = ((NW + 3) * 4) | 1;
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+    enum : uint32_t { FREE = 0, PICK = 1, SEED = 2, OSA = 3, FLAG = 4 };
+    extern __shared__ uint32_t sm[];                            // dr_staged_smem_bytes<NW>()
+    const uint32_t n_front = cand.counts[0], n_back = cand.counts[1], total = n_front + n_back;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&sink.counters[3], total);
+    const uint64_t n_bases = offsets[n_reads];
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t* S = sm + threadIdx.x * kSlot;
+    uint32_t* B = sm + kExactThreads * kSlot + threadIdx.x * kByteSlot;
+    uint32_t* ss = sm + kExactThreads * (kSlot + kByteSlot) + threadIdx.x * kStagedSs;
+    cb::PackedSearch<NW, NWIN, DMIN, DMAX, SmemSeq> st(SmemSeq{reinterpret_cast<const uint8_t*>(B)}, 0u, o, S, ss, 32u);
+    uint32_t state = FREE, r = 0;
+    bool exhausted = false;
+    // where a lane goes after a seed stage (scan/extend/cheap tests, or one more distance)
+    auto after_seed = [&]() {
+        if (st.osa_pending) { state = OSA; return; }
+        if (st.done) {
+            const int f = st.result;
+            if (f < 0) *error_flag = f;
+            if (f == 1) {
+                found[r] = 1;
+                const uint32_t slot = emit_hit(sink, r, ss, st.n_ss, st.replen);
+                if (sink.tokens && slot != 0xFFFFFFFFu) emit_token(sink.tokens + (size_t)slot * sink.token_stride, sink.token_stride, st.s, st.L, ss, st.n_ss);
+            }
+            state = FREE;
+            return;
+        }
+        state = st.need_flags ? FLAG : PICK;
+    };
+    for (;;) {
+        const uint32_t m_free = __ballot_sync(FULL, state == FREE);
+        if (!exhausted && (m_free == FULL || __popc(m_free) >= refill_min)) {
+            // candidates are taken from the queue as lanes fall free, never ahead of need: a warp that reserved a block of
+            // 64 in advance (tried) sits on work that idle warps could have had, and the kernel got 0.06 ms slower
+            const uint32_t take = __popc(m_free);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&cand.counts[2], take);
+            base = __shfl_sync(FULL, base, 0);
+            exhausted = base + take >= total;
+            const uint32_t rank = __popc(m_free & ((1u << lane) - 1u));
+            const uint32_t q = base + rank;
+            if (state == FREE && q < total) {
+                r = q < n_front ? cand.list[cand.lo + q] : cand.list[cand.hi - 1u - (q - n_front)];
+                const uint64_t b = offsets[r];
+                const uint32_t L = (uint32_t)(offsets[r + 1] - b);
+                const uint64_t a0 = b & ~(uint64_t)15;
+                const uint32_t sh = (uint32_t)(b & 15u) * 2u;
+                uint32_t prev = 0;
+                uint32_t R[NW + 2];
+#pragma unroll
+                for (int v = 0; v < NW + 3; ++v) {
+                    const uint64_t at = a0 + 16ull * v;
+                    uint4 x;
+                    if (at + 16 <= n_bases) x = __ldg(reinterpret_cast<const uint4*>(bases + at));
+                    else x = ragged_vector(bases, at, n_bases);
+                    B[4 * v] = x.x; B[4 * v + 1] = x.y; B[4 * v + 2] = x.z; B[4 * v + 3] = x.w;
+                    const uint32_t w = cb::pack16(x.x, x.y, x.z, x.w);
+                    if (v > 0) R[v - 1] = cb::funnel_r(prev, w, sh);
+                    prev = w;
+                }
+#pragma unroll
+                for (int k = 0; k < NW + 2; ++k) S[k] = R[k];
+                uint32_t acc[NWIN];
+                cb::seed_flags<NW, NWIN, DMIN, DMAX>(R, acc);
+                st.rebind(SmemSeq{reinterpret_cast<const uint8_t*>(B) + (uint32_t)(b & 15u)}, L);
+                st.init(cb::flag_mask<NWIN>(acc));
+                state = PICK;
+            }
+            __syncwarp();
+        }
+        // which stages have a quorum; without one, the fullest stage runs alone (the tail of the list, or a lone lane
+        // that everybody else is waiting behind)
+        const uint32_t c_pick = __popc(__ballot_sync(FULL, state == PICK)), c_seed = __popc(__ballot_sync(FULL, state == SEED)),
+                       c_osa = __popc(__ballot_sync(FULL, state == OSA)), c_flag = __popc(__ballot_sync(FULL, state == FLAG));
+        if (!(c_pick | c_seed | c_osa | c_flag)) {
+            if (exhausted) break;
+            continue;
+        }
+        uint32_t forced = FREE;
+        if (c_pick < quorum && c_seed < quorum && c_osa < quorum && c_flag < quorum) {
+            forced = PICK; uint32_t best = c_pick;
+            if (c_seed > best) { forced = SEED; best = c_seed; }
+            if (c_osa > best) { forced = OSA; best = c_osa; }
+            if (c_flag > best) { forced = FLAG; best = c_flag; }
+        }
+        if (forced == PICK || __popc(__ballot_sync(FULL, state == PICK)) >= quorum) {
+            if (state == PICK) {
+                do { st.pick(); if (!st.have) break; st.find(); } while (st.pos < 0);   // flagged windows until one holds on the bytes
+                if (!st.have) state = FREE;                     // no window left: the read has no array
+                else state = SEED;
+            }
+            __syncwarp();
+        }
+        if (forced == SEED || __popc(__ballot_sync(FULL, state == SEED)) >= quorum) {
+            if (state == SEED) { st.seed_start(); after_seed(); }
+            __syncwarp();
+        }
+        if (forced == OSA || __popc(__ballot_sync(FULL, state == OSA)) >= quorum) {
+            if (state == OSA) {
+                st.seed_resume(cb::edit_distance(st.s, st.q.job_a0, st.q.job_n, st.q.job_b0, st.q.job_m));
+                after_seed();
+            }
+            __syncwarp();
+        }
+        if (forced == FLAG || __popc(__ballot_sync(FULL, state == FLAG)) >= quorum) {
+            if (state == FLAG) { st.reflag(); state = PICK; }
+            __syncwarp();
+        }
     }
 }
 

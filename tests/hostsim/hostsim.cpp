@@ -81,7 +81,7 @@ int hs_low_complexity(const uint8_t* a, uint32_t la) {
 // 2-bit seed flags exactly as the K1 filter kernel computes them: pack 16 bytes per word (zero padded), realign
 // to an arbitrary base offset `shift_bases` (as a read inside a tile is), then seed_flags<NW,NWIN,49,97>.
 // mode 0: returns the filter decision; mode 1: runs search_core_packed (the exact candidate kernel's logic) and
-// returns found, filling ss / n_ss / replen.
+// returns found, filling ss / n_ss / replen; mode 2: the same through the staged form (seed cut at the edit distance).
 template <int NW, int NWIN>
 static int run_packed(const uint32_t* R, const uint8_t* seq, uint32_t len, int mode, uint32_t* ss, uint32_t* n_ss, uint32_t* replen) {
     uint32_t acc[NWIN];
@@ -96,7 +96,8 @@ static int run_packed(const uint32_t* R, const uint8_t* seq, uint32_t len, int m
     for (int k = 0; k < NW + 2; ++k) S[k] = R[k];
     S[NW + 2] = S[NW + 3] = 0;
     uint32_t n = 0, rl = 0;
-    const int r = search_core_packed<NW, NWIN, 49, 97>(s, len, o, S, flag_mask<NWIN>(acc), ss, 32, n, rl);
+    const int r = mode == 2 ? search_core_staged<NW, NWIN, 49, 97>(s, len, o, S, flag_mask<NWIN>(acc), ss, 32, n, rl)
+                            : search_core_packed<NW, NWIN, 49, 97>(s, len, o, S, flag_mask<NWIN>(acc), ss, 32, n, rl);
     *n_ss = n; *replen = rl;
     return r;
 }

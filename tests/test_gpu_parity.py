@@ -32,6 +32,7 @@ def ctx():
 
 K1_ENV = {"fast": {"CRASS_B200_K1": "fast"},
           "fast-r1": {"CRASS_B200_K1": "fast", "CRASS_B200_K1F": "tma", "CRASS_B200_K1E": "lockstep"},
+          "fast-refill": {"CRASS_B200_K1": "fast", "CRASS_B200_K1E": "refill"},
           "fast-piped": {"CRASS_B200_K1": "fast", "CRASS_B200_K1_CHUNKS": "3"},
           "fast-r1-piped": {"CRASS_B200_K1": "fast", "CRASS_B200_K1F": "tma", "CRASS_B200_K1E": "lockstep", "CRASS_B200_K1_CHUNKS": "5"},
           "generic": {"CRASS_B200_K1": "generic"}}
@@ -40,7 +41,7 @@ K1_ENV = {"fast": {"CRASS_B200_K1": "fast"},
 @pytest.fixture(params=list(K1_ENV))
 def k1path(request):
     """K1's device paths, all with identical results: the 2-bit seed filter + exact candidate kernel (default options,
-    reads <= 304 bp) in its warp-tile / lane-refill form ("fast"), in the round-1 form (CTA tiles staged by bulk copies,
+    reads <= 304 bp) in its warp-tile / staged form ("fast"; "fast-refill": exact kernel with refilled lanes), in the round-1 form (CTA tiles staged by bulk copies,
     32 candidates per warp in lock step: "fast-r1"), either of them cut into chunks with the exact kernel of one chunk on
     a second stream beside the filter of the next ("-piped"), and the generic one-thread-per-read kernel."""
     keys = ("CRASS_B200_K1", "CRASS_B200_K1F", "CRASS_B200_K1E", "CRASS_B200_K1_CHUNKS")

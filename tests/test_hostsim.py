@@ -62,7 +62,7 @@ def test_two_bit_filter_only_over_reports_and_the_packed_exact_path_matches(HS, 
     searchCore's hits; K1b's packed state machine returns searchCore's answer."""
     rng = random.Random(4)
     found = flagged = 0
-    for _ in range(1500):
+    for _ in range(4000):
         seq = fuzzgen.fuzz_read(rng, 304)
         if len(seq) < 16:
             continue
@@ -75,6 +75,7 @@ def test_two_bit_filter_only_over_reports_and_the_packed_exact_path_matches(HS, 
             assert flag == 1
         got = hs_packed(HS, seq, shift, tail, 1)
         assert got[0] == (1 if want[0] else 0)
+        assert hs_packed(HS, seq, shift, tail, 2) == got     # the staged form (qcFoundRepeats cut at the edit distance)
         if want[0]:
             assert (got[1], got[2]) == (list(want[1]), want[2])
             found += 1

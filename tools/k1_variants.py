@@ -5,7 +5,8 @@
 
 Knobs (environment, read by crass_b200_dr_search_dev):
   CRASS_B200_K1F=tma        filter on CTA tiles staged by bulk copies (round 1); default: warp tiles, no staged bytes
-  CRASS_B200_K1E=lockstep   exact kernel with 32 candidates per warp task (round 1); default: lane refill
+  CRASS_B200_K1E=lockstep   exact kernel with 32 candidates per warp task (round 1); =refill: finished lanes take new
+                            candidates; default: staged (lanes wait for a quorum per stage)
   CRASS_B200_K1_CHUNKS=n    chunks of the batch; with n > 1 the exact kernel of chunk i runs beside the filter of chunk i+1
   CRASS_B200_K1F_CTAS / CRASS_B200_K1E_CTAS   CTAs per SM of the two kernels
 Prints one JSON object per variant: CUDA-event milliseconds of the whole K1 call, candidates, hits, and whether the found
@@ -20,27 +21,21 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-KEYS = ("CRASS_B200_K1F", "CRASS_B200_K1E", "CRASS_B200_K1_CHUNKS", "CRASS_B200_K1F_CTAS", "CRASS_B200_K1E_CTAS")
+KEYS = ("CRASS_B200_K1F", "CRASS_B200_K1E", "CRASS_B200_K1_CHUNKS", "CRASS_B200_K1F_CTAS", "CRASS_B200_K1E_CTAS", "CRASS_B200_K1_QUORUM", "CRASS_B200_K1_REFILL")
 
 VARIANTS = [
-    ("r1: tma filter + lockstep exact, 1 chunk", {"CRASS_B200_K1F": "tma", "CRASS_B200_K1E": "lockstep", "CRASS_B200_K1_CHUNKS": "1"}),
-    ("warp filter 16/SM + lockstep exact, 1 chunk", {"CRASS_B200_K1E": "lockstep", "CRASS_B200_K1_CHUNKS": "1"}),
-    ("warp filter 12/SM + lockstep exact, 1 chunk", {"CRASS_B200_K1E": "lockstep", "CRASS_B200_K1_CHUNKS": "1", "CRASS_B200_K1F_CTAS": "12"}),
-    ("tma filter + refill exact 4/SM, 1 chunk", {"CRASS_B200_K1F": "tma", "CRASS_B200_K1_CHUNKS": "1"}),
-    ("warp filter + refill exact 1/SM, 1 chunk", {"CRASS_B200_K1_CHUNKS": "1", "CRASS_B200_K1E_CTAS": "1"}),
-    ("warp filter + refill exact 2/SM, 1 chunk", {"CRASS_B200_K1_CHUNKS": "1", "CRASS_B200_K1E_CTAS": "2"}),
-    ("warp filter + refill exact 4/SM, 1 chunk", {"CRASS_B200_K1_CHUNKS": "1"}),
-    ("warp filter + refill exact 8/SM, 1 chunk", {"CRASS_B200_K1_CHUNKS": "1", "CRASS_B200_K1E_CTAS": "8"}),
-    ("default: warp 12/SM + refill 2/SM, 4 chunks piped", {}),
-    ("piped 4 chunks, filter 16/SM, refill 2/SM", {"CRASS_B200_K1F_CTAS": "16"}),
-    ("piped 4 chunks, filter 14/SM, refill 1/SM", {"CRASS_B200_K1F_CTAS": "14", "CRASS_B200_K1E_CTAS": "1"}),
-    ("piped 4 chunks, filter 12/SM, refill 3/SM", {"CRASS_B200_K1E_CTAS": "3"}),
-    ("piped 2 chunks", {"CRASS_B200_K1_CHUNKS": "2"}),
-    ("piped 3 chunks", {"CRASS_B200_K1_CHUNKS": "3"}),
-    ("piped 6 chunks", {"CRASS_B200_K1_CHUNKS": "6"}),
-    ("piped 8 chunks", {"CRASS_B200_K1_CHUNKS": "8"}),
-    ("piped 4 chunks, lockstep exact 2/SM", {"CRASS_B200_K1E": "lockstep", "CRASS_B200_K1E_CTAS": "2"}),
-    ("piped 4 chunks, tma filter 6/SM + refill 2/SM", {"CRASS_B200_K1F": "tma", "CRASS_B200_K1F_CTAS": "6"}),
+    ("r1: tma filter + lockstep exact", {"CRASS_B200_K1F": "tma", "CRASS_B200_K1E": "lockstep"}),
+    ("warp filter + lockstep exact", {"CRASS_B200_K1E": "lockstep"}),
+    ("default: warp filter + staged exact 4/SM, quorum 16, refill 8", {}),
+    ("staged quorum 8", {"CRASS_B200_K1_QUORUM": "8"}),
+    ("staged quorum 12", {"CRASS_B200_K1_QUORUM": "12"}),
+    ("staged quorum 20", {"CRASS_B200_K1_QUORUM": "20"}),
+    ("staged quorum 24", {"CRASS_B200_K1_QUORUM": "24"}),
+    ("staged quorum 32", {"CRASS_B200_K1_QUORUM": "32"}),
+    ("staged refill 4", {"CRASS_B200_K1_REFILL": "4"}),
+    ("staged refill 16", {"CRASS_B200_K1_REFILL": "16"}),
+    ("staged quorum 24 refill 4", {"CRASS_B200_K1_QUORUM": "24", "CRASS_B200_K1_REFILL": "4"}),
+    ("staged 3/SM", {"CRASS_B200_K1E_CTAS": "3"}),
 ]
 
 
