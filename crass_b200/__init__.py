@@ -4,8 +4,8 @@ The product is the CUDA library ``libcrass_b200.so`` (sources in ``crass_b200/cs
 ``include/crass_b200.h``).  This package is its ctypes binding plus the seeded synthetic read
 generator and the multi-GPU driver used by the benchmarks.
 """
-from .api import (Automaton, Batch, Context, CrassB200Error, Hit, HIT_DTYPE, Params, Results, device_count, lib,  # noqa: F401
-                  non_redundant_set, pack_reads)
+from .api import (Automaton, Batch, Context, CrassB200Error, Engine, Hit, HIT_DTYPE, Params, Results, device_count, lib,  # noqa: F401
+                  non_redundant_set, pack_reads, run_files_multi)
 
-__all__ = ["Automaton", "Batch", "Context", "CrassB200Error", "Hit", "HIT_DTYPE", "Params", "Results", "device_count", "lib",
-           "non_redundant_set", "pack_reads"]
+__all__ = ["Automaton", "Batch", "Context", "CrassB200Error", "Engine", "Hit", "HIT_DTYPE", "Params", "Results", "device_count", "lib",
+           "non_redundant_set", "pack_reads", "run_files_multi"]

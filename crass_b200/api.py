@@ -135,6 +135,19 @@ def lib():
         "crass_b200_ac_build_from_pattern_list": (C.c_int, [cp, C.POINTER(vp), C.POINTER(C.c_uint32)]),
         "crass_b200_run_files": (C.c_int, [vp, C.POINTER(cp), C.c_uint32, C.POINTER(Params), C.c_int, C.POINTER(vp), C.POINTER(C.c_int)]),
         "crass_b200_free": (None, [vp]),
+        "crass_b200_engine_create": (C.c_int, [C.POINTER(C.c_int), C.c_uint32, C.POINTER(vp)]),
+        "crass_b200_engine_destroy": (None, [vp]),
+        "crass_b200_engine_num_devices": (C.c_uint32, [vp]),
+        "crass_b200_engine_uses_nccl": (C.c_int, [vp]),
+        "crass_b200_engine_search_file": (C.c_int, [vp, cp, C.POINTER(Params), C.POINTER(vp), C.POINTER(vp), u32p, C.POINTER(vp), u32p]),
+        "crass_b200_engine_exchange": (C.c_int, [vp, cp, C.c_uint32, C.POINTER(vp), u32p, u32p]),
+        "crass_b200_engine_find_singletons": (C.c_int, [vp, cp, vp, C.c_int, C.POINTER(vp), C.POINTER(vp), u32p, C.POINTER(vp), u32p]),
+        "crass_b200_engine_release_file": (None, [vp, cp]),
+        "crass_b200_engine_run_files": (C.c_int, [vp, C.POINTER(cp), C.c_uint32, C.POINTER(Params), C.c_int, C.POINTER(vp), C.POINTER(C.c_int)]),
+        "crass_b200_run_files_multi": (C.c_int, [C.POINTER(C.c_int), C.c_uint32, C.POINTER(cp), C.c_uint32, C.POINTER(Params), C.c_int, C.POINTER(vp), C.POINTER(C.c_int)]),
+        "crass_b200_engine_transfer_bytes": (None, [vp, u64p, u64p]),
+        "crass_b200_engine_launch_count": (C.c_uint64, [vp]),
+        "crass_b200_engine_stage_ms": (None, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError here == the library does not export what the header declares
@@ -640,3 +653,107 @@ class Context:
                                             d_skip.data_ptr() if d_skip is not None else None,
                                             d_found.data_ptr() if d_found is not None else None, d_hits.data_ptr(), d_hits.numel() // 4,
                                             d_pool.data_ptr(), d_pool.numel(), d_counters.data_ptr(), stream))
+
+
+class Engine:
+    """The whole path on one or more GPUs of one box behind the C-ABI (crass_b200_engine_*): one caller, one set of
+    containers; reads are sharded contiguously over `devices` (a device may be named more than once)."""
+
+    def __init__(self, devices=(0,)):
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        _check(lib().crass_b200_engine_create(devs, len(devices), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib().crass_b200_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def num_devices(self):
+        return int(lib().crass_b200_engine_num_devices(self.h))
+
+    @property
+    def uses_nccl(self):
+        return bool(lib().crass_b200_engine_uses_nccl(self.h))
+
+    @property
+    def launch_count(self):
+        return int(lib().crass_b200_engine_launch_count(self.h))
+
+    def transfer_bytes(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        lib().crass_b200_engine_transfer_bytes(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def stage_ms(self):
+        v = [C.c_double(0) for _ in range(4)]
+        lib().crass_b200_engine_stage_ms(self.h, *[C.byref(x) for x in v])
+        return dict(zip(("parse", "phase1_h2d_k1_d2h", "exchange_cluster", "phase2"), (x.value for x in v)))
+
+    def run_files(self, paths, params=None, phases=2):
+        """searchFile* -> createNonRedundantSet -> findSingletons* on all devices; returns (Results, max_read_len)."""
+        params = params or Params()
+        arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+        out = C.c_void_p()
+        ml = C.c_int(0)
+        _check(lib().crass_b200_engine_run_files(self.h, arr, len(paths), C.byref(params), phases, C.byref(out), C.byref(ml)))
+        return Results(out), ml.value
+
+    def _take_hits(self, hp, nh, pp, npool):
+        hits = np.empty(nh.value, dtype=HIT_DTYPE)
+        pool = np.empty(npool.value, dtype=np.uint32)
+        if nh.value:
+            C.memmove(hits.ctypes.data, hp.value, hits.nbytes)
+        if npool.value:
+            C.memmove(pool.ctypes.data, pp.value, pool.nbytes)
+        lib().crass_b200_free(hp)
+        lib().crass_b200_free(pp)
+        return hits, pool
+
+    def search_file(self, path, params=None):
+        """searchFile on all devices -> (hits in global read order, ss_pool); the parsed file stays with the engine."""
+        params = params or Params()
+        b, hp, pp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nh, npool = C.c_uint32(0), C.c_uint32(0)
+        _check(lib().crass_b200_engine_search_file(self.h, path.encode(), C.byref(params), C.byref(b), C.byref(hp), C.byref(nh), C.byref(pp), C.byref(npool)))
+        return self._take_hits(hp, nh, pp, npool)
+
+    def exchange(self, path, kmer_clust=6):
+        """token blocks -> all-gather -> merge -> createNonRedundantSet -> (Automaton or None, n_variants, n_patterns)"""
+        ac = C.c_void_p()
+        nv, npat = C.c_uint32(0), C.c_uint32(0)
+        _check(lib().crass_b200_engine_exchange(self.h, path.encode(), kmer_clust, C.byref(ac), C.byref(nv), C.byref(npat)))
+        a = None
+        if ac.value:
+            a = Automaton.__new__(Automaton)
+            a.h = ac
+            a.num_patterns = npat.value
+        return a, nv.value, npat.value
+
+    def find_singletons(self, path, ac, skip_found=True):
+        b, hp, pp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nh, npool = C.c_uint32(0), C.c_uint32(0)
+        _check(lib().crass_b200_engine_find_singletons(self.h, path.encode(), ac.h, 1 if skip_found else 0, C.byref(b), C.byref(hp), C.byref(nh), C.byref(pp), C.byref(npool)))
+        return self._take_hits(hp, nh, pp, npool)
+
+    def release_file(self, path):
+        lib().crass_b200_engine_release_file(self.h, path.encode())
+
+
+def run_files_multi(devices, paths, params=None, phases=2):
+    """crass_b200_run_files_multi: a one-shot engine over `devices`; returns (Results, max_read_len)."""
+    params = params or Params()
+    devs = (C.c_int * len(devices))(*devices)
+    arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+    out = C.c_void_p()
+    ml = C.c_int(0)
+    _check(lib().crass_b200_run_files_multi(devs, len(devices), arr, len(paths), C.byref(params), phases, C.byref(out), C.byref(ml)))
+    return Results(out), ml.value

@@ -213,6 +213,7 @@ char* crass_b200_results_non_redundant(crass_b200_results* rh, uint32_t kmer_clu
     if (!rh) return nullptr;
     Results& r = rh->r;
     r.token_groups.clear();
+    r.lazy_kmer_clust = 0;
     r.non_redundant = non_redundant_set(r.t2s, (int)kmer_clust, &r.token_groups);
     if (n_patterns) *n_patterns = (uint32_t)r.non_redundant.size();
     std::string s;

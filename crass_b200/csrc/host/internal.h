@@ -63,6 +63,7 @@ struct Results {
     size_t n_found_phase1 = 0;
     std::vector<std::string> non_redundant;          // last computed pattern list
     std::vector<std::pair<int, int> > token_groups;  // (token, group id) in group order
+    int lazy_kmer_clust = 0;            // != 0: non_redundant / token_groups have not been computed yet (done by the first dump)
     ~Results();
     size_t num_reads() const;
 };

@@ -650,6 +650,11 @@ static uint32_t fnv1a32(const std::string& s) {
 }
 
 std::string dump_results(Results& r, int max_read_len) {
+    if (r.lazy_kmer_clust) {                             // the whole-path drivers leave this to whoever wants the text
+        r.token_groups.clear();
+        r.non_redundant = non_redundant_set(r.t2s, r.lazy_kmer_clust, &r.token_groups);
+        r.lazy_kmer_clust = 0;
+    }
     std::ostringstream os;
     os << "# crass-dump v1\n";
     os << "M\t" << max_read_len << "\t" << r.n_found_phase1 << "\t" << r.patterns_hash.size() << "\n";

@@ -318,6 +318,50 @@ int crass_b200_ac_build_from_pattern_list(const char* patterns, crass_b200_ac** 
 int crass_b200_run_files(crass_b200_ctx* ctx, const char* const* paths, uint32_t n_paths,
                          const crass_b200_params* params, int phases, crass_b200_results** out, int* max_read_len);
 
+/* ---- the same on one or more GPUs of one box, one caller, one set of containers -----------------------
+ * An engine owns one context, stream and host thread per device.  A file's reads are cut into contiguous shards, one per
+ * device; phase 1 and phase 2 run on the shards side by side; the shards' distinct DR tokens meet on the first device in
+ * ONE all-gather of fixed-size token blocks (NCCL when the devices are distinct and libnccl.so.2 can be loaded -- it is
+ * dlopen'ed, not linked -- peer copies otherwise; CRASS_B200_EXCHANGE=peer|host selects) and are merged there in
+ * first-appearance order, the numbering StringCheck gives a sequential run (StringCheck.cpp:46-55).  Hit records come
+ * back to the CALLING thread as one list in global read order with batch-wide read indices, so the caller fills its
+ * single ReadMap exactly as after a one-GPU run (WorkHorse.cpp:321-414; readsFound is tested on the host by header,
+ * libcrispr.cpp:411, which also covers headers that repeat across shards).  The same device may be named more than once
+ * (the shards then share it): that is how the multi-device logic is tested on a box with one GPU.
+ * A searched file stays parsed (page-locked host memory) and resident in HBM (bytes, offsets, phase-1 flags, 2-bit stream)
+ * until released, so findSingletons neither parses nor uploads it again; CRASS_B200_RESIDENT_MB bounds the bytes a device
+ * keeps (default: half its memory), older files are uploaded again from the host copy. */
+typedef struct crass_b200_engine crass_b200_engine;
+int crass_b200_engine_create(const int* devices, uint32_t n_devices, crass_b200_engine** out);
+void crass_b200_engine_destroy(crass_b200_engine* e);
+uint32_t crass_b200_engine_num_devices(const crass_b200_engine* e);
+int crass_b200_engine_uses_nccl(const crass_b200_engine* e);
+/* searchFile (libcrispr.h:74-80): parse, shard, copy in, K1 on every device; hits / ss_pool are malloc'd (crass_b200_free),
+ * *batch stays owned by the engine until crass_b200_engine_release_file (or a new search of the same path). */
+int crass_b200_engine_search_file(crass_b200_engine* e, const char* path, const crass_b200_params* params,
+                                  const crass_b200_batch** batch, crass_b200_hit** hits, uint32_t* n_hits,
+                                  uint32_t** ss_pool, uint32_t* n_ss_pool);
+/* the step between the phases for the ONE file searched last: K4b on every device, all-gather, K4c merge and
+ * createNonRedundantSet (K5 + host passes) on the first device; *ac = the matcher for phase 2 (NULL: no DR found) */
+int crass_b200_engine_exchange(crass_b200_engine* e, const char* path, uint32_t kmer_clust, crass_b200_ac** ac,
+                               uint32_t* n_variants, uint32_t* n_patterns);
+/* findSingletons (libcrispr.h:86-92): K2 on every device over the resident shards of `path` (parsed and copied in now if it
+ * was not searched through this engine); skip_found != 0 leaves out the reads this engine's phase 1 flagged */
+int crass_b200_engine_find_singletons(crass_b200_engine* e, const char* path, const crass_b200_ac* ac, int skip_found,
+                                      const crass_b200_batch** batch, crass_b200_hit** hits, uint32_t* n_hits,
+                                      uint32_t** ss_pool, uint32_t* n_ss_pool);
+void crass_b200_engine_release_file(crass_b200_engine* e, const char* path);
+/* WorkHorse::parseSeqFiles: searchFile* -> createNonRedundantSet -> findSingletons* on the engine's devices */
+int crass_b200_engine_run_files(crass_b200_engine* e, const char* const* paths, uint32_t n_paths, const crass_b200_params* params,
+                                int phases, crass_b200_results** out, int* max_read_len);
+int crass_b200_run_files_multi(const int* devices, uint32_t n_devices, const char* const* paths, uint32_t n_paths,
+                               const crass_b200_params* params, int phases, crass_b200_results** out, int* max_read_len);
+/* bookkeeping for bench.py: bytes copied host-to-device / device-to-host so far, kernel launches so far, and the stage
+ * times (ms) of the most recent crass_b200_engine_run_files */
+void crass_b200_engine_transfer_bytes(const crass_b200_engine* e, uint64_t* h2d, uint64_t* d2h);
+uint64_t crass_b200_engine_launch_count(const crass_b200_engine* e);
+void crass_b200_engine_stage_ms(const crass_b200_engine* e, double* parse, double* phase1, double* exchange, double* phase2);
+
 void crass_b200_free(void* p);
 
 #ifdef __cplusplus
