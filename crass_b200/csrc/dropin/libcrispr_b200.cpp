@@ -10,6 +10,7 @@
 //
 // What stays on the host, exactly as in the reference: ReadHolder construction, addReadHolder (DRLowLexi is the
 // reference's own ReadHolder method), the container updates in read order, progress lines, logging.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -28,19 +29,44 @@
 
 namespace {
 
+// One context for the single-read entry points, one engine for the two file-level ones.  CRASS_B200_DEVICES=0,1,...
+// (default: CRASS_B200_DEVICE or 0) names the GPUs the reads are sharded over; the hit records come back to this thread
+// as one list in read order whatever their number, so the containers below are filled as by a one-GPU run.
 struct Engine {
     crass_b200_ctx* ctx = nullptr;
-    ~Engine() { if (ctx) crass_b200_ctx_destroy(ctx); }
+    crass_b200_engine* eng = nullptr;
+    ~Engine() { if (eng) crass_b200_engine_destroy(eng); if (ctx) crass_b200_ctx_destroy(ctx); }
 };
+Engine& the_engine() { static Engine e; return e; }
+
+std::vector<int> device_list() {
+    std::vector<int> devs;
+    if (const char* l = getenv("CRASS_B200_DEVICES")) {
+        std::stringstream ss(l);
+        std::string tok;
+        while (std::getline(ss, tok, ',')) if (!tok.empty()) devs.push_back(atoi(tok.c_str()));
+    }
+    if (devs.empty()) { const char* dev = getenv("CRASS_B200_DEVICE"); devs.push_back(dev ? atoi(dev) : 0); }
+    return devs;
+}
 
 crass_b200_ctx* engine() {
-    static Engine e;
+    Engine& e = the_engine();
     if (!e.ctx) {
-        const char* dev = getenv("CRASS_B200_DEVICE");
-        if (crass_b200_ctx_create(dev ? atoi(dev) : 0, &e.ctx))
+        if (crass_b200_ctx_create(device_list()[0], &e.ctx))
             throw crispr::exception(__FILE__, __LINE__, __PRETTY_FUNCTION__, crass_b200_last_error());
     }
     return e.ctx;
+}
+
+crass_b200_engine* file_engine() {
+    Engine& e = the_engine();
+    if (!e.eng) {
+        const std::vector<int> devs = device_list();
+        if (crass_b200_engine_create(devs.data(), (uint32_t)devs.size(), &e.eng))
+            throw crispr::exception(__FILE__, __LINE__, __PRETTY_FUNCTION__, crass_b200_last_error());
+    }
+    return e.eng;
 }
 
 void check(int rc, const char* file, int line, const char* fn) {
@@ -56,10 +82,6 @@ crass_b200_params to_params(const options& o) {
     return p;
 }
 
-struct BatchGuard {
-    crass_b200_batch* b = nullptr;
-    ~BatchGuard() { crass_b200_batch_destroy(b); }
-};
 struct HitGuard {
     crass_b200_hit* hits = nullptr; uint32_t* pool = nullptr; uint32_t n = 0, np = 0;
     ~HitGuard() { crass_b200_free(hits); crass_b200_free(pool); }
@@ -97,29 +119,40 @@ void one_read(const ReadHolder& h, const uint32_t* extra, size_t n_extra, std::v
 int searchFile(const char* inputFastq, const options& opts, ReadMap* mReads, StringCheck* mStringCheck,
                lookupTable& patternsHash, lookupTable& readsFound, time_t& time_start) {
     static int read_counter = 0;
-    BatchGuard bg;
-    if (crass_b200_parse_file(inputFastq, &bg.b)) {                  // getFileHandle() exits on an unopenable file (SeqUtils.cpp:112-122)
-        std::cerr << PACKAGE_NAME << " : [ERROR] Could not open FASTQ " << inputFastq << " for reading." << std::endl;
-        exit(1);
+    const crass_b200_batch* batch = NULL;
+    HitGuard hg;
+    crass_b200_params p = to_params(opts);
+    // parse (worker threads) -> shards -> HBM -> K1 on every device; the file stays parsed and resident for findSingletons
+    if (crass_b200_engine_search_file(file_engine(), inputFastq, &p, &batch, &hg.hits, &hg.n, &hg.pool, &hg.np)) {
+        const std::string why = crass_b200_last_error();
+        if (why.find("cannot open") != std::string::npos) {          // getFileHandle() exits on an unopenable file (SeqUtils.cpp:112-122)
+            std::cerr << PACKAGE_NAME << " : [ERROR] Could not open FASTQ " << inputFastq << " for reading." << std::endl;
+            exit(1);
+        }
+        std::cerr << why << std::endl;
+        throw crispr::exception(__FILE__, __LINE__, __PRETTY_FUNCTION__, "Fatal error in search algorithm!");
     }
-    const uint32_t n = crass_b200_batch_num_reads(bg.b);
-    const int max_read_length = (int)crass_b200_batch_max_read_len(bg.b);
+    const uint32_t n = crass_b200_batch_num_reads(batch);
+    const int max_read_length = (int)crass_b200_batch_max_read_len(batch);
     try {
-        crass_b200_params p = to_params(opts);
-        HitGuard hg;
-        B200_TRY(crass_b200_batch_upload(engine(), crass_b200_batch_bases(bg.b), crass_b200_batch_offsets(bg.b), n));
-        B200_TRY(crass_b200_dr_search_resident(engine(), &p, NULL, &hg.hits, &hg.n, &hg.pool, &hg.np));
-        uint32_t next_tick = CRASS_DEF_READ_COUNTER_LOGGER;
-        for (uint32_t k = 0; k < hg.n; ++k) {                        // hits come back sorted by read index
-            const crass_b200_hit& ht = hg.hits[k];
-            while (ht.read_index >= next_tick) { progress("patternFinder", read_counter + (int)next_tick, time_start); next_tick += CRASS_DEF_READ_COUNTER_LOGGER; }
-            ReadHolder tmp_holder;
-            fill_holder(tmp_holder, bg.b, ht.read_index);
-            for (uint32_t i = 0; i + 1 < ht.n_ss; i += 2) tmp_holder.startStopsAdd(hg.pool[ht.ss_offset + i], hg.pool[ht.ss_offset + i + 1]);
-            tmp_holder.setRepeatLength((int)ht.repeat_len);
-            addReadHolder(mReads, mStringCheck, tmp_holder);
-            patternsHash[tmp_holder.repeatStringAt(0)] = true;
-            readsFound[tmp_holder.getHeader()] = true;
+        // the reference prints a progress line before every 100 000th read of a FILE (its log_counter is per call,
+        // libcrispr.cpp:91,99-109) showing the running total; the reads are all through the device by now, so the lines of
+        // this file come in one go, with the hits replayed in between in read order
+        uint32_t k = 0;
+        for (uint32_t done = 0; done < n;) {
+            const uint32_t upto = (uint32_t)std::min<uint64_t>(n, (uint64_t)done + CRASS_DEF_READ_COUNTER_LOGGER);
+            for (; k < hg.n && hg.hits[k].read_index < upto; ++k) {     // hits come back sorted by read index
+                const crass_b200_hit& ht = hg.hits[k];
+                ReadHolder tmp_holder;
+                fill_holder(tmp_holder, batch, ht.read_index);
+                for (uint32_t i = 0; i + 1 < ht.n_ss; i += 2) tmp_holder.startStopsAdd(hg.pool[ht.ss_offset + i], hg.pool[ht.ss_offset + i + 1]);
+                tmp_holder.setRepeatLength((int)ht.repeat_len);
+                addReadHolder(mReads, mStringCheck, tmp_holder);
+                patternsHash[tmp_holder.repeatStringAt(0)] = true;
+                readsFound[tmp_holder.getHeader()] = true;
+            }
+            done = upto;
+            if (done < n) progress("patternFinder", read_counter + (int)done, time_start);
         }
     } catch (crispr::exception& e) {
         std::cerr << e.what() << std::endl;
@@ -144,30 +177,40 @@ void findSingletons(const char* inputFastq, const options& opts, std::vector<std
     }
     crass_b200_ac* ac = NULL;
     B200_TRY(crass_b200_ac_build(bytes.data(), offs.data(), (uint32_t)nonRedundantPatterns->size(), &ac));
-    BatchGuard bg;
-    if (crass_b200_parse_file(inputFastq, &bg.b)) {
-        crass_b200_ac_destroy(ac);
-        std::cerr << PACKAGE_NAME << " : [ERROR] Could not open FASTQ " << inputFastq << " for reading." << std::endl;
-        exit(1);
-    }
-    const uint32_t n = crass_b200_batch_num_reads(bg.b);
+    const crass_b200_batch* batch = NULL;
     HitGuard hg;
-    // every read is scanned (readsFound is keyed by header, so the test stays on the host, libcrispr.cpp:411)
-    int rc = crass_b200_ac_scan(engine(), ac, crass_b200_batch_bases(bg.b), crass_b200_batch_offsets(bg.b), n, NULL, NULL,
-                                &hg.hits, &hg.n, &hg.pool, &hg.np);
+    // K2 over the shards searchFile left in HBM (no second parse, no second copy; a file this engine has not seen is parsed
+    // and copied in now).  Every read is scanned: readsFound is the CALLER's table, keyed by header, and may hold names the
+    // device flags know nothing about, so that test stays on the host (libcrispr.cpp:411).
+    int rc = crass_b200_engine_find_singletons(file_engine(), inputFastq, ac, 0, &batch, &hg.hits, &hg.n, &hg.pool, &hg.np);
     crass_b200_ac_destroy(ac);
-    B200_TRY(rc);
-    for (uint32_t k = 0; k < hg.n; ++k) {                            // on_match (libcrispr.cpp:408-442)
-        const crass_b200_hit& ht = hg.hits[k];
-        const char* name = crass_b200_batch_name(bg.b, ht.read_index);
-        if (readsFound.find(name) != readsFound.end()) continue;
-        ReadHolder tmp_holder;
-        fill_holder(tmp_holder, bg.b, ht.read_index);
-        tmp_holder.startStopsAdd(hg.pool[ht.ss_offset], hg.pool[ht.ss_offset + 1]);
-        addReadHolder(mReads, mStringCheck, tmp_holder);
+    if (rc) {
+        const std::string why = crass_b200_last_error();
+        if (why.find("cannot open") != std::string::npos) {
+            std::cerr << PACKAGE_NAME << " : [ERROR] Could not open FASTQ " << inputFastq << " for reading." << std::endl;
+            exit(1);
+        }
+        throw crispr::exception(__FILE__, __LINE__, __PRETTY_FUNCTION__, why.c_str());
+    }
+    const uint32_t n = crass_b200_batch_num_reads(batch);
+    uint32_t k = 0;
+    for (uint32_t done = 0; done < n;) {                             // progress lines as in libcrispr.cpp:495-496
+        const uint32_t upto = (uint32_t)std::min<uint64_t>(n, (uint64_t)done + CRASS_DEF_READ_COUNTER_LOGGER);
+        for (; k < hg.n && hg.hits[k].read_index < upto; ++k) {      // on_match (libcrispr.cpp:408-442)
+            const crass_b200_hit& ht = hg.hits[k];
+            const char* name = crass_b200_batch_name(batch, ht.read_index);
+            if (readsFound.find(name) != readsFound.end()) continue;
+            ReadHolder tmp_holder;
+            fill_holder(tmp_holder, batch, ht.read_index);
+            tmp_holder.startStopsAdd(hg.pool[ht.ss_offset], hg.pool[ht.ss_offset + 1]);
+            addReadHolder(mReads, mStringCheck, tmp_holder);
+        }
+        done = upto;
+        if (done < n) progress("singletonFinder", read_counter + (int)done, startTime);
     }
     read_counter += (int)n;
     progress("singletonFinder", read_counter, startTime);
+    crass_b200_engine_release_file(file_engine(), inputFastq);      // phase 2 is the last use of a file (WorkHorse.cpp:381-399)
 }
 
 // ---- single-read entry points kept for source compatibility (and used by crass's own unit tests) -----------------

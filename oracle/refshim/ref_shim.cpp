@@ -43,11 +43,12 @@ extern "C" {
 
 namespace {
 
-struct CoutSilencer {
+struct CoutSilencer {                                      // the progress lines of libcrispr; CRASS_REF_SHOW_PROGRESS=1 lets them through
     std::streambuf* old;
     std::ostringstream sink;
-    CoutSilencer() { old = std::cout.rdbuf(sink.rdbuf()); }
-    ~CoutSilencer() { std::cout.rdbuf(old); }
+    bool on;
+    CoutSilencer() : old(nullptr), on(getenv("CRASS_REF_SHOW_PROGRESS") == nullptr) { if (on) old = std::cout.rdbuf(sink.rdbuf()); }
+    ~CoutSilencer() { if (on) std::cout.rdbuf(old); }
 };
 
 bool g_inited = false;

@@ -80,3 +80,63 @@ def test_reference_catch_tests_on_the_gpu():
         pytest.skip("crass-test-b200 not built")
     out = subprocess.run([CATCH_B200], capture_output=True, text=True, env=dict(os.environ, MALLOC_PERTURB_="255"))
     assert out.returncode == 0 and "139 assertions in 7 test cases" in out.stdout, out.stdout[-2000:]
+
+
+_CHILD = r"""
+import os, sys, hashlib, ctypes as C
+sys.path.insert(0, %(tests)r)
+import checkers
+which, paths = sys.argv[1], sys.argv[2:]
+if which == "dropin":
+    lib = C.CDLL(%(dropin)r)
+    lib.ref_init()
+    class D(checkers._Base):
+        prefix = "ref_"
+    H = D(lib)
+else:
+    H = checkers.ref()
+sys.stdout.flush()
+dump, _ = H.run_files(paths)
+sys.stdout.flush()
+print("\nDUMP_MD5 " + hashlib.md5(dump.encode("latin-1")).hexdigest())
+"""
+
+
+def _run_child(which, paths, env=None):
+    """the harness in a process of its own: the shim's engine is a process-wide object created on first use, and the
+    progress lines go to the C++ std::cout of that process"""
+    import re
+    import sys
+    code = _CHILD % dict(tests=os.path.dirname(os.path.abspath(__file__)), dropin=DROPIN_SO)
+    out = subprocess.run([sys.executable, "-c", code, which] + list(paths), capture_output=True, text=True,
+                         env=dict(os.environ, CRASS_REF_SHOW_PROGRESS="1", **(env or {})))
+    assert out.returncode == 0, out.stderr[-3000:]
+    md5 = re.search(r"DUMP_MD5 (\w+)", out.stdout).group(1)
+    ticks = re.findall(r"\[crass_(\w+)\]: Processed (\d+) \.\.\.", out.stdout)
+    return md5, ticks
+
+
+@pytest.mark.parametrize("devices", ["0", "0,0", "0,0,0,0"])
+def test_shim_on_several_devices_and_its_progress_lines(D, devices, tmp_path):
+    """CRASS_B200_DEVICES shards the reads of searchFile / findSingletons over the named GPUs (here the same one several
+    times); the reference's containers come out the same, and so do the progress lines the reference prints before every
+    100 000th read of a file and at the end of each file (libcrispr.cpp:99-109,161-162,495-496,515-516)."""
+    import random
+    import fuzzgen
+    if not checkers.have_ref():
+        pytest.skip("oracle/_ref/libcrass_ref.so not built")
+    rng = random.Random(77)
+    pool = [fuzzgen.rand_seq(rng, rng.randint(24, 40)) for _ in range(5)]
+    paths = []
+    for f, n in enumerate((230_000, 100_000, 7)):                     # ticks inside a file, a file of exactly one tick, a tiny one
+        p = str(tmp_path / ("f%d.fa" % f))
+        with open(p, "wb") as fh:
+            for i in range(n):
+                r = rng.random()
+                s = fuzzgen.planted_read(rng, 120, dr=rng.choice(pool)) if r < 0.01 else (fuzzgen.rand_seq(rng, 30) + rng.choice(pool) + fuzzgen.rand_seq(rng, 50) if r < 0.02 else fuzzgen.rand_seq(rng, 100))
+                fh.write(b">f%d_%06d\n%s\n" % (f, i, s))
+        paths.append(p)
+    want_md5, want_ticks = _run_child("ref", paths)
+    got_md5, got_ticks = _run_child("dropin", paths, {"CRASS_B200_DEVICES": devices})
+    assert got_md5 == want_md5
+    assert got_ticks == want_ticks and len(want_ticks) >= 10
