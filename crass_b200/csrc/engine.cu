@@ -130,6 +130,7 @@ struct Lane {                                             // one device: context
     void* comm = nullptr;                                 // ncclComm_t
     int rc = 0;
     std::string err;
+    std::vector<std::unique_ptr<Shard> > spare;           // shards of released files: their HBM buffers serve the next file
 };
 
 struct FileState {
@@ -145,6 +146,7 @@ struct FileState {
 struct crass_b200_engine {
     std::vector<std::unique_ptr<Lane> > lanes;
     std::vector<std::unique_ptr<FileState> > files;
+    std::vector<crass_b200_batch*> batch_pool;            // released batches: their buffers (page-locked bases) serve the next parse
     Nccl nccl;
     bool use_nccl = false;
     uint32_t block_cap = 16384;                           // token-block capacity per shard (grows on overflow)
@@ -179,6 +181,43 @@ int for_each_lane(crass_b200_engine* e, F fn) {
     }
     for (auto& l : e->lanes) if (l->rc) return cbh::fail(l->rc, "device " + std::to_string(l->device) + ": " + l->err);
     return 0;
+}
+
+// kseq-compatible parse of `path` into a batch from the engine's pool (a fresh one the first time)
+int parse_pooled(crass_b200_engine* e, const char* path, crass_b200_batch** out) {
+    crass_b200_batch* h = nullptr;
+    if (!e->batch_pool.empty()) { h = e->batch_pool.back(); e->batch_pool.pop_back(); }
+    else h = new crass_b200_batch();
+    cbh::Batch* got = nullptr;
+    const int rc = cbh::parse_file(path, &got, &h->b);
+    if (rc) { e->batch_pool.push_back(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+void retire_batch(crass_b200_engine* e, crass_b200_batch* b) {
+    if (!b) return;
+    if (e->batch_pool.size() < 2) e->batch_pool.push_back(b);
+    else crass_b200_batch_destroy(b);
+}
+
+std::unique_ptr<Shard> take_shard(Lane& l) {
+    if (l.spare.empty()) return std::unique_ptr<Shard>(new Shard());
+    std::unique_ptr<Shard> s = std::move(l.spare.back());
+    l.spare.pop_back();
+    s->resident = s->searched = false;
+    return s;
+}
+
+void make_shards(crass_b200_engine* e, FileState& fs) {               // contiguous shards of (almost) equal read counts
+    const cbh::Batch& b = fs.batch->b;
+    const uint32_t n = b.n(), G = (uint32_t)e->lanes.size();
+    for (uint32_t g = 0; g < G; ++g) {
+        std::unique_ptr<Shard> s = take_shard(*e->lanes[g]);
+        s->r0 = (uint32_t)((uint64_t)n * g / G); s->r1 = (uint32_t)((uint64_t)n * (g + 1) / G);
+        s->b0 = b.offsets[s->r0]; s->b1 = b.offsets[s->r1];
+        fs.shards.push_back(std::move(s));
+    }
 }
 
 FileState* find_file(crass_b200_engine* e, const char* path) {
@@ -355,8 +394,10 @@ void crass_b200_engine_destroy(crass_b200_engine* e) {
         }
         crass_b200_batch_destroy(f->batch);
     }
+    for (crass_b200_batch* b : e->batch_pool) crass_b200_batch_destroy(b);
     for (auto& l : e->lanes) {
         cudaSetDevice(l->device);
+        for (auto& s : l->spare) { s->d_bases.release(); s->d_offsets.release(); s->d_found.release(); }
         if (l->stream) cudaStreamSynchronize(l->stream);
         if (l->comm && e->nccl.CommDestroy) e->nccl.CommDestroy(l->comm);
         for (DBuf* b : {&l->d_hits, &l->d_sorted, &l->d_pool, &l->d_cnt, &l->d_tokens, &l->d_found2, &l->d_block, &l->d_recv, &l->d_merged}) b->release();
@@ -397,10 +438,12 @@ void crass_b200_engine_release_file(crass_b200_engine* e, const char* path) {
         if (e->files[i]->path != path) continue;
         FileState* f = e->files[i].get();
         for (size_t g = 0; g < f->shards.size(); ++g) {
-            cudaSetDevice(e->lanes[g]->device);
+            Lane& l = *e->lanes[g];
+            if (l.spare.size() < 2) { l.spare.push_back(std::move(f->shards[g])); continue; }
+            cudaSetDevice(l.device);
             f->shards[g]->d_bases.release(); f->shards[g]->d_offsets.release(); f->shards[g]->d_found.release();
         }
-        crass_b200_batch_destroy(f->batch);
+        retire_batch(e, f->batch);
         e->files.erase(e->files.begin() + (long)i);
         return;
     }
@@ -415,17 +458,12 @@ int crass_b200_engine_search_file(crass_b200_engine* e, const char* path, const 
     std::unique_ptr<FileState> fs(new FileState());
     fs->path = path;
     double t0 = now_ms();
-    if (int r = crass_b200_parse_file(path, &fs->batch)) return r;
+    if (int r = parse_pooled(e, path, &fs->batch)) return r;
     fs->parse_ms = now_ms() - t0;
     e->t_parse += fs->parse_ms;
     const cbh::Batch& b = fs->batch->b;
-    const uint32_t n = b.n(), G = (uint32_t)e->lanes.size();
-    for (uint32_t g = 0; g < G; ++g) {                                        // contiguous shards of (almost) equal read counts
-        std::unique_ptr<Shard> s(new Shard());
-        s->r0 = (uint32_t)((uint64_t)n * g / G); s->r1 = (uint32_t)((uint64_t)n * (g + 1) / G);
-        s->b0 = b.offsets[s->r0]; s->b1 = b.offsets[s->r1];
-        fs->shards.push_back(std::move(s));
-    }
+    const uint32_t G = (uint32_t)e->lanes.size();
+    make_shards(e, *fs);
     FileState* f = fs.get();
     e->files.push_back(std::move(fs));
     drop_residency_if_needed(e, f);
@@ -474,16 +512,9 @@ int crass_b200_engine_find_singletons(crass_b200_engine* e, const char* path, co
         std::unique_ptr<FileState> fs(new FileState());
         fs->path = path;
         const double t0 = now_ms();
-        if (int r = crass_b200_parse_file(path, &fs->batch)) return r;
+        if (int r = parse_pooled(e, path, &fs->batch)) return r;
         e->t_parse += now_ms() - t0;
-        const cbh::Batch& b = fs->batch->b;
-        const uint32_t n = b.n(), G = (uint32_t)e->lanes.size();
-        for (uint32_t g = 0; g < G; ++g) {
-            std::unique_ptr<Shard> s(new Shard());
-            s->r0 = (uint32_t)((uint64_t)n * g / G); s->r1 = (uint32_t)((uint64_t)n * (g + 1) / G);
-            s->b0 = b.offsets[s->r0]; s->b1 = b.offsets[s->r1];
-            fs->shards.push_back(std::move(s));
-        }
+        make_shards(e, *fs);
         f = fs.get();
         e->files.push_back(std::move(fs));
     }

@@ -135,25 +135,65 @@ int crass_b200_results_create(crass_b200_results** out) {
 }
 void crass_b200_results_destroy(crass_b200_results* r) { delete r; }
 
+// Replay is the serial end of the path, so it is cut in two: building the holders (string copies, DRLowLexi with its
+// reverse complements) is per-read work and runs on the helper threads; only the container updates, whose order is the
+// result, stay on the calling thread.
+namespace {
+struct Built { HeldRead* h; std::string token, raw0; };
+
+void build_holders(const Batch& b, const crass_b200_hit* hits, const uint32_t* which, uint32_t n, const uint32_t* ss_pool, int phase,
+                   std::vector<Built>& out) {
+    out.resize(n);
+    const unsigned workers = n >= 2048 ? std::min<unsigned>(cbh::host_threads(), 16) : 1;
+    cbh::parallel_run(workers, [&](unsigned w) {
+        const uint32_t lo = (uint32_t)((uint64_t)n * w / workers), hi = (uint32_t)((uint64_t)n * (w + 1) / workers);
+        for (uint32_t k = lo; k < hi; ++k) {
+            const crass_b200_hit& ht = hits[which ? which[k] : k];
+            HeldRead* h = new HeldRead();
+            fill_holder(*h, b, ht.read_index);
+            h->ss.assign(ss_pool + ht.ss_offset, ss_pool + ht.ss_offset + ht.n_ss);
+            h->repeat_len = phase == 1 ? ht.repeat_len : 0;
+            h->phase = phase;
+            Built& o = out[k];
+            o.h = h;
+            if (phase == 1) {                                        // patternsHash takes repeatStringAt(0) of the un-flipped temporary holder
+                const uint32_t st = h->ss[0];
+                if (st <= h->seq.size()) o.raw0 = h->seq.substr(st, (size_t)(h->ss[1] - h->ss[0] + 1));
+            }
+            o.token = dr_lowlexi(*h);
+        }
+    });
+}
+
+void insert_holder(Results& r, Built& o) {                           // addReadHolder's container half (libcrispr.cpp:1119-1162)
+    auto it = r.s2t.find(o.token);
+    int tok;
+    if (it == r.s2t.end()) {
+        tok = ++r.next_free_token;                                   // first token is 2
+        r.s2t[o.token] = tok;
+        r.t2s.push_back(o.token);
+    } else tok = it->second;
+    o.h->token = tok;
+    r.reads[tok].push_back(o.h);
+}
+}  // namespace
+
 int crass_b200_results_add_phase1(crass_b200_results* rh, const crass_b200_batch* bh, const crass_b200_hit* hits, uint32_t n_hits,
                                   const uint32_t* ss_pool) {
     if (!rh || !bh || (n_hits && (!hits || !ss_pool))) return fail(CRASS_B200_EINVAL, "NULL argument");
     Results& r = rh->r;
     const Batch& b = bh->b;
     if (int e = check_hits(b, hits, n_hits)) return e;
-    for (uint32_t k = 0; k < n_hits; ++k) {                                 // searchFile's loop body for a hit (libcrispr.cpp:134-139)
-        const crass_b200_hit& ht = hits[k];
-        HeldRead* h = new HeldRead();
-        fill_holder(*h, b, ht.read_index);
-        h->ss.assign(ss_pool + ht.ss_offset, ss_pool + ht.ss_offset + ht.n_ss);
-        h->repeat_len = ht.repeat_len;
-        h->phase = 1;
-        // patternsHash takes repeatStringAt(0) of the un-flipped temporary holder
-        const uint32_t st = h->ss[0];
-        std::string raw0 = st <= h->seq.size() ? h->seq.substr(st, (size_t)(h->ss[1] - h->ss[0] + 1)) : std::string();
-        add_read_holder(r, h);
-        r.patterns_hash[raw0] = true;
-        r.reads_found[h->header] = true;
+    try {
+        std::vector<Built> built;
+        build_holders(b, hits, nullptr, n_hits, ss_pool, 1, built);
+        for (uint32_t k = 0; k < n_hits; ++k) {                             // searchFile's loop body for a hit (libcrispr.cpp:134-139)
+            insert_holder(r, built[k]);
+            r.patterns_hash[built[k].raw0] = true;
+            r.reads_found.emplace_hint(r.reads_found.end(), built[k].h->header, true);   // a no-op for a header that is there already
+        }
+    } catch (std::exception& ex) {
+        return fail(CRASS_B200_ENOMEM, std::string("results_add_phase1: ") + ex.what());
     }
     r.n_found_phase1 = r.reads_found.size();
     return 0;
@@ -165,16 +205,20 @@ int crass_b200_results_add_phase2(crass_b200_results* rh, const crass_b200_batch
     Results& r = rh->r;
     const Batch& b = bh->b;
     if (int e = check_hits(b, hits, n_hits)) return e;
-    for (uint32_t k = 0; k < n_hits; ++k) {                                 // on_match (libcrispr.cpp:408-442)
-        const crass_b200_hit& ht = hits[k];
-        const char* name = b.name_pool.data() + b.name_off[ht.read_index];
-        if (r.reads_found.find(name) != r.reads_found.end()) continue;      // keyed by HEADER, not by index
-        HeldRead* h = new HeldRead();
-        fill_holder(*h, b, ht.read_index);
-        h->ss.assign(ss_pool + ht.ss_offset, ss_pool + ht.ss_offset + ht.n_ss);
-        h->repeat_len = 0;
-        h->phase = 2;
-        add_read_holder(r, h);
+    try {
+        // on_match (libcrispr.cpp:408-442): readsFound is tested by HEADER and never written here, so the test can be made
+        // for all hits up front
+        std::vector<uint32_t> take;
+        take.reserve(n_hits);
+        for (uint32_t k = 0; k < n_hits; ++k) {
+            const char* name = b.name_pool.data() + b.name_off[hits[k].read_index];
+            if (r.reads_found.find(name) == r.reads_found.end()) take.push_back(k);
+        }
+        std::vector<Built> built;
+        build_holders(b, hits, take.data(), (uint32_t)take.size(), ss_pool, 2, built);
+        for (Built& o : built) insert_holder(r, o);
+    } catch (std::exception& ex) {
+        return fail(CRASS_B200_ENOMEM, std::string("results_add_phase2: ") + ex.what());
     }
     return 0;
 }

@@ -37,9 +37,16 @@ struct Batch {
     uint32_t n() const { return (uint32_t)(offsets.size() - 1); }
     ~Batch();
     void reserve_bases(size_t need);
+    // empty again, keeping every buffer (the page-locked base buffer above all: allocating one costs more than parsing
+    // a file into it, so the engine hands released batches to the next parse)
+    void reset() {
+        offsets.clear(); name_pool.clear(); name_off.clear(); text_pool.clear(); comment_off.clear(); qual_off.clear();
+        max_len = 0; parse_status = -1;
+    }
 };
 
-int parse_file(const char* path, Batch** out);
+// parses into `reuse` when given (which the caller keeps owning, also on failure), else into a new Batch
+int parse_file(const char* path, Batch** out, Batch* reuse = nullptr);
 
 // ---- the containers the reference fills (ReadMap / StringCheck / lookupTable) ----------------------
 struct HeldRead {                       // the fields of ReadHolder the path sets (ReadHolder.h:440-451)
@@ -90,6 +97,11 @@ struct ClusterPre {
 };
 std::vector<std::string> non_redundant_set(const std::vector<std::string_view>& drs, int min_count,
                                            std::vector<std::pair<int, int> >* groups, const ClusterPre* pre = nullptr);
+// runs job(0..n-1) on the library's persistent helper threads (job(0) on the caller) and returns when all are through; an
+// exception thrown by a job is rethrown on the caller.  host_threads(): how many the host passes may use
+// (CRASS_B200_HOST_THREADS, default min(8, hardware threads)).
+void parallel_run(unsigned n, const std::function<void(unsigned)>& job);
+unsigned host_threads();
 // wakes the helper threads of non_redundant_set ahead of a call that is about to come (they poll for it for spin_us)
 void prewake_cluster_workers(unsigned spin_us);
 // the DR tokens of a host copy of a token block (include/crass_b200.h) as views into it, in first-appearance order

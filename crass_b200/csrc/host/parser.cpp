@@ -42,7 +42,7 @@ void Batch::reserve_bases(size_t need) {
     uint8_t* nb = (uint8_t*)alloc_host(ncap, &pin);
     if (!nb) throw std::bad_alloc();
     if (bases) {
-        memcpy(nb, bases, (size_t)offsets.back());
+        if (!offsets.empty()) memcpy(nb, bases, (size_t)offsets.back());
         free_host(bases, pinned);
     }
     bases = nb; bases_cap = ncap; pinned = pin;
@@ -287,10 +287,11 @@ size_t env_size(const char* name, size_t dflt) {
 // resynchronisation point that can be recognised locally ('@' and '>' are legal quality characters), so a piece is
 // only kept when the piece before it ENDS exactly on the header it started from; otherwise the gap is parsed again
 // from the true position on the calling thread.  The record stream is therefore the sequential one by construction.
-int parse_file(const char* path, Batch** out) {
+int parse_file(const char* path, Batch** out, Batch* reuse) {
     Input in;
     if (!in.open(path)) return fail(CRASS_B200_EIO, std::string("cannot open ") + path);
-    Batch* B = new Batch();
+    Batch* B = reuse ? reuse : new Batch();
+    B->reset();
     try {
         B->offsets.push_back(0);
         const size_t n = in.size;
@@ -422,7 +423,7 @@ int parse_file(const char* path, Batch** out) {
                     "parse %.1f ms, gaps %.1f ms, alloc %.1f ms, splice %.1f ms\n",
                     np, order.size() - patches.size(), patches.size(), n_threads, t1 - t0, t2 - t1, t3 - t2, now() - t3);
     } catch (std::exception& ex) {
-        delete B;
+        if (!reuse) delete B;
         return fail(CRASS_B200_ENOMEM, std::string("parse_file: ") + ex.what());
     }
     *out = B;

@@ -281,6 +281,9 @@ struct HeadTable {
 };
 }  // namespace
 
+void parallel_run(unsigned n, const std::function<void(unsigned)>& job) { WorkerPool::instance().run(n, job); }
+unsigned host_threads() { return cluster_workers((size_t)1 << 20); }
+
 void prewake_cluster_workers(unsigned spin_us) { WorkerPool::instance().prewake(cluster_workers((size_t)1 << 20), spin_us); }
 
 std::vector<std::string> non_redundant_set(const std::vector<std::string>& drs, int min_count,
