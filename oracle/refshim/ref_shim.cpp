@@ -146,8 +146,8 @@ void cluster_dr(ClusterState& cs, StringCheck& sc, int token, int min_count) { /
     for (size_t i = 0; i < homeless.size(); ++i) cs.k2gid[homeless[i]] = group;
 }
 
-std::vector<std::string> non_redundant_set(ReadMap& reads, StringCheck& sc, int min_count,
-                                           std::vector<std::pair<int, int> >* token_groups) {
+std::vector<std::string> restated_non_redundant_set(ReadMap& reads, StringCheck& sc, int min_count,
+                                                    std::vector<std::pair<int, int> >* token_groups) {
     ClusterState cs;
     for (ReadMapIterator it = reads.begin(); it != reads.end(); ++it) cluster_dr(cs, sc, it->first, min_count);
     std::vector<std::string> out;
@@ -164,6 +164,19 @@ std::vector<std::string> non_redundant_set(ReadMap& reads, StringCheck& sc, int 
         out.insert(out.end(), rc.begin(), rc.end());
     }
     return out;
+}
+
+}  // namespace
+// the reference's own clusterDRReads / removeRedundantRepeats / createNonRedundantSet (workhorse_pin.cpp)
+std::vector<std::string> workhorse_non_redundant_set(ReadMap& reads, StringCheck& sc, options& o, std::vector<std::pair<int, int> >* token_groups);
+namespace {
+
+// The step between the phases runs the reference's own WorkHorse code; CRASS_REF_CLUSTER=restated selects the restatement
+// above instead (tests compare the two).
+std::vector<std::string> non_redundant_set(ReadMap& reads, StringCheck& sc, options& o, std::vector<std::pair<int, int> >* token_groups) {
+    const char* sel = getenv("CRASS_REF_CLUSTER");
+    if (sel && !strcmp(sel, "restated")) return restated_non_redundant_set(reads, sc, o.kmer_clust_size, token_groups);
+    return workhorse_non_redundant_set(reads, sc, o, token_groups);
 }
 
 uint32_t fnv1a(const std::string& s) {
@@ -387,7 +400,7 @@ char* ref_run_files(const char* const* paths, uint32_t n_paths, const uint32_t* 
             for (ReadListIterator r = it->second->begin(); r != it->second->end(); ++r) phase_of[*r] = 1;
         size_t n_p1 = found.size();
         std::vector<std::pair<int, int> > token_groups;
-        std::vector<std::string> nr = non_redundant_set(reads, sc, o.kmer_clust_size, &token_groups);
+        std::vector<std::string> nr = non_redundant_set(reads, sc, o, &token_groups);
         clk::time_point c = clk::now();
         if (phases >= 2 && nr.size() > 0) {
             time(&t0);
@@ -421,13 +434,23 @@ char* ref_run_files(const char* const* paths, uint32_t n_paths, const uint32_t* 
     return dup_string(os.str());
 }
 
+// which code runs the step between the phases in this build / environment
+const char* ref_cluster_impl(void) {
+    const char* sel = getenv("CRASS_REF_CLUSTER");
+    return (sel && !strcmp(sel, "restated")) ? "restatement (ref_shim.cpp)" : "reference WorkHorse.cpp:612-709,1404-1637 (compiled from the reference's own text)";
+}
+
 // clustering + non-redundant set alone, on an ordered list of DR token strings (tokens 2,3,...)
 char* ref_non_redundant(const char* const* drs, const uint32_t* lens, uint32_t n, int min_count) {
     StringCheck sc;
     ReadMap reads;
     for (uint32_t i = 0; i < n; ++i) { int t = sc.addString(std::string(drs[i], lens[i])); reads[t] = NULL; }
     std::vector<std::pair<int, int> > tg;
-    std::vector<std::string> nr = non_redundant_set(reads, sc, min_count, &tg);
+    options o;
+    uint32_t dflt[7] = {23, 47, 26, 50, 8, 2, (uint32_t)min_count};
+    fill_options(o, dflt);
+    CoutSilencer quiet;
+    std::vector<std::string> nr = non_redundant_set(reads, sc, o, &tg);
     std::ostringstream os;
     for (size_t i = 0; i < tg.size(); ++i) os << "G\t" << tg[i].first << "\t" << tg[i].second << "\n";
     for (size_t i = 0; i < nr.size(); ++i) os << "P\t" << nr[i] << "\n";

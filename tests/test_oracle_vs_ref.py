@@ -188,3 +188,38 @@ def test_bundled_files_ref_vs_port(R, P, name):
         a, _ = R.run_files([path], prm)
         b, _ = P.run_files([path], prm)
         assert a == b, (name, prm)
+
+
+def test_the_step_between_the_phases_is_the_references_own_code(R, P):
+    """clusterDRReads / removeRedundantRepeats / createNonRedundantSet in oracle/_ref are cut verbatim out of the
+    reference's WorkHorse.cpp at build time (oracle/refshim/gen_workhorse_excerpt.py) -- the checker does not restate them.
+    The restatement kept in the harness (CRASS_REF_CLUSTER=restated) and the plain-C oracle must agree with it, also on
+    letters outside A/C/G/T and on lists of the size a multi-GPU run merges."""
+    import ctypes as C
+    import os
+    R.lib.ref_cluster_impl.restype = C.c_char_p
+    assert b"WorkHorse.cpp" in R.lib.ref_cluster_impl()
+    rng = random.Random(23)
+    comp = bytes.maketrans(b"ACGTN", b"TGCAN")
+    for trial in range(6):
+        base = [fuzzgen.rand_seq(rng, rng.randint(23, 47)) for _k in range(rng.randint(3, 40))]
+        drs = set()
+        for b in base:
+            for _k in range(rng.randint(1, 60 if trial == 5 else 12)):
+                v = fuzzgen.mutate(rng, b, rng.choice([0, 0.02, 0.05]), b"ACGTN" if trial % 2 else b"ACGT")
+                a, e = rng.randint(0, 4), rng.randint(0, 4)
+                v = v[a:len(v) - e] if rng.random() < 0.5 else fuzzgen.rand_seq(rng, a) + v + fuzzgen.rand_seq(rng, e)
+                drs.add(min(v, v.translate(comp)[::-1]))
+        drs = list(drs)
+        rng.shuffle(drs)
+        real = R.non_redundant(drs)
+        os.environ["CRASS_REF_CLUSTER"] = "restated"
+        try:
+            assert b"restatement" in R.lib.ref_cluster_impl()
+            restated = R.non_redundant(drs)
+        finally:
+            os.environ.pop("CRASS_REF_CLUSTER", None)
+        port = P.non_redundant(drs)
+        for other in (restated, port):
+            assert [l for l in real.split("\n") if l.startswith("G")] == [l for l in other.split("\n") if l.startswith("G")]
+            assert sorted(l for l in real.split("\n") if l.startswith("P")) == sorted(l for l in other.split("\n") if l.startswith("P"))
