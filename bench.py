@@ -235,10 +235,14 @@ class Resident:
         self.d_tokens = torch.empty(self.hits_cap * TOK, dtype=torch.uint8, device=dev)
         self.h_hits = [torch.empty(self.hits_cap * 4, dtype=torch.int32, pin_memory=True) for _ in range(2)]
         self.h_pool = [torch.empty(self.pool_cap, dtype=torch.int32, pin_memory=True) for _ in range(2)]
-        if world == 1:
-            self.exchange = cbdist.TokenExchange(ctx, dev, shard_reads=n, stride=TOK, cap=cap)
-        else:
+        # every rank merges the gathered token blocks and clusters them on its own GPU (K5: the whole of
+        # createNonRedundantSet runs as kernels), so nothing is broadcast; CRASS_B200_EXCHANGE=root selects the
+        # round-1 form (the root clusters on its host, one broadcast returns the pattern set) for comparison
+        self.root_form = world > 1 and os.environ.get("CRASS_B200_EXCHANGE", "") == "root"
+        if self.root_form:
             self.exchange = cbdist.PatternExchange(ctx, dev, shard_reads=n, kmer_clust=params.kmer_clust, stride=TOK, cap=cap)
+        else:
+            self.exchange = cbdist.TokenExchange(ctx, dev, shard_reads=n, stride=TOK, cap=cap)
         self.kt = {"k1": [], "k2": []}
         self.host_ms = {k: [] for k in self.HOST_KEYS}
         self.stats = {}
@@ -273,7 +277,7 @@ class Resident:
         t1 = time.perf_counter()
         self.fetch_async(0, nh, npool)                                 # the phase-1 hit records travel while the host clusters
         pat_text = None
-        if self.world == 1:
+        if not self.root_form:
             ac, nu = self.exchange.run_matcher(self.d_hits, nh, self.d_tokens, self.params.kmer_clust, self.stream)
             t3 = t4 = time.perf_counter()
         else:
@@ -308,6 +312,8 @@ class Resident:
         if keep:
             h1, p1 = self.host_hits(0, nh, npool)
             h2, p2 = self.host_hits(1, n2, npool2)
+            if pat_text is None and ac is not None:
+                pat_text = ac.pattern_text()
             self.last = (h1.copy(), p1.copy(), h2.copy(), p2.copy(), pat_text)
 
     def summary(self, n_bases, peak):

@@ -89,6 +89,7 @@ def lib():
         "crass_b200_ac_num_states": (C.c_uint32, [vp]),
         "crass_b200_ac_num_symbols": (C.c_uint32, [vp]),
         "crass_b200_ac_table_bytes": (C.c_uint64, [vp]),
+        "crass_b200_ac_pattern_text": (vp, [vp, C.POINTER(C.c_uint32)]),
         "crass_b200_ac_scan_dev": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp]),
         "crass_b200_ac_scan": (C.c_int, [vp, vp, vp, vp, C.c_uint32, vp, vp, C.POINTER(vp), u32p, C.POINTER(vp), u32p]),
         "crass_b200_edit_distance_batch": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, vp, C.c_uint32, vp, vp]),
@@ -323,6 +324,11 @@ class Automaton:
     @property
     def table_bytes(self):
         return lib().crass_b200_ac_table_bytes(self.h)
+
+    def pattern_text(self):
+        """The patterns the matcher was built from, '\\n'-separated in build order."""
+        n = C.c_uint32(0)
+        return _take_str(lib().crass_b200_ac_pattern_text(self.h, C.byref(n)))
 
 
 class Results:

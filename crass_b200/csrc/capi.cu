@@ -123,6 +123,14 @@ struct crass_b200_ctx {
     DevBuf d_cl_group, d_cl_chain, d_cl_next, d_cl_odd, d_cl_dead, d_cl_str;
     PinnedBuf h_cl_block, h_cl_order, h_cl_keys, h_cl_first, h_cl_info, h_cl_group, h_cl_dead, h_cl_str;
     PinnedBuf h_ac_stage;                // matcher tables on their way to the device
+    DevBuf d_ac_ones;                    // {some pattern holds the all-ones 16-mer, head of the chain of patterns that begin with it}
+    DevBuf d_cl_tail;                    // every array of cluster.cuh's ClusterTail, carved from one allocation
+    PinnedBuf h_cl_pat;                  // the pattern set on its way back from the device
+    cudaEvent_t ev_ac_ready = nullptr;   // recorded on `stream` behind the build of the matcher tables; scans on other streams wait for it
+    cudaEvent_t ev_scan = nullptr;       // recorded behind the last scan; a new matcher's tables wait for it before they overwrite the old ones
+    bool scan_recorded = false;
+    uint32_t cl_last_patterns = 0, cl_last_bytes = 0;   // sizes of the last device-built pattern set (how much the next call copies back unasked)
+    bool stage_busy = false;             // h_ac_stage is the source of copies that may not have run yet (ev_ac_ready tells)
     // the 2-bit stream of the batch, written by k_dr_filter and read by k_ac_filter_packed (crass_b200_ctx_keep_packed)
     DevBuf d_packed;
     uint64_t keep_packed_bases = 0;      // caller opt-in for the *_dev calls: capacity in bases, 0 = off
@@ -192,6 +200,8 @@ int crass_b200_ctx_create(int device, crass_b200_ctx** out) {
     CUDA_TRY(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_ac_ready, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_scan, cudaEventDisableTiming));
     for (cudaEvent_t& e : c->ev_chunk) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CUDA_TRY(cudaHostAlloc((void**)&c->h_counters, 8 * sizeof(uint32_t), cudaHostAllocDefault));
     *out = c;
@@ -207,14 +217,16 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
                       &c->d_ac_bitmap, &c->d_ac_keys, &c->d_ac_skeys, &c->d_ac_shead, &c->d_ac_pnext, &c->d_ac_poffs, &c->d_ac_pbytes,
                       &c->d_rank, &c->d_hits_sorted, &c->d_cand_counts, &c->d_cand_mask, &c->d_ac_bitmap_small, &c->d_packed,
                       &c->d_cl_order, &c->d_cl_koff, &c->d_cl_keys, &c->d_cl_first, &c->d_cl_tab, &c->d_cl_info,
-                      &c->d_cl_group, &c->d_cl_chain, &c->d_cl_next, &c->d_cl_odd, &c->d_cl_dead, &c->d_cl_str};
+                      &c->d_cl_group, &c->d_cl_chain, &c->d_cl_next, &c->d_cl_odd, &c->d_cl_dead, &c->d_cl_str, &c->d_ac_ones, &c->d_cl_tail};
     for (DevBuf* b : bufs) b->release();
     for (PinnedBuf* b : {&c->h_cl_block, &c->h_cl_order, &c->h_cl_keys, &c->h_cl_first, &c->h_cl_info, &c->h_ac_stage,
-                         &c->h_cl_group, &c->h_cl_dead, &c->h_cl_str}) b->release();
+                         &c->h_cl_group, &c->h_cl_dead, &c->h_cl_str, &c->h_cl_pat}) b->release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_ac_ready) cudaEventDestroy(c->ev_ac_ready);
+    if (c->ev_scan) cudaEventDestroy(c->ev_scan);
     for (cudaEvent_t e : c->ev_chunk) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -359,9 +371,10 @@ int crass_b200_merge_token_blocks_dev(crass_b200_ctx* c, const void* d_blocks, u
 // ---- K5 + host passes: the step between the phases from a token block on the device --------------------------------
 }  // extern "C"
 namespace {
+int ensure_ac_on_device(crass_b200_ctx* c, crass_b200_ac* ac);
 const uint32_t kClusterDeviceMax = 32768;            // the rank kernel is O(n^2); longer lists take the host passes
 
-int cluster_block(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t stride, uint32_t kmer_clust,
+int cluster_block_host_passes(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t stride, uint32_t kmer_clust,
                   std::vector<std::string>* patterns, uint32_t* count, uint32_t* flags, cudaStream_t st) {
     patterns->clear();
     // CRASS_B200_TRACE=1: stage times of this call on stderr
@@ -392,7 +405,7 @@ int cluster_block(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t
     cbk::ClusterArrays a{(const uint8_t*)d_block, cap, stride, c->d_cl_order.as<uint32_t>(), c->d_cl_koff.as<uint32_t>(),
                          c->d_cl_keys.as<uint32_t>(), c->d_cl_first.as<uint32_t>(), c->d_cl_tab.as<uint32_t>(),
                          c->d_cl_tab.as<uint32_t>() + tab, (uint32_t)(tab - 1), c->d_cl_info.as<uint32_t>(),
-                         c->d_cl_str.as<uint32_t>(), kStrListCap};
+                         c->d_cl_str.as<uint32_t>(), kStrListCap, kClusterDeviceMax};
     CUDA_TRY(cudaMemsetAsync(c->d_cl_info.p, 0, 16, st));
     CUDA_TRY(cudaMemsetAsync(c->d_cl_tab.p, 0xFF, tab * 8, st));
     cbk::k_cl_rank<<<(cap + cbk::kClRankThreads) / cbk::kClRankThreads, cbk::kClRankThreads, 0, st>>>(a);
@@ -485,6 +498,133 @@ int cluster_block(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t
     mark("host passes");
     return reduce_rc;
 }
+
+// The whole step on the device (K5 + cluster.cuh): one host synchronisation, after which the host holds the pattern set
+// (bytes + offsets) and its sizes.  *handled = false: the kernels declined (see the flags in cluster.cuh) or the list is
+// longer than the O(n^2) rank kernel should see; the caller takes the host passes.
+struct PatternSet {
+    std::vector<uint8_t> bytes;
+    std::vector<uint32_t> offs;                       // n + 1
+    uint32_t n() const { return offs.empty() ? 0u : (uint32_t)offs.size() - 1; }
+    void from_strings(const std::vector<std::string>& v) {
+        bytes.clear(); offs.assign(1, 0);
+        for (const std::string& p : v) { bytes.insert(bytes.end(), p.begin(), p.end()); offs.push_back((uint32_t)bytes.size()); }
+    }
+};
+
+int cluster_block_device(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t stride, uint32_t kmer_clust,
+                         PatternSet* ps, uint32_t* count, uint32_t* flags, bool* handled, cudaStream_t st) {
+    *handled = false;
+    static const bool trace = getenv("CRASS_B200_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    const size_t max_kmers = (size_t)cap * (stride - 16);
+    size_t tab = 1024;
+    while (tab < 2 * max_kmers) tab <<= 1;
+    const uint32_t kStrListCap = 4096;                 // string-keyed 11-mers resolved pairwise on the device
+    if (int r = c->d_cl_order.reserve((size_t)cap * 4)) return r;
+    if (int r = c->d_cl_koff.reserve(((size_t)cap + 1025) * 4)) return r;
+    if (int r = c->d_cl_keys.reserve(max_kmers * 4 + 16)) return r;
+    if (int r = c->d_cl_first.reserve(max_kmers * 4 + 16)) return r;
+    if (int r = c->d_cl_tab.reserve(tab * 8)) return r;
+    if (int r = c->d_cl_info.reserve(cbk::kInfoWords * 4)) return r;
+    if (int r = c->d_cl_str.reserve((size_t)16384 * 8)) return r;
+    if (int r = c->h_cl_block.reserve(cbk::kTokenBlockHeader + (size_t)cap * stride)) return r;
+    if (int r = c->h_cl_info.reserve(cbk::kInfoWords * 4)) return r;
+    // the tail's arrays, carved from one allocation
+    size_t at = 0;
+    auto carve = [&](size_t bytes) { const size_t o = at; at += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_lens = carve((size_t)cap * 4), o_runc = carve(max_kmers * 4 + 16), o_nruns = carve((size_t)cap * 4),
+                 o_group = carve((size_t)cap * 4), o_gnum = carve(((size_t)cap + 2) * 4), o_gstart = carve(((size_t)cap + 2) * 4),
+                 o_gfill = carve((size_t)cap * 4), o_members = carve((size_t)cap * 4), o_sorted = carve((size_t)cap * 4),
+                 o_alive = carve(((size_t)cap + 2) * 4), o_plen = carve((2 * (size_t)cap + 2) * 4), o_psrc = carve(2 * (size_t)cap * 4),
+                 o_pbytes = carve(2 * (size_t)cap * (stride - 6) + 32), o_canon = carve((size_t)kStrListCap * 12);
+    if (int r = c->d_cl_tail.reserve(at)) return r;
+    uint8_t* tb = c->d_cl_tail.as<uint8_t>();
+    cbk::ClusterArrays a{(const uint8_t*)d_block, cap, stride, c->d_cl_order.as<uint32_t>(), c->d_cl_koff.as<uint32_t>(),
+                         c->d_cl_keys.as<uint32_t>(), c->d_cl_first.as<uint32_t>(), c->d_cl_tab.as<uint32_t>(),
+                         c->d_cl_tab.as<uint32_t>() + tab, (uint32_t)(tab - 1), c->d_cl_info.as<uint32_t>(),
+                         c->d_cl_str.as<uint32_t>(), kStrListCap, kClusterDeviceMax};
+    cbk::ClusterTail t{a, (uint32_t*)(tb + o_lens), (uint32_t*)(tb + o_runc), (uint32_t*)(tb + o_nruns), (uint32_t*)(tb + o_group),
+                       (uint32_t*)(tb + o_gnum), (uint32_t*)(tb + o_gstart), (uint32_t*)(tb + o_gfill), (uint32_t*)(tb + o_members),
+                       (uint32_t*)(tb + o_sorted), (uint32_t*)(tb + o_alive), (uint32_t*)(tb + o_plen), (uint32_t*)(tb + o_psrc),
+                       tb + o_pbytes, tb + o_canon, kmer_clust};
+    CUDA_TRY(cudaMemsetAsync(c->d_cl_info.p, 0, cbk::kInfoWords * 4, st));
+    CUDA_TRY(cudaMemsetAsync(c->d_cl_tab.p, 0xFF, tab * 8, st));
+    CUDA_TRY(cudaMemsetAsync(t.plen, 0, (2 * (size_t)cap + 2) * 4, st));
+    const uint32_t per_dr128 = (cap + 127) / 128, per_dr256 = (cap + 1 + 255) / 256, warp_per_dr = (cap + 1 + 3) / 4;
+    cbk::k_cl_rank<<<(cap + cbk::kClRankThreads) / cbk::kClRankThreads, cbk::kClRankThreads, 0, st>>>(a);
+    cbk::k_rank_scan<<<1, 1024, 0, st>>>(a.koff, cap + 1, a.info);                  // info[0] = n, written by k_cl_rank
+    cbk::k_cl_keys<<<(cap * 32 + cbk::kClKeysThreads - 1) / cbk::kClKeysThreads, cbk::kClKeysThreads, 0, st>>>(a);
+    cbk::k_cl_first<<<c->sm_count * 4, 256, 0, st>>>(a);
+    cbk::k_cl_str_canon<<<kStrListCap / 128, 128, 0, st>>>(t);
+    cbk::k_cl_str_first<<<kStrListCap / 128, 128, 0, st>>>(t);
+    cbk::k_cl_runs<<<per_dr128, 128, 0, st>>>(t);
+    cbk::k_cl_walk<<<per_dr128, 128, 0, st>>>(t);
+    cbk::k_cl_founders<<<per_dr256, 256, 0, st>>>(t);
+    cbk::k_rank_scan<<<1, 1024, 0, st>>>(t.gnum, cap + 1, a.info);
+    cbk::k_cl_hist<<<per_dr256, 256, 0, st>>>(t);
+    cbk::k_rank_scan<<<1, 1024, 0, st>>>(t.gstart, cap + 1, a.info);
+    cbk::k_cl_members<<<per_dr256, 256, 0, st>>>(t);
+    cbk::k_cl_group_sort<<<warp_per_dr, 128, 0, st>>>(t);
+    cbk::k_cl_dead<<<warp_per_dr, 128, 4 * stride, st>>>(t);
+    cbk::k_rank_scan<<<1, 1024, 0, st>>>(t.alive, cap + 1, a.info);
+    cbk::k_cl_place<<<per_dr256, 256, 0, st>>>(t);
+    cbk::k_rank_scan<<<1, 1024, 0, st>>>(t.plen, 2 * cap + 1, a.info + cbk::kInfoPatterns);
+    cbk::k_cl_emit<<<(2 * cap + 127) / 128, 128, 0, st>>>(t);
+    c->launches += 19;
+    CUDA_TRY(cudaGetLastError());
+    // one round trip: header, info record, and as much of the pattern set as the last call needed (twice that, in fact)
+    const size_t all_offs = 2 * (size_t)cap + 1, all_bytes = 2 * (size_t)cap * (stride - 6) + 16;
+    const size_t spec_offs = std::min<size_t>(all_offs, std::max<size_t>(1024, 2 * (size_t)c->cl_last_patterns) + 1);
+    const size_t spec_bytes = std::min<size_t>(all_bytes, std::max<size_t>(32768, 2 * (size_t)c->cl_last_bytes));
+    const size_t h_offs_at = 0, h_bytes_at = (all_offs * 4 + 255) & ~(size_t)255;
+    if (int r = c->h_cl_pat.reserve(h_bytes_at + all_bytes)) return r;
+    CUDA_TRY(cudaMemcpyAsync(c->h_cl_block.p, d_block, cbk::kTokenBlockHeader, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(c->h_cl_info.p, a.info, cbk::kInfoWords * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(c->h_cl_pat.as<uint8_t>() + h_offs_at, t.plen, spec_offs * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(c->h_cl_pat.as<uint8_t>() + h_bytes_at, t.pbytes, spec_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    uint32_t hdr[2];
+    memcpy(hdr, c->h_cl_block.p, sizeof hdr);
+    if (count) *count = hdr[0];
+    if (flags) *flags = hdr[1];
+    if (hdr[1] || hdr[0] > cap || hdr[0] == 0) { *handled = true; ps->bytes.clear(); ps->offs.clear(); return 0; }   // overflowed / empty: the caller looks at count and flags
+    const uint32_t* info = c->h_cl_info.as<uint32_t>();
+    if (trace) fprintf(stderr, "cluster_block: on the device: %u DRs, %u groups, %u patterns (%u bytes), %u string-keyed k-mers, flags %u, %.3f ms\n",
+                       info[cbk::kInfoN], info[cbk::kInfoGroups], info[cbk::kInfoPatterns], info[cbk::kInfoBytes], info[cbk::kInfoStr],
+                       info[cbk::kInfoFlags], std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    if (info[cbk::kInfoN] != hdr[0] || info[cbk::kInfoFlags]) return 0;            // declined
+    const uint32_t np = info[cbk::kInfoPatterns], nbytes = info[cbk::kInfoBytes];
+    if ((size_t)np + 1 > spec_offs || nbytes > spec_bytes) {                       // more than guessed: fetch the rest
+        if ((size_t)np + 1 > spec_offs)
+            CUDA_TRY(cudaMemcpyAsync(c->h_cl_pat.as<uint8_t>() + h_offs_at + spec_offs * 4, t.plen + spec_offs, ((size_t)np + 1 - spec_offs) * 4, cudaMemcpyDeviceToHost, st));
+        if (nbytes > spec_bytes)
+            CUDA_TRY(cudaMemcpyAsync(c->h_cl_pat.as<uint8_t>() + h_bytes_at + spec_bytes, t.pbytes + spec_bytes, nbytes - spec_bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    c->cl_last_patterns = np; c->cl_last_bytes = nbytes;
+    const uint32_t* ho = (const uint32_t*)(c->h_cl_pat.as<uint8_t>() + h_offs_at);
+    ps->offs.assign(ho, ho + np + 1);
+    ps->bytes.assign(c->h_cl_pat.as<uint8_t>() + h_bytes_at, c->h_cl_pat.as<uint8_t>() + h_bytes_at + nbytes);
+    *handled = true;
+    return 0;
+}
+
+int cluster_block(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t stride, uint32_t kmer_clust,
+                  PatternSet* ps, uint32_t* count, uint32_t* flags, cudaStream_t st) {
+    // CRASS_B200_CLUSTER: (unset) everything on the device; "device-passes" = K5's first passes on the device, the rest on the
+    // host (the round-1 default); "device-reduce" = that plus pass D on the device
+    const char* sel = getenv("CRASS_B200_CLUSTER");
+    if (!sel || (strcmp(sel, "device-passes") && strcmp(sel, "device-reduce"))) {
+        bool handled = false;
+        if (int r = cluster_block_device(c, d_block, cap, stride, kmer_clust, ps, count, flags, &handled, st)) return r;
+        if (handled) return 0;
+    }
+    std::vector<std::string> nr;
+    if (int r = cluster_block_host_passes(c, d_block, cap, stride, kmer_clust, &nr, count, flags, st)) return r;
+    ps->from_strings(nr);
+    return 0;
+}
 }  // namespace
 extern "C" {
 
@@ -495,29 +635,27 @@ int crass_b200_cluster_block_dev(crass_b200_ctx* c, const void* d_block, uint32_
     *out = nullptr;
     if (n_patterns) *n_patterns = 0;
     CUDA_TRY(cudaSetDevice(c->device));
-    std::vector<std::string> nr;
-    if (int r = cluster_block(c, d_block, cap, stride, kmer_clust, &nr, count, flags, (cudaStream_t)stream_v)) return r;
-    if (n_patterns) *n_patterns = (uint32_t)nr.size();
-    if (nr.empty()) return 0;
-    std::vector<uint8_t> bytes;
-    std::vector<uint32_t> offs(1, 0);
-    for (const std::string& p : nr) { bytes.insert(bytes.end(), p.begin(), p.end()); offs.push_back((uint32_t)bytes.size()); }
-    return crass_b200_ac_build(bytes.data(), offs.data(), (uint32_t)nr.size(), out);
+    PatternSet ps;
+    if (int r = cluster_block(c, d_block, cap, stride, kmer_clust, &ps, count, flags, (cudaStream_t)stream_v)) return r;
+    if (n_patterns) *n_patterns = ps.n();
+    if (ps.n() == 0) return 0;
+    if (int r = crass_b200_ac_build(ps.bytes.data(), ps.offs.data(), ps.n(), out)) return r;
+    // the tables are built on this context's device straight away (k_ac_build): the scan that follows finds them ready
+    if (int r = ensure_ac_on_device(c, *out)) { crass_b200_ac_destroy(*out); *out = nullptr; return r; }
+    return 0;
 }
 
 char* crass_b200_cluster_block_patterns_dev(crass_b200_ctx* c, const void* d_block, uint32_t cap, uint32_t stride, uint32_t kmer_clust,
                                             uint32_t* count, uint32_t* flags, uint32_t* n_patterns, void* stream_v) {
     if (!c || !d_block || stride < 28 || (stride & 3) || cap == 0) { cbh::fail(CRASS_B200_EINVAL, "bad argument"); return nullptr; }
     if (cudaSetDevice(c->device) != cudaSuccess) { cbh::fail(CRASS_B200_ECUDA, "cudaSetDevice failed"); return nullptr; }
-    std::vector<std::string> nr;
-    if (cluster_block(c, d_block, cap, stride, kmer_clust, &nr, count, flags, (cudaStream_t)stream_v)) return nullptr;
-    if (n_patterns) *n_patterns = (uint32_t)nr.size();
-    size_t total = 1;
-    for (const std::string& p : nr) total += p.size() + 1;
-    char* text = (char*)malloc(total);
+    PatternSet ps;
+    if (cluster_block(c, d_block, cap, stride, kmer_clust, &ps, count, flags, (cudaStream_t)stream_v)) return nullptr;
+    if (n_patterns) *n_patterns = ps.n();
+    char* text = (char*)malloc(ps.bytes.size() + ps.n() + 1);
     if (!text) { cbh::fail(CRASS_B200_ENOMEM, "malloc"); return nullptr; }
     char* w = text;
-    for (const std::string& p : nr) { memcpy(w, p.data(), p.size()); w += p.size(); *w++ = '\n'; }
+    for (uint32_t i = 0; i < ps.n(); ++i) { memcpy(w, ps.bytes.data() + ps.offs[i], ps.offs[i + 1] - ps.offs[i]); w += ps.offs[i + 1] - ps.offs[i]; *w++ = '\n'; }
     *w = 0;
     return text;
 }
@@ -867,7 +1005,27 @@ uint32_t crass_b200_ac_num_states(const crass_b200_ac* ac) {
     cbh::ensure_dfa(&const_cast<crass_b200_ac*>(ac)->a);
     return ac->a.n_states;
 }
-uint32_t crass_b200_ac_num_symbols(const crass_b200_ac* ac) { return ac ? ac->a.n_syms : 0; }
+uint32_t crass_b200_ac_num_symbols(const crass_b200_ac* ac) {
+    if (!ac) return 0;
+    cbh::ensure_symbols(&const_cast<crass_b200_ac*>(ac)->a);
+    return ac->a.n_syms;
+}
+char* crass_b200_ac_pattern_text(const crass_b200_ac* ac, uint32_t* n_patterns) {
+    if (!ac) { cbh::fail(CRASS_B200_EINVAL, "NULL argument"); return nullptr; }
+    const cbh::Automaton& a = ac->a;
+    if (n_patterns) *n_patterns = a.n_patterns;
+    char* text = (char*)malloc((size_t)a.p_offs[a.n_patterns] + a.n_patterns + 1);
+    if (!text) { cbh::fail(CRASS_B200_ENOMEM, "malloc"); return nullptr; }
+    char* w = text;
+    for (uint32_t i = 0; i < a.n_patterns; ++i) {
+        const uint32_t len = a.p_offs[i + 1] - a.p_offs[i];
+        memcpy(w, a.p_bytes.data() + a.p_offs[i], len);
+        w += len;
+        *w++ = '\n';
+    }
+    *w = 0;
+    return text;
+}
 uint64_t crass_b200_ac_table_bytes(const crass_b200_ac* ac) {
     if (!ac) return 0;
     cbh::ensure_dfa(&const_cast<crass_b200_ac*>(ac)->a);
@@ -879,38 +1037,74 @@ uint64_t crass_b200_ac_table_bytes(const crass_b200_ac* ac) {
 namespace {
 int ensure_ac_on_device(crass_b200_ctx* c, crass_b200_ac* ac) {
     // The device copy lives in context-owned, grow-only buffers (no cudaMalloc/cudaFree per pattern set); it is
-    // refreshed whenever a different automaton (by build serial) is used with this context.
+    // refreshed whenever a different automaton (by build serial) is used with this context.  Only the pattern bytes and
+    // offsets travel: bitmap, key table and start table are built on the device (k_ac_build), unless the matcher carries
+    // host-built tables (CRASS_B200_AC_BUILD=host).  Nothing here waits on the host: the work is ordered on c->stream
+    // behind the last scan (ev_scan) and scans order themselves behind it (ev_ac_ready).
     cbh::Automaton& a = ac->a;
     if (c->ac_serial == a.serial && a.serial != 0) return 0;
     c->ac_dfa_serial = 0;
-    // the tables are context-owned and about to be overwritten: a scan of the previous matcher may still be running on
-    // a stream of the caller's that c->stream knows nothing about
-    CUDA_TRY(cudaDeviceSynchronize());
+    c->ac_serial = 0;
+    if (c->scan_recorded) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_scan, 0));
     if (a.q_bits) {                                   // filter + pattern-start table (fast path)
+        const size_t bm_words = (size_t)1 << (a.q_bits - 5), bms_words = a.q_bits_small ? (size_t)1 << (a.q_bits_small - 5) : 0;
+        const size_t t_words = (size_t)1 << a.q_table_bits, s_words = (size_t)1 << a.s_bits;
+        if (int r = c->d_ac_bitmap.reserve(bm_words * 4)) return r;
+        if (int r = c->d_ac_bitmap_small.reserve(bms_words * 4 + 16)) return r;
+        if (int r = c->d_ac_keys.reserve(t_words * 4)) return r;
+        if (int r = c->d_ac_skeys.reserve(s_words * 4)) return r;
+        if (int r = c->d_ac_shead.reserve(s_words * 4)) return r;
+        if (int r = c->d_ac_pnext.reserve((size_t)a.n_patterns * 4 + 16)) return r;
+        if (int r = c->d_ac_ones.reserve(16)) return r;
+        const uint32_t ones_host[2] = {a.q_has_ones, a.s_ones_head};
         struct Up { DevBuf* d; const void* h; size_t bytes; } ups[] = {
+            {&c->d_ac_poffs, a.p_offs.data(), a.p_offs.size() * sizeof(uint32_t)},
+            {&c->d_ac_pbytes, a.p_bytes.data(), a.p_bytes.size()},
             {&c->d_ac_bitmap, a.q_bitmap.data(), a.q_bitmap.size() * sizeof(uint32_t)},
             {&c->d_ac_bitmap_small, a.q_bitmap_small.data(), a.q_bitmap_small.size() * sizeof(uint32_t)},
             {&c->d_ac_keys, a.q_keys.data(), a.q_keys.size() * sizeof(uint32_t)},
             {&c->d_ac_skeys, a.s_keys.data(), a.s_keys.size() * sizeof(uint32_t)},
             {&c->d_ac_shead, a.s_head.data(), a.s_head.size() * sizeof(uint32_t)},
             {&c->d_ac_pnext, a.p_next.data(), a.p_next.size() * sizeof(uint32_t)},
-            {&c->d_ac_poffs, a.p_offs.data(), a.p_offs.size() * sizeof(uint32_t)},
-            {&c->d_ac_pbytes, a.p_bytes.data(), a.p_bytes.size()},
+            {&c->d_ac_ones, ones_host, sizeof ones_host},
         };
-        // staged through one page-locked buffer: copies from pageable vectors are synchronous and slow for small tables
+        const size_t n_up = a.tables_on_host ? sizeof ups / sizeof ups[0] : 2;
+        // staged through one page-locked buffer: copies from pageable vectors are synchronous and slow for small tables.
+        // The buffer may still be feeding the previous matcher's copies, hence the event before it is written again.
         size_t total = 0;
-        for (const Up& u : ups) total += (u.bytes + 63) & ~(size_t)63;
+        for (size_t i = 0; i < n_up; ++i) total += (ups[i].bytes + 63) & ~(size_t)63;
+        total += 64;                                  // the initial value of d_ac_ones
+        if (c->stage_busy) { CUDA_TRY(cudaEventSynchronize(c->ev_ac_ready)); c->stage_busy = false; }
         if (int r = c->h_ac_stage.reserve(total)) return r;
         size_t at = 0;
-        for (const Up& u : ups) {
+        for (size_t i = 0; i < n_up; ++i) {
+            const Up& u = ups[i];
             if (!u.bytes) continue;
             if (int r = u.d->reserve(u.bytes + 16)) return r;
             memcpy(c->h_ac_stage.as<uint8_t>() + at, u.h, u.bytes);
             CUDA_TRY(cudaMemcpyAsync(u.d->p, c->h_ac_stage.as<uint8_t>() + at, u.bytes, cudaMemcpyHostToDevice, c->stream));
             at += (u.bytes + 63) & ~(size_t)63;
         }
+        if (!a.tables_on_host) {
+            CUDA_TRY(cudaMemsetAsync(c->d_ac_bitmap.p, 0, bm_words * 4, c->stream));
+            if (bms_words) CUDA_TRY(cudaMemsetAsync(c->d_ac_bitmap_small.p, 0, bms_words * 4, c->stream));
+            CUDA_TRY(cudaMemsetAsync(c->d_ac_keys.p, 0xFF, t_words * 4, c->stream));
+            CUDA_TRY(cudaMemsetAsync(c->d_ac_skeys.p, 0xFF, s_words * 4, c->stream));
+            CUDA_TRY(cudaMemsetAsync(c->d_ac_shead.p, 0xFF, s_words * 4, c->stream));
+            const uint32_t ones_init[2] = {0u, 0xFFFFFFFFu};
+            memcpy(c->h_ac_stage.as<uint8_t>() + at, ones_init, sizeof ones_init);      // 
+            CUDA_TRY(cudaMemcpyAsync(c->d_ac_ones.p, c->h_ac_stage.as<uint8_t>() + at, sizeof ones_init, cudaMemcpyHostToDevice, c->stream));
+            cbk::MatcherTables m{c->d_ac_pbytes.as<uint8_t>(), c->d_ac_poffs.as<uint32_t>(), a.n_patterns,
+                                 c->d_ac_bitmap.as<uint32_t>(), a.q_bits, c->d_ac_bitmap_small.as<uint32_t>(), a.q_bits_small,
+                                 c->d_ac_keys.as<uint32_t>(), a.q_table_bits, c->d_ac_skeys.as<uint32_t>(), c->d_ac_shead.as<uint32_t>(),
+                                 a.s_bits, c->d_ac_pnext.as<uint32_t>(), c->d_ac_ones.as<uint32_t>()};
+            cbk::k_ac_build<<<(a.n_patterns * 8 + 255) / 256, 256, 0, c->stream>>>(m);
+            c->launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+        c->stage_busy = true;
     }
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev_ac_ready, c->stream));
     c->ac_serial = a.serial;
     return 0;
 }
@@ -919,6 +1113,7 @@ int ensure_dfa_on_device(crass_b200_ctx* c, crass_b200_ac* ac) {      // generic
     cbh::Automaton& a = ac->a;
     if (c->ac_dfa_serial == a.serial && a.serial != 0) return 0;
     cbh::ensure_dfa(&a);
+    if (c->scan_recorded) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_scan, 0));
     if (int r = c->d_ac_table.reserve(a.table.size() * sizeof(uint32_t))) return r;
     if (int r = c->d_ac_symv.reserve(256)) return r;
     CUDA_TRY(cudaMemcpyAsync(c->d_ac_table.p, a.table.data(), a.table.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
@@ -941,11 +1136,12 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
     CUDA_TRY(cudaSetDevice(c->device));
     if (int r = ensure_ac_on_device(c, ac)) return r;
     cudaStream_t st = (cudaStream_t)stream_v;
+    if (st != c->stream) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_ac_ready, 0));            // the tables are built on c->stream
     CUDA_TRY(cudaMemsetAsync(d_counters, 0, 4 * sizeof(uint32_t), st));
     if (n_reads == 0) return 0;
     cbk::HitSink sink{d_hits, hits_cap, d_ss_pool, ss_cap, d_counters, nullptr, 0};
-    uint32_t stride_log2 = 0;
-    while ((1u << stride_log2) < ac->a.stride) ++stride_log2;
+    // a later matcher's tables must not overwrite these before the scan is through
+    auto scan_enqueued = [&]() -> int { CUDA_TRY(cudaEventRecord(c->ev_scan, st)); c->scan_recorded = true; return 0; };
     // Fast path: 16-mer q-gram filter over every read + automaton walk over the few candidates.
     const char* force = getenv("CRASS_B200_K2");
     if (ac->a.q_bits && max_read_len <= 304 && (((uintptr_t)d_bases) & 15) == 0 && !(force && !strcmp(force, "generic"))) {
@@ -954,7 +1150,7 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         if (int r = c->d_cand_mask.reserve(((size_t)n_reads + 16) * sizeof(uint64_t))) return r;
         uint32_t* cand = c->d_cand.as<uint32_t>();
         uint64_t* cmask = c->d_cand_mask.as<uint64_t>();
-        cbk::QgramFilter q{c->d_ac_bitmap.as<uint32_t>(), c->d_ac_keys.as<uint32_t>(), ac->a.q_bits, ac->a.q_table_bits, ac->a.q_has_ones};
+        cbk::QgramFilter q{c->d_ac_bitmap.as<uint32_t>(), c->d_ac_keys.as<uint32_t>(), ac->a.q_bits, ac->a.q_table_bits, c->d_ac_ones.as<uint32_t>()};
         const uint32_t n_tiles = (n_reads + cbk::kAcTile - 1) / cbk::kAcTile;
         const size_t bm_bytes = ((size_t)1 << ac->a.q_bits) / 8;
 #define CB_ACF(NW)                                                                                                              \
@@ -997,7 +1193,7 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
 #undef CB_ACP
         CUDA_TRY(cudaGetLastError());
         cbk::PatternStarts ps{c->d_ac_pbytes.as<uint8_t>(), c->d_ac_poffs.as<uint32_t>(), c->d_ac_skeys.as<uint32_t>(),
-                              c->d_ac_shead.as<uint32_t>(), c->d_ac_pnext.as<uint32_t>(), ac->a.s_bits, ac->a.s_ones_head,
+                              c->d_ac_shead.as<uint32_t>(), c->d_ac_pnext.as<uint32_t>(), ac->a.s_bits, c->d_ac_ones.as<uint32_t>(),
                               ac->a.min_pattern_len};
         // one warp per candidate: a single thread walking a read's dependent table probes is latency-bound even at 150 bp
         // (CRASS_B200_K2V=list selects the thread-per-candidate form for comparison)
@@ -1018,14 +1214,14 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         }
         c->launches += 2;
         CUDA_TRY(cudaGetLastError());
-        return 0;
+        return scan_enqueued();
     }
     if (ac->a.q_bits && max_read_len > 304 && (((uintptr_t)d_bases) & 15) == 0 && !(force && !strcmp(force, "generic"))) {
         // long reads: warp-per-read q-gram filter, then the same verify kernel over the candidates
         if (!d_found) { if (int r = c->d_found.reserve((size_t)n_reads + 16)) return r; d_found = c->d_found.as<uint8_t>(); }
         if (int r = c->d_cand.reserve(((size_t)n_reads + 16) * sizeof(uint32_t))) return r;
         uint32_t* cand = c->d_cand.as<uint32_t>();
-        cbk::QgramFilter q{c->d_ac_bitmap.as<uint32_t>(), c->d_ac_keys.as<uint32_t>(), ac->a.q_bits, ac->a.q_table_bits, ac->a.q_has_ones};
+        cbk::QgramFilter q{c->d_ac_bitmap.as<uint32_t>(), c->d_ac_keys.as<uint32_t>(), ac->a.q_bits, ac->a.q_table_bits, c->d_ac_ones.as<uint32_t>()};
         const size_t smem = ((size_t)1 << ac->a.q_bits) / 8;
         const char* fsel = getenv("CRASS_B200_K2F");
         const bool use_packed = c->packed_valid && c->packed_src == (const void*)d_bases && c->packed_reads == n_reads &&
@@ -1040,21 +1236,23 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         else cbk::k_ac_filter_long<false><<<blocks, cbk::kAcLongThreads, smem, st>>>(d_bases, d_offsets, n_reads, q, d_skip, d_found, cand, d_counters);
         CUDA_TRY(cudaGetLastError());
         cbk::PatternStarts ps{c->d_ac_pbytes.as<uint8_t>(), c->d_ac_poffs.as<uint32_t>(), c->d_ac_skeys.as<uint32_t>(),
-                              c->d_ac_shead.as<uint32_t>(), c->d_ac_pnext.as<uint32_t>(), ac->a.s_bits, ac->a.s_ones_head,
+                              c->d_ac_shead.as<uint32_t>(), c->d_ac_pnext.as<uint32_t>(), ac->a.s_bits, c->d_ac_ones.as<uint32_t>(),
                               ac->a.min_pattern_len};
         cbk::k_ac_verify_warp<<<c->sm_count * 16, 128, 0, st>>>(d_bases, d_offsets, cand, ps, d_found, sink);      // 28 registers: 16 CTAs per SM
         c->launches += 2;
         CUDA_TRY(cudaGetLastError());
-        return 0;
+        return scan_enqueued();
     }
     if (int r = ensure_dfa_on_device(c, ac)) return r;
+    uint32_t stride_log2 = 0;
+    while ((1u << stride_log2) < ac->a.stride) ++stride_log2;
     const int threads = 256;
     int blocks = (int)std::min<uint64_t>(((uint64_t)n_reads + threads - 1) / threads, (uint64_t)c->sm_count * 32);
     cbk::k_ac_scan_generic<<<blocks, threads, 0, st>>>(d_bases, d_offsets, n_reads, c->d_ac_table.as<uint32_t>(), stride_log2,
                                                        c->d_ac_symv.as<uint8_t>(), d_skip, d_found, sink);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
-    return 0;
+    return scan_enqueued();
 }
 
 int crass_b200_ac_scan(crass_b200_ctx* c, const crass_b200_ac* ac, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,

@@ -37,28 +37,29 @@ Automaton::~Automaton() { free_device_tables(this); }
 
 uint32_t qgram_hash(uint32_t code, uint32_t bits) { return (code * 0x9E3779B1u) >> (32 - bits); }
 
-static void build_filter_and_starts(Automaton* A) {
+// The tables themselves are built on the device (k_ac_build in cluster.cuh, launched when a context first uses the
+// matcher): one thread per (pattern, window) sets the bitmap bits and claims the key-table / start-table slots with
+// atomics -- the same open-addressing scheme, so look-ups probe exactly as they would in a table filled sequentially.
+// What the host decides here are the sizes.  CRASS_B200_AC_BUILD=host fills the tables on the host as well (the round-1
+// path; tests compare the two).
+static void plan_filter_and_starts(Automaton* A) {
     A->q_bits = 0;
     A->q_bitmap.clear(); A->q_keys.clear(); A->s_keys.clear(); A->s_head.clear(); A->p_next.clear();
+    A->tables_on_host = false;
     if (A->min_pattern_len < 23) return;                             // no aligned 16-mer guaranteed: K2 walks the DFA instead
     const uint32_t n = A->n_patterns;
-    const uint8_t* bytes = A->p_bytes.data();
-    const uint32_t* offs = A->p_offs.data();
     // the key table is sized for the number of 16-mer POSITIONS (an upper bound of the distinct codes), so that the
     // codes can be inserted in one pass without sorting
     const size_t positions = (size_t)n * 8;                          // pattern offsets 0..7 (every pattern is >= 23 bytes)
     uint32_t tbits = 4;
     while (((size_t)1 << tbits) < positions * 2 + 2) ++tbits;
     A->q_table_bits = tbits;
-    A->q_keys.assign((size_t)1 << tbits, 0xFFFFFFFFu);               // 0xFFFFFFFF = empty; the all-G 16-mer is kept in q_has_ones
-    A->q_has_ones = 0;
     // keys up to which the 64 KB bitmap is used (128 KB above).  Measured on config 5 (tools/bench_ac_sweep.py): even at
     // 160 k keys (20 k patterns, 27 % of the bits set) two resident CTAs with 64 KB each beat one with 128 KB.
     uint32_t small_max = 1000000;
     if (const char* e = getenv("CRASS_B200_QGRAM_SMALL_MAX")) small_max = (uint32_t)strtoul(e, nullptr, 10);
     A->q_bits = positions <= small_max ? 19 : 20;
     if (const char* e = getenv("CRASS_B200_QGRAM_BITS")) { const int b = atoi(e); if (b >= 15 && b <= 20) A->q_bits = (uint32_t)b; }
-    A->q_bitmap.assign((size_t)1 << (A->q_bits - 5), 0);
     // A half-size copy for the 2-bit-stream filter (k_ac_filter_packed): its CTA is the bitmap + 40 KB of tiles, so 32 KB
     // instead of 64 KB lets three CTAs instead of two live on an SM, which is worth more than the bits while the set is
     // sparse (config 5, 50 M reads: 100 patterns 1.80 -> 1.63 ms, 1 000: 2.33 -> 2.15 ms, 3 000: level, 20 000: worse).
@@ -67,17 +68,27 @@ static void build_filter_and_starts(Automaton* A) {
     A->q_bitmap_small.clear();
     uint32_t fold_max = 16384;
     if (const char* e = getenv("CRASS_B200_QGRAM_FOLD_MAX")) fold_max = (uint32_t)strtoul(e, nullptr, 10);
-    if (A->q_bits == 19 && positions <= fold_max) {                  // filled next to the main bitmap below
-        A->q_bits_small = 18;
-        A->q_bitmap_small.assign((size_t)1 << (18 - 5), 0);
-    }
+    if (A->q_bits == 19 && positions <= fold_max) A->q_bits_small = 18;
     uint32_t sbits = 4;
     while (((size_t)1 << sbits) < (size_t)n * 2 + 2) ++sbits;
     A->s_bits = sbits;
+    A->s_ones_head = 0xFFFFFFFFu;
+    A->q_has_ones = 0;
+}
+
+static void fill_filter_and_starts_on_host(Automaton* A) {
+    const uint32_t n = A->n_patterns;
+    const uint8_t* bytes = A->p_bytes.data();
+    const uint32_t* offs = A->p_offs.data();
+    const uint32_t tbits = A->q_table_bits, sbits = A->s_bits;
+    A->q_keys.assign((size_t)1 << tbits, 0xFFFFFFFFu);               // 0xFFFFFFFF = empty; the all-G 16-mer is kept in q_has_ones
+    A->q_bitmap.assign((size_t)1 << (A->q_bits - 5), 0);
+    if (A->q_bits_small) A->q_bitmap_small.assign((size_t)1 << (A->q_bits_small - 5), 0);
     A->s_keys.assign((size_t)1 << sbits, 0xFFFFFFFFu);
     A->s_head.assign((size_t)1 << sbits, 0xFFFFFFFFu);
     A->p_next.assign(n, 0xFFFFFFFFu);
     A->s_ones_head = 0xFFFFFFFFu;
+    A->q_has_ones = 0;
     const uint32_t tmask = ((uint32_t)1 << tbits) - 1, smask = ((uint32_t)1 << sbits) - 1;
     uint32_t distinct = 0;
     for (uint32_t i = 0; i < n; ++i) {
@@ -109,33 +120,32 @@ static void build_filter_and_starts(Automaton* A) {
         }
     }
     A->q_count = distinct;
+    A->tables_on_host = true;
+}
+
+static void build_filter_and_starts(Automaton* A) {
+    plan_filter_and_starts(A);
+    const char* sel = getenv("CRASS_B200_AC_BUILD");
+    if (A->q_bits && sel && !strcmp(sel, "host")) fill_filter_and_starts_on_host(A);
 }
 
 int build_automaton(const uint8_t* bytes, const uint32_t* offs, uint32_t n, Automaton** out) {
     if (n == 0) return fail(CRASS_B200_EINVAL, "ac_build: empty pattern set (the reference guards this case in WorkHorse.cpp:373)");
-    Automaton* A = new Automaton();
-    memset(A->symv, 0, sizeof A->symv);
-    uint32_t ns = 1;
-    size_t total = 1;
-    A->min_pattern_len = 0xffffffffu;
+    uint32_t lo = 0xffffffffu, hi = 0;
     for (uint32_t i = 0; i < n; ++i) {
         const uint32_t len = offs[i + 1] - offs[i];
-        if (len == 0) { delete A; return fail(CRASS_B200_EINVAL, "ac_build: empty pattern"); }
-        if (len > 255) { delete A; return fail(CRASS_B200_EINVAL, "ac_build: pattern longer than 255 bytes"); }
-        if (len < A->min_pattern_len) A->min_pattern_len = len;
-        if (len > A->max_pattern_len) A->max_pattern_len = len;
-        total += len;
-        for (uint32_t k = offs[i]; k < offs[i + 1]; ++k)
-            if (!A->symv[bytes[k]]) A->symv[bytes[k]] = (uint8_t)(ns++);
+        if (len == 0) return fail(CRASS_B200_EINVAL, "ac_build: empty pattern");
+        if (len > 255) return fail(CRASS_B200_EINVAL, "ac_build: pattern longer than 255 bytes");
+        lo = std::min(lo, len); hi = std::max(hi, len);
     }
-    if (total >= (1u << 24)) { delete A; return fail(CRASS_B200_EINVAL, "ac_build: more than 2^24 automaton states"); }
-    A->n_syms = ns;
+    if ((size_t)offs[n] + 1 >= (1u << 24)) return fail(CRASS_B200_EINVAL, "ac_build: more than 2^24 automaton states");
+    Automaton* A = new Automaton();
+    A->min_pattern_len = lo;
+    A->max_pattern_len = hi;
     A->n_patterns = n;
-    uint32_t stride = 1;
-    while (stride < ns - 1) stride <<= 1;
-    A->stride = stride;
-    A->p_bytes.assign(bytes, bytes + offs[n]);
-    A->p_bytes.resize(A->p_bytes.size() + 16, 0);                    // slack for word-wise device reads
+    A->p_bytes.resize((size_t)offs[n] + 16);                         // 16 bytes of slack for word-wise device reads
+    memcpy(A->p_bytes.data(), bytes, offs[n]);
+    memset(A->p_bytes.data() + offs[n], 0, 16);
     A->p_offs.assign(offs, offs + n + 1);
     build_filter_and_starts(A);
     static std::atomic<uint64_t> next_serial{1};
@@ -144,8 +154,24 @@ int build_automaton(const uint8_t* bytes, const uint32_t* offs, uint32_t n, Auto
     return 0;
 }
 
+// byte -> symbol map of the dense DFA (1..n_syms-1 in order of first appearance, 0 = in no pattern); only the generic K2
+// path and the introspection calls need it, so it is not part of every build
+void ensure_symbols(Automaton* A) {
+    if (A->n_syms) return;
+    memset(A->symv, 0, sizeof A->symv);
+    uint32_t ns = 1;
+    const size_t total = A->p_offs[A->n_patterns];
+    for (size_t k = 0; k < total; ++k)
+        if (!A->symv[A->p_bytes[k]]) A->symv[A->p_bytes[k]] = (uint8_t)(ns++);
+    A->n_syms = ns;
+    uint32_t stride = 1;
+    while (stride < ns - 1) stride <<= 1;
+    A->stride = stride;
+}
+
 void ensure_dfa(Automaton* A) {
     if (A->has_dfa) return;
+    ensure_symbols(A);
     const uint32_t n = A->n_patterns;
     const uint8_t* bytes = A->p_bytes.data();
     const uint32_t* offs = A->p_offs.data();

@@ -111,7 +111,7 @@ std::string dump_results(Results& r, int max_read_len);
 // ---- multi-pattern automaton (dense DFA, failure links resolved) ---------------------------------------
 struct Automaton {
     uint32_t n_states = 0, n_syms = 0;          // n_syms includes symbol 0 = "byte not in any pattern"
-    uint8_t symv[256];
+    uint8_t symv[256] = {0};
     std::vector<uint32_t> table;                // n_states * stride entries: next_state | (out_len << 24)?  see ac_build.cpp
     uint32_t stride = 0;                        // entries per state (n_syms rounded up to a power of two)
     uint32_t min_pattern_len = 0, max_pattern_len = 0, n_patterns = 0;
@@ -127,6 +127,7 @@ struct Automaton {
     std::vector<uint32_t> q_bitmap_small;
     uint32_t s_bits = 0, s_ones_head = 0xFFFFFFFFu;
     std::vector<uint32_t> s_keys, s_head, p_next;
+    bool tables_on_host = false;                // false: bitmap / key table / start table are built on the device (k_ac_build)
     // device copies, owned by the context that uploaded them
     void* d_table = nullptr;
     void* d_out_len = nullptr;
@@ -137,6 +138,7 @@ struct Automaton {
     ~Automaton();
 };
 int build_automaton(const uint8_t* bytes, const uint32_t* offs, uint32_t n, Automaton** out);
+void ensure_symbols(Automaton* a);              // symv / n_syms / stride, on first use
 void ensure_dfa(Automaton* a);                  // builds table/out_len on first use (generic K2 path, introspection)
 void free_device_tables(Automaton* a);          // implemented in the CUDA TU
 

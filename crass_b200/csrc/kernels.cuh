@@ -237,7 +237,8 @@ struct ClusterArrays {
     uint32_t* info;              // [0] n, [1] total k-mers, [2] k-mers that need the string map
     uint32_t* str_tq;            // (t, q) of the first str_cap of those, in no particular order
     uint32_t str_cap;
-    __device__ uint32_t n() const { return min(*reinterpret_cast<const uint32_t*>(block), cap); }
+    uint32_t max_n;              // lists longer than this are left to the host (the rank kernel is O(n^2)): the kernels then see n = 0
+    __device__ uint32_t n() const { const uint32_t k = min(*reinterpret_cast<const uint32_t*>(block), cap); return k > max_n ? 0u : k; }
     __device__ const uint8_t* rec(uint32_t slot) const { return block + kTokenBlockHeader + (size_t)slot * stride; }
     __device__ uint32_t key_of(uint32_t slot) const { return *reinterpret_cast<const uint32_t*>(rec(slot) + stride - 4); }
     __device__ uint32_t len_of(uint32_t slot) const { const uint32_t l = rec(slot)[0]; return l + 6u <= stride ? l : stride - 6u; }
@@ -1215,13 +1216,14 @@ k_ac_scan_generic(const uint8_t* __restrict__ bases, const uint64_t* __restrict_
 struct QgramFilter {
     const uint32_t* bitmap;     // 2^bits bits
     const uint32_t* keys;       // 2^table_bits slots, 0xFFFFFFFF = empty
-    uint32_t bits, table_bits, has_ones;
+    uint32_t bits, table_bits;
+    const uint32_t* ones;       // [0] != 0: some pattern holds the all-ones 16-mer (which cannot be a table key), [1] head of the chain of patterns that begin with it
 };
 
 constexpr int kAcTile = 1024;     // big CTAs: the 64-128 KB bitmap is staged once per CTA, so threads/CTA sets the occupancy
 
 __device__ __forceinline__ bool qgram_member(const QgramFilter& q, uint32_t code) {
-    if (code == 0xFFFFFFFFu) return q.has_ones != 0;
+    if (code == 0xFFFFFFFFu) return __ldg(q.ones) != 0;
     const uint32_t mask = (1u << q.table_bits) - 1u;
     uint32_t slot = (code * 0x85EBCA6Bu) >> (32 - q.table_bits);
     for (;;) {
@@ -1475,7 +1477,9 @@ struct PatternStarts {
     const uint32_t* s_keys;
     const uint32_t* s_head;
     const uint32_t* p_next;
-    uint32_t s_bits, s_ones_head, min_len;
+    uint32_t s_bits;
+    const uint32_t* ones;       // see QgramFilter
+    uint32_t min_len;
 };
 
 __global__ void __launch_bounds__(128)
@@ -1496,7 +1500,7 @@ k_ac_verify_list(const uint8_t* __restrict__ bases, const uint64_t* __restrict__
             const uint32_t p = i - 15;                               // start of this 16-mer
             if (best_len && p + ps.min_len > best_end) break;        // later starts cannot end earlier
             uint32_t pi;
-            if (code == 0xFFFFFFFFu) pi = ps.s_ones_head;
+            if (code == 0xFFFFFFFFu) pi = __ldg(ps.ones + 1);
             else {
                 uint32_t slot = (code * 0x85EBCA6Bu) >> (32 - ps.s_bits);
                 for (;;) {
@@ -1552,7 +1556,7 @@ k_ac_verify_warp(const uint8_t* __restrict__ bases, const uint64_t* __restrict__
 #pragma unroll
                 for (int k = 0; k < 16; ++k) code |= (uint32_t)((__ldg(s + p + k) >> 1) & 3u) << (2 * k);
                 uint32_t pi;
-                if (code == 0xFFFFFFFFu) pi = ps.s_ones_head;
+                if (code == 0xFFFFFFFFu) pi = __ldg(ps.ones + 1);
                 else {
                     uint32_t slot = (code * 0x85EBCA6Bu) >> (32 - ps.s_bits);
                     for (;;) {
@@ -1628,7 +1632,7 @@ k_ac_verify_mask(const uint8_t* __restrict__ bases, const uint64_t* __restrict__
 #pragma unroll
                 for (int k = 0; k < 16; ++k) code |= (uint32_t)((__ldg(s + p + k) >> 1) & 3u) << (2 * k);
                 uint32_t pi;
-                if (code == 0xFFFFFFFFu) pi = ps.s_ones_head;
+                if (code == 0xFFFFFFFFu) pi = __ldg(ps.ones + 1);
                 else {
                     uint32_t slot = (code * 0x85EBCA6Bu) >> (32 - ps.s_bits);
                     for (;;) {
@@ -1777,3 +1781,5 @@ __global__ void k_qc_one(const uint8_t* __restrict__ seq, uint32_t L, const uint
 }
 
 }  // namespace cbk
+
+#include "cluster.cuh"

@@ -181,6 +181,8 @@ int crass_b200_ac_upload(crass_b200_ctx* ctx, const crass_b200_ac* ac);
 uint32_t crass_b200_ac_num_states(const crass_b200_ac* ac);
 uint32_t crass_b200_ac_num_symbols(const crass_b200_ac* ac);
 uint64_t crass_b200_ac_table_bytes(const crass_b200_ac* ac);
+/* the patterns the matcher was built from, '\n'-separated in build order (malloc'd, crass_b200_free) */
+char* crass_b200_ac_pattern_text(const crass_b200_ac* ac, uint32_t* n_patterns);
 
 /* d_skip[n_reads] may be NULL; reads with d_skip[i]!=0 are not scanned (the readsFound test of
  * on_match, libcrispr.cpp:411, for reads already found in phase 1).  For every scanned read with a
@@ -293,9 +295,13 @@ char* crass_b200_non_redundant_set(const char* dr_list, uint32_t kmer_clust);
  * libcrispr.cpp:455-470).  *n_patterns (optional) = size of the non-redundant set; an empty set is EINVAL. */
 int crass_b200_ac_build_from_dr_list(const char* dr_list, uint32_t kmer_clust, crass_b200_ac** out, uint32_t* n_patterns);
 /* K5: the same step from a token block that is still on the device (the output of unique_tokens_block_dev or
- * merge_token_blocks_dev).  The data-parallel passes of createNonRedundantSet -- token order, the canonical key of every
- * 11-mer and the first DR holding it (clusterDRReads' k-mer map, WorkHorse.cpp:1404-1637) -- run as kernels; the
- * order-dependent walk, the substring reduction and the matcher build follow on the host.  Synchronises the stream.
+ * merge_token_blocks_dev).  All of createNonRedundantSet runs as kernels (K5, csrc/cluster.cuh): token order, the canonical
+ * key of every 11-mer and the first DR holding it (clusterDRReads' k-mer map, WorkHorse.cpp:1404-1637), the
+ * order-dependent group walk (:1542-1625) as a dependency graph, removeRedundantRepeats (:612-645) and the emission of
+ * survivors + reverse complements (:690-697); the pattern bytes come back in the one host synchronisation of the call and
+ * the matcher's tables are built on the device (k_ac_build) before the call returns, so a scan can follow at once.
+ * Lists the kernels decline (a letter with a non-involutive complement such as 'U', more than 32768 variants, ...) take
+ * the host passes; CRASS_B200_CLUSTER=device-passes selects the round-1 split (first passes on the device, rest on the host).
  * *count / *flags as in dr_list_from_block; *out stays NULL (return 0) for an overflowed or empty block.
  * The second form returns the pattern set as '\n'-separated text instead (malloc'd). */
 int crass_b200_cluster_block_dev(crass_b200_ctx* ctx, const void* d_block, uint32_t cap, uint32_t stride, uint32_t kmer_clust,

@@ -368,9 +368,22 @@ def test_token_blocks_of_three_shards_merge_like_one_sequential_run(ctx):
     assert api.dr_list_from_block(out.cpu().numpy(), 16, TOK)[1] == len(want)
 
 
+def _token_block(uniq, keys, slots, cap, stride):
+    blk = np.zeros(api.token_block_bytes(cap, stride), dtype=np.uint8)
+    blk[:4] = np.frombuffer(np.uint32(len(uniq)).tobytes(), dtype=np.uint8)
+    for t, slot in enumerate(slots):
+        rec = blk[16 + slot * stride: 16 + (slot + 1) * stride]
+        rec[0] = len(uniq[t])
+        rec[2:2 + len(uniq[t])] = np.frombuffer(uniq[t], dtype=np.uint8)
+        rec[stride - 4:] = np.frombuffer(np.uint32(keys[t]).tobytes(), dtype=np.uint8)
+    return blk
+
+
 def test_clustering_passes_on_the_device_match_the_host(ctx, P):
-    """K5: token order, 11-mer keys and first holders computed by kernels on a token block must lead to exactly the pattern
-    set (same strings, same order) of the host passes and of the oracle, incl. N/U/R letters, tiny and long lists."""
+    """K5: createNonRedundantSet as kernels on a token block (token order, 11-mer keys and first holders, the group walk,
+    the substring reduction, survivors + reverse complements) must give exactly the pattern set (same strings, same order)
+    of the host passes and of the oracle, incl. N/R letters (string-keyed k-mers), 'U' (declined: host passes), DRs shorter
+    than a k-mer, tiny and long lists -- and so must the round-1 splits between device and host."""
     import torch
     rng = random.Random(109)
     comp = bytes.maketrans(b"ACGT", b"TGCA")
@@ -378,7 +391,7 @@ def test_clustering_passes_on_the_device_match_the_host(ctx, P):
     stride = 64
     for n_base, n_var, alphabet, lo, hi in ((1, 1, b"ACGT", 23, 47), (3, 4, b"ACGT", 23, 47), (40, 12, b"ACGTN", 23, 47), (60, 10, b"ACGTUR", 23, 47),
                                            (30, 10, b"ACGTN", 6, 20), (25, 14, b"ACUR", 11, 30), (400, 16, b"ACGTN", 23, 47), (1500, 28, b"ACGT", 23, 47),
-                                           (2200, 16, b"ACGT", 23, 47)):          # the last one is past the device limit (32768): host passes
+                                           (50, 40, b"ACGTNRY", 23, 47), (2200, 16, b"ACGT", 23, 47)):   # the last one is past the device limit (32768): host passes
         base = [fuzzgen.rand_seq(rng, rng.randint(lo, hi)) for _k in range(n_base)]
         drs = []
         for b in base:
@@ -393,26 +406,25 @@ def test_clustering_passes_on_the_device_match_the_host(ctx, P):
         slots = list(range(len(uniq)))
         rng.shuffle(slots)                                                # records sit in the block in arbitrary order
         cap = len(uniq) + rng.randint(0, 50)
-        blk = np.zeros(api.token_block_bytes(cap, stride), dtype=np.uint8)
-        blk[:4] = np.frombuffer(np.uint32(len(uniq)).tobytes(), dtype=np.uint8)
-        for t, slot in enumerate(slots):
-            rec = blk[16 + slot * stride: 16 + (slot + 1) * stride]
-            rec[0] = len(uniq[t])
-            rec[2:2 + len(uniq[t])] = np.frombuffer(uniq[t], dtype=np.uint8)
-            rec[stride - 4:] = np.frombuffer(np.uint32(keys[t]).tobytes(), dtype=np.uint8)
+        blk = _token_block(uniq, keys, slots, cap, stride)
         want, cnt_h, fl_h = api.non_redundant_patterns_from_block(blk, cap, stride, 6)
         assert want == api.non_redundant_patterns(b"".join(d + b"\n" for d in uniq), 6)
         d_blk = torch.from_numpy(blk).to(dev)
+        before = ctx.launch_count
         got, cnt, fl = ctx.cluster_block_patterns_dev(d_blk, cap, stride, 6)
         assert (cnt, fl) == (cnt_h, fl_h) == (len(uniq), 0)
         assert got == want, (n_base, n_var, alphabet, lo, hi)
-        os.environ["CRASS_B200_CLUSTER"] = "device-reduce"                # ... and with the substring reduction on the device too
-        try:
-            assert ctx.cluster_block_patterns_dev(d_blk, cap, stride, 6)[0] == want
-        finally:
-            os.environ.pop("CRASS_B200_CLUSTER", None)
+        if (alphabet == b"ACGT" or len(uniq) < 1000) and b"U" not in alphabet and len(uniq) <= 32768:
+            assert ctx.launch_count - before == 19                        # really the kernels, not a quiet detour over the host (which lists with more than 4096 string-keyed k-mers take)
+        for mode in ("device-passes", "device-reduce"):                  # the round-1 splits: first passes (and pass D) on the device, rest on the host
+            os.environ["CRASS_B200_CLUSTER"] = mode
+            try:
+                assert ctx.cluster_block_patterns_dev(d_blk, cap, stride, 6)[0] == want
+            finally:
+                os.environ.pop("CRASS_B200_CLUSTER", None)
         ac, cnt2, fl2 = ctx.cluster_block_dev(d_blk, cap, stride, 6)
         assert ac is not None and ac.num_patterns == want.count(b"\n") and cnt2 == len(uniq)
+        assert ac.pattern_text() == want
         if len(uniq) < 3000:                                              # the oracle's clustering is quadratic
             ref = P.non_redundant(uniq)
             assert sorted(l[2:] for l in ref.split("\n") if l.startswith("P\t")) == sorted(want.decode().split("\n")[:-1])
@@ -420,6 +432,41 @@ def test_clustering_passes_on_the_device_match_the_host(ctx, P):
     blk[:4] = np.frombuffer(np.uint32(cap + 5).tobytes(), dtype=np.uint8)
     got, cnt, fl = ctx.cluster_block_patterns_dev(torch.from_numpy(blk).to(dev), cap, stride, 6)
     assert got == b"" and cnt == cap + 5
+
+
+def test_group_walk_on_the_device_follows_long_dependency_chains(ctx, P):
+    """The order-dependent walk of clusterDRReads (WorkHorse.cpp:1542-1625) runs as a dependency graph on the device: DR t
+    waits for the groups of the earlier DRs its k-mers were first seen in.  Windows sliding over one long sequence make
+    that graph a single chain as long as the list (every DR hangs on the one before it), the worst case for it; windows
+    over several sequences in interleaved order give many chains at once."""
+    import torch
+    rng = random.Random(110)
+    dev = torch.device("cuda", 0)
+    stride = 64
+    for n_seq, n_win, step, shuffle in ((1, 3000, 5, False), (1, 800, 9, False), (7, 400, 3, True), (1, 600, 1, False)):
+        uniq = []
+        seqs = [fuzzgen.rand_seq(rng, n_win * step + 60) for _ in range(n_seq)]
+        for w in range(n_win):
+            for sq in seqs:
+                uniq.append(sq[w * step: w * step + rng.randint(30, 44)])
+        uniq = list(dict.fromkeys(uniq))
+        if shuffle:
+            # keep every chain's order, interleave the chains at random
+            chains = [uniq[i::n_seq] for i in range(n_seq)]
+            uniq = []
+            while any(chains):
+                c = rng.choice([c for c in chains if c])
+                uniq.append(c.pop(0))
+        keys = sorted(rng.sample(range(50_000_000), len(uniq)))
+        slots = list(range(len(uniq)))
+        rng.shuffle(slots)
+        cap = len(uniq) + 7
+        blk = _token_block(uniq, keys, slots, cap, stride)
+        want, _, _ = api.non_redundant_patterns_from_block(blk, cap, stride, 6)
+        before = ctx.launch_count
+        got, cnt, fl = ctx.cluster_block_patterns_dev(torch.from_numpy(blk).to(dev), cap, stride, 6)
+        assert ctx.launch_count - before == 19 and (cnt, fl) == (len(uniq), 0)
+        assert got == want, (n_seq, n_win, step)
 
 
 def test_singleton_scan_on_the_kept_2bit_stream(ctx, P):
@@ -459,6 +506,53 @@ def test_singleton_scan_on_the_kept_2bit_stream(ctx, P):
             assert (m is None) == (i not in by_read)
         P.ac_destroy(h)
         assert len(h2) > 100
+
+
+def test_matcher_tables_built_on_the_device(ctx, P):
+    """k_ac_build fills bitmap, key table and start table with atomics on the device; CRASS_B200_AC_BUILD=host fills them
+    sequentially on the host and uploads them.  Both must answer every read like the oracle's automaton -- also for
+    patterns with long G runs, whose all-ones 16-mer is the tables' empty marker and goes through the side words."""
+    rng = random.Random(111)
+    for n_pat in (1, 60, 3000):
+        pats = fuzzgen.dr_like_patterns(rng, n_pat)
+        pats += [b"G" * rng.randint(23, 40) for _ in range(2)]                                   # every window is all ones
+        pats += [fuzzgen.rand_seq(rng, rng.randint(0, 7)) + b"G" * 16 + fuzzgen.rand_seq(rng, rng.randint(7, 20)) for _ in range(6)]   # one all-ones window at offset 0..7
+        pats += [b"G" * 16 + fuzzgen.rand_seq(rng, rng.randint(8, 20)) for _ in range(3)]       # ... chained from the side word
+        pats += [pats[0][:16] + fuzzgen.rand_seq(rng, 12), pats[0][:16] + fuzzgen.rand_seq(rng, 20)]   # shared first 16-mer: one start-table chain
+        pats = [p for p in dict.fromkeys(pats) if len(p) >= 23]
+        texts = []
+        for _ in range(3000):
+            t = bytearray(fuzzgen.rand_seq(rng, rng.choice([30, 100, 150, 150, 300, 900])))
+            r = rng.random()
+            if r < 0.5:
+                p = rng.choice(pats)
+                pos = rng.randint(0, len(t) - 1)
+                t = (t[:pos] + p + t[pos:])[:len(t)]
+            elif r < 0.6:
+                pos = rng.randint(0, len(t) - 1)
+                t = (t[:pos] + b"G" * rng.randint(10, 60) + t[pos:])[:len(t)]
+            texts.append(bytes(t))
+        bases, offs = cb.pack_reads(texts)
+        h = P.ac_create(pats)
+        want = {}
+        for i, t in enumerate(texts):
+            m = P.ac_first_match(h, t)
+            if m is not None:
+                dr_end = min(m[0] - 1, len(t) - 1)
+                want[i] = ([dr_end - (m[1] - 1), dr_end], 0)
+        P.ac_destroy(h)
+        assert len(want) > 1000
+        for build in ("device", "host"):
+            os.environ["CRASS_B200_AC_BUILD"] = build
+            try:
+                for short_only in (False, True):                            # long reads take the warp filter, reads <= 304 the tile filters
+                    sel = [i for i, t in enumerate(texts) if len(t) <= 304] if short_only else list(range(len(texts)))
+                    b2, o2 = cb.pack_reads([texts[i] for i in sel])
+                    hits, pool, found = ctx.ac_scan(cb.Automaton(pats), b2, o2)
+                    got = hits_by_read(hits, pool)
+                    assert got == {k: want[i] for k, i in enumerate(sel) if i in want}, (n_pat, build, short_only)
+            finally:
+                os.environ.pop("CRASS_B200_AC_BUILD", None)
 
 
 def test_singleton_scan_fuzz(ctx, P, k2path):
