@@ -408,7 +408,7 @@ int cluster_block_host_passes(crass_b200_ctx* c, const void* d_block, uint32_t c
                          c->d_cl_str.as<uint32_t>(), kStrListCap, kClusterDeviceMax};
     CUDA_TRY(cudaMemsetAsync(c->d_cl_info.p, 0, 16, st));
     CUDA_TRY(cudaMemsetAsync(c->d_cl_tab.p, 0xFF, tab * 8, st));
-    cbk::k_cl_rank<<<(cap + cbk::kClRankThreads) / cbk::kClRankThreads, cbk::kClRankThreads, 0, st>>>(a);
+    cbk::k_cl_rank<<<(cap + cbk::kClRankThreads) / cbk::kClRankThreads, cbk::kClRankThreads * cbk::kClRankParts, 0, st>>>(a);
     cbk::k_rank_scan<<<1, 1024, 0, st>>>(a.koff, cap + 1, a.info);                  // info[0] = n, written by k_cl_rank
     cbk::k_cl_keys<<<(cap * 32 + cbk::kClKeysThreads - 1) / cbk::kClKeysThreads, cbk::kClKeysThreads, 0, st>>>(a);
     cbk::k_cl_first<<<c->sm_count * 4, 256, 0, st>>>(a);
@@ -537,7 +537,7 @@ int cluster_block_device(crass_b200_ctx* c, const void* d_block, uint32_t cap, u
                  o_group = carve((size_t)cap * 4), o_gnum = carve(((size_t)cap + 2) * 4), o_gstart = carve(((size_t)cap + 2) * 4),
                  o_gfill = carve((size_t)cap * 4), o_members = carve((size_t)cap * 4), o_sorted = carve((size_t)cap * 4),
                  o_alive = carve(((size_t)cap + 2) * 4), o_plen = carve((2 * (size_t)cap + 2) * 4), o_psrc = carve(2 * (size_t)cap * 4),
-                 o_pbytes = carve(2 * (size_t)cap * (stride - 6) + 32), o_canon = carve((size_t)kStrListCap * 12);
+                 o_pbytes = carve(2 * (size_t)cap * (stride - 6) + 32), o_canon = carve((size_t)kStrListCap * 12), o_packed = carve((size_t)cap * 32);
     if (int r = c->d_cl_tail.reserve(at)) return r;
     uint8_t* tb = c->d_cl_tail.as<uint8_t>();
     cbk::ClusterArrays a{(const uint8_t*)d_block, cap, stride, c->d_cl_order.as<uint32_t>(), c->d_cl_koff.as<uint32_t>(),
@@ -547,12 +547,12 @@ int cluster_block_device(crass_b200_ctx* c, const void* d_block, uint32_t cap, u
     cbk::ClusterTail t{a, (uint32_t*)(tb + o_lens), (uint32_t*)(tb + o_runc), (uint32_t*)(tb + o_nruns), (uint32_t*)(tb + o_group),
                        (uint32_t*)(tb + o_gnum), (uint32_t*)(tb + o_gstart), (uint32_t*)(tb + o_gfill), (uint32_t*)(tb + o_members),
                        (uint32_t*)(tb + o_sorted), (uint32_t*)(tb + o_alive), (uint32_t*)(tb + o_plen), (uint32_t*)(tb + o_psrc),
-                       tb + o_pbytes, tb + o_canon, kmer_clust};
+                       tb + o_pbytes, tb + o_canon, (ulonglong4*)(tb + o_packed), kmer_clust};
     CUDA_TRY(cudaMemsetAsync(c->d_cl_info.p, 0, cbk::kInfoWords * 4, st));
     CUDA_TRY(cudaMemsetAsync(c->d_cl_tab.p, 0xFF, tab * 8, st));
     CUDA_TRY(cudaMemsetAsync(t.plen, 0, (2 * (size_t)cap + 2) * 4, st));
     const uint32_t per_dr128 = (cap + 127) / 128, per_dr256 = (cap + 1 + 255) / 256, warp_per_dr = (cap + 1 + 3) / 4;
-    cbk::k_cl_rank<<<(cap + cbk::kClRankThreads) / cbk::kClRankThreads, cbk::kClRankThreads, 0, st>>>(a);
+    cbk::k_cl_rank<<<(cap + cbk::kClRankThreads) / cbk::kClRankThreads, cbk::kClRankThreads * cbk::kClRankParts, 0, st>>>(a);
     cbk::k_rank_scan<<<1, 1024, 0, st>>>(a.koff, cap + 1, a.info);                  // info[0] = n, written by k_cl_rank
     cbk::k_cl_keys<<<(cap * 32 + cbk::kClKeysThreads - 1) / cbk::kClKeysThreads, cbk::kClKeysThreads, 0, st>>>(a);
     cbk::k_cl_first<<<c->sm_count * 4, 256, 0, st>>>(a);
@@ -566,7 +566,8 @@ int cluster_block_device(crass_b200_ctx* c, const void* d_block, uint32_t cap, u
     cbk::k_rank_scan<<<1, 1024, 0, st>>>(t.gstart, cap + 1, a.info);
     cbk::k_cl_members<<<per_dr256, 256, 0, st>>>(t);
     cbk::k_cl_group_sort<<<warp_per_dr, 128, 0, st>>>(t);
-    cbk::k_cl_dead<<<warp_per_dr, 128, 4 * stride, st>>>(t);
+    if (stride <= 70) cbk::k_cl_dead_packed<<<warp_per_dr, 128, 0, st>>>(t);          // tokens of at most 64 bases: compared as 2-bit codes
+    else cbk::k_cl_dead<<<warp_per_dr, 128, 4 * stride, st>>>(t);
     cbk::k_rank_scan<<<1, 1024, 0, st>>>(t.alive, cap + 1, a.info);
     cbk::k_cl_place<<<per_dr256, 256, 0, st>>>(t);
     cbk::k_rank_scan<<<1, 1024, 0, st>>>(t.plen, 2 * cap + 1, a.info + cbk::kInfoPatterns);

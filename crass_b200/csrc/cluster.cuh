@@ -45,6 +45,7 @@ struct ClusterTail {
     uint32_t* psrc;      // [2 cap]    pattern -> DR t, bit 31 = reverse complement
     uint8_t* pbytes;     // pattern bytes (+ 16 bytes of zeroed slack)
     uint8_t* canon;      // [str_cap * 12] canonical bytes of the string-keyed k-mers
+    ulonglong4* packed;  // [cap]      2-bit codes ((byte >> 1) & 3) of DR t: x, y = bases 0..31, 32..63; z, w = the same of its reverse complement
     uint32_t min_count;
     __device__ const uint8_t* dr(uint32_t t) const { return a.rec(a.order[t]) + 2; }
 };
@@ -76,15 +77,23 @@ k_cl_str_canon(ClusterTail c) {
 
 __global__ void __launch_bounds__(128)
 k_cl_str_first(ClusterTail c) {
+    __shared__ uint32_t tw[128 * 3], tt[128];
     const uint32_t m = min(c.a.info[kInfoStr], c.a.str_cap);
+    if (blockIdx.x * 128 >= m) return;
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
-    if (i >= m) return;
     const uint32_t* w = reinterpret_cast<const uint32_t*>(c.canon);
-    const uint32_t w0 = w[3 * i], w1 = w[3 * i + 1], w2 = w[3 * i + 2];
-    uint32_t best = c.a.str_tq[2 * i];
-    for (uint32_t j = 0; j < m; ++j)
-        if (w[3 * j] == w0 && w[3 * j + 1] == w1 && w[3 * j + 2] == w2) best = min(best, c.a.str_tq[2 * j]);
-    c.a.first[c.a.str_tq[2 * i + 1]] = best;
+    uint32_t w0 = 0, w1 = 0, w2 = 0, best = 0xFFFFFFFFu;
+    if (i < m) { w0 = w[3 * i]; w1 = w[3 * i + 1]; w2 = w[3 * i + 2]; }
+    for (uint32_t j0 = 0; j0 < m; j0 += 128) {
+        __syncthreads();
+        const uint32_t j = j0 + threadIdx.x;
+        if (j < m) { tw[threadIdx.x * 3] = w[3 * j]; tw[threadIdx.x * 3 + 1] = w[3 * j + 1]; tw[threadIdx.x * 3 + 2] = w[3 * j + 2]; tt[threadIdx.x] = c.a.str_tq[2 * j]; }
+        __syncthreads();
+        const uint32_t lim = min(128u, m - j0);
+        for (uint32_t k = 0; k < lim; ++k)
+            if (tw[3 * k] == w0 && tw[3 * k + 1] == w1 && tw[3 * k + 2] == w2) best = min(best, tt[k]);
+    }
+    if (i < m) c.a.first[c.a.str_tq[2 * i + 1]] = best;
 }
 
 // pass B2.  first[q] >= t means "never seen before this DR": such k-mers change no tally in the walk, so runs reach across them.
@@ -99,10 +108,18 @@ k_cl_runs(ClusterTail c) {
     c.lens[t] = len;
     c.group[t] = 0;
     uint32_t flags = len ? 0u : (uint32_t)kClFlagEmpty;
+    unsigned long long f0 = 0, f1 = 0, r0 = 0, r1 = 0;
     for (uint32_t i = 0; i < len; ++i) {
         const uint8_t b = dr[i];
-        if (b >= 128 || c_comp_tab[c_comp_tab[b]] != b) flags |= kClFlagLetter;       // 'U' -> 'A' -> 'T': containment on both strands is no longer transitive
+        if (b >= 128 || c_comp_tab[c_comp_tab[b & 127]] != b) flags |= kClFlagLetter;   // 'U' -> 'A' -> 'T': containment on both strands is no longer transitive
+        if (i < 64) {
+            const unsigned long long cf = (b >> 1) & 3u, cr = (c_comp_tab[b & 127] >> 1) & 3u;
+            const uint32_t j = len - 1 - i;                      // where the complement of base i sits in the reverse complement
+            if (i < 32) f0 |= cf << (2 * i); else f1 |= cf << (2 * (i - 32));
+            if (j < 32) r0 |= cr << (2 * j); else if (j < 64) r1 |= cr << (2 * (j - 32));
+        }
     }
+    c.packed[t] = make_ulonglong4(f0, f1, r0, r1);
     if (flags) atomicOr(&c.a.info[kInfoFlags], flags);
     const uint32_t q0 = c.a.koff[t], q1 = c.a.koff[t + 1];
     uint32_t out = q0;
@@ -202,7 +219,54 @@ k_cl_group_sort(ClusterTail c) {
     if (lane == 0) c.sorted[gs + before] = t;
 }
 
-// pass D.  One warp per DR b, lanes over the members in front of it; containment is transitive on both strands (for the
+// pass D on the 2-bit codes (DRs up to 64 bases: every default-geometry token).  b's code sits in registers and slides by one
+// base per step; a lane holds one earlier member a (code, code of its reverse complement, mask of its length) and compares
+// 128 bits per position and strand.  Equal bytes give equal codes, so the codes can only over-report ('N' codes like 'G'):
+// a code match is confirmed on the bytes before it counts.
+__device__ __forceinline__ bool cl_bytes_at(const uint8_t* b, uint32_t at, const uint8_t* a, uint32_t la, bool revcomp) {
+    if (!revcomp) { for (uint32_t i = 0; i < la; ++i) if (b[at + i] != a[i]) return false; }
+    else { for (uint32_t i = 0; i < la; ++i) if (b[at + i] != c_comp_tab[a[la - 1 - i] & 127]) return false; }
+    return true;
+}
+
+__global__ void __launch_bounds__(128)
+k_cl_dead_packed(ClusterTail c) {
+    const uint32_t n = c.a.n();
+    const uint32_t s = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (s == n && lane == 0) c.alive[n] = 0;
+    if (s >= n) return;
+    const uint32_t tb = c.sorted[s];
+    const uint32_t lb = c.lens[tb];
+    const ulonglong4 pb = c.packed[tb];
+    const uint32_t gs = c.gstart[cl_group_of(c, tb)];
+    bool dead = false;
+    for (uint32_t i0 = gs; i0 < s; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        if (i < s) {
+            const uint32_t ta = c.sorted[i];
+            const uint32_t la = c.lens[ta];                      // <= lb by the order
+            const ulonglong4 pa = c.packed[ta];
+            const unsigned long long m0 = la >= 32 ? ~0ull : (1ull << (2 * la)) - 1ull;
+            const unsigned long long m1 = la <= 32 ? 0ull : la >= 64 ? ~0ull : (1ull << (2 * (la - 32))) - 1ull;
+            unsigned long long b0 = pb.x, b1 = pb.y;
+            for (uint32_t at = 0; at + la <= lb && !dead; ++at) {
+                const bool fw = (((b0 ^ pa.x) & m0) | ((b1 ^ pa.y) & m1)) == 0;
+                const bool rc = (((b0 ^ pa.z) & m0) | ((b1 ^ pa.w) & m1)) == 0;
+                if (fw || rc) {
+                    const uint8_t* bg = c.dr(tb);
+                    const uint8_t* ag = c.dr(ta);
+                    dead = (fw && cl_bytes_at(bg, at, ag, la, false)) || (rc && cl_bytes_at(bg, at, ag, la, true));
+                }
+                b0 = (b0 >> 2) | (b1 << 62);
+                b1 >>= 2;
+            }
+        }
+        if (__any_sync(0xFFFFFFFFu, dead)) { dead = true; break; }
+    }
+    if (lane == 0) c.alive[s] = dead ? 0u : 1u;
+}
+
+// pass D on the bytes (tokens longer than 64 bases: wider DR bounds than the default).  One warp per DR b, lanes over the members in front of it; containment is transitive on both strands (for the
 // letters k_cl_runs lets through), so "an earlier member" and the reference's "an earlier survivor" are the same test.
 __global__ void __launch_bounds__(128)
 k_cl_dead(ClusterTail c) {

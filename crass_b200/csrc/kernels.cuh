@@ -166,6 +166,8 @@ k_rank_chunks(const uint8_t* __restrict__ found, uint32_t n_reads, uint32_t* __r
     if (threadIdx.x == 0) chunk_count[c] = w[0] + w[1];
 }
 
+constexpr uint32_t kScanItems = 8;                   // consecutive entries per thread: 8192 per pass of the one CTA
+
 __global__ void __launch_bounds__(1024)
 k_rank_scan(uint32_t* __restrict__ chunk_count, uint32_t n_chunks, const uint32_t* __restrict__ n_dev = nullptr) {   // in place: counts -> exclusive prefix
     if (n_dev) n_chunks = min(n_chunks, *n_dev + 1u);                                 // only the part that is in use (+ the total)
@@ -173,10 +175,21 @@ k_rank_scan(uint32_t* __restrict__ chunk_count, uint32_t n_chunks, const uint32_
     __shared__ uint32_t carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (uint32_t base = 0; base < n_chunks; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < n_chunks ? chunk_count[i] : 0u;
-        uint32_t x = v;
+    const bool aligned = (reinterpret_cast<uintptr_t>(chunk_count) & 15u) == 0;
+    for (uint32_t base = 0; base < n_chunks; base += 1024 * kScanItems) {
+        const uint32_t i0 = base + threadIdx.x * kScanItems;
+        uint32_t v[kScanItems];
+        if (aligned && i0 + kScanItems <= n_chunks) {
+            const uint4 a = *reinterpret_cast<const uint4*>(chunk_count + i0), b = *reinterpret_cast<const uint4*>(chunk_count + i0 + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (uint32_t k = 0; k < kScanItems; ++k) v[k] = i0 + k < n_chunks ? chunk_count[i0 + k] : 0u;
+        }
+        uint32_t mine = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < kScanItems; ++k) mine += v[k];
+        uint32_t x = mine;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
         if ((threadIdx.x & 31u) == 31u) warp_sum[threadIdx.x >> 5] = x;
@@ -188,10 +201,19 @@ k_rank_scan(uint32_t* __restrict__ chunk_count, uint32_t n_chunks, const uint32_
             warp_sum[threadIdx.x] = s;                                                  // inclusive over the warps
         }
         __syncthreads();
-        const uint32_t before = carry + (threadIdx.x >= 32 ? warp_sum[(threadIdx.x >> 5) - 1] : 0u) + x - v;
-        if (i < n_chunks) chunk_count[i] = before;
+        uint32_t before = carry + (threadIdx.x >= 32 ? warp_sum[(threadIdx.x >> 5) - 1] : 0u) + x - mine;
+        const uint32_t after_me = before + mine;
+#pragma unroll
+        for (uint32_t k = 0; k < kScanItems; ++k) { const uint32_t t = v[k]; v[k] = before; before += t; }
+        if (aligned && i0 + kScanItems <= n_chunks) {
+            *reinterpret_cast<uint4*>(chunk_count + i0) = make_uint4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<uint4*>(chunk_count + i0 + 4) = make_uint4(v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+            for (uint32_t k = 0; k < kScanItems; ++k) if (i0 + k < n_chunks) chunk_count[i0 + k] = v[k];
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) carry = before + v;
+        if (threadIdx.x == 1023) carry = after_me;
         __syncthreads();
     }
 }
@@ -244,28 +266,41 @@ struct ClusterArrays {
     __device__ uint32_t len_of(uint32_t slot) const { const uint32_t l = rec(slot)[0]; return l + 6u <= stride ? l : stride - 6u; }
 };
 
-// token position of every record = number of records with a smaller key (keys are distinct: one token per first read)
-constexpr uint32_t kClRankThreads = 64;              // small CTAs: the O(n^2) loop is spread over n / 64 of them
+// token position of every record = number of records with a smaller key (keys are distinct: one token per first read).
+// O(n^2), so it is spread wide: a CTA ranks 64 records, four threads per record each counting a quarter of every
+// 256-key tile (read as 16-byte vectors from shared memory).
+constexpr uint32_t kClRankThreads = 64;              // records per CTA
+constexpr uint32_t kClRankParts = 4;
 
-__global__ void __launch_bounds__(kClRankThreads)
+__global__ void __launch_bounds__(kClRankThreads * kClRankParts)
 k_cl_rank(ClusterArrays a) {
-    __shared__ uint32_t tile[kClRankThreads];
+    __shared__ __align__(16) uint32_t tile[kClRankThreads * kClRankParts];
+    __shared__ uint32_t partial[kClRankParts][kClRankThreads];
     const uint32_t n = a.n();
-    const uint32_t i = blockIdx.x * kClRankThreads + threadIdx.x;
+    const uint32_t il = threadIdx.x % kClRankThreads, part = threadIdx.x / kClRankThreads;
+    const uint32_t i = blockIdx.x * kClRankThreads + il;
     if (blockIdx.x * kClRankThreads >= n) {                          // CTAs past the list only clear their part of koff
-        if (i <= a.cap) a.koff[i] = 0;
-        if (i == 0) a.info[0] = n;
+        if (part == 0 && i <= a.cap) a.koff[i] = 0;
+        if (i == 0 && part == 0) a.info[0] = n;
         return;
     }
     const uint32_t mine = i < n ? a.key_of(i) : 0u;
     uint32_t rank = 0;
-    for (uint32_t j0 = 0; j0 < n; j0 += kClRankThreads) {
+    for (uint32_t j0 = 0; j0 < n; j0 += kClRankThreads * kClRankParts) {
         __syncthreads();
         tile[threadIdx.x] = j0 + threadIdx.x < n ? a.key_of(j0 + threadIdx.x) : 0xFFFFFFFFu;   // padding never counts
         __syncthreads();
-#pragma unroll 16
-        for (uint32_t j = 0; j < kClRankThreads; ++j) rank += tile[j] < mine ? 1u : 0u;
+        const uint4* t4 = reinterpret_cast<const uint4*>(tile + part * kClRankThreads);
+#pragma unroll
+        for (uint32_t j = 0; j < kClRankThreads / 4; ++j) {
+            const uint4 k = t4[j];
+            rank += (k.x < mine ? 1u : 0u) + (k.y < mine ? 1u : 0u) + (k.z < mine ? 1u : 0u) + (k.w < mine ? 1u : 0u);
+        }
     }
+    partial[part][il] = rank;
+    __syncthreads();
+    if (part != 0) return;
+    rank = partial[0][il] + partial[1][il] + partial[2][il] + partial[3][il];
     if (i < n) {
         a.order[rank] = i;
         const uint32_t len = a.len_of(i);

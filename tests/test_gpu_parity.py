@@ -388,10 +388,11 @@ def test_clustering_passes_on_the_device_match_the_host(ctx, P):
     rng = random.Random(109)
     comp = bytes.maketrans(b"ACGT", b"TGCA")
     dev = torch.device("cuda", 0)
-    stride = 64
     for n_base, n_var, alphabet, lo, hi in ((1, 1, b"ACGT", 23, 47), (3, 4, b"ACGT", 23, 47), (40, 12, b"ACGTN", 23, 47), (60, 10, b"ACGTUR", 23, 47),
                                            (30, 10, b"ACGTN", 6, 20), (25, 14, b"ACUR", 11, 30), (400, 16, b"ACGTN", 23, 47), (1500, 28, b"ACGT", 23, 47),
-                                           (50, 40, b"ACGTNRY", 23, 47), (2200, 16, b"ACGT", 23, 47)):   # the last one is past the device limit (32768): host passes
+                                           (50, 40, b"ACGTNRY", 23, 47), (60, 30, b"ACGTN", 40, 110), (30, 30, b"ACGT", 50, 64),
+                                           (2200, 16, b"ACGT", 23, 47)):   # the last one is past the device limit (32768): host passes
+        stride = 64 if hi <= 47 else 128 if hi > 64 else 68            # wider DR bounds: longer tokens (pass D on the bytes instead of the 2-bit codes)
         base = [fuzzgen.rand_seq(rng, rng.randint(lo, hi)) for _k in range(n_base)]
         drs = []
         for b in base:
@@ -399,7 +400,7 @@ def test_clustering_passes_on_the_device_match_the_host(ctx, P):
                 v = fuzzgen.mutate(rng, b, rng.choice([0, 0.02, 0.05]), alphabet)
                 a, e = rng.randint(0, 4), rng.randint(0, 4)
                 v = v[a:len(v) - e] if rng.random() < 0.5 else fuzzgen.rand_seq(rng, a) + v + fuzzgen.rand_seq(rng, e)
-                drs.append(min(v, v.translate(comp)[::-1])[:58])
+                drs.append(min(v, v.translate(comp)[::-1])[:stride - 6])
         uniq = [u for u in dict.fromkeys(drs) if u]
         rng.shuffle(uniq)                                                 # token order = order of `uniq`
         keys = sorted(rng.sample(range(50_000_000), len(uniq)))
