@@ -520,7 +520,7 @@ int cluster_block_device(crass_b200_ctx* c, const void* d_block, uint32_t cap, u
     const size_t max_kmers = (size_t)cap * (stride - 16);
     size_t tab = 1024;
     while (tab < 2 * max_kmers) tab <<= 1;
-    const uint32_t kStrListCap = 4096;                 // string-keyed 11-mers resolved pairwise on the device
+    const uint32_t kStrListCap = 16384;                // string-keyed 11-mers the device resolves (a power of two)
     if (int r = c->d_cl_order.reserve((size_t)cap * 4)) return r;
     if (int r = c->d_cl_koff.reserve(((size_t)cap + 1025) * 4)) return r;
     if (int r = c->d_cl_keys.reserve(max_kmers * 4 + 16)) return r;
@@ -537,7 +537,9 @@ int cluster_block_device(crass_b200_ctx* c, const void* d_block, uint32_t cap, u
                  o_group = carve((size_t)cap * 4), o_gnum = carve(((size_t)cap + 2) * 4), o_gstart = carve(((size_t)cap + 2) * 4),
                  o_gfill = carve((size_t)cap * 4), o_members = carve((size_t)cap * 4), o_sorted = carve((size_t)cap * 4),
                  o_alive = carve(((size_t)cap + 2) * 4), o_plen = carve((2 * (size_t)cap + 2) * 4), o_psrc = carve(2 * (size_t)cap * 4),
-                 o_pbytes = carve(2 * (size_t)cap * (stride - 6) + 32), o_canon = carve((size_t)kStrListCap * 12), o_packed = carve((size_t)cap * 32);
+                 o_pbytes = carve(2 * (size_t)cap * (stride - 6) + 32), o_canon = carve((size_t)kStrListCap * 12), o_packed = carve((size_t)cap * 32),
+                 o_str_rep = carve((size_t)kStrListCap * 8), o_str_min = carve((size_t)kStrListCap * 8), o_str_slot = carve((size_t)kStrListCap * 4),
+                 o_spacked = carve((size_t)cap * 32), o_slens = carve((size_t)cap * 4);
     if (int r = c->d_cl_tail.reserve(at)) return r;
     uint8_t* tb = c->d_cl_tail.as<uint8_t>();
     cbk::ClusterArrays a{(const uint8_t*)d_block, cap, stride, c->d_cl_order.as<uint32_t>(), c->d_cl_koff.as<uint32_t>(),
@@ -547,16 +549,19 @@ int cluster_block_device(crass_b200_ctx* c, const void* d_block, uint32_t cap, u
     cbk::ClusterTail t{a, (uint32_t*)(tb + o_lens), (uint32_t*)(tb + o_runc), (uint32_t*)(tb + o_nruns), (uint32_t*)(tb + o_group),
                        (uint32_t*)(tb + o_gnum), (uint32_t*)(tb + o_gstart), (uint32_t*)(tb + o_gfill), (uint32_t*)(tb + o_members),
                        (uint32_t*)(tb + o_sorted), (uint32_t*)(tb + o_alive), (uint32_t*)(tb + o_plen), (uint32_t*)(tb + o_psrc),
-                       tb + o_pbytes, tb + o_canon, (ulonglong4*)(tb + o_packed), kmer_clust};
+                       tb + o_pbytes, tb + o_canon, (uint32_t*)(tb + o_str_rep), (uint32_t*)(tb + o_str_min), (uint32_t*)(tb + o_str_slot),
+                       (ulonglong4*)(tb + o_spacked), (uint32_t*)(tb + o_slens), (ulonglong4*)(tb + o_packed), kmer_clust};
     CUDA_TRY(cudaMemsetAsync(c->d_cl_info.p, 0, cbk::kInfoWords * 4, st));
     CUDA_TRY(cudaMemsetAsync(c->d_cl_tab.p, 0xFF, tab * 8, st));
     CUDA_TRY(cudaMemsetAsync(t.plen, 0, (2 * (size_t)cap + 2) * 4, st));
+    CUDA_TRY(cudaMemsetAsync(t.str_rep, 0xFF, (size_t)kStrListCap * 16, st));           // str_rep and str_min lie back to back
     const uint32_t per_dr128 = (cap + 127) / 128, per_dr256 = (cap + 1 + 255) / 256, warp_per_dr = (cap + 1 + 3) / 4;
     cbk::k_cl_rank<<<(cap + cbk::kClRankThreads) / cbk::kClRankThreads, cbk::kClRankThreads * cbk::kClRankParts, 0, st>>>(a);
     cbk::k_rank_scan<<<1, 1024, 0, st>>>(a.koff, cap + 1, a.info);                  // info[0] = n, written by k_cl_rank
     cbk::k_cl_keys<<<(cap * 32 + cbk::kClKeysThreads - 1) / cbk::kClKeysThreads, cbk::kClKeysThreads, 0, st>>>(a);
     cbk::k_cl_first<<<c->sm_count * 4, 256, 0, st>>>(a);
     cbk::k_cl_str_canon<<<kStrListCap / 128, 128, 0, st>>>(t);
+    cbk::k_cl_str_insert<<<kStrListCap / 128, 128, 0, st>>>(t);
     cbk::k_cl_str_first<<<kStrListCap / 128, 128, 0, st>>>(t);
     cbk::k_cl_runs<<<per_dr128, 128, 0, st>>>(t);
     cbk::k_cl_walk<<<per_dr128, 128, 0, st>>>(t);
@@ -572,7 +577,7 @@ int cluster_block_device(crass_b200_ctx* c, const void* d_block, uint32_t cap, u
     cbk::k_cl_place<<<per_dr256, 256, 0, st>>>(t);
     cbk::k_rank_scan<<<1, 1024, 0, st>>>(t.plen, 2 * cap + 1, a.info + cbk::kInfoPatterns);
     cbk::k_cl_emit<<<(2 * cap + 127) / 128, 128, 0, st>>>(t);
-    c->launches += 19;
+    c->launches += 20;
     CUDA_TRY(cudaGetLastError());
     // one round trip: header, info record, and as much of the pattern set as the last call needed (twice that, in fact)
     const size_t all_offs = 2 * (size_t)cap + 1, all_bytes = 2 * (size_t)cap * (stride - 6) + 16;

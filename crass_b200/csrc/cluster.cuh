@@ -2,8 +2,8 @@
 // patterns already are.  Included by kernels.cuh after K5's first kernels (k_cl_rank / k_cl_keys / k_cl_first), whose
 // arrays it continues from:
 //
-//   k_cl_str_canon / k_cl_str_first   the rare 11-mers with a letter outside A/C/G/T: first DR holding each (the host's
-//                                     string map, results.cpp resolve_str), by comparing their canonical bytes pairwise
+//   k_cl_str_canon / _insert / _first the rare 11-mers with a letter outside A/C/G/T: first DR holding each (the host's
+//                                     string map, results.cpp resolve_str), through a table keyed by their canonical bytes
 //   k_cl_runs                         pass B2: the k-mers of every DR folded into runs (first DR, count)
 //   k_cl_walk                         pass C: clusterDRReads' greedy, order-dependent group assignment
 //                                     (WorkHorse.cpp:1542-1625).  DR t only ever looks at groups of DRs before it, so the
@@ -45,6 +45,11 @@ struct ClusterTail {
     uint32_t* psrc;      // [2 cap]    pattern -> DR t, bit 31 = reverse complement
     uint8_t* pbytes;     // pattern bytes (+ 16 bytes of zeroed slack)
     uint8_t* canon;      // [str_cap * 12] canonical bytes of the string-keyed k-mers
+    uint32_t* str_rep;   // [2 str_cap] open-addressing table over the canonical bytes: entry that claimed the slot ...
+    uint32_t* str_min;   // [2 str_cap] ... and the smallest DR holding that k-mer
+    uint32_t* str_slot;  // [str_cap]   slot of entry i
+    ulonglong4* spacked; // [cap]      packed[] in sorted order
+    uint32_t* slens;     // [cap]      lens[] in sorted order
     ulonglong4* packed;  // [cap]      2-bit codes ((byte >> 1) & 3) of DR t: x, y = bases 0..31, 32..63; z, w = the same of its reverse complement
     uint32_t min_count;
     __device__ const uint8_t* dr(uint32_t t) const { return a.rec(a.order[t]) + 2; }
@@ -75,25 +80,33 @@ k_cl_str_canon(ClusterTail c) {
     for (uint32_t b = 0; b < 12; ++b) c.canon[(size_t)i * 12 + b] = out[b];
 }
 
+// (k-mer -> first DR) for the string-keyed k-mers: an open-addressing table keyed by the twelve canonical bytes; a slot
+// belongs to the entry that claimed it, later entries compare their bytes with the owner's (written by the kernel before)
+__global__ void __launch_bounds__(128)
+k_cl_str_insert(ClusterTail c) {
+    const uint32_t m = min(c.a.info[kInfoStr], c.a.str_cap);
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(c.canon);
+    const uint32_t w0 = w[3 * i], w1 = w[3 * i + 1], w2 = w[3 * i + 2];
+    const uint32_t mask = 2 * c.a.str_cap - 1;
+    uint32_t s = ((w0 * 0x9E3779B1u) ^ (w1 * 0x85EBCA6Bu) ^ (w2 * 0xC2B2AE35u));
+    s = (s ^ (s >> 15)) & mask;
+    for (;;) {
+        uint32_t cur = atomicCAS(&c.str_rep[s], 0xFFFFFFFFu, i);
+        if (cur == 0xFFFFFFFFu) cur = i;
+        if (cur == i || (w[3 * cur] == w0 && w[3 * cur + 1] == w1 && w[3 * cur + 2] == w2)) break;
+        s = (s + 1) & mask;
+    }
+    atomicMin(&c.str_min[s], c.a.str_tq[2 * i]);
+    c.str_slot[i] = s;
+}
+
 __global__ void __launch_bounds__(128)
 k_cl_str_first(ClusterTail c) {
-    __shared__ uint32_t tw[128 * 3], tt[128];
     const uint32_t m = min(c.a.info[kInfoStr], c.a.str_cap);
-    if (blockIdx.x * 128 >= m) return;
     const uint32_t i = blockIdx.x * 128 + threadIdx.x;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(c.canon);
-    uint32_t w0 = 0, w1 = 0, w2 = 0, best = 0xFFFFFFFFu;
-    if (i < m) { w0 = w[3 * i]; w1 = w[3 * i + 1]; w2 = w[3 * i + 2]; }
-    for (uint32_t j0 = 0; j0 < m; j0 += 128) {
-        __syncthreads();
-        const uint32_t j = j0 + threadIdx.x;
-        if (j < m) { tw[threadIdx.x * 3] = w[3 * j]; tw[threadIdx.x * 3 + 1] = w[3 * j + 1]; tw[threadIdx.x * 3 + 2] = w[3 * j + 2]; tt[threadIdx.x] = c.a.str_tq[2 * j]; }
-        __syncthreads();
-        const uint32_t lim = min(128u, m - j0);
-        for (uint32_t k = 0; k < lim; ++k)
-            if (tw[3 * k] == w0 && tw[3 * k + 1] == w1 && tw[3 * k + 2] == w2) best = min(best, tt[k]);
-    }
-    if (i < m) c.a.first[c.a.str_tq[2 * i + 1]] = best;
+    if (i < m) c.a.first[c.a.str_tq[2 * i + 1]] = c.str_min[c.str_slot[i]];
 }
 
 // pass B2.  first[q] >= t means "never seen before this DR": such k-mers change no tally in the walk, so runs reach across them.
@@ -216,7 +229,7 @@ k_cl_group_sort(ClusterTail c) {
         before += (lm < len || (lm == len && m < t)) ? 1u : 0u;
     }
     before = __reduce_add_sync(0xFFFFFFFFu, before);
-    if (lane == 0) c.sorted[gs + before] = t;
+    if (lane == 0) { c.sorted[gs + before] = t; c.spacked[gs + before] = c.packed[t]; c.slens[gs + before] = len; }
 }
 
 // pass D on the 2-bit codes (DRs up to 64 bases: every default-geometry token).  b's code sits in registers and slides by one
@@ -236,16 +249,15 @@ k_cl_dead_packed(ClusterTail c) {
     if (s == n && lane == 0) c.alive[n] = 0;
     if (s >= n) return;
     const uint32_t tb = c.sorted[s];
-    const uint32_t lb = c.lens[tb];
-    const ulonglong4 pb = c.packed[tb];
+    const uint32_t lb = c.slens[s];
+    const ulonglong4 pb = c.spacked[s];
     const uint32_t gs = c.gstart[cl_group_of(c, tb)];
     bool dead = false;
     for (uint32_t i0 = gs; i0 < s; i0 += 32) {
         const uint32_t i = i0 + lane;
         if (i < s) {
-            const uint32_t ta = c.sorted[i];
-            const uint32_t la = c.lens[ta];                      // <= lb by the order
-            const ulonglong4 pa = c.packed[ta];
+            const uint32_t la = c.slens[i];                      // <= lb by the order
+            const ulonglong4 pa = c.spacked[i];
             const unsigned long long m0 = la >= 32 ? ~0ull : (1ull << (2 * la)) - 1ull;
             const unsigned long long m1 = la <= 32 ? 0ull : la >= 64 ? ~0ull : (1ull << (2 * (la - 32))) - 1ull;
             unsigned long long b0 = pb.x, b1 = pb.y;
@@ -254,7 +266,7 @@ k_cl_dead_packed(ClusterTail c) {
                 const bool rc = (((b0 ^ pa.z) & m0) | ((b1 ^ pa.w) & m1)) == 0;
                 if (fw || rc) {
                     const uint8_t* bg = c.dr(tb);
-                    const uint8_t* ag = c.dr(ta);
+                    const uint8_t* ag = c.dr(c.sorted[i]);
                     dead = (fw && cl_bytes_at(bg, at, ag, la, false)) || (rc && cl_bytes_at(bg, at, ag, la, true));
                 }
                 b0 = (b0 >> 2) | (b1 << 62);
