@@ -119,6 +119,7 @@ struct crass_b200_ctx {
     DevBuf d_ac_bitmap_small;            // folded copy of the q-gram bitmap for k_ac_filter_packed (0 bytes when unused)
     DevBuf d_cand_mask;                  // K2 fast path: per candidate, the aligned 16-mers that can belong to an occurrence
     // K5 (clustering passes A/B on the token block): device arrays and their pinned host mirrors
+    DevBuf d_cl_ckeys;
     DevBuf d_cl_order, d_cl_koff, d_cl_keys, d_cl_first, d_cl_tab, d_cl_info;
     DevBuf d_cl_group, d_cl_chain, d_cl_next, d_cl_odd, d_cl_dead, d_cl_str;
     PinnedBuf h_cl_block, h_cl_order, h_cl_keys, h_cl_first, h_cl_info, h_cl_group, h_cl_dead, h_cl_str;
@@ -217,7 +218,7 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
                       &c->d_ac_bitmap, &c->d_ac_keys, &c->d_ac_skeys, &c->d_ac_shead, &c->d_ac_pnext, &c->d_ac_poffs, &c->d_ac_pbytes,
                       &c->d_rank, &c->d_hits_sorted, &c->d_cand_counts, &c->d_cand_mask, &c->d_ac_bitmap_small, &c->d_packed,
                       &c->d_cl_order, &c->d_cl_koff, &c->d_cl_keys, &c->d_cl_first, &c->d_cl_tab, &c->d_cl_info,
-                      &c->d_cl_group, &c->d_cl_chain, &c->d_cl_next, &c->d_cl_odd, &c->d_cl_dead, &c->d_cl_str, &c->d_ac_ones, &c->d_cl_tail};
+                      &c->d_cl_group, &c->d_cl_chain, &c->d_cl_next, &c->d_cl_odd, &c->d_cl_dead, &c->d_cl_str, &c->d_ac_ones, &c->d_cl_tail, &c->d_cl_ckeys};
     for (DevBuf* b : bufs) b->release();
     for (PinnedBuf* b : {&c->h_cl_block, &c->h_cl_order, &c->h_cl_keys, &c->h_cl_first, &c->h_cl_info, &c->h_ac_stage,
                          &c->h_cl_group, &c->h_cl_dead, &c->h_cl_str, &c->h_cl_pat}) b->release();
@@ -391,6 +392,7 @@ int cluster_block_host_passes(crass_b200_ctx* c, const void* d_block, uint32_t c
     size_t tab = 1024;
     while (tab < 2 * max_kmers) tab <<= 1;
     if (int r = c->d_cl_order.reserve((size_t)cap * 4)) return r;
+    if (int r = c->d_cl_ckeys.reserve((size_t)cap * 4 + 16)) return r;
     if (int r = c->d_cl_koff.reserve(((size_t)cap + 1025) * 4)) return r;
     if (int r = c->d_cl_keys.reserve(max_kmers * 4 + 16)) return r;
     if (int r = c->d_cl_first.reserve(max_kmers * 4 + 16)) return r;
@@ -405,14 +407,15 @@ int cluster_block_host_passes(crass_b200_ctx* c, const void* d_block, uint32_t c
     cbk::ClusterArrays a{(const uint8_t*)d_block, cap, stride, c->d_cl_order.as<uint32_t>(), c->d_cl_koff.as<uint32_t>(),
                          c->d_cl_keys.as<uint32_t>(), c->d_cl_first.as<uint32_t>(), c->d_cl_tab.as<uint32_t>(),
                          c->d_cl_tab.as<uint32_t>() + tab, (uint32_t)(tab - 1), c->d_cl_info.as<uint32_t>(),
-                         c->d_cl_str.as<uint32_t>(), kStrListCap, kClusterDeviceMax};
+                         c->d_cl_str.as<uint32_t>(), kStrListCap, c->d_cl_ckeys.as<uint32_t>(), kClusterDeviceMax};
     CUDA_TRY(cudaMemsetAsync(c->d_cl_info.p, 0, 16, st));
     CUDA_TRY(cudaMemsetAsync(c->d_cl_tab.p, 0xFF, tab * 8, st));
+    cbk::k_cl_gather<<<(cap + 255) / 256, 256, 0, st>>>(a);
     cbk::k_cl_rank<<<(cap + cbk::kClRankThreads) / cbk::kClRankThreads, cbk::kClRankThreads * cbk::kClRankParts, 0, st>>>(a);
     cbk::k_rank_scan<<<1, 1024, 0, st>>>(a.koff, cap + 1, a.info);                  // info[0] = n, written by k_cl_rank
     cbk::k_cl_keys<<<(cap * 32 + cbk::kClKeysThreads - 1) / cbk::kClKeysThreads, cbk::kClKeysThreads, 0, st>>>(a);
     cbk::k_cl_first<<<c->sm_count * 4, 256, 0, st>>>(a);
-    c->launches += 4;
+    c->launches += 5;
     CUDA_TRY(cudaGetLastError());
     cbh::prewake_cluster_workers(1000);                        // the host passes start in a few hundred microseconds
     // two round trips: the sizes first, then exactly the records and array entries that exist
@@ -522,6 +525,7 @@ int cluster_block_device(crass_b200_ctx* c, const void* d_block, uint32_t cap, u
     while (tab < 2 * max_kmers) tab <<= 1;
     const uint32_t kStrListCap = 16384;                // string-keyed 11-mers the device resolves (a power of two)
     if (int r = c->d_cl_order.reserve((size_t)cap * 4)) return r;
+    if (int r = c->d_cl_ckeys.reserve((size_t)cap * 4 + 16)) return r;
     if (int r = c->d_cl_koff.reserve(((size_t)cap + 1025) * 4)) return r;
     if (int r = c->d_cl_keys.reserve(max_kmers * 4 + 16)) return r;
     if (int r = c->d_cl_first.reserve(max_kmers * 4 + 16)) return r;
@@ -533,10 +537,10 @@ int cluster_block_device(crass_b200_ctx* c, const void* d_block, uint32_t cap, u
     // the tail's arrays, carved from one allocation
     size_t at = 0;
     auto carve = [&](size_t bytes) { const size_t o = at; at += (bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_lens = carve((size_t)cap * 4), o_runc = carve(max_kmers * 4 + 16), o_nruns = carve((size_t)cap * 4),
+    const size_t o_lens = carve((size_t)cap * 4), o_impure = carve((size_t)cap), o_runc = carve(max_kmers * 4 + 16), o_nruns = carve((size_t)cap * 4),
                  o_group = carve((size_t)cap * 4), o_gnum = carve(((size_t)cap + 2) * 4), o_gstart = carve(((size_t)cap + 2) * 4),
                  o_gfill = carve((size_t)cap * 4), o_members = carve((size_t)cap * 4), o_sorted = carve((size_t)cap * 4),
-                 o_alive = carve(((size_t)cap + 2) * 4), o_plen = carve((2 * (size_t)cap + 2) * 4), o_psrc = carve(2 * (size_t)cap * 4),
+                 o_alive = carve(((size_t)cap + 2) * 4), o_alive1 = carve(((size_t)cap + 2) * 4), o_listed = carve((size_t)cap * 4), o_plen = carve((2 * (size_t)cap + 2) * 4), o_psrc = carve(2 * (size_t)cap * 4),
                  o_pbytes = carve(2 * (size_t)cap * (stride - 6) + 32), o_canon = carve((size_t)kStrListCap * 12), o_packed = carve((size_t)cap * 32),
                  o_str_rep = carve((size_t)kStrListCap * 8), o_str_min = carve((size_t)kStrListCap * 8), o_str_slot = carve((size_t)kStrListCap * 4),
                  o_spacked = carve((size_t)cap * 32), o_slens = carve((size_t)cap * 4);
@@ -545,10 +549,10 @@ int cluster_block_device(crass_b200_ctx* c, const void* d_block, uint32_t cap, u
     cbk::ClusterArrays a{(const uint8_t*)d_block, cap, stride, c->d_cl_order.as<uint32_t>(), c->d_cl_koff.as<uint32_t>(),
                          c->d_cl_keys.as<uint32_t>(), c->d_cl_first.as<uint32_t>(), c->d_cl_tab.as<uint32_t>(),
                          c->d_cl_tab.as<uint32_t>() + tab, (uint32_t)(tab - 1), c->d_cl_info.as<uint32_t>(),
-                         c->d_cl_str.as<uint32_t>(), kStrListCap, kClusterDeviceMax};
-    cbk::ClusterTail t{a, (uint32_t*)(tb + o_lens), (uint32_t*)(tb + o_runc), (uint32_t*)(tb + o_nruns), (uint32_t*)(tb + o_group),
+                         c->d_cl_str.as<uint32_t>(), kStrListCap, c->d_cl_ckeys.as<uint32_t>(), kClusterDeviceMax};
+    cbk::ClusterTail t{a, (uint32_t*)(tb + o_lens), tb + o_impure, (uint32_t*)(tb + o_runc), (uint32_t*)(tb + o_nruns), (uint32_t*)(tb + o_group),
                        (uint32_t*)(tb + o_gnum), (uint32_t*)(tb + o_gstart), (uint32_t*)(tb + o_gfill), (uint32_t*)(tb + o_members),
-                       (uint32_t*)(tb + o_sorted), (uint32_t*)(tb + o_alive), (uint32_t*)(tb + o_plen), (uint32_t*)(tb + o_psrc),
+                       (uint32_t*)(tb + o_sorted), (uint32_t*)(tb + o_alive), (uint32_t*)(tb + o_alive1), (uint32_t*)(tb + o_listed), (uint32_t*)(tb + o_plen), (uint32_t*)(tb + o_psrc),
                        tb + o_pbytes, tb + o_canon, (uint32_t*)(tb + o_str_rep), (uint32_t*)(tb + o_str_min), (uint32_t*)(tb + o_str_slot),
                        (ulonglong4*)(tb + o_spacked), (uint32_t*)(tb + o_slens), (ulonglong4*)(tb + o_packed), kmer_clust};
     CUDA_TRY(cudaMemsetAsync(c->d_cl_info.p, 0, cbk::kInfoWords * 4, st));
@@ -556,6 +560,7 @@ int cluster_block_device(crass_b200_ctx* c, const void* d_block, uint32_t cap, u
     CUDA_TRY(cudaMemsetAsync(t.plen, 0, (2 * (size_t)cap + 2) * 4, st));
     CUDA_TRY(cudaMemsetAsync(t.str_rep, 0xFF, (size_t)kStrListCap * 16, st));           // str_rep and str_min lie back to back
     const uint32_t per_dr128 = (cap + 127) / 128, per_dr256 = (cap + 1 + 255) / 256, warp_per_dr = (cap + 1 + 3) / 4;
+    cbk::k_cl_gather<<<(cap + 255) / 256, 256, 0, st>>>(a);
     cbk::k_cl_rank<<<(cap + cbk::kClRankThreads) / cbk::kClRankThreads, cbk::kClRankThreads * cbk::kClRankParts, 0, st>>>(a);
     cbk::k_rank_scan<<<1, 1024, 0, st>>>(a.koff, cap + 1, a.info);                  // info[0] = n, written by k_cl_rank
     cbk::k_cl_keys<<<(cap * 32 + cbk::kClKeysThreads - 1) / cbk::kClKeysThreads, cbk::kClKeysThreads, 0, st>>>(a);
@@ -571,13 +576,19 @@ int cluster_block_device(crass_b200_ctx* c, const void* d_block, uint32_t cap, u
     cbk::k_rank_scan<<<1, 1024, 0, st>>>(t.gstart, cap + 1, a.info);
     cbk::k_cl_members<<<per_dr256, 256, 0, st>>>(t);
     cbk::k_cl_group_sort<<<warp_per_dr, 128, 0, st>>>(t);
-    if (stride <= 70) cbk::k_cl_dead_packed<<<warp_per_dr, 128, 0, st>>>(t);          // tokens of at most 64 bases: compared as 2-bit codes
+    if (stride <= 70) {                                     // tokens of at most 64 bases: compared as 2-bit codes, in two rounds
+        cbk::k_cl_dead_packed<1><<<warp_per_dr, 128, 0, st>>>(t);
+        cbk::k_rank_scan<<<1, 1024, 0, st>>>(t.alive1, cap + 1, a.info);
+        cbk::k_cl_dead_list<<<per_dr256, 256, 0, st>>>(t);
+        cbk::k_cl_dead_packed<2><<<warp_per_dr, 128, 0, st>>>(t);
+        c->launches += 3;
+    }
     else cbk::k_cl_dead<<<warp_per_dr, 128, 4 * stride, st>>>(t);
     cbk::k_rank_scan<<<1, 1024, 0, st>>>(t.alive, cap + 1, a.info);
     cbk::k_cl_place<<<per_dr256, 256, 0, st>>>(t);
     cbk::k_rank_scan<<<1, 1024, 0, st>>>(t.plen, 2 * cap + 1, a.info + cbk::kInfoPatterns);
     cbk::k_cl_emit<<<(2 * cap + 127) / 128, 128, 0, st>>>(t);
-    c->launches += 20;
+    c->launches += 21;
     CUDA_TRY(cudaGetLastError());
     // one round trip: header, info record, and as much of the pattern set as the last call needed (twice that, in fact)
     const size_t all_offs = 2 * (size_t)cap + 1, all_bytes = 2 * (size_t)cap * (stride - 6) + 16;

@@ -32,6 +32,7 @@ enum : uint32_t { kClFlagLetter = 1, kClFlagWalk = 2, kClFlagEmpty = 4, kClFlagS
 struct ClusterTail {
     ClusterArrays a;
     uint32_t* lens;      // [cap]      length of DR t
+    uint8_t* impure;     // [cap]      1 = DR t holds a letter outside A/C/G/T
     uint32_t* runc;      // [k-mers]   length of each run (the first DR of a run overwrites a.first in place)
     uint32_t* nruns;     // [cap]
     uint32_t* group;     // [cap]      founder of DR t's group + 1; 0 = not known yet
@@ -41,6 +42,8 @@ struct ClusterTail {
     uint32_t* members;   // [cap]      DRs group by group, no order inside a group
     uint32_t* sorted;    // [cap]      DRs in (group, length, token position) order
     uint32_t* alive;     // [cap + 1]  survivor flags in that order -> exclusive scan
+    uint32_t* alive1;    // [cap + 1]  the same after the first round of pass D
+    uint32_t* listed;    // [cap]      sorted positions that survived the first round
     uint32_t* plen;      // [2 cap + 1] pattern lengths -> offsets
     uint32_t* psrc;      // [2 cap]    pattern -> DR t, bit 31 = reverse complement
     uint8_t* pbytes;     // pattern bytes (+ 16 bytes of zeroed slack)
@@ -49,7 +52,7 @@ struct ClusterTail {
     uint32_t* str_min;   // [2 str_cap] ... and the smallest DR holding that k-mer
     uint32_t* str_slot;  // [str_cap]   slot of entry i
     ulonglong4* spacked; // [cap]      packed[] in sorted order
-    uint32_t* slens;     // [cap]      lens[] in sorted order
+    uint32_t* slens;     // [cap]      lens[] in sorted order; bit 31 = the DR holds a letter outside A/C/G/T (code matches must be confirmed on the bytes)
     ulonglong4* packed;  // [cap]      2-bit codes ((byte >> 1) & 3) of DR t: x, y = bases 0..31, 32..63; z, w = the same of its reverse complement
     uint32_t min_count;
     __device__ const uint8_t* dr(uint32_t t) const { return a.rec(a.order[t]) + 2; }
@@ -122,9 +125,11 @@ k_cl_runs(ClusterTail c) {
     c.group[t] = 0;
     uint32_t flags = len ? 0u : (uint32_t)kClFlagEmpty;
     unsigned long long f0 = 0, f1 = 0, r0 = 0, r1 = 0;
+    bool impure = false;
     for (uint32_t i = 0; i < len; ++i) {
         const uint8_t b = dr[i];
         if (b >= 128 || c_comp_tab[c_comp_tab[b & 127]] != b) flags |= kClFlagLetter;   // 'U' -> 'A' -> 'T': containment on both strands is no longer transitive
+        impure |= cl_code(b) < 0;
         if (i < 64) {
             const unsigned long long cf = (b >> 1) & 3u, cr = (c_comp_tab[b & 127] >> 1) & 3u;
             const uint32_t j = len - 1 - i;                      // where the complement of base i sits in the reverse complement
@@ -133,6 +138,7 @@ k_cl_runs(ClusterTail c) {
         }
     }
     c.packed[t] = make_ulonglong4(f0, f1, r0, r1);
+    c.impure[t] = impure ? 1 : 0;
     if (flags) atomicOr(&c.a.info[kInfoFlags], flags);
     const uint32_t q0 = c.a.koff[t], q1 = c.a.koff[t + 1];
     uint32_t out = q0;
@@ -229,7 +235,7 @@ k_cl_group_sort(ClusterTail c) {
         before += (lm < len || (lm == len && m < t)) ? 1u : 0u;
     }
     before = __reduce_add_sync(0xFFFFFFFFu, before);
-    if (lane == 0) { c.sorted[gs + before] = t; c.spacked[gs + before] = c.packed[t]; c.slens[gs + before] = len; }
+    if (lane == 0) { c.sorted[gs + before] = t; c.spacked[gs + before] = c.packed[t]; c.slens[gs + before] = len | (c.impure[t] ? 0x80000000u : 0u); }
 }
 
 // pass D on the 2-bit codes (DRs up to 64 bases: every default-geometry token).  b's code sits in registers and slides by one
@@ -242,21 +248,34 @@ __device__ __forceinline__ bool cl_bytes_at(const uint8_t* b, uint32_t at, const
     return true;
 }
 
+// Most members die, and most of those to one of the shortest members of their group, so the test runs in two rounds:
+// PHASE 1 tries only the first kClDeadFirst members of the group; what survives that (a superset of the real survivors) is
+// listed (k_cl_dead_list, after a scan of the flags), and PHASE 2 tries every listed earlier member on the listed DRs only.
+constexpr uint32_t kClDeadFirst = 64;
+
+template <int PHASE>
 __global__ void __launch_bounds__(128)
 k_cl_dead_packed(ClusterTail c) {
     const uint32_t n = c.a.n();
     const uint32_t s = (blockIdx.x * 128 + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (s == n && lane == 0) c.alive[n] = 0;
     if (s >= n) return;
+    if (PHASE == 2 && c.alive1[s + 1] == c.alive1[s]) { if (lane == 0) c.alive[s] = 0; return; }     // died in phase 1 (alive1 = scan of its flags)
     const uint32_t tb = c.sorted[s];
-    const uint32_t lb = c.slens[s];
+    const uint32_t lb = c.slens[s] & 0x7FFFFFFFu;
+    const bool b_impure = (c.slens[s] >> 31) != 0;
     const ulonglong4 pb = c.spacked[s];
     const uint32_t gs = c.gstart[cl_group_of(c, tb)];
+    // phase 1: positions [gs, min(s, gs + 64)) of the sorted order; phase 2: entries [alive1[gs], alive1[s]) of the list
+    const uint32_t j_begin = PHASE == 1 ? gs : c.alive1[gs];
+    const uint32_t j_end = PHASE == 1 ? min(s, gs + kClDeadFirst) : c.alive1[s];
     bool dead = false;
-    for (uint32_t i0 = gs; i0 < s; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        if (i < s) {
-            const uint32_t la = c.slens[i];                      // <= lb by the order
+    for (uint32_t j0 = j_begin; j0 < j_end; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        if (j < j_end) {
+            const uint32_t i = PHASE == 1 ? j : c.listed[j];
+            const uint32_t la = c.slens[i] & 0x7FFFFFFFu;        // <= lb by the order
+            const bool confirm = b_impure || (c.slens[i] >> 31) != 0;   // A, C, G, T have four different codes: nothing to confirm between two such DRs
             const ulonglong4 pa = c.spacked[i];
             const unsigned long long m0 = la >= 32 ? ~0ull : (1ull << (2 * la)) - 1ull;
             const unsigned long long m1 = la <= 32 ? 0ull : la >= 64 ? ~0ull : (1ull << (2 * (la - 32))) - 1ull;
@@ -264,18 +283,28 @@ k_cl_dead_packed(ClusterTail c) {
             for (uint32_t at = 0; at + la <= lb && !dead; ++at) {
                 const bool fw = (((b0 ^ pa.x) & m0) | ((b1 ^ pa.y) & m1)) == 0;
                 const bool rc = (((b0 ^ pa.z) & m0) | ((b1 ^ pa.w) & m1)) == 0;
-                if (fw || rc) {
+                if ((fw || rc) && confirm) {
                     const uint8_t* bg = c.dr(tb);
                     const uint8_t* ag = c.dr(c.sorted[i]);
                     dead = (fw && cl_bytes_at(bg, at, ag, la, false)) || (rc && cl_bytes_at(bg, at, ag, la, true));
-                }
+                } else dead = fw || rc;
                 b0 = (b0 >> 2) | (b1 << 62);
                 b1 >>= 2;
             }
         }
         if (__any_sync(0xFFFFFFFFu, dead)) { dead = true; break; }
     }
-    if (lane == 0) c.alive[s] = dead ? 0u : 1u;
+    if (lane == 0) {
+        if (PHASE == 1) { c.alive1[s] = dead ? 0u : 1u; if (s + 1 == n) c.alive1[n] = 0; }
+        else c.alive[s] = dead ? 0u : 1u;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_cl_dead_list(ClusterTail c) {
+    const uint32_t n = c.a.n();
+    const uint32_t s = blockIdx.x * 256 + threadIdx.x;
+    if (s < n && c.alive1[s + 1] != c.alive1[s]) c.listed[c.alive1[s]] = s;
 }
 
 // pass D on the bytes (tokens longer than 64 bases: wider DR bounds than the default).  One warp per DR b, lanes over the members in front of it; containment is transitive on both strands (for the

@@ -259,6 +259,7 @@ struct ClusterArrays {
     uint32_t* info;              // [0] n, [1] total k-mers, [2] k-mers that need the string map
     uint32_t* str_tq;            // (t, q) of the first str_cap of those, in no particular order
     uint32_t str_cap;
+    uint32_t* ckeys;             // [cap] the order keys gathered from the records (k_cl_gather), what k_cl_rank reads
     uint32_t max_n;              // lists longer than this are left to the host (the rank kernel is O(n^2)): the kernels then see n = 0
     __device__ uint32_t n() const { const uint32_t k = min(*reinterpret_cast<const uint32_t*>(block), cap); return k > max_n ? 0u : k; }
     __device__ const uint8_t* rec(uint32_t slot) const { return block + kTokenBlockHeader + (size_t)slot * stride; }
@@ -267,10 +268,16 @@ struct ClusterArrays {
 };
 
 // token position of every record = number of records with a smaller key (keys are distinct: one token per first read).
-// O(n^2), so it is spread wide: a CTA ranks 64 records, four threads per record each counting a quarter of every
-// 256-key tile (read as 16-byte vectors from shared memory).
+// O(n^2), so it is spread wide: a CTA ranks 64 records, eight threads per record each counting an eighth of every
+// 512-key tile (read as 16-byte vectors from shared memory).
+__global__ void __launch_bounds__(256)
+k_cl_gather(ClusterArrays a) {                       // the keys sit 64 bytes apart in the block: read them once, not once per CTA
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i < a.n()) a.ckeys[i] = a.key_of(i);
+}
+
 constexpr uint32_t kClRankThreads = 64;              // records per CTA
-constexpr uint32_t kClRankParts = 4;
+constexpr uint32_t kClRankParts = 8;
 
 __global__ void __launch_bounds__(kClRankThreads * kClRankParts)
 k_cl_rank(ClusterArrays a) {
@@ -284,11 +291,11 @@ k_cl_rank(ClusterArrays a) {
         if (i == 0 && part == 0) a.info[0] = n;
         return;
     }
-    const uint32_t mine = i < n ? a.key_of(i) : 0u;
+    const uint32_t mine = i < n ? a.ckeys[i] : 0u;
     uint32_t rank = 0;
     for (uint32_t j0 = 0; j0 < n; j0 += kClRankThreads * kClRankParts) {
         __syncthreads();
-        tile[threadIdx.x] = j0 + threadIdx.x < n ? a.key_of(j0 + threadIdx.x) : 0xFFFFFFFFu;   // padding never counts
+        tile[threadIdx.x] = j0 + threadIdx.x < n ? a.ckeys[j0 + threadIdx.x] : 0xFFFFFFFFu;   // padding never counts
         __syncthreads();
         const uint4* t4 = reinterpret_cast<const uint4*>(tile + part * kClRankThreads);
 #pragma unroll
@@ -300,7 +307,9 @@ k_cl_rank(ClusterArrays a) {
     partial[part][il] = rank;
     __syncthreads();
     if (part != 0) return;
-    rank = partial[0][il] + partial[1][il] + partial[2][il] + partial[3][il];
+    rank = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kClRankParts; ++k) rank += partial[k][il];
     if (i < n) {
         a.order[rank] = i;
         const uint32_t len = a.len_of(i);

@@ -416,7 +416,7 @@ def test_clustering_passes_on_the_device_match_the_host(ctx, P):
         assert (cnt, fl) == (cnt_h, fl_h) == (len(uniq), 0)
         assert got == want, (n_base, n_var, alphabet, lo, hi)
         if (alphabet == b"ACGT" or len(uniq) < 2000) and b"U" not in alphabet and len(uniq) <= 32768:
-            assert ctx.launch_count - before == 20                        # really the kernels, not a quiet detour over the host (which lists with more than 16384 string-keyed k-mers take)
+            assert ctx.launch_count - before == (24 if stride <= 70 else 21)                        # really the kernels, not a quiet detour over the host (which lists with more than 16384 string-keyed k-mers take)
         for mode in ("device-passes", "device-reduce"):                  # the round-1 splits: first passes (and pass D) on the device, rest on the host
             os.environ["CRASS_B200_CLUSTER"] = mode
             try:
@@ -466,7 +466,7 @@ def test_group_walk_on_the_device_follows_long_dependency_chains(ctx, P):
         want, _, _ = api.non_redundant_patterns_from_block(blk, cap, stride, 6)
         before = ctx.launch_count
         got, cnt, fl = ctx.cluster_block_patterns_dev(torch.from_numpy(blk).to(dev), cap, stride, 6)
-        assert ctx.launch_count - before == 20 and (cnt, fl) == (len(uniq), 0)
+        assert ctx.launch_count - before == 24 and (cnt, fl) == (len(uniq), 0)
         assert got == want, (n_seq, n_win, step)
 
 
