@@ -120,6 +120,7 @@ struct crass_b200_ctx {
     DevBuf d_cand_mask;                  // K2 fast path: per candidate, the aligned 16-mers that can belong to an occurrence
     // K5 (clustering passes A/B on the token block): device arrays and their pinned host mirrors
     DevBuf d_cl_ckeys;
+    DevBuf d_ticket;                     // work counter of the long-read kernel
     DevBuf d_cl_order, d_cl_koff, d_cl_keys, d_cl_first, d_cl_tab, d_cl_info;
     DevBuf d_cl_group, d_cl_chain, d_cl_next, d_cl_odd, d_cl_dead, d_cl_str;
     PinnedBuf h_cl_block, h_cl_order, h_cl_keys, h_cl_first, h_cl_info, h_cl_group, h_cl_dead, h_cl_str;
@@ -218,7 +219,7 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
                       &c->d_ac_bitmap, &c->d_ac_keys, &c->d_ac_skeys, &c->d_ac_shead, &c->d_ac_pnext, &c->d_ac_poffs, &c->d_ac_pbytes,
                       &c->d_rank, &c->d_hits_sorted, &c->d_cand_counts, &c->d_cand_mask, &c->d_ac_bitmap_small, &c->d_packed,
                       &c->d_cl_order, &c->d_cl_koff, &c->d_cl_keys, &c->d_cl_first, &c->d_cl_tab, &c->d_cl_info,
-                      &c->d_cl_group, &c->d_cl_chain, &c->d_cl_next, &c->d_cl_odd, &c->d_cl_dead, &c->d_cl_str, &c->d_ac_ones, &c->d_cl_tail, &c->d_cl_ckeys};
+                      &c->d_cl_group, &c->d_cl_chain, &c->d_cl_next, &c->d_cl_odd, &c->d_cl_dead, &c->d_cl_str, &c->d_ac_ones, &c->d_cl_tail, &c->d_cl_ckeys, &c->d_ticket};
     for (DevBuf* b : bufs) b->release();
     for (PinnedBuf* b : {&c->h_cl_block, &c->h_cl_order, &c->h_cl_keys, &c->h_cl_first, &c->h_cl_info, &c->h_ac_stage,
                          &c->h_cl_group, &c->h_cl_dead, &c->h_cl_str, &c->h_cl_pat}) b->release();
@@ -808,7 +809,7 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
     const bool geometry_ok = o.window == 8 && cb::window_skips(o) == 8 && o.low_dr + o.low_spacer == 49 && o.high_dr + o.high_spacer == 97;
     if (geometry_ok && max_read_len > 304 && max_read_len <= 65536 && (((uintptr_t)d_bases) & 15) == 0 && !(force && !strcmp(force, "generic"))) {
         const uint32_t words = max_read_len / 16 + 32;
-        const size_t smem = (size_t)cbk::kLongWarps * 2 * words * sizeof(uint32_t);
+        const size_t smem = (size_t)cbk::kLongWarps * words * sizeof(uint32_t);
         CUDA_TRY(cudaFuncSetAttribute(cbk::k_dr_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 1;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbk::k_dr_long, cbk::kLongWarps * 32, smem));
@@ -817,8 +818,10 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
         if (int r = c->d_scratch.reserve((size_t)blocks * cbk::kLongWarps * 2 * cap * sizeof(uint32_t))) return r;
         uint32_t* keep = nullptr;
         if (int r = keep_stream(&keep)) return r;
+        if (int r = c->d_ticket.reserve(16)) return r;
+        CUDA_TRY(cudaMemsetAsync(c->d_ticket.p, 0, 16, st));
         cbk::k_dr_long<<<blocks, cbk::kLongWarps * 32, smem, st>>>(d_bases, d_offsets, n_reads, o, d_found, sink, c->d_scratch.as<uint32_t>(), cap,
-                                                                   c->d_error.as<int>(), words, keep);
+                                                                   c->d_error.as<int>(), words, keep, c->d_ticket.as<uint32_t>());
         c->launches++;
         CUDA_TRY(cudaGetLastError());
         return 0;

@@ -238,17 +238,30 @@ template <class Seq>
 CB_HD int osa_distance_bitpar(const Seq& s, uint32_t a0, uint32_t n, uint32_t b0, uint32_t m) {
     const bool usable = !(n == 0 || m == 0 || n > 64);
     if (!usable) { n = 0; m = 0; }
-    uint64_t p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0;
+    // match vectors, built as two 32-bit halves (a variable 64-bit shift and five 64-bit selects per byte were a fifth of
+    // the long-read kernel's instructions)
+    uint32_t l0 = 0, l1 = 0, l2 = 0, l3 = 0, l4 = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
     bool bad = !usable;
     const uint32_t n_loop = uniform_bound(n);
-    for (uint32_t i = 0; i < n_loop; ++i) {
+    const uint32_t n_lo = n_loop < 32 ? n_loop : 32;
+    for (uint32_t i = 0; i < n_lo; ++i) {
         if (i < n) {
             const int k = osa_slot(s[a0 + i]);
-            const uint64_t bit = 1ull << i;
+            const uint32_t bit = 1u << i;
             bad |= k < 0;
-            p0 |= k == 0 ? bit : 0; p1 |= k == 1 ? bit : 0; p2 |= k == 2 ? bit : 0; p3 |= k == 3 ? bit : 0; p4 |= k == 4 ? bit : 0;
+            l0 |= k == 0 ? bit : 0; l1 |= k == 1 ? bit : 0; l2 |= k == 2 ? bit : 0; l3 |= k == 3 ? bit : 0; l4 |= k == 4 ? bit : 0;
         }
     }
+    for (uint32_t i = 32; i < n_loop; ++i) {
+        if (i < n) {
+            const int k = osa_slot(s[a0 + i]);
+            const uint32_t bit = 1u << (i - 32);
+            bad |= k < 0;
+            h0 |= k == 0 ? bit : 0; h1 |= k == 1 ? bit : 0; h2 |= k == 2 ? bit : 0; h3 |= k == 3 ? bit : 0; h4 |= k == 4 ? bit : 0;
+        }
+    }
+    const uint64_t p0 = l0 | ((uint64_t)h0 << 32), p1 = l1 | ((uint64_t)h1 << 32), p2 = l2 | ((uint64_t)h2 << 32),
+                   p3 = l3 | ((uint64_t)h3 << 32), p4 = l4 | ((uint64_t)h4 << 32);
     const uint64_t top = n ? 1ull << (n - 1) : 0;
     uint64_t vp = n >= 64 ? ~0ull : ((1ull << n) - 1ull), vn = 0, d0 = 0, pm_prev = 0;
     int score = (int)n;

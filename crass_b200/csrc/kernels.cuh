@@ -1118,19 +1118,24 @@ k_dr_exact_staged(const uint8_t* __restrict__ bases, const uint64_t* __restrict_
 // ---- K1 for long reads: one warp per read (dr_long.cuh) -------------------------------------------------------
 constexpr int kLongWarps = 4;
 
-__global__ void __launch_bounds__(kLongWarps * 32)
+__global__ void __launch_bounds__(kLongWarps * 32, 10)
 k_dr_long(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads, Params o,
           uint8_t* __restrict__ found, HitSink sink, uint32_t* __restrict__ ss_scratch, uint32_t ss_cap, int* __restrict__ error_flag,
-          uint32_t words_per_warp, uint32_t* __restrict__ keep) {
+          uint32_t words_per_warp, uint32_t* __restrict__ keep, uint32_t* __restrict__ ticket) {
     extern __shared__ uint32_t long_smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    uint32_t* P = long_smem + (size_t)warp * 2 * words_per_warp;      // packed, aligned to the 16-byte grid of the batch
-    uint32_t* S = P + words_per_warp;                                   // packed, aligned to the read start, zero padded
-    const uint32_t gw = blockIdx.x * kLongWarps + warp, nw = gridDim.x * kLongWarps;
+    uint32_t* S = long_smem + (size_t)warp * words_per_warp;           // the read, 2 bits per base, aligned to its start, zero padded
+    const uint32_t gw = blockIdx.x * kLongWarps + warp;
     uint32_t* ss = ss_scratch + (size_t)gw * 2 * ss_cap;
     float* sims = reinterpret_cast<float*>(ss + ss_cap);
     const uint64_t n_bases = offsets[n_reads];
-    for (uint32_t r = gw; r < n_reads; r += nw) {
+    // reads are handed out one at a time in order (a ticket per warp): lengths of 1-10 kb and the few reads that carry an
+    // array make a fixed assignment end with most warps idle
+    for (;;) {
+        uint32_t r = 0;
+        if (lane == 0) r = atomicAdd(ticket, 1u);
+        r = __shfl_sync(cbl::kFull, r, 0);
+        if (r >= n_reads) break;
         const uint64_t b = offsets[r];
         const uint32_t L = (uint32_t)(offsets[r + 1] - b);
         const int se = cb::search_end(o, L);
@@ -1138,29 +1143,42 @@ k_dr_long(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offset
         cbl::GSeq s{bases + b};
         const uint64_t a0 = b & ~(uint64_t)15;
         const uint32_t shb = (uint32_t)(b & 15u);
-        const uint32_t nvec = (shb + L + 15) >> 4;
-        for (uint32_t v = lane; v < nvec + 2; v += 32) {
-            uint32_t w = 0;
-            if (v < nvec) {
+        const uint32_t nvec = (shb + L + 15) >> 4;                      // 16-byte vectors of the batch grid that hold the read
+        const uint32_t nW = (L + 15) >> 4;                              // words of the read-aligned stream
+        // word v of the grid = recode of bases[a0 + 16v, +16) (0 past the read's last vector); stream word k is cut out of grid
+        // words k and k+1, the second of which is the next lane's: four vectors per lane in flight, neighbours by shuffle
+        uint32_t carry = 0;                                             // grid word v0 - 1 of the round before
+        for (uint32_t v0 = 0; v0 <= nW; v0 += 128) {
+            uint4 x[4];
+            uint32_t w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t v = v0 + 32u * u + lane;
                 const uint64_t at = a0 + 16ull * v;
-                if (at + 16 <= n_bases) {
-                    const uint4 x = ldg_stream128(bases + at);
-                    w = cb::pack16(x.x, x.y, x.z, x.w);
-                } else {
-                    uint32_t q[4] = {0, 0, 0, 0};
-                    for (int i = 0; i < 16; ++i)
-                        if (at + i < n_bases) q[i >> 2] |= (uint32_t)__ldg(bases + at + i) << (8 * (i & 3));
-                    w = cb::pack16(q[0], q[1], q[2], q[3]);
-                }
+                x[u] = make_uint4(0, 0, 0, 0);
+                if (v < nvec && at + 16 <= n_bases) x[u] = ldg_stream128(bases + at);
             }
-            P[v] = w;
-            if (keep && v < nvec) keep[(a0 >> 4) + v] = w;              // the batch-wide 2-bit stream for the singleton scan
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t v = v0 + 32u * u + lane;
+                const uint64_t at = a0 + 16ull * v;
+                if (v < nvec && at + 16 > n_bases) x[u] = ragged_vector(bases, at, n_bases);      // the batch's last bytes
+                w[u] = v < nvec ? cb::pack16(x[u].x, x[u].y, x[u].z, x[u].w) : 0u;
+                if (keep && v < nvec) keep[(a0 >> 4) + v] = w[u];      // the batch-wide 2-bit stream for the singleton scan
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t v = v0 + 32u * u + lane;
+                uint32_t prev = __shfl_up_sync(cbl::kFull, w[u], 1);
+                const uint32_t edge = __shfl_sync(cbl::kFull, u ? w[u ? u - 1 : 0] : carry, 31);
+                if (lane == 0) prev = u ? edge : carry;
+                if (v >= 1 && v <= nW) S[v - 1] = cb::funnel_r(prev, w[u], 2 * shb);
+            }
+            carry = __shfl_sync(cbl::kFull, w[3], 31);
         }
+        for (uint32_t k = nW + lane; k < nW + 24; k += 32) S[k] = 0u;
         __syncwarp();
         if (se < 0) { if (lane == 0 && found) found[r] = 0; continue; }
-        const uint32_t nW = (L + 15) >> 4;
-        for (uint32_t k = lane; k < nW + 24; k += 32) S[k] = k < nW ? cb::funnel_r(P[k], P[k + 1], 2 * shb) : 0u;
-        __syncwarp();
         uint32_t base = 0, n_ss = 0, replen = 0;
         int result = 0;
         for (;;) {                                                      // one iteration per phase of the window grid
