@@ -1481,43 +1481,62 @@ k_ac_filter_long(const uint8_t* __restrict__ bases, const uint64_t* __restrict__
     const uint32_t gw = (blockIdx.x * kAcLongThreads + threadIdx.x) >> 5, nw = (gridDim.x * kAcLongThreads) >> 5;
     const uint64_t n_bases = offsets[n_reads];
     const uint32_t hshift = 32 - q.bits;
+    const uint64_t n_words = (n_bases + 15) >> 4;                  // words of the batch-wide stream
     for (uint32_t r = gw; r < n_reads; r += nw) {
         if (lane == 0) found[r] = 0;
         if (skip && skip[r]) continue;
         const uint64_t b = offsets[r];
         const uint32_t L = (uint32_t)(offsets[r + 1] - b);
         if (L < 16) continue;
-        const uint64_t a0 = b & ~(uint64_t)15;
-        const uint32_t shb = (uint32_t)(b & 15u), d = shb & 7u;
-        const uint32_t nvec = (shb + L + 15) >> 4;
-        const uint32_t x_end = shb + L;                             // one past the last base, in stream coordinates
+        // A lane takes FOUR consecutive words of the stream (one 16-byte load of the 2-bit stream, or four of the bytes) and the
+        // first word of the next lane: eight read-aligned 16-mers per lane and round, 1 984 bases per warp and round -- with
+        // one word per lane a 5 kb read was eleven dependent trips to DRAM.  Groups start at a multiple of four words, so up to
+        // three words in front of the read ride along (their 16-mers fail the range test below).
+        const uint64_t w_read = b >> 4;                             // word that holds the read's first base
+        const uint64_t w_first = w_read & ~(uint64_t)3;
+        const int32_t x0 = (int32_t)((int64_t)(w_first << 4) - (int64_t)b);   // first base of word w_first, relative to the read start (<= 0)
+        const int32_t d = (int32_t)((uint32_t)(b & 7u));            // read-aligned 16-mers start at stream offsets == b mod 8
+        const uint32_t n_groups = (uint32_t)((((b + L + 15) >> 4) - w_first + 3) >> 2);
         bool cand = false;
-        for (uint32_t v0 = 0; v0 < nvec && !cand; v0 += 31) {
-            const uint32_t v = v0 + lane;
-            uint32_t w = 0;
-            if (v < nvec) {
-                const uint64_t at = a0 + 16ull * v;
-                if (PACKED) w = __ldg(reinterpret_cast<const uint32_t*>(bases) + (at >> 4));
-                else if (at + 16 <= n_bases) {
-                    const uint4 x = ldg_stream128(bases + at);
-                    w = cb::pack16(x.x, x.y, x.z, x.w);
+        for (uint32_t g0 = 0; g0 < n_groups && !cand; g0 += 31) {
+            const uint32_t g = g0 + lane;
+            uint32_t w[5] = {0, 0, 0, 0, 0};
+            if (g < n_groups + 1) {                                 // (the group past the last one only lends its first word)
+                const uint64_t wi = w_first + 4ull * g;
+                if (PACKED) {
+                    if (wi + 4 <= n_words) {
+                        const uint4 x = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(bases) + wi));
+                        w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) if (wi + k < n_words) w[k] = __ldg(reinterpret_cast<const uint32_t*>(bases) + wi + k);
+                    }
                 } else {
-                    uint32_t qq[4] = {0, 0, 0, 0};
-                    for (int i = 0; i < 16; ++i)
-                        if (at + i < n_bases) qq[i >> 2] |= (uint32_t)__ldg(bases + at + i) << (8 * (i & 3));
-                    w = cb::pack16(qq[0], qq[1], qq[2], qq[3]);
+                    uint4 x[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t at = (wi + k) << 4;
+                        x[k] = make_uint4(0, 0, 0, 0);
+                        if (at + 16 <= n_bases) x[k] = ldg_stream128(bases + at);
+                        else if (at < n_bases) x[k] = ragged_vector(bases, at, n_bases);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) w[k] = cb::pack16(x[k].x, x[k].y, x[k].z, x[k].w);
                 }
             }
-            const uint32_t wn = __shfl_down_sync(0xFFFFFFFFu, w, 1);
+            w[4] = __shfl_down_sync(0xFFFFFFFFu, w[0], 1);
             bool hit = false;
-            if (lane < 31 && v < nvec) {
+            if (lane < 31 && g < n_groups) {
 #pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const uint32_t x = 16u * v + d + 8u * (uint32_t)t;          // start of the 16-mer in stream coordinates
-                    if (x >= shb && x + 16 <= x_end) {
-                        const uint32_t code = cb::funnel_r(w, wn, 2u * (d + 8u * (uint32_t)t));
-                        const uint32_t h = (code * 0x9E3779B1u) >> hshift;
-                        if ((bm[h >> 5] >> (h & 31u)) & 1u) hit = hit || qgram_member(q, code);
+                for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const int32_t x = x0 + 16 * (int32_t)(4u * g + (uint32_t)k) + d + 8 * t;       // start of the 16-mer, relative to the read start
+                        if (x >= 0 && x + 16 <= (int32_t)L) {
+                            const uint32_t code = cb::funnel_r(w[k], w[k + 1], 2u * (uint32_t)(d + 8 * t));
+                            const uint32_t h = (code * 0x9E3779B1u) >> hshift;
+                            if ((bm[h >> 5] >> (h & 31u)) & 1u) hit = hit || qgram_member(q, code);
+                        }
                     }
                 }
             }
