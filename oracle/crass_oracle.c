@@ -1026,4 +1026,290 @@ int orc_update_start_stops(const uint8_t* seq, uint32_t L, uint32_t* ss, uint32_
     return 0;
 }
 
+/* ======================================================================================================================
+ * Consensus DR of a group: ksw_align + Aligner (reference: src/crass/ksw.c, src/crass/Aligner.cpp)
+ * ====================================================================================================================== */
+#define ORC_KSW_XSTOP  0x20000
+#define ORC_KSW_XSUBO  0x40000
+#define ORC_KSW_XSTART 0x80000
+#define ORC_KSW_MAXQ   512                     /* query length the fixed work arrays take (DRs are < 100) */
+
+typedef struct { int score, te, qe, score2, te2, tb, qb; } orc_kswr;
+
+static int orc_sat_add16(int a, int b) { int s = a + b; return s > 32767 ? 32767 : s < -32768 ? -32768 : s; }   /* _mm_adds_epi16 */
+static int orc_sat_subu16(int a, int b) {                                                                           /* _mm_subs_epu16 */
+    const unsigned ua = (unsigned)a & 0xFFFFu, ub = (unsigned)b & 0xFFFFu;
+    return (int)(int16_t)(ua > ub ? ua - ub : 0u);
+}
+static int orc_max(int a, int b) { return a > b ? a : b; }
+
+/* ksw_i16 (ksw.c:219-322): eight 16-bit lanes, query position k = j + lane * slen sits in lane `lane` of vector j */
+static orc_kswr orc_ksw_i16(int qlen, const uint8_t* query, int tlen, const uint8_t* target, const int8_t* mat, int gapo, int gape, int xtra) {
+    orc_kswr r = {0, -1, -1, -1, -1, -1, -1};
+    const int p = 8, slen = (qlen + p - 1) / p, gapoe = gapo + gape;
+    const int minsc = (xtra & ORC_KSW_XSUBO) ? (xtra & 0xffff) : 0x10000;
+    const int endsc = (xtra & ORC_KSW_XSTOP) ? (xtra & 0xffff) : 0x10000;
+    static __thread int16_t bufs[4][ORC_KSW_MAXQ + 8];
+    int16_t *H0 = bufs[0], *H1 = bufs[1], *E = bufs[2], *Hmax = bufs[3];
+    int te = -1, gmax = 0, qmax = 0;
+    int n_b = 0, m_b = 0;
+    uint64_t* b = NULL;
+    for (int a = 0; a < 25; ++a) if (mat[a] > qmax) qmax = mat[a];                   /* q->max */
+    if (qlen <= 0 || qlen > ORC_KSW_MAXQ) return r;
+    memset(H0, 0, sizeof(int16_t) * (size_t)slen * 8);
+    memset(E, 0, sizeof(int16_t) * (size_t)slen * 8);
+    memset(Hmax, 0, sizeof(int16_t) * (size_t)slen * 8);
+    for (int i = 0; i < tlen; ++i) {
+        int f[8] = {0}, mx[8] = {0}, h[8], imax = 0;
+        const int8_t* ma = mat + target[i] * 5;
+        h[0] = 0;
+        for (int l = 1; l < 8; ++l) h[l] = H0[(slen - 1) * 8 + l - 1];               /* _mm_slli_si128(H0[slen-1], 2) */
+        for (int j = 0; j < slen; ++j) {
+            for (int l = 0; l < 8; ++l) {
+                const int k = j + l * slen;
+                const int sc = k >= qlen ? 0 : ma[query[k]];
+                int hh = orc_sat_add16(h[l], sc);
+                int e = E[j * 8 + l];
+                hh = orc_max(hh, e);
+                hh = orc_max(hh, f[l]);
+                mx[l] = orc_max(mx[l], hh);
+                H1[j * 8 + l] = (int16_t)hh;
+                hh = orc_sat_subu16(hh, gapoe);
+                e = orc_sat_subu16(e, gape);
+                e = orc_max(e, hh);
+                E[j * 8 + l] = (int16_t)e;
+                f[l] = orc_max(orc_sat_subu16(f[l], gape), hh);
+                h[l] = H0[j * 8 + l];
+            }
+        }
+        for (int k = 0; k < 16; ++k) {                                              /* the lazy-F loop */
+            int stop = 0;
+            for (int l = 7; l > 0; --l) f[l] = f[l - 1];
+            f[0] = 0;
+            for (int j = 0; j < slen; ++j) {
+                int any = 0;
+                for (int l = 0; l < 8; ++l) {
+                    int hh = orc_max(H1[j * 8 + l], f[l]);
+                    H1[j * 8 + l] = (int16_t)hh;
+                    hh = orc_sat_subu16(hh, gapoe);
+                    f[l] = orc_sat_subu16(f[l], gape);
+                    if (f[l] > hh) any = 1;
+                }
+                if (!any) { stop = 1; break; }
+            }
+            if (stop) break;
+        }
+        for (int l = 0; l < 8; ++l) imax = orc_max(imax, mx[l]);
+        if (imax >= minsc) {
+            if (n_b == 0 || (int32_t)b[n_b - 1] + 1 != i) {
+                if (n_b == m_b) { m_b = m_b ? m_b << 1 : 8; b = (uint64_t*)realloc(b, 8 * (size_t)m_b); }
+                b[n_b++] = (uint64_t)imax << 32 | (uint32_t)i;
+            } else if ((int)(b[n_b - 1] >> 32) < imax) b[n_b - 1] = (uint64_t)imax << 32 | (uint32_t)i;
+        }
+        if (imax > gmax) {
+            gmax = imax; te = i;
+            memcpy(Hmax, H1, sizeof(int16_t) * (size_t)slen * 8);
+            if (gmax >= endsc) break;
+        }
+        { int16_t* t = H1; H1 = H0; H0 = t; }
+    }
+    r.score = gmax; r.te = te;
+    {
+        int max = -1;
+        for (int i = 0; i < slen * 8; ++i)
+            if ((int)(uint16_t)Hmax[i] > max) { max = (uint16_t)Hmax[i]; r.qe = i / 8 + i % 8 * slen; }
+        if (b) {
+            const int w = (r.score + qmax - 1) / qmax;
+            const int low = te - w, high = te + w;
+            for (int i = 0; i < n_b; ++i) {
+                const int e = (int32_t)b[i];
+                if ((e < low || e > high) && (uint32_t)(b[i] >> 32) > (uint32_t)r.score2) { r.score2 = (int)(b[i] >> 32); r.te2 = e; }
+            }
+        }
+    }
+    free(b);
+    return r;
+}
+
+static void orc_revseq(int l, uint8_t* s) { for (int i = 0; i < l >> 1; ++i) { const uint8_t t = s[i]; s[i] = s[l - 1 - i]; s[l - 1 - i] = t; } }
+
+static void orc_aligner_matrix(int8_t* mat) {                                        /* Aligner.h:119-131 */
+    int k = 0;
+    for (int i = 0; i < 4; ++i) { for (int j = 0; j < 4; ++j) mat[k++] = i == j ? 1 : -3; mat[k++] = 0; }
+    for (int j = 0; j < 5; ++j) mat[k++] = 0;
+}
+
+/* ksw_align (ksw.c:330-354): forward pass, then -- for the start positions -- the same kernel on the reversed prefixes */
+static orc_kswr orc_ksw_align_codes(int qlen, uint8_t* query, int tlen, uint8_t* target, const int8_t* mat, int gapo, int gape, int xtra) {
+    orc_kswr r = orc_ksw_i16(qlen, query, tlen, target, mat, gapo, gape, xtra);
+    if ((xtra & ORC_KSW_XSTART) == 0 || ((xtra & ORC_KSW_XSUBO) && r.score < (xtra & 0xffff))) return r;
+    orc_revseq(r.qe + 1, query); orc_revseq(r.te + 1, target);
+    const orc_kswr rr = orc_ksw_i16(r.qe + 1, query, tlen, target, mat, gapo, gape, ORC_KSW_XSTOP | r.score);
+    orc_revseq(r.qe + 1, query); orc_revseq(r.te + 1, target);
+    if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
+    return r;
+}
+
+int orc_ksw_align(const uint8_t* query, int qlen, const uint8_t* target, int tlen, int xtra, int* out7) {
+    int8_t mat[25];
+    orc_aligner_matrix(mat);
+    uint8_t* q = (uint8_t*)malloc((size_t)qlen + 1);
+    uint8_t* t = (uint8_t*)malloc((size_t)tlen + 1);
+    memcpy(q, query, (size_t)qlen); memcpy(t, target, (size_t)tlen);
+    const orc_kswr r = orc_ksw_align_codes(qlen, q, tlen, t, mat, 5, 2, xtra);
+    free(q); free(t);
+    out7[0] = r.score; out7[1] = r.te; out7[2] = r.qe; out7[3] = r.score2; out7[4] = r.te2; out7[5] = r.tb; out7[6] = r.qb;
+    return 0;
+}
+
+static uint8_t orc_nt4(uint8_t c) {                                                 /* Aligner::seq_nt4_table (Aligner.cpp:41-58) */
+    switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 4; }
+}
+static int orc_cov_row(uint8_t c) {                                                 /* CHAR_TO_INDEX - 1 (Aligner.cpp:61-70): everything but C, G, T counts as A */
+    switch (c) { case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return 0; }
+}
+
+enum { ORC_AL_REVERSED = 1, ORC_AL_FAILED = 2, ORC_AL_EQUAL = 4 };
+
+/* Aligner::getOffsetAgainstMaster (Aligner.cpp:263-362) */
+static int orc_offset_against_master(const uint8_t* slave, int slen, const uint8_t* master_codes, int mlen, const int8_t* mat, int* flags) {
+    const int xtra = ORC_KSW_XSTART | ORC_KSW_XSUBO | 5;
+    if (slen <= 0) { *flags |= ORC_AL_EQUAL; return 0; }                            /* (the reference reads before its arrays here) */
+    uint8_t* fw = (uint8_t*)malloc((size_t)slen + 1);
+    uint8_t* rv = (uint8_t*)malloc((size_t)slen + 1);
+    uint8_t* rc = (uint8_t*)malloc((size_t)slen + 1);
+    uint8_t* mt = (uint8_t*)malloc((size_t)mlen + 1);
+    orc_revcomp(slave, (uint32_t)slen, rc);
+    for (int i = 0; i < slen; ++i) { fw[i] = orc_nt4(slave[i]); rv[i] = orc_nt4(rc[i]); }
+    memcpy(mt, master_codes, (size_t)mlen);
+    const orc_kswr f = orc_ksw_align_codes(slen, fw, mlen, mt, mat, 5, 2, xtra);
+    const orc_kswr v = orc_ksw_align_codes(slen, rv, mlen, mt, mat, 5, 2, xtra);
+    free(fw); free(rv); free(rc); free(mt);
+    if (v.score == f.score) { *flags |= ORC_AL_EQUAL; return 0; }
+    orc_kswr best = f;
+    if (v.score > f.score) { best = v; *flags |= ORC_AL_REVERSED; }
+    if (slen / 2 > best.score) { *flags |= ORC_AL_FAILED; return 0; }
+    if (best.score < 5) { *flags |= ORC_AL_FAILED; return 0; }
+    return best.tb - best.qb;
+}
+
+/* first repeat of the list whose length is dr_len, as the reference's unbounded loops look for it (Aligner.cpp:372-376); -1 = none */
+static int orc_first_full_repeat(const uint32_t* ss, uint32_t n_ss, int dr_len) {
+    for (uint32_t k = 0; k + 1 < n_ss; k += 2) if ((int)ss[k + 1] - (int)ss[k] == dr_len - 1) return (int)k;
+    return -1;
+}
+
+/* Aligner::placeReadsInCoverageArray (Aligner.cpp:364-417) for one read; `rev`: the read and its list were reverse complemented
+ * (ReadHolder::reverseComplementSeq, ReadHolder.cpp:593-608) */
+static int orc_place_read(const uint8_t* seq, uint32_t L, const uint32_t* ss_in, uint32_t n_ss, int rev, int dr_len, int dr_place,
+                          uint32_t array_len, int32_t* coverage) {
+    uint8_t* s = (uint8_t*)malloc(L + 1);
+    uint32_t* ss = (uint32_t*)malloc(sizeof(uint32_t) * (n_ss + 1));
+    if (rev) {
+        orc_revcomp(seq, L, s);
+        for (uint32_t k = 0; k < n_ss; ++k) ss[k] = L - 1 - ss_in[n_ss - 1 - k];
+    } else { memcpy(s, seq, L); memcpy(ss, ss_in, sizeof(uint32_t) * n_ss); }
+    int rc = 0;
+    int k = orc_first_full_repeat(ss, n_ss, dr_len);
+    if (k < 0) rc = 1;                                                               /* the reference would run off the list */
+    else {
+        do {
+            if ((int)ss[k + 1] - (int)ss[k] == dr_len - 1) {
+                const int start_pos = dr_place - (int)ss[k];
+                for (uint32_t i = 0; i < L; ++i) {
+                    const int at = (int)i + start_pos;
+                    if (at < 0 || at >= (int)array_len) { rc = 2; continue; }       /* logged as memory corruption by the reference, then written anyway */
+                    coverage[(size_t)orc_cov_row(s[i]) * array_len + (uint32_t)at]++;
+                }
+            }
+            k += 2;
+            if (k >= (int)(n_ss / 2) * 2) break;
+        } while ((int)ss[k + 1] - (int)ss[k] == dr_len - 1);
+    }
+    free(s); free(ss);
+    return rc;
+}
+
+int orc_consensus_group(const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, const uint32_t* read_dr,
+                        const uint32_t* ss_offsets, const uint32_t* ss_pool, const uint8_t* dr_bytes, const uint32_t* dr_offsets,
+                        uint32_t n_drs, uint32_t array_len, int32_t* dr_place, uint8_t* dr_flags, int32_t* zone,
+                        uint8_t* consensus, float* conservation, int32_t* coverage) {
+    int8_t mat[25];
+    orc_aligner_matrix(mat);
+    int status = 0;
+    memset(coverage, 0, sizeof(int32_t) * 4 * (size_t)array_len);
+    const int mlen = (int)(dr_offsets[1] - dr_offsets[0]);
+    uint8_t* master = (uint8_t*)malloc((size_t)mlen + 1);
+    for (int i = 0; i < mlen; ++i) master[i] = orc_nt4(dr_bytes[dr_offsets[0] + i]);
+    dr_place[0] = (int32_t)(array_len * 0.5);                                        /* CRASS_DEF_CONS_ARRAY_START */
+    dr_flags[0] = 0;
+    for (uint32_t d = 1; d < n_drs; ++d) {
+        const uint8_t* slave = dr_bytes + dr_offsets[d];
+        const int slen = (int)(dr_offsets[d + 1] - dr_offsets[d]);
+        int flags = 0;
+        int off = orc_offset_against_master(slave, slen, master, mlen, mat, &flags);
+        if (flags & ORC_AL_EQUAL) {                                                  /* extendSlaveDR (Aligner.cpp:420-452): two more bases on either side, from the first read that has them */
+            uint8_t ext[ORC_KSW_MAXQ + 8];
+            int ext_len = 0;
+            for (uint32_t i = 0; i < n_reads && !ext_len; ++i) {
+                if (read_dr[i] != d) continue;
+                const uint32_t* ss = ss_pool + ss_offsets[i];
+                const uint32_t n_ss = ss_offsets[i + 1] - ss_offsets[i];
+                const uint32_t L = (uint32_t)(offsets[i + 1] - offsets[i]);
+                const int k = orc_first_full_repeat(ss, n_ss, slen);
+                if (k < 0) continue;
+                if ((int)ss[k] - 2 < 0 || (int)ss[k + 1] + 2 > (int)L) continue;
+                uint32_t st = ss[k] - 2, ln = (uint32_t)slen + 4;                    /* std::string::substr clamps at the end of the read */
+                if (st + ln > L) ln = L - st;
+                memcpy(ext, bases + offsets[i] + st, ln);
+                ext_len = (int)ln;
+            }
+            flags = 0;
+            off = orc_offset_against_master(ext, ext_len, master, mlen, mat, &flags);
+            if (flags & ORC_AL_EQUAL) flags |= ORC_AL_FAILED;
+        }
+        if (flags & ORC_AL_FAILED) flags &= ~ORC_AL_REVERSED;                     /* alignSlave returns before it turns the reads round */
+        dr_flags[d] = (uint8_t)flags;
+        dr_place[d] = (flags & ORC_AL_FAILED) ? -1 : dr_place[0] + off;
+    }
+    free(master);
+    /* the reads of the master and of every placed slave go into the coverage array */
+    for (uint32_t i = 0; i < n_reads; ++i) {
+        const uint32_t d = read_dr[i];
+        if (d >= n_drs || (dr_place[d] < 0 && d != 0)) continue;
+        const int rc = orc_place_read(bases + offsets[i], (uint32_t)(offsets[i + 1] - offsets[i]), ss_pool + ss_offsets[i],
+                                      ss_offsets[i + 1] - ss_offsets[i], (dr_flags[d] & ORC_AL_REVERSED) != 0,
+                                      (int)(dr_offsets[d + 1] - dr_offsets[d]), dr_place[d], array_len, coverage);
+        if (rc) status = rc;
+    }
+    /* calculateDRZone (Aligner.cpp:456-484): the master's own interval */
+    zone[0] = dr_place[0];
+    zone[1] = dr_place[0] + mlen - 1;
+    /* generateConsensus (Aligner.cpp:147-246) */
+    int num_gt_zero = 0;
+    for (uint32_t j = 0; j < array_len; ++j) {
+        static const char alphabet[4] = {'A', 'C', 'G', 'T'};
+        int max_count = 0;
+        float total = 0.0f;
+        consensus[j] = 'N';
+        for (int k = 0; k < 4; ++k) {
+            const int c = coverage[(size_t)k * array_len + j];
+            total += (float)c;
+            if (c > max_count) { max_count = c; consensus[j] = (uint8_t)alphabet[k]; }
+        }
+        if (total > 2) { conservation[j] = (float)max_count / total; num_gt_zero++; }
+        else conservation[j] = 0;
+    }
+    int zs = zone[0], ze = zone[1];
+    const int n = (int)array_len;
+    if (num_gt_zero >= 2) {
+        while (zs > 0 && zs <= n) { if (conservation[zs - 1] < 0.55f) zs++; else break; }      /* (sic: the zone shrinks while its neighbour is poor) */
+        while (ze < n - 1 && ze >= -1) { if (conservation[ze + 1] < 0.55f) ze--; else break; }
+    }
+    while (zs > 0 && zs <= n) { if (conservation[zs - 1] >= 0.55f) zs--; else break; }
+    while (ze < n - 1 && ze >= -1) { if (conservation[ze + 1] >= 0.55f) ze++; else break; }
+    zone[0] = zs; zone[1] = ze;
+    return status;
+}
+
 void orc_free(void* p) { free(p); }

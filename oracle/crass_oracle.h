@@ -77,6 +77,18 @@ int orc_smith_waterman(const uint8_t* a, uint32_t la, const uint8_t* b, uint32_t
                        uint32_t* a_ret_pos, uint32_t* a_ret_len, uint32_t* b_ret_pos, uint32_t* b_ret_len);
 int orc_update_start_stops(const uint8_t* seq, uint32_t L, uint32_t* ss, uint32_t* n_ss, uint32_t cap, int front_offset,
                            const uint8_t* dr, uint32_t dr_len, uint32_t low_spacer);
+/* Consensus DR of a group (second half).
+ * orc_ksw_align: ksw_align (ksw.c:330-354) on nt4 codes with the Aligner's scores (match 1, mismatch -3, ambiguous 0, gap open 5,
+ * extend 2; Aligner.h:105-131), 16-bit form: a lane-by-lane restatement of the striped SSE2 kernel ksw_i16 (ksw.c:219-322), whose
+ * lazy-F loop and saturating arithmetic decide the corner cases.  out7 = score, te, qe, score2, te2, tb, qb.
+ * orc_consensus_group: Aligner::setMasterDR / alignSlave / generateConsensus (Aligner.cpp:72-246) with getOffsetAgainstMaster
+ * (:263-362), placeReadsInCoverageArray (:364-417), extendSlaveDR (:420-452), calculateDRZone (:456-484); same interface as
+ * ref_consensus_group (oracle/refshim/ref_shim.cpp). */
+int orc_ksw_align(const uint8_t* query, int qlen, const uint8_t* target, int tlen, int xtra, int* out7);
+int orc_consensus_group(const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, const uint32_t* read_dr,
+                        const uint32_t* ss_offsets, const uint32_t* ss_pool, const uint8_t* dr_bytes, const uint32_t* dr_offsets,
+                        uint32_t n_drs, uint32_t array_len, int32_t* dr_place, uint8_t* dr_flags, int32_t* zone,
+                        uint8_t* consensus, float* conservation, int32_t* coverage);
 void orc_free(void* p);
 
 #ifdef __cplusplus

@@ -35,6 +35,11 @@
 #include "kseq.h"
 
 #include "SmithWaterman.h"
+#include "Aligner.h"
+#include "Types.h"
+extern "C" {
+#include "ksw.h"
+}
 
 extern "C" {
 #include "../aho-corasick/msutil.h"
@@ -488,6 +493,69 @@ int ref_update_start_stops(const char* seq, uint32_t len, uint32_t* ss, uint32_t
         if (copy_ss(h, ss, cap, n_ss)) return -2;
         return 0;
     } catch (crispr::exception& e) { return -1; } catch (std::exception& e) { return -3; }
+}
+
+// ---- consensus DR of a group (second half): the reference's own Aligner (Aligner.cpp:72-418) and the
+// ksw_align it calls (ksw.c:330), driven the way WorkHorse::parseGroupedDRs does (WorkHorse.cpp:1166-1171, 750-773):
+// setMasterDR on DR 0, alignSlave for every other DR of the group, generateConsensus.
+// reads: n_reads sequences back to back with their start/stop lists; read_dr[i] = index of the DR (token) the read hangs on.
+// Out: dr_place[d] = AL_Offsets of DR d (-1: the slave could not be placed), dr_flags[d] bit 0 = the slave and its reads were
+// reverse complemented, zone[2], consensus / conservation [array_len], coverage[4 * array_len] (rows A C G T).
+int ref_ksw_align(const uint8_t* query, int qlen, const uint8_t* target, int tlen, int xtra, int* out7) {
+    // query / target are nt4 codes (0..4); mat / gaps as the Aligner sets them up (Aligner.h:105-131)
+    int8_t mat[25]; int k = 0;
+    for (int i = 0; i < 4; ++i) { for (int j = 0; j < 4; ++j) mat[k++] = i == j ? 1 : -3; mat[k++] = 0; }
+    for (int j = 0; j < 5; ++j) mat[k++] = 0;
+    std::vector<uint8_t> q(query, query + qlen), t(target, target + tlen);
+    q.push_back(0); t.push_back(0);
+    kswq_t* prof = 0;
+    kswr_t r = ksw_align(qlen, q.data(), tlen, t.data(), 5, mat, 5, 2, xtra, &prof);
+    free(prof);
+    out7[0] = r.score; out7[1] = r.te; out7[2] = r.qe; out7[3] = r.score2; out7[4] = r.te2; out7[5] = r.tb; out7[6] = r.qb;
+    return 0;
+}
+
+int ref_consensus_group(const char* bases, const uint64_t* offsets, uint32_t n_reads, const uint32_t* read_dr,
+                        const uint32_t* ss_offsets, const uint32_t* ss_pool, const char* dr_bytes, const uint32_t* dr_offsets,
+                        uint32_t n_drs, uint32_t array_len, int32_t* dr_place, uint8_t* dr_flags, int32_t* zone,
+                        char* consensus, float* conservation, int32_t* coverage) {
+    ref_init();
+    CoutSilencer quiet;
+    ReadMap reads;
+    StringCheck sc;
+    std::vector<StringToken> tok(n_drs);
+    try {
+        for (uint32_t d = 0; d < n_drs; ++d) {
+            tok[d] = sc.addString(std::string(dr_bytes + dr_offsets[d], dr_offsets[d + 1] - dr_offsets[d]));
+            reads[tok[d]] = new ReadList();
+        }
+        for (uint32_t i = 0; i < n_reads; ++i) {
+            ReadHolder* h = new ReadHolder();
+            holder_from(*h, bases + offsets[i], (uint32_t)(offsets[i + 1] - offsets[i]), ss_pool + ss_offsets[i], ss_offsets[i + 1] - ss_offsets[i]);
+            reads[tok[read_dr[i]]]->push_back(h);
+        }
+        Aligner al((int)array_len, &reads, &sc);
+        al.setMasterDR(tok[0]);
+        dr_place[0] = al.offset(tok[0]);
+        dr_flags[0] = 0;
+        for (uint32_t d = 1; d < n_drs; ++d) {
+            StringToken t = tok[d];
+            al.alignSlave(t);
+            dr_flags[d] = t != tok[d] ? 1 : 0;
+            dr_place[d] = al.offset(t);
+        }
+        al.generateConsensus();
+        zone[0] = al.getDRZoneStart(); zone[1] = al.getDRZoneEnd();
+        const char alphabet[4] = {'A', 'C', 'G', 'T'};
+        for (uint32_t j = 0; j < array_len; ++j) {
+            consensus[j] = al.consensusAt((int)j);
+            conservation[j] = al.conservationAt((int)j);
+            for (int k = 0; k < 4; ++k) coverage[(size_t)k * array_len + j] = al.coverageAt((int)j, alphabet[k]);
+        }
+    } catch (crispr::exception& e) { return -1; } catch (std::exception& e) { return -3; }
+    for (ReadMapIterator it = reads.begin(); it != reads.end(); ++it)
+        if (it->second) { for (size_t i = 0; i < it->second->size(); ++i) delete (*it->second)[i]; delete it->second; }
+    return 0;
 }
 
 void ref_free(void* p) { free(p); }

@@ -136,6 +136,46 @@ class _Base:
         r = self._update_start_stops(seq, len(seq), arr, C.byref(n), cap, front_offset, dr, len(dr), low_spacer)
         return r, list(arr[: n.value])
 
+    # -- consensus DR of a group (ksw_align + Aligner) ---------------------------------------
+    def ksw_align(self, query, target, xtra=0x80000 | 0x40000 | 5):
+        """query / target: nt4 code bytes -> (score, te, qe, score2, te2, tb, qb)"""
+        out = (C.c_int * 7)()
+        fn = getattr(self.lib, self.prefix + "ksw_align")
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        fn(bytes(query), len(query), bytes(target), len(target), xtra, out)
+        return tuple(out)
+
+    def consensus_group(self, case):
+        """case: dict(reads=[(seq, ss, dr index)], drs=[bytes, ...] (0 = master), array_len) ->
+        dict(status, place, flags, zone, consensus, conservation (uint32 bit patterns), coverage)"""
+        import numpy as np
+        reads, drs, n = case["reads"], case["drs"], case["array_len"]
+        bases = np.frombuffer(b"".join(r[0] for r in reads), dtype=np.uint8).copy() if reads else np.zeros(1, np.uint8)
+        offs = np.zeros(len(reads) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(r[0]) for r in reads])
+        ss_offs = np.zeros(len(reads) + 1, dtype=np.uint32)
+        ss_offs[1:] = np.cumsum([len(r[1]) for r in reads])
+        pool = np.array([x for r in reads for x in r[1]] or [0], dtype=np.uint32)
+        read_dr = np.array([r[2] for r in reads] or [0], dtype=np.uint32)
+        dr_bytes = np.frombuffer(b"".join(drs), dtype=np.uint8).copy()
+        dr_offs = np.zeros(len(drs) + 1, dtype=np.uint32)
+        dr_offs[1:] = np.cumsum([len(d) for d in drs])
+        place = np.zeros(len(drs), dtype=np.int32)
+        flags = np.zeros(len(drs), dtype=np.uint8)
+        zone = np.zeros(2, dtype=np.int32)
+        cons = np.zeros(n, dtype=np.uint8)
+        conserv = np.zeros(n, dtype=np.float32)
+        cov = np.zeros(4 * n, dtype=np.int32)
+        fn = getattr(self.lib, self.prefix + "consensus_group")
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p] * 2 + [C.c_uint32] + [C.c_void_p] * 5 + [C.c_uint32, C.c_uint32] + [C.c_void_p] * 6
+        st = fn(bases.ctypes.data, offs.ctypes.data, len(reads), read_dr.ctypes.data, ss_offs.ctypes.data, pool.ctypes.data,
+                dr_bytes.ctypes.data, dr_offs.ctypes.data, len(drs), n, place.ctypes.data, flags.ctypes.data, zone.ctypes.data,
+                cons.ctypes.data, conserv.ctypes.data, cov.ctypes.data)
+        return dict(status=st, place=place.tolist(), reversed=[int(f) & 1 for f in flags], zone=zone.tolist(),
+                    consensus=cons.tobytes(), conservation=conserv.view(np.uint32).tolist(), coverage=cov.tolist())
+
     # -- automaton -----------------------------------------------------------------------------
     def ac_create(self, patterns):
         n = len(patterns)

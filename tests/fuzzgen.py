@@ -103,3 +103,57 @@ def uss_case(rng):
     if rng.random() < 0.05:
         seq = seq.lower() if rng.random() < 0.5 else seq.replace(b"A", b"R", 1)
     return seq, ss, front, dr
+
+
+def consensus_case(rng, n_slaves=None, read_len=(100, 150), alphabet=b"ACGT"):
+    """A DR group as WorkHorse::parseGroupedDRs hands it to the Aligner: DR 0 is the master (the longest), the others are
+    variants of it -- trimmed or grown at either end, with substitutions, some on the other strand, some of them their own
+    reverse complement (forward and reverse scores equal: the extendSlaveDR path), one unrelated (alignment fails) -- and
+    every DR has a few reads that carry it one to three times (first repeat sometimes a partial one)."""
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    master = rand_seq(rng, rng.randint(34, 46))
+    drs = [master]
+    for _ in range(n_slaves if n_slaves is not None else rng.randint(2, 10)):
+        kind = rng.random()
+        if kind < 0.1:
+            v = rand_seq(rng, rng.randint(23, 32))                                  # unrelated
+        elif kind < 0.25:
+            half = master[rng.randint(0, 6): rng.randint(14, 18)]
+            v = half + half.translate(comp)[::-1]                                   # its own reverse complement
+        else:
+            v = master[rng.randint(0, 6): len(master) - rng.randint(0, 6)]
+            v = mutate(rng, v, rng.choice([0, 0, 0.03, 0.08]), b"ACGT")
+            if rng.random() < 0.3:
+                v = rand_seq(rng, rng.randint(0, 2)) + v + rand_seq(rng, rng.randint(0, 2))
+            if rng.random() < 0.3:
+                v = v.translate(comp)[::-1]
+        if len(v) >= 12 and len(v) < len(master) and v not in drs:
+            drs.append(v)
+    reads = []
+    for d, dr in enumerate(drs):
+        for _ in range(rng.randint(1, 4)):
+            L = rng.randint(*read_len)
+            seq = bytearray(rand_seq(rng, L, alphabet))
+            ss = []
+            pos = rng.randint(0, 12)
+            if rng.random() < 0.3 and pos >= 0:                                       # a partial repeat in front (its tail only)
+                cut = rng.randint(3, len(dr) - 2)
+                part = dr[cut:]
+                seq[0:len(part)] = part
+                ss += [0, len(part) - 1]
+                pos = len(part) + rng.randint(26, 36)
+            for _k in range(rng.randint(1, 3)):
+                if pos + len(dr) > L:
+                    break
+                seq[pos:pos + len(dr)] = dr
+                ss += [pos, pos + len(dr) - 1]
+                pos += len(dr) + rng.randint(26, 40)
+            if not any(ss[k + 1] - ss[k] == len(dr) - 1 for k in range(0, len(ss), 2)):
+                continue
+            reads.append((bytes(seq[:L]), ss, d))
+    if not any(r[2] == 0 for r in reads):                                           # the master always has a read
+        L = read_len[1]
+        seq = bytearray(rand_seq(rng, L))
+        seq[40:40 + len(master)] = master
+        reads.append((bytes(seq), [40, 40 + len(master) - 1], 0))
+    return dict(reads=reads, drs=drs, array_len=4 * read_len[1])

@@ -16,6 +16,10 @@ Outputs (all under tests/golden/):
                              lengths of the two strings, find/rfind of the second in the DR);
                              `python make_golden.py uss` regenerates this file alone
 
+  consensus_vectors.json     ksw_align calls (nt4 codes of q / t -> score, te, qe, score2, te2, tb, qb) and DR groups through
+                             Aligner::setMasterDR / alignSlave / generateConsensus -> placements, strands, zone, consensus,
+                             conservation bits, coverage; `python make_golden.py consensus` regenerates this file alone
+
 catch_vectors.json is NOT generated: it restates the known-answer tests of the reference's own
 src/test/test_libcrispr.cpp by hand (each entry cites its line range).
 """
@@ -69,10 +73,48 @@ def gen_update_start_stops(R):
     json.dump(dict(update_start_stops=uss, smith_waterman=sw), open(os.path.join(HERE, "update_start_stops_vectors.json"), "w"))
 
 
+def gen_consensus(R):
+    """ksw_align calls and whole DR groups through the reference's Aligner (`python make_golden.py consensus`)."""
+    rng = random.Random(20241)
+    nt = bytes.maketrans(b"ACGTN", bytes([0, 1, 2, 3, 4]))
+    ksw = []
+    while len(ksw) < 600:
+        t = fuzzgen.rand_seq(rng, rng.randint(20, 60))
+        if rng.random() < 0.75:
+            a, b = sorted(rng.sample(range(len(t)), 2))
+            q = fuzzgen.mutate(rng, t[a:b + 1], rng.choice([0, 0.05, 0.2]), b"ACGTN")
+            if rng.random() < 0.3 and len(q) > 6:
+                k = rng.randint(1, len(q) - 2)
+                q = q[:k] + fuzzgen.rand_seq(rng, rng.randint(1, 3)) + q[k:]
+            if rng.random() < 0.3 and len(q) > 8:
+                k = rng.randint(1, len(q) - 4)
+                q = q[:k] + q[k + rng.randint(1, 3):]
+        else:
+            q = fuzzgen.rand_seq(rng, rng.randint(1, 50))
+        if q:
+            ksw.append(dict(q=q.decode(), t=t.decode(), out=list(R.ksw_align(q.translate(nt), t.translate(nt)))))
+    groups = []
+    for it in range(40):
+        case = fuzzgen.consensus_case(rng, read_len=(70, 90), alphabet=b"ACGTN" if it % 4 == 0 else b"ACGT")
+        out = R.consensus_group(case)
+        assert out["status"] == 0
+        cov = out.pop("coverage")
+        out["coverage_md5"] = hashlib.md5(struct.pack("<%di" % len(cov), *cov)).hexdigest()
+        if it < 4:
+            out["coverage"] = cov
+        out["consensus"] = out["consensus"].decode()
+        groups.append(dict(reads=[[r[0].decode(), r[1], r[2]] for r in case["reads"]], drs=[d.decode() for d in case["drs"]],
+                           array_len=case["array_len"], out=out))
+    json.dump(dict(ksw_align=ksw, groups=groups), open(os.path.join(HERE, "consensus_vectors.json"), "w"))
+
+
 def main():
     R = checkers.ref()
     if sys.argv[1:] == ["uss"]:
         gen_update_start_stops(R)
+        return
+    if sys.argv[1:] == ["consensus"]:
+        gen_consensus(R)
         return
     os.makedirs(os.path.join(HERE, "bundled"), exist_ok=True)
     sums = []

@@ -69,6 +69,36 @@ def test_update_start_stops_vectors(P):
         assert list(P.smith_waterman(v["a"].encode(), v["b"].encode(), v["start"], v["len"], v["similarity"])) == v["out"]
 
 
+def consensus_expected(g):
+    """golden group entry -> (case, expected output without the coverage array, md5 of the coverage array)"""
+    case = dict(reads=[(r[0].encode(), r[1], r[2]) for r in g["reads"]], drs=[d.encode() for d in g["drs"]], array_len=g["array_len"])
+    want = {k: v for k, v in g["out"].items() if k not in ("coverage", "coverage_md5")}
+    want["consensus"] = want["consensus"].encode()
+    return case, want, g["out"]["coverage_md5"], g["out"].get("coverage")
+
+
+def test_consensus_vectors(P):
+    """ksw_align and the Aligner (consensus DR of a group) against vectors made by the compiled reference."""
+    import hashlib
+    import struct
+    g = load("consensus_vectors.json")
+    nt = bytes.maketrans(b"ACGTN", bytes([0, 1, 2, 3, 4]))
+    for v in g["ksw_align"]:
+        assert list(P.ksw_align(v["q"].encode().translate(nt), v["t"].encode().translate(nt))) == v["out"]
+    placed = turned = 0
+    for grp in g["groups"]:
+        case, want, md5, cov = consensus_expected(grp)
+        got = P.consensus_group(case)
+        c = got.pop("coverage")
+        assert got == want
+        assert hashlib.md5(struct.pack("<%di" % len(c), *c)).hexdigest() == md5
+        if cov is not None:
+            assert c == cov
+        placed += sum(1 for p in want["place"][1:] if p >= 0)
+        turned += sum(want["reversed"])
+    assert placed > 100 and turned > 20                  # the fixture does exercise both strands
+
+
 def test_ac_vectors(P):
     for case in load("ac_vectors.json"):
         h = P.ac_create([p.encode() for p in case["patterns"]])

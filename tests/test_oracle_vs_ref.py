@@ -116,6 +116,39 @@ def test_smith_waterman_and_update_start_stops_fuzz(R, P):
     assert grew > 1000
 
 
+def test_ksw_align_and_consensus_fuzz(R, P):
+    """The consensus step (second half): the lane-by-lane restatement of ksw_i16 / ksw_align and of the Aligner
+    against the reference's own ksw.c and Aligner.cpp -- alignment end points, tie breaks of the striped kernel, second-best
+    scores, both strands, the extendSlaveDR detour, coverage, consensus, conservation bits and the DR zone."""
+    rng = random.Random(18)
+    nt = bytes.maketrans(b"ACGTN", bytes([0, 1, 2, 3, 4]))
+    for _ in range(2000):
+        t = fuzzgen.rand_seq(rng, rng.randint(20, 70))
+        if rng.random() < 0.75:
+            a, b = sorted(rng.sample(range(len(t)), 2))
+            q = fuzzgen.mutate(rng, t[a:b + 1], rng.choice([0, 0.05, 0.2]), b"ACGTN")
+            if rng.random() < 0.3 and len(q) > 6:
+                k = rng.randint(1, len(q) - 2)
+                q = q[:k] + fuzzgen.rand_seq(rng, rng.randint(1, 3)) + q[k:]
+            if rng.random() < 0.3 and len(q) > 8:
+                k = rng.randint(1, len(q) - 4)
+                q = q[:k] + q[k + rng.randint(1, 3):]
+        else:
+            q = fuzzgen.rand_seq(rng, rng.randint(1, 60))
+        if not q:
+            continue
+        xtra = rng.choice([0x80000 | 0x40000 | 5, 0x80000, 0x40000 | 12, 0])
+        assert R.ksw_align(q.translate(nt), t.translate(nt), xtra) == P.ksw_align(q.translate(nt), t.translate(nt), xtra)
+    turned = failed = 0
+    for it in range(500):
+        case = fuzzgen.consensus_case(rng, alphabet=b"ACGTN" if it % 5 == 0 else b"ACGT")
+        want, got = R.consensus_group(case), P.consensus_group(case)
+        assert want["status"] == 0 and got == want
+        turned += sum(want["reversed"])
+        failed += sum(1 for p in want["place"] if p < 0)
+    assert turned > 200 and failed > 200
+
+
 def test_lowlexi_fuzz(R, P):
     rng = random.Random(15)
     for _ in range(10000):
