@@ -90,6 +90,8 @@ def lib():
         "crass_b200_ac_num_symbols": (C.c_uint32, [vp]),
         "crass_b200_ac_table_bytes": (C.c_uint64, [vp]),
         "crass_b200_ac_pattern_text": (vp, [vp, C.POINTER(C.c_uint32)]),
+        "crass_b200_ksw_align": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint32, vp]),
+        "crass_b200_consensus_groups": (C.c_int, [vp, vp, vp, C.c_uint32, vp, vp, vp, vp, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_uint32)]),
         "crass_b200_ac_scan_dev": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp]),
         "crass_b200_ac_scan": (C.c_int, [vp, vp, vp, vp, C.c_uint32, vp, vp, C.POINTER(vp), u32p, C.POINTER(vp), u32p]),
         "crass_b200_edit_distance_batch": (C.c_int, [vp, vp, C.c_uint64, vp, vp, vp, vp, C.c_uint32, vp, vp]),
@@ -625,6 +627,61 @@ class Context:
         _check(lib().crass_b200_update_start_stops_dev(self.h, d_bases.data_ptr(), d_offsets.data_ptr(), d_dr_bytes.data_ptr(), d_dr_offsets.data_ptr(),
                                                        d_jobs.data_ptr(), n_jobs, d_ss_in.data_ptr(), low_spacer, d_ss_out.data_ptr(),
                                                        d_n_out.data_ptr(), d_status.data_ptr(), stream))
+
+    # -- K7: consensus DR of DR groups ------------------------------------------------------------
+    def ksw_align(self, pairs, xtra=0x80000 | 0x40000 | 5):
+        """pairs: [(query letters, target letters, reverse-complement the query?)] -> [(score, te, qe, score2, te2, tb, qb)]"""
+        pool = bytearray()
+        jobs = np.zeros((len(pairs), 6), dtype=np.uint32)
+        for i, (q, t, rc) in enumerate(pairs):
+            jobs[i] = (len(pool), len(q), len(pool) + len(q), len(t), 1 if rc else 0, xtra)
+            pool += q + t
+        poolb = np.frombuffer(bytes(pool) or b"\0", dtype=np.uint8).copy()
+        out = np.zeros((len(pairs), 8), dtype=np.int32)
+        _check(lib().crass_b200_ksw_align(self.h, _np_ptr(poolb), len(pool), _np_ptr(jobs), len(pairs), _np_ptr(out)))
+        assert not out[:, 7].any(), "a job was not taken (query longer than 128?)"
+        return [tuple(int(x) for x in r[:7]) for r in out]
+
+    def consensus_groups(self, cases):
+        """cases: [dict(reads=[(seq, ss, dr index inside the group)], drs=[master, slaves...], array_len)] (one array_len for all)
+        -> [dict(place, reversed, flags, zone, consensus, conservation (uint32 bit patterns), coverage)], status bits"""
+        n = cases[0]["array_len"]
+        assert all(c["array_len"] == n for c in cases)
+        reads, drs, gfirst = [], [], [0]
+        for c in cases:
+            base = len(drs)
+            drs += c["drs"]
+            reads += [(r[0], r[1], base + r[2]) for r in c["reads"]]
+            gfirst.append(len(drs))
+        bases = np.frombuffer(b"".join(r[0] for r in reads) or b"\0", dtype=np.uint8).copy()
+        offs = np.zeros(len(reads) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(r[0]) for r in reads])
+        ss_offs = np.zeros(len(reads) + 1, dtype=np.uint32)
+        ss_offs[1:] = np.cumsum([len(r[1]) for r in reads])
+        pool = np.array([x for r in reads for x in r[1]] or [0], dtype=np.uint32)
+        read_dr = np.array([r[2] for r in reads] or [0], dtype=np.uint32)
+        dr_bytes = np.frombuffer(b"".join(drs), dtype=np.uint8).copy()
+        dr_offs = np.zeros(len(drs) + 1, dtype=np.uint32)
+        dr_offs[1:] = np.cumsum([len(d) for d in drs])
+        gf = np.array(gfirst, dtype=np.uint32)
+        G = len(cases)
+        place = np.zeros(len(drs), dtype=np.int32)
+        flags = np.zeros(len(drs), dtype=np.uint8)
+        zone = np.zeros(2 * G, dtype=np.int32)
+        cons = np.zeros(G * n, dtype=np.uint8)
+        conserv = np.zeros(G * n, dtype=np.float32)
+        cov = np.zeros(G * 4 * n, dtype=np.int32)
+        status = C.c_uint32(0)
+        _check(lib().crass_b200_consensus_groups(self.h, _np_ptr(bases), _np_ptr(offs), len(reads), _np_ptr(read_dr), _np_ptr(ss_offs), _np_ptr(pool),
+                                                 _np_ptr(dr_bytes), _np_ptr(dr_offs), len(drs), _np_ptr(gf), G, n, _np_ptr(place), _np_ptr(flags),
+                                                 _np_ptr(zone), _np_ptr(cons), _np_ptr(conserv), _np_ptr(cov), C.byref(status)))
+        out = []
+        for g in range(G):
+            a, b = gfirst[g], gfirst[g + 1]
+            out.append(dict(place=place[a:b].tolist(), reversed=[int(f) & 1 for f in flags[a:b]], flags=flags[a:b].tolist(),
+                            zone=zone[2 * g:2 * g + 2].tolist(), consensus=cons[g * n:(g + 1) * n].tobytes(),
+                            conservation=conserv[g * n:(g + 1) * n].view(np.uint32).tolist(), coverage=cov[g * 4 * n:(g + 1) * 4 * n].tolist()))
+        return out, status.value
 
     def scan_right(self, seq, ss, pattern, min_spacer, scan_range=24):
         cap = 2 * (len(seq) // 4 + 8)

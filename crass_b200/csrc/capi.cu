@@ -120,6 +120,7 @@ struct crass_b200_ctx {
     DevBuf d_cand_mask;                  // K2 fast path: per candidate, the aligned 16-mers that can belong to an occurrence
     // K5 (clustering passes A/B on the token block): device arrays and their pinned host mirrors
     DevBuf d_cl_ckeys;
+    DevBuf d_cons;                       // K7 (consensus DR): every device array of a call, carved from one allocation
     DevBuf d_ticket;                     // work counter of the long-read kernel
     DevBuf d_cl_order, d_cl_koff, d_cl_keys, d_cl_first, d_cl_tab, d_cl_info;
     DevBuf d_cl_group, d_cl_chain, d_cl_next, d_cl_odd, d_cl_dead, d_cl_str;
@@ -219,7 +220,7 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
                       &c->d_ac_bitmap, &c->d_ac_keys, &c->d_ac_skeys, &c->d_ac_shead, &c->d_ac_pnext, &c->d_ac_poffs, &c->d_ac_pbytes,
                       &c->d_rank, &c->d_hits_sorted, &c->d_cand_counts, &c->d_cand_mask, &c->d_ac_bitmap_small, &c->d_packed,
                       &c->d_cl_order, &c->d_cl_koff, &c->d_cl_keys, &c->d_cl_first, &c->d_cl_tab, &c->d_cl_info,
-                      &c->d_cl_group, &c->d_cl_chain, &c->d_cl_next, &c->d_cl_odd, &c->d_cl_dead, &c->d_cl_str, &c->d_ac_ones, &c->d_cl_tail, &c->d_cl_ckeys, &c->d_ticket};
+                      &c->d_cl_group, &c->d_cl_chain, &c->d_cl_next, &c->d_cl_odd, &c->d_cl_dead, &c->d_cl_str, &c->d_ac_ones, &c->d_cl_tail, &c->d_cl_ckeys, &c->d_ticket, &c->d_cons};
     for (DevBuf* b : bufs) b->release();
     for (PinnedBuf* b : {&c->h_cl_block, &c->h_cl_order, &c->h_cl_keys, &c->h_cl_first, &c->h_cl_info, &c->h_ac_stage,
                          &c->h_cl_group, &c->h_cl_dead, &c->h_cl_str, &c->h_cl_pat}) b->release();
@@ -676,6 +677,127 @@ char* crass_b200_cluster_block_patterns_dev(crass_b200_ctx* c, const void* d_blo
     for (uint32_t i = 0; i < ps.n(); ++i) { memcpy(w, ps.bytes.data() + ps.offs[i], ps.offs[i + 1] - ps.offs[i]); w += ps.offs[i + 1] - ps.offs[i]; *w++ = '\n'; }
     *w = 0;
     return text;
+}
+
+// ---- K7: consensus DR of DR groups ---------------------------------------------------------------------------------------
+int crass_b200_ksw_align(crass_b200_ctx* c, const uint8_t* pool, uint64_t pool_bytes, const crass_b200_ksw_job* jobs, uint32_t n_jobs,
+                         crass_b200_ksw_result* out) {
+    if (!c || !pool || !jobs || !out) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    static_assert(sizeof(crass_b200_ksw_job) == sizeof(cbk::KswJob) && sizeof(crass_b200_ksw_result) == sizeof(cbk::KswResult), "layout");
+    for (uint32_t i = 0; i < n_jobs; ++i)
+        if ((uint64_t)jobs[i].q_off + jobs[i].q_len > pool_bytes || (uint64_t)jobs[i].t_off + jobs[i].t_len > pool_bytes)
+            return cbh::fail(CRASS_B200_EINVAL, "ksw job reaches past the pool");
+    if (n_jobs == 0) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    size_t at = 0;
+    auto carve = [&](size_t bytes) { const size_t o = at; at += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_pool = carve(pool_bytes + 16), o_jobs = carve((size_t)n_jobs * sizeof(cbk::KswJob)), o_res = carve((size_t)n_jobs * sizeof(cbk::KswResult));
+    if (int r = c->d_cons.reserve(at)) return r;
+    uint8_t* d = c->d_cons.as<uint8_t>();
+    CUDA_TRY(cudaMemcpyAsync(d + o_pool, pool, pool_bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(d + o_jobs, jobs, (size_t)n_jobs * sizeof(cbk::KswJob), cudaMemcpyHostToDevice, c->stream));
+    cbk::k_ksw_align<<<(n_jobs * 8 + 127) / 128, 128, 0, c->stream>>>(d + o_pool, (const cbk::KswJob*)(d + o_jobs), nullptr, n_jobs, (cbk::KswResult*)(d + o_res));
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, d + o_res, (size_t)n_jobs * sizeof(cbk::KswResult), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int crass_b200_consensus_groups(crass_b200_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
+                                const uint32_t* read_dr, const uint32_t* ss_offsets, const uint32_t* ss_pool,
+                                const uint8_t* dr_bytes, const uint32_t* dr_offsets, uint32_t n_drs,
+                                const uint32_t* group_first_dr, uint32_t n_groups, uint32_t array_len,
+                                int32_t* dr_place, uint8_t* dr_flags, int32_t* zone, uint8_t* consensus, float* conservation,
+                                int32_t* coverage, uint32_t* status) {
+    if (!c || !offsets || !dr_bytes || !dr_offsets || !group_first_dr || !dr_place || !dr_flags || !zone || !consensus || !conservation || !coverage)
+        return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    if (n_reads && (!bases || !read_dr || !ss_offsets || !ss_pool)) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    if (n_groups == 0 || n_drs == 0 || array_len == 0 || group_first_dr[0] != 0 || group_first_dr[n_groups] != n_drs)
+        return cbh::fail(CRASS_B200_EINVAL, "bad group layout");
+    const uint32_t kExtStride = 8 * cbk::kKswMaxSlen;                          // the longest query the alignment kernel takes
+    std::vector<uint32_t> dr_group(n_drs);
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        if (group_first_dr[g] >= group_first_dr[g + 1]) return cbh::fail(CRASS_B200_EINVAL, "empty group");
+        for (uint32_t d = group_first_dr[g]; d < group_first_dr[g + 1]; ++d) {
+            dr_group[d] = g;
+            const uint32_t len = dr_offsets[d + 1] - dr_offsets[d];
+            if (len == 0 || len + 4 > kExtStride) return cbh::fail(CRASS_B200_EINVAL, "DR length not in 1..124");
+        }
+    }
+    for (uint32_t i = 0; i < n_reads; ++i) if (read_dr[i] >= n_drs) return cbh::fail(CRASS_B200_EINVAL, "read_dr out of range");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const uint64_t n_bases = n_reads ? offsets[n_reads] : 0;
+    const uint32_t n_ss = n_reads ? ss_offsets[n_reads] : 0;
+    const uint32_t dr_total = dr_offsets[n_drs];
+    const int xtra = 0x80000 | 0x40000 | 5;                                     // KSW_XSTART | KSW_XSUBO | AL_minAlignmentScore (Aligner.h:105-123)
+    // round-1 jobs: DR d against its master on both strands (a master's own pair stays empty)
+    std::vector<cbk::KswJob> jobs(2 * (size_t)n_drs);
+    for (uint32_t d = 0; d < n_drs; ++d) {
+        const uint32_t m = group_first_dr[dr_group[d]];
+        cbk::KswJob jb{dr_offsets[d], d == m ? 0u : dr_offsets[d + 1] - dr_offsets[d], dr_offsets[m], dr_offsets[m + 1] - dr_offsets[m], 0u, xtra};
+        jobs[2 * d] = jb; jb.q_rc = 1; jobs[2 * d + 1] = jb;
+    }
+    size_t at = 0;
+    auto carve = [&](size_t bytes) { const size_t o = at; at += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t cols = (size_t)n_groups * array_len;
+    const size_t o_bases = carve(n_bases + 16), o_offs = carve(((size_t)n_reads + 1) * 8), o_rdr = carve((size_t)n_reads * 4 + 4),
+                 o_sso = carve(((size_t)n_reads + 1) * 4), o_ssp = carve((size_t)n_ss * 4 + 4), o_pool = carve((size_t)dr_total + (size_t)n_drs * kExtStride + 16),
+                 o_dro = carve(((size_t)n_drs + 1) * 4), o_drg = carve((size_t)n_drs * 4), o_gf = carve(((size_t)n_groups + 1) * 4),
+                 o_place = carve((size_t)n_drs * 4), o_flags = carve(n_drs), o_extr = carve((size_t)n_drs * 4), o_extl = carve((size_t)n_drs * 4),
+                 o_jobs = carve(jobs.size() * sizeof(cbk::KswJob)), o_jobs2 = carve(jobs.size() * sizeof(cbk::KswJob)), o_j2dr = carve((size_t)n_drs * 4),
+                 o_res = carve(jobs.size() * sizeof(cbk::KswResult)), o_cnt = carve(256),
+                 o_cov = carve(cols * 16), o_cons = carve(cols), o_conserv = carve(cols * 4), o_zone = carve((size_t)n_groups * 8), o_good = carve((size_t)n_groups * 4);
+    if (int r = c->d_cons.reserve(at)) return r;
+    uint8_t* d = c->d_cons.as<uint8_t>();
+    const uint64_t zero_off = 0;
+    if (n_reads) {
+        CUDA_TRY(cudaMemcpyAsync(d + o_bases, bases, n_bases, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d + o_offs, offsets, ((size_t)n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d + o_rdr, read_dr, (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d + o_sso, ss_offsets, ((size_t)n_reads + 1) * 4, cudaMemcpyHostToDevice, st));
+        if (n_ss) CUDA_TRY(cudaMemcpyAsync(d + o_ssp, ss_pool, (size_t)n_ss * 4, cudaMemcpyHostToDevice, st));
+    } else CUDA_TRY(cudaMemcpyAsync(d + o_offs, &zero_off, 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d + o_pool, dr_bytes, dr_total, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d + o_dro, dr_offsets, ((size_t)n_drs + 1) * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d + o_drg, dr_group.data(), (size_t)n_drs * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d + o_gf, group_first_dr, ((size_t)n_groups + 1) * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d + o_jobs, jobs.data(), jobs.size() * sizeof(cbk::KswJob), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(d + o_cnt, 0, 256, st));
+    CUDA_TRY(cudaMemsetAsync(d + o_cov, 0, cols * 16, st));
+    CUDA_TRY(cudaMemsetAsync(d + o_good, 0, (size_t)n_groups * 4, st));
+    uint32_t* cnt = (uint32_t*)(d + o_cnt);                                    // [0] round-2 slaves, [1] status bits
+    cbk::ConsArrays a{d + o_bases, (const uint64_t*)(d + o_offs), n_reads, (const uint32_t*)(d + o_rdr), (const uint32_t*)(d + o_sso),
+                      (const uint32_t*)(d + o_ssp), d + o_pool, (const uint32_t*)(d + o_dro), n_drs, (const uint32_t*)(d + o_drg),
+                      (const uint32_t*)(d + o_gf), n_groups, array_len, dr_total, kExtStride, (int32_t*)(d + o_place), d + o_flags,
+                      (uint32_t*)(d + o_extr), (uint32_t*)(d + o_extl), (cbk::KswJob*)(d + o_jobs2), cnt, (uint32_t*)(d + o_j2dr),
+                      (int32_t*)(d + o_cov), d + o_cons, (float*)(d + o_conserv), (int32_t*)(d + o_zone), (uint32_t*)(d + o_good)};
+    cbk::KswResult* res = (cbk::KswResult*)(d + o_res);
+    const uint32_t n_jobs = 2 * n_drs;
+    cbk::k_ksw_align<<<(n_jobs * 8 + 127) / 128, 128, 0, st>>>(d + o_pool, (const cbk::KswJob*)(d + o_jobs), nullptr, n_jobs, res);
+    cbk::k_cons_decide<<<(n_drs + 127) / 128, 128, 0, st>>>(a, res, nullptr, nullptr, n_drs, 1);
+    // slaves whose forward and reverse scores are equal: extendSlaveDR, then once more (lists built on the device, launches sized for all)
+    if (n_reads) cbk::k_cons_ext_find<<<(n_reads + 127) / 128, 128, 0, st>>>(a);
+    cbk::k_cons_ext_build<<<(n_drs + 127) / 128, 128, 0, st>>>(a, xtra);
+    cbk::k_ksw_align<<<(n_jobs * 8 + 127) / 128, 128, 0, st>>>(d + o_pool, a.jobs2, cnt, n_jobs, res);
+    cbk::k_cons_decide<<<(n_drs + 127) / 128, 128, 0, st>>>(a, res, a.job2_dr, cnt, n_drs, 2);
+    if (n_reads) cbk::k_cons_place<<<(n_reads * 32 + 127) / 128, 128, 0, st>>>(a, cnt + 1);
+    cbk::k_cons_columns<<<(uint32_t)((cols + 255) / 256), 256, 0, st>>>(a);
+    cbk::k_cons_zone<<<(n_groups + 63) / 64, 64, 0, st>>>(a);
+    c->launches += 7 + (n_reads ? 2 : 0);
+    CUDA_TRY(cudaGetLastError());
+    uint32_t h_cnt[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(dr_place, d + o_place, (size_t)n_drs * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(dr_flags, d + o_flags, n_drs, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(zone, d + o_zone, (size_t)n_groups * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(consensus, d + o_cons, cols, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(conservation, d + o_conserv, cols * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(coverage, d + o_cov, cols * 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h_cnt, cnt, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (status) *status = h_cnt[1];
+    return 0;
 }
 
 // ---- K1 ------------------------------------------------------------------------------------------------

@@ -1864,3 +1864,4 @@ __global__ void k_qc_one(const uint8_t* __restrict__ seq, uint32_t L, const uint
 }  // namespace cbk
 
 #include "cluster.cuh"
+#include "consensus.cuh"

@@ -320,6 +320,33 @@ int crass_b200_ac_build_from_block(const void* block, uint32_t cap, uint32_t str
                                    uint32_t* count, uint32_t* flags, uint32_t* n_patterns);
 int crass_b200_ac_build_from_pattern_list(const char* patterns, crass_b200_ac** out, uint32_t* n_patterns);
 
+/* ---- K7: consensus ("true") DR of DR groups (second half) ----------------------------------------------
+ * Replaces, for the groups WorkHorse::parseGroupedDRs (WorkHorse.cpp:1135-1171) walks, Aligner::setMasterDR / alignSlave /
+ * generateConsensus (Aligner.cpp:72-246) and the ksw_align (ksw.c:330-354) under them.
+ *
+ * crass_b200_ksw_align: a batch of ksw_align calls with the Aligner's scoring (match 1, mismatch -3, ambiguous 0, gap open 5,
+ * extend 2; Aligner.h:105-131), 16-bit kernel.  Sequences are LETTERS in `pool` (nt4-coded on the device as
+ * Aligner::prepareSequenceForAlignment does); q_rc != 0 aligns the reverse complement of the query.  All HOST pointers.
+ *
+ * crass_b200_consensus_groups: n_groups groups at once.  DRs group_first_dr[g] .. group_first_dr[g+1]-1 belong to group g, the
+ * first of them is its master (findMasterDR: the longest).  reads: the reads hanging on those DRs, back to back (offsets[n_reads
+ * + 1]), read_dr[i] = DR index, start/stop list of read i = ss_pool[ss_offsets[i] .. ss_offsets[i+1]).  array_len =
+ * CRASS_DEF_CONS_ARRAY_RL_MULTIPLIER * max read length.  Out: dr_place[n_drs] (AL_Offsets, -1 = the slave could not be placed),
+ * dr_flags[n_drs] (bit 0: slave and its reads were reverse complemented, bit 1: alignment failed, bit 2: forward and reverse
+ * scores stayed equal), and per group zone[2] (AL_ZoneStart/End after generateConsensus), consensus[array_len],
+ * conservation[array_len], coverage[4 * array_len] (rows A C G T).  *status: bit 0 = a read without a full-length repeat was
+ * skipped, bit 1 = a read reached past the array (the reference writes out of bounds in both cases).  All HOST pointers. */
+typedef struct { uint32_t q_off, q_len, t_off, t_len, q_rc; int32_t xtra; } crass_b200_ksw_job;
+typedef struct { int32_t score, te, qe, score2, te2, tb, qb, status; } crass_b200_ksw_result;
+int crass_b200_ksw_align(crass_b200_ctx* ctx, const uint8_t* pool, uint64_t pool_bytes, const crass_b200_ksw_job* jobs, uint32_t n_jobs,
+                         crass_b200_ksw_result* out);
+int crass_b200_consensus_groups(crass_b200_ctx* ctx, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
+                                const uint32_t* read_dr, const uint32_t* ss_offsets, const uint32_t* ss_pool,
+                                const uint8_t* dr_bytes, const uint32_t* dr_offsets, uint32_t n_drs,
+                                const uint32_t* group_first_dr, uint32_t n_groups, uint32_t array_len,
+                                int32_t* dr_place, uint8_t* dr_flags, int32_t* zone, uint8_t* consensus, float* conservation,
+                                int32_t* coverage, uint32_t* status);
+
 /* ---- whole path, one call: searchFile* -> createNonRedundantSet -> findSingletons* --------------- */
 int crass_b200_run_files(crass_b200_ctx* ctx, const char* const* paths, uint32_t n_paths,
                          const crass_b200_params* params, int phases, crass_b200_results** out, int* max_read_len);

@@ -796,3 +796,69 @@ def test_update_start_stops_on_the_hits_of_a_bundled_read_set(ctx, k6path):
         seq = bytes(bases[int(offsets[r]): int(offsets[r + 1])])
         want = P.update_start_stops(seq, ss, front, drs[d])
         assert (st, out) == ((3, []) if want[0] == -3 else (0, want[1]))
+
+
+# ---- K7: consensus DR of DR groups (ksw_align + Aligner) --------------------------------------------------------------------
+
+def test_ksw_align_golden_vectors_and_fuzz(ctx, P):
+    """k_ksw_align (eight threads per alignment, one per lane of the reference's striped SSE2 kernel) against the vectors the
+    compiled reference made and against the oracle on fresh cases: score, both end points, both start points."""
+    g = json.load(open(os.path.join(G, "consensus_vectors.json")))
+    got = ctx.ksw_align([(v["q"].encode(), v["t"].encode(), False) for v in g["ksw_align"]])
+    for v, r in zip(g["ksw_align"], got):
+        assert list(r) == v["out"], (v["q"], v["t"])
+    rng = random.Random(112)
+    nt = bytes.maketrans(b"ACGTN", bytes([0, 1, 2, 3, 4]))
+    comp = bytes.maketrans(b"ACGTN", b"TGCAN")
+    for xtra in (0x80000 | 0x40000 | 5, 0x80000, 0x40000 | 12, 0):
+        pairs = []
+        for _ in range(1500):
+            t = fuzzgen.rand_seq(rng, rng.randint(8, 150))
+            if rng.random() < 0.75:
+                a, b = sorted(rng.sample(range(len(t)), 2))
+                q = fuzzgen.mutate(rng, t[a:b + 1][:120], rng.choice([0, 0.05, 0.2]), b"ACGTN")
+                if rng.random() < 0.3 and len(q) > 6:
+                    k = rng.randint(1, len(q) - 2)
+                    q = q[:k] + fuzzgen.rand_seq(rng, rng.randint(1, 3)) + q[k:]
+                if rng.random() < 0.3 and len(q) > 8:
+                    k = rng.randint(1, len(q) - 4)
+                    q = q[:k] + q[k + rng.randint(1, 3):]
+            else:
+                q = fuzzgen.rand_seq(rng, rng.randint(1, 128))
+            if q:
+                pairs.append((q, t, rng.random() < 0.4))
+        got = ctx.ksw_align(pairs, xtra)
+        for (q, t, rc), r in zip(pairs, got):
+            qq = q.translate(comp)[::-1] if rc else q
+            assert r == P.ksw_align(qq.translate(nt), t.translate(nt), xtra), (q, t, rc, xtra)
+
+
+def test_consensus_groups_golden_vectors_and_fuzz(ctx, P):
+    """K7 on whole DR groups: placements, strands, the extendSlaveDR detour, coverage rows, consensus, conservation bits and the
+    DR zone must be those of the reference's Aligner (golden vectors) and of the oracle (fresh groups, many per call)."""
+    import hashlib
+    import struct
+    from test_oracle_golden import consensus_expected
+    g = json.load(open(os.path.join(G, "consensus_vectors.json")))
+    exp = [consensus_expected(grp) for grp in g["groups"]]
+    got, status = ctx.consensus_groups([e[0] for e in exp])
+    assert status == 0
+    for (case, want, md5, cov), out in zip(exp, got):
+        c = out.pop("coverage")
+        out.pop("flags")
+        assert want.pop("status") == 0 and out == want
+        assert hashlib.md5(struct.pack("<%di" % len(c), *c)).hexdigest() == md5
+    rng = random.Random(113)
+    for batch in range(6):
+        cases = [fuzzgen.consensus_case(rng, alphabet=b"ACGTN" if k % 5 == 0 else b"ACGT") for k in range(1 if batch == 0 else 60)]
+        got, status = ctx.consensus_groups(cases)
+        assert status == 0
+        turned = 0
+        for case, out in zip(cases, got):
+            want = P.consensus_group(case)
+            assert want.pop("status") == 0
+            flags = out.pop("flags")
+            assert out == want
+            assert all(((f >> 1) & 1) == (p < 0) for f, p in zip(flags[1:], out["place"][1:]))
+            turned += sum(out["reversed"])
+        assert batch == 0 or turned > 20
