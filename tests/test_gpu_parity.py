@@ -862,3 +862,71 @@ def test_consensus_groups_golden_vectors_and_fuzz(ctx, P):
             assert all(((f >> 1) & 1) == (p < 0) for f, p in zip(flags[1:], out["place"][1:]))
             turned += sum(out["reversed"])
         assert batch == 0 or turned > 20
+
+
+def test_consensus_of_a_bundled_read_set_feeds_partial_repeat_recovery(ctx, P, k6path):
+    """The chain behind the scan, on the reference's own reads: K1's hits of Ill100.fx.gz -> low-lexi DR tokens -> the groups
+    createNonRedundantSet forms -> K7 (master = longest DR of the group, every other DR aligned against it, consensus and zone
+    from the coverage of all their reads) -> the zone's consensus as the DR K6 shifts every read's repeats to.  K7 against the
+    oracle's Aligner group by group, K6 against the oracle's updateStartStops read by read."""
+    if not os.path.exists(os.path.join(checkers.REF_DATA, "Ill100.fx.gz")):
+        pytest.skip("bundled read sets not staged")
+    n_groups = n_drs = n_jobs = n_grew = 0
+    for name in ("Ill100.fx.gz", "CN_gDC.fa.gz", "front_offset_bug.fa.gz"):
+        a, b, c, d = _consensus_chain(ctx, P, os.path.join(checkers.REF_DATA, name))
+        n_groups += a; n_drs += b; n_jobs += c; n_grew += d
+    assert n_groups >= 3 and n_drs > 50 and n_jobs > 200 and n_grew > 0
+
+
+def _consensus_chain(ctx, P, path):
+    batch = cb.Batch.from_file(path)
+    bases, offsets = batch.bases, batch.offsets
+    hits, pool, _ = ctx.dr_search(bases, offsets)
+    reads_of, order = {}, []                                             # token string -> oriented reads, tokens in first-appearance order
+    for h in sorted(hits, key=lambda h: int(h["read_index"])):
+        r, o, n = int(h["read_index"]), int(h["ss_offset"]), int(h["n_ss"])
+        seq = bytes(bases[int(offsets[r]): int(offsets[r + 1])])
+        dr, low, ss2, seq2 = P.dr_lowlexi(seq, [int(x) for x in pool[o: o + n]])
+        if dr not in reads_of:
+            reads_of[dr] = []
+            order.append(dr)
+        reads_of[dr].append((seq2, ss2))
+    groups = {}
+    for line in api.non_redundant_set(order, 6).split("\n"):
+        if line.startswith("G\t"):
+            _, tok, gid = line.split("\t")
+            groups.setdefault(int(gid), []).append(order[int(tok) - 2])
+    cases = []
+    for gid in sorted(groups):
+        drs = groups[gid]
+        m = max(range(len(drs)), key=lambda i: (len(drs[i]), -i))         # findMasterDR: the first of the longest
+        drs = [drs[m]] + drs[:m] + drs[m + 1:]
+        cases.append(dict(drs=drs, reads=[(s_, ss_, d) for d, dr in enumerate(drs) for (s_, ss_) in reads_of[dr]], array_len=4 * batch.max_read_len))
+    got, status = ctx.consensus_groups(cases)
+    assert status == 0
+    jobs, job_drs, all_reads = [], [], []
+    for case, out in zip(cases, got):
+        want = P.consensus_group(case)
+        assert want.pop("status") == 0
+        out.pop("flags")
+        assert out == want
+        true_dr = out["consensus"][out["zone"][0]: out["zone"][1] + 1]
+        if not (23 <= len(true_dr) <= 47):
+            continue
+        job_drs.append(true_dr)
+        for (seq, ss, d) in case["reads"]:
+            if out["place"][d] < 0 or out["reversed"][d]:
+                continue
+            front = out["place"][d] - out["zone"][0]                      # where the read's DR starts inside the consensus DR
+            jobs.append((len(all_reads), ss, front, len(job_drs) - 1))
+            all_reads.append(seq)
+    if not jobs:
+        return len(cases), sum(len(c["drs"]) for c in cases), 0, 0
+    b2, o2 = cb.pack_reads(all_reads)
+    res = ctx.update_start_stops(b2, o2, job_drs, jobs)
+    grew = 0
+    for (st, out), (r, ss, front, d) in zip(res, jobs):
+        want = P.update_start_stops(all_reads[r], ss, front, job_drs[d])
+        assert (st, out) == ((3, []) if want[0] == -3 else (0, want[1]))
+        grew += len(out) > len(ss)
+    return len(cases), sum(len(c["drs"]) for c in cases), len(jobs), grew
