@@ -1237,7 +1237,7 @@ int ensure_ac_on_device(crass_b200_ctx* c, crass_b200_ac* ac) {
             memcpy(c->h_ac_stage.as<uint8_t>() + at, ones_init, sizeof ones_init);      // 
             CUDA_TRY(cudaMemcpyAsync(c->d_ac_ones.p, c->h_ac_stage.as<uint8_t>() + at, sizeof ones_init, cudaMemcpyHostToDevice, c->stream));
             cbk::MatcherTables m{c->d_ac_pbytes.as<uint8_t>(), c->d_ac_poffs.as<uint32_t>(), a.n_patterns,
-                                 c->d_ac_bitmap.as<uint32_t>(), a.q_bits, c->d_ac_bitmap_small.as<uint32_t>(), a.q_bits_small,
+                                 c->d_ac_bitmap.as<uint32_t>(), a.q_bits, a.q_hashes, c->d_ac_bitmap_small.as<uint32_t>(), a.q_bits_small,
                                  c->d_ac_keys.as<uint32_t>(), a.q_table_bits, c->d_ac_skeys.as<uint32_t>(), c->d_ac_shead.as<uint32_t>(),
                                  a.s_bits, c->d_ac_pnext.as<uint32_t>(), c->d_ac_ones.as<uint32_t>()};
             cbk::k_ac_build<<<(a.n_patterns * 8 + 255) / 256, 256, 0, c->stream>>>(m);
@@ -1292,7 +1292,7 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         if (int r = c->d_cand_mask.reserve(((size_t)n_reads + 16) * sizeof(uint64_t))) return r;
         uint32_t* cand = c->d_cand.as<uint32_t>();
         uint64_t* cmask = c->d_cand_mask.as<uint64_t>();
-        cbk::QgramFilter q{c->d_ac_bitmap.as<uint32_t>(), c->d_ac_keys.as<uint32_t>(), ac->a.q_bits, ac->a.q_table_bits, c->d_ac_ones.as<uint32_t>()};
+        cbk::QgramFilter q{c->d_ac_bitmap.as<uint32_t>(), c->d_ac_keys.as<uint32_t>(), ac->a.q_bits, ac->a.q_table_bits, ac->a.q_hashes, c->d_ac_ones.as<uint32_t>()};
         const uint32_t n_tiles = (n_reads + cbk::kAcTile - 1) / cbk::kAcTile;
         const size_t bm_bytes = ((size_t)1 << ac->a.q_bits) / 8;
 #define CB_ACF(NW)                                                                                                              \
@@ -1363,7 +1363,7 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         if (!d_found) { if (int r = c->d_found.reserve((size_t)n_reads + 16)) return r; d_found = c->d_found.as<uint8_t>(); }
         if (int r = c->d_cand.reserve(((size_t)n_reads + 16) * sizeof(uint32_t))) return r;
         uint32_t* cand = c->d_cand.as<uint32_t>();
-        cbk::QgramFilter q{c->d_ac_bitmap.as<uint32_t>(), c->d_ac_keys.as<uint32_t>(), ac->a.q_bits, ac->a.q_table_bits, c->d_ac_ones.as<uint32_t>()};
+        cbk::QgramFilter q{c->d_ac_bitmap.as<uint32_t>(), c->d_ac_keys.as<uint32_t>(), ac->a.q_bits, ac->a.q_table_bits, ac->a.q_hashes, c->d_ac_ones.as<uint32_t>()};
         const size_t smem = ((size_t)1 << ac->a.q_bits) / 8;
         const char* fsel = getenv("CRASS_B200_K2F");
         const bool use_packed = c->packed_valid && c->packed_src == (const void*)d_bases && c->packed_reads == n_reads &&

@@ -397,7 +397,7 @@ struct MatcherTables {
     const uint8_t* pbytes;
     const uint32_t* poffs;
     uint32_t n_patterns;
-    uint32_t* bitmap;  uint32_t bits;
+    uint32_t* bitmap;  uint32_t bits;  uint32_t hashes;
     uint32_t* bitmap_small;  uint32_t bits_small;       // 0 = none
     uint32_t* keys;  uint32_t table_bits;
     uint32_t* s_keys;  uint32_t* s_head;  uint32_t s_bits;
@@ -416,6 +416,11 @@ k_ac_build(MatcherTables m) {
     const uint32_t h = (code * 0x9E3779B1u) >> (32 - m.bits);
     atomicOr(&m.bitmap[h >> 5], 1u << (h & 31));
     if (m.bits_small) { const uint32_t hs = h >> (m.bits - m.bits_small); atomicOr(&m.bitmap_small[hs >> 5], 1u << (hs & 31)); }
+    if (m.hashes > 1) {                                                          // second hash of the Bloom filter (qgram_second_bit)
+        const uint32_t h2 = (code * kQgramHash2) >> (32 - m.bits);
+        atomicOr(&m.bitmap[h2 >> 5], 1u << (h2 & 31));
+        if (m.bits_small) { const uint32_t hs = h2 >> (m.bits - m.bits_small); atomicOr(&m.bitmap_small[hs >> 5], 1u << (hs & 31)); }
+    }
     if (code == 0xFFFFFFFFu) {
         m.ones[0] = 1;
         if (w == 0) m.p_next[i] = atomicExch(&m.ones[1], i);

@@ -69,6 +69,10 @@ static void plan_filter_and_starts(Automaton* A) {
     uint32_t fold_max = 16384;
     if (const char* e = getenv("CRASS_B200_QGRAM_FOLD_MAX")) fold_max = (uint32_t)strtoul(e, nullptr, 10);
     if (A->q_bits == 19 && positions <= fold_max) A->q_bits_small = 18;
+    // two hash functions behind the bitmap while that keeps it sparse (kernels.cuh: qgram_second_bit)
+    uint32_t two_max = 100000;
+    if (const char* e = getenv("CRASS_B200_QGRAM_TWO_MAX")) two_max = (uint32_t)strtoul(e, nullptr, 10);
+    A->q_hashes = positions <= two_max ? 2 : 1;
     uint32_t sbits = 4;
     while (((size_t)1 << sbits) < (size_t)n * 2 + 2) ++sbits;
     A->s_bits = sbits;
@@ -101,6 +105,11 @@ static void fill_filter_and_starts_on_host(Automaton* A) {
             const uint32_t h = qgram_hash(code, A->q_bits);
             A->q_bitmap[h >> 5] |= 1u << (h & 31);
             if (A->q_bits_small) { const uint32_t hs = h >> 1; A->q_bitmap_small[hs >> 5] |= 1u << (hs & 31); }
+            if (A->q_hashes > 1) {                                               // second hash of the Bloom filter (kernels.cuh: qgram_second_bit)
+                const uint32_t h2 = (code * 0xC2B2AE35u) >> (32 - A->q_bits);
+                A->q_bitmap[h2 >> 5] |= 1u << (h2 & 31);
+                if (A->q_bits_small) { const uint32_t hs = h2 >> 1; A->q_bitmap_small[hs >> 5] |= 1u << (hs & 31); }
+            }
             if (code == 0xFFFFFFFFu) { distinct += !A->q_has_ones; A->q_has_ones = 1; }
             else {
                 uint32_t slot = (code * 0x85EBCA6Bu) >> (32 - tbits);

@@ -123,6 +123,7 @@ struct Automaton {
     // q-gram pre-filter + pattern-start table (ac_build.cpp): empty when the shortest pattern is below 23 bytes
     uint32_t q_bits = 0, q_table_bits = 0, q_count = 0, q_has_ones = 0;
     std::vector<uint32_t> q_bitmap, q_keys;
+    uint32_t q_hashes = 1;                      // hash functions behind the bitmap (1 or 2)
     uint32_t q_bits_small = 0;                  // 0 = none; else a folded copy of the bitmap with fewer bits (same hash family)
     std::vector<uint32_t> q_bitmap_small;
     uint32_t s_bits = 0, s_ones_head = 0xFFFFFFFFu;
