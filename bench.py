@@ -219,7 +219,7 @@ class Resident:
 
     HOST_KEYS = ("k1_wait", "exchange_cluster", "matcher_build", "ac_upload", "k2_wait", "fetch_hits2")
 
-    def __init__(self, ctx, dev, world, d_bases, d_offsets, n, max_len, params, stream, hits_frac=4, pool_per_read=1.0, cap=16384):
+    def __init__(self, ctx, dev, world, d_bases, d_offsets, n, max_len, params, stream, hits_frac=4, pool_per_read=1.0, cap=8192):
         import torch
         from crass_b200 import dist as cbdist
         self.torch, self.ctx, self.dev, self.world, self.n, self.max_len, self.params, self.stream = torch, ctx, dev, world, n, max_len, params, stream
@@ -235,6 +235,7 @@ class Resident:
         self.d_tokens = torch.empty(self.hits_cap * TOK, dtype=torch.uint8, device=dev)
         self.h_hits = [torch.empty(self.hits_cap * 4, dtype=torch.int32, pin_memory=True) for _ in range(2)]
         self.h_pool = [torch.empty(self.pool_cap, dtype=torch.int32, pin_memory=True) for _ in range(2)]
+        # token blocks of `cap` records per rank (they double by themselves if a shard ever holds more distinct DRs);
         # every rank merges the gathered token blocks and clusters them on its own GPU (K5: the whole of
         # createNonRedundantSet runs as kernels), so nothing is broadcast; CRASS_B200_EXCHANGE=root selects the
         # round-1 form (the root clusters on its host, one broadcast returns the pattern set) for comparison

@@ -154,7 +154,8 @@ int crass_b200_dr_search_dev(crass_b200_ctx* ctx, const uint8_t* d_bases, const 
                              uint8_t* d_found, crass_b200_hit* d_hits, uint32_t hits_cap,
                              uint32_t* d_ss_pool, uint32_t ss_cap, uint32_t* d_counters, void* stream);
 
-/* Host form: copies the batch in (pinned, chunked, double-buffered), runs K1, copies the hits out,
+/* Host form: copies the batch in (one asynchronous copy on the context's stream; the copy is 98 % of this call, so the
+ * multi-device engine below is where transfers are sliced over two copy streams), runs K1, copies the hits out,
  * sorted by read_index.  hits/ss_pool are malloc'd by the library (free with crass_b200_free).
  * found may be NULL. */
 int crass_b200_dr_search(crass_b200_ctx* ctx, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
