@@ -537,6 +537,7 @@ def main():
             j = torch.arange(47, device=dev)
             mask = j[None, :] < plen[:, None]
             d_bases[((pick * READ_LEN + at)[:, None] + j[None, :])[mask]] = d_mat[which][mask]
+            torch.cuda.synchronize()                                   # (the planting above is asynchronous: it must not land in the build time)
             t0 = time.perf_counter()
             ac = cb.Automaton(patterns)
             ctx.ac_upload(ac)

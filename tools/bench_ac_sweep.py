@@ -100,6 +100,7 @@ def main():
     for P in [int(x) for x in args.patterns.split(",")]:
         patterns = synth.pattern_set(P, seed=20245 + P)
         planted = plant(d_bases, n, patterns, 0.01, 20245 + 7 * P, dev)      # earlier sets stay in the reads as background
+        torch.cuda.synchronize()                                           # the planting is asynchronous
         t0 = time.perf_counter()
         ac = cb.Automaton(patterns)
         ctx.ac_upload(ac)
