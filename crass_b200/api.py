@@ -101,6 +101,9 @@ def lib():
         "crass_b200_extend_pre_repeat": (C.c_int, [vp, cp, C.c_uint32, u32p, C.c_uint32, C.c_uint32, C.c_uint32, u32p]),
         "crass_b200_qc_found_repeats": (C.c_int, [vp, cp, C.c_uint32, u32p, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_int)]),
         "crass_b200_parse_file": (C.c_int, [cp, C.POINTER(vp)]),
+        "crass_b200_parse_stream_open": (C.c_int, [cp, C.c_uint64, C.POINTER(vp)]),
+        "crass_b200_parse_stream_next": (C.c_int, [vp, C.POINTER(vp)]),
+        "crass_b200_parse_stream_close": (None, [vp]),
         "crass_b200_batch_from_memory": (C.c_int, [vp, vp, C.c_uint32, vp, C.POINTER(vp)]),
         "crass_b200_batch_destroy": (None, [vp]),
         "crass_b200_batch_num_reads": (C.c_uint32, [vp]),
@@ -204,6 +207,23 @@ class Batch:
         h = C.c_void_p()
         _check(lib().crass_b200_parse_file(path.encode(), C.byref(h)))
         return cls(h)
+
+    @classmethod
+    def stream_file(cls, path, range_bytes):
+        """The file's records as a sequence of batches of about range_bytes of input each (the streamed feed)."""
+        s = C.c_void_p()
+        _check(lib().crass_b200_parse_stream_open(path.encode(), range_bytes, C.byref(s)))
+        try:
+            while True:
+                h = C.c_void_p()
+                got = lib().crass_b200_parse_stream_next(s, C.byref(h))
+                if got < 0:
+                    _check(-got)
+                if got == 0:
+                    return
+                yield cls(h)
+        finally:
+            lib().crass_b200_parse_stream_close(s)
 
     @classmethod
     def from_arrays(cls, bases, offsets, names=None):

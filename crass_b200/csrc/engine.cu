@@ -25,6 +25,9 @@
 #include <chrono>
 #include <exception>
 #include <memory>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -147,6 +150,8 @@ struct crass_b200_engine {
     std::vector<std::unique_ptr<Lane> > lanes;
     std::vector<std::unique_ptr<FileState> > files;
     std::vector<crass_b200_batch*> batch_pool;            // released batches: their buffers (page-locked bases) serve the next parse
+    std::mutex pool_mu;                                   // ... taken by the parsing thread of a streamed run while another thread searches
+    size_t stream_bytes = (size_t)256 << 20;              // range size of the streamed feed (CRASS_B200_STREAM_MB; 0 = whole files)
     Nccl nccl;
     bool use_nccl = false;
     uint32_t block_cap = 16384;                           // token-block capacity per shard (grows on overflow)
@@ -183,22 +188,36 @@ int for_each_lane(crass_b200_engine* e, F fn) {
     return 0;
 }
 
-// kseq-compatible parse of `path` into a batch from the engine's pool (a fresh one the first time)
-int parse_pooled(crass_b200_engine* e, const char* path, crass_b200_batch** out) {
-    crass_b200_batch* h = nullptr;
-    if (!e->batch_pool.empty()) { h = e->batch_pool.back(); e->batch_pool.pop_back(); }
-    else h = new crass_b200_batch();
-    cbh::Batch* got = nullptr;
-    const int rc = cbh::parse_file(path, &got, &h->b);
-    if (rc) { e->batch_pool.push_back(h); return rc; }
-    *out = h;
-    return 0;
-}
-
 void retire_batch(crass_b200_engine* e, crass_b200_batch* b) {
     if (!b) return;
-    if (e->batch_pool.size() < 2) e->batch_pool.push_back(b);
+    std::lock_guard<std::mutex> g(e->pool_mu);
+    if (e->batch_pool.size() < 64) e->batch_pool.push_back(b);                 // (a streamed file is many small batches)
     else crass_b200_batch_destroy(b);
+}
+
+crass_b200_batch* take_batch(crass_b200_engine* e, size_t want_bytes) {       // the pooled batch whose base buffer fits best
+    std::lock_guard<std::mutex> g(e->pool_mu);
+    int best = -1;
+    for (size_t i = 0; i < e->batch_pool.size(); ++i) {
+        const size_t cap = e->batch_pool[i]->b.bases_cap;
+        if (best < 0) { best = (int)i; continue; }
+        const size_t bc = e->batch_pool[(size_t)best]->b.bases_cap;
+        if ((cap >= want_bytes && (bc < want_bytes || cap < bc)) || (cap < want_bytes && bc < want_bytes && cap > bc)) best = (int)i;
+    }
+    if (best < 0) return new crass_b200_batch();
+    crass_b200_batch* h = e->batch_pool[(size_t)best];
+    e->batch_pool.erase(e->batch_pool.begin() + best);
+    return h;
+}
+
+// kseq-compatible parse of `path` into a batch from the engine's pool (a fresh one the first time)
+int parse_pooled(crass_b200_engine* e, const char* path, crass_b200_batch** out) {
+    crass_b200_batch* h = take_batch(e, (size_t)-1);                          // whole files: the largest buffer there is
+    cbh::Batch* got = nullptr;
+    const int rc = cbh::parse_file(path, &got, &h->b);
+    if (rc) { retire_batch(e, h); return rc; }
+    *out = h;
+    return 0;
 }
 
 std::unique_ptr<Shard> take_shard(Lane& l) {
@@ -219,6 +238,9 @@ void make_shards(crass_b200_engine* e, FileState& fs) {               // contigu
         fs.shards.push_back(std::move(s));
     }
 }
+
+int search_parsed(crass_b200_engine* e, std::unique_ptr<FileState> fs, const crass_b200_params* params,
+                  const crass_b200_batch** batch_out, crass_b200_hit** hits_out, uint32_t* n_hits, uint32_t** pool_out, uint32_t* n_pool);
 
 FileState* find_file(crass_b200_engine* e, const char* path) {
     for (auto& f : e->files) if (f->path == path) return f.get();
@@ -363,6 +385,8 @@ int crass_b200_engine_create(const int* devices, uint32_t n_devices, crass_b200_
     }
     e->resident_budget = min_mem / 2;
     if (const char* v = getenv("CRASS_B200_RESIDENT_MB")) e->resident_budget = (size_t)strtoull(v, nullptr, 10) << 20;
+    if (const char* v = getenv("CRASS_B200_STREAM_MB")) e->stream_bytes = (size_t)strtoull(v, nullptr, 10) << 20;
+    if (const char* v = getenv("CRASS_B200_STREAM_BYTES")) e->stream_bytes = (size_t)strtoull(v, nullptr, 10);   // (tests: ranges of a few KB)
     // peer access for the block gather without NCCL
     for (size_t i = 0; i < devs.size(); ++i)
         for (size_t j = 0; j < devs.size(); ++j) {
@@ -439,7 +463,7 @@ void crass_b200_engine_release_file(crass_b200_engine* e, const char* path) {
         FileState* f = e->files[i].get();
         for (size_t g = 0; g < f->shards.size(); ++g) {
             Lane& l = *e->lanes[g];
-            if (l.spare.size() < 2) { l.spare.push_back(std::move(f->shards[g])); continue; }
+            if (l.spare.size() < 64) { l.spare.push_back(std::move(f->shards[g])); continue; }
             cudaSetDevice(l.device);
             f->shards[g]->d_bases.release(); f->shards[g]->d_offsets.release(); f->shards[g]->d_found.release();
         }
@@ -461,6 +485,17 @@ int crass_b200_engine_search_file(crass_b200_engine* e, const char* path, const 
     if (int r = parse_pooled(e, path, &fs->batch)) return r;
     fs->parse_ms = now_ms() - t0;
     e->t_parse += fs->parse_ms;
+    return search_parsed(e, std::move(fs), params, batch_out, hits_out, n_hits, pool_out, n_pool);
+}
+
+}  // extern "C"
+namespace {
+// searchFile from the parsed batch on: shards, copy in, K1 on every device, one hit list in read order
+int search_parsed(crass_b200_engine* e, std::unique_ptr<FileState> fs, const crass_b200_params* params,
+                  const crass_b200_batch** batch_out, crass_b200_hit** hits_out, uint32_t* n_hits, uint32_t** pool_out, uint32_t* n_pool) {
+    const std::string path_s = fs->path;
+    const char* path = path_s.c_str();
+    double t0 = now_ms();
     const cbh::Batch& b = fs->batch->b;
     const uint32_t G = (uint32_t)e->lanes.size();
     make_shards(e, *fs);
@@ -499,6 +534,115 @@ int crass_b200_engine_search_file(crass_b200_engine* e, const char* path, const 
     if (batch_out) *batch_out = f->batch;
     return 0;
 }
+
+// a queue between two stages of the streamed run
+template <class T>
+struct StageQueue {
+    std::mutex mu; std::condition_variable cv; std::deque<T> q; bool closed = false;
+    void push(T v) { { std::lock_guard<std::mutex> g(mu); q.push_back(std::move(v)); } cv.notify_one(); }
+    void close() { { std::lock_guard<std::mutex> g(mu); closed = true; } cv.notify_all(); }
+    bool pop(T& v) {
+        std::unique_lock<std::mutex> g(mu);
+        cv.wait(g, [&] { return !q.empty() || closed; });
+        if (q.empty()) return false;
+        v = std::move(q.front()); q.pop_front();
+        return true;
+    }
+};
+
+struct SearchedRange {
+    const crass_b200_batch* batch = nullptr;
+    crass_b200_hit* hits = nullptr; uint32_t nh = 0;
+    uint32_t* pool = nullptr; uint32_t np = 0;
+};
+
+int run_streamed(crass_b200_engine* e, cbh::ParseStream* ps, const char* path, const crass_b200_params* params, int phases,
+                 crass_b200_results* res, int* max_len) {
+    StageQueue<std::unique_ptr<FileState> > parsed;
+    StageQueue<SearchedRange> searched;
+    std::atomic<int> fail_rc{0};
+    std::string fail_msg;
+    std::mutex fail_mu;
+    auto note_failure = [&](int rc) {
+        std::lock_guard<std::mutex> g(fail_mu);
+        if (!fail_rc.load()) { fail_msg = crass_b200_last_error(); fail_rc.store(rc); }
+    };
+    std::vector<std::string> range_paths;
+    std::thread searcher([&]() {
+        std::unique_ptr<FileState> fs;
+        while (parsed.pop(fs)) {
+            if (fail_rc.load()) { retire_batch(e, fs->batch); continue; }
+            SearchedRange r;
+            const int rc = search_parsed(e, std::move(fs), params, &r.batch, &r.hits, &r.nh, &r.pool, &r.np);
+            if (rc) { note_failure(rc); continue; }
+            searched.push(r);
+        }
+        searched.close();
+    });
+    std::thread replayer([&]() {
+        SearchedRange r;
+        while (searched.pop(r)) {
+            if (!fail_rc.load()) {
+                const double t0 = now_ms();
+                const int rc = crass_b200_results_add_phase1(res, r.batch, r.hits, r.nh, r.pool);
+                e->t_replay += now_ms() - t0;
+                if (rc) note_failure(rc);
+            }
+            free(r.hits); free(r.pool);
+        }
+    });
+    // this thread: the parser (its own worker threads inside)
+    for (uint32_t i = 0; !fail_rc.load(); ++i) {
+        crass_b200_batch* h = take_batch(e, e->stream_bytes);
+        const double t0 = now_ms();
+        const int got = cbh::parse_stream_next(ps, &h->b);
+        e->t_parse += now_ms() - t0;
+        if (got <= 0) { retire_batch(e, h); if (got < 0) note_failure(-got); break; }
+        *max_len = std::max(*max_len, (int)h->b.max_len);
+        std::unique_ptr<FileState> fs(new FileState());
+        fs->path = std::string(path) + "#" + std::to_string(i);
+        fs->batch = h;
+        range_paths.push_back(fs->path);
+        parsed.push(std::move(fs));
+    }
+    parsed.close();
+    searcher.join();
+    replayer.join();
+    int rc = fail_rc.load();
+    if (rc) cbh::fail(rc, fail_msg);
+    if (!rc && phases >= 2) {
+        // the containers' token list (filled in read order above) is the sequential numbering
+        crass_b200_ac* ac = nullptr;
+        uint32_t n_pat = 0;
+        const double t0 = now_ms();
+        char* pats = crass_b200_results_non_redundant(res, params->kmer_clust, &n_pat);
+        free(pats);
+        if (n_pat) {
+            std::vector<uint8_t> bytes; std::vector<uint32_t> offs(1, 0);
+            for (const std::string& p : res->r.non_redundant) { bytes.insert(bytes.end(), p.begin(), p.end()); offs.push_back((uint32_t)bytes.size()); }
+            rc = crass_b200_ac_build(bytes.data(), offs.data(), n_pat, &ac);
+        }
+        e->t_exchange += now_ms() - t0;
+        for (size_t f = 0; f < range_paths.size() && !rc && ac; ++f) {
+            const crass_b200_batch* b = nullptr;
+            crass_b200_hit* hits = nullptr; uint32_t nh = 0, np = 0; uint32_t* pool = nullptr;
+            rc = crass_b200_engine_find_singletons(e, range_paths[f].c_str(), ac, 1, &b, &hits, &nh, &pool, &np);
+            if (!rc) {
+                const double t1 = now_ms();
+                rc = crass_b200_results_add_phase2(res, b, hits, nh, pool);
+                e->t_replay += now_ms() - t1;
+            }
+            free(hits); free(pool);
+        }
+        crass_b200_ac_destroy(ac);
+    } else if (!rc) {
+        res->r.lazy_kmer_clust = (int)params->kmer_clust;
+    }
+    for (const std::string& p : range_paths) crass_b200_engine_release_file(e, p.c_str());
+    return rc;
+}
+}  // namespace
+extern "C" {
 
 // findSingletons (libcrispr.cpp:444-518) for one file: every device scans its shard with the given matcher.  skip_found != 0
 // leaves out the reads phase 1 flagged on the device (their headers are in readsFound anyway); 0 scans every read, which is
@@ -628,6 +772,26 @@ int crass_b200_engine_run_files(crass_b200_engine* e, const char* const* paths, 
     if (int r = crass_b200_results_create(&res)) return r;
     int rc = 0, max_len = 0;
     const char* xsel = getenv("CRASS_B200_EXCHANGE");
+    // A large file is STREAMED (the reference's O(1)-memory kseq loop turned into a pipeline): the parser hands
+    // out ranges of about stream_bytes, each ending on a true record start; while its worker threads parse range i+1, a second
+    // thread copies range i to the devices and runs K1 on it, and a third replays the hits of range i-1 into the containers.
+    // The ranges then behave like the files of a multi-file run (token order from the containers, K2 over the resident ranges).
+    if (n_paths == 1 && e->stream_bytes) {
+        cbh::ParseStream* ps = cbh::parse_stream_open(paths[0], e->stream_bytes);
+        if (!ps) { crass_b200_results_destroy(res); return CRASS_B200_EIO; }
+        if (cbh::parse_stream_size(ps) >= 2 * e->stream_bytes) {
+            rc = run_streamed(e, ps, paths[0], params, phases, res, &max_len);
+            cbh::parse_stream_close(ps);
+            if (e->trace)
+                fprintf(stderr, "[crass_b200] engine run (streamed): parse %.1f ms, phase 1 (H2D + K1 + D2H) %.1f ms, clustering %.1f ms, phase 2 %.1f ms, replay %.1f ms (stages overlap)\n",
+                        e->t_parse, e->t_phase1, e->t_exchange, e->t_phase2, e->t_replay);
+            if (rc) { crass_b200_results_destroy(res); return rc; }
+            if (max_read_len) *max_read_len = max_len;
+            *out = res;
+            return 0;
+        }
+        cbh::parse_stream_close(ps);
+    }
     // One file (the common case): the token exchange on the devices numbers the tokens of the whole input, so nothing the
     // devices do next waits for the host containers -- the phase-1 hits are replayed on a helper thread while the devices
     // exchange, cluster and scan; only the phase-2 replay (which tests readsFound) has to come after it.

@@ -77,6 +77,31 @@ int crass_b200_parse_file(const char* path, crass_b200_batch** out) {
     return 0;
 }
 
+struct crass_b200_parse_stream { cbh::ParseStream* s; };
+
+int crass_b200_parse_stream_open(const char* path, uint64_t range_bytes, crass_b200_parse_stream** out) {
+    if (!path || !out) return fail(CRASS_B200_EINVAL, "NULL argument");
+    cbh::ParseStream* s = parse_stream_open(path, (size_t)range_bytes);
+    if (!s) return CRASS_B200_EIO;
+    *out = new crass_b200_parse_stream{s};
+    return 0;
+}
+
+int crass_b200_parse_stream_next(crass_b200_parse_stream* s, crass_b200_batch** out) {
+    if (!s || !out) return -fail(CRASS_B200_EINVAL, "NULL argument");
+    crass_b200_batch* h = new crass_b200_batch();
+    const int got = parse_stream_next(s->s, &h->b);
+    if (got <= 0) { delete h; *out = nullptr; return got; }
+    *out = h;
+    return 1;
+}
+
+void crass_b200_parse_stream_close(crass_b200_parse_stream* s) {
+    if (!s) return;
+    parse_stream_close(s->s);
+    delete s;
+}
+
 int crass_b200_batch_from_memory(const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, const char* const* names,
                                  crass_b200_batch** out) {
     if (!offsets || !out || (n_reads && !bases)) return fail(CRASS_B200_EINVAL, "NULL argument");

@@ -62,6 +62,14 @@ struct Batch {
 
 // parses into `reuse` when given (which the caller keeps owning, also on failure), else into a new Batch
 int parse_file(const char* path, Batch** out, Batch* reuse = nullptr);
+// the same record stream handed out range by range (about range_bytes of the input each; each range ends on a true record
+// start and carries kseq's stale comment / quality into the next): 1 = a range was parsed into `reuse`, 0 = the stream had
+// ended, < 0 = -(error code).  The batch of the LAST range carries the parse status of the stream, the others 0.
+struct ParseStream;
+ParseStream* parse_stream_open(const char* path, size_t range_bytes);
+size_t parse_stream_size(const ParseStream* s);
+int parse_stream_next(ParseStream* s, Batch* reuse);
+void parse_stream_close(ParseStream* s);
 
 // ---- the containers the reference fills (ReadMap / StringCheck / lookupTable) ----------------------
 struct HeldRead {                       // the fields of ReadHolder the path sets (ReadHolder.h:440-451)

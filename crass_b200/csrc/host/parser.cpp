@@ -298,156 +298,195 @@ size_t env_size(const char* name, size_t dflt) {
 // resynchronisation point that can be recognised locally ('@' and '>' are legal quality characters), so a piece is
 // only kept when the piece before it ENDS exactly on the header it started from; otherwise the gap is parsed again
 // from the true position on the calling thread.  The record stream is therefore the sequential one by construction.
+//
+// parse_range() is that for the records whose header lies in [start, about stop_hint): the unit of the streamed feed
+// (ParseStream below).  start == SIZE_MAX: from the top of the file; stop_hint == SIZE_MAX: to the end.  A range ends on a
+// TRUE record start (out->next_hp, where the next range begins); what kseq carries from record to record -- the stale
+// comment and quality strings -- travels in the RangeCarry.
+namespace {
+struct RangeCarry {
+    size_t next_hp = (size_t)-1;
+    bool has_comment = false, has_qual = false;
+    std::string comment, qual;
+    int status = 0;                                       // 0: more records follow; -1 / -2: the stream ended in this range
+};
+
+void parse_range(Input& in, size_t start, size_t stop_hint, const RangeCarry* cin, Batch* B, RangeCarry* cout) {
+    B->reset();
+    B->offsets.push_back(0);
+    const size_t n = in.size;
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 1;
+    const size_t n_threads = env_size("CRASS_B200_PARSE_THREADS", hw < 16 ? hw : 16);
+    const size_t chunk = env_size("CRASS_B200_PARSE_CHUNK", (size_t)16 << 20);
+    const bool whole = start == (size_t)-1 && stop_hint == (size_t)-1 && !cin && !cout;
+    const size_t first = start == (size_t)-1 ? 0 : start;
+    // the range's end: a guessed record start at or after stop_hint (SIZE_MAX: the range runs to the end of the input)
+    size_t range_stop = (size_t)-1;
+    if (stop_hint != (size_t)-1 && stop_hint < n) range_stop = guess_record_start(in.data, n, stop_hint, n);
+    const size_t limit = range_stop == (size_t)-1 ? n : range_stop;
+    std::vector<size_t> starts;                           // header positions the pieces 1.. start from
+    if (n_threads > 1 && limit - first > chunk) {
+        for (size_t at = first + chunk; at < limit; at += chunk) {
+            const size_t s = guess_record_start(in.data, n, at, at + chunk < limit ? at + chunk : limit);
+            if (s != (size_t)-1 && s < limit && (starts.empty() || s > starts.back())) starts.push_back(s);
+        }
+    }
+    if (starts.empty() && whole) {                        // one piece, written straight into the batch
+        B->reserve_bases(n + 16);
+        Piece P;
+        P.bases = B->bases; P.cap = B->bases_cap;
+        parse_span(in.data, n, (size_t)-1, (size_t)-1, P);
+        B->name_pool.swap(P.name_pool); B->text_pool.swap(P.text_pool);   // piece-relative == batch-relative here
+        B->name_off.swap(P.name_off); B->comment_off.swap(P.comment_off); B->qual_off.swap(P.qual_off);
+        B->offsets.reserve(P.ends.size() + 1);
+        B->offsets.insert(B->offsets.end(), P.ends.begin(), P.ends.end());
+        B->max_len = P.max_len;
+        B->parse_status = P.status;
+        return;
+    }
+    const size_t np = starts.size() + 1;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    // one anonymous mapping for the bases of all pieces (huge pages when the kernel grants them: a 16 MB malloc per piece
+    // was 400 k page faults on the way in and as many pages to give back), unmapped on a detached thread at the end
+    struct Scratch {
+        uint8_t* p = nullptr; size_t len = 0;
+        ~Scratch() { if (p) Input::unmap_later(p, len); }
+    } scratch_map;
+    scratch_map.len = (limit - first) + 64 * np + 4096;
+    void* sm = mmap(nullptr, scratch_map.len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (sm == MAP_FAILED) throw std::bad_alloc();
+    scratch_map.p = (uint8_t*)sm;
+    madvise(sm, scratch_map.len, MADV_HUGEPAGE);
+    uint8_t* const scratch = scratch_map.p;
+    std::vector<Piece> pieces(np);
+    std::atomic<size_t> next{0};
+    std::atomic<bool> failed{false};
+    auto work = [&]() {
+        for (;;) {
+            const size_t k = next.fetch_add(1);
+            if (k >= np || failed.load()) return;
+            try {
+                Piece& P = pieces[k];
+                const size_t from = k ? starts[k - 1] : first, stop = k + 1 < np ? starts[k] : range_stop;
+                // a piece's bases are a subset of its bytes: its slice of the scratch mapping, at its own file offset
+                P.own = false;
+                P.cap = ((stop == (size_t)-1 ? n : stop) - from) + 64;
+                P.bases = scratch + (from - first) + 64 * k;
+                parse_span(in.data, n, k ? from : start, stop, P);
+            } catch (...) { failed.store(true); }
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        const size_t nt = n_threads < np ? n_threads : np;
+        for (size_t t = 1; t < nt; ++t) pool.emplace_back(work);
+        work();
+        for (auto& t : pool) t.join();
+    }
+    if (failed.load()) throw std::bad_alloc();
+
+    const double t1 = now();
+    // walk the pieces in file order; `order` lists what the sequential reader would have produced
+    std::vector<const Piece*> order;
+    std::vector<std::unique_ptr<Piece>> patches;
+    size_t k = 0;
+    const Piece* cur = &pieces[0];
+    int status = 0;
+    size_t end_hp = (size_t)-1;
+    for (;;) {
+        order.push_back(cur);
+        if (cur->status != 0) { status = cur->status; break; }
+        const size_t hp = cur->next_hp;
+        if (hp >= range_stop) { end_hp = hp; break; }                 // the range is complete: the next one starts at hp
+        while (k < starts.size() && starts[k] < hp) ++k;          // pieces that began inside a record
+        if (k < starts.size() && starts[k] == hp) { cur = &pieces[++k]; continue; }
+        std::unique_ptr<Piece> Q(new Piece());                    // no piece begins here: parse up to the next one
+        const size_t stop = k < starts.size() ? starts[k] : range_stop;
+        Q->own = true;
+        Q->cap = ((stop == (size_t)-1 ? n : stop) - hp) + 64;
+        Q->bases = (uint8_t*)malloc(Q->cap);
+        if (!Q->bases) throw std::bad_alloc();
+        parse_span(in.data, n, hp, stop, *Q);
+        cur = Q.get();
+        patches.push_back(std::move(Q));
+    }
+    // where each piece lands in the batch, and the stale comment/quality it inherits (a range inherits the strings the
+    // range before it left: they open this batch's text pool)
+    struct Slot { uint64_t base0, rec0, name0; int64_t text0, in_comment, in_qual; };
+    std::vector<Slot> slot(order.size());
+    uint64_t total = 0, n_rec = 0, n_name = 0;
+    int64_t n_text = 0, cc = -1, cq = -1;
+    if (cin && cin->has_comment) { cc = n_text; n_text += (int64_t)cin->comment.size() + 1; }
+    if (cin && cin->has_qual) { cq = n_text; n_text += (int64_t)cin->qual.size() + 1; }
+    const int64_t carried_text = n_text;
+    for (size_t i = 0; i < order.size(); ++i) {
+        const Piece& P = *order[i];
+        slot[i] = Slot{total, n_rec, n_name, n_text, cc, cq};
+        if (P.last_comment >= 0) cc = n_text + P.last_comment;
+        if (P.last_qual >= 0) cq = n_text + P.last_qual;
+        total += P.nb; n_rec += P.ends.size(); n_name += P.name_pool.size(); n_text += (int64_t)P.text_pool.size();
+        if (P.max_len > B->max_len) B->max_len = P.max_len;
+    }
+    const double t2 = now();
+    B->reserve_bases(total + 16);
+    B->offsets.resize(n_rec + 1); B->offsets[0] = 0; B->name_off.resize(n_rec); B->comment_off.resize(n_rec); B->qual_off.resize(n_rec);
+    B->name_pool.resize(n_name); B->text_pool.resize((size_t)n_text);
+    if (carried_text) {
+        char* t = B->text_pool.data();
+        if (cin->has_comment) { memcpy(t, cin->comment.c_str(), cin->comment.size() + 1); t += cin->comment.size() + 1; }
+        if (cin->has_qual) memcpy(t, cin->qual.c_str(), cin->qual.size() + 1);
+    }
+    const double t3 = now();
+    std::atomic<size_t> nextc{0};
+    auto splice = [&]() {
+        for (;;) {
+            const size_t i = nextc.fetch_add(1);
+            if (i >= order.size()) return;
+            const Piece& P = *order[i];
+            const Slot& S = slot[i];
+            if (P.nb) memcpy(B->bases + S.base0, P.bases, (size_t)P.nb);
+            if (!P.name_pool.empty()) memcpy(B->name_pool.data() + S.name0, P.name_pool.data(), P.name_pool.size());
+            if (!P.text_pool.empty()) memcpy(B->text_pool.data() + S.text0, P.text_pool.data(), P.text_pool.size());
+            const size_t m = P.ends.size();
+            for (size_t r = 0; r < m; ++r) {
+                B->name_off[S.rec0 + r] = S.name0 + P.name_off[r];
+                B->comment_off[S.rec0 + r] = P.comment_off[r] < 0 ? S.in_comment : S.text0 + P.comment_off[r];
+                B->qual_off[S.rec0 + r] = P.qual_off[r] < 0 ? S.in_qual : S.text0 + P.qual_off[r];
+                B->offsets[S.rec0 + r + 1] = S.base0 + P.ends[r];
+            }
+            const_cast<Piece&>(P).release();                  // the per-piece vectors, on this thread
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        const size_t nt = n_threads < order.size() ? n_threads : order.size();
+        for (size_t t = 1; t < nt; ++t) pool.emplace_back(splice);
+        splice();
+        for (auto& t : pool) t.join();
+    }
+    B->parse_status = status;
+    if (cout) {
+        cout->status = status;
+        cout->next_hp = end_hp;
+        cout->has_comment = cc >= 0; cout->has_qual = cq >= 0;
+        cout->comment = cc >= 0 ? std::string(B->text_pool.data() + cc) : std::string();
+        cout->qual = cq >= 0 ? std::string(B->text_pool.data() + cq) : std::string();
+    }
+    if (getenv("CRASS_B200_TRACE"))
+        fprintf(stderr, "[crass_b200] parse: bytes [%zu, %zu): %zu pieces guessed, %zu kept in order, %zu re-parsed gaps, %zu threads; "
+                "parse %.1f ms, gaps %.1f ms, alloc %.1f ms, splice %.1f ms\n",
+                first, end_hp == (size_t)-1 ? n : end_hp, np, order.size() - patches.size(), patches.size(), n_threads, t1 - t0, t2 - t1, t3 - t2, now() - t3);
+}
+}  // namespace
+
 int parse_file(const char* path, Batch** out, Batch* reuse) {
     Input in;
     if (!in.open(path)) return fail(CRASS_B200_EIO, std::string("cannot open ") + path);
     Batch* B = reuse ? reuse : new Batch();
-    B->reset();
     try {
-        B->offsets.push_back(0);
-        const size_t n = in.size;
-        unsigned hw = std::thread::hardware_concurrency();
-        if (hw == 0) hw = 1;
-        const size_t n_threads = env_size("CRASS_B200_PARSE_THREADS", hw < 16 ? hw : 16);
-        const size_t chunk = env_size("CRASS_B200_PARSE_CHUNK", (size_t)16 << 20);
-        std::vector<size_t> starts;                       // header positions the pieces 1.. start from
-        if (n_threads > 1 && n > chunk) {
-            for (size_t at = chunk; at < n; at += chunk) {
-                const size_t s = guess_record_start(in.data, n, at, at + chunk < n ? at + chunk : n);
-                if (s != (size_t)-1) starts.push_back(s);
-            }
-        }
-        if (starts.empty()) {                             // one piece, written straight into the batch
-            B->reserve_bases(n + 16);
-            Piece P;
-            P.bases = B->bases; P.cap = B->bases_cap;
-            parse_span(in.data, n, (size_t)-1, (size_t)-1, P);
-            B->name_pool.swap(P.name_pool); B->text_pool.swap(P.text_pool);   // piece-relative == batch-relative here
-            B->name_off.swap(P.name_off); B->comment_off.swap(P.comment_off); B->qual_off.swap(P.qual_off);
-            B->offsets.reserve(P.ends.size() + 1);
-            B->offsets.insert(B->offsets.end(), P.ends.begin(), P.ends.end());
-            B->max_len = P.max_len;
-            B->parse_status = P.status;
-            *out = B;
-            return 0;
-        }
-        const size_t np = starts.size() + 1;
-        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-        const double t0 = now();
-        // one anonymous mapping for the bases of all pieces (huge pages when the kernel grants them: a 16 MB malloc per piece
-        // was 400 k page faults on the way in and as many pages to give back), unmapped on a detached thread at the end
-        struct Scratch {
-            uint8_t* p = nullptr; size_t len = 0;
-            ~Scratch() { if (p) Input::unmap_later(p, len); }
-        } scratch_map;
-        scratch_map.len = n + 64 * np + 4096;
-        void* sm = mmap(nullptr, scratch_map.len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
-        if (sm == MAP_FAILED) throw std::bad_alloc();
-        scratch_map.p = (uint8_t*)sm;
-        madvise(sm, scratch_map.len, MADV_HUGEPAGE);
-        uint8_t* const scratch = scratch_map.p;
-        std::vector<Piece> pieces(np);
-        std::atomic<size_t> next{0};
-        std::atomic<bool> failed{false};
-        auto work = [&]() {
-            for (;;) {
-                const size_t k = next.fetch_add(1);
-                if (k >= np || failed.load()) return;
-                try {
-                    Piece& P = pieces[k];
-                    const size_t from = k ? starts[k - 1] : 0, stop = k + 1 < np ? starts[k] : (size_t)-1;
-                    // a piece's bases are a subset of its bytes: its slice of one scratch mapping, at its own file offset
-                    P.own = false;
-                    P.cap = (k + 1 < np ? stop - from : n - from) + 64;
-                    P.bases = scratch + from + 64 * k;
-                    parse_span(in.data, n, k ? from : (size_t)-1, stop, P);
-                } catch (...) { failed.store(true); }
-            }
-        };
-        {
-            std::vector<std::thread> pool;
-            const size_t nt = n_threads < np ? n_threads : np;
-            for (size_t t = 1; t < nt; ++t) pool.emplace_back(work);
-            work();
-            for (auto& t : pool) t.join();
-        }
-        if (failed.load()) throw std::bad_alloc();
-
-        const double t1 = now();
-        // walk the pieces in file order; `order` lists what the sequential reader would have produced
-        std::vector<const Piece*> order;
-        std::vector<std::unique_ptr<Piece>> patches;
-        size_t k = 0;
-        const Piece* cur = &pieces[0];
-        int status = -1;
-        for (;;) {
-            order.push_back(cur);
-            if (cur->status != 0) { status = cur->status; break; }
-            const size_t hp = cur->next_hp;
-            while (k < starts.size() && starts[k] < hp) ++k;          // pieces that began inside a record
-            if (k < starts.size() && starts[k] == hp) { cur = &pieces[++k]; continue; }
-            std::unique_ptr<Piece> Q(new Piece());                    // no piece begins here: parse up to the next one
-            const size_t stop = k < starts.size() ? starts[k] : (size_t)-1;
-            Q->own = true;
-            Q->cap = (stop == (size_t)-1 ? n - hp : stop - hp) + 64;
-            Q->bases = (uint8_t*)malloc(Q->cap);
-            if (!Q->bases) throw std::bad_alloc();
-            parse_span(in.data, n, hp, stop, *Q);
-            cur = Q.get();
-            patches.push_back(std::move(Q));
-        }
-        // where each piece lands in the batch, and the stale comment/quality it inherits
-        struct Slot { uint64_t base0, rec0, name0; int64_t text0, in_comment, in_qual; };
-        std::vector<Slot> slot(order.size());
-        uint64_t total = 0, n_rec = 0, n_name = 0;
-        int64_t n_text = 0, cc = -1, cq = -1;
-        for (size_t i = 0; i < order.size(); ++i) {
-            const Piece& P = *order[i];
-            slot[i] = Slot{total, n_rec, n_name, n_text, cc, cq};
-            if (P.last_comment >= 0) cc = n_text + P.last_comment;
-            if (P.last_qual >= 0) cq = n_text + P.last_qual;
-            total += P.nb; n_rec += P.ends.size(); n_name += P.name_pool.size(); n_text += (int64_t)P.text_pool.size();
-            if (P.max_len > B->max_len) B->max_len = P.max_len;
-        }
-        const double t2 = now();
-        B->reserve_bases(total + 16);
-        B->offsets.resize(n_rec + 1); B->offsets[0] = 0; B->name_off.resize(n_rec); B->comment_off.resize(n_rec); B->qual_off.resize(n_rec);
-        B->name_pool.resize(n_name); B->text_pool.resize((size_t)n_text);
-        const double t3 = now();
-        std::atomic<size_t> nextc{0};
-        auto splice = [&]() {
-            for (;;) {
-                const size_t i = nextc.fetch_add(1);
-                if (i >= order.size()) return;
-                const Piece& P = *order[i];
-                const Slot& S = slot[i];
-                if (P.nb) memcpy(B->bases + S.base0, P.bases, (size_t)P.nb);
-                if (!P.name_pool.empty()) memcpy(B->name_pool.data() + S.name0, P.name_pool.data(), P.name_pool.size());
-                if (!P.text_pool.empty()) memcpy(B->text_pool.data() + S.text0, P.text_pool.data(), P.text_pool.size());
-                const size_t m = P.ends.size();
-                for (size_t r = 0; r < m; ++r) {
-                    B->name_off[S.rec0 + r] = S.name0 + P.name_off[r];
-                    B->comment_off[S.rec0 + r] = P.comment_off[r] < 0 ? S.in_comment : S.text0 + P.comment_off[r];
-                    B->qual_off[S.rec0 + r] = P.qual_off[r] < 0 ? S.in_qual : S.text0 + P.qual_off[r];
-                    B->offsets[S.rec0 + r + 1] = S.base0 + P.ends[r];
-                }
-                // 16 MB buffers go back to the kernel page by page: done here, on as many threads as there are, it is hidden;
-                // left to the destructors it was a serial 40 ms at the end of a 10 M-read file
-                const_cast<Piece&>(P).release();
-            }
-        };
-        {
-            std::vector<std::thread> pool;
-            const size_t nt = n_threads < order.size() ? n_threads : order.size();
-            for (size_t t = 1; t < nt; ++t) pool.emplace_back(splice);
-            splice();
-            for (auto& t : pool) t.join();
-        }
-        B->parse_status = status;
-        if (getenv("CRASS_B200_TRACE"))
-            fprintf(stderr, "[crass_b200] parse_file: %zu pieces guessed, %zu kept in order, %zu re-parsed gaps, %zu threads; "
-                    "parse %.1f ms, gaps %.1f ms, alloc %.1f ms, splice %.1f ms\n",
-                    np, order.size() - patches.size(), patches.size(), n_threads, t1 - t0, t2 - t1, t3 - t2, now() - t3);
+        parse_range(in, (size_t)-1, (size_t)-1, nullptr, B, nullptr);
     } catch (std::exception& ex) {
         if (!reuse) delete B;
         return fail(CRASS_B200_ENOMEM, std::string("parse_file: ") + ex.what());
@@ -455,5 +494,44 @@ int parse_file(const char* path, Batch** out, Batch* reuse) {
     *out = B;
     return 0;
 }
+
+// ---- the streamed feed: one input parsed range by range (engine.cu overlaps the ranges with the copy, K1 and the replay) ------
+struct ParseStream {
+    Input in;
+    size_t range_bytes = 0;
+    RangeCarry carry;
+    bool started = false, ended = false;
+};
+
+ParseStream* parse_stream_open(const char* path, size_t range_bytes) {
+    std::unique_ptr<ParseStream> s(new ParseStream());
+    if (!s->in.open(path)) { fail(CRASS_B200_EIO, std::string("cannot open ") + path); return nullptr; }
+    s->range_bytes = range_bytes;
+    return s.release();
+}
+
+size_t parse_stream_size(const ParseStream* s) { return s->in.size; }
+
+// parses the next range into `reuse`; 1: a range was parsed (it may hold no record), 0: the stream had ended before, < 0: error
+int parse_stream_next(ParseStream* s, Batch* reuse) {
+    if (s->ended) return 0;
+    try {
+        const size_t start = s->started ? s->carry.next_hp : (size_t)-1;
+        const size_t first = s->started ? start : 0;
+        const size_t hint = s->range_bytes && first + s->range_bytes + (s->range_bytes >> 2) < s->in.size ? first + s->range_bytes : (size_t)-1;
+        RangeCarry out;
+        parse_range(s->in, start, hint, s->started ? &s->carry : nullptr, reuse, &out);
+        s->started = true;
+        s->carry = out;
+        if (out.status != 0 || out.next_hp == (size_t)-1) s->ended = true;
+        if (!s->ended) reuse->parse_status = 0;               // the loop goes on in the next range
+    } catch (std::exception& ex) {
+        s->ended = true;
+        return -fail(CRASS_B200_ENOMEM, std::string("parse_stream_next: ") + ex.what());
+    }
+    return 1;
+}
+
+void parse_stream_close(ParseStream* s) { delete s; }
 
 }  // namespace cbh

@@ -247,6 +247,16 @@ int crass_b200_qc_found_repeats(crass_b200_ctx* ctx, const uint8_t* seq, uint32_
 
 /* ---- feed path: kseq-compatible FASTA/FASTQ(.gz) parser ------------------------------------------ */
 int crass_b200_parse_file(const char* path, crass_b200_batch** out);      /* "-" = stdin */
+/* The same record stream handed out range by range -- the streamed feed (the reference's loop over kseq_read holds one record
+ * at a time, libcrispr.cpp:96-131; here a range of about range_bytes of the input is one batch, so that parsing, copying,
+ * K1 and the replay of successive ranges overlap: crass_b200_engine_run_files does that for files of two ranges or more).
+ * Every range ends on a true record start and inherits kseq's stale comment / quality strings from the one before it;
+ * crass_b200_parse_stream_next returns 1 and a batch (parse status 0 while more follows, the stream's final status in the
+ * last one), 0 when the stream had ended, a negative error code otherwise. */
+typedef struct crass_b200_parse_stream crass_b200_parse_stream;
+int crass_b200_parse_stream_open(const char* path, uint64_t range_bytes, crass_b200_parse_stream** out);
+int crass_b200_parse_stream_next(crass_b200_parse_stream* s, crass_b200_batch** out);
+void crass_b200_parse_stream_close(crass_b200_parse_stream* s);
 int crass_b200_batch_from_memory(const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
                                  const char* const* names /* may be NULL: r%010u */, crass_b200_batch** out);
 void crass_b200_batch_destroy(crass_b200_batch* b);

@@ -50,6 +50,33 @@ def exchange(request):
 
 
 @pytest.mark.parametrize("name", BUNDLED)
+@pytest.mark.parametrize("devices", [(0,), (0, 0, 0)])
+@pytest.mark.parametrize("stream_bytes", [30000, 250000])
+def test_bundled_files_streamed(name, devices, stream_bytes):
+    """The streamed feed: a file of two ranges or more is parsed range by range while another thread copies and searches the
+    range before and a third replays the one before that; the ranges then behave like the files of a multi-file run.  The
+    dump must be the reference's whatever the range size (here a few dozen to a few hundred ranges per file), also with
+    small parser pieces inside the ranges and on several (emulated) devices."""
+    path = os.path.join(checkers.REF_DATA, name)
+    if not os.path.exists(path):
+        pytest.skip("bundled read sets not staged")
+    want = gzip.open(os.path.join(G, "bundled", name + ".dump.gz")).read().decode("latin-1")
+    old = {k: os.environ.get(k) for k in ("CRASS_B200_STREAM_BYTES", "CRASS_B200_PARSE_CHUNK", "CRASS_B200_PARSE_THREADS")}
+    os.environ.update(CRASS_B200_STREAM_BYTES=str(stream_bytes), CRASS_B200_PARSE_CHUNK=str(stream_bytes // 3), CRASS_B200_PARSE_THREADS="4")
+    try:
+        n_ranges = sum(1 for _ in cb.Batch.stream_file(path, stream_bytes))
+        res, max_len = cb.run_files_multi(devices, [path])
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert n_ranges >= 2 or stream_bytes > 30000 or name == "poor_dr_ext.fa.gz"
+    assert res.dump(max_len) == want
+
+
+@pytest.mark.parametrize("name", BUNDLED)
 @pytest.mark.parametrize("devices", [(0,), (0, 0), (0, 0, 0, 0, 0)])
 def test_bundled_files_on_emulated_devices(name, devices, exchange):
     path = os.path.join(checkers.REF_DATA, name)

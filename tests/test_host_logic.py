@@ -176,6 +176,16 @@ def test_parser_pieces_on_worker_threads_match_the_sequential_stream():
                 assert got == want, (style, chunk, it)
                 lens = np.diff(b.offsets.astype(np.int64))
                 assert (int(lens.max()) if len(lens) else 0) == b.max_read_len
+                # the streamed feed: the same records range by range (a range = a few pieces), each range inheriting kseq's
+                # stale strings; only the last batch carries the stream's status
+                old = _pieces_env(chunk)
+                try:
+                    parts_got = [x.record_stream() for x in cb.Batch.stream_file(p, 3 * chunk + 17)]
+                finally:
+                    _restore_env(old)
+                assert len(parts_got) >= 1 and all(x.endswith(b"#ret=0\n") for x in parts_got[:-1])
+                joined = b"".join(x[:x.rindex(b"#ret=")] for x in parts_got[:-1]) + parts_got[-1]
+                assert joined == want, (style, chunk, it, "streamed")
         # wrong guesses on purpose (any '>'/'@' byte is taken for a record start): pieces are dropped and the gaps parsed
         # again from the true position.  The switch is read once per process, hence the child.
         r = subprocess.run([sys.executable, "-c", _NAIVE, d], env=dict(os.environ, CRASS_B200_PARSE_GUESS="naive", CRASS_B200_PARSE_THREADS="4"),
