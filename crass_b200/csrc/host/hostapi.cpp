@@ -191,15 +191,23 @@ void build_holders(const Batch& b, const crass_b200_hit* hits, const uint32_t* w
 }
 
 void insert_holder(Results& r, Built& o) {                           // addReadHolder's container half (libcrispr.cpp:1119-1162)
-    auto it = r.s2t.find(o.token);
+    // the ordered maps are what the dump walks; a hash index in front of them answers the 99 % of look-ups that hit
+    auto hit = r.s2t_index.find(o.token);
     int tok;
-    if (it == r.s2t.end()) {
-        tok = ++r.next_free_token;                                   // first token is 2
-        r.s2t[o.token] = tok;
-        r.t2s.push_back(o.token);
-    } else tok = it->second;
+    if (hit == r.s2t_index.end()) {
+        auto it = r.s2t.find(o.token);                               // (the index is rebuilt lazily: containers filled by other calls)
+        if (it == r.s2t.end()) {
+            tok = ++r.next_free_token;                               // first token is 2
+            r.s2t[o.token] = tok;
+            r.t2s.push_back(o.token);
+        } else tok = it->second;
+        r.s2t_index.emplace(o.token, tok);
+    } else tok = hit->second;
     o.h->token = tok;
-    r.reads[tok].push_back(o.h);
+    if ((size_t)tok >= r.reads_index.size()) r.reads_index.resize((size_t)tok + 64, nullptr);
+    std::vector<HeldRead*>*& list = r.reads_index[(size_t)tok];
+    if (!list) list = &r.reads[tok];                                 // std::map nodes do not move
+    list->push_back(o.h);
 }
 }  // namespace
 
@@ -214,8 +222,9 @@ int crass_b200_results_add_phase1(crass_b200_results* rh, const crass_b200_batch
         build_holders(b, hits, nullptr, n_hits, ss_pool, 1, built);
         for (uint32_t k = 0; k < n_hits; ++k) {                             // searchFile's loop body for a hit (libcrispr.cpp:134-139)
             insert_holder(r, built[k]);
-            r.patterns_hash[built[k].raw0] = true;
-            r.reads_found.emplace_hint(r.reads_found.end(), built[k].h->header, true);   // a no-op for a header that is there already
+            if (r.patterns_index.insert(built[k].raw0).second) r.patterns_hash[built[k].raw0] = true;
+            if (r.found_index.insert(built[k].h->header).second)
+                r.reads_found.emplace_hint(r.reads_found.end(), built[k].h->header, true);   // (a no-op for a header that is there already)
         }
     } catch (std::exception& ex) {
         return fail(CRASS_B200_ENOMEM, std::string("results_add_phase1: ") + ex.what());
@@ -235,9 +244,14 @@ int crass_b200_results_add_phase2(crass_b200_results* rh, const crass_b200_batch
         // for all hits up front
         std::vector<uint32_t> take;
         take.reserve(n_hits);
+        if (r.found_index.size() != r.reads_found.size()) {                  // containers filled by other calls: index them now
+            r.found_index.clear();
+            for (const auto& kv : r.reads_found) r.found_index.insert(kv.first);
+        }
+        std::string name;
         for (uint32_t k = 0; k < n_hits; ++k) {
-            const char* name = b.name_pool.data() + b.name_off[hits[k].read_index];
-            if (r.reads_found.find(name) == r.reads_found.end()) take.push_back(k);
+            name.assign(b.name_pool.data() + b.name_off[hits[k].read_index]);
+            if (r.found_index.find(name) == r.found_index.end()) take.push_back(k);
         }
         std::vector<Built> built;
         build_holders(b, hits, take.data(), (uint32_t)take.size(), ss_pool, 2, built);
@@ -273,6 +287,7 @@ int crass_b200_results_adopt_tokens(crass_b200_results* rh, const char* dr_list_
     }
     r.reads.swap(reads);
     r.s2t.swap(s2t);
+    r.s2t_index.clear(); r.reads_index.clear();                     // they pointed into the old containers
     r.t2s.swap(t2s);
     r.next_free_token = (int)r.t2s.size() + 1;
     return 0;

@@ -9,6 +9,8 @@
 #include <map>
 #include <string>
 #include <string_view>
+#include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../../../include/crass_b200.h"
@@ -90,6 +92,10 @@ struct Results {
     // ReadMap: token -> reads in insertion order
     std::map<int, std::vector<HeldRead*> > reads;
     std::map<std::string, bool> patterns_hash, reads_found;
+    // hash indexes in front of the ordered containers (replay only; whoever rewrites the containers clears them)
+    std::unordered_map<std::string, int> s2t_index;
+    std::unordered_set<std::string> patterns_index, found_index;
+    std::vector<std::vector<HeldRead*>*> reads_index;
     size_t n_found_phase1 = 0;
     std::vector<std::string> non_redundant;          // last computed pattern list
     std::vector<std::pair<int, int> > token_groups;  // (token, group id) in group order

@@ -22,6 +22,7 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <memory>
@@ -318,13 +319,15 @@ void parse_range(Input& in, size_t start, size_t stop_hint, const RangeCarry* ci
     unsigned hw = std::thread::hardware_concurrency();
     if (hw == 0) hw = 1;
     const size_t n_threads = env_size("CRASS_B200_PARSE_THREADS", hw < 16 ? hw : 16);
-    const size_t chunk = env_size("CRASS_B200_PARSE_CHUNK", (size_t)16 << 20);
+    size_t chunk = env_size("CRASS_B200_PARSE_CHUNK", (size_t)16 << 20);
     const bool whole = start == (size_t)-1 && stop_hint == (size_t)-1 && !cin && !cout;
     const size_t first = start == (size_t)-1 ? 0 : start;
     // the range's end: a guessed record start at or after stop_hint (SIZE_MAX: the range runs to the end of the input)
     size_t range_stop = (size_t)-1;
     if (stop_hint != (size_t)-1 && stop_hint < n) range_stop = guess_record_start(in.data, n, stop_hint, n);
     const size_t limit = range_stop == (size_t)-1 ? n : range_stop;
+    // a range is a few hundred MB: at least two pieces per thread, so that the threads finish together
+    if (!whole && !getenv("CRASS_B200_PARSE_CHUNK")) chunk = std::max<size_t>((size_t)1 << 20, std::min(chunk, (limit - first) / (2 * n_threads) + 1));
     std::vector<size_t> starts;                           // header positions the pieces 1.. start from
     if (n_threads > 1 && limit - first > chunk) {
         for (size_t at = first + chunk; at < limit; at += chunk) {
