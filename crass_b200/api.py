@@ -90,6 +90,10 @@ def lib():
         "crass_b200_ac_num_symbols": (C.c_uint32, [vp]),
         "crass_b200_ac_table_bytes": (C.c_uint64, [vp]),
         "crass_b200_ac_pattern_text": (vp, [vp, C.POINTER(C.c_uint32)]),
+        "crass_b200_comm_unique_id": (C.c_int, [vp]),
+        "crass_b200_ctx_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
+        "crass_b200_ctx_comm_world": (C.c_int, [vp]),
+        "crass_b200_exchange_tokens_dev": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp]),
         "crass_b200_ksw_align": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint32, vp]),
         "crass_b200_consensus_groups": (C.c_int, [vp, vp, vp, C.c_uint32, vp, vp, vp, vp, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_uint32)]),
         "crass_b200_ac_scan_dev": (C.c_int, [vp, vp, vp, vp, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp]),
@@ -541,6 +545,25 @@ class Context:
     def unique_tokens_block_dev(self, d_hits, n_hits, d_tokens, stride, d_block, cap, stream=0):
         """K4b in block form (see include/crass_b200.h): distinct tokens of the hit list -> one token block."""
         _check(lib().crass_b200_unique_tokens_block_dev(self.h, d_hits.data_ptr(), n_hits, d_tokens.data_ptr(), stride, d_block.data_ptr(), cap, stream))
+
+    # -- one process per GPU: the library's own NCCL communicator ------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_uint8 * 128)()
+        _check(lib().crass_b200_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(lib().crass_b200_ctx_comm_init(self.h, buf, rank, world))
+
+    @property
+    def comm_world(self):
+        return lib().crass_b200_ctx_comm_world(self.h)
+
+    def exchange_tokens_dev(self, d_hits, n_hits, d_tokens, stride, d_send, cap, d_recv, shard_reads, d_merged, out_cap, stream=0):
+        _check(lib().crass_b200_exchange_tokens_dev(self.h, d_hits.data_ptr(), n_hits, d_tokens.data_ptr(), stride, d_send.data_ptr(), cap,
+                                                    d_recv.data_ptr(), shard_reads, d_merged.data_ptr(), out_cap, stream))
 
     def merge_token_blocks_dev(self, d_blocks, n_ranks, cap, stride, shard_reads, d_out_block, out_cap, stream=0):
         """K4c: the blocks of all ranks (rank order, back to back) -> one block with global first-appearance keys."""

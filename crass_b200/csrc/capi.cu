@@ -18,6 +18,7 @@
 #include "../../include/crass_b200.h"
 #include "host/internal.h"
 #include "kernels.cuh"
+#include "nccl_dl.h"
 
 namespace cbh { const char* last_error_cstr(); }
 
@@ -67,6 +68,7 @@ struct PinnedBuf {                                  // grow-only page-locked hos
 };
 
 int g_device_count = -2;    // -2: not probed
+Nccl g_nccl;
 
 int probe_devices() {
     if (g_device_count == -2) {
@@ -120,6 +122,8 @@ struct crass_b200_ctx {
     DevBuf d_cand_mask;                  // K2 fast path: per candidate, the aligned 16-mers that can belong to an occurrence
     // K5 (clustering passes A/B on the token block): device arrays and their pinned host mirrors
     DevBuf d_cl_ckeys;
+    void* comm = nullptr;                // ncclComm_t of the one-process-per-GPU mode (crass_b200_ctx_comm_init)
+    int comm_world = 0, comm_rank = 0;
     DevBuf d_cons;                       // K7 (consensus DR): every device array of a call, carved from one allocation
     DevBuf d_ticket;                     // work counter of the long-read kernel
     DevBuf d_cl_order, d_cl_koff, d_cl_keys, d_cl_first, d_cl_tab, d_cl_info;
@@ -231,6 +235,7 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
     if (c->ev_ac_ready) cudaEventDestroy(c->ev_ac_ready);
     if (c->ev_scan) cudaEventDestroy(c->ev_scan);
     for (cudaEvent_t e : c->ev_chunk) if (e) cudaEventDestroy(e);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -352,6 +357,41 @@ int crass_b200_unique_tokens_block_dev(crass_b200_ctx* c, const crass_b200_hit* 
     cudaStream_t st = (cudaStream_t)stream_v;
     cbk::HitTokens src{d_hits, (const uint8_t*)d_tokens, stride};
     return dedupe_into_block(c, src, n_hits, stride, d_block, cap, st);
+}
+
+int crass_b200_comm_unique_id(uint8_t id[128]) {
+    if (!id) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    if (!g_nccl.load()) return cbh::fail(CRASS_B200_ECUDA, "libnccl.so.2 could not be loaded (CRASS_B200_NCCL_LIB names another)");
+    Nccl::UniqueId u;
+    if (const int rc = g_nccl.GetUniqueId(&u)) return cbh::fail(CRASS_B200_ECUDA, std::string("ncclGetUniqueId failed: ") + g_nccl.why(rc));
+    memcpy(id, u.internal, 128);
+    return 0;
+}
+
+int crass_b200_ctx_comm_init(crass_b200_ctx* c, const uint8_t id[128], int rank, int world) {
+    if (!c || !id || world < 1 || rank < 0 || rank >= world) return cbh::fail(CRASS_B200_EINVAL, "bad argument");
+    if (!g_nccl.load()) return cbh::fail(CRASS_B200_ECUDA, "libnccl.so.2 could not be loaded (CRASS_B200_NCCL_LIB names another)");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->comm) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; c->comm_world = 0; }
+    Nccl::UniqueId u;
+    memcpy(u.internal, id, 128);
+    if (const int rc = g_nccl.CommInitRank(&c->comm, world, u, rank)) { c->comm = nullptr; return cbh::fail(CRASS_B200_ECUDA, std::string("ncclCommInitRank failed: ") + g_nccl.why(rc)); }
+    c->comm_world = world; c->comm_rank = rank;
+    return 0;
+}
+
+int crass_b200_ctx_comm_world(const crass_b200_ctx* c) { return c ? c->comm_world : 0; }
+
+int crass_b200_exchange_tokens_dev(crass_b200_ctx* c, const crass_b200_hit* d_hits, uint32_t n_hits, const void* d_tokens, uint32_t stride,
+                                   void* d_send, uint32_t cap, void* d_recv, uint32_t shard_reads, void* d_merged, uint32_t out_cap,
+                                   void* stream_v) {
+    if (!c || !d_send || !d_recv || !d_merged) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    if (!c->comm) return cbh::fail(CRASS_B200_EINVAL, "no communicator: call crass_b200_ctx_comm_init first");
+    if (int r = crass_b200_unique_tokens_block_dev(c, d_hits, n_hits, d_tokens, stride, d_send, cap, stream_v)) return r;
+    const size_t nb = crass_b200_token_block_bytes(cap, stride);
+    if (const int rc = g_nccl.AllGather(d_send, d_recv, nb, /*ncclUint8*/ 1, c->comm, (cudaStream_t)stream_v))
+        return cbh::fail(CRASS_B200_ECUDA, std::string("ncclAllGather failed: ") + g_nccl.why(rc));
+    return crass_b200_merge_token_blocks_dev(c, d_recv, (uint32_t)c->comm_world, cap, stride, shard_reads, d_merged, out_cap, stream_v);
 }
 
 int crass_b200_merge_token_blocks_dev(crass_b200_ctx* c, const void* d_blocks, uint32_t n_ranks, uint32_t cap, uint32_t stride,

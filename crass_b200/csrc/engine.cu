@@ -35,6 +35,7 @@
 
 #include "../../include/crass_b200.h"
 #include "host/internal.h"
+#include "nccl_dl.h"
 
 namespace {
 
@@ -47,36 +48,6 @@ double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::
             return cbh::fail(_e == cudaErrorMemoryAllocation ? CRASS_B200_ENOMEM : CRASS_B200_ECUDA,                \
                              std::string(#expr) + " failed: " + cudaGetErrorString(_e));                            \
     } while (0)
-
-// ---- NCCL through dlopen: the library has no link-time dependency on it ----------------------------------------------
-struct Nccl {
-    typedef int (*CommInitAll_t)(void** comms, int ndev, const int* devlist);
-    typedef int (*CommDestroy_t)(void* comm);
-    typedef int (*AllGather_t)(const void* send, void* recv, size_t count, int dtype, void* comm, cudaStream_t s);
-    typedef int (*Group_t)();
-    typedef const char* (*ErrStr_t)(int);
-    void* lib = nullptr;
-    CommInitAll_t CommInitAll = nullptr; CommDestroy_t CommDestroy = nullptr; AllGather_t AllGather = nullptr;
-    Group_t GroupStart = nullptr, GroupEnd = nullptr; ErrStr_t GetErrorString = nullptr;
-    bool load() {
-        if (lib) return true;
-        const char* names[] = {getenv("CRASS_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
-        for (const char* n : names) {
-            if (!n || !*n) continue;
-            lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
-            if (lib) break;
-        }
-        if (!lib) return false;
-        CommInitAll = (CommInitAll_t)dlsym(lib, "ncclCommInitAll");
-        CommDestroy = (CommDestroy_t)dlsym(lib, "ncclCommDestroy");
-        AllGather = (AllGather_t)dlsym(lib, "ncclAllGather");
-        GroupStart = (Group_t)dlsym(lib, "ncclGroupStart");
-        GroupEnd = (Group_t)dlsym(lib, "ncclGroupEnd");
-        GetErrorString = (ErrStr_t)dlsym(lib, "ncclGetErrorString");
-        if (!CommInitAll || !CommDestroy || !AllGather || !GroupStart || !GroupEnd) { dlclose(lib); lib = nullptr; return false; }
-        return true;
-    }
-};
 
 struct DBuf {                                             // grow-only device buffer of the lane's device
     void* p = nullptr; size_t cap = 0;

@@ -33,6 +33,31 @@ class TokenExchange:
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.shard_reads = int(shard_reads)
         self._alloc(cap)
+        self.own_comm = False
+        if self.world > 1 and group is None and self.dev.type == "cuda" and os.environ.get("CRASS_B200_EXCHANGE", "") != "torch":
+            self._init_own_comm()
+
+    def _init_own_comm(self):
+        """The library's own NCCL communicator (libnccl is dlopen'ed by it): K4b, the all-gather and K4c then go onto the caller's
+        stream as three enqueues of one C call -- through torch.distributed the collective alone costs 0.1 ms of host time per
+        step and hops to NCCL's stream and back.  The unique id travels over the process group that is there anyway."""
+        rank = dist.get_rank()
+        try:
+            uid = api.Context.comm_unique_id() if rank == 0 else bytes(128)
+        except api.CrassB200Error:
+            uid = None
+        box = [uid]
+        dist.broadcast_object_list(box, src=0)
+        if box[0] is None:
+            return
+        try:
+            self.ctx.comm_init(box[0], rank, self.world)
+            ok = 1
+        except api.CrassB200Error:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)                      # all ranks or none
+        self.own_comm = bool(int(flag.item()))
 
     def _alloc(self, cap):
         self.cap = cap
@@ -76,10 +101,14 @@ class TokenExchange:
         stream = self._stream(stream)
         while True:
             t0 = time.perf_counter()
-            self.ctx.unique_tokens_block_dev(d_hits, n_hits, d_tokens, self.stride, self.send, self.cap, stream)
-            if self.world > 1:
-                dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
-                self.ctx.merge_token_blocks_dev(self.recv, self.world, self.cap, self.stride, self.shard_reads, self.merged, self.out_cap, stream)
+            if self.world > 1 and self.own_comm:
+                self.ctx.exchange_tokens_dev(d_hits, n_hits, d_tokens, self.stride, self.send, self.cap, self.recv, self.shard_reads,
+                                             self.merged, self.out_cap, stream)
+            else:
+                self.ctx.unique_tokens_block_dev(d_hits, n_hits, d_tokens, self.stride, self.send, self.cap, stream)
+                if self.world > 1:
+                    dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+                    self.ctx.merge_token_blocks_dev(self.recv, self.world, self.cap, self.stride, self.shard_reads, self.merged, self.out_cap, stream)
             if _HOST_PASSES:                                      # CRASS_B200_CLUSTER=host: all clustering passes on the host
                 self.host.copy_(self.merged, non_blocking=True)
                 torch.cuda.current_stream(self.dev).synchronize()

@@ -358,6 +358,21 @@ int crass_b200_consensus_groups(crass_b200_ctx* ctx, const uint8_t* bases, const
                                 int32_t* dr_place, uint8_t* dr_flags, int32_t* zone, uint8_t* consensus, float* conservation,
                                 int32_t* coverage, uint32_t* status);
 
+/* ---- one process per GPU: the exchange of SURVEY.md 8e with the collective enqueued by the library -----------------------
+ * crass_b200_comm_unique_id: an NCCL unique id (libnccl is dlopen'ed); rank 0 makes one and hands it to the other ranks by
+ * whatever means the driver has (a file, MPI, torch.distributed).  crass_b200_ctx_comm_init: ncclCommInitRank for this
+ * context's device (collective: every rank calls it).  crass_b200_exchange_tokens_dev: K4b on this rank's hits, ONE
+ * ncclAllGather of the fixed-size token blocks, K4c over the gathered blocks -- three enqueues on the caller's stream, no host
+ * synchronisation, no other stream; d_merged then holds the merged block of all ranks in first-appearance order of the
+ * rank-ordered shards (= the sequential token order, StringCheck.cpp:46-55), ready for crass_b200_cluster_block_dev on every
+ * rank.  d_send: token_block_bytes(cap), d_recv: world x that, d_merged: token_block_bytes(out_cap). */
+int crass_b200_comm_unique_id(uint8_t id[128]);
+int crass_b200_ctx_comm_init(crass_b200_ctx* ctx, const uint8_t id[128], int rank, int world);
+int crass_b200_ctx_comm_world(const crass_b200_ctx* ctx);          /* 0 = no communicator */
+int crass_b200_exchange_tokens_dev(crass_b200_ctx* ctx, const crass_b200_hit* d_hits, uint32_t n_hits, const void* d_tokens, uint32_t stride,
+                                   void* d_send, uint32_t cap, void* d_recv, uint32_t shard_reads, void* d_merged, uint32_t out_cap,
+                                   void* stream);
+
 /* ---- whole path, one call: searchFile* -> createNonRedundantSet -> findSingletons* --------------- */
 int crass_b200_run_files(crass_b200_ctx* ctx, const char* const* paths, uint32_t n_paths,
                          const crass_b200_params* params, int phases, crass_b200_results** out, int* max_read_len);
