@@ -70,15 +70,80 @@ bool inflate_all(const char* path, std::vector<uint8_t>& buf) {
     return true;
 }
 
+size_t env_size_early(const char* name, size_t dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    char* end = nullptr;
+    const unsigned long long x = strtoull(v, &end, 10);
+    return end && *end == 0 ? (size_t)x : dflt;
+}
+
 // The file's bytes: a read-only mapping for plain files (no copy at all), the inflated stream otherwise (gzip members,
 // stdin).  zlib's transparent mode would read plain files too, but at a third of the speed of the parser behind it.
 struct Input {
+    // gz inputs of a ParseStream are inflated by a thread of their own into a large reserved mapping while the ranges already
+    // inflated are parsed, copied and searched (the reference inflates inside its read loop, SeqUtils.cpp:100-125 + kseq.cpp:55-69)
+    std::thread inflater;
+    std::atomic<size_t> avail{0};
+    std::atomic<bool> inflate_done{false}, inflate_failed{false};
+    bool incremental = false;
+    size_t vcap = 0;
     std::vector<uint8_t> inflated;
     const uint8_t* data = nullptr;
     size_t size = 0;
     void* map = nullptr;
     size_t map_len = 0;
-    ~Input() { if (map) unmap_later(map, map_len); }
+    ~Input() {
+        if (inflater.joinable()) inflater.join();
+        if (map) unmap_later(map, map_len);
+    }
+    // open for streaming: plain files as open() does; gz files start an inflater thread and return at once
+    bool open_streaming(const char* path) {
+        if (strcmp(path, "-") == 0) return open(path);
+        const int fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        unsigned char magic[2] = {0, 0};
+        const bool regular = fstat(fd, &st) == 0 && S_ISREG(st.st_mode);
+        const bool gz = regular && pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+        ::close(fd);
+        if (!gz || (size_t)st.st_size < env_size_early("CRASS_B200_GZ_STREAM_MIN", (size_t)8 << 20)) return open(path);      // small archives: inflate first, as before
+        vcap = (size_t)st.st_size * 64 + ((size_t)1 << 30);                        // address space only (MAP_NORESERVE)
+        void* m = mmap(nullptr, vcap, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (m == MAP_FAILED) return open(path);
+        map = m; map_len = vcap; data = (const uint8_t*)m; size = 0; incremental = true;
+        const std::string p = path;
+        // (tests shrink the inflater's step and the parser's margin so that ranges are cut while the stream is still arriving)
+        const size_t step = std::min<size_t>((size_t)8 << 20, std::max<size_t>(4096, env_size_early("CRASS_B200_GZ_STREAM_MARGIN", (size_t)8 << 20)));
+        inflater = std::thread([this, p, step]() {
+            gzFile fp = gzopen(p.c_str(), "r");
+            if (!fp) { inflate_failed.store(true); inflate_done.store(true); return; }
+            gzbuffer(fp, 1 << 20);
+            size_t nread = 0;
+            for (;;) {
+                const size_t want = std::min<size_t>(step, vcap - nread);
+                if (!want) { inflate_failed.store(true); break; }                  // more than 64 x the archive: give up loudly
+                const int r = gzread(fp, (uint8_t*)map + nread, (unsigned)want);
+                if (r <= 0) break;
+                nread += (size_t)r;
+                avail.store(nread, std::memory_order_release);
+            }
+            gzclose(fp);
+            inflate_done.store(true, std::memory_order_release);
+        });
+        return true;
+    }
+    // blocks until `want` bytes are there or the stream has ended; returns what is there
+    size_t wait_for(size_t want, bool* final_size) {
+        if (!incremental) { *final_size = true; return size; }
+        for (;;) {
+            const bool d = inflate_done.load(std::memory_order_acquire);
+            const size_t a = avail.load(std::memory_order_acquire);
+            if (d) { size = a; *final_size = true; return a; }
+            if (a >= want) { *final_size = false; return a; }
+            std::this_thread::sleep_for(std::chrono::microseconds(200));
+        }
+    }
     // giving 1.6 GB of mapped pages back takes the kernel tens of milliseconds: nobody has to wait for it
     static void unmap_later(void* p, size_t len) {
         if (len < ((size_t)64 << 20)) { munmap(p, len); return; }
@@ -312,7 +377,9 @@ struct RangeCarry {
     int status = 0;                                       // 0: more records follow; -1 / -2: the stream ended in this range
 };
 
-void parse_range(Input& in, size_t start, size_t stop_hint, const RangeCarry* cin, Batch* B, RangeCarry* cout) {
+struct View { const uint8_t* data; size_t size; };     // the input's bytes as far as a range may look
+
+void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarry* cin, Batch* B, RangeCarry* cout) {
     B->reset();
     B->offsets.push_back(0);
     const size_t n = in.size;
@@ -489,7 +556,7 @@ int parse_file(const char* path, Batch** out, Batch* reuse) {
     if (!in.open(path)) return fail(CRASS_B200_EIO, std::string("cannot open ") + path);
     Batch* B = reuse ? reuse : new Batch();
     try {
-        parse_range(in, (size_t)-1, (size_t)-1, nullptr, B, nullptr);
+        parse_range(View{in.data, in.size}, (size_t)-1, (size_t)-1, nullptr, B, nullptr);
     } catch (std::exception& ex) {
         if (!reuse) delete B;
         return fail(CRASS_B200_ENOMEM, std::string("parse_file: ") + ex.what());
@@ -508,12 +575,13 @@ struct ParseStream {
 
 ParseStream* parse_stream_open(const char* path, size_t range_bytes) {
     std::unique_ptr<ParseStream> s(new ParseStream());
-    if (!s->in.open(path)) { fail(CRASS_B200_EIO, std::string("cannot open ") + path); return nullptr; }
+    if (!s->in.open_streaming(path)) { fail(CRASS_B200_EIO, std::string("cannot open ") + path); return nullptr; }
     s->range_bytes = range_bytes;
     return s.release();
 }
 
-size_t parse_stream_size(const ParseStream* s) { return s->in.size; }
+// the input's size; for a gz archive that is still being inflated, a guess (four times the archive)
+size_t parse_stream_size(const ParseStream* s) { return s->in.incremental ? s->in.map_len / 64 * 4 : s->in.size; }
 
 // parses the next range into `reuse`; 1: a range was parsed (it may hold no record), 0: the stream had ended before, < 0: error
 int parse_stream_next(ParseStream* s, Batch* reuse) {
@@ -521,9 +589,20 @@ int parse_stream_next(ParseStream* s, Batch* reuse) {
     try {
         const size_t start = s->started ? s->carry.next_hp : (size_t)-1;
         const size_t first = s->started ? start : 0;
-        const size_t hint = s->range_bytes && first + s->range_bytes + (s->range_bytes >> 2) < s->in.size ? first + s->range_bytes : (size_t)-1;
         RangeCarry out;
-        parse_range(s->in, start, hint, s->started ? &s->carry : nullptr, reuse, &out);
+        // a range may look a little past its end (the record that straddles it): for an input that is still being inflated
+        // that margin must be there before the range is parsed, and if a record turns out longer than the margin the range is
+        // parsed again once more has arrived
+        size_t margin = env_size_early("CRASS_B200_GZ_STREAM_MARGIN", std::max<size_t>((size_t)32 << 20, s->range_bytes >> 2));
+        for (;;) {
+            bool final_size = true;
+            const size_t have = s->in.wait_for(first + s->range_bytes + margin, &final_size);
+            if (s->in.inflate_failed.load()) throw std::runtime_error("gz stream could not be inflated");
+            const bool to_end = !s->range_bytes || (final_size && first + s->range_bytes + (s->range_bytes >> 2) >= have);
+            parse_range(View{s->in.data, have}, start, to_end ? (size_t)-1 : first + s->range_bytes, s->started ? &s->carry : nullptr, reuse, &out);
+            if (final_size || (out.status == 0 && out.next_hp != (size_t)-1)) break;
+            margin *= 4;                                              // the view ended inside a record: wait for more of it
+        }
         s->started = true;
         s->carry = out;
         if (out.status != 0 || out.next_hp == (size_t)-1) s->ended = true;

@@ -61,8 +61,9 @@ def test_bundled_files_streamed(name, devices, stream_bytes):
     if not os.path.exists(path):
         pytest.skip("bundled read sets not staged")
     want = gzip.open(os.path.join(G, "bundled", name + ".dump.gz")).read().decode("latin-1")
-    old = {k: os.environ.get(k) for k in ("CRASS_B200_STREAM_BYTES", "CRASS_B200_PARSE_CHUNK", "CRASS_B200_PARSE_THREADS")}
-    os.environ.update(CRASS_B200_STREAM_BYTES=str(stream_bytes), CRASS_B200_PARSE_CHUNK=str(stream_bytes // 3), CRASS_B200_PARSE_THREADS="4")
+    old = {k: os.environ.get(k) for k in ("CRASS_B200_STREAM_BYTES", "CRASS_B200_PARSE_CHUNK", "CRASS_B200_PARSE_THREADS", "CRASS_B200_GZ_STREAM_MIN", "CRASS_B200_GZ_STREAM_MARGIN")}
+    os.environ.update(CRASS_B200_STREAM_BYTES=str(stream_bytes), CRASS_B200_PARSE_CHUNK=str(stream_bytes // 3), CRASS_B200_PARSE_THREADS="4",
+                      CRASS_B200_GZ_STREAM_MIN="1", CRASS_B200_GZ_STREAM_MARGIN="20000")     # the archives are inflated while their first ranges are parsed
     try:
         n_ranges = sum(1 for _ in cb.Batch.stream_file(path, stream_bytes))
         res, max_len = cb.run_files_multi(devices, [path])
