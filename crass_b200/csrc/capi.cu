@@ -181,8 +181,10 @@ extern "C" {
 const char* crass_b200_last_error(void) { return cbh::last_error_cstr(); }
 int crass_b200_abi_version(void) { return CRASS_B200_ABI_VERSION; }
 const char* crass_b200_build_info(void) {
-    return "crass_b200 hot path; CUDA " CB_STR(CUDART_VERSION) "; sm_100a; kernels: K1 dr_filter (2-bit, TMA) + dr_exact_packed, dr_long; K2 ac_filter[_packed|_long] (16-mer q-gram) + ac_verify_warp; "
-           "K4 tokens, K4b/K4c token blocks, K5 clustering passes, hit ordering; K6 update_start_stops (warp Smith-Waterman); generic dr_search / ac_scan; edit_distance";
+    return "crass_b200 hot path; CUDA " CB_STR(CUDART_VERSION) "; sm_100a; kernels: K1 dr_filter_warp (2-bit seeds, VIADDMNMX) | dr_filter (TMA tiles) + dr_exact_staged, dr_long; "
+           "K2 ac_build (tables on the device) + ac_filter[_packed|_long] (16-mer q-gram, two-hash bitmap) + ac_verify_mask|_warp; K4 tokens, K4b/K4c token blocks; "
+           "K5 createNonRedundantSet on the device (cl_rank .. cl_walk .. cl_dead_packed .. cl_emit); hit ordering; K6 update_start_stops (warp Smith-Waterman); "
+           "K7 ksw_align (8 threads per alignment) + consensus groups; generic dr_search / ac_scan; edit_distance";
 }
 int crass_b200_device_count(void) { return probe_devices(); }
 

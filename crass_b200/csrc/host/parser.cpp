@@ -175,9 +175,19 @@ struct Input {
     }
 };
 
+// kstream refills a 4096-byte buffer and learns about the end of the input from a SHORT read: when the input's size is a
+// multiple of 4096 that flag is still clear after the last byte has been consumed, and the first ks_getuntil called there
+// returns an empty string instead of -1 (kseq.cpp:71-92) -- one extra record with an empty name and an empty sequence when
+// the last byte of such an input is a header character.  With the whole input in memory that state is one bit.
 struct Cursor {
     const uint8_t* p; size_t n, pos;
-    int getc() { return pos < n ? (int)(signed char)p[pos++] : -1; }      // ks_getc (kseq.cpp:55-69)
+    bool is_eof;
+    Cursor(const uint8_t* p_, size_t n_, size_t pos_) : p(p_), n(n_), pos(pos_), is_eof(n_ % 4096 != 0) {}
+    int getc() {                                                          // ks_getc (kseq.cpp:55-69)
+        if (pos < n) return (int)(signed char)p[pos++];
+        is_eof = true;
+        return -1;
+    }
 };
 
 inline bool c_isspace(uint8_t c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
@@ -194,7 +204,12 @@ const PlainTab kPlain;
 // (the reference returns -1 and leaves the target string untouched).
 bool get_until(Cursor& c, int delimiter, size_t& b, size_t& e, int& dret) {
     dret = 0;
-    if (c.pos >= c.n) return false;
+    if (c.pos >= c.n) {
+        if (c.is_eof) return false;
+        c.is_eof = true;                                                  // the refill that finds nothing happens inside this call
+        b = e = c.n;
+        return true;
+    }
     size_t i = c.pos;
     if (delimiter == 0) { while (i < c.n && !c_isspace(c.p[i])) ++i; }
     else {
@@ -202,7 +217,7 @@ bool get_until(Cursor& c, int delimiter, size_t& b, size_t& e, int& dret) {
         i = q ? (size_t)((const uint8_t*)q - c.p) : c.n;
     }
     b = c.pos; e = i;
-    if (i < c.n) { dret = (int)(signed char)c.p[i]; c.pos = i + 1; } else c.pos = c.n;
+    if (i < c.n) { dret = (int)(signed char)c.p[i]; c.pos = i + 1; } else { c.pos = c.n; c.is_eof = true; }
     return true;
 }
 
@@ -240,7 +255,7 @@ struct Piece {
 // The reference's read loop (libcrispr.cpp:96 over kseq_read, kseq.cpp:171-225) from the header character at `start`
 // (start == SIZE_MAX: from the top of the file, looking for the first header) until a header at or past `stop`.
 void parse_span(const uint8_t* data, size_t n, size_t start, size_t stop, Piece& P) {
-    Cursor c{data, n, 0};
+    Cursor c(data, n, 0);
     int last_char = 0;
     if (start != (size_t)-1) { c.pos = start + 1; last_char = (int)(signed char)data[start]; }
     int64_t cur_comment = -1, cur_qual = -1;

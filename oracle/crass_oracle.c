@@ -484,9 +484,18 @@ typedef struct {
     uint8_t* buf; size_t n, pos;
     kstr name, comment, seq, qual;
     int last_char;
+    int is_eof;                                       /* kstream's flag: a read of its 4096-byte buffer came back short */
 } kparser;
 
-static int kp_getc(kparser* k) { return k->pos < k->n ? (int)(signed char)k->buf[k->pos++] : -1; }
+/* kstream refills a 4096-byte buffer and learns about the end of the input from a SHORT read: when the input's size is a
+ * multiple of 4096 the flag is still clear after the last byte has been consumed, and the first ks_getuntil called there
+ * returns an empty string instead of -1 (kseq.cpp:71-92) -- one extra record with an empty name and an empty sequence when
+ * the last byte is a header character.  With the whole input in memory that state is one bit. */
+static int kp_getc(kparser* k) {
+    if (k->pos < k->n) return (int)(signed char)k->buf[k->pos++];
+    k->is_eof = 1;
+    return -1;
+}
 
 static void ks_put(kstr* s, size_t need) { if (need > s->m) { s->m = need * 2 + 16; s->s = (char*)realloc(s->s, s->m); } }
 
@@ -494,14 +503,20 @@ static void ks_put(kstr* s, size_t need) { if (need > s->m) { s->m = need * 2 + 
 static int kp_getuntil(kparser* k, int delimiter, kstr* str, int* dret) {
     if (dret) *dret = 0;
     str->l = 0;
-    if (k->pos >= k->n) return -1;
+    if (k->pos >= k->n) {
+        if (k->is_eof) return -1;
+        k->is_eof = 1;                                /* the refill that finds nothing happens inside this call */
+        ks_put(str, 1);
+        str->s[0] = 0;
+        return 0;
+    }
     size_t i = k->pos;
     if (delimiter > 1) { while (i < k->n && k->buf[i] != (uint8_t)delimiter) ++i; }
     else { while (i < k->n && !isspace(k->buf[i])) ++i; }
     ks_put(str, i - k->pos + 1);
     memcpy(str->s, k->buf + k->pos, i - k->pos);
     str->l = i - k->pos;
-    if (i < k->n) { if (dret) *dret = (int)(signed char)k->buf[i]; k->pos = i + 1; } else k->pos = i;
+    if (i < k->n) { if (dret) *dret = (int)(signed char)k->buf[i]; k->pos = i + 1; } else { k->pos = i; k->is_eof = 1; }
     str->s[str->l] = 0;
     return (int)str->l;
 }
@@ -549,6 +564,7 @@ static int kp_open(kparser* k, const char* path) {
         k->n += (size_t)r;
     }
     gzclose(fp);
+    k->is_eof = k->n % 4096 != 0;                     /* the short read has happened by the time the last byte is consumed */
     return 0;
 }
 static void kp_close(kparser* k) { free(k->buf); free(k->name.s); free(k->comment.s); free(k->seq.s); free(k->qual.s); }

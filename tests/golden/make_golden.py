@@ -50,6 +50,15 @@ KSEQ_CASES = {
     "empty_comment_then_stale": ">r1 \nAAAA\n>r2 real\nCCCC\n>r3\nGGGG\n",
     "lowercase_and_iupac": ">l1\nacgtNNRYacgt\n>l2\nACGTUacgtu\n",
 }
+# kstream's 4096-byte buffer: inputs whose size is a multiple of it and whose last byte is a header character yield one more
+# (empty) record than the same bytes one byte longer or shorter
+_fa = "".join(">q%03d\nACGTTGCAACGT\n" % i for i in range(100))
+KSEQ_CASES["exactly_4096_ending_in_gt"] = _fa + ">z c\n" + "A" * (4096 - len(_fa) - 5 - 2) + "\n>"
+_fq = "".join("@f%03d\nACGTAC\n+\nIIIIII\n" % i for i in range(300))
+_m = (8192 - len(_fq) - 3 - 3 - 2) // 2
+KSEQ_CASES["exactly_8192_fastq_then_at"] = _fq + "@p\n" + "C" * _m + "\n+\n" + "I" * _m + "\n@" + ("" if (8192 - len(_fq)) % 2 == 0 else "@")
+KSEQ_CASES["one_more_than_4096_ending_in_gt"] = KSEQ_CASES["exactly_4096_ending_in_gt"][:-2] + "A\n>"
+assert len(KSEQ_CASES["exactly_4096_ending_in_gt"]) == 4096 and len(KSEQ_CASES["exactly_8192_fastq_then_at"]) == 8192 and len(KSEQ_CASES["one_more_than_4096_ending_in_gt"]) == 4097
 
 
 def gen_update_start_stops(R):
@@ -115,6 +124,9 @@ def main():
         return
     if sys.argv[1:] == ["consensus"]:
         gen_consensus(R)
+        return
+    if sys.argv[1:] == ["kseq"]:
+        gen_kseq(R)
         return
     os.makedirs(os.path.join(HERE, "bundled"), exist_ok=True)
     sums = []
@@ -184,6 +196,12 @@ def main():
         vec.append(dict(patterns=[p.decode() for p in pats], texts=texts))
     json.dump(vec, open(os.path.join(HERE, "ac_vectors.json"), "w"))
 
+    gen_kseq(R)
+    gen_update_start_stops(R)
+    print("golden fixtures regenerated from", checkers.REF_SO)
+
+
+def gen_kseq(R):
     vec = {}
     with tempfile.TemporaryDirectory() as d:
         for name, content in KSEQ_CASES.items():
@@ -199,8 +217,6 @@ def main():
                     assert vec[name]["records"] == out
                 vec[name] = dict(content=content, records=out)
     json.dump(vec, open(os.path.join(HERE, "kseq_vectors.json"), "w"), indent=1)
-    gen_update_start_stops(R)
-    print("golden fixtures regenerated from", checkers.REF_SO)
 
 
 if __name__ == "__main__":
