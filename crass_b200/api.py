@@ -129,6 +129,7 @@ def lib():
         "crass_b200_results_non_redundant": (vp, [vp, C.c_uint32, u32p]),
         "crass_b200_results_dump": (vp, [vp, C.c_int]),
         "crass_b200_ctx_keep_packed": (C.c_int, [vp, C.c_int]),
+        "crass_b200_ctx_keep_packed_bases": (C.c_int, [vp, C.c_uint64]),
         "crass_b200_cluster_block_dev": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), vp]),
         "crass_b200_cluster_block_patterns_dev": (vp, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), vp]),
         "crass_b200_sort_hits": (None, [vp, C.c_uint32]),

@@ -126,6 +126,7 @@ struct crass_b200_ctx {
     int comm_world = 0, comm_rank = 0;
     DevBuf d_cons;                       // K7 (consensus DR): every device array of a call, carved from one allocation
     DevBuf d_ticket;                     // work counter of the long-read kernel
+    DevBuf d_long_list;                  // mixed batches: the reads the short-read filter leaves to the long-read kernel
     DevBuf d_cl_order, d_cl_koff, d_cl_keys, d_cl_first, d_cl_tab, d_cl_info;
     DevBuf d_cl_group, d_cl_chain, d_cl_next, d_cl_odd, d_cl_dead, d_cl_str;
     PinnedBuf h_cl_block, h_cl_order, h_cl_keys, h_cl_first, h_cl_info, h_cl_group, h_cl_dead, h_cl_str;
@@ -226,7 +227,7 @@ void crass_b200_ctx_destroy(crass_b200_ctx* c) {
                       &c->d_ac_bitmap, &c->d_ac_keys, &c->d_ac_skeys, &c->d_ac_shead, &c->d_ac_pnext, &c->d_ac_poffs, &c->d_ac_pbytes,
                       &c->d_rank, &c->d_hits_sorted, &c->d_cand_counts, &c->d_cand_mask, &c->d_ac_bitmap_small, &c->d_packed,
                       &c->d_cl_order, &c->d_cl_koff, &c->d_cl_keys, &c->d_cl_first, &c->d_cl_tab, &c->d_cl_info,
-                      &c->d_cl_group, &c->d_cl_chain, &c->d_cl_next, &c->d_cl_odd, &c->d_cl_dead, &c->d_cl_str, &c->d_ac_ones, &c->d_cl_tail, &c->d_cl_ckeys, &c->d_ticket, &c->d_cons};
+                      &c->d_cl_group, &c->d_cl_chain, &c->d_cl_next, &c->d_cl_odd, &c->d_cl_dead, &c->d_cl_str, &c->d_ac_ones, &c->d_cl_tail, &c->d_cl_ckeys, &c->d_ticket, &c->d_cons, &c->d_long_list};
     for (DevBuf* b : bufs) b->release();
     for (PinnedBuf* b : {&c->h_cl_block, &c->h_cl_order, &c->h_cl_keys, &c->h_cl_first, &c->h_cl_info, &c->h_ac_stage,
                          &c->h_cl_group, &c->h_cl_dead, &c->h_cl_str, &c->h_cl_pat}) b->release();
@@ -252,6 +253,12 @@ int crass_b200_ctx_set_token_output(crass_b200_ctx* c, void* d_tokens, uint32_t 
     return 0;
 }
 const char* crass_b200_ctx_last_dr_list(const crass_b200_ctx* c) { return c ? c->last_dr_list.c_str() : ""; }
+int crass_b200_ctx_keep_packed_bases(crass_b200_ctx* c, uint64_t n_bases) {
+    if (!c) return cbh::fail(CRASS_B200_EINVAL, "ctx is NULL");
+    c->keep_packed_bases = n_bases > 1 ? n_bases : (n_bases ? 1 : 0);
+    if (!n_bases) c->packed_valid = false;
+    return 0;
+}
 int crass_b200_ctx_keep_packed(crass_b200_ctx* c, int on) {
     if (!c) return cbh::fail(CRASS_B200_EINVAL, "ctx is NULL");
     c->keep_packed_bases = on ? 1 : 0;
@@ -868,7 +875,14 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
     auto keep_stream = [&](uint32_t** keep) -> int {
         *keep = nullptr;
         if (!(c->keep_packed_bases || c->packed_internal)) return 0;
-        const size_t words = (((size_t)n_reads * max_read_len) >> 4) + 256;          // n_bases <= n_reads * max_read_len
+        // the stream's size: the bases of the batch when the caller has said how many (crass_b200_ctx_keep_packed_bases; the
+        // resident calls know), else the bound n_reads * max_read_len -- which one long read among millions of short ones
+        // makes absurd: above 2^35 bases the stream is not kept (phase 2 then reads the bytes)
+        uint64_t bases_bound = (uint64_t)n_reads * max_read_len;
+        if (c->packed_internal && c->res_n_bases) bases_bound = c->res_n_bases;
+        else if (c->keep_packed_bases > 1) bases_bound = std::min<uint64_t>(bases_bound, c->keep_packed_bases);
+        if (bases_bound > ((uint64_t)1 << 35)) { c->packed_valid = false; return 0; }
+        const size_t words = (size_t)(bases_bound >> 4) + 256;
         const bool grew = words * sizeof(uint32_t) > c->d_packed.cap;
         if (int r = c->d_packed.reserve(words * sizeof(uint32_t))) return r;
         if (grew) CUDA_TRY(cudaMemsetAsync(c->d_packed.p, 0, c->d_packed.cap, st));       // look-ahead words past the batch are defined
@@ -972,6 +986,36 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
     // Long reads (config 3): one warp per read, 2-bit window flags in shared memory, warp-cooperative candidate handling.
     const bool geometry_ok = o.window == 8 && cb::window_skips(o) == 8 && o.low_dr + o.low_spacer == 49 && o.high_dr + o.high_spacer == 97;
     if (geometry_ok && max_read_len > 304 && max_read_len <= 65536 && (((uintptr_t)d_bases) & 15) == 0 && !(force && !strcmp(force, "generic"))) {
+        // Some read is longer than the 304 bases of the thread-per-read path.  Both paths are enqueued and sort it out on the
+        // device without a host round trip: in a batch of mostly short reads the warp filter takes everything up to 304 bases
+        // and lists the longer reads for the warp-per-read kernel; in a batch of mostly long reads (mean above 400 bases) the
+        // filter steps aside and the warp-per-read kernel takes all of it, as before.
+        const char* msel = getenv("CRASS_B200_K1_MIXED");
+        const bool mixed = !(msel && !strcmp(msel, "0"));
+        uint32_t* long_list = nullptr;
+        uint32_t* long_count = nullptr;
+        if (mixed) {
+            if (!d_found) { if (int r = c->d_found.reserve((size_t)n_reads + 16)) return r; d_found = c->d_found.as<uint8_t>(); }
+            if (int r = c->d_cand.reserve(((size_t)n_reads + 16) * sizeof(uint32_t))) return r;
+            if (int r = c->d_long_list.reserve(((size_t)n_reads + 16) * sizeof(uint32_t))) return r;
+            if (int r = c->d_cand_counts.reserve(16 * 4 * sizeof(uint32_t))) return r;
+            uint32_t* cand_counts = c->d_cand_counts.as<uint32_t>();
+            CUDA_TRY(cudaMemsetAsync(cand_counts, 0, 16 * 4 * sizeof(uint32_t), st));
+            long_list = c->d_long_list.as<uint32_t>();
+            long_count = cand_counts + 3;
+            uint32_t* keep_m = nullptr;
+            if (int r = keep_stream(&keep_m)) return r;
+            cbk::CandRegion region{c->d_cand.as<uint32_t>(), 0u, n_reads, cand_counts};
+            const size_t ssmem = cbk::dr_staged_smem_bytes<19>();
+            CUDA_TRY(cudaFuncSetAttribute(cbk::k_dr_exact_staged<19, 16, 49, 97>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+            const uint32_t w_tiles = (n_reads + 31) / 32;
+            cbk::k_dr_filter_warp<19, 16, 49, 97><<<(w_tiles + cbk::kFwWarps - 1) / cbk::kFwWarps, cbk::kFwWarps * 32, 0, st>>>(
+                d_bases, d_offsets, n_reads, 0u, n_reads, d_found, region, keep_m, long_list, long_count);
+            cbk::k_dr_exact_staged<19, 16, 49, 97><<<c->sm_count * 4, cbk::kExactThreads, ssmem, st>>>(
+                d_bases, d_offsets, n_reads, region, o, d_found, sink, c->d_error.as<int>(), cbk::kStageMin, cbk::kRefillMin);
+            c->launches += 2;
+            CUDA_TRY(cudaGetLastError());
+        }
         const uint32_t words = max_read_len / 16 + 32;
         const size_t smem = (size_t)cbk::kLongWarps * words * sizeof(uint32_t);
         CUDA_TRY(cudaFuncSetAttribute(cbk::k_dr_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -985,7 +1029,7 @@ int crass_b200_dr_search_dev(crass_b200_ctx* c, const uint8_t* d_bases, const ui
         if (int r = c->d_ticket.reserve(16)) return r;
         CUDA_TRY(cudaMemsetAsync(c->d_ticket.p, 0, 16, st));
         cbk::k_dr_long<<<blocks, cbk::kLongWarps * 32, smem, st>>>(d_bases, d_offsets, n_reads, o, d_found, sink, c->d_scratch.as<uint32_t>(), cap,
-                                                                   c->d_error.as<int>(), words, keep, c->d_ticket.as<uint32_t>());
+                                                                   c->d_error.as<int>(), words, keep, c->d_ticket.as<uint32_t>(), long_list, long_count);
         c->launches++;
         CUDA_TRY(cudaGetLastError());
         return 0;

@@ -481,6 +481,7 @@ int search_parsed(crass_b200_engine* e, std::unique_ptr<FileState> fs, const cra
         Shard& s = *f->shards[l.index];
         if (s.n() == 0) { s.searched = true; l.h_cnt.reserve(32); if (l.h_cnt.p) l.h_cnt.as<uint32_t>()[0] = 0; return 0; }
         if (int r = upload_shard(l, b, s)) return r;
+        crass_b200_ctx_keep_packed_bases(l.ctx, std::max<uint64_t>(2, s.b1 - s.b0));      // the 2-bit stream of exactly this shard
         auto launch = [&](uint32_t hits_cap, uint32_t pool_cap) {
             return crass_b200_dr_search_dev(l.ctx, s.d_bases.as<uint8_t>(), s.d_offsets.as<uint64_t>(), s.n(), (uint32_t)max_len, params,
                                             s.d_found.as<uint8_t>(), l.d_hits.as<crass_b200_hit>(), hits_cap, l.d_pool.as<uint32_t>(), pool_cap,

@@ -729,6 +729,11 @@ k_dr_filter(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offs
 // to keep the pipe fed.  Latency is hidden by the other warps instead of by a bulk copy in flight.
 constexpr int kFwWarps = 4;
 
+// a batch whose mean read length is above 400 bases is handled by the warp-per-read kernel as a whole
+__device__ __forceinline__ bool batch_is_mostly_long(const uint64_t* __restrict__ offsets, uint32_t n_reads) {
+    return offsets[n_reads] > 400ull * n_reads;
+}
+
 __device__ __noinline__ uint4 ragged_vector(const uint8_t* __restrict__ bases, uint64_t at, uint64_t n_bases) {
     uint32_t q[4] = {0, 0, 0, 0};
     for (int i = 0; i < 16; ++i)
@@ -740,7 +745,7 @@ template <int NW, int NWIN, int DMIN, int DMAX>
 __global__ void __launch_bounds__(kFwWarps * 32, (NW <= 10 ? 16 : 8))
 k_dr_filter_warp(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads,
                  uint32_t r_begin, uint32_t r_end, uint8_t* __restrict__ found, CandRegion cand,
-                 uint32_t* __restrict__ keep_packed) {
+                 uint32_t* __restrict__ keep_packed, uint32_t* __restrict__ long_list = nullptr, uint32_t* __restrict__ long_count = nullptr) {
     constexpr int kWords = 32 * NW + NW + 8;                   // a warp tile's packed words (+ look-ahead + realignment)
     __shared__ uint32_t sm_all[kFwWarps][kWords];
     uint32_t* sm = sm_all[threadIdx.x >> 5];
@@ -748,9 +753,14 @@ k_dr_filter_warp(const uint8_t* __restrict__ bases, const uint64_t* __restrict__
     // one tile per warp, no loop: nothing but the read's own registers is live while the flags are evaluated
     const uint32_t r0 = r_begin + ((blockIdx.x * kFwWarps + (threadIdx.x >> 5)) << 5);
     if (r0 >= r_end) return;
+    // MIXED batches (long_list given: some read is longer than the NW words a lane holds).  Reads that long go onto long_list
+    // for the warp-per-read kernel; everything else stays here -- one 305 bp read used to send ten million 150 bp reads to
+    // the warp-per-read kernel.  A batch of mostly long reads is that kernel's as a whole: this one steps aside.
+    if (long_list && batch_is_mostly_long(offsets, n_reads)) return;
     const uint32_t r1 = min(r0 + 32u, r_end);
     const uint32_t r = r0 + lane;
     uint32_t b;                                                 // base offset of the lane's read inside the packed tile
+    bool too_long = false;
     {
         const uint64_t my_off = offsets[min(r, r1 - 1u)];       // one coalesced load; the tile's extent comes by shuffle
         const uint64_t a0 = __shfl_sync(0xFFFFFFFFu, my_off, 0) & ~(uint64_t)15;
@@ -758,9 +768,33 @@ k_dr_filter_warp(const uint8_t* __restrict__ bases, const uint64_t* __restrict__
         b = (uint32_t)(my_off - a0);
         // the last read's realignment touches the words [wi, wi + NW + 2]
         uint32_t nvec = (uint32_t)((last_off - a0) >> 4) + NW + 3;
-        if (nvec > (uint32_t)kWords) nvec = kWords;
         uint32_t* keep = keep_packed ? keep_packed + (a0 >> 4) : nullptr;
         const uint64_t n_bases = offsets[n_reads];
+        if (long_list) {
+            const uint64_t tile_end = offsets[r1];
+            uint64_t nxt = __shfl_down_sync(0xFFFFFFFFu, my_off, 1);
+            if (r + 1u >= r1) nxt = tile_end;
+            too_long = r < r1 && nxt - my_off > (uint64_t)(16 * NW);
+            if (nvec > (uint32_t)kWords) {
+                // the tile does not fit its words (a long read inside it): its short reads go to the exact kernel unfiltered
+                // (it computes the flags of every candidate itself), and the 2-bit stream of the tile's bytes is written here
+                if (keep) {
+                    const uint64_t nv = (tile_end - a0 + 15) >> 4;
+                    for (uint64_t v = lane; v < nv; v += 32) {
+                        const uint64_t at = a0 + 16ull * v;
+                        const uint4 x = at + 16 <= n_bases ? ldg_stream128(bases + at) : ragged_vector(bases, at, n_bases);
+                        keep[v] = cb::pack16(x.x, x.y, x.z, x.w);
+                    }
+                }
+                if (r < r1) {
+                    found[r] = 0;
+                    if (too_long) long_list[atomicAdd(long_count, 1u)] = r;
+                    else cand.list[cand.lo + atomicAdd(&cand.counts[0], 1u)] = r;
+                }
+                return;
+            }
+        }
+        if (nvec > (uint32_t)kWords) nvec = kWords;
         const uint64_t avail = (n_bases - a0) >> 4;             // whole vectors the batch still holds from a0 on
         const uint32_t n_whole = avail < (uint64_t)nvec ? (uint32_t)avail : nvec;
         const uint8_t* src = bases + a0 + 16u * lane;
@@ -788,6 +822,7 @@ k_dr_filter_warp(const uint8_t* __restrict__ bases, const uint64_t* __restrict__
     }
     __syncwarp();
     if (r >= r1) return;
+    if (too_long) { found[r] = 0; long_list[atomicAdd(long_count, 1u)] = r; return; }    // (a long read in a tile that still fits)
     const uint32_t wi = b >> 4, sh = (b & 15u) * 2u;
     uint32_t R[NW + 2];
 #pragma unroll
@@ -1121,7 +1156,8 @@ constexpr int kLongWarps = 4;
 __global__ void __launch_bounds__(kLongWarps * 32, 10)
 k_dr_long(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads, Params o,
           uint8_t* __restrict__ found, HitSink sink, uint32_t* __restrict__ ss_scratch, uint32_t ss_cap, int* __restrict__ error_flag,
-          uint32_t words_per_warp, uint32_t* __restrict__ keep, uint32_t* __restrict__ ticket) {
+          uint32_t words_per_warp, uint32_t* __restrict__ keep, uint32_t* __restrict__ ticket,
+          const uint32_t* __restrict__ long_list = nullptr, const uint32_t* __restrict__ long_count = nullptr) {
     extern __shared__ uint32_t long_smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     uint32_t* S = long_smem + (size_t)warp * words_per_warp;           // the read, 2 bits per base, aligned to its start, zero padded
@@ -1131,11 +1167,15 @@ k_dr_long(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offset
     const uint64_t n_bases = offsets[n_reads];
     // reads are handed out one at a time in order (a ticket per warp): lengths of 1-10 kb and the few reads that carry an
     // array make a fixed assignment end with most warps idle
+    // mixed batches: only the reads the short-read filter listed (unless the batch is mostly long reads: then all of it)
+    const bool listed = long_list && !batch_is_mostly_long(offsets, n_reads);
+    const uint32_t n_mine = listed ? *long_count : n_reads;
     for (;;) {
         uint32_t r = 0;
         if (lane == 0) r = atomicAdd(ticket, 1u);
         r = __shfl_sync(cbl::kFull, r, 0);
-        if (r >= n_reads) break;
+        if (r >= n_mine) break;
+        if (listed) r = long_list[r];
         const uint64_t b = offsets[r];
         const uint32_t L = (uint32_t)(offsets[r + 1] - b);
         const int se = cb::search_end(o, L);

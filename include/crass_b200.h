@@ -102,6 +102,9 @@ int crass_b200_ctx_set_token_output(crass_b200_ctx* ctx, void* d_tokens, uint32_
  * the bytes (a quarter of the traffic, no recoding).  The caller promises that the bases are not modified between the
  * two launches.  Results are identical either way.  The resident host-buffer calls do this on their own. */
 int crass_b200_ctx_keep_packed(crass_b200_ctx* ctx, int on);
+/* the same with the number of bases of the batches that follow (0 = off): the stream is then sized exactly, which matters for
+ * batches of mixed lengths (n_reads * max_read_len is far too much when one read in millions is long) */
+int crass_b200_ctx_keep_packed_bases(crass_b200_ctx* ctx, uint64_t n_bases);
 /* the distinct tokens of the most recent crass_b200_dr_search_resident in read order, '\n'-separated (owned by ctx) */
 const char* crass_b200_ctx_last_dr_list(const crass_b200_ctx* ctx);
 /* the *_dev entry points leave hit records in device slot order; this puts a host copy into read order (what the

@@ -265,6 +265,44 @@ def test_long_reads_mixed_lengths_and_odd_content(ctx, P, k1path):
     assert check_batch_against_oracle(ctx, P, reads) > 100
 
 
+def test_mixed_batches_of_mostly_short_reads(ctx, P):
+    """A few reads above 304 bases among thousands of short ones: the warp filter keeps everything up to 304 bases (reads of
+    tiles that a long read blows up go to the exact kernel unfiltered) and lists the long ones for the warp-per-read kernel --
+    one long read used to send the whole batch there.  Hits against the oracle read by read, and phase 2 on the 2-bit stream
+    the mixed launch leaves behind against the byte-reading filter."""
+    rng = random.Random(114)
+    for n_long, long_lens in ((1, [305]), (25, [305, 320, 500, 1200, 4000]), (400, [310, 350, 400])):
+        reads = []
+        for _ in range(4000):
+            L = rng.choice([0, 40, 100, 150, 150, 150, 250, 304])
+            reads.append(fuzzgen.planted_read(rng, L, sub_rate=rng.choice([0, 0.01])) if L >= 100 and rng.random() < 0.4 else fuzzgen.rand_seq(rng, L))
+        for _ in range(n_long):
+            L = rng.choice(long_lens)
+            s_ = fuzzgen.planted_read(rng, L) if rng.random() < 0.6 else fuzzgen.rand_seq(rng, L)
+            reads.insert(rng.randint(0, len(reads)), s_)
+        reads = [fuzzgen.mutate(rng, r, 0.01, b"Nacgt") if rng.random() < 0.1 else r for r in reads]
+        assert sum(map(len, reads)) < 400 * len(reads)                    # mostly short: the mixed mode, not the long-read one
+        for mixed in ("1", "0"):
+            os.environ["CRASS_B200_K1_MIXED"] = mixed
+            try:
+                assert check_batch_against_oracle(ctx, P, reads) > 300
+            finally:
+                os.environ.pop("CRASS_B200_K1_MIXED", None)
+        # phase 2 of the same (resident) batch: the kept 2-bit stream must be complete whatever tile wrote it
+        bases, offs = cb.pack_reads(reads)
+        ctx.upload(bases, offs)
+        hits, pool, _ = ctx.dr_search_resident(cb.Params())
+        pats = api.non_redundant_list(ctx.last_dr_list(), 6)
+        ac = cb.Automaton(pats)
+        h_packed = ctx.ac_scan_resident(ac, skip_found=False)
+        os.environ["CRASS_B200_K2F"] = "bytes"
+        try:
+            h_bytes = ctx.ac_scan_resident(ac, skip_found=False)
+        finally:
+            os.environ.pop("CRASS_B200_K2F", None)
+        assert hits_by_read(h_packed[0], h_packed[1]) == hits_by_read(h_bytes[0], h_bytes[1]) and len(h_packed[0]) > 300
+
+
 def test_synthetic_config2_prefix(ctx, P, k1path):
     """A 300k-read prefix of the BASELINE config-2 recipe, compared read by read with the oracle."""
     genome, drs, _ = synth.make_genome(20242)
