@@ -320,6 +320,105 @@ def test_synthetic_config2_prefix(ctx, P, k1path):
         assert got[int(i)] == (ss, rl)
 
 
+def test_full_size_config2_properties(ctx, P):
+    """BASELINE.json configs[1] at its FULL size (10 M x 150 bp, the bench's recipe and seed): properties that do not need the
+    oracle on every read.  (1) determinism: two runs give the same hit set; (2) shard additivity: the hits of the whole
+    batch are the hits of its two halves and of an odd three-way cut (no result depends on what lies next to a read: tiles,
+    look-ahead words, the kept 2-bit stream); (3) the read-ordered copy is a permutation of the slot-ordered hits, sorted
+    and one per flagged read; (4) phase 2 never reports a read phase 1 flagged, and its answers on the kept 2-bit stream
+    equal those of the byte-reading filter; (5) the oracle on 3 000 reads drawn from all over the batch agrees flag by flag
+    and list by list."""
+    import hashlib
+    import torch
+    dev = torch.device("cuda", 0)
+    s = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(s)
+    n, L, TOK = 10_000_000, 150, 64
+    genome, _, _ = synth.make_genome(20242)
+    d_bases, d_offsets = synth.sample_fixed_torch(genome, n, L, 20242 + 1000, dev)
+    d_offsets = d_offsets.to(torch.int64)
+    cap = n // 4 + 1024
+    d_found = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_hits = torch.empty(cap * 4, dtype=torch.int32, device=dev)
+    d_sorted = torch.empty(cap * 4, dtype=torch.int32, device=dev)
+    d_pool = torch.empty(n + 4096, dtype=torch.int32, device=dev)
+    d_cnt = torch.zeros(8, dtype=torch.int32, device=dev)
+    prm = cb.Params()
+    ctx.keep_packed(True)
+
+    def search(lo, hi):
+        """hits of reads [lo, hi) as {global read index: (start/stop tuple, repeat length)} + the sorted copy's read indices"""
+        m = hi - lo
+        off = d_offsets[lo:hi + 1] - d_offsets[lo]
+        bas = d_bases[int(d_offsets[lo]): int(d_offsets[hi])]
+        ctx.dr_search_dev(bas, off, m, L, prm, d_found, d_hits, d_pool, d_cnt, s.cuda_stream)
+        ctx.sort_hits_dev(d_found, m, d_hits, d_cnt, cap, d_sorted, s.cuda_stream)
+        s.synchronize()
+        c = d_cnt.cpu().numpy()
+        assert c[2] == 0
+        nh = int(c[0])
+        hits = d_sorted[: nh * 4].cpu().numpy().view(api.HIT_DTYPE)
+        raw = d_hits[: nh * 4].cpu().numpy().view(api.HIT_DTYPE)
+        pool = d_pool[: int(c[1])].cpu().numpy().view(np.uint32)
+        flags = d_found[:m].cpu().numpy()
+        # (3) sorted, one per flagged read, a permutation of the slot-ordered records
+        assert np.all(np.diff(hits["read_index"].astype(np.int64)) > 0)
+        assert np.array_equal(hits["read_index"], np.flatnonzero(flags).astype(np.uint32))
+        assert np.array_equal(np.sort(raw, order=["read_index"]), hits)
+        out = {int(h["read_index"]) + lo: (tuple(int(x) for x in pool[h["ss_offset"]: h["ss_offset"] + h["n_ss"]]), int(h["repeat_len"])) for h in hits}
+        return out, flags
+
+    whole, flags = search(0, n)
+    assert len(whole) > 50_000
+    digest = hashlib.md5(repr(sorted(whole.items())).encode()).hexdigest()
+    again, _ = search(0, n)
+    assert hashlib.md5(repr(sorted(again.items())).encode()).hexdigest() == digest                 # (1)
+    for cuts in ((0, n // 2, n), (0, 3_333_337, 6_000_001, n)):                                        # (2)
+        parts = {}
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            parts.update(search(lo, hi)[0])
+        assert parts == whole, cuts
+    # (5) the oracle on reads from all over the batch
+    rng = np.random.default_rng(7)
+    pick = np.unique(np.concatenate([rng.integers(0, n, 2500), np.flatnonzero(flags)[:: max(1, len(whole) // 500)]]))
+    h_reads = d_bases.view(n, L)[torch.from_numpy(pick).to(dev)].cpu().numpy()
+    for i, row in zip(pick, h_reads):
+        f, ss, rl = P.search_core(row.tobytes())
+        assert bool(f) == bool(flags[i])
+        if f:
+            assert whole[int(i)] == (tuple(ss), rl)
+    # (4) phase 2 on the whole batch: the matcher from the batch's own DR variants
+    whole2, flags = search(0, n)                                                                       # d_found / the 2-bit stream of the WHOLE batch again
+    d_tok = torch.empty(cap * TOK, dtype=torch.uint8, device=dev)
+    ctx.set_token_output(d_tok, TOK)
+    ctx.dr_search_dev(d_bases, d_offsets, n, L, prm, d_found, d_hits, d_pool, d_cnt, s.cuda_stream)
+    ctx.set_token_output(None)
+    nh = int(d_cnt.cpu()[0])
+    blk = torch.empty(api.token_block_bytes(16384, TOK), dtype=torch.uint8, device=dev)
+    ctx.unique_tokens_block_dev(d_hits, nh, d_tok, TOK, blk, 16384, s.cuda_stream)
+    ac, cnt, fl = ctx.cluster_block_dev(blk, 16384, TOK, 6, s.cuda_stream)
+    assert fl == 0 and ac is not None and ac.num_patterns > 500
+    d_found2 = torch.empty(n, dtype=torch.uint8, device=dev)
+    answers = []
+    for mode in (None, "bytes"):
+        if mode:
+            os.environ["CRASS_B200_K2F"] = mode
+        try:
+            ctx.ac_scan_dev(ac, d_bases, d_offsets, n, L, d_found, d_found2, d_hits, d_pool, d_cnt, s.cuda_stream)
+            s.synchronize()
+        finally:
+            os.environ.pop("CRASS_B200_K2F", None)
+        c = d_cnt.cpu().numpy()
+        h2 = np.sort(d_hits[: int(c[0]) * 4].cpu().numpy().view(api.HIT_DTYPE), order=["read_index"])
+        p2 = d_pool[: int(c[1])].cpu().numpy().view(np.uint32)
+        f2 = d_found2.cpu().numpy()
+        assert not np.any(f2 & d_found.cpu().numpy())                      # never a read phase 1 has
+        answers.append((h2["read_index"].copy(), np.stack([p2[h2["ss_offset"]], p2[h2["ss_offset"] + 1]], axis=1), f2))
+    assert len(answers[0][0]) > 20_000
+    assert all(np.array_equal(a, b) for a, b in zip(answers[0], answers[1]))
+    ctx.keep_packed(False)
+
+
 def test_device_dr_tokens_match_host_lowlexi(ctx, k1path):
     """K4: the low-lexi DR token written next to every hit on the device == ReadHolder::DRLowLexi replayed on the host
     (which test_host_logic pins against the reference), including first-appearance order of the distinct tokens."""
