@@ -105,6 +105,7 @@ struct crass_b200_ctx {
     int sm_count = 0;
     uint64_t launches = 0;
     uint64_t last_candidates = 0;
+    uint64_t hits_per_64k = 0, pool_per_64k = 0;         // the most records / pool words per 65 536 reads any host-form call needed
     DevBuf d_bases, d_offsets, d_found, d_skip, d_hits, d_pool, d_counters, d_scratch, d_error, d_misc, d_symv;
     uint32_t* h_counters = nullptr;   // pinned, 8 words
     // resident batch (crass_b200_batch_upload)
@@ -1056,8 +1057,12 @@ namespace {
 template <class Launch>
 int run_with_outputs(crass_b200_ctx* c, uint32_t n_reads, uint64_t n_bases, uint8_t* found_host, Launch launch,
                      crass_b200_hit** hits, uint32_t* n_hits, uint32_t** ss_pool, uint32_t* n_ss_pool, uint32_t token_stride = 0) {
+    // first guess: a quarter of the reads hit; later calls start from what this context has seen plus a quarter, so a
+    // sample where phase 2 recruits most reads re-runs one kernel once and not once per batch
     uint32_t hits_cap = std::max<uint32_t>(4096, n_reads / 4 + 16);
     uint32_t pool_cap = hits_cap * 6;
+    hits_cap = (uint32_t)std::min<uint64_t>((uint64_t)n_reads + 16, std::max<uint64_t>(hits_cap, (c->hits_per_64k * n_reads >> 16) * 5 / 4 + 1024));
+    pool_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFF0ull, std::max<uint64_t>(pool_cap, (c->pool_per_64k * n_reads >> 16) * 5 / 4 + 4096));
     if (int r = c->d_counters.reserve(8 * sizeof(uint32_t))) return r;
     if (int r = c->d_found.reserve((size_t)n_reads + 16)) return r;
     // the "reference would throw" flag belongs to this call: a flag left by an earlier search must not fail a scan
@@ -1087,6 +1092,10 @@ int run_with_outputs(crass_b200_ctx* c, uint32_t n_reads, uint64_t n_bases, uint
     }
     const uint32_t nh = c->h_counters[0], np = c->h_counters[1];
     c->last_candidates = c->h_counters[3];
+    if (n_reads) {
+        c->hits_per_64k = std::max<uint64_t>(c->hits_per_64k, (((uint64_t)nh << 16) + n_reads - 1) / n_reads);
+        c->pool_per_64k = std::max<uint64_t>(c->pool_per_64k, (((uint64_t)np << 16) + n_reads - 1) / n_reads);
+    }
     crass_b200_hit* h = (crass_b200_hit*)malloc(sizeof(crass_b200_hit) * (size_t)(nh ? nh : 1));
     uint32_t* p = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(np ? np : 1));
     if (!h || !p) { free(h); free(p); return cbh::fail(CRASS_B200_ENOMEM, "malloc"); }

@@ -113,17 +113,108 @@ void one_read(const ReadHolder& h, const uint32_t* extra, size_t n_extra, std::v
     offs[0] = 0; offs[1] = bases.size();
 }
 
+
+
+// The progress lines of one file.  The reference prints one before every 100 000th read of a FILE as it reads it (its
+// log_counter is per call, libcrispr.cpp:91,99-109; :495-496 in phase 2) showing the running total over all files, and one
+// more when the file ends.  Here the reads arrive range by range: a line that falls exactly on the end of a range is held back
+// until the next range shows that the file goes on.
+struct Ticker {
+    const char* who; int base; time_t* start;
+    uint64_t seen = 0;                                              // reads of this file handed over so far
+    bool held = false;
+    Ticker(const char* w, int b, time_t* s) : who(w), base(b), start(s) {}
+    // reads [seen, seen + n) arrive; `replay(upto)` handles the hits of the reads below local index upto
+    template <class Replay>
+    void range(uint32_t n, Replay replay) {
+        if (held && n) { progress(who, base + (int)seen, *start); held = false; }
+        uint32_t done = 0;
+        while (done < n) {
+            const uint64_t to_tick = CRASS_DEF_READ_COUNTER_LOGGER - seen % CRASS_DEF_READ_COUNTER_LOGGER;
+            const uint32_t upto = (uint32_t)std::min<uint64_t>(n, (uint64_t)done + to_tick);
+            replay(upto);
+            seen += upto - done;
+            done = upto;
+            if (seen % CRASS_DEF_READ_COUNTER_LOGGER == 0) {
+                if (done < n) progress(who, base + (int)seen, *start); else held = true;
+            }
+        }
+    }
+};
+
+struct Phase1Sink {
+    ReadMap* reads; StringCheck* strings; lookupTable* patterns; lookupTable* found;
+    Ticker tick;
+    std::string failure;                                            // what() of an exception the containers threw
+    Phase1Sink(ReadMap* r, StringCheck* s, lookupTable* p, lookupTable* f, int base, time_t* t)
+        : reads(r), strings(s), patterns(p), found(f), tick("patternFinder", base, t) {}
+};
+
+int phase1_range(void* user, const crass_b200_batch* batch, const crass_b200_hit* hits, uint32_t n_hits, const uint32_t* pool,
+                 uint32_t, uint64_t) {
+    Phase1Sink& k = *(Phase1Sink*)user;
+    try {
+        uint32_t at = 0;
+        k.tick.range(crass_b200_batch_num_reads(batch), [&](uint32_t upto) {
+            for (; at < n_hits && hits[at].read_index < upto; ++at) {           // hits come sorted by read index
+                const crass_b200_hit& ht = hits[at];
+                ReadHolder tmp_holder;
+                fill_holder(tmp_holder, batch, ht.read_index);
+                for (uint32_t i = 0; i + 1 < ht.n_ss; i += 2) tmp_holder.startStopsAdd(pool[ht.ss_offset + i], pool[ht.ss_offset + i + 1]);
+                tmp_holder.setRepeatLength((int)ht.repeat_len);
+                addReadHolder(k.reads, k.strings, tmp_holder);
+                (*k.patterns)[tmp_holder.repeatStringAt(0)] = true;
+                (*k.found)[tmp_holder.getHeader()] = true;
+            }
+        });
+    } catch (crispr::exception& e) {                                            // must not leave the engine's thread
+        k.failure = e.what();
+        return CRASS_B200_EINVAL;
+    }
+    return 0;
+}
+
+struct Phase2Sink {
+    ReadMap* reads; StringCheck* strings; lookupTable* found;
+    Ticker tick;
+    Phase2Sink(ReadMap* r, StringCheck* s, lookupTable* f, int base, time_t* t) : reads(r), strings(s), found(f), tick("singletonFinder", base, t) {}
+};
+
+int phase2_range(void* user, const crass_b200_batch* batch, const crass_b200_hit* hits, uint32_t n_hits, const uint32_t* pool,
+                 uint32_t, uint64_t) {
+    Phase2Sink& k = *(Phase2Sink*)user;
+    uint32_t at = 0;
+    k.tick.range(crass_b200_batch_num_reads(batch), [&](uint32_t upto) {
+        for (; at < n_hits && hits[at].read_index < upto; ++at) {               // on_match (libcrispr.cpp:408-442)
+            const crass_b200_hit& ht = hits[at];
+            const char* name = crass_b200_batch_name(batch, ht.read_index);
+            if (k.found->find(name) != k.found->end()) continue;
+            ReadHolder tmp_holder;
+            fill_holder(tmp_holder, batch, ht.read_index);
+            tmp_holder.startStopsAdd(pool[ht.ss_offset], pool[ht.ss_offset + 1]);
+            addReadHolder(k.reads, k.strings, tmp_holder);
+        }
+    });
+    return 0;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
 int searchFile(const char* inputFastq, const options& opts, ReadMap* mReads, StringCheck* mStringCheck,
                lookupTable& patternsHash, lookupTable& readsFound, time_t& time_start) {
     static int read_counter = 0;
-    const crass_b200_batch* batch = NULL;
-    HitGuard hg;
     crass_b200_params p = to_params(opts);
-    // parse (worker threads) -> shards -> HBM -> K1 on every device; the file stays parsed and resident for findSingletons
-    if (crass_b200_engine_search_file(file_engine(), inputFastq, &p, &batch, &hg.hits, &hg.n, &hg.pool, &hg.np)) {
+    Phase1Sink sink(mReads, mStringCheck, &patternsHash, &readsFound, read_counter, &time_start);
+    int max_read_length = 0;
+    // The kseq loop of libcrispr.cpp:96-131 as a pipeline: worker threads parse range i+1 of the file while range i is copied
+    // to the devices and searched (K1 on every device) and the hits of range i-1 are replayed, in read order, into the caller's
+    // containers by phase1_range.  The ranges stay parsed and resident in HBM for findSingletons.
+    if (crass_b200_engine_search_file_ranges(file_engine(), inputFastq, &p, phase1_range, &sink, &max_read_length)) {
+        if (!sink.failure.empty()) {
+            std::cerr << sink.failure << std::endl;
+            throw crispr::exception(__FILE__, __LINE__, __PRETTY_FUNCTION__, "Fatal error in search algorithm!");
+        }
         const std::string why = crass_b200_last_error();
         if (why.find("cannot open") != std::string::npos) {          // getFileHandle() exits on an unopenable file (SeqUtils.cpp:112-122)
             std::cerr << PACKAGE_NAME << " : [ERROR] Could not open FASTQ " << inputFastq << " for reading." << std::endl;
@@ -132,33 +223,7 @@ int searchFile(const char* inputFastq, const options& opts, ReadMap* mReads, Str
         std::cerr << why << std::endl;
         throw crispr::exception(__FILE__, __LINE__, __PRETTY_FUNCTION__, "Fatal error in search algorithm!");
     }
-    const uint32_t n = crass_b200_batch_num_reads(batch);
-    const int max_read_length = (int)crass_b200_batch_max_read_len(batch);
-    try {
-        // the reference prints a progress line before every 100 000th read of a FILE (its log_counter is per call,
-        // libcrispr.cpp:91,99-109) showing the running total; the reads are all through the device by now, so the lines of
-        // this file come in one go, with the hits replayed in between in read order
-        uint32_t k = 0;
-        for (uint32_t done = 0; done < n;) {
-            const uint32_t upto = (uint32_t)std::min<uint64_t>(n, (uint64_t)done + CRASS_DEF_READ_COUNTER_LOGGER);
-            for (; k < hg.n && hg.hits[k].read_index < upto; ++k) {     // hits come back sorted by read index
-                const crass_b200_hit& ht = hg.hits[k];
-                ReadHolder tmp_holder;
-                fill_holder(tmp_holder, batch, ht.read_index);
-                for (uint32_t i = 0; i + 1 < ht.n_ss; i += 2) tmp_holder.startStopsAdd(hg.pool[ht.ss_offset + i], hg.pool[ht.ss_offset + i + 1]);
-                tmp_holder.setRepeatLength((int)ht.repeat_len);
-                addReadHolder(mReads, mStringCheck, tmp_holder);
-                patternsHash[tmp_holder.repeatStringAt(0)] = true;
-                readsFound[tmp_holder.getHeader()] = true;
-            }
-            done = upto;
-            if (done < n) progress("patternFinder", read_counter + (int)done, time_start);
-        }
-    } catch (crispr::exception& e) {
-        std::cerr << e.what() << std::endl;
-        throw crispr::exception(__FILE__, __LINE__, __PRETTY_FUNCTION__, "Fatal error in search algorithm!");
-    }
-    read_counter += (int)n;
+    read_counter += (int)sink.tick.seen;
     logInfo("finished processing file:" << inputFastq, 1);
     progress("patternFinder", read_counter, time_start);
     logInfo("So far " << mReads->size() << " direct repeat variants have been found from " << read_counter << " reads", 2);
@@ -177,12 +242,12 @@ void findSingletons(const char* inputFastq, const options& opts, std::vector<std
     }
     crass_b200_ac* ac = NULL;
     B200_TRY(crass_b200_ac_build(bytes.data(), offs.data(), (uint32_t)nonRedundantPatterns->size(), &ac));
-    const crass_b200_batch* batch = NULL;
-    HitGuard hg;
-    // K2 over the shards searchFile left in HBM (no second parse, no second copy; a file this engine has not seen is parsed
-    // and copied in now).  Every read is scanned: readsFound is the CALLER's table, keyed by header, and may hold names the
-    // device flags know nothing about, so that test stays on the host (libcrispr.cpp:411).
-    int rc = crass_b200_engine_find_singletons(file_engine(), inputFastq, ac, 0, &batch, &hg.hits, &hg.n, &hg.pool, &hg.np);
+    Phase2Sink sink(mReads, mStringCheck, &readsFound, read_counter, &startTime);
+    // K2 over the ranges searchFile left in HBM (no second parse, no second copy; a file this engine has not seen is parsed
+    // and copied in now), the matches of one range replayed while the next is scanned.  Every read is scanned: readsFound is the
+    // CALLER's table, keyed by header, and may hold names the device flags know nothing about, so that test stays on the host
+    // (libcrispr.cpp:411).
+    int rc = crass_b200_engine_find_singletons_ranges(file_engine(), inputFastq, ac, 0, phase2_range, &sink);
     crass_b200_ac_destroy(ac);
     if (rc) {
         const std::string why = crass_b200_last_error();
@@ -192,23 +257,7 @@ void findSingletons(const char* inputFastq, const options& opts, std::vector<std
         }
         throw crispr::exception(__FILE__, __LINE__, __PRETTY_FUNCTION__, why.c_str());
     }
-    const uint32_t n = crass_b200_batch_num_reads(batch);
-    uint32_t k = 0;
-    for (uint32_t done = 0; done < n;) {                             // progress lines as in libcrispr.cpp:495-496
-        const uint32_t upto = (uint32_t)std::min<uint64_t>(n, (uint64_t)done + CRASS_DEF_READ_COUNTER_LOGGER);
-        for (; k < hg.n && hg.hits[k].read_index < upto; ++k) {      // on_match (libcrispr.cpp:408-442)
-            const crass_b200_hit& ht = hg.hits[k];
-            const char* name = crass_b200_batch_name(batch, ht.read_index);
-            if (readsFound.find(name) != readsFound.end()) continue;
-            ReadHolder tmp_holder;
-            fill_holder(tmp_holder, batch, ht.read_index);
-            tmp_holder.startStopsAdd(hg.pool[ht.ss_offset], hg.pool[ht.ss_offset + 1]);
-            addReadHolder(mReads, mStringCheck, tmp_holder);
-        }
-        done = upto;
-        if (done < n) progress("singletonFinder", read_counter + (int)done, startTime);
-    }
-    read_counter += (int)n;
+    read_counter += (int)sink.tick.seen;
     progress("singletonFinder", read_counter, startTime);
     crass_b200_engine_release_file(file_engine(), inputFastq);      // phase 2 is the last use of a file (WorkHorse.cpp:381-399)
 }

@@ -28,6 +28,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <deque>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -101,6 +102,7 @@ struct Lane {                                             // one device: context
     DBuf d_hits, d_sorted, d_pool, d_cnt, d_tokens, d_found2, d_block, d_recv, d_merged;
     HBuf h_cnt, h_offsets, h_hits, h_pool;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
+    uint64_t hits_per_64k = 0, pool_per_64k = 0;          // the most records / pool words per 65 536 reads any call needed so far
     void* comm = nullptr;                                 // ncclComm_t
     int rc = 0;
     std::string err;
@@ -120,6 +122,7 @@ struct FileState {
 struct crass_b200_engine {
     std::vector<std::unique_ptr<Lane> > lanes;
     std::vector<std::unique_ptr<FileState> > files;
+    std::map<std::string, std::vector<std::string> > ranged;  // files searched range by range: the names their ranges are resident under
     std::vector<crass_b200_batch*> batch_pool;            // released batches: their buffers (page-locked bases) serve the next parse
     std::mutex pool_mu;                                   // ... taken by the parsing thread of a streamed run while another thread searches
     size_t stream_bytes = (size_t)256 << 20;              // range size of the streamed feed (CRASS_B200_STREAM_MB; 0 = whole files)
@@ -249,7 +252,11 @@ int upload_shard(Lane& l, const cbh::Batch& b, Shard& s) {
 template <class Launch>
 int collect_hits(Lane& l, uint32_t n_reads, const uint8_t* d_flags, Launch launch, HitList& out, uint32_t kTokStride) {
     const bool want_tokens = kTokStride != 0;
+    // first guess: a quarter of the reads hit; afterwards what this lane has seen, plus a quarter (a sample where phase 2
+    // recruits most reads overflows once, on its first range, and never again)
     uint32_t hits_cap = std::max<uint32_t>(4096, n_reads / 4 + 1024), pool_cap = hits_cap * 6;
+    hits_cap = (uint32_t)std::min<uint64_t>((uint64_t)n_reads + 16, std::max<uint64_t>(hits_cap, (l.hits_per_64k * n_reads >> 16) * 5 / 4 + 1024));
+    pool_cap = (uint32_t)std::min<uint64_t>(0xFFFFFFF0ull, std::max<uint64_t>(pool_cap, (l.pool_per_64k * n_reads >> 16) * 5 / 4 + 4096));
     if (int r = l.d_cnt.reserve(8 * sizeof(uint32_t))) return r;
     if (int r = l.h_cnt.reserve(8 * sizeof(uint32_t))) return r;
     uint32_t* hc = l.h_cnt.as<uint32_t>();
@@ -270,6 +277,10 @@ int collect_hits(Lane& l, uint32_t n_reads, const uint8_t* d_flags, Launch launc
         hits_cap = hc[0] + 16; pool_cap = hc[1] + 16;                             // the counters include what did not fit
     }
     const uint32_t nh = hc[0], np = hc[1];
+    if (n_reads) {
+        l.hits_per_64k = std::max<uint64_t>(l.hits_per_64k, (((uint64_t)nh << 16) + n_reads - 1) / n_reads);
+        l.pool_per_64k = std::max<uint64_t>(l.pool_per_64k, (((uint64_t)np << 16) + n_reads - 1) / n_reads);
+    }
     out.hits.resize(nh); out.pool.resize(np);
     if (nh) {
         if (int r = l.d_sorted.reserve((size_t)nh * sizeof(crass_b200_hit))) return r;
@@ -429,6 +440,12 @@ void crass_b200_engine_stage_ms(const crass_b200_engine* e, double* parse, doubl
 
 void crass_b200_engine_release_file(crass_b200_engine* e, const char* path) {
     if (!e || !path) return;
+    auto rg = e->ranged.find(path);
+    if (rg != e->ranged.end()) {                                               // a file searched range by range: all its ranges
+        const std::vector<std::string> names = rg->second;
+        e->ranged.erase(rg);
+        for (const std::string& nm : names) crass_b200_engine_release_file(e, nm.c_str());
+    }
     for (size_t i = 0; i < e->files.size(); ++i) {
         if (e->files[i]->path != path) continue;
         FileState* f = e->files[i].get();
@@ -528,8 +545,12 @@ struct SearchedRange {
     uint32_t* pool = nullptr; uint32_t np = 0;
 };
 
-int run_streamed(crass_b200_engine* e, cbh::ParseStream* ps, const char* path, const crass_b200_params* params, int phases,
-                 crass_b200_results* res, int* max_len) {
+// phase 1 of a streamed run: this thread parses range after range (worker threads inside the parser), a second thread copies
+// each parsed range to the devices and runs K1 on it, a third hands the hits of each searched range, in file order, to
+// `consume` (the replay into the containers).  The ranges stay resident under the names left in range_paths.
+template <class Consume>
+int stream_phase1(crass_b200_engine* e, cbh::ParseStream* ps, const char* path, const crass_b200_params* params, Consume consume,
+                  int* max_len, std::vector<std::string>& range_paths) {
     StageQueue<std::unique_ptr<FileState> > parsed;
     StageQueue<SearchedRange> searched;
     std::atomic<int> fail_rc{0};
@@ -539,7 +560,6 @@ int run_streamed(crass_b200_engine* e, cbh::ParseStream* ps, const char* path, c
         std::lock_guard<std::mutex> g(fail_mu);
         if (!fail_rc.load()) { fail_msg = crass_b200_last_error(); fail_rc.store(rc); }
     };
-    std::vector<std::string> range_paths;
     std::thread searcher([&]() {
         std::unique_ptr<FileState> fs;
         while (parsed.pop(fs)) {
@@ -553,17 +573,18 @@ int run_streamed(crass_b200_engine* e, cbh::ParseStream* ps, const char* path, c
     });
     std::thread replayer([&]() {
         SearchedRange r;
+        uint64_t first_read = 0;
         while (searched.pop(r)) {
             if (!fail_rc.load()) {
                 const double t0 = now_ms();
-                const int rc = crass_b200_results_add_phase1(res, r.batch, r.hits, r.nh, r.pool);
+                const int rc = consume(r, first_read);
                 e->t_replay += now_ms() - t0;
                 if (rc) note_failure(rc);
             }
+            first_read += crass_b200_batch_num_reads(r.batch);
             free(r.hits); free(r.pool);
         }
     });
-    // this thread: the parser (its own worker threads inside)
     for (uint32_t i = 0; !fail_rc.load(); ++i) {
         crass_b200_batch* h = take_batch(e, e->stream_bytes);
         const double t0 = now_ms();
@@ -580,8 +601,17 @@ int run_streamed(crass_b200_engine* e, cbh::ParseStream* ps, const char* path, c
     parsed.close();
     searcher.join();
     replayer.join();
-    int rc = fail_rc.load();
+    const int rc = fail_rc.load();
     if (rc) cbh::fail(rc, fail_msg);
+    return rc;
+}
+
+int run_streamed(crass_b200_engine* e, cbh::ParseStream* ps, const char* path, const crass_b200_params* params, int phases,
+                 crass_b200_results* res, int* max_len) {
+    std::vector<std::string> range_paths;
+    int rc = stream_phase1(e, ps, path, params, [&](const SearchedRange& r, uint64_t) {
+        return crass_b200_results_add_phase1(res, r.batch, r.hits, r.nh, r.pool);
+    }, max_len, range_paths);
     if (!rc && phases >= 2) {
         // the containers' token list (filled in read order above) is the sequential numbering
         crass_b200_ac* ac = nullptr;
@@ -665,6 +695,61 @@ int crass_b200_engine_find_singletons(crass_b200_engine* e, const char* path, co
     *hits_out = h; *n_hits = (uint32_t)hits.size(); *pool_out = p; *n_pool = (uint32_t)pool.size();
     if (batch_out) *batch_out = f->batch;
     return 0;
+}
+
+// searchFile, streamed: what crass_b200_engine_search_file does, but the file goes through the devices range by range
+// (stream_phase1) and `fn` gets the hits of each range, in file order, on ONE helper thread while later ranges are still being
+// parsed and searched.  The caller is inside this call the whole time, so its containers are only ever touched by that one
+// thread.  A non-zero return of fn ends the run with that code.  The ranges stay resident for
+// crass_b200_engine_find_singletons_ranges and go with crass_b200_engine_release_file(path).
+int crass_b200_engine_search_file_ranges(crass_b200_engine* e, const char* path, const crass_b200_params* params,
+                                         crass_b200_range_fn fn, void* user, int* max_read_len) {
+    if (!e || !path || !params || !fn) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    crass_b200_engine_release_file(e, path);
+    cbh::ParseStream* ps = cbh::parse_stream_open(path, e->stream_bytes);       // 0: the whole file is one range
+    if (!ps) return CRASS_B200_EIO;
+    int max_len = 0;
+    std::vector<std::string> range_paths;
+    const int rc = stream_phase1(e, ps, path, params, [&](const SearchedRange& r, uint64_t first_read) {
+        return fn(user, r.batch, r.hits, r.nh, r.pool, r.np, first_read);
+    }, &max_len, range_paths);
+    cbh::parse_stream_close(ps);
+    e->ranged[path] = range_paths;
+    if (rc) { crass_b200_engine_release_file(e, path); return rc; }
+    if (max_read_len) *max_read_len = max_len;
+    return 0;
+}
+
+// findSingletons over the ranges crass_b200_engine_search_file_ranges left resident (a file it has not seen is searched as a
+// whole, parsed and copied in now): a helper thread runs K2 range after range, `fn` is called on THIS thread in file order.
+int crass_b200_engine_find_singletons_ranges(crass_b200_engine* e, const char* path, const crass_b200_ac* ac, int skip_found,
+                                             crass_b200_range_fn fn, void* user) {
+    if (!e || !path || !ac || !fn) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    std::vector<std::string> names;
+    auto it = e->ranged.find(path);
+    if (it != e->ranged.end()) names = it->second; else names.push_back(path);
+    StageQueue<SearchedRange> scanned;
+    int scan_rc = 0; std::string scan_err;
+    std::thread scanner([&]() {
+        for (const std::string& nm : names) {
+            SearchedRange r;
+            scan_rc = crass_b200_engine_find_singletons(e, nm.c_str(), ac, skip_found, &r.batch, &r.hits, &r.nh, &r.pool, &r.np);
+            if (scan_rc) { scan_err = crass_b200_last_error(); break; }
+            scanned.push(r);
+        }
+        scanned.close();
+    });
+    int rc = 0;
+    uint64_t first_read = 0;
+    SearchedRange r;
+    while (scanned.pop(r)) {
+        if (!rc) rc = fn(user, r.batch, r.hits, r.nh, r.pool, r.np, first_read);
+        first_read += crass_b200_batch_num_reads(r.batch);
+        free(r.hits); free(r.pool);
+    }
+    scanner.join();
+    if (scan_rc) return cbh::fail(scan_rc, scan_err);
+    return rc;
 }
 
 // The exchange step for the files searched so far: every device de-duplicates the DR tokens of its most recent search (K4b)

@@ -413,6 +413,19 @@ int crass_b200_engine_find_singletons(crass_b200_engine* e, const char* path, co
                                       const crass_b200_batch** batch, crass_b200_hit** hits, uint32_t* n_hits,
                                       uint32_t** ss_pool, uint32_t* n_ss_pool);
 void crass_b200_engine_release_file(crass_b200_engine* e, const char* path);
+/* The same two calls STREAMED, for a caller that fills its own containers (the drop-in libcrispr, whose ReadMap holds the
+ * reference's ReadHolder objects): the file goes through the devices in ranges of about CRASS_B200_STREAM_MB (each ending
+ * on a record start), and `fn` receives the hits of each range in file order -- batch / hits / ss_pool are valid during the
+ * call only, first_read is the file index of the range's read 0, a non-zero return ends the run with that code.  For
+ * search_file_ranges fn runs on one helper thread of the engine while this call parses and searches later ranges (the caller
+ * is blocked in the call, so its containers see one thread); for find_singletons_ranges it runs on the calling thread while a
+ * helper runs K2 on the next range.  Replaces the kseq loop of libcrispr.cpp:96-131 and the second one of :487-513. */
+typedef int (*crass_b200_range_fn)(void* user, const crass_b200_batch* batch, const crass_b200_hit* hits, uint32_t n_hits,
+                                   const uint32_t* ss_pool, uint32_t n_ss_pool, uint64_t first_read);
+int crass_b200_engine_search_file_ranges(crass_b200_engine* e, const char* path, const crass_b200_params* params,
+                                         crass_b200_range_fn fn, void* user, int* max_read_len);
+int crass_b200_engine_find_singletons_ranges(crass_b200_engine* e, const char* path, const crass_b200_ac* ac, int skip_found,
+                                             crass_b200_range_fn fn, void* user);
 /* WorkHorse::parseSeqFiles: searchFile* -> createNonRedundantSet -> findSingletons* on the engine's devices */
 int crass_b200_engine_run_files(crass_b200_engine* e, const char* const* paths, uint32_t n_paths, const crass_b200_params* params,
                                 int phases, crass_b200_results** out, int* max_read_len);

@@ -116,11 +116,13 @@ def _run_child(which, paths, env=None):
     return md5, ticks
 
 
-@pytest.mark.parametrize("devices", ["0", "0,0", "0,0,0,0"])
-def test_shim_on_several_devices_and_its_progress_lines(D, devices, tmp_path):
+@pytest.mark.parametrize("devices,stream_bytes", [("0", None), ("0,0", None), ("0,0,0,0", None), ("0", 3 << 20), ("0,0", 1 << 20)])
+def test_shim_on_several_devices_and_its_progress_lines(D, devices, stream_bytes, tmp_path):
     """CRASS_B200_DEVICES shards the reads of searchFile / findSingletons over the named GPUs (here the same one several
     times); the reference's containers come out the same, and so do the progress lines the reference prints before every
-    100 000th read of a file and at the end of each file (libcrispr.cpp:99-109,161-162,495-496,515-516)."""
+    100 000th read of a file and at the end of each file (libcrispr.cpp:99-109,161-162,495-496,515-516).  With
+    stream_bytes the shim's searchFile takes each file through the devices in ranges of that size (parse, K1 and the replay into
+    the reference's containers overlapped), and findSingletons scans those ranges: same containers, same lines."""
     import random
     import fuzzgen
     if not checkers.have_ref():
@@ -137,6 +139,9 @@ def test_shim_on_several_devices_and_its_progress_lines(D, devices, tmp_path):
                 fh.write(b">f%d_%06d\n%s\n" % (f, i, s))
         paths.append(p)
     want_md5, want_ticks = _run_child("ref", paths)
-    got_md5, got_ticks = _run_child("dropin", paths, {"CRASS_B200_DEVICES": devices})
+    env = {"CRASS_B200_DEVICES": devices}
+    if stream_bytes:
+        env["CRASS_B200_STREAM_BYTES"] = str(stream_bytes)
+    got_md5, got_ticks = _run_child("dropin", paths, env)
     assert got_md5 == want_md5
     assert got_ticks == want_ticks and len(want_ticks) >= 10
