@@ -560,12 +560,19 @@ int stream_phase1(crass_b200_engine* e, cbh::ParseStream* ps, const char* path, 
         std::lock_guard<std::mutex> g(fail_mu);
         if (!fail_rc.load()) { fail_msg = crass_b200_last_error(); fail_rc.store(rc); }
     };
+    const double t_run = now_ms();
+    auto mark = [&](const char* what, uint32_t i, double t0) {                 // CRASS_B200_TRACE: the timeline of the stages
+        if (e->trace) fprintf(stderr, "[crass_b200]   %-7s range %2u: %8.1f -> %8.1f ms\n", what, i, t0 - t_run, now_ms() - t_run);
+    };
     std::thread searcher([&]() {
         std::unique_ptr<FileState> fs;
+        uint32_t i = 0;
         while (parsed.pop(fs)) {
             if (fail_rc.load()) { retire_batch(e, fs->batch); continue; }
             SearchedRange r;
+            const double t0 = now_ms();
             const int rc = search_parsed(e, std::move(fs), params, &r.batch, &r.hits, &r.nh, &r.pool, &r.np);
+            mark("search", i++, t0);
             if (rc) { note_failure(rc); continue; }
             searched.push(r);
         }
@@ -574,11 +581,13 @@ int stream_phase1(crass_b200_engine* e, cbh::ParseStream* ps, const char* path, 
     std::thread replayer([&]() {
         SearchedRange r;
         uint64_t first_read = 0;
+        uint32_t i = 0;
         while (searched.pop(r)) {
             if (!fail_rc.load()) {
                 const double t0 = now_ms();
                 const int rc = consume(r, first_read);
                 e->t_replay += now_ms() - t0;
+                mark("replay", i++, t0);
                 if (rc) note_failure(rc);
             }
             first_read += crass_b200_batch_num_reads(r.batch);
@@ -590,6 +599,7 @@ int stream_phase1(crass_b200_engine* e, cbh::ParseStream* ps, const char* path, 
         const double t0 = now_ms();
         const int got = cbh::parse_stream_next(ps, &h->b);
         e->t_parse += now_ms() - t0;
+        mark("parse", i, t0);
         if (got <= 0) { retire_batch(e, h); if (got < 0) note_failure(-got); break; }
         *max_len = std::max(*max_len, (int)h->b.max_len);
         std::unique_ptr<FileState> fs(new FileState());
@@ -612,6 +622,7 @@ int run_streamed(crass_b200_engine* e, cbh::ParseStream* ps, const char* path, c
     int rc = stream_phase1(e, ps, path, params, [&](const SearchedRange& r, uint64_t) {
         return crass_b200_results_add_phase1(res, r.batch, r.hits, r.nh, r.pool);
     }, max_len, range_paths);
+    const double t_p1 = now_ms();
     if (!rc && phases >= 2) {
         // the containers' token list (filled in read order above) is the sequential numbering
         crass_b200_ac* ac = nullptr;
@@ -625,22 +636,31 @@ int run_streamed(crass_b200_engine* e, cbh::ParseStream* ps, const char* path, c
             rc = crass_b200_ac_build(bytes.data(), offs.data(), n_pat, &ac);
         }
         e->t_exchange += now_ms() - t0;
+        if (e->trace) fprintf(stderr, "[crass_b200]   clustering + matcher %.1f ms (%u patterns)\n", now_ms() - t0, n_pat);
+        // K2 over every resident range first (a fraction of a millisecond each), then ONE replay of all their matches
+        std::vector<const crass_b200_batch*> bs; std::vector<crass_b200_hit*> hs; std::vector<uint32_t> nhs; std::vector<uint32_t*> pools;
+        const double tf = now_ms();
         for (size_t f = 0; f < range_paths.size() && !rc && ac; ++f) {
             const crass_b200_batch* b = nullptr;
             crass_b200_hit* hits = nullptr; uint32_t nh = 0, np = 0; uint32_t* pool = nullptr;
             rc = crass_b200_engine_find_singletons(e, range_paths[f].c_str(), ac, 1, &b, &hits, &nh, &pool, &np);
-            if (!rc) {
-                const double t1 = now_ms();
-                rc = crass_b200_results_add_phase2(res, b, hits, nh, pool);
-                e->t_replay += now_ms() - t1;
-            }
-            free(hits); free(pool);
+            if (rc) { free(hits); free(pool); break; }
+            bs.push_back(b); hs.push_back(hits); nhs.push_back(nh); pools.push_back(pool);
         }
+        const double t1 = now_ms();
+        if (!rc && !bs.empty()) {
+            rc = crass_b200_results_add_phase2_ranges(res, (uint32_t)bs.size(), bs.data(), hs.data(), nhs.data(), pools.data());
+            e->t_replay += now_ms() - t1;
+        }
+        if (e->trace) fprintf(stderr, "[crass_b200]   phase 2: scan of %zu ranges %.1f ms, replay %.1f ms\n", bs.size(), t1 - tf, now_ms() - t1);
+        for (size_t f = 0; f < hs.size(); ++f) { free(hs[f]); free(pools[f]); }
         crass_b200_ac_destroy(ac);
     } else if (!rc) {
         res->r.lazy_kmer_clust = (int)params->kmer_clust;
     }
+    const double t_p2 = now_ms();
     for (const std::string& p : range_paths) crass_b200_engine_release_file(e, p.c_str());
+    if (e->trace) fprintf(stderr, "[crass_b200]   after phase 1: clustering + phase 2 + replay %.1f ms, release %.1f ms\n", t_p2 - t_p1, now_ms() - t_p2);
     return rc;
 }
 }  // namespace

@@ -219,7 +219,11 @@ int crass_b200_results_add_phase1(crass_b200_results* rh, const crass_b200_batch
     if (int e = check_hits(b, hits, n_hits)) return e;
     try {
         std::vector<Built> built;
+        static const bool trace = getenv("CRASS_B200_TRACE_REPLAY") != nullptr;
+        const auto tb0 = std::chrono::steady_clock::now();
         build_holders(b, hits, nullptr, n_hits, ss_pool, 1, built);
+        if (trace) fprintf(stderr, "[crass_b200]     phase-1 replay: %u holders built in %.2f ms\n", n_hits,
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count());
         for (uint32_t k = 0; k < n_hits; ++k) {                             // searchFile's loop body for a hit (libcrispr.cpp:134-139)
             insert_holder(r, built[k]);
             if (r.patterns_index.insert(built[k].raw0).second) r.patterns_hash[built[k].raw0] = true;
@@ -235,27 +239,55 @@ int crass_b200_results_add_phase1(crass_b200_results* rh, const crass_b200_batch
 
 int crass_b200_results_add_phase2(crass_b200_results* rh, const crass_b200_batch* bh, const crass_b200_hit* hits, uint32_t n_hits,
                                   const uint32_t* ss_pool) {
-    if (!rh || !bh || (n_hits && (!hits || !ss_pool))) return fail(CRASS_B200_EINVAL, "NULL argument");
+    return crass_b200_results_add_phase2_ranges(rh, 1, &bh, &hits, &n_hits, &ss_pool);
+}
+
+// findSingletons' replay for several batches at once (the ranges of a streamed file, the files of a run), in the order given:
+// readsFound is only read in phase 2, so the header test and the holders of ALL the hits are made on the worker threads in one
+// go, and only the container inserts (which number new tokens in order) walk the hits one by one.
+int crass_b200_results_add_phase2_ranges(crass_b200_results* rh, uint32_t n_ranges, const crass_b200_batch* const* bhs,
+                                         const crass_b200_hit* const* hits, const uint32_t* n_hits, const uint32_t* const* ss_pools) {
+    if (!rh || (n_ranges && (!bhs || !hits || !n_hits || !ss_pools))) return fail(CRASS_B200_EINVAL, "NULL argument");
     Results& r = rh->r;
-    const Batch& b = bh->b;
-    if (int e = check_hits(b, hits, n_hits)) return e;
+    for (uint32_t f = 0; f < n_ranges; ++f) {
+        if (!bhs[f] || (n_hits[f] && (!hits[f] || !ss_pools[f]))) return fail(CRASS_B200_EINVAL, "NULL argument");
+        if (int e = check_hits(bhs[f]->b, hits[f], n_hits[f])) return e;
+    }
     try {
+        static const bool trace = getenv("CRASS_B200_TRACE_REPLAY") != nullptr;
+        const auto tb0 = std::chrono::steady_clock::now();
         // on_match (libcrispr.cpp:408-442): readsFound is tested by HEADER and never written here, so the test can be made
         // for all hits up front
-        std::vector<uint32_t> take;
-        take.reserve(n_hits);
         if (r.found_index.size() != r.reads_found.size()) {                  // containers filled by other calls: index them now
             r.found_index.clear();
             for (const auto& kv : r.reads_found) r.found_index.insert(kv.first);
         }
-        std::string name;
-        for (uint32_t k = 0; k < n_hits; ++k) {
-            name.assign(b.name_pool.data() + b.name_off[hits[k].read_index]);
-            if (r.found_index.find(name) == r.found_index.end()) take.push_back(k);
+        std::vector<std::vector<uint32_t> > take(n_ranges);
+        std::vector<std::vector<Built> > built(n_ranges);
+        size_t total = 0;
+        for (uint32_t f = 0; f < n_ranges; ++f) total += n_hits[f];
+        const unsigned workers = total >= 2048 ? std::min<unsigned>(cbh::host_threads(), 16) : 1;
+        for (uint32_t f = 0; f < n_ranges; ++f) {
+            const Batch& b = bhs[f]->b;
+            const uint32_t n = n_hits[f];
+            std::vector<std::vector<uint32_t> > part(workers);
+            cbh::parallel_run(workers, [&](unsigned w) {
+                const uint32_t lo = (uint32_t)((uint64_t)n * w / workers), hi = (uint32_t)((uint64_t)n * (w + 1) / workers);
+                std::string name;
+                for (uint32_t k = lo; k < hi; ++k) {
+                    name.assign(b.name_pool.data() + b.name_off[hits[f][k].read_index]);
+                    if (r.found_index.find(name) == r.found_index.end()) part[w].push_back(k);
+                }
+            });
+            for (unsigned w = 0; w < workers; ++w) take[f].insert(take[f].end(), part[w].begin(), part[w].end());
+            build_holders(b, hits[f], take[f].data(), (uint32_t)take[f].size(), ss_pools[f], 2, built[f]);
         }
-        std::vector<Built> built;
-        build_holders(b, hits, take.data(), (uint32_t)take.size(), ss_pool, 2, built);
-        for (Built& o : built) insert_holder(r, o);
+        const auto tb1 = std::chrono::steady_clock::now();
+        size_t taken = 0;
+        for (uint32_t f = 0; f < n_ranges; ++f) { for (Built& o : built[f]) insert_holder(r, o); taken += built[f].size(); }
+        if (trace) fprintf(stderr, "[crass_b200]     phase-2 replay: %zu of %zu hits new (%u batches), holders built in %.2f ms, inserted in %.2f ms\n", taken, total, n_ranges,
+                           std::chrono::duration<double, std::milli>(tb1 - tb0).count(),
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb1).count());
     } catch (std::exception& ex) {
         return fail(CRASS_B200_ENOMEM, std::string("results_add_phase2: ") + ex.what());
     }

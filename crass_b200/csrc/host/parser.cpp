@@ -23,6 +23,9 @@
 #include <zlib.h>
 
 #include <algorithm>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <atomic>
 #include <chrono>
 #include <memory>
@@ -200,6 +203,48 @@ struct PlainTab {
 };
 const PlainTab kPlain;
 
+// bytes [b, e) plus a terminating NUL appended to a pool with one memcpy (vector::insert with a custom allocator constructs
+// element by element)
+inline void append_str(PodVec<char>& v, const char* b, const char* e, bool nul = true) {
+    const size_t at = v.size(), len = (size_t)(e - b);
+    if (v.capacity() < at + len + 1) v.reserve(std::max<size_t>(v.capacity() * 2, at + len + 1 + 4096));
+    v.resize(at + len + (nul ? 1 : 0));
+    memcpy(v.data() + at, b, len);
+    if (nul) v[at + len] = 0;
+}
+
+// the end of the run of plain bytes that starts at i (first byte that is not plain, or lim), 16 bytes at a time:
+// not plain == below 33 as a SIGNED byte (control, blank, and everything from 0x80 up), 127, or one of '>' '+' '@'
+inline size_t plain_run_end(const uint8_t* p, size_t i, size_t lim) {
+#if defined(__SSE2__)
+    const __m128i k33 = _mm_set1_epi8(33), k127 = _mm_set1_epi8(127), kgt = _mm_set1_epi8('>'), kplus = _mm_set1_epi8('+'), kat = _mm_set1_epi8('@');
+    while (i + 16 <= lim) {
+        const __m128i x = _mm_loadu_si128((const __m128i*)(p + i));
+        const __m128i bad = _mm_or_si128(_mm_or_si128(_mm_cmplt_epi8(x, k33), _mm_cmpeq_epi8(x, k127)),
+                                         _mm_or_si128(_mm_cmpeq_epi8(x, kgt), _mm_or_si128(_mm_cmpeq_epi8(x, kplus), _mm_cmpeq_epi8(x, kat))));
+        const int m = _mm_movemask_epi8(bad);
+        if (m) return i + (size_t)__builtin_ctz((unsigned)m);
+        i += 16;
+    }
+#endif
+    while (i < lim && kPlain.t[p[i]]) ++i;
+    return i;
+}
+
+// the end of the run of quality characters (33..127) that starts at i
+inline size_t qual_run_end(const uint8_t* p, size_t i, size_t lim) {
+#if defined(__SSE2__)
+    const __m128i k33 = _mm_set1_epi8(33);
+    while (i + 16 <= lim) {
+        const int m = _mm_movemask_epi8(_mm_cmplt_epi8(_mm_loadu_si128((const __m128i*)(p + i)), k33));
+        if (m) return i + (size_t)__builtin_ctz((unsigned)m);
+        i += 16;
+    }
+#endif
+    while (i < lim && p[i] >= 33 && p[i] <= 127) ++i;
+    return i;
+}
+
 // ks_getuntil (kseq.cpp:71-147); delimiter 0 == any whitespace.  Returns false when already at EOF
 // (the reference returns -1 and leaves the target string untouched).
 bool get_until(Cursor& c, int delimiter, size_t& b, size_t& e, int& dret) {
@@ -211,11 +256,26 @@ bool get_until(Cursor& c, int delimiter, size_t& b, size_t& e, int& dret) {
         return true;
     }
     size_t i = c.pos;
-    if (delimiter == 0) { while (i < c.n && !c_isspace(c.p[i])) ++i; }
+    if (delimiter == 0) {
+#if defined(__SSE2__)
+        // isspace: ' ' or '\t'..'\r', 16 bytes at a time (a name is rarely longer)
+        const __m128i ksp = _mm_set1_epi8(' '), k8 = _mm_set1_epi8(8), k14 = _mm_set1_epi8(14);
+        while (i + 16 <= c.n) {
+            const __m128i x = _mm_loadu_si128((const __m128i*)(c.p + i));
+            const int m = _mm_movemask_epi8(_mm_or_si128(_mm_cmpeq_epi8(x, ksp), _mm_and_si128(_mm_cmpgt_epi8(x, k8), _mm_cmplt_epi8(x, k14))));
+            if (m) { i += (size_t)__builtin_ctz((unsigned)m); goto found_space; }
+            i += 16;
+        }
+#endif
+        while (i < c.n && !c_isspace(c.p[i])) ++i;
+    }
     else {
         const void* q = memchr(c.p + i, delimiter, c.n - i);
         i = q ? (size_t)((const uint8_t*)q - c.p) : c.n;
     }
+#if defined(__SSE2__)
+found_space:
+#endif
     b = c.pos; e = i;
     if (i < c.n) { dret = (int)(signed char)c.p[i]; c.pos = i + 1; } else { c.pos = c.n; c.is_eof = true; }
     return true;
@@ -242,6 +302,15 @@ struct Piece {
         PodVec<uint64_t>().swap(ends); PodVec<char>().swap(name_pool); PodVec<char>().swap(text_pool);
         PodVec<uint64_t>().swap(name_off); PodVec<int64_t>().swap(comment_off); PodVec<int64_t>().swap(qual_off);
     }
+    // room for the records of `span` input bytes without growing (address space only: pages are touched as they are written);
+    // shorter records than assumed here grow the vectors as usual
+    void expect(size_t span) {
+        const size_t recs = span / 48 + 16;
+        ends.reserve(recs); name_off.reserve(recs); comment_off.reserve(recs); qual_off.reserve(recs);
+        name_pool.reserve(span / 6 + 64);
+        text_span = span;
+    }
+    size_t text_span = 0;
     void room(size_t need) {
         if (need <= cap) return;
         if (!own) throw std::length_error("base buffer");
@@ -275,8 +344,7 @@ void parse_span(const uint8_t* data, size_t n, size_t start, size_t stop, Piece&
             size_t cb, ce; int d2;
             if (get_until(c, '\n', cb, ce, d2)) {
                 cur_comment = (int64_t)P.text_pool.size();
-                P.text_pool.insert(P.text_pool.end(), (const char*)data + cb, (const char*)data + ce);
-                P.text_pool.push_back(0);
+                append_str(P.text_pool, (const char*)data + cb, (const char*)data + ce);
             }
         }
         const uint64_t seq_b = nb;
@@ -284,8 +352,7 @@ void parse_span(const uint8_t* data, size_t n, size_t start, size_t stop, Piece&
         // taken in runs: bytes that are isgraph and none of the three terminators are copied in bulk, every other
         // byte is looked at on its own (0xFF reads as -1 and ends the loop like the others)
         for (;;) {
-            size_t i = c.pos;
-            while (i < c.n && kPlain.t[c.p[i]]) ++i;
+            const size_t i = plain_run_end(c.p, c.pos, c.n);
             if (i > c.pos) {
                 P.room(nb + (i - c.pos));
                 memcpy(P.bases + nb, c.p + c.pos, i - c.pos); nb += i - c.pos; c.pos = i;
@@ -301,17 +368,16 @@ void parse_span(const uint8_t* data, size_t n, size_t start, size_t stop, Piece&
             while ((ch = c.getc()) != -1 && ch != '\n') {}
             if (ch == -1) { bad = -2; emit = false; }
             else {
+                if (P.text_span && P.text_pool.capacity() < P.text_span / 2) P.text_pool.reserve(P.text_span / 2 + P.text_span / 8 + 64);
                 const int64_t q0 = (int64_t)P.text_pool.size();
                 uint64_t ql = 0;
                 // kseq: while ((c = getc()) != -1 && qual.l < seq.l) if (c >= 33 && c <= 127) append(c);  -- the byte
                 // is fetched before the length test, so one byte past the last quality character is consumed
                 while ((ch = c.getc()) != -1 && ql < L) {
                     if (ch < 33) continue;                             // (signed) also skips bytes >= 0x80
-                    size_t i = c.pos;                                  // the rest of this run of quality characters
                     const size_t lim = c.pos + (size_t)(L - ql - 1) < c.n ? c.pos + (size_t)(L - ql - 1) : c.n;
-                    while (i < lim && c.p[i] >= 33 && c.p[i] <= 127) ++i;
-                    P.text_pool.push_back((char)ch);
-                    P.text_pool.insert(P.text_pool.end(), (const char*)c.p + c.pos, (const char*)c.p + i);
+                    const size_t i = qual_run_end(c.p, c.pos, lim);     // the rest of this run of quality characters
+                    append_str(P.text_pool, (const char*)c.p + c.pos - 1, (const char*)c.p + i, false);   // (ch is the byte before pos)
                     ql += 1 + (i - c.pos);
                     c.pos = i;
                 }
@@ -323,8 +389,7 @@ void parse_span(const uint8_t* data, size_t n, size_t start, size_t stop, Piece&
         }
         if (!emit) { nb = seq_b; P.status = bad; break; }
         P.name_off.push_back(P.name_pool.size());
-        P.name_pool.insert(P.name_pool.end(), (const char*)data + name_b, (const char*)data + name_e);
-        P.name_pool.push_back(0);
+        append_str(P.name_pool, (const char*)data + name_b, (const char*)data + name_e);
         P.comment_off.push_back(cur_comment);
         P.qual_off.push_back(cur_qual);
         P.ends.push_back(nb);
@@ -459,6 +524,7 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
                 P.own = false;
                 P.cap = ((stop == (size_t)-1 ? n : stop) - from) + 64;
                 P.bases = scratch + (from - first) + 64 * k;
+                P.expect(P.cap);
                 parse_span(in.data, n, k ? from : start, stop, P);
             } catch (...) { failed.store(true); }
         }

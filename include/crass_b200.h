@@ -283,6 +283,10 @@ int crass_b200_results_add_phase1(crass_b200_results* r, const crass_b200_batch*
 /* replays phase-2 hits in read order: on_match (header not in readsFound -> addReadHolder) */
 int crass_b200_results_add_phase2(crass_b200_results* r, const crass_b200_batch* b,
                                   const crass_b200_hit* hits, uint32_t n_hits, const uint32_t* ss_pool);
+/* the same for several batches at once, in the order given (the ranges of a streamed file): the header test and the holders of
+ * all hits are made on the worker threads, only the container inserts walk the hits in order */
+int crass_b200_results_add_phase2_ranges(crass_b200_results* r, uint32_t n_batches, const crass_b200_batch* const* batches,
+                                         const crass_b200_hit* const* hits, const uint32_t* n_hits, const uint32_t* const* ss_pools);
 uint32_t crass_b200_results_num_tokens(const crass_b200_results* r);
 uint32_t crass_b200_results_num_reads(const crass_b200_results* r);
 /* the distinct low-lexi DR strings in token order (token = index + 2), '\n'-separated; malloc'd */
