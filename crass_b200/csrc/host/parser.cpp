@@ -296,6 +296,10 @@ struct Piece {
     int status = 0;                              // 0: stopped at a header >= stop (next_hp); -1/-2: the stream ended here
     size_t next_hp = 0;
     ~Piece() { if (own) free(bases); }
+    void rewind() {                              // empty, with the memory kept (a piece of a ParseArena, range after range)
+        nb = 0; ends.clear(); name_pool.clear(); text_pool.clear(); name_off.clear(); comment_off.clear(); qual_off.clear();
+        last_comment = last_qual = -1; max_len = 0; status = 0; next_hp = 0;
+    }
     void release() {                             // give everything back now (called by the thread that has just spliced the piece)
         if (own) free(bases);
         bases = nullptr; cap = 0;
@@ -459,7 +463,27 @@ struct RangeCarry {
 
 struct View { const uint8_t* data; size_t size; };     // the input's bytes as far as a range may look
 
-void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarry* cin, Batch* B, RangeCarry* cout) {
+// What a streamed input keeps from one range to the next: the scratch mapping the pieces write their bases to and the pieces'
+// own vectors.  Fresh memory for them (a few hundred MB per range) costs a page fault per 4 KB on the way in and a munmap on the
+// way out, which for FASTQ (half the bytes are quality strings that go through a pool) was half the parsing time.
+struct ParseArena {
+    uint8_t* scratch = nullptr; size_t scratch_len = 0;
+    std::vector<std::unique_ptr<Piece> > pieces;
+    ~ParseArena() { if (scratch) Input::unmap_later(scratch, scratch_len); }
+    uint8_t* room(size_t need) {
+        if (need <= scratch_len) return scratch;
+        if (scratch) Input::unmap_later(scratch, scratch_len);
+        scratch = nullptr; scratch_len = 0;
+        const size_t len = need + need / 8;
+        void* sm = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (sm == MAP_FAILED) throw std::bad_alloc();
+        madvise(sm, len, MADV_HUGEPAGE);
+        scratch = (uint8_t*)sm; scratch_len = len;
+        return scratch;
+    }
+};
+
+void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarry* cin, Batch* B, RangeCarry* cout, ParseArena* arena = nullptr) {
     B->reset();
     B->offsets.push_back(0);
     const size_t n = in.size;
@@ -499,18 +523,14 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
     // one anonymous mapping for the bases of all pieces (huge pages when the kernel grants them: a 16 MB malloc per piece
-    // was 400 k page faults on the way in and as many pages to give back), unmapped on a detached thread at the end
-    struct Scratch {
-        uint8_t* p = nullptr; size_t len = 0;
-        ~Scratch() { if (p) Input::unmap_later(p, len); }
-    } scratch_map;
-    scratch_map.len = (limit - first) + 64 * np + 4096;
-    void* sm = mmap(nullptr, scratch_map.len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
-    if (sm == MAP_FAILED) throw std::bad_alloc();
-    scratch_map.p = (uint8_t*)sm;
-    madvise(sm, scratch_map.len, MADV_HUGEPAGE);
-    uint8_t* const scratch = scratch_map.p;
-    std::vector<Piece> pieces(np);
+    // was 400 k page faults on the way in and as many pages to give back), unmapped on a detached thread at the end -- or, for
+    // a streamed input, the arena's, kept from range to range
+    ParseArena local_arena;
+    ParseArena& A = arena ? *arena : local_arena;
+    uint8_t* const scratch = A.room((limit - first) + 64 * np + 4096);
+    while (A.pieces.size() < np) A.pieces.emplace_back(new Piece());
+    for (size_t k = 0; k < np; ++k) A.pieces[k]->rewind();
+    std::vector<std::unique_ptr<Piece> >& pieces = A.pieces;
     std::atomic<size_t> next{0};
     std::atomic<bool> failed{false};
     auto work = [&]() {
@@ -518,7 +538,7 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
             const size_t k = next.fetch_add(1);
             if (k >= np || failed.load()) return;
             try {
-                Piece& P = pieces[k];
+                Piece& P = *pieces[k];
                 const size_t from = k ? starts[k - 1] : first, stop = k + 1 < np ? starts[k] : range_stop;
                 // a piece's bases are a subset of its bytes: its slice of the scratch mapping, at its own file offset
                 P.own = false;
@@ -543,7 +563,7 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
     std::vector<const Piece*> order;
     std::vector<std::unique_ptr<Piece>> patches;
     size_t k = 0;
-    const Piece* cur = &pieces[0];
+    const Piece* cur = pieces[0].get();
     int status = 0;
     size_t end_hp = (size_t)-1;
     for (;;) {
@@ -552,7 +572,7 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
         const size_t hp = cur->next_hp;
         if (hp >= range_stop) { end_hp = hp; break; }                 // the range is complete: the next one starts at hp
         while (k < starts.size() && starts[k] < hp) ++k;          // pieces that began inside a record
-        if (k < starts.size() && starts[k] == hp) { cur = &pieces[++k]; continue; }
+        if (k < starts.size() && starts[k] == hp) { cur = pieces[++k].get(); continue; }
         std::unique_ptr<Piece> Q(new Piece());                    // no piece begins here: parse up to the next one
         const size_t stop = k < starts.size() ? starts[k] : range_stop;
         Q->own = true;
@@ -607,7 +627,7 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
                 B->qual_off[S.rec0 + r] = P.qual_off[r] < 0 ? S.in_qual : S.text0 + P.qual_off[r];
                 B->offsets[S.rec0 + r + 1] = S.base0 + P.ends[r];
             }
-            const_cast<Piece&>(P).release();                  // the per-piece vectors, on this thread
+            if (!arena || P.own) const_cast<Piece&>(P).release();   // the per-piece vectors, on this thread (an arena keeps its pieces' memory)
         }
     };
     {
@@ -651,6 +671,7 @@ struct ParseStream {
     Input in;
     size_t range_bytes = 0;
     RangeCarry carry;
+    ParseArena arena;                             // scratch and piece memory, kept from range to range
     bool started = false, ended = false;
 };
 
@@ -680,7 +701,7 @@ int parse_stream_next(ParseStream* s, Batch* reuse) {
             const size_t have = s->in.wait_for(first + s->range_bytes + margin, &final_size);
             if (s->in.inflate_failed.load()) throw std::runtime_error("gz stream could not be inflated");
             const bool to_end = !s->range_bytes || (final_size && first + s->range_bytes + (s->range_bytes >> 2) >= have);
-            parse_range(View{s->in.data, have}, start, to_end ? (size_t)-1 : first + s->range_bytes, s->started ? &s->carry : nullptr, reuse, &out);
+            parse_range(View{s->in.data, have}, start, to_end ? (size_t)-1 : first + s->range_bytes, s->started ? &s->carry : nullptr, reuse, &out, &s->arena);
             if (final_size || (out.status == 0 && out.next_hp != (size_t)-1)) break;
             margin *= 4;                                              // the view ended inside a record: wait for more of it
         }

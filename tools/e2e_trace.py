@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--reads", type=int, default=4_000_000)
     ap.add_argument("--repeat", type=int, default=3)
     ap.add_argument("--devices", default="0")
+    ap.add_argument("--fastq", action="store_true", help="write the reads as FASTQ (one fixed quality string)")
     args = ap.parse_args()
     os.environ.setdefault("CRASS_B200_TRACE", "1")
     import crass_b200 as cb
@@ -26,8 +27,14 @@ def main():
     bases, offs = synth.sample_fixed(genome, n, 150, 21242)
     with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
         path = os.path.join(d, "reads.fa")
-        hdr = np.frombuffer(b"".join(b">r%010d\n" % i for i in range(n)), dtype=np.uint8).reshape(n, 13)
-        np.concatenate([hdr, bases.reshape(n, 150), np.full((n, 1), 10, dtype=np.uint8)], axis=1).tofile(path)
+        hdr = np.frombuffer(b"".join(b">r%010d\n" % i for i in range(n)), dtype=np.uint8).reshape(n, 13).copy()
+        nl = np.full((n, 1), 10, dtype=np.uint8)
+        cols = [hdr, bases.reshape(n, 150), nl]
+        if args.fastq:
+            hdr[:, 0] = ord("@")
+            qual = np.frombuffer(bytes(33 + (7 * k) % 41 for k in range(150)), dtype=np.uint8)
+            cols += [np.full((n, 1), ord("+"), dtype=np.uint8), nl, np.broadcast_to(qual, (n, 150)), nl]
+        np.concatenate(cols, axis=1).tofile(path)
         eng = cb.Engine(tuple(int(x) for x in args.devices.split(",")))
         for it in range(args.repeat):
             t0 = time.time()
