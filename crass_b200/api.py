@@ -114,6 +114,7 @@ def lib():
         "crass_b200_batch_max_read_len": (C.c_uint32, [vp]),
         "crass_b200_batch_parse_status": (C.c_int, [vp]),
         "crass_b200_batch_bases": (vp, [vp]),
+        "crass_b200_batch_read": (vp, [vp, C.c_uint32, C.POINTER(C.c_uint32)]),
         "crass_b200_batch_offsets": (vp, [vp]),
         "crass_b200_batch_name": (cp, [vp, C.c_uint32]),
         "crass_b200_batch_comment": (cp, [vp, C.c_uint32, C.POINTER(C.c_int)]),
@@ -271,6 +272,12 @@ class Batch:
         if n == 0:
             return np.zeros(0, dtype=np.uint8)
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n,))
+
+    def read(self, i):
+        """bases of record i (no copy of the whole batch: a range of a streamed file keeps its reads in segments)"""
+        ln = C.c_uint32(0)
+        p = lib().crass_b200_batch_read(self.h, i, C.byref(ln))
+        return C.string_at(p, ln.value) if p else b""
 
     def name(self, i):
         return lib().crass_b200_batch_name(self.h, i)

@@ -89,9 +89,9 @@ struct HitGuard {
 
 // the holder searchFile / on_match build from a kseq record (libcrispr.cpp:112-131, 425-435)
 void fill_holder(ReadHolder& h, const crass_b200_batch* b, uint32_t i) {
-    const uint8_t* bases = crass_b200_batch_bases(b);
-    const uint64_t* offs = crass_b200_batch_offsets(b);
-    h.setSequence(std::string((const char*)bases + offs[i], (size_t)(offs[i + 1] - offs[i])));
+    uint32_t len = 0;
+    const uint8_t* seq = crass_b200_batch_read(b, i, &len);
+    h.setSequence(std::string((const char*)seq, (size_t)len));
     h.setHeader(crass_b200_batch_name(b, i));
     int has = 0;
     const char* c = crass_b200_batch_comment(b, i, &has);

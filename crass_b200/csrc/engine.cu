@@ -234,9 +234,16 @@ int upload_shard(Lane& l, const cbh::Batch& b, Shard& s) {
     ENG_CUDA(cudaMemcpyAsync(s.d_offsets.p, ho, ((size_t)s.n() + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, l.copy[0]));
     const uint64_t slice = (uint64_t)64 << 20;
     int which = 0;
-    for (uint64_t at = 0; at < nbytes; at += slice, which ^= 1) {
-        const uint64_t len = std::min(slice, nbytes - at);
-        ENG_CUDA(cudaMemcpyAsync(s.d_bases.as<uint8_t>() + at, b.bases + s.b0 + at, len, cudaMemcpyHostToDevice, l.copy[which]));
+    // back to back on the device; on the host a streamed range lies in segments (cbh::Batch::segs), each copied to its place
+    const size_t n_seg = b.segs.empty() ? 1 : b.segs.size();
+    for (size_t k = 0; k < n_seg; ++k) {
+        const uint64_t dev0 = b.segs.empty() ? 0 : b.segs[k].dev0, host0 = b.segs.empty() ? 0 : b.segs[k].host0;
+        const uint64_t dev1 = k + 1 < n_seg ? b.segs[k + 1].dev0 : b.offsets.back();
+        const uint64_t lo = std::max<uint64_t>(dev0, s.b0), hi = std::min<uint64_t>(dev1, s.b1);
+        for (uint64_t at = lo; at < hi; at += slice, which ^= 1) {
+            const uint64_t len = std::min(slice, hi - at);
+            ENG_CUDA(cudaMemcpyAsync(s.d_bases.as<uint8_t>() + (at - s.b0), b.bases + host0 + (at - dev0), len, cudaMemcpyHostToDevice, l.copy[which]));
+        }
     }
     for (int k = 0; k < 2; ++k) {
         ENG_CUDA(cudaEventRecord(l.ev_copy[k], l.copy[k]));

@@ -42,7 +42,7 @@ std::vector<std::string> split_lines(const char* text) {
 
 // the (header, comment, qual) triple searchFile copies into the ReadHolder (libcrispr.cpp:112-131)
 void fill_holder(HeldRead& h, const Batch& b, uint32_t i) {
-    h.seq.assign((const char*)b.bases + b.offsets[i], (size_t)(b.offsets[i + 1] - b.offsets[i]));
+    h.seq.assign((const char*)b.read_ptr(i), (size_t)(b.offsets[i + 1] - b.offsets[i]));
     h.header = b.name_pool.data() + b.name_off[i];
     if (b.comment_off[i] >= 0) h.comment = b.text_pool.data() + b.comment_off[i];
     if (b.qual_off[i] >= 0) { h.qual = b.text_pool.data() + b.qual_off[i]; h.is_fasta = false; }
@@ -134,7 +134,16 @@ void crass_b200_batch_destroy(crass_b200_batch* b) { delete b; }
 uint32_t crass_b200_batch_num_reads(const crass_b200_batch* b) { return b ? b->b.n() : 0; }
 uint32_t crass_b200_batch_max_read_len(const crass_b200_batch* b) { return b ? b->b.max_len : 0; }
 int crass_b200_batch_parse_status(const crass_b200_batch* b) { return b ? b->b.parse_status : -1; }
-const uint8_t* crass_b200_batch_bases(const crass_b200_batch* b) { return b ? b->b.bases : nullptr; }
+const uint8_t* crass_b200_batch_bases(const crass_b200_batch* b) {
+    if (!b) return nullptr;
+    try { return const_cast<Batch&>(b->b).contiguous(); }           // (a streamed range is copied back to back on first use)
+    catch (std::exception&) { fail(CRASS_B200_ENOMEM, "batch_bases"); return nullptr; }
+}
+const uint8_t* crass_b200_batch_read(const crass_b200_batch* b, uint32_t i, uint32_t* len) {
+    if (!b || i >= b->b.n()) { if (len) *len = 0; return nullptr; }
+    if (len) *len = (uint32_t)(b->b.offsets[i + 1] - b->b.offsets[i]);
+    return b->b.read_ptr(i);
+}
 const uint64_t* crass_b200_batch_offsets(const crass_b200_batch* b) { return b ? b->b.offsets.data() : nullptr; }
 const char* crass_b200_batch_name(const crass_b200_batch* b, uint32_t i) {
     return (b && i < b->b.n()) ? b->b.name_pool.data() + b->b.name_off[i] : nullptr;

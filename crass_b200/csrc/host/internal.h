@@ -51,7 +51,21 @@ struct Batch {
     PodVec<int64_t> qual_off;           // -1: seq->qual.s == NULL    ; (may be a STALE string of an earlier record)
     uint32_t max_len = 0;
     int parse_status = -1;              // value of the kseq_read() call that ended the loop
+    // A range of a streamed input keeps the bases where the parser's pieces wrote them (each piece at its own file offset
+    // inside `bases`, so nothing is copied together on the host): `offsets` are then the positions in the back-to-back layout
+    // the DEVICE gets (one copy per segment), and the records [rec0, next rec0) of a segment lie on the host from host0 on.
+    // Empty = the host layout is back to back too.
+    struct Segment { uint64_t rec0, dev0, host0; };
+    std::vector<Segment> segs;
+    uint8_t* compact = nullptr;         // back-to-back host copy of a segmented batch, made when somebody asks for one
     uint32_t n() const { return (uint32_t)(offsets.size() - 1); }
+    const uint8_t* read_ptr(size_t i) const {
+        if (segs.empty()) return bases + offsets[i];
+        size_t lo = 0, hi = segs.size();                              // last segment with rec0 <= i
+        while (hi - lo > 1) { const size_t mid = (lo + hi) / 2; if (segs[mid].rec0 <= i) lo = mid; else hi = mid; }
+        return bases + segs[lo].host0 + (offsets[i] - segs[lo].dev0);
+    }
+    const uint8_t* contiguous();        // `bases` when back to back, else `compact` (built on first use; not thread safe)
     ~Batch();
     void reserve_bases(size_t need);
     // empty again, keeping every buffer (the page-locked base buffer above all: allocating one costs more than parsing
@@ -59,6 +73,8 @@ struct Batch {
     void reset() {
         offsets.clear(); name_pool.clear(); name_off.clear(); text_pool.clear(); comment_off.clear(); qual_off.clear();
         max_len = 0; parse_status = -1;
+        segs.clear();
+        if (compact) { free(compact); compact = nullptr; }
     }
 };
 

@@ -36,7 +36,21 @@
 
 namespace cbh {
 
-Batch::~Batch() { if (bases) free_host(bases, pinned); }
+Batch::~Batch() { if (bases) free_host(bases, pinned); if (compact) free(compact); }
+
+const uint8_t* Batch::contiguous() {
+    if (segs.empty()) return bases;
+    if (!compact) {
+        const size_t total = offsets.empty() ? 0 : (size_t)offsets.back();
+        compact = (uint8_t*)malloc(total + 16);
+        if (!compact) throw std::bad_alloc();
+        for (size_t k = 0; k < segs.size(); ++k) {
+            const uint64_t end = k + 1 < segs.size() ? segs[k + 1].dev0 : (uint64_t)total;
+            memcpy(compact + segs[k].dev0, bases + segs[k].host0, (size_t)(end - segs[k].dev0));
+        }
+    }
+    return compact;
+}
 
 void Batch::reserve_bases(size_t need) {
     if (need <= bases_cap) return;
@@ -46,7 +60,7 @@ void Batch::reserve_bases(size_t need) {
     uint8_t* nb = (uint8_t*)alloc_host(ncap, &pin);
     if (!nb) throw std::bad_alloc();
     if (bases) {
-        if (!offsets.empty()) memcpy(nb, bases, (size_t)offsets.back());
+        if (!offsets.empty() && segs.empty()) memcpy(nb, bases, (size_t)offsets.back());
         free_host(bases, pinned);
     }
     bases = nb; bases_cap = ncap; pinned = pin;
@@ -295,8 +309,11 @@ struct Piece {
     uint32_t max_len = 0;
     int status = 0;                              // 0: stopped at a header >= stop (next_hp); -1/-2: the stream ended here
     size_t next_hp = 0;
+    size_t from = 0;                             // file position the piece starts at (where its bases lie in a shared buffer)
     ~Piece() { if (own) free(bases); }
     void rewind() {                              // empty, with the memory kept (a piece of a ParseArena, range after range)
+        if (own) free(bases);
+        own = false; bases = nullptr; cap = 0;
         nb = 0; ends.clear(); name_pool.clear(); text_pool.clear(); name_off.clear(); comment_off.clear(); qual_off.clear();
         last_comment = last_qual = -1; max_len = 0; status = 0; next_hp = 0;
     }
@@ -315,10 +332,19 @@ struct Piece {
         text_span = span;
     }
     size_t text_span = 0;
-    void room(size_t need) {
+    // room for `need` bases, `have` of which are written.  A piece that writes into its slice of a shared buffer fills it only
+    // when its last record runs past the piece's end (the next piece's start was guessed inside a record): it goes on in a
+    // buffer of its own, which the splice copies to where the piece belongs.
+    void room(size_t need, size_t have) {
         if (need <= cap) return;
-        if (!own) throw std::length_error("base buffer");
         size_t ncap = cap * 2 > need ? cap * 2 : need;
+        if (!own) {
+            uint8_t* nbuf = (uint8_t*)malloc(ncap);
+            if (!nbuf) throw std::bad_alloc();
+            if (have) memcpy(nbuf, bases, have);
+            bases = nbuf; cap = ncap; own = true;
+            return;
+        }
         uint8_t* nbuf = (uint8_t*)realloc(bases, ncap);
         if (!nbuf) throw std::bad_alloc();
         bases = nbuf; cap = ncap;
@@ -358,7 +384,7 @@ void parse_span(const uint8_t* data, size_t n, size_t start, size_t stop, Piece&
         for (;;) {
             const size_t i = plain_run_end(c.p, c.pos, c.n);
             if (i > c.pos) {
-                P.room(nb + (i - c.pos));
+                P.room(nb + (i - c.pos), nb);
                 memcpy(P.bases + nb, c.p + c.pos, i - c.pos); nb += i - c.pos; c.pos = i;
             }
             ch = c.getc();
@@ -525,9 +551,16 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
     // one anonymous mapping for the bases of all pieces (huge pages when the kernel grants them: a 16 MB malloc per piece
     // was 400 k page faults on the way in and as many pages to give back), unmapped on a detached thread at the end -- or, for
     // a streamed input, the arena's, kept from range to range
+    //
+    // A streamed range (arena given) goes one step further: its pieces write straight into the batch's own (page-locked) base
+    // buffer, each at its file offset -- a piece's bases are fewer than its bytes, so the slices cannot collide -- and STAY
+    // there: the batch records the segments, the device copy puts them back to back (Batch::segs).  No splice of the bases.
     ParseArena local_arena;
     ParseArena& A = arena ? *arena : local_arena;
-    uint8_t* const scratch = A.room((limit - first) + 64 * np + 4096);
+    const bool in_place = arena != nullptr;
+    uint8_t* scratch;
+    if (in_place) { B->reserve_bases((limit - first) + 64); scratch = B->bases; }
+    else scratch = A.room((limit - first) + 64 * np + 4096);
     while (A.pieces.size() < np) A.pieces.emplace_back(new Piece());
     for (size_t k = 0; k < np; ++k) A.pieces[k]->rewind();
     std::vector<std::unique_ptr<Piece> >& pieces = A.pieces;
@@ -542,8 +575,9 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
                 const size_t from = k ? starts[k - 1] : first, stop = k + 1 < np ? starts[k] : range_stop;
                 // a piece's bases are a subset of its bytes: its slice of the scratch mapping, at its own file offset
                 P.own = false;
-                P.cap = ((stop == (size_t)-1 ? n : stop) - from) + 64;
-                P.bases = scratch + (from - first) + 64 * k;
+                P.from = from;
+                P.cap = ((stop == (size_t)-1 ? n : stop) - from) + (in_place ? 0 : 64);
+                P.bases = scratch + (from - first) + (in_place ? 0 : 64 * k);
                 P.expect(P.cap);
                 parse_span(in.data, n, k ? from : start, stop, P);
             } catch (...) { failed.store(true); }
@@ -575,10 +609,17 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
         if (k < starts.size() && starts[k] == hp) { cur = pieces[++k].get(); continue; }
         std::unique_ptr<Piece> Q(new Piece());                    // no piece begins here: parse up to the next one
         const size_t stop = k < starts.size() ? starts[k] : range_stop;
-        Q->own = true;
-        Q->cap = ((stop == (size_t)-1 ? n : stop) - hp) + 64;
-        Q->bases = (uint8_t*)malloc(Q->cap);
-        if (!Q->bases) throw std::bad_alloc();
+        Q->from = hp;
+        if (in_place) {                                           // the slices of the pieces that began inside a record are free
+            Q->own = false;
+            Q->cap = (stop == (size_t)-1 ? n : stop) - hp;
+            Q->bases = scratch + (hp - first);
+        } else {
+            Q->own = true;
+            Q->cap = ((stop == (size_t)-1 ? n : stop) - hp) + 64;
+            Q->bases = (uint8_t*)malloc(Q->cap);
+            if (!Q->bases) throw std::bad_alloc();
+        }
         parse_span(in.data, n, hp, stop, *Q);
         cur = Q.get();
         patches.push_back(std::move(Q));
@@ -601,7 +642,27 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
         if (P.max_len > B->max_len) B->max_len = P.max_len;
     }
     const double t2 = now();
-    B->reserve_bases(total + 16);
+    // in place: a piece that went on in a buffer of its own (room()) is copied to where it belongs, which is free by now (what it
+    // overran were slices of pieces that began inside its last record); should the last record of the range run past the
+    // buffer, everything moves into a larger one, back to back
+    if (in_place) {
+        size_t need_end = 0;
+        for (const Piece* P : order) need_end = std::max(need_end, (P->from - first) + (size_t)P->nb);
+        if (need_end + 16 > B->bases_cap) {
+            bool pin = false;
+            uint8_t* nbuf = (uint8_t*)alloc_host(total + 64, &pin);
+            if (!nbuf) throw std::bad_alloc();
+            for (size_t i = 0; i < order.size(); ++i) if (order[i]->nb) memcpy(nbuf + slot[i].base0, order[i]->bases, (size_t)order[i]->nb);
+            free_host(B->bases, B->pinned);
+            B->bases = nbuf; B->bases_cap = total + 64; B->pinned = pin;
+        } else {
+            for (size_t i = 0; i < order.size(); ++i) {
+                const Piece& P = *order[i];
+                if (P.own && P.nb) memcpy(B->bases + (P.from - first), P.bases, (size_t)P.nb);
+                if (!P.ends.empty()) B->segs.push_back(Batch::Segment{slot[i].rec0, slot[i].base0, (uint64_t)(P.from - first)});
+            }
+        }
+    } else B->reserve_bases(total + 16);
     B->offsets.resize(n_rec + 1); B->offsets[0] = 0; B->name_off.resize(n_rec); B->comment_off.resize(n_rec); B->qual_off.resize(n_rec);
     B->name_pool.resize(n_name); B->text_pool.resize((size_t)n_text);
     if (carried_text) {
@@ -617,7 +678,7 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
             if (i >= order.size()) return;
             const Piece& P = *order[i];
             const Slot& S = slot[i];
-            if (P.nb) memcpy(B->bases + S.base0, P.bases, (size_t)P.nb);
+            if (P.nb && !in_place) memcpy(B->bases + S.base0, P.bases, (size_t)P.nb);
             if (!P.name_pool.empty()) memcpy(B->name_pool.data() + S.name0, P.name_pool.data(), P.name_pool.size());
             if (!P.text_pool.empty()) memcpy(B->text_pool.data() + S.text0, P.text_pool.data(), P.text_pool.size());
             const size_t m = P.ends.size();

@@ -266,7 +266,10 @@ void crass_b200_batch_destroy(crass_b200_batch* b);
 uint32_t crass_b200_batch_num_reads(const crass_b200_batch* b);
 uint32_t crass_b200_batch_max_read_len(const crass_b200_batch* b);
 int crass_b200_batch_parse_status(const crass_b200_batch* b);             /* last kseq_read return: -1 EOF, -2 truncated */
-const uint8_t* crass_b200_batch_bases(const crass_b200_batch* b);         /* pinned host memory when a device exists */
+const uint8_t* crass_b200_batch_bases(const crass_b200_batch* b);          /* all reads back to back (offsets below index it); a range
+                                                                              of a streamed file keeps its reads in segments and is
+                                                                              copied together on the first call: prefer _batch_read */
+const uint8_t* crass_b200_batch_read(const crass_b200_batch* b, uint32_t i, uint32_t* len);   /* seq->seq.s / seq->seq.l of record i */         /* pinned host memory when a device exists */
 const uint64_t* crass_b200_batch_offsets(const crass_b200_batch* b);
 /* record fields exactly as searchFile sees them (stale comment/qual buffers of kseq included);
  * has_comment / has_qual mirror (seq->comment.s != NULL) / (seq->qual.s != NULL) */

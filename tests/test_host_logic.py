@@ -108,6 +108,14 @@ for it in range(40):
     for chunk in (64, 300, 1500):
         os.environ["CRASS_B200_PARSE_CHUNK"] = str(chunk)
         assert cb.Batch.from_file(p).record_stream() == want, (it, chunk)
+        # the same through the streamed feed, whose pieces stay where they were parsed (segments): dropped pieces, gaps
+        # parsed again in place, pieces whose last record overran their slice
+        got = [x.record_stream() for x in cb.Batch.stream_file(p, 5 * chunk + 3)]
+        assert b"".join(x[:x.rindex(b"#ret=")] for x in got[:-1]) + got[-1] == want, (it, chunk, "streamed")
+    for b in cb.Batch.stream_file(p, 700):                   # record by record == the back-to-back copy
+        off, bases = b.offsets, b.bases
+        for i in range(len(b)):
+            assert b.read(i) == bytes(bases[int(off[i]):int(off[i + 1])]), (it, i)
     n += 1
 print("ok", n)
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
