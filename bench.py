@@ -725,7 +725,7 @@ def main():
             b1 = eng.transfer_bytes()
             e2e = {"value": total_reads / (ms_file / args.steps / 1e3), "unit": "reads/s", "ms_per_step": ms_file / args.steps,
                    "h2d_bytes_per_step": int((b1[0] - b0[0]) // args.steps), "d2h_bytes_per_step": int((b1[1] - b0[1]) // args.steps),
-                   "what": "crass_b200_engine_run_files on the shard's FASTA (%d bytes, tmpfs), streamed in ranges of 256 MB: parse of range i+1 || pinned -> H2D -> K1 -> D2H of range i || replay of range i-1 into the containers; then clustering -> K2 over the resident ranges -> D2H -> replay (stage_ms overlap)" % os.path.getsize(fasta),
+                   "what": "crass_b200_engine_run_files on the shard's FASTA (%d bytes, tmpfs), streamed in ranges of 128 MB: parse of range i+1 || pinned -> H2D -> K1 -> D2H of range i || replay of range i-1 into the containers; then clustering -> K2 over the resident ranges -> D2H -> replay (stage_ms overlap)" % os.path.getsize(fasta),
                    "file_bytes": os.path.getsize(fasta), "gpu_launches_per_step": int((eng.launch_count - l0) // args.steps),
                    "stage_ms": info.get("stage_ms"), "found_reads": info.get("found_reads"), "tokens": info.get("tokens")}
             eng.close()

@@ -125,7 +125,7 @@ struct crass_b200_engine {
     std::map<std::string, std::vector<std::string> > ranged;  // files searched range by range: the names their ranges are resident under
     std::vector<crass_b200_batch*> batch_pool;            // released batches: their buffers (page-locked bases) serve the next parse
     std::mutex pool_mu;                                   // ... taken by the parsing thread of a streamed run while another thread searches
-    size_t stream_bytes = (size_t)256 << 20;              // range size of the streamed feed (CRASS_B200_STREAM_MB; 0 = whole files)
+    size_t stream_bytes = (size_t)128 << 20;              // range size of the streamed feed (CRASS_B200_STREAM_MB; 0 = whole files)
     Nccl nccl;
     bool use_nccl = false;
     uint32_t block_cap = 16384;                           // token-block capacity per shard (grows on overflow)

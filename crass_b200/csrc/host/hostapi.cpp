@@ -7,8 +7,10 @@
 
 #include <algorithm>
 #include <chrono>
+#include <exception>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <string_view>
 #include <unordered_set>
 #include <vector>
@@ -233,12 +235,30 @@ int crass_b200_results_add_phase1(crass_b200_results* rh, const crass_b200_batch
         build_holders(b, hits, nullptr, n_hits, ss_pool, 1, built);
         if (trace) fprintf(stderr, "[crass_b200]     phase-1 replay: %u holders built in %.2f ms\n", n_hits,
                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb0).count());
-        for (uint32_t k = 0; k < n_hits; ++k) {                             // searchFile's loop body for a hit (libcrispr.cpp:134-139)
-            insert_holder(r, built[k]);
-            if (r.patterns_index.insert(built[k].raw0).second) r.patterns_hash[built[k].raw0] = true;
-            if (r.found_index.insert(built[k].h->header).second)
-                r.reads_found.emplace_hint(r.reads_found.end(), built[k].h->header, true);   // (a no-op for a header that is there already)
-        }
+        // searchFile's loop body for a hit (libcrispr.cpp:134-139) fills three containers that do not know of each other: the
+        // ReadMap / StringCheck pair, patternsHash and readsFound.  Each is filled in hit order, on a thread of its own.
+        std::exception_ptr err_a, err_b, err_c;
+        auto fill_reads = [&]() {
+            try { for (uint32_t k = 0; k < n_hits; ++k) insert_holder(r, built[k]); } catch (...) { err_a = std::current_exception(); }
+        };
+        auto fill_patterns = [&]() {
+            try {
+                for (uint32_t k = 0; k < n_hits; ++k)
+                    if (r.patterns_index.insert(built[k].raw0).second) r.patterns_hash[built[k].raw0] = true;
+            } catch (...) { err_b = std::current_exception(); }
+        };
+        auto fill_found = [&]() {
+            try {
+                for (uint32_t k = 0; k < n_hits; ++k)
+                    if (r.found_index.insert(built[k].h->header).second)
+                        r.reads_found.emplace_hint(r.reads_found.end(), built[k].h->header, true);   // (a no-op for a header that is there already)
+            } catch (...) { err_c = std::current_exception(); }
+        };
+        if (n_hits >= 1024 && cbh::host_threads() >= 3) cbh::parallel_run(3, [&](unsigned w) { if (w == 0) fill_reads(); else if (w == 1) fill_patterns(); else fill_found(); });
+        else { fill_reads(); fill_patterns(); fill_found(); }
+        if (err_a) std::rethrow_exception(err_a);
+        if (err_b) std::rethrow_exception(err_b);
+        if (err_c) std::rethrow_exception(err_c);
     } catch (std::exception& ex) {
         return fail(CRASS_B200_ENOMEM, std::string("results_add_phase1: ") + ex.what());
     }
