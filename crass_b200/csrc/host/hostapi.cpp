@@ -291,29 +291,46 @@ int crass_b200_results_add_phase2_ranges(crass_b200_results* rh, uint32_t n_rang
             r.found_index.clear();
             for (const auto& kv : r.reads_found) r.found_index.insert(kv.first);
         }
-        std::vector<std::vector<uint32_t> > take(n_ranges);
-        std::vector<std::vector<Built> > built(n_ranges);
+        // all hits of all batches as one list: one pass over it on the worker threads for the header test, one for the holders
         size_t total = 0;
-        for (uint32_t f = 0; f < n_ranges; ++f) total += n_hits[f];
+        std::vector<size_t> first(n_ranges + 1, 0);
+        for (uint32_t f = 0; f < n_ranges; ++f) { total += n_hits[f]; first[f + 1] = total; }
         const unsigned workers = total >= 2048 ? std::min<unsigned>(cbh::host_threads(), 16) : 1;
-        for (uint32_t f = 0; f < n_ranges; ++f) {
-            const Batch& b = bhs[f]->b;
-            const uint32_t n = n_hits[f];
-            std::vector<std::vector<uint32_t> > part(workers);
-            cbh::parallel_run(workers, [&](unsigned w) {
-                const uint32_t lo = (uint32_t)((uint64_t)n * w / workers), hi = (uint32_t)((uint64_t)n * (w + 1) / workers);
-                std::string name;
-                for (uint32_t k = lo; k < hi; ++k) {
-                    name.assign(b.name_pool.data() + b.name_off[hits[f][k].read_index]);
-                    if (r.found_index.find(name) == r.found_index.end()) part[w].push_back(k);
-                }
-            });
-            for (unsigned w = 0; w < workers; ++w) take[f].insert(take[f].end(), part[w].begin(), part[w].end());
-            build_holders(b, hits[f], take[f].data(), (uint32_t)take[f].size(), ss_pools[f], 2, built[f]);
-        }
+        struct Ref { uint32_t f, k; };
+        std::vector<std::vector<Ref> > part(workers);
+        cbh::parallel_run(workers, [&](unsigned w) {
+            const size_t lo = total * w / workers, hi = total * (w + 1) / workers;
+            uint32_t f = 0;
+            std::string name;
+            for (size_t g = lo; g < hi; ++g) {
+                while (g >= first[f + 1]) ++f;
+                const uint32_t k = (uint32_t)(g - first[f]);
+                const Batch& b = bhs[f]->b;
+                name.assign(b.name_pool.data() + b.name_off[hits[f][k].read_index]);
+                if (r.found_index.find(name) == r.found_index.end()) part[w].push_back(Ref{f, k});
+            }
+        });
+        std::vector<Ref> take;
+        for (unsigned w = 0; w < workers; ++w) take.insert(take.end(), part[w].begin(), part[w].end());
+        std::vector<Built> built(take.size());
+        const unsigned bw = take.size() >= 2048 ? workers : 1;
+        cbh::parallel_run(bw, [&](unsigned w) {
+            const size_t lo = take.size() * w / bw, hi = take.size() * (w + 1) / bw;
+            for (size_t g = lo; g < hi; ++g) {
+                const Batch& b = bhs[take[g].f]->b;
+                const crass_b200_hit& ht = hits[take[g].f][take[g].k];
+                HeldRead* h = new HeldRead();
+                fill_holder(*h, b, ht.read_index);
+                h->ss.assign(ss_pools[take[g].f] + ht.ss_offset, ss_pools[take[g].f] + ht.ss_offset + ht.n_ss);
+                h->repeat_len = 0;
+                h->phase = 2;
+                built[g].h = h;
+                built[g].token = dr_lowlexi(*h);
+            }
+        });
         const auto tb1 = std::chrono::steady_clock::now();
-        size_t taken = 0;
-        for (uint32_t f = 0; f < n_ranges; ++f) { for (Built& o : built[f]) insert_holder(r, o); taken += built[f].size(); }
+        const size_t taken = built.size();
+        for (Built& o : built) insert_holder(r, o);
         if (trace) fprintf(stderr, "[crass_b200]     phase-2 replay: %zu of %zu hits new (%u batches), holders built in %.2f ms, inserted in %.2f ms\n", taken, total, n_ranges,
                            std::chrono::duration<double, std::milli>(tb1 - tb0).count(),
                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb1).count());

@@ -310,12 +310,35 @@ struct Piece {
     int status = 0;                              // 0: stopped at a header >= stop (next_hp); -1/-2: the stream ended here
     size_t next_hp = 0;
     size_t from = 0;                             // file position the piece starts at (where its bases lie in a shared buffer)
+    // comments and qualities: the piece's own pool, or -- for a streamed range -- its slice of the batch's text pool (a piece's
+    // strings are no longer than its bytes); a slice that fills up (the last record ran past the piece's end, or the input
+    // ended without a newline) is continued in the own pool and copied into place by the splice
+    char* text_ext = nullptr; size_t text_n = 0, text_cap = 0;
+    bool text_diverted = false;
+    size_t text_size() const { return text_ext ? text_n : text_pool.size(); }
+    const char* text_data() const { return text_ext ? text_ext : text_pool.data(); }
+    void text_append(const char* b, const char* e, bool nul) {
+        const size_t len = (size_t)(e - b), add = len + (nul ? 1 : 0);
+        if (text_ext) {
+            if (text_n + add <= text_cap) {
+                if (len) memcpy(text_ext + text_n, b, len);
+                if (nul) text_ext[text_n + len] = 0;
+                text_n += add;
+                return;
+            }
+            text_pool.clear();
+            append_str(text_pool, text_ext, text_ext + text_n, false);
+            text_ext = nullptr; text_diverted = true;
+        }
+        append_str(text_pool, b, e, nul);
+    }
     ~Piece() { if (own) free(bases); }
     void rewind() {                              // empty, with the memory kept (a piece of a ParseArena, range after range)
         if (own) free(bases);
         own = false; bases = nullptr; cap = 0;
         nb = 0; ends.clear(); name_pool.clear(); text_pool.clear(); name_off.clear(); comment_off.clear(); qual_off.clear();
         last_comment = last_qual = -1; max_len = 0; status = 0; next_hp = 0;
+        text_ext = nullptr; text_n = text_cap = 0; text_diverted = false;
     }
     void release() {                             // give everything back now (called by the thread that has just spliced the piece)
         if (own) free(bases);
@@ -373,8 +396,8 @@ void parse_span(const uint8_t* data, size_t n, size_t start, size_t stop, Piece&
         if (dret != '\n') {
             size_t cb, ce; int d2;
             if (get_until(c, '\n', cb, ce, d2)) {
-                cur_comment = (int64_t)P.text_pool.size();
-                append_str(P.text_pool, (const char*)data + cb, (const char*)data + ce);
+                cur_comment = (int64_t)P.text_size();
+                P.text_append((const char*)data + cb, (const char*)data + ce, true);
             }
         }
         const uint64_t seq_b = nb;
@@ -398,8 +421,8 @@ void parse_span(const uint8_t* data, size_t n, size_t start, size_t stop, Piece&
             while ((ch = c.getc()) != -1 && ch != '\n') {}
             if (ch == -1) { bad = -2; emit = false; }
             else {
-                if (P.text_span && P.text_pool.capacity() < P.text_span / 2) P.text_pool.reserve(P.text_span / 2 + P.text_span / 8 + 64);
-                const int64_t q0 = (int64_t)P.text_pool.size();
+                if (!P.text_ext && P.text_span && P.text_pool.capacity() < P.text_span / 2) P.text_pool.reserve(P.text_span / 2 + P.text_span / 8 + 64);
+                const int64_t q0 = (int64_t)P.text_size();
                 uint64_t ql = 0;
                 // kseq: while ((c = getc()) != -1 && qual.l < seq.l) if (c >= 33 && c <= 127) append(c);  -- the byte
                 // is fetched before the length test, so one byte past the last quality character is consumed
@@ -407,11 +430,11 @@ void parse_span(const uint8_t* data, size_t n, size_t start, size_t stop, Piece&
                     if (ch < 33) continue;                             // (signed) also skips bytes >= 0x80
                     const size_t lim = c.pos + (size_t)(L - ql - 1) < c.n ? c.pos + (size_t)(L - ql - 1) : c.n;
                     const size_t i = qual_run_end(c.p, c.pos, lim);     // the rest of this run of quality characters
-                    append_str(P.text_pool, (const char*)c.p + c.pos - 1, (const char*)c.p + i, false);   // (ch is the byte before pos)
+                    P.text_append((const char*)c.p + c.pos - 1, (const char*)c.p + i, false);   // (ch is the byte before pos)
                     ql += 1 + (i - c.pos);
                     c.pos = i;
                 }
-                P.text_pool.push_back(0);
+                P.text_append(nullptr, nullptr, true);
                 cur_qual = q0;
                 last_char = 0;
                 if (ql != L) { bad = -2; emit = false; }
@@ -559,8 +582,14 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
     ParseArena& A = arena ? *arena : local_arena;
     const bool in_place = arena != nullptr;
     uint8_t* scratch;
-    if (in_place) { B->reserve_bases((limit - first) + 64); scratch = B->bases; }
-    else scratch = A.room((limit - first) + 64 * np + 4096);
+    // (the strings the range before left behind open this batch's text pool)
+    const size_t carried = (cin && cin->has_comment ? cin->comment.size() + 1 : 0) + (cin && cin->has_qual ? cin->qual.size() + 1 : 0);
+    if (in_place) {
+        B->reserve_bases((limit - first) + 64);
+        scratch = B->bases;
+        B->text_pool.resize(carried + (limit - first) + 64);           // (address space: pages are touched as they are written)
+    } else scratch = A.room((limit - first) + 64 * np + 4096);
+    char* const text0 = in_place ? B->text_pool.data() + carried : nullptr;
     while (A.pieces.size() < np) A.pieces.emplace_back(new Piece());
     for (size_t k = 0; k < np; ++k) A.pieces[k]->rewind();
     std::vector<std::unique_ptr<Piece> >& pieces = A.pieces;
@@ -578,6 +607,7 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
                 P.from = from;
                 P.cap = ((stop == (size_t)-1 ? n : stop) - from) + (in_place ? 0 : 64);
                 P.bases = scratch + (from - first) + (in_place ? 0 : 64 * k);
+                if (in_place) { P.text_ext = text0 + (from - first); P.text_cap = P.cap; }
                 P.expect(P.cap);
                 parse_span(in.data, n, k ? from : start, stop, P);
             } catch (...) { failed.store(true); }
@@ -614,6 +644,7 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
             Q->own = false;
             Q->cap = (stop == (size_t)-1 ? n : stop) - hp;
             Q->bases = scratch + (hp - first);
+            Q->text_ext = text0 + (hp - first); Q->text_cap = Q->cap;
         } else {
             Q->own = true;
             Q->cap = ((stop == (size_t)-1 ? n : stop) - hp) + 64;
@@ -635,12 +666,16 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
     const int64_t carried_text = n_text;
     for (size_t i = 0; i < order.size(); ++i) {
         const Piece& P = *order[i];
-        slot[i] = Slot{total, n_rec, n_name, n_text, cc, cq};
-        if (P.last_comment >= 0) cc = n_text + P.last_comment;
-        if (P.last_qual >= 0) cq = n_text + P.last_qual;
-        total += P.nb; n_rec += P.ends.size(); n_name += P.name_pool.size(); n_text += (int64_t)P.text_pool.size();
+        // (in place, a piece's strings are -- or, if it had to go on in its own pool, will be -- in its slice of the text pool)
+        const int64_t t0p = in_place ? (int64_t)(carried + (P.from - first)) : n_text;
+        slot[i] = Slot{total, n_rec, n_name, t0p, cc, cq};
+        if (P.last_comment >= 0) cc = t0p + P.last_comment;
+        if (P.last_qual >= 0) cq = t0p + P.last_qual;
+        total += P.nb; n_rec += P.ends.size(); n_name += P.name_pool.size();
+        n_text = in_place ? std::max<int64_t>(n_text, t0p + (int64_t)P.text_size()) : n_text + (int64_t)P.text_size();
         if (P.max_len > B->max_len) B->max_len = P.max_len;
     }
+    if (in_place) n_text = std::max<int64_t>(n_text, (int64_t)B->text_pool.size());   // (never shrunk: slices of later pieces lie further up)
     const double t2 = now();
     // in place: a piece that went on in a buffer of its own (room()) is copied to where it belongs, which is free by now (what it
     // overran were slices of pieces that began inside its last record); should the last record of the range run past the
@@ -680,7 +715,7 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
             const Slot& S = slot[i];
             if (P.nb && !in_place) memcpy(B->bases + S.base0, P.bases, (size_t)P.nb);
             if (!P.name_pool.empty()) memcpy(B->name_pool.data() + S.name0, P.name_pool.data(), P.name_pool.size());
-            if (!P.text_pool.empty()) memcpy(B->text_pool.data() + S.text0, P.text_pool.data(), P.text_pool.size());
+            if (P.text_size() && (!in_place || P.text_diverted)) memcpy(B->text_pool.data() + S.text0, P.text_data(), P.text_size());
             const size_t m = P.ends.size();
             for (size_t r = 0; r < m; ++r) {
                 B->name_off[S.rec0 + r] = S.name0 + P.name_off[r];

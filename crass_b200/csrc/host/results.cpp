@@ -282,7 +282,10 @@ struct HeadTable {
 }  // namespace
 
 void parallel_run(unsigned n, const std::function<void(unsigned)>& job) { WorkerPool::instance().run(n, job); }
-unsigned host_threads() { return cluster_workers((size_t)1 << 20); }
+unsigned host_threads() {                                // helpers for per-read work (holders of a replay): every core up to 16
+    if (getenv("CRASS_B200_HOST_THREADS")) return cluster_workers((size_t)1 << 20);
+    return std::min<unsigned>(16, std::max<unsigned>(1, std::thread::hardware_concurrency()));
+}
 
 void prewake_cluster_workers(unsigned spin_us) { WorkerPool::instance().prewake(cluster_workers((size_t)1 << 20), spin_us); }
 
