@@ -687,7 +687,7 @@ def main():
             torch.cuda.synchronize()
             np_bases, np_offsets = h_bases.numpy(), h_offsets.numpy().view(np.uint64)
             if not threads_given:                                      # every rank clusters its own shard here: share the cores evenly
-                os.environ["CRASS_B200_HOST_THREADS"] = str(max(1, min(8, cores // max(local_world, 1))))
+                os.environ["CRASS_B200_HOST_THREADS"] = str(max(1, min(16, cores // max(local_world, 1))))
 
             def step_hostbuf():
                 ctx.upload(h_bases, h_offsets)                         # H2D from pinned host memory
