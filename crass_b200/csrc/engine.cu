@@ -29,6 +29,7 @@
 #include <condition_variable>
 #include <deque>
 #include <map>
+#include <unistd.h>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -556,8 +557,8 @@ struct SearchedRange {
 // each parsed range to the devices and runs K1 on it, a third hands the hits of each searched range, in file order, to
 // `consume` (the replay into the containers).  The ranges stay resident under the names left in range_paths.
 template <class Consume>
-int stream_phase1(crass_b200_engine* e, cbh::ParseStream* ps, const char* path, const crass_b200_params* params, Consume consume,
-                  int* max_len, std::vector<std::string>& range_paths) {
+int stream_phase1(crass_b200_engine* e, cbh::ParseStream* first_ps, const char* const* paths, uint32_t n_paths, const crass_b200_params* params,
+                  Consume consume, int* max_len, std::vector<std::string>& range_paths) {
     StageQueue<std::unique_ptr<FileState> > parsed;
     StageQueue<SearchedRange> searched;
     std::atomic<int> fail_rc{0};
@@ -601,19 +602,27 @@ int stream_phase1(crass_b200_engine* e, cbh::ParseStream* ps, const char* path, 
             free(r.hits); free(r.pool);
         }
     });
-    for (uint32_t i = 0; !fail_rc.load(); ++i) {
-        crass_b200_batch* h = take_batch(e, e->stream_bytes);
-        const double t0 = now_ms();
-        const int got = cbh::parse_stream_next(ps, &h->b);
-        e->t_parse += now_ms() - t0;
-        mark("parse", i, t0);
-        if (got <= 0) { retire_batch(e, h); if (got < 0) note_failure(-got); break; }
-        *max_len = std::max(*max_len, (int)h->b.max_len);
-        std::unique_ptr<FileState> fs(new FileState());
-        fs->path = std::string(path) + "#" + std::to_string(i);
-        fs->batch = h;
-        range_paths.push_back(fs->path);
-        parsed.push(std::move(fs));
+    // the files one after the other (each a kseq stream of its own: nothing is carried from file to file), their ranges
+    // numbered through; first_ps, if given, is the already opened stream of paths[0]
+    uint32_t i = 0;
+    for (uint32_t f = 0; f < n_paths && !fail_rc.load(); ++f) {
+        cbh::ParseStream* ps = f == 0 && first_ps ? first_ps : cbh::parse_stream_open(paths[f], e->stream_bytes);
+        if (!ps) { note_failure(CRASS_B200_EIO); break; }
+        for (; !fail_rc.load(); ++i) {
+            crass_b200_batch* h = take_batch(e, e->stream_bytes);
+            const double t0 = now_ms();
+            const int got = cbh::parse_stream_next(ps, &h->b);
+            e->t_parse += now_ms() - t0;
+            mark("parse", i, t0);
+            if (got <= 0) { retire_batch(e, h); if (got < 0) note_failure(-got); break; }
+            *max_len = std::max(*max_len, (int)h->b.max_len);
+            std::unique_ptr<FileState> fs(new FileState());
+            fs->path = std::string(paths[f]) + "#" + std::to_string(i);
+            fs->batch = h;
+            range_paths.push_back(fs->path);
+            parsed.push(std::move(fs));
+        }
+        if (!(f == 0 && first_ps)) cbh::parse_stream_close(ps);
     }
     parsed.close();
     searcher.join();
@@ -623,10 +632,10 @@ int stream_phase1(crass_b200_engine* e, cbh::ParseStream* ps, const char* path, 
     return rc;
 }
 
-int run_streamed(crass_b200_engine* e, cbh::ParseStream* ps, const char* path, const crass_b200_params* params, int phases,
-                 crass_b200_results* res, int* max_len) {
+int run_streamed(crass_b200_engine* e, cbh::ParseStream* first_ps, const char* const* paths, uint32_t n_paths, const crass_b200_params* params,
+                 int phases, crass_b200_results* res, int* max_len) {
     std::vector<std::string> range_paths;
-    int rc = stream_phase1(e, ps, path, params, [&](const SearchedRange& r, uint64_t) {
+    int rc = stream_phase1(e, first_ps, paths, n_paths, params, [&](const SearchedRange& r, uint64_t) {
         return crass_b200_results_add_phase1(res, r.batch, r.hits, r.nh, r.pool);
     }, max_len, range_paths);
     const double t_p1 = now_ms();
@@ -737,7 +746,7 @@ int crass_b200_engine_search_file_ranges(crass_b200_engine* e, const char* path,
     if (!ps) return CRASS_B200_EIO;
     int max_len = 0;
     std::vector<std::string> range_paths;
-    const int rc = stream_phase1(e, ps, path, params, [&](const SearchedRange& r, uint64_t first_read) {
+    const int rc = stream_phase1(e, ps, &path, 1, params, [&](const SearchedRange& r, uint64_t first_read) {
         return fn(user, r.batch, r.hits, r.nh, r.pool, r.np, first_read);
     }, &max_len, range_paths);
     cbh::parse_stream_close(ps);
@@ -860,11 +869,17 @@ int crass_b200_engine_run_files(crass_b200_engine* e, const char* const* paths, 
     // out ranges of about stream_bytes, each ending on a true record start; while its worker threads parse range i+1, a second
     // thread copies range i to the devices and runs K1 on it, and a third replays the hits of range i-1 into the containers.
     // The ranges then behave like the files of a multi-file run (token order from the containers, K2 over the resident ranges).
-    if (n_paths == 1 && e->stream_bytes) {
+    // Several files (paired-end reads) go through the same pipeline one after the other, whatever their sizes.
+    if (e->stream_bytes && n_paths >= 1) {
+        for (uint32_t f = 0; f < n_paths; ++f)
+            if (!paths[f] || (strcmp(paths[f], "-") != 0 && access(paths[f], R_OK) != 0)) {
+                crass_b200_results_destroy(res);
+                return cbh::fail(CRASS_B200_EIO, std::string("cannot open ") + (paths[f] ? paths[f] : "(null)"));
+            }
         cbh::ParseStream* ps = cbh::parse_stream_open(paths[0], e->stream_bytes);
         if (!ps) { crass_b200_results_destroy(res); return CRASS_B200_EIO; }
-        if (cbh::parse_stream_size(ps) >= 2 * e->stream_bytes) {
-            rc = run_streamed(e, ps, paths[0], params, phases, res, &max_len);
+        if (n_paths >= 2 || cbh::parse_stream_size(ps) >= 2 * e->stream_bytes) {
+            rc = run_streamed(e, ps, paths, n_paths, params, phases, res, &max_len);
             cbh::parse_stream_close(ps);
             if (e->trace)
                 fprintf(stderr, "[crass_b200] engine run (streamed): parse %.1f ms, phase 1 (H2D + K1 + D2H) %.1f ms, clustering %.1f ms, phase 2 %.1f ms, replay %.1f ms (stages overlap)\n",

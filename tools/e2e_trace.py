@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--repeat", type=int, default=3)
     ap.add_argument("--devices", default="0")
     ap.add_argument("--fastq", action="store_true", help="write the reads as FASTQ (one fixed quality string)")
+    ap.add_argument("--files", type=int, default=1, help="split the reads over this many files (paired-end style run)")
     args = ap.parse_args()
     os.environ.setdefault("CRASS_B200_TRACE", "1")
     import crass_b200 as cb
@@ -34,11 +35,16 @@ def main():
             hdr[:, 0] = ord("@")
             qual = np.frombuffer(bytes(33 + (7 * k) % 41 for k in range(150)), dtype=np.uint8)
             cols += [np.full((n, 1), ord("+"), dtype=np.uint8), nl, np.broadcast_to(qual, (n, 150)), nl]
-        np.concatenate(cols, axis=1).tofile(path)
+        rows = np.concatenate(cols, axis=1)
+        paths = []
+        for f in range(args.files):
+            paths.append(os.path.join(d, "reads%d.fx" % f))
+            rows[n * f // args.files:n * (f + 1) // args.files].tofile(paths[-1])
+        del rows
         eng = cb.Engine(tuple(int(x) for x in args.devices.split(",")))
         for it in range(args.repeat):
             t0 = time.time()
-            res, ml = eng.run_files([path])
+            res, ml = eng.run_files(paths)
             dt = time.time() - t0
             print("run %d: %.3f s, %.2f M reads/s, %d found reads, %d tokens, stages %s" % (it, dt, n / dt / 1e6, res.num_reads, res.num_tokens, eng.stage_ms()), flush=True)
             del res
