@@ -1447,7 +1447,7 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
             // flight are what it runs on (CRASS_B200_K2V_CTAS = CTAs per SM, for measurements)
             int per_sm = 16;
             if (const char* e = getenv("CRASS_B200_K2V_CTAS")) per_sm = std::max(1, atoi(e));
-            cbk::k_ac_verify_warp<<<c->sm_count * per_sm, 128, 0, st>>>(d_bases, d_offsets, cand, ps, d_found, sink);
+            cbk::k_ac_verify_warp<<<c->sm_count * per_sm, 128, 0, st>>>(d_bases, d_offsets, cand, nullptr, ps, d_found, sink);
         }
         c->launches += 2;
         CUDA_TRY(cudaGetLastError());
@@ -1458,6 +1458,8 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         if (!d_found) { if (int r = c->d_found.reserve((size_t)n_reads + 16)) return r; d_found = c->d_found.as<uint8_t>(); }
         if (int r = c->d_cand.reserve(((size_t)n_reads + 16) * sizeof(uint32_t))) return r;
         uint32_t* cand = c->d_cand.as<uint32_t>();
+        if (int r = c->d_cand_mask.reserve(((size_t)n_reads + 16) * sizeof(uint32_t))) return r;
+        uint32_t* cand_from = getenv("CRASS_B200_K2V_FROM0") ? nullptr : c->d_cand_mask.as<uint32_t>();   // per candidate: where the verification may start
         cbk::QgramFilter q{c->d_ac_bitmap.as<uint32_t>(), c->d_ac_keys.as<uint32_t>(), ac->a.q_bits, ac->a.q_table_bits, ac->a.q_hashes, c->d_ac_ones.as<uint32_t>()};
         const size_t smem = ((size_t)1 << ac->a.q_bits) / 8;
         const char* fsel = getenv("CRASS_B200_K2F");
@@ -1469,13 +1471,13 @@ int crass_b200_ac_scan_dev(crass_b200_ctx* c, const crass_b200_ac* ac_c, const u
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cbk::k_ac_filter_long<false>, cbk::kAcLongThreads, smem));
         const uint32_t want_blocks = (n_reads + (cbk::kAcLongThreads / 32) - 1) / (cbk::kAcLongThreads / 32);
         const int blocks = (int)std::min<uint32_t>(want_blocks, (uint32_t)(c->sm_count * std::max(per_sm, 1)));
-        if (use_packed) cbk::k_ac_filter_long<true><<<blocks, cbk::kAcLongThreads, smem, st>>>((const uint8_t*)c->d_packed.p, d_offsets, n_reads, q, d_skip, d_found, cand, d_counters);
-        else cbk::k_ac_filter_long<false><<<blocks, cbk::kAcLongThreads, smem, st>>>(d_bases, d_offsets, n_reads, q, d_skip, d_found, cand, d_counters);
+        if (use_packed) cbk::k_ac_filter_long<true><<<blocks, cbk::kAcLongThreads, smem, st>>>((const uint8_t*)c->d_packed.p, d_offsets, n_reads, q, d_skip, d_found, cand, c->d_cand_mask.as<uint32_t>(), d_counters);
+        else cbk::k_ac_filter_long<false><<<blocks, cbk::kAcLongThreads, smem, st>>>(d_bases, d_offsets, n_reads, q, d_skip, d_found, cand, c->d_cand_mask.as<uint32_t>(), d_counters);
         CUDA_TRY(cudaGetLastError());
         cbk::PatternStarts ps{c->d_ac_pbytes.as<uint8_t>(), c->d_ac_poffs.as<uint32_t>(), c->d_ac_skeys.as<uint32_t>(),
                               c->d_ac_shead.as<uint32_t>(), c->d_ac_pnext.as<uint32_t>(), ac->a.s_bits, c->d_ac_ones.as<uint32_t>(),
                               ac->a.min_pattern_len};
-        cbk::k_ac_verify_warp<<<c->sm_count * 16, 128, 0, st>>>(d_bases, d_offsets, cand, ps, d_found, sink);      // 28 registers: 16 CTAs per SM
+        cbk::k_ac_verify_warp<<<c->sm_count * 16, 128, 0, st>>>(d_bases, d_offsets, cand, cand_from, ps, d_found, sink);      // 16 CTAs per SM
         c->launches += 2;
         CUDA_TRY(cudaGetLastError());
         return scan_enqueued();

@@ -1526,7 +1526,7 @@ template <bool PACKED>                               // PACKED: `bases` is the 2
 __global__ void __launch_bounds__(kAcLongThreads)
 k_ac_filter_long(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, uint32_t n_reads, QgramFilter q,
                  const uint8_t* __restrict__ skip, uint8_t* __restrict__ found, uint32_t* __restrict__ cand_list,
-                 uint32_t* __restrict__ counters) {
+                 uint32_t* __restrict__ cand_from, uint32_t* __restrict__ counters) {
     extern __shared__ uint32_t dsm[];
     uint32_t* bm = dsm;
     for (uint32_t i = threadIdx.x; i < (1u << (q.bits - 5)); i += kAcLongThreads) bm[i] = __ldg(q.bitmap + i);
@@ -1552,6 +1552,7 @@ k_ac_filter_long(const uint8_t* __restrict__ bases, const uint64_t* __restrict__
         const int32_t d = (int32_t)((uint32_t)(b & 7u));            // read-aligned 16-mers start at stream offsets == b mod 8
         const uint32_t n_groups = (uint32_t)((((b + L + 15) >> 4) - w_first + 3) >> 2);
         bool cand = false;
+        uint32_t g_hit = 0;
         for (uint32_t g0 = 0; g0 < n_groups && !cand; g0 += 31) {
             const uint32_t g = g0 + lane;
             uint32_t w[5] = {0, 0, 0, 0, 0};
@@ -1595,8 +1596,16 @@ k_ac_filter_long(const uint8_t* __restrict__ bases, const uint64_t* __restrict__
                 }
             }
             cand = __any_sync(0xFFFFFFFFu, hit);
+            g_hit = g0;
         }
-        if (cand && lane == 0) cand_list[atomicAdd(&counters[3], 1u)] = r;
+        if (cand && lane == 0) {
+            const uint32_t at = atomicAdd(&counters[3], 1u);
+            cand_list[at] = r;
+            // No aligned 16-mer before this round is a key, and an occurrence that starts at a holds the aligned 16-mer at
+            // a ... a + 7: the verification may start seven bases before the round's first 16-mer.
+            const int32_t first_x = x0 + 64 * (int32_t)g_hit + d;
+            cand_from[at] = first_x > 7 ? (uint32_t)(first_x - 7) : 0u;
+        }
     }
 }
 
@@ -1671,7 +1680,7 @@ k_ac_verify_list(const uint8_t* __restrict__ bases, const uint64_t* __restrict__
 // the warp minimum of (end, -len) is the answer.  The scan stops once no later start can end earlier.
 __global__ void __launch_bounds__(128)
 k_ac_verify_warp(const uint8_t* __restrict__ bases, const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ cand_list,
-                 PatternStarts ps, uint8_t* __restrict__ found, HitSink sink) {
+                 const uint32_t* __restrict__ cand_from, PatternStarts ps, uint8_t* __restrict__ found, HitSink sink) {
     const uint32_t n_cand = sink.counters[3];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
@@ -1682,7 +1691,7 @@ k_ac_verify_warp(const uint8_t* __restrict__ bases, const uint64_t* __restrict__
         const uint32_t L = (uint32_t)(offsets[r + 1] - b);
         const uint8_t* s = bases + b;
         uint32_t best = 0xFFFFFFFFu;                                  // (end << 8) | (255 - len): min == earliest end, longest pattern
-        for (uint32_t p0 = 0; p0 + 16 <= L; p0 += 32) {
+        for (uint32_t p0 = cand_from ? cand_from[c] : 0u; p0 + 16 <= L; p0 += 32) {      // (the long-read filter knows where nothing can start)
             const uint32_t warp_best = __reduce_min_sync(0xFFFFFFFFu, best);
             if (warp_best != 0xFFFFFFFFu && p0 + ps.min_len > (warp_best >> 8)) break;
             const uint32_t p = p0 + lane;

@@ -252,7 +252,8 @@ int crass_b200_qc_found_repeats(crass_b200_ctx* ctx, const uint8_t* seq, uint32_
 int crass_b200_parse_file(const char* path, crass_b200_batch** out);      /* "-" = stdin */
 /* The same record stream handed out range by range -- the streamed feed (the reference's loop over kseq_read holds one record
  * at a time, libcrispr.cpp:96-131; here a range of about range_bytes of the input is one batch, so that parsing, copying,
- * K1 and the replay of successive ranges overlap: crass_b200_engine_run_files does that for files of two ranges or more).
+ * K1 and the replay of successive ranges overlap: crass_b200_engine_run_files does that for a file of two ranges or more and for
+ * every run over several files, which go through the pipeline one after the other).
  * Every range ends on a true record start and inherits kseq's stale comment / quality strings from the one before it;
  * crass_b200_parse_stream_next returns 1 and a batch (parse status 0 while more follows, the stream's final status in the
  * last one), 0 when the stream had ended, a negative error code otherwise. */
@@ -433,7 +434,8 @@ int crass_b200_engine_search_file_ranges(crass_b200_engine* e, const char* path,
                                          crass_b200_range_fn fn, void* user, int* max_read_len);
 int crass_b200_engine_find_singletons_ranges(crass_b200_engine* e, const char* path, const crass_b200_ac* ac, int skip_found,
                                              crass_b200_range_fn fn, void* user);
-/* WorkHorse::parseSeqFiles: searchFile* -> createNonRedundantSet -> findSingletons* on the engine's devices */
+/* WorkHorse::parseSeqFiles: searchFile* -> createNonRedundantSet -> findSingletons* on the engine's devices (streamed: parsing
+ * of range i+1, copy + K1 of range i and the replay of range i-1 overlap, across file boundaries too) */
 int crass_b200_engine_run_files(crass_b200_engine* e, const char* const* paths, uint32_t n_paths, const crass_b200_params* params,
                                 int phases, crass_b200_results** out, int* max_read_len);
 int crass_b200_run_files_multi(const int* devices, uint32_t n_devices, const char* const* paths, uint32_t n_paths,
