@@ -577,12 +577,14 @@ int stream_phase1(crass_b200_engine* e, cbh::ParseStream* first_ps, const char* 
         uint32_t i = 0;
         while (parsed.pop(fs)) {
             if (fail_rc.load()) { retire_batch(e, fs->batch); continue; }
-            SearchedRange r;
-            const double t0 = now_ms();
-            const int rc = search_parsed(e, std::move(fs), params, &r.batch, &r.hits, &r.nh, &r.pool, &r.np);
-            mark("search", i++, t0);
-            if (rc) { note_failure(rc); continue; }
-            searched.push(r);
+            try {                                                               // (nothing may leave a thread as an exception)
+                SearchedRange r;
+                const double t0 = now_ms();
+                const int rc = search_parsed(e, std::move(fs), params, &r.batch, &r.hits, &r.nh, &r.pool, &r.np);
+                mark("search", i++, t0);
+                if (rc) { note_failure(rc); continue; }
+                searched.push(r);
+            } catch (std::exception& ex) { cbh::fail(CRASS_B200_ENOMEM, std::string("streamed search: ") + ex.what()); note_failure(CRASS_B200_ENOMEM); }
         }
         searched.close();
     });
@@ -592,11 +594,13 @@ int stream_phase1(crass_b200_engine* e, cbh::ParseStream* first_ps, const char* 
         uint32_t i = 0;
         while (searched.pop(r)) {
             if (!fail_rc.load()) {
-                const double t0 = now_ms();
-                const int rc = consume(r, first_read);
-                e->t_replay += now_ms() - t0;
-                mark("replay", i++, t0);
-                if (rc) note_failure(rc);
+                try {
+                    const double t0 = now_ms();
+                    const int rc = consume(r, first_read);
+                    e->t_replay += now_ms() - t0;
+                    mark("replay", i++, t0);
+                    if (rc) note_failure(rc);
+                } catch (std::exception& ex) { cbh::fail(CRASS_B200_ENOMEM, std::string("streamed replay: ") + ex.what()); note_failure(CRASS_B200_ENOMEM); }
             }
             first_read += crass_b200_batch_num_reads(r.batch);
             free(r.hits); free(r.pool);
@@ -767,12 +771,14 @@ int crass_b200_engine_find_singletons_ranges(crass_b200_engine* e, const char* p
     StageQueue<SearchedRange> scanned;
     int scan_rc = 0; std::string scan_err;
     std::thread scanner([&]() {
-        for (const std::string& nm : names) {
-            SearchedRange r;
-            scan_rc = crass_b200_engine_find_singletons(e, nm.c_str(), ac, skip_found, &r.batch, &r.hits, &r.nh, &r.pool, &r.np);
-            if (scan_rc) { scan_err = crass_b200_last_error(); break; }
-            scanned.push(r);
-        }
+        try {
+            for (const std::string& nm : names) {
+                SearchedRange r;
+                scan_rc = crass_b200_engine_find_singletons(e, nm.c_str(), ac, skip_found, &r.batch, &r.hits, &r.nh, &r.pool, &r.np);
+                if (scan_rc) { scan_err = crass_b200_last_error(); break; }
+                scanned.push(r);
+            }
+        } catch (std::exception& ex) { scan_rc = CRASS_B200_ENOMEM; scan_err = std::string("streamed scan: ") + ex.what(); }
         scanned.close();
     });
     int rc = 0;
