@@ -134,6 +134,23 @@ def test_duplicate_headers_across_shards_and_several_files(P, tmp_path, exchange
     for devices in [(0,), (0, 0, 0)]:
         res, max_len = cb.run_files_multi(devices, paths)
         assert res.dump(max_len) == want, devices
+    # several files go through the streamed pipeline one after the other: with small ranges every file is several ranges (numbered
+    # through, each file a kseq stream of its own), with CRASS_B200_STREAM_MB=0 the files are taken whole, one after the other
+    old = {k: os.environ.get(k) for k in ("CRASS_B200_STREAM_BYTES", "CRASS_B200_STREAM_MB")}
+    try:
+        for env in ({"CRASS_B200_STREAM_BYTES": "150000"}, {"CRASS_B200_STREAM_BYTES": "40000"}, {"CRASS_B200_STREAM_MB": "0"}):
+            os.environ.pop("CRASS_B200_STREAM_BYTES", None)
+            os.environ.pop("CRASS_B200_STREAM_MB", None)
+            os.environ.update(env)
+            for devices in [(0,), (0, 0, 0)]:
+                res, max_len = cb.run_files_multi(devices, paths)
+                assert res.dump(max_len) == want, (env, devices)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
 
 def test_engine_steps_and_resident_reuse(P, tmp_path):
