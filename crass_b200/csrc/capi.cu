@@ -4,6 +4,7 @@
 // CRASS_B200_ENODEVICE otherwise.  Host-side bookkeeping (parser, replay, clustering, automaton
 // construction) is in host/*.cpp.
 #include <cuda_runtime.h>
+#include <sys/mman.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -158,19 +159,32 @@ struct crass_b200_ctx {
 
 namespace cbh {
 
-void* alloc_host(size_t bytes, bool* pinned) {
+void* alloc_host(size_t bytes, bool* pinned, bool want_pinned) {
     *pinned = false;
-    if (probe_devices() > 0) {
+    if (want_pinned && probe_devices() > 0) {
         void* p = nullptr;
         if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) { *pinned = true; return p; }
         (void)cudaGetLastError();
     }
+    if (bytes >= ((size_t)8 << 20)) {                            // large and ordinary: 2 MB aligned, huge pages if the kernel grants them
+        void* p = nullptr;
+        if (posix_memalign(&p, (size_t)2 << 20, bytes) == 0) { madvise(p, bytes, MADV_HUGEPAGE); return p; }
+    }
     return malloc(bytes);
 }
 
-void free_host(void* p, bool pinned) {
+void free_host(void* p, bool pinned, bool registered) {
     if (!p) return;
-    if (pinned) cudaFreeHost(p); else free(p);
+    if (pinned) { cudaFreeHost(p); return; }
+    if (registered) { if (cudaHostUnregister(p) != cudaSuccess) (void)cudaGetLastError(); }
+    free(p);
+}
+
+bool register_host(void* p, size_t bytes) {
+    if (!p || probe_devices() <= 0) return false;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) return true;
+    (void)cudaGetLastError();
+    return false;
 }
 
 void free_device_tables(Automaton*) {}                     // device copies are owned by the contexts (d_ac_*)

@@ -126,6 +126,8 @@ struct crass_b200_engine {
     std::map<std::string, std::vector<std::string> > ranged;  // files searched range by range: the names their ranges are resident under
     std::vector<crass_b200_batch*> batch_pool;            // released batches: their buffers (page-locked bases) serve the next parse
     std::mutex pool_mu;                                   // ... taken by the parsing thread of a streamed run while another thread searches
+    int pin_policy = 1;                                   // CRASS_B200_PIN: 0 never, 1 auto (from an engine's second run on), 2 always
+    std::atomic<int> runs_done{0};
     size_t stream_bytes = (size_t)128 << 20;              // range size of the streamed feed (CRASS_B200_STREAM_MB; 0 = whole files)
     Nccl nccl;
     bool use_nccl = false;
@@ -179,9 +181,15 @@ crass_b200_batch* take_batch(crass_b200_engine* e, size_t want_bytes) {       //
         const size_t bc = e->batch_pool[(size_t)best]->b.bases_cap;
         if ((cap >= want_bytes && (bc < want_bytes || cap < bc)) || (cap < want_bytes && bc < want_bytes && cap > bc)) best = (int)i;
     }
-    if (best < 0) return new crass_b200_batch();
-    crass_b200_batch* h = e->batch_pool[(size_t)best];
-    e->batch_pool.erase(e->batch_pool.begin() + best);
+    // Page-locking the base buffers is worth it for an engine that is used again (its buffers are pooled): locking 1.6 GB costs
+    // well over a second, a run on it 0.1 s.  The FIRST run of an engine therefore parses into ordinary memory (copied to the
+    // device through the driver's staging buffers); from the second run on, buffers are page-locked as they are taken from the pool.
+    const bool pin = e->pin_policy == 2 || (e->pin_policy == 1 && e->runs_done.load() >= 1);
+    crass_b200_batch* h;
+    if (best < 0) h = new crass_b200_batch();
+    else { h = e->batch_pool[(size_t)best]; e->batch_pool.erase(e->batch_pool.begin() + best); }
+    h->b.want_pinned = pin;
+    if (pin) h->b.pin_now();
     return h;
 }
 
@@ -375,6 +383,7 @@ int crass_b200_engine_create(const int* devices, uint32_t n_devices, crass_b200_
     }
     e->resident_budget = min_mem / 2;
     if (const char* v = getenv("CRASS_B200_RESIDENT_MB")) e->resident_budget = (size_t)strtoull(v, nullptr, 10) << 20;
+    if (const char* v = getenv("CRASS_B200_PIN")) e->pin_policy = !strcmp(v, "never") ? 0 : !strcmp(v, "always") ? 2 : 1;
     if (const char* v = getenv("CRASS_B200_STREAM_MB")) e->stream_bytes = (size_t)strtoull(v, nullptr, 10) << 20;
     if (const char* v = getenv("CRASS_B200_STREAM_BYTES")) e->stream_bytes = (size_t)strtoull(v, nullptr, 10);   // (tests: ranges of a few KB)
     // peer access for the block gather without NCCL
@@ -863,9 +872,19 @@ int crass_b200_engine_exchange(crass_b200_engine* e, const char* path, uint32_t 
 
 // WorkHorse::parseSeqFiles on the engine's devices: searchFile for every path, createNonRedundantSet, findSingletons for
 // every path; *out holds the containers a single sequential run would have filled.
+static int run_files_impl(crass_b200_engine* e, const char* const* paths, uint32_t n_paths, const crass_b200_params* params,
+                          int phases, crass_b200_results** out, int* max_read_len);
+
 int crass_b200_engine_run_files(crass_b200_engine* e, const char* const* paths, uint32_t n_paths, const crass_b200_params* params,
                                 int phases, crass_b200_results** out, int* max_read_len) {
     if (!e || !paths || !params || !out) return cbh::fail(CRASS_B200_EINVAL, "NULL argument");
+    const int rc = run_files_impl(e, paths, n_paths, params, phases, out, max_read_len);
+    e->runs_done.fetch_add(1);                                                // (an engine that is used again page-locks its pooled buffers)
+    return rc;
+}
+
+static int run_files_impl(crass_b200_engine* e, const char* const* paths, uint32_t n_paths, const crass_b200_params* params,
+                          int phases, crass_b200_results** out, int* max_read_len) {
     e->t_parse = e->t_phase1 = e->t_exchange = e->t_phase2 = e->t_replay = 0;
     crass_b200_results* res = nullptr;
     if (int r = crass_b200_results_create(&res)) return r;

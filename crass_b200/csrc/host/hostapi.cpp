@@ -70,7 +70,7 @@ int crass_b200_parse_file(const char* path, crass_b200_batch** out) {
     if (int r = parse_file(path, &b)) return r;
     crass_b200_batch* h = new crass_b200_batch();
     // move the parsed content into the handle
-    std::swap(h->b.bases, b->bases); std::swap(h->b.bases_cap, b->bases_cap); std::swap(h->b.pinned, b->pinned);
+    std::swap(h->b.bases, b->bases); std::swap(h->b.bases_cap, b->bases_cap); std::swap(h->b.pinned, b->pinned); std::swap(h->b.registered, b->registered);
     h->b.offsets.swap(b->offsets); h->b.name_pool.swap(b->name_pool); h->b.name_off.swap(b->name_off);
     h->b.text_pool.swap(b->text_pool); h->b.comment_off.swap(b->comment_off); h->b.qual_off.swap(b->qual_off);
     h->b.max_len = b->max_len; h->b.parse_status = b->parse_status;

@@ -22,8 +22,11 @@ void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 
 // ---- pinned host memory hooks (implemented next to the CUDA runtime; plain malloc without a device)
-void* alloc_host(size_t bytes, bool* pinned);
-void free_host(void* p, bool pinned);
+// host memory for read bases: page-locked when a device exists and `want_pinned` (cudaHostAlloc), else ordinary memory (2 MB
+// aligned, huge pages asked for); register_host page-locks ordinary memory after the fact (cudaHostRegister)
+void* alloc_host(size_t bytes, bool* pinned, bool want_pinned = true);
+void free_host(void* p, bool pinned, bool registered = false);
+bool register_host(void* p, size_t bytes);
 
 // std::vector whose resize() does not value-initialise: the per-read arrays of a 10 M-read batch are 440 MB, and zero-filling
 // them on one thread cost more than the worker threads need to fill them (30 ms of a 350 ms run)
@@ -42,7 +45,10 @@ template <class T> using PodVec = std::vector<T, NoInitAlloc<T> >;
 struct Batch {
     uint8_t* bases = nullptr;           // all reads back to back (pinned when a device exists)
     size_t bases_cap = 0;
-    bool pinned = false;
+    bool pinned = false;                // from cudaHostAlloc
+    bool registered = false;            // ordinary memory, page-locked later (pin_now)
+    bool want_pinned = true;            // what reserve_bases asks alloc_host for
+    void pin_now() { if (bases && !pinned && !registered) registered = register_host(bases, bases_cap); }
     PodVec<uint64_t> offsets;           // n+1
     PodVec<char> name_pool;             // NUL-terminated strings
     PodVec<uint64_t> name_off;

@@ -36,7 +36,7 @@
 
 namespace cbh {
 
-Batch::~Batch() { if (bases) free_host(bases, pinned); if (compact) free(compact); }
+Batch::~Batch() { if (bases) free_host(bases, pinned, registered); if (compact) free(compact); }
 
 const uint8_t* Batch::contiguous() {
     if (segs.empty()) return bases;
@@ -57,13 +57,13 @@ void Batch::reserve_bases(size_t need) {
     size_t ncap = bases_cap ? bases_cap : (1u << 20);
     while (ncap < need) ncap *= 2;
     bool pin = false;
-    uint8_t* nb = (uint8_t*)alloc_host(ncap, &pin);
+    uint8_t* nb = (uint8_t*)alloc_host(ncap, &pin, want_pinned);
     if (!nb) throw std::bad_alloc();
     if (bases) {
         if (!offsets.empty() && segs.empty()) memcpy(nb, bases, (size_t)offsets.back());
-        free_host(bases, pinned);
+        free_host(bases, pinned, registered);
     }
-    bases = nb; bases_cap = ncap; pinned = pin;
+    bases = nb; bases_cap = ncap; pinned = pin; registered = false;
 }
 
 namespace {
@@ -685,11 +685,11 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
         for (const Piece* P : order) need_end = std::max(need_end, (P->from - first) + (size_t)P->nb);
         if (need_end + 16 > B->bases_cap) {
             bool pin = false;
-            uint8_t* nbuf = (uint8_t*)alloc_host(total + 64, &pin);
+            uint8_t* nbuf = (uint8_t*)alloc_host(total + 64, &pin, B->want_pinned);
             if (!nbuf) throw std::bad_alloc();
             for (size_t i = 0; i < order.size(); ++i) if (order[i]->nb) memcpy(nbuf + slot[i].base0, order[i]->bases, (size_t)order[i]->nb);
-            free_host(B->bases, B->pinned);
-            B->bases = nbuf; B->bases_cap = total + 64; B->pinned = pin;
+            free_host(B->bases, B->pinned, B->registered);
+            B->bases = nbuf; B->bases_cap = total + 64; B->pinned = pin; B->registered = false;
         } else {
             for (size_t i = 0; i < order.size(); ++i) {
                 const Piece& P = *order[i];
