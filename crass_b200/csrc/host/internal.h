@@ -47,7 +47,8 @@ struct Batch {
     size_t bases_cap = 0;
     bool pinned = false;                // from cudaHostAlloc
     bool registered = false;            // ordinary memory, page-locked later (pin_now)
-    bool want_pinned = true;            // what reserve_bases asks alloc_host for
+    bool want_pinned = false;           // what reserve_bases asks alloc_host for: page-locking costs more than one copy from ordinary memory,
+                                        // so only an engine that reuses its pooled batches asks for it
     void pin_now() { if (bases && !pinned && !registered) registered = register_host(bases, bases_cap); }
     PodVec<uint64_t> offsets;           // n+1
     PodVec<char> name_pool;             // NUL-terminated strings

@@ -270,7 +270,7 @@ int crass_b200_batch_parse_status(const crass_b200_batch* b);             /* las
 const uint8_t* crass_b200_batch_bases(const crass_b200_batch* b);          /* all reads back to back (offsets below index it); a range
                                                                               of a streamed file keeps its reads in segments and is
                                                                               copied together on the first call: prefer _batch_read */
-const uint8_t* crass_b200_batch_read(const crass_b200_batch* b, uint32_t i, uint32_t* len);   /* seq->seq.s / seq->seq.l of record i */         /* pinned host memory when a device exists */
+const uint8_t* crass_b200_batch_read(const crass_b200_batch* b, uint32_t i, uint32_t* len);   /* seq->seq.s / seq->seq.l of record i */
 const uint64_t* crass_b200_batch_offsets(const crass_b200_batch* b);
 /* record fields exactly as searchFile sees them (stale comment/qual buffers of kseq included);
  * has_comment / has_qual mirror (seq->comment.s != NULL) / (seq->qual.s != NULL) */
@@ -398,7 +398,7 @@ int crass_b200_run_files(crass_b200_ctx* ctx, const char* const* paths, uint32_t
  * single ReadMap exactly as after a one-GPU run (WorkHorse.cpp:321-414; readsFound is tested on the host by header,
  * libcrispr.cpp:411, which also covers headers that repeat across shards).  The same device may be named more than once
  * (the shards then share it): that is how the multi-device logic is tested on a box with one GPU.
- * A searched file stays parsed (page-locked host memory) and resident in HBM (bytes, offsets, phase-1 flags, 2-bit stream)
+ * A searched file stays parsed (host memory; page-locked once the engine reuses its pooled buffers, CRASS_B200_PIN) and resident in HBM (bytes, offsets, phase-1 flags, 2-bit stream)
  * until released, so findSingletons neither parses nor uploads it again; CRASS_B200_RESIDENT_MB bounds the bytes a device
  * keeps (default: half its memory), older files are uploaded again from the host copy. */
 typedef struct crass_b200_engine crass_b200_engine;
