@@ -100,6 +100,13 @@ struct Lane {                                             // one device: context
     crass_b200_ctx* ctx = nullptr;
     cudaStream_t stream = nullptr, copy[2] = {nullptr, nullptr};
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+    // copies from ORDINARY host memory (an engine's first run, CRASS_B200_PIN): slices are memcpy'd into small page-locked
+    // staging buffers by a few threads and sent from there -- what the driver does for a pageable source, on more than one core
+    static constexpr int kStageBufs = 8;
+    static constexpr size_t kStageBytes = (size_t)4 << 20;
+    HBuf stage;                                           // kStageBufs x kStageBytes
+    cudaEvent_t ev_stage[kStageBufs] = {};
+    bool stage_used[kStageBufs] = {};
     DBuf d_hits, d_sorted, d_pool, d_cnt, d_tokens, d_found2, d_block, d_recv, d_merged;
     HBuf h_cnt, h_offsets, h_hits, h_pool;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
@@ -243,16 +250,49 @@ int upload_shard(Lane& l, const cbh::Batch& b, Shard& s) {
     ENG_CUDA(cudaMemcpyAsync(s.d_offsets.p, ho, ((size_t)s.n() + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, l.copy[0]));
     const uint64_t slice = (uint64_t)64 << 20;
     int which = 0;
+    struct Slice { uint8_t* dst; const uint8_t* src; uint64_t len; };
+    std::vector<Slice> work;
+    const bool staged = !b.pinned && !b.registered && nbytes >= ((uint64_t)16 << 20) && !getenv("CRASS_B200_NO_STAGING");
+    if (staged) {
+        if (int r = l.stage.reserve((size_t)Lane::kStageBufs * Lane::kStageBytes)) return r;
+        for (int k = 0; k < Lane::kStageBufs; ++k) if (!l.ev_stage[k]) ENG_CUDA(cudaEventCreateWithFlags(&l.ev_stage[k], cudaEventDisableTiming));
+    }
     // back to back on the device; on the host a streamed range lies in segments (cbh::Batch::segs), each copied to its place
     const size_t n_seg = b.segs.empty() ? 1 : b.segs.size();
     for (size_t k = 0; k < n_seg; ++k) {
         const uint64_t dev0 = b.segs.empty() ? 0 : b.segs[k].dev0, host0 = b.segs.empty() ? 0 : b.segs[k].host0;
         const uint64_t dev1 = k + 1 < n_seg ? b.segs[k + 1].dev0 : b.offsets.back();
         const uint64_t lo = std::max<uint64_t>(dev0, s.b0), hi = std::min<uint64_t>(dev1, s.b1);
+        if (staged) {
+            for (uint64_t at = lo; at < hi; at += Lane::kStageBytes)
+                work.push_back(Slice{s.d_bases.as<uint8_t>() + (at - s.b0), b.bases + host0 + (at - dev0), std::min<uint64_t>(Lane::kStageBytes, hi - at)});
+            continue;
+        }
         for (uint64_t at = lo; at < hi; at += slice, which ^= 1) {
             const uint64_t len = std::min(slice, hi - at);
             ENG_CUDA(cudaMemcpyAsync(s.d_bases.as<uint8_t>() + (at - s.b0), b.bases + host0 + (at - dev0), len, cudaMemcpyHostToDevice, l.copy[which]));
         }
+    }
+    if (staged && !work.empty()) {
+        constexpr int kThreads = 4, kPer = Lane::kStageBufs / kThreads;
+        std::atomic<int> bad{0};
+        auto run = [&](int t) {
+            if (cudaSetDevice(l.device) != cudaSuccess) { bad.store(1); return; }
+            for (size_t j = (size_t)t, k = 0; j < work.size() && !bad.load(); j += kThreads, ++k) {
+                const int buf = t * kPer + (int)(k % kPer);
+                uint8_t* st = l.stage.as<uint8_t>() + (size_t)buf * Lane::kStageBytes;
+                if (l.stage_used[buf] && cudaEventSynchronize(l.ev_stage[buf]) != cudaSuccess) { bad.store(1); return; }   // its last copy has left
+                memcpy(st, work[j].src, (size_t)work[j].len);
+                if (cudaMemcpyAsync(work[j].dst, st, (size_t)work[j].len, cudaMemcpyHostToDevice, l.copy[t & 1]) != cudaSuccess ||
+                    cudaEventRecord(l.ev_stage[buf], l.copy[t & 1]) != cudaSuccess) { bad.store(1); return; }
+                l.stage_used[buf] = true;
+            }
+        };
+        std::thread helpers[kThreads - 1];
+        for (int t = 1; t < kThreads; ++t) helpers[t - 1] = std::thread(run, t);
+        run(0);
+        for (auto& h : helpers) h.join();
+        if (bad.load()) { (void)cudaGetLastError(); return cbh::fail(CRASS_B200_ECUDA, "staged copy to the device failed"); }
     }
     for (int k = 0; k < 2; ++k) {
         ENG_CUDA(cudaEventRecord(l.ev_copy[k], l.copy[k]));
@@ -426,6 +466,8 @@ void crass_b200_engine_destroy(crass_b200_engine* e) {
         for (DBuf* b : {&l->d_hits, &l->d_sorted, &l->d_pool, &l->d_cnt, &l->d_tokens, &l->d_found2, &l->d_block, &l->d_recv, &l->d_merged}) b->release();
         for (HBuf* b : {&l->h_cnt, &l->h_offsets, &l->h_hits, &l->h_pool}) b->release();
         for (int k = 0; k < 2; ++k) { if (l->ev_copy[k]) cudaEventDestroy(l->ev_copy[k]); if (l->copy[k]) cudaStreamDestroy(l->copy[k]); }
+        for (int k = 0; k < Lane::kStageBufs; ++k) if (l->ev_stage[k]) cudaEventDestroy(l->ev_stage[k]);
+        l->stage.release();
         if (l->stream) cudaStreamDestroy(l->stream);
         crass_b200_ctx_destroy(l->ctx);
     }
