@@ -177,24 +177,30 @@ int phase1_range(void* user, const crass_b200_batch* batch, const crass_b200_hit
 struct Phase2Sink {
     ReadMap* reads; StringCheck* strings; lookupTable* found;
     Ticker tick;
+    std::string failure;                                            // what() of an exception the containers threw
     Phase2Sink(ReadMap* r, StringCheck* s, lookupTable* f, int base, time_t* t) : reads(r), strings(s), found(f), tick("singletonFinder", base, t) {}
 };
 
 int phase2_range(void* user, const crass_b200_batch* batch, const crass_b200_hit* hits, uint32_t n_hits, const uint32_t* pool,
                  uint32_t, uint64_t) {
     Phase2Sink& k = *(Phase2Sink*)user;
-    uint32_t at = 0;
-    k.tick.range(crass_b200_batch_num_reads(batch), [&](uint32_t upto) {
-        for (; at < n_hits && hits[at].read_index < upto; ++at) {               // on_match (libcrispr.cpp:408-442)
-            const crass_b200_hit& ht = hits[at];
-            const char* name = crass_b200_batch_name(batch, ht.read_index);
-            if (k.found->find(name) != k.found->end()) continue;
-            ReadHolder tmp_holder;
-            fill_holder(tmp_holder, batch, ht.read_index);
-            tmp_holder.startStopsAdd(pool[ht.ss_offset], pool[ht.ss_offset + 1]);
-            addReadHolder(k.reads, k.strings, tmp_holder);
-        }
-    });
+    try {
+        uint32_t at = 0;
+        k.tick.range(crass_b200_batch_num_reads(batch), [&](uint32_t upto) {
+            for (; at < n_hits && hits[at].read_index < upto; ++at) {           // on_match (libcrispr.cpp:408-442)
+                const crass_b200_hit& ht = hits[at];
+                const char* name = crass_b200_batch_name(batch, ht.read_index);
+                if (k.found->find(name) != k.found->end()) continue;
+                ReadHolder tmp_holder;
+                fill_holder(tmp_holder, batch, ht.read_index);
+                tmp_holder.startStopsAdd(pool[ht.ss_offset], pool[ht.ss_offset + 1]);
+                addReadHolder(k.reads, k.strings, tmp_holder);
+            }
+        });
+    } catch (crispr::exception& e) {                                            // must not unwind through the engine (its helper thread is running)
+        k.failure = e.what();
+        return CRASS_B200_EINVAL;
+    }
     return 0;
 }
 
@@ -249,6 +255,7 @@ void findSingletons(const char* inputFastq, const options& opts, std::vector<std
     // (libcrispr.cpp:411).
     int rc = crass_b200_engine_find_singletons_ranges(file_engine(), inputFastq, ac, 0, phase2_range, &sink);
     crass_b200_ac_destroy(ac);
+    if (rc && !sink.failure.empty()) throw crispr::exception(__FILE__, __LINE__, __PRETTY_FUNCTION__, sink.failure.c_str());
     if (rc) {
         const std::string why = crass_b200_last_error();
         if (why.find("cannot open") != std::string::npos) {
