@@ -224,7 +224,7 @@ class Batch:
                 h = C.c_void_p()
                 got = lib().crass_b200_parse_stream_next(s, C.byref(h))
                 if got < 0:
-                    _check(-got)
+                    _check(got)
                 if got == 0:
                     return
                 yield cls(h)

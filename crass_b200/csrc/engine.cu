@@ -669,7 +669,7 @@ int stream_phase1(crass_b200_engine* e, cbh::ParseStream* first_ps, const char* 
             const int got = cbh::parse_stream_next(ps, &h->b);
             e->t_parse += now_ms() - t0;
             mark("parse", i, t0);
-            if (got <= 0) { retire_batch(e, h); if (got < 0) note_failure(-got); break; }
+            if (got <= 0) { retire_batch(e, h); if (got < 0) note_failure(got); break; }
             *max_len = std::max(*max_len, (int)h->b.max_len);
             std::unique_ptr<FileState> fs(new FileState());
             fs->path = std::string(paths[f]) + "#" + std::to_string(i);

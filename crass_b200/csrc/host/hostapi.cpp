@@ -90,7 +90,7 @@ int crass_b200_parse_stream_open(const char* path, uint64_t range_bytes, crass_b
 }
 
 int crass_b200_parse_stream_next(crass_b200_parse_stream* s, crass_b200_batch** out) {
-    if (!s || !out) return -fail(CRASS_B200_EINVAL, "NULL argument");
+    if (!s || !out) return fail(CRASS_B200_EINVAL, "NULL argument");
     crass_b200_batch* h = new crass_b200_batch();
     const int got = parse_stream_next(s->s, &h->b);
     if (got <= 0) { delete h; *out = nullptr; return got; }

@@ -89,7 +89,7 @@ struct Batch {
 int parse_file(const char* path, Batch** out, Batch* reuse = nullptr);
 // the same record stream handed out range by range (about range_bytes of the input each; each range ends on a true record
 // start and carries kseq's stale comment / quality into the next): 1 = a range was parsed into `reuse`, 0 = the stream had
-// ended, < 0 = -(error code).  The batch of the LAST range carries the parse status of the stream, the others 0.
+// ended, < 0 = the error code.  The batch of the LAST range carries the parse status of the stream, the others 0.
 struct ParseStream;
 ParseStream* parse_stream_open(const char* path, size_t range_bytes);
 size_t parse_stream_size(const ParseStream* s);

@@ -29,6 +29,7 @@
 #include <atomic>
 #include <chrono>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <thread>
 
@@ -105,6 +106,80 @@ struct Input {
     std::atomic<bool> inflate_done{false}, inflate_failed{false};
     bool incremental = false;
     size_t vcap = 0;
+    size_t expect_size = 0;                        // BGZF: the inflated size, known from the block trailers before anything is inflated
+    // A BGZF archive (bgzip, htslib: gzip members of at most 64 KB whose extra field says how long each member is) can be inflated
+    // by several threads: the block list is read off the headers, every block's place in the output is the sum of the ISIZE
+    // trailers before it.  Any other gzip file is one deflate stream, and one thread (zlib) is all that can work on it.
+    struct BgzfBlock { size_t cpos, clen, out; uint32_t isize, crc; };
+    void* cmap = nullptr; size_t cmap_len = 0;     // the archive itself, mapped (BGZF only)
+    static bool bgzf_index(const uint8_t* c, size_t n, std::vector<BgzfBlock>& blocks, size_t* total) {
+        size_t pos = 0, out = 0;
+        while (pos < n) {
+            if (n - pos < 28 || c[pos] != 0x1f || c[pos + 1] != 0x8b || c[pos + 2] != 8 || !(c[pos + 3] & 4)) return false;
+            if (c[pos + 3] & ~4u) return false;                                  // a name, comment or header CRC: not what bgzip writes
+            const size_t xlen = c[pos + 10] | ((size_t)c[pos + 11] << 8);
+            if (pos + 12 + xlen > n) return false;
+            size_t bsize = 0;
+            for (size_t x = pos + 12; x + 4 <= pos + 12 + xlen;) {               // subfields: SI1 SI2 SLEN data
+                const size_t slen = c[x + 2] | ((size_t)c[x + 3] << 8);
+                if (c[x] == 'B' && c[x + 1] == 'C' && slen == 2 && x + 6 <= pos + 12 + xlen) bsize = (size_t)(c[x + 4] | (c[x + 5] << 8)) + 1;
+                x += 4 + slen;
+            }
+            if (!bsize || bsize < 12 + xlen + 8 || pos + bsize > n) return false;
+            const uint8_t* t = c + pos + bsize - 8;
+            const uint32_t crc = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
+            const uint32_t isize = t[4] | (t[5] << 8) | (t[6] << 16) | ((uint32_t)t[7] << 24);
+            if (isize > (1u << 16)) return false;
+            blocks.push_back(BgzfBlock{pos + 12 + xlen, bsize - 12 - xlen - 8, out, isize, crc});
+            out += isize;
+            pos += bsize;
+        }
+        *total = out;
+        return !blocks.empty();
+    }
+    // the inflater of a BGZF archive: worker threads take groups of blocks in file order; `avail` is the end of the leading run of
+    // finished groups
+    void inflate_bgzf(std::vector<BgzfBlock> blocks, unsigned n_threads) {
+        const uint8_t* c = (const uint8_t*)cmap;
+        const size_t group = 32, n_groups = (blocks.size() + group - 1) / group;
+        std::vector<std::atomic<uint8_t> > done(n_groups);
+        for (auto& d : done) d.store(0);
+        std::atomic<size_t> next{0};
+        std::mutex lead_mu;
+        size_t lead = 0;
+        auto work = [&]() {
+            z_stream z;
+            memset(&z, 0, sizeof z);
+            if (inflateInit2(&z, -15) != Z_OK) { inflate_failed.store(true); return; }
+            for (;;) {
+                const size_t g = next.fetch_add(1);
+                if (g >= n_groups || inflate_failed.load()) break;
+                for (size_t b = g * group; b < std::min(blocks.size(), (g + 1) * group); ++b) {
+                    const BgzfBlock& k = blocks[b];
+                    uint8_t* dst = (uint8_t*)map + k.out;
+                    inflateReset(&z);
+                    z.next_in = const_cast<Bytef*>(c + k.cpos); z.avail_in = (uInt)k.clen;
+                    z.next_out = dst; z.avail_out = k.isize;
+                    const int r = inflate(&z, Z_FINISH);
+                    if (r != Z_STREAM_END || z.total_out != k.isize || (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, k.isize) != k.crc) { inflate_failed.store(true); break; }
+                }
+                done[g].store(1, std::memory_order_release);
+                std::lock_guard<std::mutex> l(lead_mu);
+                while (lead < n_groups && done[lead].load(std::memory_order_acquire)) ++lead;
+                avail.store(lead < n_groups ? blocks[lead * group].out : expect_size, std::memory_order_release);
+            }
+            inflateEnd(&z);
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < n_threads; ++t) pool.emplace_back(work);
+        work();
+        for (auto& t : pool) t.join();
+        if (inflate_failed.load()) {                                             // what is usable is what came before the bad block
+            std::lock_guard<std::mutex> l(lead_mu);
+            avail.store(lead < n_groups ? blocks[lead * group].out : expect_size, std::memory_order_release);
+        }
+        inflate_done.store(true, std::memory_order_release);
+    }
     std::vector<uint8_t> inflated;
     const uint8_t* data = nullptr;
     size_t size = 0;
@@ -113,6 +188,7 @@ struct Input {
     ~Input() {
         if (inflater.joinable()) inflater.join();
         if (map) unmap_later(map, map_len);
+        if (cmap) munmap(cmap, cmap_len);
     }
     // open for streaming: plain files as open() does; gz files start an inflater thread and return at once
     bool open_streaming(const char* path) {
@@ -125,6 +201,29 @@ struct Input {
         const bool gz = regular && pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
         ::close(fd);
         if (!gz || (size_t)st.st_size < env_size_early("CRASS_B200_GZ_STREAM_MIN", (size_t)8 << 20)) return open(path);      // small archives: inflate first, as before
+        if (!getenv("CRASS_B200_GZ_SERIAL")) {                                     // BGZF: every block on its own, several threads
+            const int cfd = ::open(path, O_RDONLY);
+            void* cm = cfd >= 0 ? mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, cfd, 0) : MAP_FAILED;
+            if (cfd >= 0) ::close(cfd);
+            if (cm != MAP_FAILED) {
+                std::vector<BgzfBlock> blocks;
+                size_t total = 0;
+                if (bgzf_index((const uint8_t*)cm, (size_t)st.st_size, blocks, &total)) {
+                    vcap = total + ((size_t)1 << 20);
+                    void* m = mmap(nullptr, vcap, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+                    if (m != MAP_FAILED) {
+                        madvise(m, vcap, MADV_HUGEPAGE);
+                        cmap = cm; cmap_len = (size_t)st.st_size;
+                        map = m; map_len = vcap; data = (const uint8_t*)m; size = 0; incremental = true; expect_size = total;
+                        unsigned hw = std::thread::hardware_concurrency();
+                        const unsigned nt = (unsigned)std::max<size_t>(1, env_size_early("CRASS_B200_GZ_THREADS", std::max<unsigned>(2, std::min<unsigned>(16, hw > 2 ? hw - 2 : 1))));
+                        inflater = std::thread([this, nt](std::vector<BgzfBlock> bl) { inflate_bgzf(std::move(bl), nt); }, std::move(blocks));
+                        return true;
+                    }
+                }
+                munmap(cm, (size_t)st.st_size);
+            }
+        }
         vcap = (size_t)st.st_size * 64 + ((size_t)1 << 30);                        // address space only (MAP_NORESERVE)
         void* m = mmap(nullptr, vcap, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
         if (m == MAP_FAILED) return open(path);
@@ -779,9 +878,9 @@ ParseStream* parse_stream_open(const char* path, size_t range_bytes) {
 }
 
 // the input's size; for a gz archive that is still being inflated, a guess (four times the archive)
-size_t parse_stream_size(const ParseStream* s) { return s->in.incremental ? s->in.map_len / 64 * 4 : s->in.size; }
+size_t parse_stream_size(const ParseStream* s) { return s->in.incremental ? (s->in.expect_size ? s->in.expect_size : s->in.map_len / 64 * 4) : s->in.size; }
 
-// parses the next range into `reuse`; 1: a range was parsed (it may hold no record), 0: the stream had ended before, < 0: error
+// parses the next range into `reuse`; 1: a range was parsed (it may hold no record), 0: the stream had ended before, < 0: the error code
 int parse_stream_next(ParseStream* s, Batch* reuse) {
     if (s->ended) return 0;
     try {
@@ -807,7 +906,7 @@ int parse_stream_next(ParseStream* s, Batch* reuse) {
         if (!s->ended) reuse->parse_status = 0;               // the loop goes on in the next range
     } catch (std::exception& ex) {
         s->ended = true;
-        return -fail(CRASS_B200_ENOMEM, std::string("parse_stream_next: ") + ex.what());
+        return fail(CRASS_B200_ENOMEM, std::string("parse_stream_next: ") + ex.what());   // (the codes are negative)
     }
     return 1;
 }

@@ -201,6 +201,77 @@ def test_parser_pieces_on_worker_threads_match_the_sequential_stream():
         assert r.returncode == 0 and r.stdout.strip() == "ok 40", r.stdout + r.stderr
 
 
+def _write_bgzf(path, data, block=0xff00, corrupt_block=None):
+    """what bgzip writes: gzip members of at most 64 KB with the BC extra field (total member size - 1) and an empty last one"""
+    import struct
+    import zlib
+
+    def member(chunk):
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        comp = c.compress(chunk) + c.flush()
+        return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(comp) + 25) + comp +
+                struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+    with open(path, "wb") as fh:
+        for k, i in enumerate(range(0, len(data), block)):
+            m = member(data[i:i + block])
+            if corrupt_block == k:
+                m = m[:40] + bytes([m[40] ^ 0x55]) + m[41:]
+            fh.write(m)
+        fh.write(member(b""))
+
+
+def test_parser_inflates_a_bgzf_archive_on_several_threads():
+    """A BGZF archive (bgzip / htslib) says in every member's header how long the member is, so its blocks are inflated by
+    several threads, each block straight to its place in the output, while the parser takes the ranges that are complete
+    (the reference inflates inside its read loop, SeqUtils.cpp:100-125).  Same record stream as zlib's sequential read;
+    an archive that stops being BGZF half way is read by the one-thread path; a damaged block fails loudly."""
+    rng = random.Random(14)
+    P = checkers.port()
+    with tempfile.TemporaryDirectory() as d:
+        parts = []
+        for k in range(50000):
+            seq = fuzzgen.rand_seq(rng, rng.randint(30, 150)).decode()
+            if rng.random() < 0.5:
+                parts.append("@r%d c%d\n%s\n+\n%s\n" % (k, k, seq, "".join(rng.choice("!5I@>F") for _ in seq)))
+            else:
+                parts.append(">r%d\n%s\n" % (k, seq))
+        text = "".join(parts).encode()
+        p = os.path.join(d, "b.fx.gz")
+        _write_bgzf(p, text)
+        assert gzip.open(p).read() == text                               # (a valid multi-member gzip file)
+        want = P.kseq_dump(p)
+        keys = ("CRASS_B200_GZ_STREAM_MIN", "CRASS_B200_PARSE_CHUNK", "CRASS_B200_PARSE_THREADS", "CRASS_B200_GZ_THREADS", "CRASS_B200_GZ_SERIAL")
+        old = {k: os.environ.get(k) for k in keys}
+        os.environ.update(CRASS_B200_GZ_STREAM_MIN="1", CRASS_B200_PARSE_CHUNK="200000", CRASS_B200_PARSE_THREADS="4")
+        try:
+            for threads, range_bytes in (("1", 900000), ("3", 300000), ("8", 2500000), ("5", 0)):
+                os.environ["CRASS_B200_GZ_THREADS"] = threads
+                got = [x.record_stream() for x in cb.Batch.stream_file(p, range_bytes)]
+                assert b"".join(x[:x.rindex(b"#ret=")] for x in got[:-1]) + got[-1] == want, (threads, range_bytes)
+            os.environ["CRASS_B200_GZ_SERIAL"] = "1"                     # the one-thread path on the same archive
+            got = [x.record_stream() for x in cb.Batch.stream_file(p, 900000)]
+            assert b"".join(x[:x.rindex(b"#ret=")] for x in got[:-1]) + got[-1] == want
+            os.environ.pop("CRASS_B200_GZ_SERIAL")
+            # BGZF blocks followed by an ordinary gzip member: not a BGZF archive, zlib reads it all
+            p2 = os.path.join(d, "mixed.fx.gz")
+            with open(p2, "wb") as fh:
+                fh.write(open(p, "rb").read())
+                fh.write(gzip.compress(b">tail\nACGTACGTACGTACGT\n"))
+            got = [x.record_stream() for x in cb.Batch.stream_file(p2, 900000)]
+            assert b"".join(x[:x.rindex(b"#ret=")] for x in got[:-1]) + got[-1] == P.kseq_dump(p2)
+            # a damaged block
+            p3 = os.path.join(d, "bad.fx.gz")
+            _write_bgzf(p3, text, corrupt_block=20)
+            with pytest.raises(cb.CrassB200Error):
+                list(cb.Batch.stream_file(p3, 900000))
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+
+
 def test_parser_streams_a_gz_archive_while_it_inflates():
     """A gz input of a parse stream is inflated by a thread of its own while the ranges that are already there are parsed
     (the reference inflates inside its read loop); the record stream must not depend on how far the inflater is when a range
