@@ -69,7 +69,31 @@ void Batch::reserve_bases(size_t need) {
 
 namespace {
 
-bool inflate_all(const char* path, std::vector<uint8_t>& buf) {
+// zlib drops what a FAILING gzread call had inflated so far.  The reference reads 4096 bytes per call (kseq.cpp:44,60-66) and so
+// keeps everything up to the 4096-byte chunk a damaged stretch of the archive falls into; a reader that asks for megabytes per
+// call goes back over the failed call the reference's way.  `have` (a multiple of 4096) bytes are good; returns the new count.
+size_t reread_like_kseq(const char* path, uint8_t* dst, size_t have, size_t cap, bool* ended_by_error) {
+    *ended_by_error = false;
+    gzFile fp = gzopen(path, "r");
+    if (!fp) return have;
+    if (gzseek(fp, (z_off_t)have, SEEK_SET) == (z_off_t)have) {
+        while (have + 4096 <= cap) {
+            // kstream reads into ONE buffer: when a call fails, what the buffer's first byte holds -- zlib may have copied part of
+            // the chunk before it met the damage, else it is still the previous chunk's -- is what ks_getc hands out (see Cursor).
+            // dst[have] plays that byte.
+            if (have >= 4096) dst[have] = dst[have - 4096];
+            const int r = gzread(fp, dst + have, 4096);
+            if (r < 0) { *ended_by_error = true; break; }
+            have += (size_t)r;
+            if (r < 4096) break;
+        }
+    }
+    gzclose(fp);
+    return have;
+}
+
+bool inflate_all(const char* path, std::vector<uint8_t>& buf, bool* read_error) {
+    *read_error = false;
     gzFile fp = (strcmp(path, "-") == 0) ? gzdopen(fileno(stdin), "r") : gzopen(path, "r");
     if (!fp) return false;
     gzbuffer(fp, 1 << 20);
@@ -80,10 +104,11 @@ bool inflate_all(const char* path, std::vector<uint8_t>& buf) {
         size_t want = buf.size() - n;
         if (want > (1u << 30)) want = 1u << 30;
         int r = gzread(fp, buf.data() + n, (unsigned)want);
+        if (r < 0 && strcmp(path, "-") != 0 && n % 4096 == 0) { gzclose(fp); fp = nullptr; n = reread_like_kseq(path, buf.data(), n, buf.size(), read_error); break; }
         if (r <= 0) break;
         n += (size_t)r;
     }
-    gzclose(fp);
+    if (fp) gzclose(fp);
     buf.resize(n);
     return true;
 }
@@ -104,6 +129,7 @@ struct Input {
     std::thread inflater;
     std::atomic<size_t> avail{0};
     std::atomic<bool> inflate_done{false}, inflate_failed{false};
+    std::atomic<bool> read_error{false};           // the input ended with a failed read (a damaged archive): see Cursor
     bool incremental = false;
     size_t vcap = 0;
     size_t expect_size = 0;                        // BGZF: the inflated size, known from the block trailers before anything is inflated
@@ -230,7 +256,7 @@ struct Input {
         map = m; map_len = vcap; data = (const uint8_t*)m; size = 0; incremental = true;
         const std::string p = path;
         // (tests shrink the inflater's step and the parser's margin so that ranges are cut while the stream is still arriving)
-        const size_t step = std::min<size_t>((size_t)8 << 20, std::max<size_t>(4096, env_size_early("CRASS_B200_GZ_STREAM_MARGIN", (size_t)8 << 20)));
+        const size_t step = std::min<size_t>((size_t)8 << 20, std::max<size_t>(4096, env_size_early("CRASS_B200_GZ_STREAM_MARGIN", (size_t)8 << 20))) & ~(size_t)4095;
         inflater = std::thread([this, p, step]() {
             gzFile fp = gzopen(p.c_str(), "r");
             if (!fp) { inflate_failed.store(true); inflate_done.store(true); return; }
@@ -240,11 +266,19 @@ struct Input {
                 const size_t want = std::min<size_t>(step, vcap - nread);
                 if (!want) { inflate_failed.store(true); break; }                  // more than 64 x the archive: give up loudly
                 const int r = gzread(fp, (uint8_t*)map + nread, (unsigned)want);
+                if (r < 0 && nread % 4096 == 0) {                                  // a damaged archive: up to where the reference reads it
+                    gzclose(fp); fp = nullptr;
+                    bool by_error = false;
+                    nread = reread_like_kseq(p.c_str(), (uint8_t*)map, nread, vcap, &by_error);
+                    read_error.store(by_error, std::memory_order_release);
+                    avail.store(nread, std::memory_order_release);
+                    break;
+                }
                 if (r <= 0) break;
                 nread += (size_t)r;
                 avail.store(nread, std::memory_order_release);
             }
-            gzclose(fp);
+            if (fp) gzclose(fp);
             inflate_done.store(true, std::memory_order_release);
         });
         return true;
@@ -285,8 +319,37 @@ struct Input {
                 }
             } else ::close(fd);
         }
-        if (!inflate_all(path, inflated)) return false;
+        if (strcmp(path, "-") != 0 && !getenv("CRASS_B200_GZ_SERIAL") && open_bgzf_now(path)) return true;
+        bool by_error = false;
+        if (!inflate_all(path, inflated, &by_error)) return false;
+        read_error.store(by_error);
         data = inflated.data(); size = inflated.size();
+        return true;
+    }
+    // a BGZF archive, inflated on several threads before returning (the whole-file form of what open_streaming starts)
+    bool open_bgzf_now(const char* path) {
+        const int cfd = ::open(path, O_RDONLY);
+        struct stat st;
+        if (cfd < 0 || fstat(cfd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 28) { if (cfd >= 0) ::close(cfd); return false; }
+        void* cm = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, cfd, 0);
+        ::close(cfd);
+        if (cm == MAP_FAILED) return false;
+        std::vector<BgzfBlock> blocks;
+        size_t total = 0;
+        if (!bgzf_index((const uint8_t*)cm, (size_t)st.st_size, blocks, &total) || total < ((size_t)1 << 20)) { munmap(cm, (size_t)st.st_size); return false; }
+        const size_t len = total + 4096;
+        void* m = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (m == MAP_FAILED) { munmap(cm, (size_t)st.st_size); return false; }
+        cmap = cm; cmap_len = (size_t)st.st_size; map = m; map_len = len; expect_size = total;
+        unsigned hw = std::thread::hardware_concurrency();
+        inflate_bgzf(std::move(blocks), (unsigned)std::max<size_t>(1, env_size_early("CRASS_B200_GZ_THREADS", std::max<unsigned>(2, std::min<unsigned>(16, hw > 2 ? hw - 2 : 1)))));
+        if (inflate_failed.load()) {                                             // a damaged block: let zlib say how far the archive reads
+            munmap(map, map_len); map = nullptr; map_len = 0;
+            munmap(cmap, cmap_len); cmap = nullptr; cmap_len = 0;
+            inflate_failed.store(false); inflate_done.store(false); avail.store(0); expect_size = 0;
+            return false;
+        }
+        data = (const uint8_t*)map; size = total;
         return true;
     }
 };
@@ -295,12 +358,18 @@ struct Input {
 // multiple of 4096 that flag is still clear after the last byte has been consumed, and the first ks_getuntil called there
 // returns an empty string instead of -1 (kseq.cpp:71-92) -- one extra record with an empty name and an empty sequence when
 // the last byte of such an input is a header character.  With the whole input in memory that state is one bit.
+// A FAILED read (gzread returns -1 on a damaged archive) is taken for a short one by kstream: end = -1 sets is_eof, but only
+// end == 0 makes ks_getc return -1 -- the ks_getc that meets the failure hands out buf[0] of the last good 4096-byte chunk once
+// more before the stream ends (or, if zlib had copied part of the failing chunk into the buffer, that chunk's first byte), while a
+// ks_getuntil in that place copies nothing and leaves begin = 1 (kseq.cpp:55-69,84-96).
 struct Cursor {
     const uint8_t* p; size_t n, pos;
     bool is_eof;
+    bool read_error = false, stale_done = false;
     Cursor(const uint8_t* p_, size_t n_, size_t pos_) : p(p_), n(n_), pos(pos_), is_eof(n_ % 4096 != 0) {}
     int getc() {                                                          // ks_getc (kseq.cpp:55-69)
         if (pos < n) return (int)(signed char)p[pos++];
+        if (read_error && !stale_done && !is_eof && n >= 4096) { stale_done = true; is_eof = true; return (int)(signed char)p[n]; }   // (reread_like_kseq left it there)
         is_eof = true;
         return -1;
     }
@@ -365,6 +434,7 @@ bool get_until(Cursor& c, int delimiter, size_t& b, size_t& e, int& dret) {
     if (c.pos >= c.n) {
         if (c.is_eof) return false;
         c.is_eof = true;                                                  // the refill that finds nothing happens inside this call
+        c.stale_done = true;
         b = e = c.n;
         return true;
     }
@@ -390,7 +460,7 @@ bool get_until(Cursor& c, int delimiter, size_t& b, size_t& e, int& dret) {
 found_space:
 #endif
     b = c.pos; e = i;
-    if (i < c.n) { dret = (int)(signed char)c.p[i]; c.pos = i + 1; } else { c.pos = c.n; c.is_eof = true; }
+    if (i < c.n) { dret = (int)(signed char)c.p[i]; c.pos = i + 1; } else { c.pos = c.n; c.is_eof = true; c.stale_done = true; }
     return true;
 }
 
@@ -475,8 +545,9 @@ struct Piece {
 
 // The reference's read loop (libcrispr.cpp:96 over kseq_read, kseq.cpp:171-225) from the header character at `start`
 // (start == SIZE_MAX: from the top of the file, looking for the first header) until a header at or past `stop`.
-void parse_span(const uint8_t* data, size_t n, size_t start, size_t stop, Piece& P) {
+void parse_span(const uint8_t* data, size_t n, size_t start, size_t stop, Piece& P, bool read_error = false) {
     Cursor c(data, n, 0);
+    c.read_error = read_error;
     int last_char = 0;
     if (start != (size_t)-1) { c.pos = start + 1; last_char = (int)(signed char)data[start]; }
     int64_t cur_comment = -1, cur_qual = -1;
@@ -509,8 +580,10 @@ void parse_span(const uint8_t* data, size_t n, size_t start, size_t stop, Piece&
                 P.room(nb + (i - c.pos), nb);
                 memcpy(P.bases + nb, c.p + c.pos, i - c.pos); nb += i - c.pos; c.pos = i;
             }
+            const bool at_end = c.pos >= c.n;
             ch = c.getc();
             if (ch == -1 || ch == '>' || ch == '+' || ch == '@') break;
+            if (at_end && c_isgraph(ch)) { P.room(nb + 1, nb); P.bases[nb++] = (uint8_t)ch; }   // (the byte a failed read hands out again, see Cursor)
         }
         if (ch == '>' || ch == '@') last_char = ch;
         const uint64_t L = nb - seq_b;
@@ -525,8 +598,11 @@ void parse_span(const uint8_t* data, size_t n, size_t start, size_t stop, Piece&
                 uint64_t ql = 0;
                 // kseq: while ((c = getc()) != -1 && qual.l < seq.l) if (c >= 33 && c <= 127) append(c);  -- the byte
                 // is fetched before the length test, so one byte past the last quality character is consumed
-                while ((ch = c.getc()) != -1 && ql < L) {
+                for (;;) {
+                    const bool at_end = c.pos >= c.n;
+                    if ((ch = c.getc()) == -1 || !(ql < L)) break;
                     if (ch < 33) continue;                             // (signed) also skips bytes >= 0x80
+                    if (at_end) { const char one = (char)ch; P.text_append(&one, &one + 1, false); ql += 1; continue; }   // (see Cursor)
                     const size_t lim = c.pos + (size_t)(L - ql - 1) < c.n ? c.pos + (size_t)(L - ql - 1) : c.n;
                     const size_t i = qual_run_end(c.p, c.pos, lim);     // the rest of this run of quality characters
                     P.text_append((const char*)c.p + c.pos - 1, (const char*)c.p + i, false);   // (ch is the byte before pos)
@@ -609,7 +685,7 @@ struct RangeCarry {
     int status = 0;                                       // 0: more records follow; -1 / -2: the stream ended in this range
 };
 
-struct View { const uint8_t* data; size_t size; };     // the input's bytes as far as a range may look
+struct View { const uint8_t* data; size_t size; bool read_error = false; };     // the input's bytes as far as a range may look (read_error: they end with a failed read)
 
 // What a streamed input keeps from one range to the next: the scratch mapping the pieces write their bases to and the pieces'
 // own vectors.  Fresh memory for them (a few hundred MB per range) costs a page fault per 4 KB on the way in and a munmap on the
@@ -658,7 +734,7 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
         B->reserve_bases(n + 16);
         Piece P;
         P.bases = B->bases; P.cap = B->bases_cap;
-        parse_span(in.data, n, (size_t)-1, (size_t)-1, P);
+        parse_span(in.data, n, (size_t)-1, (size_t)-1, P, in.read_error);
         B->name_pool.swap(P.name_pool); B->text_pool.swap(P.text_pool);   // piece-relative == batch-relative here
         B->name_off.swap(P.name_off); B->comment_off.swap(P.comment_off); B->qual_off.swap(P.qual_off);
         B->offsets.reserve(P.ends.size() + 1);
@@ -708,7 +784,7 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
                 P.bases = scratch + (from - first) + (in_place ? 0 : 64 * k);
                 if (in_place) { P.text_ext = text0 + (from - first); P.text_cap = P.cap; }
                 P.expect(P.cap);
-                parse_span(in.data, n, k ? from : start, stop, P);
+                parse_span(in.data, n, k ? from : start, stop, P, in.read_error);
             } catch (...) { failed.store(true); }
         }
     };
@@ -750,7 +826,7 @@ void parse_range(const View& in, size_t start, size_t stop_hint, const RangeCarr
             Q->bases = (uint8_t*)malloc(Q->cap);
             if (!Q->bases) throw std::bad_alloc();
         }
-        parse_span(in.data, n, hp, stop, *Q);
+        parse_span(in.data, n, hp, stop, *Q, in.read_error);
         cur = Q.get();
         patches.push_back(std::move(Q));
     }
@@ -852,7 +928,7 @@ int parse_file(const char* path, Batch** out, Batch* reuse) {
     if (!in.open(path)) return fail(CRASS_B200_EIO, std::string("cannot open ") + path);
     Batch* B = reuse ? reuse : new Batch();
     try {
-        parse_range(View{in.data, in.size}, (size_t)-1, (size_t)-1, nullptr, B, nullptr);
+        parse_range(View{in.data, in.size, in.read_error.load()}, (size_t)-1, (size_t)-1, nullptr, B, nullptr);
     } catch (std::exception& ex) {
         if (!reuse) delete B;
         return fail(CRASS_B200_ENOMEM, std::string("parse_file: ") + ex.what());
@@ -896,7 +972,7 @@ int parse_stream_next(ParseStream* s, Batch* reuse) {
             const size_t have = s->in.wait_for(first + s->range_bytes + margin, &final_size);
             if (s->in.inflate_failed.load()) throw std::runtime_error("gz stream could not be inflated");
             const bool to_end = !s->range_bytes || (final_size && first + s->range_bytes + (s->range_bytes >> 2) >= have);
-            parse_range(View{s->in.data, have}, start, to_end ? (size_t)-1 : first + s->range_bytes, s->started ? &s->carry : nullptr, reuse, &out, &s->arena);
+            parse_range(View{s->in.data, have, final_size && s->in.read_error.load(std::memory_order_acquire)}, start, to_end ? (size_t)-1 : first + s->range_bytes, s->started ? &s->carry : nullptr, reuse, &out, &s->arena);
             if (final_size || (out.status == 0 && out.next_hp != (size_t)-1)) break;
             margin *= 4;                                              // the view ended inside a record: wait for more of it
         }

@@ -485,14 +485,20 @@ typedef struct {
     kstr name, comment, seq, qual;
     int last_char;
     int is_eof;                                       /* kstream's flag: a read of its 4096-byte buffer came back short */
+    int read_error, stale_done;                       /* the input ended with a FAILED read (a damaged archive), see kp_getc */
 } kparser;
 
 /* kstream refills a 4096-byte buffer and learns about the end of the input from a SHORT read: when the input's size is a
  * multiple of 4096 the flag is still clear after the last byte has been consumed, and the first ks_getuntil called there
  * returns an empty string instead of -1 (kseq.cpp:71-92) -- one extra record with an empty name and an empty sequence when
  * the last byte is a header character.  With the whole input in memory that state is one bit. */
+/* A failed gzread (-1, a damaged archive) is taken for a short read by kstream: end = -1 sets is_eof, but only end == 0 makes
+ * ks_getc return -1 (kseq.cpp:55-69) -- so the ks_getc that meets the failure hands out buf[0] once more before the stream ends:
+ * the first byte of the last good 4096-byte chunk, or of the failing one if zlib had copied part of it before it met the damage
+ * (kp_open leaves that byte at buf[n]); ks_getuntil (kseq.cpp:84-96) copies nothing in that state and leaves begin = 1. */
 static int kp_getc(kparser* k) {
     if (k->pos < k->n) return (int)(signed char)k->buf[k->pos++];
+    if (k->read_error && !k->stale_done && !k->is_eof && k->n >= 4096) { k->stale_done = 1; k->is_eof = 1; return (int)(signed char)k->buf[k->n]; }
     k->is_eof = 1;
     return -1;
 }
@@ -506,6 +512,7 @@ static int kp_getuntil(kparser* k, int delimiter, kstr* str, int* dret) {
     if (k->pos >= k->n) {
         if (k->is_eof) return -1;
         k->is_eof = 1;                                /* the refill that finds nothing happens inside this call */
+        k->stale_done = 1;
         ks_put(str, 1);
         str->s[0] = 0;
         return 0;
@@ -516,7 +523,7 @@ static int kp_getuntil(kparser* k, int delimiter, kstr* str, int* dret) {
     ks_put(str, i - k->pos + 1);
     memcpy(str->s, k->buf + k->pos, i - k->pos);
     str->l = i - k->pos;
-    if (i < k->n) { if (dret) *dret = (int)(signed char)k->buf[i]; k->pos = i + 1; } else { k->pos = i; k->is_eof = 1; }
+    if (i < k->n) { if (dret) *dret = (int)(signed char)k->buf[i]; k->pos = i + 1; } else { k->pos = i; k->is_eof = 1; k->stale_done = 1; }
     str->s[str->l] = 0;
     return (int)str->l;
 }
@@ -557,11 +564,14 @@ static int kp_open(kparser* k, const char* path) {
     if (!fp) return -1;
     size_t cap = 1 << 20;
     k->buf = (uint8_t*)malloc(cap);
-    for (;;) {
+    for (;;) {                                        /* 4096 bytes per call, as kstream reads (kseq.cpp:44,60-66): what a damaged archive
+                                                         yields depends on it (zlib drops what a failing call had inflated) */
         if (cap - k->n < (1 << 19)) { cap *= 2; k->buf = (uint8_t*)realloc(k->buf, cap); }
-        int r = gzread(fp, k->buf + k->n, (unsigned)((cap - k->n) > (1u << 30) ? (1u << 30) : (cap - k->n)));
-        if (r <= 0) break;
+        if (k->n >= 4096) k->buf[k->n] = k->buf[k->n - 4096];   /* kstream has ONE buffer: a failing call leaves its first byte or overwrites it */
+        int r = gzread(fp, k->buf + k->n, 4096);
+        if (r < 0) { k->read_error = 1; break; }
         k->n += (size_t)r;
+        if (r < 4096) break;                          /* is_eof: kstream does not read again */
     }
     gzclose(fp);
     k->is_eof = k->n % 4096 != 0;                     /* the short read has happened by the time the last byte is consumed */

@@ -248,6 +248,7 @@ def test_parser_inflates_a_bgzf_archive_on_several_threads():
                 os.environ["CRASS_B200_GZ_THREADS"] = threads
                 got = [x.record_stream() for x in cb.Batch.stream_file(p, range_bytes)]
                 assert b"".join(x[:x.rindex(b"#ret=")] for x in got[:-1]) + got[-1] == want, (threads, range_bytes)
+            assert cb.Batch.from_file(p).record_stream() == want         # the whole-file form inflates BGZF in parallel too
             os.environ["CRASS_B200_GZ_SERIAL"] = "1"                     # the one-thread path on the same archive
             got = [x.record_stream() for x in cb.Batch.stream_file(p, 900000)]
             assert b"".join(x[:x.rindex(b"#ret=")] for x in got[:-1]) + got[-1] == want
@@ -264,6 +265,7 @@ def test_parser_inflates_a_bgzf_archive_on_several_threads():
             _write_bgzf(p3, text, corrupt_block=20)
             with pytest.raises(cb.CrassB200Error):
                 list(cb.Batch.stream_file(p3, 900000))
+            assert cb.Batch.from_file(p3).record_stream() == P.kseq_dump(p3)   # whole file: falls back to zlib, which reads up to the damage
         finally:
             for k, v in old.items():
                 if v is None:

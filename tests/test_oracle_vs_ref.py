@@ -256,3 +256,50 @@ def test_the_step_between_the_phases_is_the_references_own_code(R, P):
         for other in (restated, port):
             assert [l for l in real.split("\n") if l.startswith("G")] == [l for l in other.split("\n") if l.startswith("G")]
             assert sorted(l for l in real.split("\n") if l.startswith("P")) == sorted(l for l in other.split("\n") if l.startswith("P"))
+
+
+def test_kseq_on_damaged_archives(R, P, tmp_path):
+    """A gzread that FAILS (a damaged archive) is taken for a short read by kstream (kseq.cpp:55-96): the stream ends at the
+    4096-byte call that met the damage, and the ks_getc that met it hands out the read buffer's first byte once more.  The port
+    and the product's parser restate that; both must give the reference's record stream, byte for byte -- ordinary gzip
+    archives and BGZF ones, damage in names, sequences and qualities."""
+    import gzip
+    import crass_b200 as cb
+    from test_host_logic import _write_bgzf
+    rng = random.Random(21)
+    parts = []
+    for k in range(12000):
+        seq = fuzzgen.rand_seq(rng, rng.randint(30, 150)).decode()
+        if rng.random() < 0.5:
+            parts.append("@r%d c%d\n%s\n+\n%s\n" % (k, k, seq, "".join(rng.choice("!5I@>F") for _ in seq)))
+        else:
+            parts.append(">r%d\n%s\n" % (k, seq))
+    text = "".join(parts).encode()
+    plain = gzip.compress(text, compresslevel=6)
+    cases = 0
+    old = {k: os.environ.get(k) for k in ("CRASS_B200_GZ_STREAM_MIN", "CRASS_B200_GZ_SERIAL")}
+    os.environ["CRASS_B200_GZ_STREAM_MIN"] = "1"
+    try:
+        for it in range(10):
+            p = str(tmp_path / ("bad%d.fx.gz" % it))
+            if it % 2 == 0:
+                at = rng.randint(len(plain) // 10, len(plain) - 100)
+                with open(p, "wb") as fh:
+                    fh.write(plain[:at] + bytes([plain[at] ^ (1 << rng.randint(0, 7))]) + plain[at + 1:])
+            else:
+                _write_bgzf(p, text, corrupt_block=rng.randint(1, len(text) // 0xff00 - 1))
+            want = R.kseq_dump(p)
+            assert P.kseq_dump(p) == want, it
+            assert cb.Batch.from_file(p).record_stream() == want, it           # (a damaged BGZF archive falls back to zlib's read)
+            os.environ["CRASS_B200_GZ_SERIAL"] = "1"                           # streamed, through zlib (the parallel BGZF reader fails loudly instead)
+            got = [x.record_stream() for x in cb.Batch.stream_file(p, 300000)]
+            os.environ.pop("CRASS_B200_GZ_SERIAL")
+            assert b"".join(x[:x.rindex(b"#ret=")] for x in got[:-1]) + got[-1] == want, it
+            cases += 1
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert cases == 10
