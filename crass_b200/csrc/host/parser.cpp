@@ -138,6 +138,7 @@ struct Input {
     // trailers before it.  Any other gzip file is one deflate stream, and one thread (zlib) is all that can work on it.
     struct BgzfBlock { size_t cpos, clen, out; uint32_t isize, crc; };
     void* cmap = nullptr; size_t cmap_len = 0;     // the archive itself, mapped (BGZF only)
+    std::string bgzf_path;                         // set by open_streaming: a damaged block is then read again through zlib
     static bool bgzf_index(const uint8_t* c, size_t n, std::vector<BgzfBlock>& blocks, size_t* total) {
         size_t pos = 0, out = 0;
         while (pos < n) {
@@ -170,7 +171,7 @@ struct Input {
         const size_t group = 32, n_groups = (blocks.size() + group - 1) / group;
         std::vector<std::atomic<uint8_t> > done(n_groups);
         for (auto& d : done) d.store(0);
-        std::atomic<size_t> next{0};
+        std::atomic<size_t> next{0}, first_bad{(size_t)-1};
         std::mutex lead_mu;
         size_t lead = 0;
         auto work = [&]() {
@@ -187,8 +188,14 @@ struct Input {
                     z.next_in = const_cast<Bytef*>(c + k.cpos); z.avail_in = (uInt)k.clen;
                     z.next_out = dst; z.avail_out = k.isize;
                     const int r = inflate(&z, Z_FINISH);
-                    if (r != Z_STREAM_END || z.total_out != k.isize || (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, k.isize) != k.crc) { inflate_failed.store(true); break; }
+                    if (r != Z_STREAM_END || z.total_out != k.isize || (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, k.isize) != k.crc) {
+                        size_t cur = first_bad.load();
+                        while (b < cur && !first_bad.compare_exchange_weak(cur, b)) {}
+                        inflate_failed.store(true);
+                        break;
+                    }
                 }
+                if (inflate_failed.load()) break;                                // (this group or another: nothing past a damaged block is handed out)
                 done[g].store(1, std::memory_order_release);
                 std::lock_guard<std::mutex> l(lead_mu);
                 while (lead < n_groups && done[lead].load(std::memory_order_acquire)) ++lead;
@@ -200,9 +207,17 @@ struct Input {
         for (unsigned t = 1; t < n_threads; ++t) pool.emplace_back(work);
         work();
         for (auto& t : pool) t.join();
-        if (inflate_failed.load()) {                                             // what is usable is what came before the bad block
-            std::lock_guard<std::mutex> l(lead_mu);
-            avail.store(lead < n_groups ? blocks[lead * group].out : expect_size, std::memory_order_release);
+        if (inflate_failed.load() && !bgzf_path.empty()) {
+            // A damaged block.  Everything before it is in place; how far INTO it the reference would read depends on zlib's
+            // buffering and kstream's 4096-byte calls, so that stretch is read again the reference's way (reread_like_kseq
+            // inflates from the top of the archive to get there: slow, but only a damaged archive pays).
+            const size_t bad = first_bad.load();
+            size_t have = (bad < blocks.size() ? blocks[bad].out : expect_size) & ~(size_t)4095;
+            bool by_error = false;
+            have = reread_like_kseq(bgzf_path.c_str(), (uint8_t*)map, have, vcap, &by_error);
+            read_error.store(by_error, std::memory_order_release);
+            avail.store(have, std::memory_order_release);
+            inflate_failed.store(false);
         }
         inflate_done.store(true, std::memory_order_release);
     }
@@ -241,6 +256,7 @@ struct Input {
                         madvise(m, vcap, MADV_HUGEPAGE);
                         cmap = cm; cmap_len = (size_t)st.st_size;
                         map = m; map_len = vcap; data = (const uint8_t*)m; size = 0; incremental = true; expect_size = total;
+                        bgzf_path = path;
                         unsigned hw = std::thread::hardware_concurrency();
                         const unsigned nt = (unsigned)std::max<size_t>(1, env_size_early("CRASS_B200_GZ_THREADS", std::max<unsigned>(2, std::min<unsigned>(16, hw > 2 ? hw - 2 : 1))));
                         inflater = std::thread([this, nt](std::vector<BgzfBlock> bl) { inflate_bgzf(std::move(bl), nt); }, std::move(blocks));
