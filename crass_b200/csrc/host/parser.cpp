@@ -109,7 +109,9 @@ bool inflate_all(const char* path, std::vector<uint8_t>& buf, bool* read_error) 
         n += (size_t)r;
     }
     if (fp) gzclose(fp);
-    buf.resize(n);
+    const uint8_t after = n < buf.size() ? buf[n] : 0;
+    buf.resize(n + 1);                                                    // (one byte past the input: what Cursor hands out after a failed read)
+    buf[n] = after;
     return true;
 }
 
@@ -339,7 +341,7 @@ struct Input {
         bool by_error = false;
         if (!inflate_all(path, inflated, &by_error)) return false;
         read_error.store(by_error);
-        data = inflated.data(); size = inflated.size();
+        data = inflated.data(); size = inflated.size() - 1;
         return true;
     }
     // a BGZF archive, inflated on several threads before returning (the whole-file form of what open_streaming starts)
