@@ -520,3 +520,30 @@ def test_automaton_shape():
     assert ac.table_bytes == ac.num_states * 4 * 4
     with pytest.raises(cb.CrassB200Error):
         cb.Automaton([])
+
+
+def test_parser_records_longer_than_pieces_and_ranges():
+    """Contig-sized records: a record may span many pieces and several ranges' worth of bytes.  Pieces that begin inside it are
+    dropped, the piece that holds its header overruns its slice of the shared buffer and goes on in a buffer of its own, a
+    range ends on the next true record start however far that is."""
+    rng = random.Random(3)
+    P = checkers.port()
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "contigs.fa")
+        with open(p, "w") as fh:
+            for k in range(10):
+                L = rng.choice([50, 2000, 150000, 400000, 700000])
+                seq = "".join(rng.choice("ACGT") for _ in range(L))
+                if k % 3 == 0:
+                    fh.write(">c%d single line\n%s\n" % (k, seq))
+                else:
+                    fh.write(">c%d\n%s\n" % (k, "\n".join(seq[i:i + 60] for i in range(0, L, 60))))
+        want = P.kseq_dump(p)
+        for chunk, range_bytes in ((100000, 350000), (5000, 20000), (300000, 0)):
+            old = _pieces_env(chunk)
+            try:
+                assert cb.Batch.from_file(p).record_stream() == want, chunk
+                got = [x.record_stream() for x in cb.Batch.stream_file(p, range_bytes)]
+                assert b"".join(x[:x.rindex(b"#ret=")] for x in got[:-1]) + got[-1] == want, (chunk, range_bytes)
+            finally:
+                _restore_env(old)
