@@ -547,3 +547,63 @@ def test_parser_records_longer_than_pieces_and_ranges():
                 assert b"".join(x[:x.rindex(b"#ret=")] for x in got[:-1]) + got[-1] == want, (chunk, range_bytes)
             finally:
                 _restore_env(old)
+
+
+def test_parser_own_inflate_against_zlib():
+    """An ordinary .gz of a streamed input is inflated by the library's own DEFLATE decoder (fast_inflate.h; zlib when it gives
+    up).  Archives that exercise every block type and header field -- stored, fixed and dynamic Huffman blocks, Huffman-only /
+    RLE / filtered strategies, a 512-byte window, sync and full flushes, several members (an empty one among them), a member
+    with a file name, trailing garbage, a truncated archive -- must give the record stream zlib's gzread gives."""
+    import io
+    import zlib
+    rng = random.Random(31)
+    P = checkers.port()
+    parts = []
+    for k in range(9000):
+        seq = fuzzgen.rand_seq(rng, rng.randint(30, 150)).decode()
+        if rng.random() < 0.6:
+            parts.append("@read%d/1 x\n%s\n+\n%s\n" % (k, seq, "".join(rng.choice("FFFFFFF:,#") for _ in seq)))
+        else:
+            parts.append(">r%d\n%s\n" % (k, seq * rng.choice([1, 1, 3])))
+    text = "".join(parts).encode()
+    archives = {}
+    for lvl in (0, 1, 6, 9):
+        archives["level%d" % lvl] = gzip.compress(text, compresslevel=lvl)
+    for strat, nm in ((zlib.Z_FIXED, "fixed"), (zlib.Z_HUFFMAN_ONLY, "huffman"), (zlib.Z_RLE, "rle"), (zlib.Z_FILTERED, "filtered")):
+        c = zlib.compressobj(6, zlib.DEFLATED, 31, 8, strat)
+        archives[nm] = c.compress(text) + c.flush()
+    c = zlib.compressobj(6, zlib.DEFLATED, 25)
+    archives["window512"] = c.compress(text) + c.flush()
+    c = zlib.compressobj(6, zlib.DEFLATED, 31)
+    buf = b""
+    for i in range(0, len(text), 7001):
+        buf += c.compress(text[i:i + 7001]) + c.flush(zlib.Z_SYNC_FLUSH if (i // 7001) % 2 else zlib.Z_FULL_FLUSH)
+    archives["flushes"] = buf + c.flush()
+    third = len(text) // 3
+    archives["members"] = gzip.compress(text[:third]) + gzip.compress(b"") + gzip.compress(text[third:2 * third], 1) + gzip.compress(text[2 * third:], 0)
+    b = io.BytesIO()
+    with gzip.GzipFile(filename="reads.fq", mode="wb", fileobj=b, mtime=12345) as g:
+        g.write(text)
+    archives["named"] = b.getvalue()
+    archives["garbage"] = gzip.compress(text) + b"\0\0\0\0 not gzip"
+    archives["truncated"] = gzip.compress(text)[:len(gzip.compress(text)) // 2]
+    keys = ("CRASS_B200_GZ_STREAM_MIN", "CRASS_B200_GZ_SERIAL", "CRASS_B200_PARSE_CHUNK", "CRASS_B200_PARSE_THREADS")
+    old = {k: os.environ.get(k) for k in keys}
+    os.environ.update(CRASS_B200_GZ_STREAM_MIN="1", CRASS_B200_PARSE_CHUNK="100000", CRASS_B200_PARSE_THREADS="4")
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            for name, data in archives.items():
+                p = os.path.join(d, name + ".fx.gz")
+                with open(p, "wb") as fh:
+                    fh.write(data)
+                want = P.kseq_dump(p)
+                assert len(want) > 100000, name
+                for range_bytes in (250000, 0):
+                    got = [x.record_stream() for x in cb.Batch.stream_file(p, range_bytes)]
+                    assert b"".join(x[:x.rindex(b"#ret=")] for x in got[:-1]) + got[-1] == want, (name, range_bytes)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
