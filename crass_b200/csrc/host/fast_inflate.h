@@ -165,7 +165,7 @@ struct Reader {
     inline uint32_t take(unsigned k) { const uint32_t v = peek(k); drop(k); return v; }
 };
 
-// One gzip archive (all its members) from [in, in+in_len) to out (room for out_cap bytes, of which 16 may be scribbled on past the
+// One gzip archive (all its members) from [in, in+in_len) to out (room for out_cap bytes, of which 32 may be scribbled on past the
 // data).  `progress(bytes)` is called as the output grows (after every block).  Returns the output size, or (size_t)-1 when
 // the decoder gave up -- *good then says how much output belongs to members that were completed and CRC-checked.
 template <class Progress>
@@ -254,7 +254,7 @@ inline size_t gunzip(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_
                 if (!build_table(lens + 288, btype == 1 ? 32 : ndist, kDistBits, T->dist, 256 + 3840, dist_payload)) return kFail;
                 // ---- the symbols of the block
                 for (;;) {
-                    if (out_cap - o < 258 + 16 + 2 || r.past > 16) return kFail;
+                    if (out_cap - o < 258 + 32 + 2 || r.past > 16) return kFail;
                     r.refill();
                     uint32_t e = T->lit[r.peek(kLitBits)];
                     if (e & kLiteralFlag) {                                  // up to three literals from one refill (a codeword has 15 bits at most)
@@ -272,7 +272,7 @@ inline size_t gunzip(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_
                     if (kind == 0) { out[o++] = (uint8_t)(e >> 16); continue; }   // (a literal with a long codeword)
                     if (kind == 2) break;
                     if (kind != 1) return kFail;
-                    if (r.n < 5 + 15 + 13) r.refill();
+                    r.refill();                                              // (unconditional: cheaper than a branch that depends on what came before)
                     const uint32_t length = (e >> 16) + r.take((e >> 8) & 15u);
                     uint32_t d = T->dist[r.peek(kDistBits)];
                     if (((d >> kKindShift) & 7u) == 3u) { r.drop(kDistBits); d = T->dist[(d >> 16) + r.peek((d >> 8) & 15u)]; }
@@ -283,9 +283,15 @@ inline size_t gunzip(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_
                     uint8_t* dst = out + o;
                     const uint8_t* src = dst - dist;
                     o += length;
-                    if (dist >= 8) {
-                        uint8_t* const stop = dst + length;
-                        do { uint64_t w; memcpy(&w, src, 8); memcpy(dst, &w, 8); src += 8; dst += 8; } while (dst < stop);
+                    if (dist >= 8) {                                        // sixteen bytes without asking (a match is 9 bytes on average), more in a loop
+                        uint64_t w;
+                        memcpy(&w, src, 8); memcpy(dst, &w, 8);
+                        memcpy(&w, src + 8, 8); memcpy(dst + 8, &w, 8);
+                        if (length > 16) {
+                            uint8_t* const stop = dst + length;
+                            src += 16; dst += 16;
+                            do { memcpy(&w, src, 8); memcpy(dst, &w, 8); src += 8; dst += 8; } while (dst < stop);
+                        }
                     } else if (dist == 1) {
                         memset(dst, *src, length);
                     } else {
