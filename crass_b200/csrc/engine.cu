@@ -289,9 +289,12 @@ int upload_shard(Lane& l, const cbh::Batch& b, Shard& s) {
             }
         };
         std::thread helpers[kThreads - 1];
-        for (int t = 1; t < kThreads; ++t) helpers[t - 1] = std::thread(run, t);
+        bool started[kThreads - 1] = {};
+        for (int t = 1; t < kThreads; ++t) {
+            try { helpers[t - 1] = std::thread(run, t); started[t - 1] = true; } catch (...) {}   // (no thread to be had: its share is done below)
+        }
         run(0);
-        for (auto& h : helpers) h.join();
+        for (int t = 1; t < kThreads; ++t) { if (started[t - 1]) helpers[t - 1].join(); else run(t); }
         if (bad.load()) { (void)cudaGetLastError(); return cbh::fail(CRASS_B200_ECUDA, "staged copy to the device failed"); }
     }
     for (int k = 0; k < 2; ++k) {
