@@ -252,8 +252,73 @@ inline size_t gunzip(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_
                 }
                 if (!build_table(lens, 288, kLitBits, T->lit, 2048 + 4608, lit_payload, kLiteralFlag)) return kFail;
                 if (!build_table(lens + 288, btype == 1 ? 32 : ndist, kDistBits, T->dist, 256 + 3840, dist_payload)) return kFail;
-                // ---- the symbols of the block
-                for (;;) {
+                // ---- the symbols of the block: first with everything in local variables while at least 16 bytes of input and 320
+                //      bytes of room are left (no end-of-input bookkeeping in here), then -- for the tail -- with every check
+                bool block_done = false;
+                {
+                    uint64_t bb = r.buf; unsigned bn = r.n;
+                    const uint8_t* ip = r.p;
+                    uint8_t* op = out + o;
+                    uint8_t* const window0 = out + member_out;
+                    const uint8_t* const ip_safe = (r.end - r.p > 16) ? r.end - 16 : r.p;
+                    uint8_t* const op_safe = out_cap - o > 320 ? out + out_cap - 320 : op;
+                    const uint32_t* const lit = T->lit;
+                    const uint32_t* const dtab = T->dist;
+#define FASTINF_REFILL() do { uint64_t w_; memcpy(&w_, ip, 8); bb |= w_ << bn; ip += (63 - bn) >> 3; bn |= 56; } while (0)
+#define FASTINF_DROP(k_) do { const unsigned d_ = (k_); bb >>= d_; bn -= d_; } while (0)
+                    while (ip < ip_safe && op < op_safe) {
+                        FASTINF_REFILL();
+                        uint32_t e = lit[bb & 2047u];
+                        if (e & kLiteralFlag) {
+                            *op++ = (uint8_t)(e >> 16); FASTINF_DROP(e & 15u);
+                            e = lit[bb & 2047u];
+                            if (e & kLiteralFlag) {
+                                *op++ = (uint8_t)(e >> 16); FASTINF_DROP(e & 15u);
+                                e = lit[bb & 2047u];
+                                if (e & kLiteralFlag) { *op++ = (uint8_t)(e >> 16); FASTINF_DROP(e & 15u); continue; }
+                            }
+                        }
+                        if (((e >> kKindShift) & 7u) == 3u) { FASTINF_DROP(kLitBits); e = lit[(e >> 16) + (uint32_t)(bb & ((1u << ((e >> 8) & 15u)) - 1u))]; }
+                        FASTINF_DROP(e & 15u);
+                        const uint32_t kind = (e >> kKindShift) & 7u;
+                        if (kind == 0) { *op++ = (uint8_t)(e >> 16); continue; }
+                        if (kind == 2) { block_done = true; break; }
+                        if (kind != 1) return kFail;
+                        FASTINF_REFILL();
+                        unsigned xb = (e >> 8) & 15u;
+                        const uint32_t length = (e >> 16) + (uint32_t)(bb & ((1u << xb) - 1u));
+                        FASTINF_DROP(xb);
+                        uint32_t d = dtab[bb & 255u];
+                        if (((d >> kKindShift) & 7u) == 3u) { FASTINF_DROP(kDistBits); d = dtab[(d >> 16) + (uint32_t)(bb & ((1u << ((d >> 8) & 15u)) - 1u))]; }
+                        if (((d >> kKindShift) & 7u) != 0) return kFail;
+                        FASTINF_DROP(d & 15u);
+                        xb = (d >> 8) & 15u;
+                        const uint32_t dist = (d >> 16) + (uint32_t)(bb & ((1u << xb) - 1u));
+                        FASTINF_DROP(xb);
+                        if (dist > (size_t)(op - window0)) return kFail;
+                        uint8_t* dst = op;
+                        const uint8_t* src = op - dist;
+                        op += length;
+                        if (dist >= 8) {
+                            uint64_t w;
+                            memcpy(&w, src, 8); memcpy(dst, &w, 8);
+                            memcpy(&w, src + 8, 8); memcpy(dst + 8, &w, 8);
+                            if (length > 16) {
+                                src += 16; dst += 16;
+                                do { memcpy(&w, src, 8); memcpy(dst, &w, 8); src += 8; dst += 8; } while (dst < op);
+                            }
+                        } else if (dist == 1) {
+                            memset(dst, *src, length);
+                        } else {
+                            for (uint32_t i = 0; i < length; ++i) dst[i] = src[i];
+                        }
+                    }
+#undef FASTINF_REFILL
+#undef FASTINF_DROP
+                    r.buf = bb; r.n = bn; r.p = ip;
+                    o = (size_t)(op - out);
+                }
+                for (; !block_done;) {
                     if (out_cap - o < 258 + 32 + 2 || r.past > 16) return kFail;
                     r.refill();
                     uint32_t e = T->lit[r.peek(kLitBits)];
