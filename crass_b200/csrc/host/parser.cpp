@@ -370,11 +370,30 @@ struct Input {
                 }
             } else ::close(fd);
         }
-        if (strcmp(path, "-") != 0 && !getenv("CRASS_B200_GZ_SERIAL") && open_bgzf_now(path)) return true;
+        if (strcmp(path, "-") != 0 && !getenv("CRASS_B200_GZ_SERIAL") && (open_bgzf_now(path) || open_gz_now(path))) return true;
         bool by_error = false;
         if (!inflate_all(path, inflated, &by_error)) return false;
         read_error.store(by_error);
         data = inflated.data(); size = inflated.size() - 1;
+        return true;
+    }
+    // an ordinary .gz, inflated by the own decoder before returning; whatever that does not accept is left to zlib (inflate_all)
+    bool open_gz_now(const char* path) {
+        const int cfd = ::open(path, O_RDONLY);
+        struct stat st;
+        if (cfd < 0 || fstat(cfd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 18) { if (cfd >= 0) ::close(cfd); return false; }
+        void* cm = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, cfd, 0);
+        ::close(cfd);
+        if (cm == MAP_FAILED) return false;
+        const size_t cap = (size_t)st.st_size * 64 + ((size_t)1 << 30);          // address space only
+        void* m = mmap(nullptr, cap, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (m == MAP_FAILED) { munmap(cm, (size_t)st.st_size); return false; }
+        if ((size_t)st.st_size >= ((size_t)1 << 20)) madvise(m, cap, MADV_HUGEPAGE);
+        size_t good = 0;
+        const size_t total = fastinf::gunzip((const uint8_t*)cm, (size_t)st.st_size, (uint8_t*)m, cap, &good, [](size_t) {});
+        munmap(cm, (size_t)st.st_size);
+        if (total == (size_t)-1) { munmap(m, cap); return false; }
+        map = m; map_len = cap; data = (const uint8_t*)m; size = total;
         return true;
     }
     // a BGZF archive, inflated on several threads before returning (the whole-file form of what open_streaming starts)
