@@ -58,6 +58,9 @@ void Batch::reserve_bases(size_t need) {
     if (need <= bases_cap) return;
     size_t ncap = bases_cap ? bases_cap : (1u << 20);
     while (ncap < need) ncap *= 2;
+    // large buffers in steps of 32 MB instead of powers of two: a 128 MB range needs 134 MB, and what an engine page-locks
+    // (time and locked memory) should be what it uses
+    if (need > ((size_t)64 << 20)) ncap = (need + ((size_t)32 << 20) - 1) & ~(((size_t)32 << 20) - 1);
     bool pin = false;
     uint8_t* nb = (uint8_t*)alloc_host(ncap, &pin, want_pinned);
     if (!nb) throw std::bad_alloc();
