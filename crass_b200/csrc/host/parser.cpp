@@ -142,7 +142,7 @@ struct Input {
     // A BGZF archive (bgzip, htslib: gzip members of at most 64 KB whose extra field says how long each member is) can be inflated
     // by several threads: the block list is read off the headers, every block's place in the output is the sum of the ISIZE
     // trailers before it.  Any other gzip file is one deflate stream, and one thread (zlib) is all that can work on it.
-    struct BgzfBlock { size_t cpos, clen, out; uint32_t isize, crc; };
+    struct BgzfBlock { size_t cpos, clen, out; uint32_t isize, crc; size_t mpos, msize; };   // deflate payload, place in the output, the whole member
     void* cmap = nullptr; size_t cmap_len = 0;     // the archive itself, mapped (BGZF only)
     std::string bgzf_path;                         // set by open_streaming: a damaged block is then read again through zlib
     static bool bgzf_index(const uint8_t* c, size_t n, std::vector<BgzfBlock>& blocks, size_t* total) {
@@ -163,7 +163,7 @@ struct Input {
             const uint32_t crc = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
             const uint32_t isize = t[4] | (t[5] << 8) | (t[6] << 16) | ((uint32_t)t[7] << 24);
             if (isize > (1u << 16)) return false;
-            blocks.push_back(BgzfBlock{pos + 12 + xlen, bsize - 12 - xlen - 8, out, isize, crc});
+            blocks.push_back(BgzfBlock{pos + 12 + xlen, bsize - 12 - xlen - 8, out, isize, crc, pos, bsize});
             out += isize;
             pos += bsize;
         }
@@ -184,12 +184,21 @@ struct Input {
             z_stream z;
             memset(&z, 0, sizeof z);
             if (inflateInit2(&z, -15) != Z_OK) { inflate_failed.store(true); return; }
+            std::vector<uint8_t> tmp((size_t)65536 + 1024);
+            const bool no_fast = getenv("CRASS_B200_GZ_ZLIB_BLOCKS") != nullptr;
             for (;;) {
                 const size_t g = next.fetch_add(1);
                 if (g >= n_groups || inflate_failed.load()) break;
                 for (size_t b = g * group; b < std::min(blocks.size(), (g + 1) * group); ++b) {
                     const BgzfBlock& k = blocks[b];
                     uint8_t* dst = (uint8_t*)map + k.out;
+                    // the own decoder first (it writes a little past its output, so it works in a buffer of the thread and the
+                    // block is copied to its place); zlib for a block it does not accept
+                    if (!no_fast) {
+                        size_t good = 0;
+                        const size_t got = fastinf::gunzip(c + k.mpos, k.msize, tmp.data(), tmp.size(), &good, [](size_t) {});
+                        if (got == (size_t)k.isize) { memcpy(dst, tmp.data(), k.isize); continue; }
+                    }
                     inflateReset(&z);
                     z.next_in = const_cast<Bytef*>(c + k.cpos); z.avail_in = (uInt)k.clen;
                     z.next_out = dst; z.avail_out = k.isize;
