@@ -165,12 +165,199 @@ struct Reader {
     inline uint32_t take(unsigned k) { const uint32_t v = peek(k); drop(k); return v; }
 };
 
+// The blocks of one deflate stream from the reader's position on (RFC 1951), decoded straight into out[o...]; back-references
+// reach down to out[member_out].  Returns 1 after a final block, 0 at the first block boundary at or past stop_bit (a bit
+// position in `in`), -1 when the decoder gives up.
+inline size_t bit_position(const Reader& r, const uint8_t* in) { return (size_t)(r.p - in) * 8 - r.n; }
+
+template <class Progress>
+inline int inflate_blocks(Reader& r, const uint8_t* in, Tables* T, uint8_t* out, size_t& o, size_t out_cap, size_t member_out, size_t stop_bit,
+                          Progress progress, FollowCrc*& follow) {
+    static const uint8_t kOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    for (;;) {
+        r.refill();
+        if (stop_bit != (size_t)-1 && r.past == 0 && bit_position(r, in) >= stop_bit) return 0;
+        const uint32_t bfinal = r.take(1), btype = r.take(2);
+        if (btype == 0) {                                                // stored
+            r.drop(r.n & 7);                                             // to a byte boundary
+            // give the bytes still in the bit buffer back
+            const unsigned back = r.n >> 3;
+            if (r.past > back) return -1;
+            r.p -= (back - r.past); r.buf = 0; r.n = 0; r.past = 0;
+            if (r.end - r.p < 4) return -1;
+            const uint32_t len = r.p[0] | ((uint32_t)r.p[1] << 8), nlen = r.p[2] | ((uint32_t)r.p[3] << 8);
+            if ((len ^ 0xFFFFu) != nlen) return -1;
+            r.p += 4;
+            if ((size_t)(r.end - r.p) < len || out_cap - o < (size_t)len + 16) return -1;
+            memcpy(out + o, r.p, len);
+            r.p += len; o += len;
+        } else if (btype == 1 || btype == 2) {
+            uint8_t lens[320];
+            int nlit, ndist;
+            if (btype == 1) {
+                for (int i = 0; i < 144; ++i) lens[i] = 8;
+                for (int i = 144; i < 256; ++i) lens[i] = 9;
+                for (int i = 256; i < 280; ++i) lens[i] = 7;
+                for (int i = 280; i < 288; ++i) lens[i] = 8;
+                for (int i = 0; i < 32; ++i) lens[288 + i] = 5;
+                nlit = 288; ndist = 32;
+            } else {
+                nlit = (int)r.take(5) + 257; ndist = (int)r.take(5) + 1;
+                const int ncl = (int)r.take(4) + 4;
+                if (nlit > 286 || ndist > 30) return -1;
+                uint8_t cl[19];
+                memset(cl, 0, sizeof cl);
+                for (int i = 0; i < ncl; ++i) { if (r.n < 3) r.refill(); cl[kOrder[i]] = (uint8_t)r.take(3); }
+                uint32_t pre[128 + 64];
+                if (!build_table(cl, 19, 7, pre, 128 + 64, [](int s) { return (uint32_t)s << 16; })) return -1;
+                int i = 0;
+                while (i < nlit + ndist) {
+                    r.refill();
+                    const uint32_t e = pre[r.peek(7)];
+                    if (((e >> kKindShift) & 7u) != 0) return -1;   // (code lengths are at most 7 bits: no sub-tables, no unused codes in use)
+                    r.drop(e & 15u);
+                    const int s = (int)(e >> 16);
+                    if (s < 16) { lens[i++] = (uint8_t)s; continue; }
+                    int rep; uint8_t v = 0;
+                    if (s == 16) { if (!i) return -1; v = lens[i - 1]; rep = 3 + (int)r.take(2); }
+                    else if (s == 17) rep = 3 + (int)r.take(3);
+                    else rep = 11 + (int)r.take(7);
+                    if (i + rep > nlit + ndist) return -1;
+                    while (rep--) lens[i++] = v;
+                }
+                if (!lens[256]) return -1;                           // no end-of-block code
+                memmove(lens + 288, lens + nlit, (size_t)ndist);      // (distance lengths to a fixed place)
+                memset(lens + nlit, 0, (size_t)(288 - nlit));
+            }
+            if (!build_table(lens, 288, kLitBits, T->lit, 2048 + 4608, lit_payload, kLiteralFlag)) return -1;
+            if (!build_table(lens + 288, btype == 1 ? 32 : ndist, kDistBits, T->dist, 256 + 3840, dist_payload)) return -1;
+            // ---- the symbols of the block: first with everything in local variables while at least 16 bytes of input and 320
+            //      bytes of room are left (no end-of-input bookkeeping in here), then -- for the tail -- with every check
+            bool block_done = false;
+            {
+                uint64_t bb = r.buf; unsigned bn = r.n;
+                const uint8_t* ip = r.p;
+                uint8_t* op = out + o;
+                uint8_t* const window0 = out + member_out;
+                const uint8_t* const ip_safe = (r.end - r.p > 16) ? r.end - 16 : r.p;
+                uint8_t* const op_safe = out_cap - o > 320 ? out + out_cap - 320 : op;
+                const uint32_t* const lit = T->lit;
+                const uint32_t* const dtab = T->dist;
+#define FASTINF_REFILL() do { uint64_t w_; memcpy(&w_, ip, 8); bb |= w_ << bn; ip += (63 - bn) >> 3; bn |= 56; } while (0)
+#define FASTINF_DROP(k_) do { const unsigned d_ = (k_); bb >>= d_; bn -= d_; } while (0)
+                while (ip < ip_safe && op < op_safe) {
+                    FASTINF_REFILL();
+                    uint32_t e = lit[bb & 2047u];
+                    if (e & kLiteralFlag) {
+                        *op++ = (uint8_t)(e >> 16); FASTINF_DROP(e & 15u);
+                        e = lit[bb & 2047u];
+                        if (e & kLiteralFlag) {
+                            *op++ = (uint8_t)(e >> 16); FASTINF_DROP(e & 15u);
+                            e = lit[bb & 2047u];
+                            if (e & kLiteralFlag) { *op++ = (uint8_t)(e >> 16); FASTINF_DROP(e & 15u); continue; }
+                        }
+                    }
+                    if (((e >> kKindShift) & 7u) == 3u) { FASTINF_DROP(kLitBits); e = lit[(e >> 16) + (uint32_t)(bb & ((1u << ((e >> 8) & 15u)) - 1u))]; }
+                    FASTINF_DROP(e & 15u);
+                    const uint32_t kind = (e >> kKindShift) & 7u;
+                    if (kind == 0) { *op++ = (uint8_t)(e >> 16); continue; }
+                    if (kind == 2) { block_done = true; break; }
+                    if (kind != 1) return -1;
+                    FASTINF_REFILL();
+                    unsigned xb = (e >> 8) & 15u;
+                    const uint32_t length = (e >> 16) + (uint32_t)(bb & ((1u << xb) - 1u));
+                    FASTINF_DROP(xb);
+                    uint32_t d = dtab[bb & 255u];
+                    if (((d >> kKindShift) & 7u) == 3u) { FASTINF_DROP(kDistBits); d = dtab[(d >> 16) + (uint32_t)(bb & ((1u << ((d >> 8) & 15u)) - 1u))]; }
+                    if (((d >> kKindShift) & 7u) != 0) return -1;
+                    FASTINF_DROP(d & 15u);
+                    xb = (d >> 8) & 15u;
+                    const uint32_t dist = (d >> 16) + (uint32_t)(bb & ((1u << xb) - 1u));
+                    FASTINF_DROP(xb);
+                    if (dist > (size_t)(op - window0)) return -1;
+                    uint8_t* dst = op;
+                    const uint8_t* src = op - dist;
+                    op += length;
+                    if (dist >= 8) {
+                        uint64_t w;
+                        memcpy(&w, src, 8); memcpy(dst, &w, 8);
+                        memcpy(&w, src + 8, 8); memcpy(dst + 8, &w, 8);
+                        if (length > 16) {
+                            src += 16; dst += 16;
+                            do { memcpy(&w, src, 8); memcpy(dst, &w, 8); src += 8; dst += 8; } while (dst < op);
+                        }
+                    } else if (dist == 1) {
+                        memset(dst, *src, length);
+                    } else {
+                        for (uint32_t i = 0; i < length; ++i) dst[i] = src[i];
+                    }
+                }
+#undef FASTINF_REFILL
+#undef FASTINF_DROP
+                r.buf = bb; r.n = bn; r.p = ip;
+                o = (size_t)(op - out);
+            }
+            for (; !block_done;) {
+                if (out_cap - o < 258 + 32 + 2 || r.past > 16) return -1;
+                r.refill();
+                uint32_t e = T->lit[r.peek(kLitBits)];
+                if (e & kLiteralFlag) {                                  // up to three literals from one refill (a codeword has 15 bits at most)
+                    out[o++] = (uint8_t)(e >> 16); r.drop(e & 15u);
+                    e = T->lit[r.peek(kLitBits)];
+                    if (e & kLiteralFlag) {
+                        out[o++] = (uint8_t)(e >> 16); r.drop(e & 15u);
+                        e = T->lit[r.peek(kLitBits)];
+                        if (e & kLiteralFlag) { out[o++] = (uint8_t)(e >> 16); r.drop(e & 15u); continue; }
+                    }
+                }
+                if (((e >> kKindShift) & 7u) == 3u) { r.drop(kLitBits); e = T->lit[(e >> 16) + r.peek((e >> 8) & 15u)]; }
+                r.drop(e & 15u);
+                const uint32_t kind = (e >> kKindShift) & 7u;
+                if (kind == 0) { out[o++] = (uint8_t)(e >> 16); continue; }   // (a literal with a long codeword)
+                if (kind == 2) break;
+                if (kind != 1) return -1;
+                r.refill();                                              // (unconditional: cheaper than a branch that depends on what came before)
+                const uint32_t length = (e >> 16) + r.take((e >> 8) & 15u);
+                uint32_t d = T->dist[r.peek(kDistBits)];
+                if (((d >> kKindShift) & 7u) == 3u) { r.drop(kDistBits); d = T->dist[(d >> 16) + r.peek((d >> 8) & 15u)]; }
+                if (((d >> kKindShift) & 7u) != 0) return -1;
+                r.drop(d & 15u);
+                const uint32_t dist = (d >> 16) + r.take((d >> 8) & 15u);
+                if (dist > o - member_out) return -1;                // (a member's window starts with the member)
+                uint8_t* dst = out + o;
+                const uint8_t* src = dst - dist;
+                o += length;
+                if (dist >= 8) {                                        // sixteen bytes without asking (a match is 9 bytes on average), more in a loop
+                    uint64_t w;
+                    memcpy(&w, src, 8); memcpy(dst, &w, 8);
+                    memcpy(&w, src + 8, 8); memcpy(dst + 8, &w, 8);
+                    if (length > 16) {
+                        uint8_t* const stop = dst + length;
+                        src += 16; dst += 16;
+                        do { memcpy(&w, src, 8); memcpy(dst, &w, 8); src += 8; dst += 8; } while (dst < stop);
+                    }
+                } else if (dist == 1) {
+                    memset(dst, *src, length);
+                } else {
+                    for (uint32_t i = 0; i < length; ++i) dst[i] = src[i];
+                }
+            }
+        } else return -1;
+        if (r.past > 16) return -1;
+        progress(o);
+        if (!follow && o - member_out > ((size_t)4 << 20)) {
+            try { follow = new FollowCrc(out, member_out); } catch (...) { follow = nullptr; }
+        }
+        if (follow) follow->target.store(o, std::memory_order_release);
+        if (bfinal) return 1;
+    }
+}
+
 // One gzip archive (all its members) from [in, in+in_len) to out (room for out_cap bytes, of which 32 may be scribbled on past the
 // data).  `progress(bytes)` is called as the output grows (after every block).  Returns the output size, or (size_t)-1 when
 // the decoder gave up -- *good then says how much output belongs to members that were completed and CRC-checked.
 template <class Progress>
 inline size_t gunzip(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_cap, size_t* good, Progress progress) {
-    static const uint8_t kOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     const size_t kFail = (size_t)-1;
     Tables* T = new Tables;
     struct Free { Tables* t; ~Free() { delete t; } } free_tables{T};
@@ -196,182 +383,7 @@ inline size_t gunzip(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_
         Reader r;
         r.p = in + h; r.end = in + in_len;
         // ---- deflate blocks (RFC 1951)
-        for (;;) {
-            r.refill();
-            const uint32_t bfinal = r.take(1), btype = r.take(2);
-            if (btype == 0) {                                                // stored
-                r.drop(r.n & 7);                                             // to a byte boundary
-                // give the bytes still in the bit buffer back
-                const unsigned back = r.n >> 3;
-                if (r.past > back) return kFail;
-                r.p -= (back - r.past); r.buf = 0; r.n = 0; r.past = 0;
-                if (r.end - r.p < 4) return kFail;
-                const uint32_t len = r.p[0] | ((uint32_t)r.p[1] << 8), nlen = r.p[2] | ((uint32_t)r.p[3] << 8);
-                if ((len ^ 0xFFFFu) != nlen) return kFail;
-                r.p += 4;
-                if ((size_t)(r.end - r.p) < len || out_cap - o < (size_t)len + 16) return kFail;
-                memcpy(out + o, r.p, len);
-                r.p += len; o += len;
-            } else if (btype == 1 || btype == 2) {
-                uint8_t lens[320];
-                int nlit, ndist;
-                if (btype == 1) {
-                    for (int i = 0; i < 144; ++i) lens[i] = 8;
-                    for (int i = 144; i < 256; ++i) lens[i] = 9;
-                    for (int i = 256; i < 280; ++i) lens[i] = 7;
-                    for (int i = 280; i < 288; ++i) lens[i] = 8;
-                    for (int i = 0; i < 32; ++i) lens[288 + i] = 5;
-                    nlit = 288; ndist = 32;
-                } else {
-                    nlit = (int)r.take(5) + 257; ndist = (int)r.take(5) + 1;
-                    const int ncl = (int)r.take(4) + 4;
-                    if (nlit > 286 || ndist > 30) return kFail;
-                    uint8_t cl[19];
-                    memset(cl, 0, sizeof cl);
-                    for (int i = 0; i < ncl; ++i) { if (r.n < 3) r.refill(); cl[kOrder[i]] = (uint8_t)r.take(3); }
-                    uint32_t pre[128 + 64];
-                    if (!build_table(cl, 19, 7, pre, 128 + 64, [](int s) { return (uint32_t)s << 16; })) return kFail;
-                    int i = 0;
-                    while (i < nlit + ndist) {
-                        r.refill();
-                        const uint32_t e = pre[r.peek(7)];
-                        if (((e >> kKindShift) & 7u) != 0) return kFail;   // (code lengths are at most 7 bits: no sub-tables, no unused codes in use)
-                        r.drop(e & 15u);
-                        const int s = (int)(e >> 16);
-                        if (s < 16) { lens[i++] = (uint8_t)s; continue; }
-                        int rep; uint8_t v = 0;
-                        if (s == 16) { if (!i) return kFail; v = lens[i - 1]; rep = 3 + (int)r.take(2); }
-                        else if (s == 17) rep = 3 + (int)r.take(3);
-                        else rep = 11 + (int)r.take(7);
-                        if (i + rep > nlit + ndist) return kFail;
-                        while (rep--) lens[i++] = v;
-                    }
-                    if (!lens[256]) return kFail;                           // no end-of-block code
-                    memmove(lens + 288, lens + nlit, (size_t)ndist);      // (distance lengths to a fixed place)
-                    memset(lens + nlit, 0, (size_t)(288 - nlit));
-                }
-                if (!build_table(lens, 288, kLitBits, T->lit, 2048 + 4608, lit_payload, kLiteralFlag)) return kFail;
-                if (!build_table(lens + 288, btype == 1 ? 32 : ndist, kDistBits, T->dist, 256 + 3840, dist_payload)) return kFail;
-                // ---- the symbols of the block: first with everything in local variables while at least 16 bytes of input and 320
-                //      bytes of room are left (no end-of-input bookkeeping in here), then -- for the tail -- with every check
-                bool block_done = false;
-                {
-                    uint64_t bb = r.buf; unsigned bn = r.n;
-                    const uint8_t* ip = r.p;
-                    uint8_t* op = out + o;
-                    uint8_t* const window0 = out + member_out;
-                    const uint8_t* const ip_safe = (r.end - r.p > 16) ? r.end - 16 : r.p;
-                    uint8_t* const op_safe = out_cap - o > 320 ? out + out_cap - 320 : op;
-                    const uint32_t* const lit = T->lit;
-                    const uint32_t* const dtab = T->dist;
-#define FASTINF_REFILL() do { uint64_t w_; memcpy(&w_, ip, 8); bb |= w_ << bn; ip += (63 - bn) >> 3; bn |= 56; } while (0)
-#define FASTINF_DROP(k_) do { const unsigned d_ = (k_); bb >>= d_; bn -= d_; } while (0)
-                    while (ip < ip_safe && op < op_safe) {
-                        FASTINF_REFILL();
-                        uint32_t e = lit[bb & 2047u];
-                        if (e & kLiteralFlag) {
-                            *op++ = (uint8_t)(e >> 16); FASTINF_DROP(e & 15u);
-                            e = lit[bb & 2047u];
-                            if (e & kLiteralFlag) {
-                                *op++ = (uint8_t)(e >> 16); FASTINF_DROP(e & 15u);
-                                e = lit[bb & 2047u];
-                                if (e & kLiteralFlag) { *op++ = (uint8_t)(e >> 16); FASTINF_DROP(e & 15u); continue; }
-                            }
-                        }
-                        if (((e >> kKindShift) & 7u) == 3u) { FASTINF_DROP(kLitBits); e = lit[(e >> 16) + (uint32_t)(bb & ((1u << ((e >> 8) & 15u)) - 1u))]; }
-                        FASTINF_DROP(e & 15u);
-                        const uint32_t kind = (e >> kKindShift) & 7u;
-                        if (kind == 0) { *op++ = (uint8_t)(e >> 16); continue; }
-                        if (kind == 2) { block_done = true; break; }
-                        if (kind != 1) return kFail;
-                        FASTINF_REFILL();
-                        unsigned xb = (e >> 8) & 15u;
-                        const uint32_t length = (e >> 16) + (uint32_t)(bb & ((1u << xb) - 1u));
-                        FASTINF_DROP(xb);
-                        uint32_t d = dtab[bb & 255u];
-                        if (((d >> kKindShift) & 7u) == 3u) { FASTINF_DROP(kDistBits); d = dtab[(d >> 16) + (uint32_t)(bb & ((1u << ((d >> 8) & 15u)) - 1u))]; }
-                        if (((d >> kKindShift) & 7u) != 0) return kFail;
-                        FASTINF_DROP(d & 15u);
-                        xb = (d >> 8) & 15u;
-                        const uint32_t dist = (d >> 16) + (uint32_t)(bb & ((1u << xb) - 1u));
-                        FASTINF_DROP(xb);
-                        if (dist > (size_t)(op - window0)) return kFail;
-                        uint8_t* dst = op;
-                        const uint8_t* src = op - dist;
-                        op += length;
-                        if (dist >= 8) {
-                            uint64_t w;
-                            memcpy(&w, src, 8); memcpy(dst, &w, 8);
-                            memcpy(&w, src + 8, 8); memcpy(dst + 8, &w, 8);
-                            if (length > 16) {
-                                src += 16; dst += 16;
-                                do { memcpy(&w, src, 8); memcpy(dst, &w, 8); src += 8; dst += 8; } while (dst < op);
-                            }
-                        } else if (dist == 1) {
-                            memset(dst, *src, length);
-                        } else {
-                            for (uint32_t i = 0; i < length; ++i) dst[i] = src[i];
-                        }
-                    }
-#undef FASTINF_REFILL
-#undef FASTINF_DROP
-                    r.buf = bb; r.n = bn; r.p = ip;
-                    o = (size_t)(op - out);
-                }
-                for (; !block_done;) {
-                    if (out_cap - o < 258 + 32 + 2 || r.past > 16) return kFail;
-                    r.refill();
-                    uint32_t e = T->lit[r.peek(kLitBits)];
-                    if (e & kLiteralFlag) {                                  // up to three literals from one refill (a codeword has 15 bits at most)
-                        out[o++] = (uint8_t)(e >> 16); r.drop(e & 15u);
-                        e = T->lit[r.peek(kLitBits)];
-                        if (e & kLiteralFlag) {
-                            out[o++] = (uint8_t)(e >> 16); r.drop(e & 15u);
-                            e = T->lit[r.peek(kLitBits)];
-                            if (e & kLiteralFlag) { out[o++] = (uint8_t)(e >> 16); r.drop(e & 15u); continue; }
-                        }
-                    }
-                    if (((e >> kKindShift) & 7u) == 3u) { r.drop(kLitBits); e = T->lit[(e >> 16) + r.peek((e >> 8) & 15u)]; }
-                    r.drop(e & 15u);
-                    const uint32_t kind = (e >> kKindShift) & 7u;
-                    if (kind == 0) { out[o++] = (uint8_t)(e >> 16); continue; }   // (a literal with a long codeword)
-                    if (kind == 2) break;
-                    if (kind != 1) return kFail;
-                    r.refill();                                              // (unconditional: cheaper than a branch that depends on what came before)
-                    const uint32_t length = (e >> 16) + r.take((e >> 8) & 15u);
-                    uint32_t d = T->dist[r.peek(kDistBits)];
-                    if (((d >> kKindShift) & 7u) == 3u) { r.drop(kDistBits); d = T->dist[(d >> 16) + r.peek((d >> 8) & 15u)]; }
-                    if (((d >> kKindShift) & 7u) != 0) return kFail;
-                    r.drop(d & 15u);
-                    const uint32_t dist = (d >> 16) + r.take((d >> 8) & 15u);
-                    if (dist > o - member_out) return kFail;                // (a member's window starts with the member)
-                    uint8_t* dst = out + o;
-                    const uint8_t* src = dst - dist;
-                    o += length;
-                    if (dist >= 8) {                                        // sixteen bytes without asking (a match is 9 bytes on average), more in a loop
-                        uint64_t w;
-                        memcpy(&w, src, 8); memcpy(dst, &w, 8);
-                        memcpy(&w, src + 8, 8); memcpy(dst + 8, &w, 8);
-                        if (length > 16) {
-                            uint8_t* const stop = dst + length;
-                            src += 16; dst += 16;
-                            do { memcpy(&w, src, 8); memcpy(dst, &w, 8); src += 8; dst += 8; } while (dst < stop);
-                        }
-                    } else if (dist == 1) {
-                        memset(dst, *src, length);
-                    } else {
-                        for (uint32_t i = 0; i < length; ++i) dst[i] = src[i];
-                    }
-                }
-            } else return kFail;
-            if (r.past > 16) return kFail;
-            progress(o);
-            if (!follow && o - member_out > ((size_t)4 << 20)) {
-                try { follow = new FollowCrc(out, member_out); } catch (...) { follow = nullptr; }
-            }
-            if (follow) follow->target.store(o, std::memory_order_release);
-            if (bfinal) break;
-        }
+        if (inflate_blocks(r, in, T, out, o, out_cap, member_out, (size_t)-1, progress, follow) != 1) return kFail;
         // ---- member trailer: to a byte boundary, CRC-32 and length of the member's output
         r.drop(r.n & 7);
         const unsigned back = r.n >> 3;
