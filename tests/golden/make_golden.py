@@ -117,8 +117,50 @@ def gen_consensus(R):
     json.dump(dict(ksw_align=ksw, groups=groups), open(os.path.join(HERE, "consensus_vectors.json"), "w"))
 
 
+def gen_damaged(R):
+    """Small damaged archives (ordinary gzip with a flipped bit, BGZF with a damaged block, a truncated one) and the record stream
+    the REFERENCE's kseq loop reads from each: what a failed gzread leaves behind (kseq.cpp:55-96) pinned without the compiled
+    reference.  The archives are committed as they are (a few KB each)."""
+    import base64
+    import zlib
+    sys.path.insert(0, os.path.dirname(HERE))
+    from test_host_logic import _write_bgzf
+    rng = random.Random(515)
+    parts = []
+    for k in range(900):
+        seq = fuzzgen.rand_seq(rng, rng.randint(30, 150)).decode()
+        if rng.random() < 0.5:
+            parts.append("@r%d c%d\n%s\n+\n%s\n" % (k, k, seq, "".join(rng.choice("!5I@>F") for _ in seq)))
+        else:
+            parts.append(">r%d\n%s\n" % (k, seq))
+    text = "".join(parts).encode()
+    plain = gzip.compress(text, compresslevel=6, mtime=0)
+    out = {}
+    d = os.path.join(HERE, "damaged_gz")
+    os.makedirs(d, exist_ok=True)
+    for it in range(6):
+        name = "bad%d.fx.gz" % it
+        p = os.path.join(d, name)
+        if it < 3:
+            at = rng.randint(len(plain) // 8, len(plain) - 64)
+            data = plain[:at] + bytes([plain[at] ^ (1 << rng.randint(0, 7))]) + plain[at + 1:]
+            with open(p, "wb") as fh:
+                fh.write(data)
+        elif it < 5:
+            _write_bgzf(p, text, block=9000, corrupt_block=rng.randint(1, len(text) // 9000 - 1))
+        else:
+            with open(p, "wb") as fh:
+                fh.write(plain[:len(plain) * 2 // 3])
+        want = R.kseq_dump(p)
+        out[name] = dict(records_md5=hashlib.md5(want).hexdigest(), records_len=len(want), tail=base64.b64encode(want[-160:]).decode())
+    json.dump(out, open(os.path.join(d, "expected.json"), "w"), indent=1)
+
+
 def main():
     R = checkers.ref()
+    if sys.argv[1:] == ["damaged"]:
+        gen_damaged(R)
+        return
     if sys.argv[1:] == ["uss"]:
         gen_update_start_stops(R)
         return

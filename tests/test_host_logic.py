@@ -607,3 +607,34 @@ def test_parser_own_inflate_against_zlib():
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+
+
+def test_parser_damaged_archive_fixtures():
+    """the product's parser on tests/golden/damaged_gz (record streams of the reference, see test_oracle_golden.py): whole-file
+    and streamed, own decoder / parallel BGZF blocks and zlib only"""
+    import base64
+    import hashlib
+    d = os.path.join(G, "damaged_gz")
+    want = json.load(open(os.path.join(d, "expected.json")))
+    keys = ("CRASS_B200_GZ_STREAM_MIN", "CRASS_B200_GZ_SERIAL")
+    old = {k: os.environ.get(k) for k in keys}
+    os.environ["CRASS_B200_GZ_STREAM_MIN"] = "1"
+    try:
+        for name, w in want.items():
+            p = os.path.join(d, name)
+            for serial in (False, True):
+                os.environ.pop("CRASS_B200_GZ_SERIAL", None)
+                if serial:
+                    os.environ["CRASS_B200_GZ_SERIAL"] = "1"
+                whole = cb.Batch.from_file(p).record_stream()
+                parts = [x.record_stream() for x in cb.Batch.stream_file(p, 40000)]
+                streamed = b"".join(x[:x.rindex(b"#ret=")] for x in parts[:-1]) + parts[-1]
+                for got in (whole, streamed):
+                    assert len(got) == w["records_len"] and got[-160:] == base64.b64decode(w["tail"]), (name, serial)
+                    assert hashlib.md5(got).hexdigest() == w["records_md5"], (name, serial)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v

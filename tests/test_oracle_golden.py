@@ -145,3 +145,18 @@ def test_golden_counts():
         p1 = [l for l in lines if l.startswith("R\t") and l.split("\t")[2] == "1"]
         assert len(p1) == hits
         assert len({l.split("\t")[1] for l in p1}) == variants
+
+
+def test_kseq_damaged_archive_fixtures():
+    """tests/golden/damaged_gz: damaged gzip / BGZF archives and a truncated one, with the record streams the REFERENCE reads
+    from them (make_golden.py damaged): a failed gzread is taken for a short read by kstream (kseq.cpp:55-96)."""
+    import base64
+    import hashlib
+    d = os.path.join(G, "damaged_gz")
+    want = json.load(open(os.path.join(d, "expected.json")))
+    assert len(want) == 6
+    P = checkers.port()
+    for name, w in want.items():
+        got = P.kseq_dump(os.path.join(d, name))
+        assert len(got) == w["records_len"] and got[-160:] == base64.b64decode(w["tail"]), name
+        assert hashlib.md5(got).hexdigest() == w["records_md5"], name
